@@ -46,6 +46,7 @@ def _load(mode):
         L.ecmref_set_kinematics.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 4
         L.ecmref_set_attraction.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 2
         L.ecmref_path_len.argtypes = [C.c_void_p, C.c_int]
+        L.ecmref_destroy_agent.argtypes = [C.c_void_p, C.c_int]
         L.ecmref_get_path.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int]
         L.ecmref_step.argtypes = [C.c_void_p, C.c_int]
         L.ecmref_num_agents.argtypes = [C.c_void_p]
@@ -124,6 +125,18 @@ class RefSim:
 
     def set_attraction(self, slot, p):
         self.L.ecmref_set_attraction(self.h, int(slot), float(p[0]), float(p[1]))
+
+    def destroy_agent(self, slot):
+        self.L.ecmref_destroy_agent(self.h, int(slot))
+
+    def path_len(self, slot) -> int:
+        return self.L.ecmref_path_len(self.h, int(slot))
+
+    def path(self, slot):
+        n = self.path_len(slot)
+        xy = np.zeros((max(n, 1), 2), np.float32)
+        self.L.ecmref_get_path(self.h, int(slot), _p(xy, f32p), n)
+        return xy[:n]
 
     def paths(self, count):
         """(path_off[count+1], path_xy[total,2]) of slots [0,count)."""

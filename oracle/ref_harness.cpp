@@ -243,6 +243,8 @@ void ecmref_set_attraction(void* h, int slot, float x, float y) {
     s->m_AttractionPoints[slot].y = y;
 }
 
+void ecmref_destroy_agent(void* h, int slot) { ((RefSim*)h)->sim->DestroyAgent(slot); }  // Simulator.cpp:202-208
+
 int ecmref_path_len(void* h, int slot) { return ((RefSim*)h)->sim->m_Paths[slot].numPoints; }
 
 int ecmref_get_path(void* h, int slot, float* out_xy, int cap) {
@@ -310,6 +312,7 @@ void ecmref_query_neighbors(void* h, int count, int* out_ids, int* out_counts) {
     RefSim* r = (RefSim*)h;
     Simulator* s = r->sim;
     s->m_KDTree->Construct(s);
+    std::fill(r->nn_cache.begin(), r->nn_cache.end(), 0);  // a fresh ORCA object starts zero-filled (ORCA.h:87)
     for (int i = 0; i < count; i++) {
         out_counts[i] = -1;
         if (i > s->m_LastEntityIdx || !s->m_ActiveAgents[i]) continue;
