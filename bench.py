@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py - agent-updates/s and ms/tick of the per-tick agent update (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3_1m] [--agents A] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  Workload at N=1: C3, 1M agents in the 2025-block city lattice
+(SURVEY.md §8d); a "step" is one Simulator::Update tick over the whole crowd.
+
+  value        whole-job agent-updates/s with all state resident in HBM (CUDA events on the
+               simulator's stream, max over ranks)
+  e2e          same metric through the C ABI with HOST buffers: every tick uploads positions and
+               velocities from pinned memory, runs ecmgpu_update, downloads positions, velocities
+               and active flags
+  roofline     dominant kernel (by measured phase time) against the measured HBM copy bandwidth
+  cpu_baseline the unmodified reference (oracle/_ref) on one host core, bounded sample
+
+--impl reference times the reference's own CPU Simulator::Update (single-threaded, as shipped).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from ecmgenerator_b200 import scenarios as S  # noqa: E402
+from ecmgenerator_b200 import host  # noqa: E402
+
+METRIC = "agent_updates_per_s"
+UNIT = "agent-updates/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def build_workload(config: str, agents: int | None, seed_offset: int = 0):
+    world_fn, crowd_fn = S.CONFIGS[config]
+    w = world_fn()
+    t = time.time()
+    c = crowd_fn(w, n=agents) if agents else crowd_fn(w)
+    t1 = time.time()
+    off, pxy, ok = host.plan_paths(w, c.pos, c.goal, c.radius, threads=0)
+    lens = np.diff(off)
+    good = lens >= 2
+    if not good.all():  # drop agents the planner could not serve (start or goal level with a cell corner)
+        keep = np.nonzero(good)[0]
+        c = c.take(keep)
+        new_off = np.zeros(len(keep) + 1, np.int32)
+        np.cumsum(lens[keep], out=new_off[1:])
+        pxy = np.concatenate([pxy[off[i]:off[i + 1]] for i in keep]) if len(keep) < 200_000 else _gather(pxy, off, keep)
+        off = new_off
+    log(f"[bench] {config}: {c.n} agents sampled in {t1 - t:.1f}s, paths planned in {time.time() - t1:.1f}s "
+        f"(mean {np.diff(off).mean():.1f} points, {int((~good).sum())} dropped)")
+    return w, c, off, pxy
+
+
+def _gather(pxy, off, keep):
+    lens = (off[1:] - off[:-1])[keep]
+    idx = np.repeat(off[:-1][keep], lens) + (np.arange(lens.sum()) - np.repeat(np.cumsum(lens) - lens, lens))
+    return pxy[idx]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class _silence_stdout:
+    """Redirects file descriptor 1 to /dev/null (C++ iostream output of the reference included)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.null)
+        os.close(self.saved)
+        return False
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(w, c, off, pxy, sample_agents: int, ticks: int, warm: int):
+    """The reference's Simulator::Update on a window of the same workload, one host core."""
+    n = min(sample_agents, c.n)
+    # spatially compact sample: the n agents closest to the crowd's centroid keep the local density
+    ctr = c.pos.mean(axis=0)
+    idx = np.argsort(((c.pos - ctr) ** 2).sum(axis=1), kind="stable")[:n]
+    idx.sort()
+    sub = c.take(idx)
+    sub_off = np.zeros(n + 1, np.int32)
+    lens = (off[1:] - off[:-1])[idx]
+    np.cumsum(lens, out=sub_off[1:])
+    sub_xy = _gather(pxy, off, idx)
+    from oracle import pyref
+
+    with _silence_stdout():  # the reference prints banners and timing tables to stdout
+        if pyref.available("ref-kdtree"):
+            kind = "reference"
+            sim = pyref.RefSim(w, n + 8, float(S.DT), "ref-kdtree")
+            sim.bulk_load(sub.pos, None, sub.radius, sub.speed, sub_off, sub_xy)
+        else:
+            from oracle.pyoracle import OracleSim
+
+            kind = "port"
+            sim = OracleSim(w, n + 8, float(S.DT), "ref-kdtree")
+            sim.bulk_load(sub.pos, sub.radius, sub.speed, sub_off, sub_xy)
+        for _ in range(warm):
+            sim.step(1)
+        t0 = time.perf_counter()
+        for _ in range(ticks):
+            sim.step(1)
+        dt = time.perf_counter() - t0
+        sim.close()
+    return {"value": n * ticks / dt, "unit": UNIT, "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
+            "sample": f"{n} agents nearest the crowd centroid of the same world ({w.n_cells} ECM cells, {w.n_obst_vertices} obstacle segments), "
+                      f"{ticks} ticks after {warm} warm-up", "ms_per_tick_sample": 1e3 * dt / ticks}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w, c, off, pxy = build_workload(args.config, args.agents)
+    res = cpu_reference_run(w, c, off, pxy, args.cpu_sample, max(1, args.steps), max(0, min(args.warmup, 2)))
+    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["ms_per_tick_sample"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"{args.config}: {c.n} agents, C3 city lattice; each step = one tick of a bounded sample",
+                       "agents": c.n, "dt": float(S.DT)},
+            "cpu_baseline": res,
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+
+    from ecmgenerator_b200 import gpu
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w, c, off, pxy = build_workload(args.config, args.agents)
+    n = c.n
+    if world > 1:
+        from ecmgenerator_b200.multigpu import StripSim
+
+        sim = StripSim(w, c, off, pxy, rank, world, local)
+    else:
+        sim = gpu.GpuSim(w, n, float(S.DT), device=local, record_neighbors=False)
+        sim.bulk_load(c.pos, c.radius, c.speed, off, pxy)
+    mean_p = float(np.diff(off).mean())
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        sim.sync()
+
+    # ---- warm-up (also builds bins / grid)
+    for _ in range(max(args.warmup, 3)):
+        sim.update(1)
+    sim.sync()
+    st0 = sim.stats()
+    active0 = st0["n_active"]
+
+    # ---- timed: K ticks, state resident in HBM
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    sim.mark(0)
+    for _ in range(args.steps):
+        sim.update(1)
+    sim.mark(1)
+    barrier()
+    ms = sim.elapsed_ms(0, 1)
+    st1 = sim.stats()
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = st1["kernel_launches"] - st0["kernel_launches"]
+    updates = float(active0) * args.steps if world == 1 else float(sim.global_active()) * args.steps
+    value = updates / (ms * 1e-3)
+
+    # ---- per-phase times for the roofline of the dominant kernel (separate pass, same state)
+    roof = None
+    if world == 1:
+        sim.set_profiling(True)
+        acc = {"grid": 0.0, "attract": 0.0, "orca": 0.0, "tick": 0.0}
+        reps = max(3, min(args.steps, 20))
+        for _ in range(reps):
+            sim.update(1)
+            t_ms = sim.last_tick_ms()
+            for k in acc:
+                acc[k] += t_ms[k]
+        sim.set_profiling(False)
+        for k in acc:
+            acc[k] /= reps
+        peak, peak_src = measured_hbm_peak()
+        # algorithmic bytes per agent-update (DESIGN.md "Roofline"): whole tick 176 + 8 P;
+        # k_attract 40 + 8 P (pos, speed, path header + polyline; attraction + prefvel out),
+        # k_orca 136 (own vel/radius, 5 x (pos,vel,radius) neighbours; pos, vel, force out)
+        alg = {"attract": 40.0 + 8.0 * mean_p, "orca": 136.0, "tick": 176.0 + 8.0 * mean_p}
+        dom = "orca" if acc["orca"] >= acc["attract"] else "attract"
+        ach = alg[dom] * active0 / (acc[dom] * 1e-3) / 1e9
+        ach_tick = alg["tick"] * active0 / (acc["tick"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_" + dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_agent": alg[dom],
+                "kernel_ms": acc[dom], "phase_ms": acc,
+                "whole_tick": {"achieved": ach_tick, "frac": ach_tick / peak, "algorithmic_bytes_per_agent": alg["tick"]}}
+    clk = clocks.stop()
+
+    # ---- end to end through the C ABI with host buffers
+    e2e = None
+    if world == 1:
+        hp = gpu.PinnedArray((n, 2), np.float32)
+        hv = gpu.PinnedArray((n, 2), np.float32)
+        ha = gpu.PinnedArray((n,), np.uint8)
+        hp.array[:] = sim.read(gpu.POS, 0, n)
+        hv.array[:] = sim.read(gpu.VEL, 0, n)
+        k = max(3, min(args.steps, 20))
+
+        def e2e_tick():
+            sim.write_async(gpu.POS, hp, 0, n)
+            sim.write_async(gpu.VEL, hv, 0, n)
+            sim.update(1)
+            sim.read_async(gpu.POS, hp, 0, n)
+            sim.read_async(gpu.VEL, hv, 0, n)
+            sim.read_async(gpu.ACTIVE, ha, 0, n)
+            sim.sync()  # the host consumes the result (getters) before the next tick
+
+        for _ in range(2):
+            e2e_tick()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            e2e_tick()
+        dt = time.perf_counter() - t0
+        act = int((ha.array > 0).sum())
+        e2e = {"value": act * k / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 17 * n,
+               "ms_per_step": 1e3 * dt / k, "steps": k}
+        for a in (hp, hv, ha):
+            a.free()
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        t = time.time()
+        cpu = cpu_reference_run(w, c, off, pxy, args.cpu_sample, args.cpu_ticks, 1)
+        log(f"[bench] cpu baseline in {time.time() - t:.1f}s")
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.config}: {n} agents, {w.n_obstacles} blocks, {w.n_cells} ECM cells, dt=1/60, mean path points {mean_p:.1f}",
+                       "agents": n, "active": int(active0), "dt": float(S.DT), "parallelism": f"strips{world}" if world > 1 else "1gpu",
+                       "l2": "working set (agent state + path pool + snapshot) exceeds the 126 MB L2", "neighbor_cell": st1["neighbor_cell"],
+                       "static_bin": st1["static_bin"]},
+            "gpu_launches": int(launches), "clocks": clk,
+            "counters": {k: int(st1[k]) for k in ("knn_fallbacks", "obstacle_overflows", "lp3d_runs", "location_failures", "replans")}}
+    if roof:
+        line["roofline"] = roof
+    if e2e:
+        line["e2e"] = e2e
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3_1m", choices=sorted(S.CONFIGS))
+    ap.add_argument("--agents", type=int, default=None)
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="agents in the CPU baseline sample")
+    ap.add_argument("--cpu-ticks", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

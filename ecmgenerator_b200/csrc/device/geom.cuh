@@ -1,0 +1,66 @@
+// Device-side 2-D primitives in the reference's operation order.
+//
+// Bit-exact decisions (cell containment, neighbour ordering) need IEEE binary32 mul/add with no
+// FMA contraction and IEEE div/sqrt: this translation unit is compiled with -fmad=false and
+// without --use_fast_math (see __graft_entry__.build).  Expression shapes follow
+//   /root/reference/ECMGenerator/ECMDataTypes.h:13-104   (Vec2 / Point operators)
+//   /root/reference/ECMGenerator/UtilityFunctions.cpp:15-349 (MathUtility)
+//   /root/reference/ECMGenerator/Configuration.h:11-15   (EPSILON, MAX_FLOAT)
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+namespace ecm {
+
+constexpr float kEpsilon = 0.0001f;   // Configuration.h:14
+constexpr float kLookAhead = 10.0f;   // ORCA.h:102-103 (agents and obstacles)
+constexpr int kK = 5;                 // Simulator.cpp:55
+
+typedef float2 v2;
+
+__device__ __forceinline__ v2 V(float x, float y) { return make_float2(x, y); }
+__device__ __forceinline__ v2 vadd(v2 a, v2 b) { return V(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ v2 vsub(v2 a, v2 b) { return V(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ v2 vmul(v2 a, float s) { return V(a.x * s, a.y * s); }
+__device__ __forceinline__ v2 vdiv(v2 a, float s) { return V(a.x / s, a.y / s); }
+__device__ __forceinline__ float vdot(v2 a, v2 b) { return a.x * b.x + a.y * b.y; }   // UtilityFunctions.cpp:172
+__device__ __forceinline__ float vdet(v2 a, v2 b) { return a.x * b.y - a.y * b.x; }   // UtilityFunctions.cpp:182
+__device__ __forceinline__ float vlen2(v2 a) { return a.x * a.x + a.y * a.y; }        // ECMDataTypes.h:38
+__device__ __forceinline__ float vlen(v2 a) { return sqrtf(a.x * a.x + a.y * a.y); }  // ECMDataTypes.h:33
+__device__ __forceinline__ v2 vright(v2 a) { return V(a.y, -a.x); }                   // UtilityFunctions.cpp:213
+__device__ __forceinline__ v2 vleft(v2 a) { return V(-a.y, a.x); }                    // UtilityFunctions.cpp:223
+// Vec2::Normalize / Normalized (ECMDataTypes.h:45-60): a zero vector stays zero.
+__device__ __forceinline__ v2 vnormalized(v2 a) {
+    float l = vlen(a);
+    if (l == 0.0f) return a;
+    return V(a.x / l, a.y / l);
+}
+// Point::Approximate (ECMDataTypes.cpp:97-100): open +-EPSILON box.
+__device__ __forceinline__ bool approx(v2 a, v2 b) {
+    return a.x < (b.x + kEpsilon) && a.x > (b.x - kEpsilon) && a.y < (b.y + kEpsilon) && a.y > (b.y - kEpsilon);
+}
+// SquareDistance(Point, Point) (UtilityFunctions.cpp:34-41)
+__device__ __forceinline__ float sqdist(v2 p1, v2 p2) {
+    float dx = p2.x - p1.x, dy = p2.y - p1.y;
+    return dx * dx + dy * dy;
+}
+// GetClosestPointOnSegment (UtilityFunctions.cpp:287-306)
+__device__ __forceinline__ v2 closest_on_segment(v2 point, v2 s1, v2 s2) {
+    if (approx(s1, s2)) return s1;
+    v2 seg = vsub(s2, s1);
+    v2 pts = vsub(point, s1);
+    float tsq = sqdist(s1, s2);
+    float d = (pts.x * seg.x + pts.y * seg.y) / tsq;
+    if (d > 1.0f) d = 1.0f;
+    if (d < 0.0f) d = 0.0f;
+    return V(s1.x + d * seg.x, s1.y + d * seg.y);
+}
+// RotateVector (UtilityFunctions.cpp:233-242).  sinf/cosf are CUDA's full-range versions (<= 2 ulp),
+// glibc's are <= 1 ulp: the only arithmetic on the path that is not bit-reproducible.
+__device__ __forceinline__ v2 rotate(v2 v, float rad) {
+    float sn, cs;
+    sincosf(rad, &sn, &cs);
+    return V(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+}
+
+}  // namespace ecm

@@ -1,0 +1,142 @@
+// ECM point location, retraction and the IRM attraction point, one thread per query.
+#pragma once
+#include "world.cuh"
+
+namespace ecm {
+
+// MathUtility::Contains(Point, vector<Segment>) for the closed chain q0 q1 q2 q3
+// (UtilityFunctions.cpp:54-86): even-odd ray cast to +x; a point within EPSILON of any corner is
+// "not contained"; strict inequalities, so a point level with a corner is missed by both
+// neighbouring cells (reference behaviour, DESIGN.md "location failures").
+__device__ __forceinline__ bool contains4(v2 p, v2 q0, v2 q1, v2 q2, v2 q3) {
+    bool inside = false;
+    v2 a = q0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        v2 b = k == 0 ? q1 : (k == 1 ? q2 : (k == 2 ? q3 : q0));
+        if (approx(p, a)) return false;
+        if (approx(p, b)) return false;
+        if (p.y > fminf(a.y, b.y) && p.y < fmaxf(a.y, b.y) && p.x < fmaxf(a.x, b.x)) {
+            float xi = (p.y - a.y) * (b.x - a.x) / (b.y - a.y) + a.x;
+            if (a.x == b.x || p.x < xi) inside = !inside;
+        }
+        a = b;
+    }
+    return inside;
+}
+
+// Cell c = 2*edge + side: polygon [v0, boundary.p0, boundary.p1, v1] with boundary (L0,L1) for the
+// left cell and (R0,R1) for the right cell (ECMCellCollection.cpp:24-45, :62-80).
+__device__ __forceinline__ bool cell_contains(const EcmView& ecm, int c, v2 p) {
+    int e = c >> 1, side = c & 1;
+    int2 ev = __ldg(&ecm.edge_v[e]);
+    const float2* cl = ecm.edge_cl + 4 * e;
+    v2 q0 = __ldg(&ecm.vert_xy[ev.x]);
+    v2 q1 = __ldg(&cl[side]);
+    v2 q2 = __ldg(&cl[2 + side]);
+    v2 q3 = __ldg(&ecm.vert_xy[ev.y]);
+    return contains4(p, q0, q1, q2, q3);
+}
+
+// ECMCellCollection::PointLocationQueryLinear (ECMCellCollection.cpp:57-90): lowest-index
+// containing cell, -1 if none.  The bin list is ascending and a superset of the cells that can
+// contain a point of the bin, so the first hit equals the linear scan's.
+__device__ __forceinline__ int find_cell(const EcmView& ecm, const BinView& bins, v2 p) {
+    int b = bins.bin_of(p);
+    if (b >= 0) {
+        int i0 = __ldg(&bins.cell_start[b]), i1 = __ldg(&bins.cell_start[b + 1]);
+        for (int i = i0; i < i1; i++) {
+            int c = __ldg(&bins.cell_items[i]);
+            if (cell_contains(ecm, c, p)) return c;
+        }
+        return -1;
+    }
+    for (int c = 0; c < 2 * ecm.n_edges; c++)
+        if (cell_contains(ecm, c, p)) return c;
+    return -1;
+}
+
+// MathUtility::GetRayToLineSegmentIntersection (UtilityFunctions.cpp:323-349).
+// `abs(dot) < 0.000001` compares the float |dot| with a DOUBLE literal; 1e-6 is not a float, so
+// the test equals |dot| <= (largest float below 1e-6) = |dot| < 1e-6f rounded up; we keep the
+// double compare to be literal about it (one DSETP per agent).
+__device__ __forceinline__ bool ray_segment(v2 origin, v2 dir, v2 p1, v2 p2, v2& out) {
+    v2 v1 = vsub(origin, p1), vv2 = vsub(p2, p1), v3 = V(-dir.y, dir.x);
+    float dot = vdot(vv2, v3);
+    if ((double)fabsf(dot) < 0.000001) return false;
+    float t1 = vdet(vv2, v1) / dot;
+    float t2 = vdot(v1, v3) / dot;
+    if (t1 >= 0.0f && (t2 >= 0.0f && t2 <= 1.0f)) {
+        out = V(origin.x + dir.x * t1, origin.y + dir.y * t1);
+        return true;
+    }
+    return false;
+}
+
+// ECM::RetractPoint (ECM.cpp:20-96) given the located cell.
+__device__ __forceinline__ bool retract_in_cell(const EcmView& ecm, int cell, v2 loc, v2& out) {
+    int e = cell >> 1;
+    int2 ev = __ldg(&ecm.edge_v[e]);
+    const float2* cl = ecm.edge_cl + 4 * e;
+    v2 p1 = __ldg(&ecm.vert_xy[ev.x]), p2 = __ldg(&ecm.vert_xy[ev.y]);
+    // IsLeftOfSegment (UtilityFunctions.cpp:193-196): the side is chosen by the edge, not by the cell
+    bool left = (p2.x - p1.x) * (loc.y - p1.y) - (p2.y - p1.y) * (loc.x - p1.x) > 0.0f;
+    v2 o1 = __ldg(&cl[left ? 0 : 1]);  // he[0].closest_left  | he[0].closest_right
+    v2 o2 = __ldg(&cl[left ? 2 : 3]);  // he[1].closest_right | he[1].closest_left
+    v2 ray;
+    if (approx(o1, o2)) {  // point obstacle
+        ray = vadd(vsub(p1, o1), vsub(p2, o1));
+    } else {
+        v2 v = vsub(o2, o1);
+        ray = left ? V(v.y, -v.x) : V(-v.y, v.x);
+    }
+    ray = vnormalized(ray);
+    return ray_segment(loc, ray, p1, p2, out);
+}
+
+// IRMPathFollower::FindAttractionPoint (IRMPathFollower.cpp:14-115).  `out` is written exactly
+// where the reference writes outPoint; `cell` receives the located cell (-1: location failed).
+__device__ __forceinline__ bool find_attraction_point(const EcmView& ecm, const BinView& bins, v2 position,
+                                                      const float2* __restrict__ path, int np, v2& out, int& cell) {
+    cell = find_cell(ecm, bins, position);
+    if (cell < 0) return false;
+    v2 R;
+    if (!retract_in_cell(ecm, cell, position, R)) return false;
+    const float2* cl = ecm.edge_cl + 4 * (cell >> 1);
+    v2 obstA = __ldg(&cl[0]), obstB = __ldg(&cl[2]);  // always the LEFT pair (IRMPathFollower.cpp:31-34)
+    v2 closest = closest_on_segment(R, obstA, obstB);
+    float clearance = vlen(vsub(R, closest));
+    float c2 = clearance * clearance;
+    v2 goal = path[np - 1];
+    if (vlen2(vsub(goal, R)) < c2) {
+        out = goal;
+        return true;
+    }
+    bool success = false;
+    v2 a = path[0];
+    for (int i = 0; i < np - 1; i++) {
+        v2 b = path[i + 1];
+        v2 p1 = vsub(a, R), p2 = vsub(b, R);
+        a = b;
+        v2 ed = vsub(p2, p1);
+        float el2 = vlen2(ed);
+        float det = vdet(p1, p2);
+        float disc = c2 * el2 - det * det;
+        if (disc < kEpsilon) continue;
+        success = true;
+        float dys = ed.y < 0.0f ? -1.0f : 1.0f;
+        float sq = sqrtf(disc);
+        v2 i1 = V((det * ed.y + dys * ed.x * sq) / el2, (-det * ed.x + fabsf(ed.y) * sq) / el2);
+        v2 i2 = V((det * ed.y - dys * ed.x * sq) / el2, (-det * ed.x - fabsf(ed.y) * sq) / el2);
+        v2 g1 = vadd(p1, R), g2 = vadd(p2, R), gi1 = vadd(i1, R), gi2 = vadd(i2, R);
+        v2 edge = vsub(g2, g1);
+        float t1 = vdot(vsub(gi1, g1), edge) / el2;
+        float t2 = vdot(vsub(gi2, g1), edge) / el2;
+        float maxT = -1.0f;
+        if (t1 >= 0.0f && t1 <= 1.0f) { out = gi1; maxT = t1; }
+        if (t2 >= 0.0f && t2 <= 1.0f) { if (t2 > maxT) out = gi2; }
+    }
+    return success;
+}
+
+}  // namespace ecm

@@ -1,0 +1,297 @@
+// ORCA: obstacle gathering, half-plane construction and the 2-D incremental linear programs,
+// one thread per agent.  Statement order and float expression shapes follow the reference:
+//   Simulator::FindNearestObstacles   /root/reference/ECMAgentSimulator/Simulator.cpp:259-292
+//   ORCA::GenerateConstraints         /root/reference/ECMAgentSimulator/ORCA.cpp:60-424
+//   ORCA::RandomizedLP                /root/reference/ECMAgentSimulator/ORCA.cpp:428-587
+//   ORCA::RandomizedLP3D              /root/reference/ECMAgentSimulator/ORCA.cpp:592-669
+#pragma once
+#include "knn.cuh"
+
+namespace ecm {
+
+constexpr int kMaxObstNeighbors = 27;             // device cap on FindNearestObstacles' list (status OBST_OVERFLOW beyond)
+constexpr int kMaxCons = kMaxObstNeighbors + kK;  // obstacle constraints + 5 agent constraints
+
+// Constraint (ORCA.h:26-80): only m_N and m_PointOnLine are ever read.  .x,.y = normal, .z,.w = point.
+typedef float4 Cons;
+__device__ __forceinline__ Cons cmake(v2 point, v2 normal) { return make_float4(normal.x, normal.y, point.x, point.y); }
+__device__ __forceinline__ v2 cn(const Cons& c) { return V(c.x, c.y); }
+__device__ __forceinline__ v2 cp(const Cons& c) { return V(c.z, c.w); }
+// Constraint::Contains, methodB (ORCA.h:52)
+__device__ __forceinline__ bool ccontains(const Cons& c, v2 p) { return vdet(vright(cn(c)), vsub(cp(c), p)) <= 0.0f; }
+
+// The reference filter of Simulator.cpp:271-287 for one segment o -> next[o].
+__device__ __forceinline__ bool obstacle_in_range(const ObstView& ob, int o, v2 a, float range2) {
+    v2 p = __ldg(&ob.xy[o]), q = __ldg(&ob.xy[__ldg(&ob.next[o])]);
+    float sl = vdet(vsub(p, a), vsub(q, p));  // LineLeftDistance (UtilityFunctions.cpp:49-52)
+    float sq = (sl * sl) / sqdist(p, q);      // std::powf(s, 2.0f) restated as s*s (DESIGN.md "powf")
+    if (sq < range2 && sl < 0.0f) {
+        v2 c = closest_on_segment(a, p, q);
+        return sqdist(c, a) < range2;
+    }
+    return false;
+}
+
+// FindNearestObstacles through the static bins; ids in (obstacle, vertex) order.  Returns the
+// number found (may exceed cap: the excess is dropped and the caller flags OBST_OVERFLOW).
+__device__ __forceinline__ int find_obstacles(const ObstView& ob, const BinView& bins, v2 a, float range2, int* out, int cap) {
+    int n = 0;
+    int b = bins.bin_of(a);
+    if (b >= 0) {
+        int i0 = __ldg(&bins.obst_start[b]), i1 = __ldg(&bins.obst_start[b + 1]);
+        for (int i = i0; i < i1; i++) {
+            int o = __ldg(&bins.obst_items[i]);
+            if (obstacle_in_range(ob, o, a, range2)) { if (n < cap) out[n] = o; n++; }
+        }
+    } else {
+        for (int o = 0; o < ob.n; o++)
+            if (obstacle_in_range(ob, o, a, range2)) { if (n < cap) out[n] = o; n++; }
+    }
+    return n;
+}
+
+// One obstacle segment -> at most one constraint (ORCA.cpp:70-333).  Returns true if `c` was produced.
+__device__ __forceinline__ bool obstacle_constraint(const ObstView& ob, int oL, v2 position, v2 velocity, float clearance, Cons& c) {
+    int oR = __ldg(&ob.next[oL]);
+    v2 pL = __ldg(&ob.xy[oL]), pR = __ldg(&ob.xy[oR]);
+    bool cvxL = __ldg(&ob.convex[oL]) != 0, cvxR = __ldg(&ob.convex[oR]) != 0;
+    v2 rp1 = vsub(pL, position), rp2 = vsub(pR, position);
+    v2 segDir = vsub(pR, pL);
+    const float sp = vdot(vmul(rp1, -1.0f), segDir) / vlen2(segDir);
+    const float distSqLine = vlen2(vsub(vmul(rp1, -1.0f), vmul(segDir, sp)));
+    const float distSq1 = vlen2(rp1), distSq2 = vlen2(rp2);
+    segDir = vnormalized(segDir);
+    const float radiusSq = clearance * clearance;
+
+    if (sp < 0.0f && distSq1 <= radiusSq) {  // collision with the left vertex (ORCA.cpp:92-105)
+        if (cvxL) { c = cmake(V(0.0f, 0.0f), vnormalized(vmul(rp1, -1.0f))); return true; }
+        return false;
+    } else if (sp > 1.0f && distSq2 <= radiusSq) {  // collision with the right vertex (ORCA.cpp:108-121)
+        v2 rnd = vnormalized(vsub(__ldg(&ob.xy[__ldg(&ob.next[oR])]), pR));
+        if (cvxR && vdet(rp2, rnd) >= 0.0f) { c = cmake(V(0.0f, 0.0f), vnormalized(vmul(rp2, -1.0f))); return true; }
+        return false;
+    } else if (sp >= 0.0f && sp < 1.0f && distSqLine <= radiusSq) {  // collision with the segment (ORCA.cpp:124-135)
+        c = cmake(V(0.0f, 0.0f), vright(segDir));
+        return true;
+    }
+
+    v2 leftLeg, rightLeg;
+    if (sp < 0.0f && distSqLine <= radiusSq) {  // ORCA.cpp:146-169
+        if (!cvxL) return false;
+        oR = oL; pR = pL; cvxR = cvxL;
+        const float leg1 = sqrtf(distSq1 - radiusSq);
+        leftLeg = vdiv(V(rp1.x * leg1 - rp1.y * clearance, rp1.x * clearance + rp1.y * leg1), distSq1);
+        rightLeg = vdiv(V(rp1.x * leg1 + rp1.y * clearance, -rp1.x * clearance + rp1.y * leg1), distSq1);
+    } else if (sp > 1.0f && distSqLine <= radiusSq) {  // ORCA.cpp:171-183
+        if (!cvxR) return false;
+        oL = oR; pL = pR; cvxL = cvxR;
+        const float leg2 = sqrtf(distSq2 - radiusSq);
+        leftLeg = vdiv(V(rp2.x * leg2 - rp2.y * clearance, rp2.x * clearance + rp2.y * leg2), distSq2);
+        rightLeg = vdiv(V(rp2.x * leg2 + rp2.y * clearance, -rp2.x * clearance + rp2.y * leg2), distSq2);
+    } else {  // ORCA.cpp:186-212
+        if (cvxL) {
+            const float leg1 = sqrtf(distSq1 - radiusSq);
+            leftLeg = vdiv(V(rp1.x * leg1 - rp1.y * clearance, rp1.x * clearance + rp1.y * leg1), distSq1);
+        } else {
+            leftLeg = vmul(segDir, -1.0f);
+        }
+        if (cvxR) {
+            const float leg2 = sqrtf(distSq2 - radiusSq);
+            rightLeg = vdiv(V(rp2.x * leg2 + rp2.y * clearance, -rp2.x * clearance + rp2.y * leg2), distSq2);
+        } else {
+            rightLeg = segDir;
+        }
+    }
+
+    // foreign legs (ORCA.cpp:218-239)
+    bool leftForeign = false, rightForeign = false;
+    v2 lnd = vnormalized(vsub(pL, __ldg(&ob.xy[__ldg(&ob.prev[oL])])));
+    if (cvxL && vdet(leftLeg, vmul(lnd, -1.0f)) >= 0.0f) { leftLeg = vmul(lnd, -1.0f); leftForeign = true; }
+    v2 rnd = vnormalized(vsub(__ldg(&ob.xy[__ldg(&ob.next[oR])]), pR));
+    if (cvxR && vdet(rightLeg, rnd) <= 0.0f) { rightLeg = rnd; rightForeign = true; }
+
+    const float recip = 1.0f / kLookAhead;  // ORCA.cpp:241
+    const v2 leftCutoff = vmul(vsub(pL, position), recip);
+    const v2 rightCutoff = vmul(vsub(pR, position), recip);
+    const v2 cutoffVec = vsub(rightCutoff, leftCutoff);
+    const bool same = (oL == oR);
+    const float t = same ? 0.5f : vdot(vsub(velocity, leftCutoff), cutoffVec) / vlen2(cutoffVec);
+    const float tLeft = vdot(vsub(velocity, leftCutoff), leftLeg);
+    const float tRight = vdot(vsub(velocity, rightCutoff), rightLeg);
+
+    if ((t < 0.0f && tLeft < 0.0f) || (same && tLeft < 0.0f && tRight < 0.0f)) {  // ORCA.cpp:259-268
+        v2 unitW = vnormalized(vsub(velocity, leftCutoff));
+        c = cmake(vadd(leftCutoff, vmul(vmul(unitW, recip), clearance)), unitW);
+        return true;
+    } else if (t > 1.0f && tRight < 0.0f) {  // ORCA.cpp:270-280
+        v2 unitW = vnormalized(vsub(velocity, rightCutoff));
+        c = cmake(vadd(rightCutoff, vmul(vmul(unitW, recip), clearance)), unitW);
+        return true;
+    }
+    // ORCA.cpp:284-286
+    const float distSqCutoff = (t < 0.0f || t > 1.0f || same) ? CUDART_INF_F : vlen2(vsub(velocity, vadd(leftCutoff, vmul(cutoffVec, t))));
+    const float distSqLeft = (tLeft < 0.0f) ? CUDART_INF_F : vlen2(vsub(velocity, vadd(leftCutoff, vmul(leftLeg, tLeft))));
+    const float distSqRight = (tRight < 0.0f) ? CUDART_INF_F : vlen2(vsub(velocity, vadd(rightCutoff, vmul(rightLeg, tRight))));
+
+    if (distSqCutoff <= distSqLeft && distSqCutoff <= distSqRight) {  // ORCA.cpp:289-301
+        v2 normal = vleft(vmul(segDir, -1.0f));
+        c = cmake(vadd(leftCutoff, vmul(vmul(normal, recip), clearance)), normal);
+        return true;
+    } else if (distSqLeft <= distSqRight) {  // ORCA.cpp:303-317
+        if (leftForeign) return false;
+        v2 normal = vleft(leftLeg);
+        c = cmake(vadd(leftCutoff, vmul(vmul(normal, clearance), recip)), normal);
+        return true;
+    }
+    if (rightForeign) return false;  // ORCA.cpp:319-332
+    v2 normal = vright(rightLeg);
+    c = cmake(vadd(rightCutoff, vmul(vmul(normal, clearance), recip)), normal);
+    return true;
+}
+
+// One agent neighbour -> exactly one constraint (ORCA.cpp:339-423).
+__device__ __forceinline__ Cons agent_constraint(v2 position, v2 velocity, float clearance, v2 npos, v2 nvel, float nclear, float stepSize) {
+    v2 VOPos = V((npos.x - position.x) / kLookAhead, (npos.y - position.y) / kLookAhead);
+    float VOPosLength = vlen(VOPos);
+    float combinedRadius = nclear + clearance;
+    float VORadius = combinedRadius / kLookAhead;
+    v2 relVel = V(velocity.x - nvel.x, velocity.y - nvel.y);
+    v2 relPos = V(npos.x - position.x, npos.y - position.y);
+    float relPosLength = vlen(relPos);
+    if (relPosLength < combinedRadius) {  // colliding (ORCA.cpp:356-372): uses the sim step, not the look-ahead
+        v2 w = vsub(relVel, vdiv(relPos, stepSize));
+        float wLength = vlen(w);
+        v2 unitW = vdiv(w, wLength);
+        v2 U = vmul(unitW, (combinedRadius / stepSize - wLength));
+        return cmake(vadd(velocity, vmul(U, 0.5f)), unitW);
+    }
+    float tanHalfAngle = atanf(VORadius / VOPosLength);  // atan, not asin (ORCA.cpp:375-376)
+    v2 VOLeftLeg = rotate(VOPos, tanHalfAngle);
+    v2 VORightLeg = rotate(VOPos, -tanHalfAngle);
+    float sqDistFromCircleCentre = sqdist(VOPos, relVel);
+    v2 base = vsub(VOLeftLeg, VOPos), chk = vsub(relVel, VOPos);
+    bool liesBelow = base.x * chk.y - base.y * chk.x > 0.0f;  // IsLeftOfVector (UtilityFunctions.cpp:198-201)
+    if (liesBelow) {  // ORCA.cpp:385-397
+        float distToEdge = VORadius - sqrtf(sqDistFromCircleCentre);
+        v2 lineNormal = vnormalized(vsub(relVel, VOPos));
+        return cmake(vadd(velocity, vmul(vmul(lineNormal, distToEdge), 0.5f)), lineNormal);
+    }
+    v2 leftPerp = vdiv(vleft(VOPos), VOPosLength);
+    if (vdot(leftPerp, relVel) >= 0.0f) {  // closer to the left leg (ORCA.cpp:403-412)
+        v2 ln = vnormalized(VOLeftLeg);
+        float l = vdot(relVel, ln);  // GetClosestPointOnLineThroughOrigin (UtilityFunctions.cpp:316-320)
+        v2 U = vsub(vmul(ln, l), relVel);
+        return cmake(vadd(velocity, vmul(U, 0.5f)), vleft(ln));
+    }
+    v2 rn = vnormalized(VORightLeg);
+    float l = vdot(relVel, rn);
+    v2 U = vsub(vmul(rn, l), relVel);
+    return cmake(vadd(velocity, vmul(U, 0.5f)), vright(rn));
+}
+
+// ORCA::RandomizedLP (ORCA.cpp:428-587).  Returns n on success, else the failing index.
+__device__ __forceinline__ int randomized_lp(const Cons* cs, int n, v2 opt, float maxSpeed, bool useDirOpt, v2& outV) {
+    if (useDirOpt) outV = vmul(opt, maxSpeed);
+    else if (vlen(opt) > maxSpeed) outV = vmul(vnormalized(opt), maxSpeed);
+    else outV = opt;
+    for (int i = 0; i < n; i++) {
+        const Cons h = cs[i];
+        if (ccontains(h, outV)) continue;
+        v2 dir = vright(cn(h));
+        float dpd = vdot(dir, cp(h));
+        float disc = dpd * dpd + maxSpeed * maxSpeed - vdot(cp(h), cp(h));
+        if (disc <= 0.0f) return i;
+        float dsq = sqrtf(disc);
+        float left = -dpd - dsq;
+        float right = -dpd + dsq;
+        for (int j = 0; j < i; j++) {
+            const Cons hj = cs[j];
+            float den = vdet(dir, vright(cn(hj)));
+            float num = vdet(vright(cn(hj)), vsub(cp(h), cp(hj)));
+            if (fabsf(den) <= kEpsilon) {
+                if (num < 0.0f) return i;
+                continue;
+            }
+            const float t = num / den;
+            if (den >= 0.0f) right = (t < right) ? t : right;  // std::min(right, t)
+            else left = (left < t) ? t : left;                 // std::max(left, t)
+            if (left > right) return i;
+        }
+        if (useDirOpt) {
+            if (vdot(opt, dir) > 0.0f) outV = vadd(cp(h), vmul(dir, right));
+            else outV = vadd(cp(h), vmul(dir, left));
+        } else {
+            float t = vdot(dir, vsub(opt, cp(h)));
+            if (t < left) outV = vadd(cp(h), vmul(dir, left));
+            else if (t > right) outV = vadd(cp(h), vmul(dir, right));
+            else outV = vadd(cp(h), vmul(dir, t));
+        }
+    }
+    return n;
+}
+
+// ORCA::RandomizedLP3D (ORCA.cpp:592-669).  `proj` is scratch for the projected constraints.
+__device__ __forceinline__ void randomized_lp3d(int nObst, const Cons* cs, int total, float maxSpeed, int failed, v2& outV, Cons* proj) {
+    float maxPen = 0.0f;
+    for (int i = failed; i < total; i++) {
+        const Cons ci = cs[i];
+        v2 dir = vright(cn(ci));
+        if (vdet(dir, vsub(cp(ci), outV)) <= maxPen) continue;
+        int np = 0;
+        for (int k = 0; k < nObst; k++) proj[np++] = cs[k];
+        for (int j = nObst; j < i; j++) {
+            const Cons cj = cs[j];
+            float det = vdet(dir, vright(cn(cj)));
+            v2 pt;
+            if (fabsf(det) <= kEpsilon) {
+                if (vdot(cn(ci), cn(cj)) > 0.0f) continue;
+                pt = vmul(vadd(cp(ci), cp(cj)), 0.5f);
+            } else {
+                float t = vdet(vright(cn(cj)), vsub(cp(ci), cp(cj))) / det;
+                pt = vadd(cp(ci), vmul(dir, t));
+            }
+            proj[np++] = cmake(pt, vnormalized(vsub(cn(cj), cn(ci))));
+        }
+        const v2 temp = outV;
+        if (randomized_lp(proj, np, cn(ci), maxSpeed, true, outV) < np) outV = temp;
+        maxPen = vdet(dir, vsub(cp(ci), outV));
+    }
+}
+
+struct OrcaResult {
+    v2 velocity;
+    unsigned status;  // ECMGPU_ST_OBST_OVERFLOW | ECMGPU_ST_LP3D
+};
+
+// ORCA::GetVelocity after the neighbour query (ORCA.cpp:23-56).  nb_q[] are snapshot indices.
+__device__ __forceinline__ OrcaResult orca_velocity(const ObstView& ob, const BinView& bins, const GridView& g, v2 position, v2 velocity,
+                                                    float clearance, float maxSpeed, v2 prefVel, int n_nb, const int* nb_q, float stepSize) {
+    OrcaResult res;
+    res.status = 0u;
+    Cons cs[kMaxCons];
+    Cons proj[kMaxCons];
+    int on[kMaxObstNeighbors];
+    float range = kLookAhead * maxSpeed + clearance;  // ORCA.cpp:27
+    int n_on = find_obstacles(ob, bins, position, range * range, on, kMaxObstNeighbors);
+    if (n_on > kMaxObstNeighbors) { n_on = kMaxObstNeighbors; res.status |= 16u; }
+    int nc = 0;
+    for (int i = 0; i < n_on; i++) {
+        Cons c;
+        if (obstacle_constraint(ob, on[i], position, velocity, clearance, c)) cs[nc++] = c;
+    }
+    const int nObst = nc;
+    for (int i = 0; i < n_nb; i++) {
+        int q = nb_q[i];
+        cs[nc++] = agent_constraint(position, velocity, clearance, __ldg(&g.s_pos[q]), __ldg(&g.s_vel[q]), __ldg(&g.s_rad[q]), stepSize);
+    }
+    v2 out = V(0.0f, 0.0f);
+    int failed = randomized_lp(cs, nc, prefVel, maxSpeed, false, out);
+    if (failed < nc) {
+        res.status |= 64u;
+        randomized_lp3d(nObst, cs, nc, maxSpeed, failed, out, proj);
+    }
+    res.velocity = out;
+    return res;
+}
+
+}  // namespace ecm

@@ -1,0 +1,366 @@
+// Kernels of one simulation tick (Simulator::Update, /root/reference/ECMAgentSimulator/Simulator.cpp:314-323).
+//
+//   k_bin_count   cell key + rank of every active agent            (replaces KDTree::Construct, KDTree.cpp:22-57)
+//   k_scan_*      exclusive scan of the per-cell counts
+//   k_scatter     counting-sort scatter: SoA snapshot of the pre-tick state in cell order
+//   k_attract     arrival test, ECM point location, IRM attraction point, preferred velocity
+//                 (UpdateAttractionPointSystem + ApplySteeringForce, Simulator.cpp:538-590, 638-657)
+//   k_orca        exact 5-NN, obstacle gather, ORCA half-planes, LP / LP3D, velocity and position
+//                 integration (ApplyObstacleAvoidanceForce, UpdateVelocitySystem, UpdatePositionSystem,
+//                 Simulator.cpp:659-686, 619-635, 592-606)
+//   k_fallback    warp-per-agent exhaustive neighbour search for agents whose ring budget ran out
+//
+// The snapshot makes the tick Jacobi-style exactly like the reference: every agent reads its
+// neighbours' PRE-tick position / velocity / radius (ORCA.cpp:342-344) while new values are written
+// to the slot arrays.  Agents destroyed on arrival this tick stay in the snapshot, i.e. remain
+// visible as neighbours for this tick (KD-tree membership is frozen before arrivals, Simulator.cpp:319).
+#pragma once
+#include "locate.cuh"
+#include "orca.cuh"
+
+namespace ecm {
+
+enum Counter {
+    C_REPLAN_N = 0,     // entries in ev_replan since the last poll
+    C_DESTROYED_N = 1,  // entries in ev_destroyed since the last poll
+    C_FALLBACK_N = 2,   // entries in fb_list this tick (reset every tick)
+    C_TOTAL_FALLBACK = 3,
+    C_TOTAL_OBST_OVF = 4,
+    C_TOTAL_LP3D = 5,
+    C_TOTAL_LOCFAIL = 6,
+    C_TOTAL_REPLAN = 7,
+    C_TOTAL_HALO_MISS = 8,
+    C_COUNT = 16
+};
+
+// Mutable per-slot agent components (structure of arrays, indexed by slot = global agent id).
+struct AgentArrays {
+    float2* pos;          // Simulator::m_Positions
+    float2* vel;          // m_Velocities
+    float2* prefvel;      // m_PreferredVelocities
+    float2* attraction;   // m_AttractionPoints
+    float2* force;        // m_Forces
+    float* radius;        // m_Clearances
+    float* speed;         // m_PreferredSpeed
+    unsigned char* active;        // m_ActiveAgents
+    unsigned char* replan_pending;
+    unsigned* status;
+    int* cell;            // located ECM cell of the last tick
+    int* nbr;             // [5*slot] neighbour slot ids of the last tick (optional)
+    int* nbr_cnt;
+    const int2* path_hdr;   // (offset, length) into path_pool
+    const float2* path_pool;
+};
+
+struct TickScratch {
+    int* key;       // [slot] cell key, -1 inactive
+    int* rank;      // [slot] arrival order inside the cell
+    int* cell_count;  // [ncells_padded] -> scanned in place into cell_start
+    int* block_sums;
+    float2* s_pos; float2* s_vel; float* s_rad; float* s_spd; int* s_slot;
+    float2* s_pref; unsigned char* s_alive;
+    int* fb_list;
+    int* ev_replan; int* ev_destroyed;
+    unsigned long long* counters;
+};
+
+struct GridParams {
+    float x0, y0, cell, inv_cell;
+    int w, h;
+};
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bin_count(int n_slots, const unsigned char* __restrict__ active,
+                                                   const float2* __restrict__ pos, GridParams gp, int* __restrict__ cell_count,
+                                                   int* __restrict__ key, int* __restrict__ rank) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    if (!active[i]) { key[i] = -1; return; }
+    float2 p = pos[i];
+    float fx = (p.x - gp.x0) * gp.inv_cell, fy = (p.y - gp.y0) * gp.inv_cell;
+    int cx = fx >= 0.0f ? (fx < (float)gp.w ? (int)fx : gp.w - 1) : 0;
+    int cy = fy >= 0.0f ? (fy < (float)gp.h ? (int)fy : gp.h - 1) : 0;
+    int k = cy * gp.w + cx;
+    key[i] = k;
+    rank[i] = atomicAdd(&cell_count[k], 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exclusive scan, 4096 elements per block (1024 threads x int4).
+constexpr int kScanBlock = 1024;
+constexpr int kScanTile = 4096;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int& total) {
+    __shared__ int warp_sums[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int s = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
+        }
+        warp_sums[lane] = s;
+    }
+    __syncthreads();
+    int base = warp > 0 ? warp_sums[warp - 1] : 0;
+    total = warp_sums[31];
+    __syncthreads();
+    return base + x - v;
+}
+
+__global__ void __launch_bounds__(kScanBlock) k_scan_tiles(int4* __restrict__ data, int* __restrict__ block_sums) {
+    int idx = blockIdx.x * kScanBlock + threadIdx.x;
+    int4 v = data[idx];
+    int s = v.x + v.y + v.z + v.w, total;
+    int ex = block_exclusive_scan(s, total);
+    int4 o;
+    o.x = ex; o.y = ex + v.x; o.z = o.y + v.y; o.w = o.z + v.z;
+    data[idx] = o;
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanBlock) k_scan_sums(int* __restrict__ block_sums, int n) {
+    // single block; n <= 4096 * k handled in chunks with a running carry
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += kScanBlock) {
+        int i = base + threadIdx.x;
+        int v = i < n ? block_sums[i] : 0, total;
+        int ex = block_exclusive_scan(v, total);
+        int carry = carry_s;
+        if (i < n) block_sums[i] = ex + carry;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kScanBlock) k_scan_add(int4* __restrict__ data, const int* __restrict__ block_sums) {
+    int idx = blockIdx.x * kScanBlock + threadIdx.x;
+    int add = block_sums[blockIdx.x];
+    int4 v = data[idx];
+    v.x += add; v.y += add; v.z += add; v.w += add;
+    data[idx] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter(int n_slots, const int* __restrict__ key, const int* __restrict__ rank,
+                                                 const int* __restrict__ cell_start, AgentArrays ag, TickScratch sc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    int k = key[i];
+    if (k < 0) return;
+    int p = cell_start[k] + rank[i];
+    sc.s_pos[p] = ag.pos[i];
+    sc.s_vel[p] = ag.vel[i];
+    sc.s_rad[p] = ag.radius[i];
+    sc.s_spd[p] = ag.speed[i];
+    sc.s_slot[p] = i;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct TickView {
+    EcmView ecm;
+    ObstView obst;
+    BinView bins;
+    GridView grid;
+    AgentArrays ag;
+    TickScratch sc;
+    const int* n_sorted_ptr;  // = &cell_start[w*h]: number of agents in the snapshot
+    float step;
+    int max_ring;
+    int record_neighbors;
+};
+
+__global__ void __launch_bounds__(128) k_attract(TickView t) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *t.n_sorted_ptr;
+    const bool valid = p < n;
+    unsigned st = 0u;
+    if (valid) {
+        const int slot = t.sc.s_slot[p];
+        const v2 pos = t.sc.s_pos[p];
+        const int2 hdr = t.ag.path_hdr[slot];
+        const float2* path = t.ag.path_pool + hdr.x;
+        const int np = hdr.y;
+        const v2 goal = path[np - 1];
+        // SquareDistance(float,float,float,float) (UtilityFunctions.cpp:43-49)
+        const float ddx = pos.x - goal.x, ddy = pos.y - goal.y;
+        const float dist = ddx * ddx + ddy * ddy;
+        int cell = -2;
+        v2 attr;
+        bool have = false, alive = true;
+        if (dist < 20.0f * 20.0f) {  // arrival radius (Simulator.cpp:543, 557-562)
+            attr = goal;
+            have = true;
+            st |= 4u;
+            if (dist < 2.0f * 2.0f) {  // delete distance (Simulator.cpp:542, 564-566)
+                alive = false;
+                st |= 8u;
+                t.ag.active[slot] = 0;
+                int e = (int)atomicAdd(&t.sc.counters[C_DESTROYED_N], 1ull);
+                t.sc.ev_destroyed[e] = slot;
+            }
+        } else {
+            v2 ap = V(0.0f, 0.0f);  // `Point attractionPoint;` is (0,0) (Simulator.cpp:570)
+            if (find_attraction_point(t.ecm, t.bins, pos, path, np, ap, cell)) {
+                attr = ap;
+                have = true;
+            } else {
+                st |= 2u;
+                if (cell == -1) st |= 1u;
+                if (!t.ag.replan_pending[slot]) {  // one event per request; cleared by ecmgpu_set_path
+                    t.ag.replan_pending[slot] = 1;
+                    int e = (int)atomicAdd(&t.sc.counters[C_REPLAN_N], 1ull);
+                    t.sc.ev_replan[e] = slot;
+                }
+            }
+        }
+        if (have) t.ag.attraction[slot] = attr;
+        else attr = t.ag.attraction[slot];  // previous attraction point is kept (Simulator.cpp:573-587)
+        if (alive) {  // ApplySteeringForce (Simulator.cpp:638-657)
+            v2 d = vnormalized(vsub(attr, pos));
+            v2 pv = vmul(d, t.sc.s_spd[p]);
+            t.ag.prefvel[slot] = pv;
+            t.sc.s_pref[p] = pv;
+        }
+        t.sc.s_alive[p] = alive ? 1 : 0;
+        t.ag.status[slot] = st;
+        t.ag.cell[slot] = cell;
+    }
+    // warp-aggregated statistics
+    unsigned m_loc = __ballot_sync(0xffffffffu, (st & 1u) != 0u);
+    unsigned m_rep = __ballot_sync(0xffffffffu, (st & 2u) != 0u);
+    if ((threadIdx.x & 31) == 0) {
+        if (m_loc) atomicAdd(&t.sc.counters[C_TOTAL_LOCFAIL], (unsigned long long)__popc(m_loc));
+        if (m_rep) atomicAdd(&t.sc.counters[C_TOTAL_REPLAN], (unsigned long long)__popc(m_rep));
+    }
+}
+
+// ORCA + integration for one agent whose neighbour list is known.
+__device__ __forceinline__ unsigned finish_agent(const TickView& t, int p, const Knn& k) {
+    const int slot = t.sc.s_slot[p];
+    const v2 pos = t.sc.s_pos[p], vel = t.sc.s_vel[p];
+    const float rad = t.sc.s_rad[p], spd = t.sc.s_spd[p];
+    const int n_nb = k.count();
+    OrcaResult r = orca_velocity(t.obst, t.bins, t.grid, pos, vel, rad, spd, t.sc.s_pref[p], n_nb, k.q, t.step);
+    // force = v_orca - v (Simulator.cpp:676-677)
+    const v2 f = V(r.velocity.x - vel.x, r.velocity.y - vel.y);
+    // v += force * (1/mass) * step (Simulator.cpp:622-633); p += v * step (Simulator.cpp:603-604)
+    const float massRecip = 1.0f / 0.8f;
+    const v2 nv = V(vel.x + f.x * massRecip * t.step, vel.y + f.y * massRecip * t.step);
+    const v2 np = V(pos.x + (nv.x * t.step), pos.y + (nv.y * t.step));
+    t.ag.force[slot] = f;
+    t.ag.vel[slot] = nv;
+    t.ag.pos[slot] = np;
+    if (t.record_neighbors) {
+#pragma unroll
+        for (int j = 0; j < kK; j++) t.ag.nbr[kK * slot + j] = k.q[j] >= 0 ? t.sc.s_slot[k.q[j]] : -1;
+        t.ag.nbr_cnt[slot] = n_nb;
+    }
+    return r.status;
+}
+
+__global__ void __launch_bounds__(128) k_orca(TickView t) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *t.n_sorted_ptr;
+    unsigned st = 0u;
+    if (p < n && t.sc.s_alive[p]) {
+        Knn k;
+        if (knn_grid(k, t.sc.s_pos[p], t.grid, t.max_ring)) {
+            st = finish_agent(t, p, k);
+        } else {
+            st = 32u;
+            int e = (int)atomicAdd(&t.sc.counters[C_FALLBACK_N], 1ull);
+            t.sc.fb_list[e] = p;
+        }
+        if (st) t.ag.status[t.sc.s_slot[p]] |= st;
+    }
+    unsigned m_ovf = __ballot_sync(0xffffffffu, (st & 16u) != 0u);
+    unsigned m_lp3 = __ballot_sync(0xffffffffu, (st & 64u) != 0u);
+    unsigned m_fb = __ballot_sync(0xffffffffu, (st & 32u) != 0u);
+    if ((threadIdx.x & 31) == 0) {
+        if (m_ovf) atomicAdd(&t.sc.counters[C_TOTAL_OBST_OVF], (unsigned long long)__popc(m_ovf));
+        if (m_lp3) atomicAdd(&t.sc.counters[C_TOTAL_LP3D], (unsigned long long)__popc(m_lp3));
+        if (m_fb) atomicAdd(&t.sc.counters[C_TOTAL_FALLBACK], (unsigned long long)__popc(m_fb));
+    }
+}
+
+// mode 0: full tick for the listed agents; mode 1: neighbour query only (ecmgpu_find_neighbors)
+__global__ void __launch_bounds__(128) k_fallback(TickView t, int mode) {
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n = (int)t.sc.counters[C_FALLBACK_N];
+    GridView g = t.grid;
+    g.n_sorted = *t.n_sorted_ptr;
+    for (int i = warp; i < n; i += warps_total) {
+        const int p = t.sc.fb_list[i];
+        Knn k;
+        knn_exhaustive(k, t.sc.s_pos[p], g);
+        if (lane == 0) {
+            if (mode == 0) {
+                unsigned st = finish_agent(t, p, k);
+                if (st & 16u) atomicAdd(&t.sc.counters[C_TOTAL_OBST_OVF], 1ull);
+                if (st & 64u) atomicAdd(&t.sc.counters[C_TOTAL_LP3D], 1ull);
+                if (st) t.ag.status[t.sc.s_slot[p]] |= st;
+            } else {
+                const int slot = t.sc.s_slot[p];
+                for (int j = 0; j < kK; j++) t.ag.nbr[kK * slot + j] = k.q[j] >= 0 ? t.sc.s_slot[k.q[j]] : -1;
+                t.ag.nbr_cnt[slot] = k.count();
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Query kernels (ecmgpu_locate / ecmgpu_retract / ecmgpu_find_neighbors / ecmgpu_find_obstacles)
+__global__ void k_locate(EcmView ecm, BinView bins, int n, const float2* __restrict__ xy, int* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = find_cell(ecm, bins, xy[i]);
+}
+
+__global__ void k_retract(EcmView ecm, BinView bins, int n, const float2* __restrict__ xy, unsigned char* __restrict__ ok,
+                          float2* __restrict__ out, int* __restrict__ edge) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    v2 p = xy[i], r = V(0.0f, 0.0f);
+    int c = find_cell(ecm, bins, p);
+    bool good = c >= 0 && retract_in_cell(ecm, c, p, r);
+    ok[i] = good ? 1 : 0;
+    out[i] = r;
+    edge[i] = c >= 0 ? (c >> 1) : -1;
+}
+
+__global__ void __launch_bounds__(128) k_knn_query(TickView t) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *t.n_sorted_ptr;
+    if (p >= n) return;
+    Knn k;
+    if (knn_grid(k, t.sc.s_pos[p], t.grid, t.max_ring)) {
+        const int slot = t.sc.s_slot[p];
+#pragma unroll
+        for (int j = 0; j < kK; j++) t.ag.nbr[kK * slot + j] = k.q[j] >= 0 ? t.sc.s_slot[k.q[j]] : -1;
+        t.ag.nbr_cnt[slot] = k.count();
+    } else {
+        int e = (int)atomicAdd(&t.sc.counters[C_FALLBACK_N], 1ull);
+        t.sc.fb_list[e] = p;
+    }
+}
+
+__global__ void k_find_obstacles(ObstView ob, BinView bins, float2 pos, float range2, int* out, int cap, int* out_n) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out_n = find_obstacles(ob, bins, pos, range2, out, cap);
+}
+
+}  // namespace ecm

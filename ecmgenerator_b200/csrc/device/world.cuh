@@ -1,0 +1,67 @@
+// Device views of the static world (flattened ECM + obstacles + the static bin grid) and of the
+// per-tick neighbour grid.  All pointers are device pointers owned by ecmgpu_sim.
+#pragma once
+#include "geom.cuh"
+
+namespace ecm {
+
+// Flattened ECMGraph (reference: ECM.h:20-50).  edge_cl holds L0 R0 L1 R1 per edge:
+//   half_edges[0].closest_left = L0, .closest_right = R0, half_edges[1].closest_left = R1, .closest_right = L1.
+struct EcmView {
+    int n_vertices, n_edges;
+    const float2* vert_xy;   // [nV]
+    const int2* edge_v;      // [nE] (v0, v1)
+    const float2* edge_cl;   // [4*nE]
+};
+
+// Obstacle vertices in (obstacle, vertex) order (reference: ECMDataTypes.h:160-166).
+struct ObstView {
+    int n;
+    const float2* xy;
+    const int* next;
+    const int* prev;
+    const unsigned char* convex;
+};
+
+// Uniform bins over the walkable-area bbox (+margin).  Per bin two ascending id lists (CSR):
+//   cell list  - ECM cells whose bounding box touches the bin: scanning it in order reproduces
+//                "first containing cell in index order" of PointLocationQueryLinear
+//                (ECMCellCollection.cpp:57-90);
+//   obst list  - obstacle segments within max_range of the bin: scanning it in order reproduces the
+//                (obstacle, vertex) order of FindNearestObstacles (Simulator.cpp:259-292).
+// A query point outside the grid falls back to the exhaustive scans (exactness over speed).
+struct BinView {
+    float x0, y0, inv_bin;
+    int w, h;
+    const int* cell_start;   // [w*h+1]
+    const int* cell_items;
+    const int* obst_start;   // [w*h+1]
+    const int* obst_items;
+    __device__ __forceinline__ int bin_of(v2 p) const {
+        float fx = (p.x - x0) * inv_bin, fy = (p.y - y0) * inv_bin;
+        // !(>=) also rejects NaN
+        if (!(fx >= 0.0f) || !(fy >= 0.0f) || !(fx < (float)w) || !(fy < (float)h)) return -1;
+        return (int)fy * w + (int)fx;
+    }
+};
+
+// Per-tick neighbour grid: agents active at the start of the tick, counting-sorted by cell key
+// (row-major), with a structure-of-arrays snapshot of their pre-tick state in sorted order.
+struct GridView {
+    float x0, y0, cell, inv_cell;
+    int w, h;
+    int n_sorted;             // number of agents in the snapshot
+    const int* cell_start;    // [w*h+1] exclusive scan of per-cell counts
+    const float2* s_pos;      // [n_sorted] pre-tick position
+    const float2* s_vel;      // [n_sorted] pre-tick velocity
+    const float* s_rad;       // [n_sorted] radius
+    const int* s_slot;        // [n_sorted] slot id (global agent id)
+    __device__ __forceinline__ void cell_of(v2 p, int& cx, int& cy) const {
+        float fx = (p.x - x0) * inv_cell, fy = (p.y - y0) * inv_cell;
+        // clamp (NaN -> 0): agents outside the grid live in the border cells
+        cx = fx >= 0.0f ? (fx < (float)w ? (int)fx : w - 1) : 0;
+        cy = fy >= 0.0f ? (fy < (float)h ? (int)fy : h - 1) : 0;
+    }
+};
+
+}  // namespace ecm

@@ -1,0 +1,941 @@
+// libecmgpu.so - implementation of the C ABI in include/ecm_b200.h.
+//
+// Owns all device state of one simulator: the flattened static world (ECM, obstacles, static bins),
+// the per-slot agent components, the path pool, the per-tick neighbour grid + snapshot, and the
+// event queues.  One CUDA stream per handle; ecmgpu_update() enqueues the kernels of device/tick.cuh.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include "../../include/ecm_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "device/tick.cuh"
+
+#ifdef ECMGPU_WITH_NCCL
+#include <nccl.h>
+#endif
+
+using namespace ecm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        free();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    void free() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+}  // namespace
+
+struct ecmgpu_sim {
+    ecmgpu_params prm{};
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // ---- static world, host copies (bins are (re)built from these)
+    float bbox[4] = {0, 0, 0, 0};
+    std::vector<float> h_vert_xy, h_edge_cl, h_obst_xy;
+    std::vector<int> h_edge_v, h_obst_next;
+    bool have_ecm = false, have_obst = false, bins_dirty = true;
+    float built_range = 0.0f;   // obstacle range the bins were built for
+    float tracked_range = 0.0f; // max over loaded agents of 10*speed + radius
+    float static_bin = 0.0f;
+    int bins_w = 0, bins_h = 0, max_cell_list = 0, max_obst_list = 0;
+    float bins_x0 = 0, bins_y0 = 0;
+
+    // ---- static world, device
+    DevBuf<float2> d_vert_xy, d_edge_cl, d_obst_xy;
+    DevBuf<int2> d_edge_v;
+    DevBuf<int> d_obst_next, d_obst_prev;
+    DevBuf<unsigned char> d_obst_convex;
+    DevBuf<int> d_bin_cell_start, d_bin_cell_items, d_bin_obst_start, d_bin_obst_items;
+    int n_vertices = 0, n_edges = 0, n_obst = 0;
+
+    // ---- agents, device (per slot)
+    DevBuf<float2> d_pos, d_vel, d_prefvel, d_attraction, d_force;
+    DevBuf<float> d_radius, d_speed;
+    DevBuf<unsigned char> d_active, d_replan_pending;
+    DevBuf<unsigned> d_status;
+    DevBuf<int> d_cell, d_nbr, d_nbr_cnt;
+    DevBuf<int2> d_path_hdr;
+    DevBuf<float2> d_path_pool;
+    // host mirror of the path pool (append-only, compacted on overflow)
+    std::vector<int2> h_path_hdr;
+    std::vector<float2> h_path_pool;
+    size_t pool_uploaded = 0;  // prefix of h_path_pool already resident on the device
+    int n_slots = 0;
+
+    // ---- neighbour grid + snapshot
+    float cell = 0.0f;
+    int gw = 0, gh = 0, ncells_padded = 0;
+    float gx0 = 0, gy0 = 0;
+    bool grid_dirty = true;
+    DevBuf<int> d_key, d_rank, d_cell_count, d_block_sums, d_s_slot, d_fb_list, d_ev_replan, d_ev_destroyed;
+    DevBuf<float2> d_s_pos, d_s_vel, d_s_pref;
+    DevBuf<float> d_s_rad, d_s_spd;
+    DevBuf<unsigned char> d_s_alive;
+    DevBuf<unsigned long long> d_counters;
+
+    // ---- bookkeeping
+    uint64_t ticks = 0, launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    int max_ring = 8;
+};
+
+namespace {
+
+int fail(ecmgpu_sim* s, int code, const std::string& msg) {
+    if (s) s->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(s, expr)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            return fail((s), ECMGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// ---- host geometry for the static bins --------------------------------------------------------
+struct Rect { double x0, y0, x1, y1; };
+
+double point_rect_dist(double px, double py, const Rect& r) {
+    double dx = std::max(std::max(r.x0 - px, 0.0), px - r.x1);
+    double dy = std::max(std::max(r.y0 - py, 0.0), py - r.y1);
+    return std::sqrt(dx * dx + dy * dy);
+}
+double point_seg_dist(double px, double py, double ax, double ay, double bx, double by) {
+    double vx = bx - ax, vy = by - ay, wx = px - ax, wy = py - ay;
+    double l2 = vx * vx + vy * vy;
+    double t = l2 > 0 ? std::min(1.0, std::max(0.0, (wx * vx + wy * vy) / l2)) : 0.0;
+    double cx = ax + t * vx - px, cy = ay + t * vy - py;
+    return std::sqrt(cx * cx + cy * cy);
+}
+bool seg_hits_rect(double ax, double ay, double bx, double by, const Rect& r) {  // Liang-Barsky
+    double t0 = 0, t1 = 1, dx = bx - ax, dy = by - ay;
+    const double p[4] = {-dx, dx, -dy, dy}, q[4] = {ax - r.x0, r.x1 - ax, ay - r.y0, r.y1 - ay};
+    for (int i = 0; i < 4; i++) {
+        if (p[i] == 0) { if (q[i] < 0) return false; }
+        else {
+            double t = q[i] / p[i];
+            if (p[i] < 0) { if (t > t1) return false; t0 = std::max(t0, t); }
+            else { if (t < t0) return false; t1 = std::min(t1, t); }
+        }
+    }
+    return true;
+}
+double seg_rect_dist(double ax, double ay, double bx, double by, const Rect& r) {
+    if (seg_hits_rect(ax, ay, bx, by, r)) return 0.0;
+    double d = std::min(point_rect_dist(ax, ay, r), point_rect_dist(bx, by, r));
+    d = std::min(d, point_seg_dist(r.x0, r.y0, ax, ay, bx, by));
+    d = std::min(d, point_seg_dist(r.x1, r.y0, ax, ay, bx, by));
+    d = std::min(d, point_seg_dist(r.x0, r.y1, ax, ay, bx, by));
+    d = std::min(d, point_seg_dist(r.x1, r.y1, ax, ay, bx, by));
+    return d;
+}
+
+// Builds the two CSR lists of BinView on the host and uploads them.
+int build_bins(ecmgpu_sim* s) {
+    const double W = (double)s->bbox[2] - s->bbox[0], H = (double)s->bbox[3] - s->bbox[1];
+    if (!(W > 0) || !(H > 0)) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_ecm: empty bbox");
+    double bin = s->prm.static_bin;
+    if (!(bin > 0)) bin = 0.4 * std::sqrt(W * H / std::max(1, s->n_edges));
+    // keep the bin count bounded
+    while ((W / bin + 3) * (H / bin + 3) > 16.0e6) bin *= 1.5;
+    s->static_bin = (float)bin;
+    s->bins_x0 = (float)(s->bbox[0] - bin);
+    s->bins_y0 = (float)(s->bbox[1] - bin);
+    s->bins_w = (int)std::ceil((W + 2 * bin) / bin) + 1;
+    s->bins_h = (int)std::ceil((H + 2 * bin) / bin) + 1;
+    const int nb = s->bins_w * s->bins_h;
+    const double x0 = s->bins_x0, y0 = s->bins_y0;
+    // The device computes the bin as (int)((p - x0) * inv_bin) in float; pad every footprint by
+    // `slack` so float rounding of that expression can never put a point in an unlisted bin.
+    const double slack = 1e-3 * bin + 1e-3;
+    auto bin_range = [&](double lo, double hi, double origin, int n, int& a, int& b) {
+        a = (int)std::floor((lo - slack - origin) / bin);
+        b = (int)std::floor((hi + slack - origin) / bin);
+        a = std::max(a, 0);
+        b = std::min(b, n - 1);
+    };
+
+    // -- ECM cells: bounding box of the cell polygon (v0, b0, b1, v1)
+    std::vector<int> cstart(nb + 1, 0), citems;
+    {
+        const int nc = 2 * s->n_edges;
+        std::vector<int> ax(nc), bx(nc), ay(nc), by(nc);
+        for (int c = 0; c < nc; c++) {
+            int e = c >> 1, side = c & 1;
+            const float* cl = &s->h_edge_cl[8 * e];
+            const float* v0 = &s->h_vert_xy[2 * s->h_edge_v[2 * e]];
+            const float* v1 = &s->h_vert_xy[2 * s->h_edge_v[2 * e + 1]];
+            const float* b0 = cl + 2 * side;
+            const float* b1 = cl + 4 + 2 * side;
+            double lox = std::min(std::min(v0[0], v1[0]), std::min(b0[0], b1[0]));
+            double hix = std::max(std::max(v0[0], v1[0]), std::max(b0[0], b1[0]));
+            double loy = std::min(std::min(v0[1], v1[1]), std::min(b0[1], b1[1]));
+            double hiy = std::max(std::max(v0[1], v1[1]), std::max(b0[1], b1[1]));
+            bin_range(lox, hix, x0, s->bins_w, ax[c], bx[c]);
+            bin_range(loy, hiy, y0, s->bins_h, ay[c], by[c]);
+            for (int y = ay[c]; y <= by[c]; y++)
+                for (int x = ax[c]; x <= bx[c]; x++) cstart[y * s->bins_w + x + 1]++;
+        }
+        for (int i = 0; i < nb; i++) cstart[i + 1] += cstart[i];
+        citems.resize(cstart[nb]);
+        std::vector<int> fill(cstart.begin(), cstart.end() - 1);
+        for (int c = 0; c < nc; c++)  // ascending c => every list ascending
+            for (int y = ay[c]; y <= by[c]; y++)
+                for (int x = ax[c]; x <= bx[c]; x++) citems[fill[y * s->bins_w + x]++] = c;
+        s->max_cell_list = 0;
+        for (int i = 0; i < nb; i++) s->max_cell_list = std::max(s->max_cell_list, cstart[i + 1] - cstart[i]);
+    }
+    // -- obstacle segments within `range` of the bin rectangle
+    const double range = std::max(s->prm.max_obstacle_range > 0 ? (double)s->prm.max_obstacle_range : 0.0, (double)s->tracked_range);
+    std::vector<int> ostart(nb + 1, 0), oitems;
+    {
+        const int no = s->n_obst;
+        const double R = range * 1.0001 + slack;
+        std::vector<std::vector<int>> hits(no);
+        for (int o = 0; o < no; o++) {
+            const double ax_ = s->h_obst_xy[2 * o], ay_ = s->h_obst_xy[2 * o + 1];
+            const int nx = s->h_obst_next[o];
+            const double bx_ = s->h_obst_xy[2 * nx], by_ = s->h_obst_xy[2 * nx + 1];
+            int xa, xb, ya, yb;
+            bin_range(std::min(ax_, bx_) - R, std::max(ax_, bx_) + R, x0, s->bins_w, xa, xb);
+            bin_range(std::min(ay_, by_) - R, std::max(ay_, by_) + R, y0, s->bins_h, ya, yb);
+            for (int y = ya; y <= yb; y++)
+                for (int x = xa; x <= xb; x++) {
+                    Rect r{x0 + x * bin - slack, y0 + y * bin - slack, x0 + (x + 1) * bin + slack, y0 + (y + 1) * bin + slack};
+                    if (seg_rect_dist(ax_, ay_, bx_, by_, r) <= R) {
+                        hits[o].push_back(y * s->bins_w + x);
+                        ostart[y * s->bins_w + x + 1]++;
+                    }
+                }
+        }
+        for (int i = 0; i < nb; i++) ostart[i + 1] += ostart[i];
+        oitems.resize(ostart[nb]);
+        std::vector<int> fill(ostart.begin(), ostart.end() - 1);
+        for (int o = 0; o < no; o++)
+            for (int b : hits[o]) oitems[fill[b]++] = o;
+        s->max_obst_list = 0;
+        for (int i = 0; i < nb; i++) s->max_obst_list = std::max(s->max_obst_list, ostart[i + 1] - ostart[i]);
+    }
+    CUDA_TRY(s, s->d_bin_cell_start.alloc(nb + 1));
+    CUDA_TRY(s, s->d_bin_cell_items.alloc(std::max<size_t>(citems.size(), 1)));
+    CUDA_TRY(s, s->d_bin_obst_start.alloc(nb + 1));
+    CUDA_TRY(s, s->d_bin_obst_items.alloc(std::max<size_t>(oitems.size(), 1)));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_bin_cell_start.p, cstart.data(), sizeof(int) * (nb + 1), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_bin_cell_items.p, citems.data(), sizeof(int) * citems.size(), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_bin_obst_start.p, ostart.data(), sizeof(int) * (nb + 1), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_bin_obst_items.p, oitems.data(), sizeof(int) * oitems.size(), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));  // the host vectors die here
+    s->built_range = (float)range;
+    s->bins_dirty = false;
+    return ECMGPU_OK;
+}
+
+// Chooses the neighbour-grid cell from the crowd's local density and allocates the grid.
+int build_grid(ecmgpu_sim* s) {
+    double cell = s->prm.neighbor_cell;
+    const double W = (double)s->bbox[2] - s->bbox[0], H = (double)s->bbox[3] - s->bbox[1];
+    if (!(cell > 0)) {
+        // local density = agents per occupied 4x4 patch
+        std::vector<float2> pos(s->n_slots);
+        std::vector<unsigned char> act(s->n_slots);
+        CUDA_TRY(s, cudaMemcpyAsync(pos.data(), s->d_pos.p, sizeof(float2) * s->n_slots, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(act.data(), s->d_active.p, s->n_slots, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        const double patch = 4.0;
+        const int pw = std::max(1, (int)std::ceil(W / patch)), ph = std::max(1, (int)std::ceil(H / patch));
+        std::vector<unsigned char> occ((size_t)pw * ph, 0);
+        size_t n = 0, nocc = 0;
+        for (int i = 0; i < s->n_slots; i++) {
+            if (!act[i]) continue;
+            n++;
+            int x = std::min(pw - 1, std::max(0, (int)((pos[i].x - s->bbox[0]) / patch)));
+            int y = std::min(ph - 1, std::max(0, (int)((pos[i].y - s->bbox[1]) / patch)));
+            if (!occ[(size_t)y * pw + x]) { occ[(size_t)y * pw + x] = 1; nocc++; }
+        }
+        double rho = n > 0 ? (double)n / ((double)nocc * patch * patch) : 1.0;
+        cell = std::min(64.0, std::max(0.5, 1.7 / std::sqrt(rho)));
+    }
+    while ((W / cell + 3) * (H / cell + 3) > 32.0e6) cell *= 1.5;
+    s->cell = (float)cell;
+    s->gx0 = (float)(s->bbox[0] - cell);
+    s->gy0 = (float)(s->bbox[1] - cell);
+    s->gw = (int)std::ceil((W + 2 * cell) / cell) + 1;
+    s->gh = (int)std::ceil((H + 2 * cell) / cell) + 1;
+    const int ncells = s->gw * s->gh;
+    s->ncells_padded = div_up(ncells + 1, kScanTile) * kScanTile;
+    CUDA_TRY(s, s->d_cell_count.alloc(s->ncells_padded));
+    CUDA_TRY(s, s->d_block_sums.alloc(s->ncells_padded / kScanTile));
+    s->grid_dirty = false;
+    return ECMGPU_OK;
+}
+
+TickView make_view(ecmgpu_sim* s) {
+    TickView t;
+    t.ecm.n_vertices = s->n_vertices;
+    t.ecm.n_edges = s->n_edges;
+    t.ecm.vert_xy = s->d_vert_xy.p;
+    t.ecm.edge_v = s->d_edge_v.p;
+    t.ecm.edge_cl = s->d_edge_cl.p;
+    t.obst.n = s->n_obst;
+    t.obst.xy = s->d_obst_xy.p;
+    t.obst.next = s->d_obst_next.p;
+    t.obst.prev = s->d_obst_prev.p;
+    t.obst.convex = s->d_obst_convex.p;
+    t.bins.x0 = s->bins_x0;
+    t.bins.y0 = s->bins_y0;
+    t.bins.inv_bin = 1.0f / s->static_bin;
+    t.bins.w = s->bins_w;
+    t.bins.h = s->bins_h;
+    t.bins.cell_start = s->d_bin_cell_start.p;
+    t.bins.cell_items = s->d_bin_cell_items.p;
+    t.bins.obst_start = s->d_bin_obst_start.p;
+    t.bins.obst_items = s->d_bin_obst_items.p;
+    t.grid.x0 = s->gx0;
+    t.grid.y0 = s->gy0;
+    t.grid.cell = s->cell;
+    t.grid.inv_cell = 1.0f / s->cell;
+    t.grid.w = s->gw;
+    t.grid.h = s->gh;
+    t.grid.n_sorted = 0;
+    t.grid.cell_start = s->d_cell_count.p;
+    t.grid.s_pos = s->d_s_pos.p;
+    t.grid.s_vel = s->d_s_vel.p;
+    t.grid.s_rad = s->d_s_rad.p;
+    t.grid.s_slot = s->d_s_slot.p;
+    t.ag.pos = s->d_pos.p;
+    t.ag.vel = s->d_vel.p;
+    t.ag.prefvel = s->d_prefvel.p;
+    t.ag.attraction = s->d_attraction.p;
+    t.ag.force = s->d_force.p;
+    t.ag.radius = s->d_radius.p;
+    t.ag.speed = s->d_speed.p;
+    t.ag.active = s->d_active.p;
+    t.ag.replan_pending = s->d_replan_pending.p;
+    t.ag.status = s->d_status.p;
+    t.ag.cell = s->d_cell.p;
+    t.ag.nbr = s->d_nbr.p;
+    t.ag.nbr_cnt = s->d_nbr_cnt.p;
+    t.ag.path_hdr = s->d_path_hdr.p;
+    t.ag.path_pool = s->d_path_pool.p;
+    t.sc.key = s->d_key.p;
+    t.sc.rank = s->d_rank.p;
+    t.sc.cell_count = s->d_cell_count.p;
+    t.sc.block_sums = s->d_block_sums.p;
+    t.sc.s_pos = s->d_s_pos.p;
+    t.sc.s_vel = s->d_s_vel.p;
+    t.sc.s_rad = s->d_s_rad.p;
+    t.sc.s_spd = s->d_s_spd.p;
+    t.sc.s_slot = s->d_s_slot.p;
+    t.sc.s_pref = s->d_s_pref.p;
+    t.sc.s_alive = s->d_s_alive.p;
+    t.sc.fb_list = s->d_fb_list.p;
+    t.sc.ev_replan = s->d_ev_replan.p;
+    t.sc.ev_destroyed = s->d_ev_destroyed.p;
+    t.sc.counters = s->d_counters.p;
+    t.n_sorted_ptr = s->d_cell_count.p + (size_t)s->gw * s->gh;
+    t.step = s->prm.step;
+    t.max_ring = s->max_ring;
+    t.record_neighbors = s->prm.record_neighbors;
+    return t;
+}
+
+int ensure_ready(ecmgpu_sim* s) {
+    if (!s->have_ecm) return fail(s, ECMGPU_ERR_INVALID, "no ECM: call ecmgpu_set_ecm first");
+    const float want = std::max(s->prm.max_obstacle_range > 0 ? s->prm.max_obstacle_range : 0.0f, s->tracked_range);
+    if (s->bins_dirty || want > s->built_range) {
+        int rc = build_bins(s);
+        if (rc) return rc;
+    }
+    if (s->grid_dirty) {
+        int rc = build_grid(s);
+        if (rc) return rc;
+    }
+    return ECMGPU_OK;
+}
+
+// count + scan + scatter: the per-tick neighbour structure
+int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
+    GridParams gp{s->gx0, s->gy0, s->cell, 1.0f / s->cell, s->gw, s->gh};
+    CUDA_TRY(s, cudaMemsetAsync(s->d_cell_count.p, 0, sizeof(int) * s->ncells_padded, s->stream));
+    CUDA_TRY(s, cudaMemsetAsync(s->d_counters.p + C_FALLBACK_N, 0, sizeof(unsigned long long), s->stream));
+    const int nb = div_up(s->n_slots, 256);
+    k_bin_count<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p);
+    const int tiles = s->ncells_padded / kScanTile;
+    k_scan_tiles<<<tiles, kScanBlock, 0, s->stream>>>((int4*)s->d_cell_count.p, s->d_block_sums.p);
+    k_scan_sums<<<1, kScanBlock, 0, s->stream>>>(s->d_block_sums.p, tiles);
+    k_scan_add<<<tiles, kScanBlock, 0, s->stream>>>((int4*)s->d_cell_count.p, s->d_block_sums.p);
+    k_scatter<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc);
+    s->launches += 5;
+    CUDA_TRY(s, cudaGetLastError());
+    return ECMGPU_OK;
+}
+
+int upload_path(ecmgpu_sim* s, int slot, const float* xy, int n) {
+    if (n < 1) return fail(s, ECMGPU_ERR_INVALID, "path needs at least 1 point");
+    const size_t cap = s->d_path_pool.n;
+    if (s->h_path_pool.size() + n > cap) {
+        // compact: rebuild the pool from the live headers
+        std::vector<float2> np;
+        np.reserve(cap);
+        for (int i = 0; i < s->n_slots; i++) {
+            int2& h = s->h_path_hdr[i];
+            if (h.y <= 0 || i == slot) { if (i == slot) h = make_int2(0, 0); continue; }
+            int off = (int)np.size();
+            np.insert(np.end(), s->h_path_pool.begin() + h.x, s->h_path_pool.begin() + h.x + h.y);
+            h.x = off;
+        }
+        if (np.size() + n > cap) return fail(s, ECMGPU_ERR_CAPACITY, "path pool full (raise ecmgpu_params.path_pool_points)");
+        s->h_path_pool.swap(np);
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_path_pool.p, s->h_path_pool.data(), sizeof(float2) * s->h_path_pool.size(), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p, s->h_path_hdr.data(), sizeof(int2) * s->n_slots, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        s->pool_uploaded = s->h_path_pool.size();
+    }
+    const int off = (int)s->h_path_pool.size();
+    for (int j = 0; j < n; j++) s->h_path_pool.push_back(make_float2(xy[2 * j], xy[2 * j + 1]));
+    s->h_path_hdr[slot] = make_int2(off, n);
+    return ECMGPU_OK;
+}
+
+size_t elem_size(int which) {
+    switch (which) {
+        case ECMGPU_POS: case ECMGPU_VEL: case ECMGPU_PREFVEL: case ECMGPU_ATTRACTION: case ECMGPU_FORCE: return 8;
+        case ECMGPU_RADIUS: case ECMGPU_SPEED: case ECMGPU_CELL: case ECMGPU_NEIGHBOR_COUNT: case ECMGPU_STATUS: return 4;
+        case ECMGPU_ACTIVE: return 1;
+        case ECMGPU_NEIGHBORS: return 20;
+        default: return 0;
+    }
+}
+void* dev_array(ecmgpu_sim* s, int which) {
+    switch (which) {
+        case ECMGPU_POS: return s->d_pos.p;
+        case ECMGPU_VEL: return s->d_vel.p;
+        case ECMGPU_PREFVEL: return s->d_prefvel.p;
+        case ECMGPU_ATTRACTION: return s->d_attraction.p;
+        case ECMGPU_FORCE: return s->d_force.p;
+        case ECMGPU_RADIUS: return s->d_radius.p;
+        case ECMGPU_SPEED: return s->d_speed.p;
+        case ECMGPU_ACTIVE: return s->d_active.p;
+        case ECMGPU_CELL: return s->d_cell.p;
+        case ECMGPU_NEIGHBORS: return s->d_nbr.p;
+        case ECMGPU_NEIGHBOR_COUNT: return s->d_nbr_cnt.p;
+        case ECMGPU_STATUS: return s->d_status.p;
+        default: return nullptr;
+    }
+}
+
+int check_range(ecmgpu_sim* s, int which, int first, int count) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (elem_size(which) == 0) return fail(s, ECMGPU_ERR_INVALID, "unknown array selector");
+    if (first < 0 || count < 0 || first + count > s->prm.max_agents) return fail(s, ECMGPU_ERR_INVALID, "slot range out of bounds");
+    return ECMGPU_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* ecmgpu_last_error(const ecmgpu_sim* sim) { return sim ? sim->err.c_str() : g_create_error.c_str(); }
+
+int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
+    if (!params || !out) return fail(nullptr, ECMGPU_ERR_INVALID, "ecmgpu_create: null argument");
+    *out = nullptr;
+    if (params->max_agents <= 0 || !(params->step > 0.0f)) return fail(nullptr, ECMGPU_ERR_INVALID, "ecmgpu_create: max_agents and step must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, ECMGPU_ERR_CUDA, std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    if (params->device < 0 || params->device >= ndev) return fail(nullptr, ECMGPU_ERR_INVALID, "ecmgpu_create: bad device ordinal");
+    e = cudaSetDevice(params->device);
+    if (e != cudaSuccess) return fail(nullptr, ECMGPU_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    ecmgpu_sim* s = new ecmgpu_sim();
+    s->prm = *params;
+    const size_t n = (size_t)params->max_agents;
+    const size_t pool = params->path_pool_points > 0 ? (size_t)params->path_pool_points : 16 * n;
+    auto bad = [&](cudaError_t ce, const char* what) {
+        fail(nullptr, ECMGPU_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
+        ecmgpu_destroy(s);
+        return ECMGPU_ERR_CUDA;
+    };
+#define TRY_ALLOC(x) do { cudaError_t ce = (x); if (ce != cudaSuccess) return bad(ce, #x); } while (0)
+    TRY_ALLOC(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    TRY_ALLOC(s->d_pos.alloc(n)); TRY_ALLOC(s->d_vel.alloc(n)); TRY_ALLOC(s->d_prefvel.alloc(n));
+    TRY_ALLOC(s->d_attraction.alloc(n)); TRY_ALLOC(s->d_force.alloc(n));
+    TRY_ALLOC(s->d_radius.alloc(n)); TRY_ALLOC(s->d_speed.alloc(n));
+    TRY_ALLOC(s->d_active.alloc(n)); TRY_ALLOC(s->d_replan_pending.alloc(n));
+    TRY_ALLOC(s->d_status.alloc(n)); TRY_ALLOC(s->d_cell.alloc(n));
+    TRY_ALLOC(s->d_nbr.alloc(5 * n)); TRY_ALLOC(s->d_nbr_cnt.alloc(n));
+    TRY_ALLOC(s->d_path_hdr.alloc(n)); TRY_ALLOC(s->d_path_pool.alloc(pool));
+    TRY_ALLOC(s->d_key.alloc(n)); TRY_ALLOC(s->d_rank.alloc(n));
+    TRY_ALLOC(s->d_s_pos.alloc(n)); TRY_ALLOC(s->d_s_vel.alloc(n)); TRY_ALLOC(s->d_s_pref.alloc(n));
+    TRY_ALLOC(s->d_s_rad.alloc(n)); TRY_ALLOC(s->d_s_spd.alloc(n)); TRY_ALLOC(s->d_s_slot.alloc(n));
+    TRY_ALLOC(s->d_s_alive.alloc(n)); TRY_ALLOC(s->d_fb_list.alloc(n));
+    TRY_ALLOC(s->d_ev_replan.alloc(n)); TRY_ALLOC(s->d_ev_destroyed.alloc(n));
+    TRY_ALLOC(s->d_counters.alloc(C_COUNT));
+    TRY_ALLOC(cudaMemsetAsync(s->d_pos.p, 0, 8 * n, s->stream)); TRY_ALLOC(cudaMemsetAsync(s->d_vel.p, 0, 8 * n, s->stream));
+    TRY_ALLOC(cudaMemsetAsync(s->d_prefvel.p, 0, 8 * n, s->stream)); TRY_ALLOC(cudaMemsetAsync(s->d_attraction.p, 0, 8 * n, s->stream));
+    TRY_ALLOC(cudaMemsetAsync(s->d_force.p, 0, 8 * n, s->stream));
+    TRY_ALLOC(cudaMemsetAsync(s->d_radius.p, 0, 4 * n, s->stream)); TRY_ALLOC(cudaMemsetAsync(s->d_speed.p, 0, 4 * n, s->stream));
+    TRY_ALLOC(cudaMemsetAsync(s->d_active.p, 0, n, s->stream)); TRY_ALLOC(cudaMemsetAsync(s->d_replan_pending.p, 0, n, s->stream));
+    TRY_ALLOC(cudaMemsetAsync(s->d_status.p, 0, 4 * n, s->stream)); TRY_ALLOC(cudaMemsetAsync(s->d_cell.p, 0xff, 4 * n, s->stream));
+    TRY_ALLOC(cudaMemsetAsync(s->d_nbr.p, 0xff, 20 * n, s->stream)); TRY_ALLOC(cudaMemsetAsync(s->d_nbr_cnt.p, 0, 4 * n, s->stream));
+    TRY_ALLOC(cudaMemsetAsync(s->d_path_hdr.p, 0, 8 * n, s->stream));
+    TRY_ALLOC(cudaMemsetAsync(s->d_counters.p, 0, sizeof(unsigned long long) * C_COUNT, s->stream));
+    for (auto& ev : s->ev) TRY_ALLOC(cudaEventCreate(&ev));
+    for (auto& ev : s->marks) TRY_ALLOC(cudaEventCreate(&ev));
+    TRY_ALLOC(cudaStreamSynchronize(s->stream));
+#undef TRY_ALLOC
+    s->h_path_hdr.assign(n, make_int2(0, 0));
+    s->h_path_pool.reserve(std::min<size_t>(pool, 1 << 20));
+    *out = s;
+    return ECMGPU_OK;
+}
+
+void ecmgpu_destroy(ecmgpu_sim* s) {
+    if (!s) return;
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : s->marks) if (ev) cudaEventDestroy(ev);
+    s->d_vert_xy.free(); s->d_edge_cl.free(); s->d_obst_xy.free(); s->d_edge_v.free();
+    s->d_obst_next.free(); s->d_obst_prev.free(); s->d_obst_convex.free();
+    s->d_bin_cell_start.free(); s->d_bin_cell_items.free(); s->d_bin_obst_start.free(); s->d_bin_obst_items.free();
+    s->d_pos.free(); s->d_vel.free(); s->d_prefvel.free(); s->d_attraction.free(); s->d_force.free();
+    s->d_radius.free(); s->d_speed.free(); s->d_active.free(); s->d_replan_pending.free(); s->d_status.free();
+    s->d_cell.free(); s->d_nbr.free(); s->d_nbr_cnt.free(); s->d_path_hdr.free(); s->d_path_pool.free();
+    s->d_key.free(); s->d_rank.free(); s->d_cell_count.free(); s->d_block_sums.free(); s->d_s_slot.free();
+    s->d_fb_list.free(); s->d_ev_replan.free(); s->d_ev_destroyed.free(); s->d_s_pos.free(); s->d_s_vel.free();
+    s->d_s_pref.free(); s->d_s_rad.free(); s->d_s_spd.free(); s->d_s_alive.free(); s->d_counters.free();
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int ecmgpu_set_ecm(ecmgpu_sim* s, const float bbox[4], int nV, const float* vert_xy, const float* vert_clear, int nE,
+                   const int* edge_v, const float* edge_cl) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (!bbox || nV <= 0 || nE <= 0 || !vert_xy || !edge_v || !edge_cl) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_ecm: bad arguments");
+    (void)vert_clear;  // vertex clearance is used by the planner (host) only
+    for (int e = 0; e < 2 * nE; e++)
+        if (edge_v[e] < 0 || edge_v[e] >= nV) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_ecm: edge vertex index out of range");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    memcpy(s->bbox, bbox, sizeof(float) * 4);
+    s->n_vertices = nV;
+    s->n_edges = nE;
+    s->h_vert_xy.assign(vert_xy, vert_xy + 2 * nV);
+    s->h_edge_v.assign(edge_v, edge_v + 2 * nE);
+    s->h_edge_cl.assign(edge_cl, edge_cl + 8 * nE);
+    CUDA_TRY(s, s->d_vert_xy.alloc(nV));
+    CUDA_TRY(s, s->d_edge_v.alloc(nE));
+    CUDA_TRY(s, s->d_edge_cl.alloc(4 * (size_t)nE));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_vert_xy.p, vert_xy, sizeof(float) * 2 * nV, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_edge_v.p, edge_v, sizeof(int) * 2 * nE, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_edge_cl.p, edge_cl, sizeof(float) * 8 * nE, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    s->have_ecm = true;
+    s->bins_dirty = true;
+    s->grid_dirty = true;
+    return ECMGPU_OK;
+}
+
+int ecmgpu_set_obstacles(ecmgpu_sim* s, int n, const float* xy, const int* next, const int* prev, const uint8_t* convex) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!xy || !next || !prev || !convex))) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_obstacles: bad arguments");
+    for (int i = 0; i < n; i++)
+        if (next[i] < 0 || next[i] >= n || prev[i] < 0 || prev[i] >= n) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_obstacles: link out of range");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    s->n_obst = n;
+    s->h_obst_xy.assign(xy, xy + 2 * (size_t)n);
+    s->h_obst_next.assign(next, next + n);
+    CUDA_TRY(s, s->d_obst_xy.alloc(std::max(n, 1)));
+    CUDA_TRY(s, s->d_obst_next.alloc(std::max(n, 1)));
+    CUDA_TRY(s, s->d_obst_prev.alloc(std::max(n, 1)));
+    CUDA_TRY(s, s->d_obst_convex.alloc(std::max(n, 1)));
+    if (n > 0) {
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_obst_xy.p, xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_obst_next.p, next, sizeof(int) * n, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_obst_prev.p, prev, sizeof(int) * n, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_obst_convex.p, convex, n, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    }
+    s->have_obst = true;
+    s->bins_dirty = true;
+    return ECMGPU_OK;
+}
+
+int ecmgpu_bulk_load(ecmgpu_sim* s, int n, const int* slots, const float* pos_xy, const float* radius, const float* speed,
+                     const int* path_off, const float* path_xy) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (n < 0 || !pos_xy || !radius || !speed || !path_off || !path_xy) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_bulk_load: bad arguments");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    int hi = s->n_slots;
+    for (int i = 0; i < n; i++) {
+        int slot = slots ? slots[i] : i;
+        if (slot < 0 || slot >= s->prm.max_agents) return fail(s, ECMGPU_ERR_CAPACITY, "ecmgpu_bulk_load: slot out of range");
+        if (path_off[i + 1] - path_off[i] < 1) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_bulk_load: empty path");
+        hi = std::max(hi, slot + 1);
+    }
+    s->n_slots = hi;
+    // host staging in slot order when contiguous, otherwise per-element copies
+    const bool contiguous = [&] {
+        if (!slots) return true;
+        for (int i = 0; i < n; i++) if (slots[i] != slots[0] + i) return false;
+        return true;
+    }();
+    const int first = slots ? (n > 0 ? slots[0] : 0) : 0;
+    for (int i = 0; i < n; i++) {
+        int slot = slots ? slots[i] : i;
+        int rc = upload_path(s, slot, path_xy + 2 * (size_t)path_off[i], path_off[i + 1] - path_off[i]);
+        if (rc) return rc;
+        s->tracked_range = std::max(s->tracked_range, kLookAhead * speed[i] + radius[i]);
+    }
+    std::vector<unsigned char> ones(n, 1);
+    if (contiguous && n > 0) {
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_pos.p + first, pos_xy, sizeof(float2) * n, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_radius.p + first, radius, sizeof(float) * n, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_speed.p + first, speed, sizeof(float) * n, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_active.p + first, ones.data(), n, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemsetAsync(s->d_vel.p + first, 0, sizeof(float2) * n, s->stream));
+        CUDA_TRY(s, cudaMemsetAsync(s->d_prefvel.p + first, 0, sizeof(float2) * n, s->stream));
+        CUDA_TRY(s, cudaMemsetAsync(s->d_force.p + first, 0, sizeof(float2) * n, s->stream));
+        CUDA_TRY(s, cudaMemsetAsync(s->d_attraction.p + first, 0, sizeof(float2) * n, s->stream));
+        CUDA_TRY(s, cudaMemsetAsync(s->d_replan_pending.p + first, 0, n, s->stream));
+    } else {
+        for (int i = 0; i < n; i++) {
+            int slot = slots[i];
+            CUDA_TRY(s, cudaMemcpyAsync(s->d_pos.p + slot, pos_xy + 2 * i, sizeof(float2), cudaMemcpyHostToDevice, s->stream));
+            CUDA_TRY(s, cudaMemcpyAsync(s->d_radius.p + slot, radius + i, sizeof(float), cudaMemcpyHostToDevice, s->stream));
+            CUDA_TRY(s, cudaMemcpyAsync(s->d_speed.p + slot, speed + i, sizeof(float), cudaMemcpyHostToDevice, s->stream));
+            CUDA_TRY(s, cudaMemcpyAsync(s->d_active.p + slot, ones.data(), 1, cudaMemcpyHostToDevice, s->stream));
+            CUDA_TRY(s, cudaMemsetAsync(s->d_vel.p + slot, 0, sizeof(float2), s->stream));
+            CUDA_TRY(s, cudaMemsetAsync(s->d_prefvel.p + slot, 0, sizeof(float2), s->stream));
+            CUDA_TRY(s, cudaMemsetAsync(s->d_force.p + slot, 0, sizeof(float2), s->stream));
+            CUDA_TRY(s, cudaMemsetAsync(s->d_attraction.p + slot, 0, sizeof(float2), s->stream));
+            CUDA_TRY(s, cudaMemsetAsync(s->d_replan_pending.p + slot, 0, 1, s->stream));
+        }
+    }
+    // path pool tail + touched headers
+    if (s->h_path_pool.size() > s->pool_uploaded) {
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_path_pool.p + s->pool_uploaded, s->h_path_pool.data() + s->pool_uploaded,
+                                    sizeof(float2) * (s->h_path_pool.size() - s->pool_uploaded), cudaMemcpyHostToDevice, s->stream));
+        s->pool_uploaded = s->h_path_pool.size();
+    }
+    if (contiguous && n > 0) {
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p + first, s->h_path_hdr.data() + first, sizeof(int2) * n, cudaMemcpyHostToDevice, s->stream));
+    } else {
+        for (int i = 0; i < n; i++)
+            CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p + slots[i], &s->h_path_hdr[slots[i]], sizeof(int2), cudaMemcpyHostToDevice, s->stream));
+    }
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    return ECMGPU_OK;
+}
+
+int ecmgpu_spawn(ecmgpu_sim* s, int slot, float x, float y, float radius, float speed, const float* path_xy, int n_points) {
+    const int off[2] = {0, n_points};
+    const float pos[2] = {x, y};
+    return ecmgpu_bulk_load(s, 1, &slot, pos, &radius, &speed, off, path_xy);
+}
+
+int ecmgpu_set_path(ecmgpu_sim* s, int slot, const float* path_xy, int n_points) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (slot < 0 || slot >= s->n_slots || !path_xy) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_path: bad arguments");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    int rc = upload_path(s, slot, path_xy, n_points);
+    if (rc) return rc;
+    const int2 h = s->h_path_hdr[slot];
+    const unsigned char zero = 0;
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_path_pool.p + h.x, s->h_path_pool.data() + h.x, sizeof(float2) * h.y, cudaMemcpyHostToDevice, s->stream));
+    s->pool_uploaded = std::max(s->pool_uploaded, (size_t)(h.x + h.y));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p + slot, &s->h_path_hdr[slot], sizeof(int2), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_replan_pending.p + slot, &zero, 1, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    return ECMGPU_OK;
+}
+
+int ecmgpu_destroy_agent(ecmgpu_sim* s, int slot) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (slot < 0 || slot >= s->prm.max_agents) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_destroy_agent: bad slot");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    CUDA_TRY(s, cudaMemsetAsync(s->d_active.p + slot, 0, 1, s->stream));
+    return ECMGPU_OK;
+}
+
+int ecmgpu_update(ecmgpu_sim* s) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    if (s->n_slots == 0) { s->ticks++; return ECMGPU_OK; }
+    int rc = ensure_ready(s);
+    if (rc) return rc;
+    TickView t = make_view(s);
+    if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[0], s->stream));
+    rc = enqueue_grid_build(s, t);
+    if (rc) return rc;
+    if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[1], s->stream));
+    const int nb = div_up(s->n_slots, 128);
+    k_attract<<<nb, 128, 0, s->stream>>>(t);
+    if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
+    k_orca<<<nb, 128, 0, s->stream>>>(t);
+    k_fallback<<<148, 128, 0, s->stream>>>(t, 0);
+    if (s->profiling) { CUDA_TRY(s, cudaEventRecord(s->ev[3], s->stream)); s->ev_valid = true; }
+    s->launches += 3;
+    s->ticks++;
+    CUDA_TRY(s, cudaGetLastError());
+    return ECMGPU_OK;
+}
+
+int ecmgpu_sync(ecmgpu_sim* s) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    return ECMGPU_OK;
+}
+
+int ecmgpu_poll_events(ecmgpu_sim* s, int* replan_slots, int replan_cap, int* n_replans, int* destroyed_slots, int destroyed_cap,
+                       int* n_destroyed) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    unsigned long long c[2] = {0, 0};
+    CUDA_TRY(s, cudaMemcpyAsync(c, s->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    const int nr = (int)c[C_REPLAN_N], nd = (int)c[C_DESTROYED_N];
+    if (n_replans) *n_replans = nr;
+    if (n_destroyed) *n_destroyed = nd;
+    if (replan_slots && nr > 0) {
+        if (replan_cap < nr) return fail(s, ECMGPU_ERR_CAPACITY, "ecmgpu_poll_events: replan buffer too small");
+        CUDA_TRY(s, cudaMemcpyAsync(replan_slots, s->d_ev_replan.p, sizeof(int) * nr, cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (destroyed_slots && nd > 0) {
+        if (destroyed_cap < nd) return fail(s, ECMGPU_ERR_CAPACITY, "ecmgpu_poll_events: destroyed buffer too small");
+        CUDA_TRY(s, cudaMemcpyAsync(destroyed_slots, s->d_ev_destroyed.p, sizeof(int) * nd, cudaMemcpyDeviceToHost, s->stream));
+    }
+    // drain only what was handed out
+    if ((replan_slots || replan_cap == 0) && (destroyed_slots || destroyed_cap == 0) && (replan_slots || destroyed_slots)) {
+        if (replan_slots) CUDA_TRY(s, cudaMemsetAsync(s->d_counters.p + C_REPLAN_N, 0, sizeof(unsigned long long), s->stream));
+        if (destroyed_slots) CUDA_TRY(s, cudaMemsetAsync(s->d_counters.p + C_DESTROYED_N, 0, sizeof(unsigned long long), s->stream));
+    }
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    // event order is arrival order of the atomics; report ascending slots like the reference's loops
+    if (replan_slots && nr > 1) std::sort(replan_slots, replan_slots + nr);
+    if (destroyed_slots && nd > 1) std::sort(destroyed_slots, destroyed_slots + nd);
+    return ECMGPU_OK;
+}
+
+static int xfer(ecmgpu_sim* s, int which, void* host, int first, int count, bool to_host, bool wait) {
+    int rc = check_range(s, which, first, count);
+    if (rc) return rc;
+    if (!host) return fail(s, ECMGPU_ERR_INVALID, "null host buffer");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    const size_t es = elem_size(which);
+    char* dev = (char*)dev_array(s, which) + es * (size_t)first;
+    if (to_host) CUDA_TRY(s, cudaMemcpyAsync(host, dev, es * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
+    else CUDA_TRY(s, cudaMemcpyAsync(dev, host, es * (size_t)count, cudaMemcpyHostToDevice, s->stream));
+    if (wait) CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    if (!to_host && (which == ECMGPU_RADIUS || which == ECMGPU_SPEED)) s->bins_dirty = true;  // ranges may have grown
+    if (!to_host) s->n_slots = std::max(s->n_slots, which == ECMGPU_ACTIVE ? first + count : s->n_slots);
+    return ECMGPU_OK;
+}
+int ecmgpu_read(ecmgpu_sim* s, int which, void* dst, int first, int count) { return xfer(s, which, dst, first, count, true, true); }
+int ecmgpu_write(ecmgpu_sim* s, int which, const void* src, int first, int count) { return xfer(s, which, (void*)src, first, count, false, true); }
+int ecmgpu_read_async(ecmgpu_sim* s, int which, void* dst, int first, int count) { return xfer(s, which, dst, first, count, true, false); }
+int ecmgpu_write_async(ecmgpu_sim* s, int which, const void* src, int first, int count) { return xfer(s, which, (void*)src, first, count, false, false); }
+
+void* ecmgpu_alloc_pinned(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void ecmgpu_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+int ecmgpu_locate(ecmgpu_sim* s, int n, const float* xy, int* out_cell) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (n < 0 || !xy || !out_cell) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_locate: bad arguments");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    if (!s->have_ecm) return fail(s, ECMGPU_ERR_INVALID, "no ECM: call ecmgpu_set_ecm first");
+    if (s->bins_dirty) { int rc = build_bins(s); if (rc) return rc; }
+    if (n == 0) return ECMGPU_OK;
+    DevBuf<float2> dxy; DevBuf<int> dout;
+    CUDA_TRY(s, dxy.alloc(n)); CUDA_TRY(s, dout.alloc(n));
+    TickView t = make_view(s);
+    CUDA_TRY(s, cudaMemcpyAsync(dxy.p, xy, sizeof(float2) * n, cudaMemcpyHostToDevice, s->stream));
+    k_locate<<<div_up(n, 128), 128, 0, s->stream>>>(t.ecm, t.bins, n, dxy.p, dout.p);
+    s->launches++;
+    CUDA_TRY(s, cudaMemcpyAsync(out_cell, dout.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    dxy.free(); dout.free();
+    return ECMGPU_OK;
+}
+
+int ecmgpu_retract(ecmgpu_sim* s, int n, const float* xy, uint8_t* out_ok, float* out_xy, int* out_edge) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (n < 0 || !xy || !out_ok || !out_xy || !out_edge) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_retract: bad arguments");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    if (!s->have_ecm) return fail(s, ECMGPU_ERR_INVALID, "no ECM: call ecmgpu_set_ecm first");
+    if (s->bins_dirty) { int rc = build_bins(s); if (rc) return rc; }
+    if (n == 0) return ECMGPU_OK;
+    DevBuf<float2> dxy, dout; DevBuf<int> dedge; DevBuf<unsigned char> dok;
+    CUDA_TRY(s, dxy.alloc(n)); CUDA_TRY(s, dout.alloc(n)); CUDA_TRY(s, dedge.alloc(n)); CUDA_TRY(s, dok.alloc(n));
+    TickView t = make_view(s);
+    CUDA_TRY(s, cudaMemcpyAsync(dxy.p, xy, sizeof(float2) * n, cudaMemcpyHostToDevice, s->stream));
+    k_retract<<<div_up(n, 128), 128, 0, s->stream>>>(t.ecm, t.bins, n, dxy.p, dok.p, dout.p, dedge.p);
+    s->launches++;
+    CUDA_TRY(s, cudaMemcpyAsync(out_ok, dok.p, n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(out_xy, dout.p, sizeof(float2) * n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(out_edge, dedge.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    dxy.free(); dout.free(); dedge.free(); dok.free();
+    return ECMGPU_OK;
+}
+
+int ecmgpu_find_neighbors(ecmgpu_sim* s, int count, int* out_ids5, int* out_counts) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (count < 0 || count > s->prm.max_agents || !out_ids5 || !out_counts) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_find_neighbors: bad arguments");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    if (s->n_slots > 0) {
+        int rc = ensure_ready(s);
+        if (rc) return rc;
+        TickView t = make_view(s);
+        rc = enqueue_grid_build(s, t);
+        if (rc) return rc;
+        CUDA_TRY(s, cudaMemsetAsync(s->d_nbr.p, 0xff, sizeof(int) * 5 * (size_t)s->n_slots, s->stream));
+        CUDA_TRY(s, cudaMemsetAsync(s->d_nbr_cnt.p, 0xff, sizeof(int) * (size_t)s->n_slots, s->stream));
+        k_knn_query<<<div_up(s->n_slots, 128), 128, 0, s->stream>>>(t);
+        k_fallback<<<148, 128, 0, s->stream>>>(t, 1);
+        s->launches += 2;
+        CUDA_TRY(s, cudaGetLastError());
+    }
+    const int m = std::min(count, s->n_slots);
+    if (m > 0) {
+        CUDA_TRY(s, cudaMemcpyAsync(out_ids5, s->d_nbr.p, sizeof(int) * 5 * (size_t)m, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(out_counts, s->d_nbr_cnt.p, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    for (int i = m; i < count; i++) { out_counts[i] = -1; for (int j = 0; j < 5; j++) out_ids5[5 * i + j] = -1; }
+    return ECMGPU_OK;
+}
+
+int ecmgpu_find_obstacles(ecmgpu_sim* s, int slot, int* out_ids, int cap, int* out_n) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (slot < 0 || slot >= s->n_slots || cap < 0 || !out_n || (cap > 0 && !out_ids)) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_find_obstacles: bad arguments");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    int rc = ensure_ready(s);
+    if (rc) return rc;
+    float2 pos; float rad, spd;
+    CUDA_TRY(s, cudaMemcpyAsync(&pos, s->d_pos.p + slot, sizeof(float2), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(&rad, s->d_radius.p + slot, sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(&spd, s->d_speed.p + slot, sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    const float range = kLookAhead * spd + rad;
+    DevBuf<int> dout, dn;
+    CUDA_TRY(s, dout.alloc(std::max(cap, 1))); CUDA_TRY(s, dn.alloc(1));
+    TickView t = make_view(s);
+    k_find_obstacles<<<1, 32, 0, s->stream>>>(t.obst, t.bins, pos, range * range, dout.p, cap, dn.p);
+    s->launches++;
+    CUDA_TRY(s, cudaMemcpyAsync(out_n, dn.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    const int m = std::min(*out_n, cap);
+    if (m > 0) CUDA_TRY(s, cudaMemcpy(out_ids, dout.p, sizeof(int) * m, cudaMemcpyDeviceToHost));
+    dout.free(); dn.free();
+    return ECMGPU_OK;
+}
+
+int ecmgpu_get_stats(ecmgpu_sim* s, ecmgpu_stats* o) {
+    if (!s || !o) return ECMGPU_ERR_INVALID;
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    unsigned long long c[C_COUNT];
+    CUDA_TRY(s, cudaMemcpyAsync(c, s->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
+    int n_sorted = 0;
+    if (!s->grid_dirty && s->d_cell_count.p && s->ticks > 0)
+        CUDA_TRY(s, cudaMemcpyAsync(&n_sorted, s->d_cell_count.p + (size_t)s->gw * s->gh, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    memset(o, 0, sizeof(*o));
+    o->n_slots = s->n_slots;
+    o->n_active = n_sorted;  // agents active at the start of the last tick
+    o->grid_w = s->gw; o->grid_h = s->gh; o->neighbor_cell = s->cell;
+    o->bins_w = s->bins_w; o->bins_h = s->bins_h; o->static_bin = s->static_bin;
+    o->max_cell_list = s->max_cell_list; o->max_obstacle_list = s->max_obst_list;
+    o->ticks = s->ticks; o->kernel_launches = s->launches;
+    o->knn_fallbacks = c[C_TOTAL_FALLBACK]; o->obstacle_overflows = c[C_TOTAL_OBST_OVF]; o->lp3d_runs = c[C_TOTAL_LP3D];
+    o->location_failures = c[C_TOTAL_LOCFAIL]; o->replans = c[C_TOTAL_REPLAN]; o->halo_misses = c[C_TOTAL_HALO_MISS];
+    return ECMGPU_OK;
+}
+
+int ecmgpu_set_profiling(ecmgpu_sim* s, int on) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    s->profiling = on != 0;
+    s->ev_valid = false;
+    return ECMGPU_OK;
+}
+
+int ecmgpu_last_tick_ms(ecmgpu_sim* s, float out_ms[4]) {
+    if (!s || !out_ms) return ECMGPU_ERR_INVALID;
+    if (!s->profiling || !s->ev_valid) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_last_tick_ms: enable profiling and run a tick first");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    CUDA_TRY(s, cudaEventSynchronize(s->ev[3]));
+    CUDA_TRY(s, cudaEventElapsedTime(&out_ms[0], s->ev[0], s->ev[3]));
+    CUDA_TRY(s, cudaEventElapsedTime(&out_ms[1], s->ev[0], s->ev[1]));
+    CUDA_TRY(s, cudaEventElapsedTime(&out_ms[2], s->ev[1], s->ev[2]));
+    CUDA_TRY(s, cudaEventElapsedTime(&out_ms[3], s->ev[2], s->ev[3]));
+    return ECMGPU_OK;
+}
+
+int ecmgpu_mark(ecmgpu_sim* s, int which) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (which < 0 || which >= 8) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_mark: mark index out of range");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    CUDA_TRY(s, cudaEventRecord(s->marks[which], s->stream));
+    return ECMGPU_OK;
+}
+
+int ecmgpu_mark_elapsed_ms(ecmgpu_sim* s, int a, int b, float* out_ms) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (a < 0 || a >= 8 || b < 0 || b >= 8 || !out_ms) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_mark_elapsed_ms: bad arguments");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    CUDA_TRY(s, cudaEventSynchronize(s->marks[b]));
+    CUDA_TRY(s, cudaEventElapsedTime(out_ms, s->marks[a], s->marks[b]));
+    return ECMGPU_OK;
+}
+
+void* ecmgpu_stream(ecmgpu_sim* s) { return s ? (void*)s->stream : nullptr; }
+
+int ecmgpu_comm_unique_id(uint8_t out_id[128]) {
+    (void)out_id;
+    return ECMGPU_ERR_COMM;
+}
+int ecmgpu_comm_init(ecmgpu_sim* s, const uint8_t id[128], int rank, int n_ranks) {
+    (void)id; (void)rank; (void)n_ranks;
+    return fail(s, ECMGPU_ERR_COMM, "multi-GPU strips not built into this library yet");
+}
+int ecmgpu_comm_set_strips(ecmgpu_sim* s, const float* bounds, float halo_width) {
+    (void)bounds; (void)halo_width;
+    return fail(s, ECMGPU_ERR_COMM, "multi-GPU strips not built into this library yet");
+}
+
+}  // extern "C"

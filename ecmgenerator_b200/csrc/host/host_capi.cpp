@@ -3,9 +3,16 @@
 
 #include "flat_world.h"
 #include "lattice_world.h"
+#include "planner.h"
 
 struct ecmhost_world {
     ecmb200::FlatWorld w;
+};
+
+struct ecmhost_paths {
+    int n = 0, ok = 0;
+    std::vector<int> off;
+    std::vector<float> xy;
 };
 
 extern "C" {
@@ -60,6 +67,28 @@ int ecmhost_world_get_view(const ecmhost_world* h, ecmhost_world_view* o) {
     o->obst_prev = w.obst.prev.data();
     o->obst_convex = w.obst.convex.data();
     o->obst_first = w.obst.first.data();
+    return 0;
+}
+
+ecmhost_paths* ecmhost_plan_paths(const ecmhost_world* w, int n, const float* start_xy, const float* goal_xy,
+                                  const float* clearance, int threads) {
+    if (!w || n < 0 || (n > 0 && (!start_xy || !goal_xy || !clearance))) return nullptr;
+    auto* p = new ecmhost_paths();
+    p->n = n;
+    p->ok = ecmb200::PlanPaths(w->w, n, start_xy, goal_xy, clearance, threads, p->off, p->xy);
+    return p;
+}
+int ecmhost_paths_count(const ecmhost_paths* p) { return p ? p->n : 0; }
+int ecmhost_paths_succeeded(const ecmhost_paths* p) { return p ? p->ok : 0; }
+const int* ecmhost_paths_offsets(const ecmhost_paths* p) { return p ? p->off.data() : nullptr; }
+const float* ecmhost_paths_xy(const ecmhost_paths* p) { return p ? p->xy.data() : nullptr; }
+void ecmhost_paths_free(ecmhost_paths* p) { delete p; }
+
+int ecmhost_find_cells(const ecmhost_world* w, int n, const float* xy, int* out_cell) {
+    if (!w || n < 0 || (n > 0 && (!xy || !out_cell))) return -1;
+    ecmb200::CellLocator loc;
+    loc.Build(w->w);
+    for (int i = 0; i < n; i++) out_cell[i] = loc.FindCell(w->w, xy[2 * i], xy[2 * i + 1]);
     return 0;
 }
 

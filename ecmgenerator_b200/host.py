@@ -56,6 +56,16 @@ def lib() -> C.CDLL:
         L.ecmhost_world_from_arrays.argtypes = [C.POINTER(_WorldView)]
         L.ecmhost_world_free.argtypes = [C.c_void_p]
         L.ecmhost_world_get_view.argtypes = [C.c_void_p, C.POINTER(_WorldView)]
+        L.ecmhost_plan_paths.restype = C.c_void_p
+        L.ecmhost_plan_paths.argtypes = [C.c_void_p, C.c_int, c_float_p, c_float_p, c_float_p, C.c_int]
+        L.ecmhost_paths_count.argtypes = [C.c_void_p]
+        L.ecmhost_paths_succeeded.argtypes = [C.c_void_p]
+        L.ecmhost_paths_offsets.restype = c_int_p
+        L.ecmhost_paths_offsets.argtypes = [C.c_void_p]
+        L.ecmhost_paths_xy.restype = c_float_p
+        L.ecmhost_paths_xy.argtypes = [C.c_void_p]
+        L.ecmhost_paths_free.argtypes = [C.c_void_p]
+        L.ecmhost_find_cells.argtypes = [C.c_void_p, C.c_int, c_float_p, c_int_p]
         _lib = L
     return _lib
 
@@ -155,3 +165,59 @@ def lattice_world(blocks_x, blocks_y, street_width: float, x0: float = 0.0, y0: 
     finally:
         L.ecmhost_world_free(h)
     return w
+
+
+class _WorldHandle:
+    """A World re-materialised inside libecmhost (ecmhost_world_from_arrays)."""
+
+    def __init__(self, w: World):
+        self.L = lib()
+        self._keep = [np.ascontiguousarray(a) for a in (w.vert_xy, w.vert_clear, w.vert_he, w.edge_v, w.edge_cl, w.he_next,
+                                                        w.obst_xy, w.obst_next, w.obst_prev, w.obst_convex, w.obst_first)]
+        k = self._keep
+        v = _WorldView()
+        for i in range(4):
+            v.bbox[i] = float(w.bbox[i])
+        v.n_vertices, v.n_edges, v.n_obst_vertices, v.n_obstacles = w.n_vertices, w.n_edges, w.n_obst_vertices, w.n_obstacles
+        v.vert_xy, v.vert_clear, v.vert_he = fptr(k[0]), fptr(k[1]), iptr(k[2])
+        v.edge_v, v.edge_cl, v.he_next = iptr(k[3]), fptr(k[4]), iptr(k[5])
+        v.obst_xy, v.obst_next, v.obst_prev, v.obst_convex, v.obst_first = fptr(k[6]), iptr(k[7]), iptr(k[8]), u8ptr(k[9]), iptr(k[10])
+        self.h = self.L.ecmhost_world_from_arrays(C.byref(v))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.ecmhost_world_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def plan_paths(w: World, start, goal, clearance, threads: int = 0):
+    """Batched ECMPathPlanner::FindPath.  Returns (path_off[n+1], path_xy[total,2], n_ok)."""
+    start = np.ascontiguousarray(start, np.float32)
+    goal = np.ascontiguousarray(goal, np.float32)
+    clearance = np.ascontiguousarray(clearance, np.float32)
+    n = len(start)
+    wh = _WorldHandle(w)
+    L = lib()
+    p = L.ecmhost_plan_paths(wh.h, n, fptr(start), fptr(goal), fptr(clearance), int(threads))
+    if not p:
+        raise RuntimeError("ecmhost_plan_paths failed")
+    try:
+        off = np.ctypeslib.as_array(L.ecmhost_paths_offsets(p), shape=(n + 1,)).astype(np.int32, copy=True)
+        total = int(off[-1])
+        xy = (np.ctypeslib.as_array(L.ecmhost_paths_xy(p), shape=(2 * total,)).astype(np.float32, copy=True).reshape(total, 2)
+              if total > 0 else np.zeros((0, 2), np.float32))
+        ok = L.ecmhost_paths_succeeded(p)
+    finally:
+        L.ecmhost_paths_free(p)
+    return off, xy, ok
+
+
+def find_cells(w: World, xy):
+    xy = np.ascontiguousarray(xy, np.float32)
+    out = np.zeros(len(xy), np.int32)
+    wh = _WorldHandle(w)
+    lib().ecmhost_find_cells(wh.h, len(xy), fptr(xy), iptr(out))
+    return out

@@ -137,8 +137,11 @@ def world_c2(seed: int = 2) -> World:
 
 
 def world_c3() -> World:
-    """C3: 45 x 45 = 2025 blocks of 40 x 40 with 20-wide streets (~2.7 km square)."""
-    return lattice_world(np.full(45, 40.0), np.full(45, 40.0), 20.0, 0.0, 0.0)
+    """C3: 45 x 45 = 2025 blocks of 40 x 40 with 20-wide streets (2.68 km square, centred on the origin).
+
+    Worlds must keep |coordinate| < 2048: beyond that half a float ulp exceeds the reference's
+    EPSILON (1e-4), Point::Approximate(p, p) turns false and its funnel never terminates."""
+    return lattice_world(np.full(45, 40.0), np.full(45, 40.0), 20.0, -1340.0, -1340.0)
 
 
 def world_c4(seed: int = 4) -> World:
@@ -146,12 +149,13 @@ def world_c4(seed: int = 4) -> World:
     rng = np.random.default_rng(seed)
     bx = np.concatenate([_blocks(50, 8.0, 12.0, rng), _blocks(40, 12.0, 18.0, rng)])
     by = np.concatenate([_blocks(45, 10.0, 14.0, rng), _blocks(45, 10.0, 16.0, rng)])
-    return lattice_world(bx, by, 10.0, 0.0, 0.0)
+    w = float(bx.sum() + 10.0 * (len(bx) - 1)), float(by.sum() + 10.0 * (len(by) - 1))
+    return lattice_world(bx, by, 10.0, -round(w[0] / 2), -round(w[1] / 2))
 
 
 def world_c5() -> World:
     """C5: bidirectional corridor stress: long 10-wide streets between 100-long blocks."""
-    return lattice_world(np.full(12, 100.0), np.full(24, 12.0), 10.0, 0.0, 0.0)
+    return lattice_world(np.full(12, 100.0), np.full(24, 12.0), 10.0, -655.0, -259.0)
 
 
 def crowd_c1(w: World, n: int = 5_000, seed: int = 1) -> Crowd:

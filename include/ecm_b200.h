@@ -1,0 +1,173 @@
+/* ecm_b200.h - C ABI of the B200 (sm_100a) implementation of ECMGenerator's per-tick agent update.
+ *
+ * The reference has no plugin/FFI mechanism; the seam this library sits behind is the C++ class
+ * ECM::Simulation::Simulator (/root/reference/ECMAgentSimulator/Simulator.h:59-188).  A host-side
+ * drop-in `Simulator` (ecmgenerator_b200/csrc/host/Simulator.h) keeps that class's public
+ * signatures and forwards to the entry points below; INTEGRATION.md shows the binding.
+ *
+ * Conventions: plain C types, caller-owned host buffers, int status codes (0 = ECMGPU_OK),
+ * one handle = one logical simulator on one CUDA device, calls on a handle serialised by the
+ * caller.  Work is enqueued on the handle's CUDA stream; ecmgpu_update() returns without waiting,
+ * ecmgpu_read()/ecmgpu_poll_events()/ecmgpu_sync() wait.  There is NO CPU fallback: without a
+ * usable CUDA device every compute entry point fails with ECMGPU_ERR_CUDA.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to /root/reference).
+ */
+#ifndef ECM_B200_H
+#define ECM_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ecmgpu_sim ecmgpu_sim;
+
+enum {
+    ECMGPU_OK = 0,
+    ECMGPU_ERR_INVALID = 1,   /* bad argument / call order */
+    ECMGPU_ERR_CUDA = 2,      /* CUDA runtime error or no device */
+    ECMGPU_ERR_CAPACITY = 3,  /* slot, path pool or event capacity exceeded */
+    ECMGPU_ERR_COMM = 4       /* NCCL error */
+};
+
+/* Hard constants of the reference are NOT parameters: k = 5 neighbours (Simulator.cpp:55),
+ * look-ahead 10 s (ORCA.h:102-103), mass 0.8 (Simulator.cpp:622), arrival radius 20 / delete
+ * distance 2 (Simulator.cpp:542-543), EPSILON 1e-4 (Configuration.h:14). */
+typedef struct ecmgpu_params {
+    int   device;            /* CUDA device ordinal */
+    int   max_agents;        /* Simulator ctor `maxAgents`   (Simulator.h:63) */
+    float step;              /* Simulator ctor `simStepTime` (Simulator.h:63); Update(dt) ignores dt (Simulator.cpp:314) */
+    float neighbor_cell;     /* neighbour-grid cell edge in world units; <= 0: chosen from crowd density at load */
+    float static_bin;        /* point-location / obstacle bin edge; <= 0: chosen from the ECM */
+    float max_obstacle_range;/* upper bound of 10*speed + radius over all agents (ORCA.cpp:27); <= 0: tracked from loaded agents */
+    int   path_pool_points;  /* capacity of the path polyline pool in points; <= 0: 16 * max_agents */
+    int   record_neighbors;  /* 1: keep each tick's neighbour ids/counts readable (parity); 0: skip the 24 B/agent write */
+} ecmgpu_params;
+
+/* which-array selectors for ecmgpu_read / ecmgpu_write.  Element layout per slot in brackets. */
+enum {
+    ECMGPU_POS = 0,          /* [2 f32] Simulator::GetPositionData           (Simulator.h:116) */
+    ECMGPU_VEL = 1,          /* [2 f32] Simulator::GetVelocityData           (Simulator.h:117) */
+    ECMGPU_PREFVEL = 2,      /* [2 f32] Simulator::GetPreferredVelocityData  (Simulator.h:118) */
+    ECMGPU_ATTRACTION = 3,   /* [2 f32] Simulator::GetAttractionPointData    (Simulator.h:121) */
+    ECMGPU_FORCE = 4,        /* [2 f32] m_Forces (no public getter)          (Simulator.h:184) */
+    ECMGPU_RADIUS = 5,       /* [1 f32] Simulator::GetClearanceData          (Simulator.h:120) */
+    ECMGPU_SPEED = 6,        /* [1 f32] m_PreferredSpeed                     (Simulator.h:186) */
+    ECMGPU_ACTIVE = 7,       /* [1 u8 ] Simulator::GetActiveFlags            (Simulator.h:123) */
+    ECMGPU_CELL = 8,         /* [1 i32] ECM cell located this tick (2*edge+side), -1 none, -2 not evaluated (ECM.cpp:220-223) */
+    ECMGPU_NEIGHBORS = 9,    /* [5 i32] neighbour slot ids of this tick, (sqDist, slot) ascending, -1 padding (KDTree.cpp:85-96) */
+    ECMGPU_NEIGHBOR_COUNT = 10, /* [1 i32] */
+    ECMGPU_STATUS = 11       /* [1 u32] ECMGPU_ST_* bits of the last tick */
+};
+
+/* per-agent status bits (ECMGPU_STATUS) */
+enum {
+    ECMGPU_ST_NO_CELL = 1u,        /* "Couldn't locate point in the ECM graph!" (ECMCellCollection.cpp:88) */
+    ECMGPU_ST_REPLAN = 2u,         /* IRM failed -> UpdatePath requested      (Simulator.cpp:581-587) */
+    ECMGPU_ST_ARRIVING = 4u,       /* within the arrival radius                (Simulator.cpp:557-562) */
+    ECMGPU_ST_DESTROYED = 8u,      /* destroyed this tick                      (Simulator.cpp:564-566) */
+    ECMGPU_ST_OBST_OVERFLOW = 16u, /* more obstacle neighbours than the device cap (excess dropped) */
+    ECMGPU_ST_KNN_FALLBACK = 32u,  /* neighbour search left the ring budget; resolved by the exhaustive pass */
+    ECMGPU_ST_LP3D = 64u,          /* RandomizedLP failed, RandomizedLP3D ran  (ORCA.cpp:51-54) */
+    ECMGPU_ST_HALO_MISS = 128u     /* multi-GPU: search reached beyond the received halo */
+};
+
+/* -- lifetime ---------------------------------------------------------------------------------
+ * Simulator::Simulator + Initialize (Simulator.h:63-74, Simulator.cpp:21-60) / ~Simulator. */
+int  ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out);
+void ecmgpu_destroy(ecmgpu_sim* sim);
+/* Last error text of this handle (or of the failed ecmgpu_create when sim == NULL). */
+const char* ecmgpu_last_error(const ecmgpu_sim* sim);
+
+/* -- static world -----------------------------------------------------------------------------
+ * Flattened ECMGraph (ECM.h:20-116): vertices, edges v0->v1 with the four closest obstacle points
+ * L0 R0 L1 R1 (edge_cl: 8 floats per edge; layout in csrc/host/flat_world.h).  Cell c = 2*edge+side
+ * as built by ECMCellCollection::Construct (ECMCellCollection.cpp:10-49).  bbox = walkable area. */
+int ecmgpu_set_ecm(ecmgpu_sim* sim, const float bbox[4], int n_vertices, const float* vert_xy, const float* vert_clear,
+                   int n_edges, const int* edge_v, const float* edge_cl);
+/* Environment::GetObstacles() flattened in (obstacle, vertex) order (Environment.h:55,
+ * ECMDataTypes.h:160-166): segment i runs xy[i] -> xy[next[i]]. */
+int ecmgpu_set_obstacles(ecmgpu_sim* sim, int n, const float* xy, const int* next, const int* prev, const uint8_t* convex);
+
+/* -- agents -----------------------------------------------------------------------------------
+ * The host owns slot allocation (free list, Simulator.h:66-69); these write one slot's components.
+ * Simulator::SpawnAgent after ValidSpawnLocation and path planning (Simulator.cpp:175-199). */
+int ecmgpu_spawn(ecmgpu_sim* sim, int slot, float x, float y, float radius, float speed, const float* path_xy, int n_points);
+/* n agents at once; slots == NULL means slots 0..n-1.  path_off[n+1] indexes points in path_xy. */
+int ecmgpu_bulk_load(ecmgpu_sim* sim, int n, const int* slots, const float* pos_xy, const float* radius, const float* speed,
+                     const int* path_off, const float* path_xy);
+/* Simulator::UpdatePath's result (Simulator.cpp:97-124): replaces the polyline, clears a pending replan. */
+int ecmgpu_set_path(ecmgpu_sim* sim, int slot, const float* path_xy, int n_points);
+/* Simulator::DestroyAgent (Simulator.cpp:202-208): clears the active flag. */
+int ecmgpu_destroy_agent(ecmgpu_sim* sim, int slot);
+
+/* -- the hot path -----------------------------------------------------------------------------
+ * Simulator::Update (Simulator.cpp:314-323) minus UpdateSpawnAreas (host): neighbour structure,
+ * attraction points, preferred velocities, ORCA, velocity and position integration.  Asynchronous. */
+int ecmgpu_update(ecmgpu_sim* sim);
+int ecmgpu_sync(ecmgpu_sim* sim);
+/* Drains the device event queues (waits for enqueued ticks): agents that asked for a replan
+ * (Simulator.cpp:581-587; they stay flagged until ecmgpu_set_path) and agents destroyed on arrival
+ * (Simulator.cpp:564-566) since the last poll.  Either array may be NULL with cap 0 to only count. */
+int ecmgpu_poll_events(ecmgpu_sim* sim, int* replan_slots, int replan_cap, int* n_replans, int* destroyed_slots,
+                       int destroyed_cap, int* n_destroyed);
+
+/* -- state transfer ---------------------------------------------------------------------------
+ * Component arrays indexed by slot, [first, first+count).  read waits for enqueued work. */
+int ecmgpu_read(ecmgpu_sim* sim, int which, void* dst, int first, int count);
+int ecmgpu_write(ecmgpu_sim* sim, int which, const void* src, int first, int count);
+/* Asynchronous variants on the handle's stream for pinned host memory (end-to-end pipelines). */
+int ecmgpu_read_async(ecmgpu_sim* sim, int which, void* dst_pinned, int first, int count);
+int ecmgpu_write_async(ecmgpu_sim* sim, int which, const void* src_pinned, int first, int count);
+/* cudaHostAlloc / cudaFreeHost pass-through so non-CUDA hosts can get pinned staging memory. */
+void* ecmgpu_alloc_pinned(uint64_t bytes);
+void  ecmgpu_free_pinned(void* p);
+
+/* -- queries (Simulator.h:106-108, ECM.h:127-128) on the CURRENT state ---------------------------
+ * ECM::GetECMCell for arbitrary points. */
+int ecmgpu_locate(ecmgpu_sim* sim, int n, const float* xy, int* out_cell);
+/* ECM::RetractPoint for arbitrary points. */
+int ecmgpu_retract(ecmgpu_sim* sim, int n, const float* xy, uint8_t* out_ok, float* out_xy, int* out_edge);
+/* Simulator::FindNNearestNeighbors(k=5) for every active slot < count on the current positions
+ * (exact-kNN contract); inactive slots get count -1. */
+int ecmgpu_find_neighbors(ecmgpu_sim* sim, int count, int* out_ids5, int* out_counts);
+/* Simulator::FindNearestObstacles with ORCA's range for one slot; returns the number found. */
+int ecmgpu_find_obstacles(ecmgpu_sim* sim, int slot, int* out_ids, int cap, int* out_n);
+
+/* -- introspection ----------------------------------------------------------------------------*/
+typedef struct ecmgpu_stats {
+    int   n_slots;            /* highest loaded slot + 1 (what the kernels iterate over) */
+    int   n_active;           /* active agents after the last completed tick */
+    int   grid_w, grid_h;     /* neighbour grid */
+    float neighbor_cell;
+    int   bins_w, bins_h;     /* static grid */
+    float static_bin;
+    int   max_cell_list, max_obstacle_list;
+    uint64_t ticks;           /* ticks enqueued so far */
+    uint64_t kernel_launches; /* kernels launched by this handle so far */
+    uint64_t knn_fallbacks, obstacle_overflows, lp3d_runs, location_failures, replans, halo_misses;
+} ecmgpu_stats;
+int ecmgpu_get_stats(ecmgpu_sim* sim, ecmgpu_stats* out);
+/* CUDA-event time of each phase of the LAST completed tick, milliseconds.
+ * phases: 0 whole tick, 1 grid build (count+scan+scatter), 2 attraction (locate+IRM+steer), 3 ORCA (kNN+obstacles+LP+integrate) */
+int ecmgpu_last_tick_ms(ecmgpu_sim* sim, float out_ms[4]);
+/* Enables per-phase event recording (adds 4 event records per tick). */
+int ecmgpu_set_profiling(ecmgpu_sim* sim, int on);
+/* Stream-ordered time marks (CUDA events on the handle's stream): record mark `which` (0..7) now;
+ * elapsed waits for mark b and returns the device time between marks a and b in milliseconds. */
+int ecmgpu_mark(ecmgpu_sim* sim, int which);
+int ecmgpu_mark_elapsed_ms(ecmgpu_sim* sim, int a, int b, float* out_ms);
+/* The stream work is enqueued on (a cudaStream_t), for callers that interleave their own CUDA work. */
+void* ecmgpu_stream(ecmgpu_sim* sim);
+
+/* -- multi-GPU strips (one process per GPU; see DESIGN.md "Multi-GPU") --------------------------
+ * nccl_unique_id: 128 bytes from ecmgpu_comm_unique_id() on rank 0, distributed by the caller. */
+int ecmgpu_comm_unique_id(uint8_t out_id[128]);
+int ecmgpu_comm_init(ecmgpu_sim* sim, const uint8_t nccl_unique_id[128], int rank, int n_ranks);
+/* Strip boundaries along x: n_ranks+1 ascending values; rank r owns [bounds[r], bounds[r+1]). */
+int ecmgpu_comm_set_strips(ecmgpu_sim* sim, const float* bounds, float halo_width);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECM_B200_H */

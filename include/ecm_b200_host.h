@@ -42,6 +42,20 @@ ecmhost_world* ecmhost_world_from_arrays(const ecmhost_world_view* view);
 void ecmhost_world_free(ecmhost_world* w);
 int ecmhost_world_get_view(const ecmhost_world* w, ecmhost_world_view* out);
 
+/* -- global path planning: ECMPathPlanner::FindPath (ECMGenerator/ECMPathPlanner.cpp:22-136) as
+ * Simulator::UpdatePath calls it (ECMAgentSimulator/Simulator.cpp:97-124), batched over `threads`
+ * host threads (0 = all).  A failed query yields a zero-length polyline. */
+typedef struct ecmhost_paths ecmhost_paths;
+ecmhost_paths* ecmhost_plan_paths(const ecmhost_world* w, int n, const float* start_xy, const float* goal_xy,
+                                  const float* clearance, int threads);
+int ecmhost_paths_count(const ecmhost_paths* p);        /* n */
+int ecmhost_paths_succeeded(const ecmhost_paths* p);    /* queries that produced a path */
+const int* ecmhost_paths_offsets(const ecmhost_paths* p); /* n+1 offsets in points */
+const float* ecmhost_paths_xy(const ecmhost_paths* p);  /* 2 * offsets[n] floats */
+void ecmhost_paths_free(ecmhost_paths* p);
+/* ECMGraph::FindCell (ECMGenerator/ECM.cpp:191-194) on the host, for n points. */
+int ecmhost_find_cells(const ecmhost_world* w, int n, const float* xy, int* out_cell);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,52 @@
+"""CPU: the C-ABI libraries load and export every symbol their headers declare; without a GPU the
+compute entry points fail loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from tests.conftest import ROOT, has_cuda
+
+
+def _declared(header, prefix):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(" + prefix + r"[a-z0-9_]+)\s*\(", text)))
+
+
+def test_gpu_library_exports_every_declared_symbol():
+    from ecmgenerator_b200 import gpu
+
+    names = _declared("ecm_b200.h", "ecmgpu_")
+    assert len(names) >= 25
+    L = C.CDLL(gpu.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert sorted(gpu.EXPORTS) == names, "python binding out of sync with include/ecm_b200.h"
+
+
+def test_host_library_exports_every_declared_symbol():
+    from ecmgenerator_b200 import host
+
+    names = _declared("ecm_b200_host.h", "ecmhost_")
+    L = host.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_param_struct_layout_matches_header():
+    from ecmgenerator_b200 import gpu
+
+    assert C.sizeof(gpu.Params) == 32
+    assert gpu.Stats.ticks.offset % 8 == 0
+
+
+@pytest.mark.skipif(has_cuda(), reason="only meaningful without a CUDA device")
+def test_no_cpu_fallback_without_gpu():
+    from ecmgenerator_b200 import gpu
+    from ecmgenerator_b200.host import lattice_world
+
+    w = lattice_world([20, 20], [20, 20], 6.0)
+    with pytest.raises(gpu.EcmGpuError, match="no CUDA device"):
+        gpu.GpuSim(w, 16, 1 / 60)

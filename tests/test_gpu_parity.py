@@ -1,0 +1,293 @@
+"""GPU (-m gpu): the CUDA path through the C ABI against the C oracle and the reference's golden
+vectors.  Bars (BASELINE.json north_star):
+  * neighbour lists and ECM cell ids bit-exact;
+  * new velocities within 1e-4 m/s absolute per step on identical input state;
+  * trajectory RMS divergence over 600 ticks reported (and bounded).
+"""
+import numpy as np
+import pytest
+
+from ecmgenerator_b200 import gpu
+from ecmgenerator_b200 import scenarios as S
+from ecmgenerator_b200.host import lattice_world
+from oracle.pyoracle import OracleSim
+from tests.util import GOLDEN, Golden, apply_events, assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+VEL_TOL = 1e-4  # m/s absolute per step (north_star)
+
+
+def _pair(g, **kw):
+    sim = gpu.GpuSim(g.world, g.n + 8, g.step, **kw)
+    sim.bulk_load(g.crowd.pos, g.crowd.radius, g.crowd.speed, g.path_off, g.path_xy)
+    ora = OracleSim(g.world, g.n + 8, g.step, "exact-knn")
+    ora.bulk_load(g.crowd.pos, g.crowd.radius, g.crowd.speed, g.path_off, g.path_xy)
+    return sim, ora
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_cells_and_retraction_match_reference_golden(name):
+    g = Golden(name)
+    sim = gpu.GpuSim(g.world, 8, g.step)
+    pts = g.z["probe/xy"]
+    assert np.array_equal(sim.query_cells(pts), g.z["probe/cell"])
+    ok, xy, edge = sim.retract(pts)
+    assert np.array_equal(ok, g.z["probe/retract_ok"])
+    good = ok > 0
+    assert np.array_equal(edge[good], g.z["probe/retract_edge"][good])
+    assert_bits_equal(xy[good], g.z["probe/retract_xy"][good], "retracted points")
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+@pytest.mark.parametrize("cell", [0.0, 0.7, 9.0])
+def test_neighbours_bit_exact_vs_reference_golden(name, cell):
+    """exact-knn golden = reference build with the exact KD-tree TU; any grid cell size must agree."""
+    g = Golden(name)
+    sim = gpu.GpuSim(g.world, g.n + 8, g.step, neighbor_cell=cell)
+    sim.bulk_load(g.crowd.pos, g.crowd.radius, g.crowd.speed, g.path_off, g.path_xy)
+    ids, cnt = sim.query_neighbors(g.n)
+    assert_bits_equal(ids, g.z["exact-knn/nbr0_ids"], "neighbour ids")
+    assert_bits_equal(cnt, g.z["exact-knn/nbr0_cnt"], "neighbour counts")
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_lockstep_velocities_within_tolerance(name):
+    """Every tick starts from the ORACLE's state on both sides (identical input state), then one
+    tick each: neighbours and cells bit-exact, velocities within 1e-4."""
+    g = Golden(name)
+    sim, ora = _pair(g)
+    n = g.n
+    worst = 0.0
+    exact_rows = 0
+    total_rows = 0
+    for t in range(g.ticks("exact-knn")):
+        st = ora.state(n)
+        sim.write(gpu.POS, st["pos"])
+        sim.write(gpu.VEL, st["vel"])
+        sim.write(gpu.ATTRACTION, st["attraction"])
+        sim.write(gpu.ACTIVE, st["active"])
+        ids_o, cnt_o = ora.query_neighbors(n)
+        cells_o = ora.query_cells(st["pos"])
+        rp_o, ds_o = ora.step(1)
+        rp_g, ds_g = sim.step(1)
+        a, b = sim.state(n), ora.state(n)
+        act = st["active"] > 0
+        assert np.array_equal(a["active"], b["active"]), f"active flags after tick {t}"
+        assert np.array_equal(rp_g, rp_o) and np.array_equal(ds_g, ds_o), f"events of tick {t}"
+        ids_g, cnt_g = sim.read(gpu.NEIGHBORS, 0, n), sim.read(gpu.NEIGHBOR_COUNT, 0, n)
+        alive = act & (b["active"] > 0)
+        assert np.array_equal(ids_g[alive], ids_o[alive]) and np.array_equal(cnt_g[alive], cnt_o[alive]), f"neighbours tick {t}"
+        cell_g = sim.read(gpu.CELL, 0, n)
+        evaluated = act & (cell_g != -2)
+        assert np.array_equal(cell_g[evaluated], cells_o[evaluated]), f"cells tick {t}"
+        assert_bits_equal(a["attraction"][act], b["attraction"][act], f"attraction tick {t}")
+        assert_bits_equal(a["prefvel"][alive], b["prefvel"][alive], f"prefvel tick {t}")
+        dv = np.abs(a["vel"][alive] - b["vel"][alive]).max()
+        worst = max(worst, float(dv))
+        assert dv <= VEL_TOL, f"tick {t}: max |dv| = {dv}"
+        exact_rows += int((a["vel"][alive].view(np.uint32) == b["vel"][alive].view(np.uint32)).all(axis=1).sum())
+        total_rows += int(alive.sum())
+        apply_events(ora, g.events_at("exact-knn", t))
+    print(f"{name}: worst |dv| {worst:.3e}; {exact_rows}/{total_rows} velocity rows bit-identical")
+    assert exact_rows / total_rows > 0.9
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_free_running_matches_reference_golden(name):
+    """No re-synchronisation: GPU trajectories vs the reference's own (exact-knn build) golden."""
+    g = Golden(name)
+    sim, _ = _pair(g)
+    n, T = g.n, g.ticks("exact-knn")
+    rms = []
+    for t in range(T):
+        sim.step(1)
+        pos = sim.read(gpu.POS, 0, n)
+        act = g.z["exact-knn/active"][t] > 0
+        assert np.array_equal(sim.read(gpu.ACTIVE, 0, n) > 0, act)
+        d = pos[act] - g.z["exact-knn/pos"][t][act]
+        rms.append(float(np.sqrt((d ** 2).sum(axis=1).mean())))
+        for slot, kind, path in g.events_at("exact-knn", t):
+            if kind == 1:
+                sim.destroy_agent(slot)
+            else:
+                sim.set_path(slot, path)
+    print(f"{name}: trajectory RMS divergence after {T} ticks = {rms[-1]:.3e} (max {max(rms):.3e})")
+    assert max(rms) < 1e-2
+
+
+def test_trajectory_rms_600_ticks():
+    """north_star: trajectory RMS divergence over 600 ticks is reported."""
+    n = 3000
+    w = S.world_c1()
+    c = S.crowd_c1(w, n=n, seed=31)
+    # straight two-point paths are enough here: the planner is not under test
+    from oracle import pyref
+
+    if pyref.available("exact-knn"):
+        r = pyref.RefSim(w, n + 8, 1 / 60, "exact-knn")
+        r.bulk_load(c.pos, c.goal, c.radius, c.speed)
+        off, pxy = r.paths(n)
+        r.close()
+    else:
+        g = Golden("c1_small")
+        c = g.crowd
+        n, off, pxy = g.n, g.path_off, g.path_xy
+    sim = gpu.GpuSim(w, n + 8, 1 / 60)
+    sim.bulk_load(c.pos, c.radius, c.speed, off, pxy)
+    ora = OracleSim(w, n + 8, 1 / 60, "exact-knn")
+    ora.bulk_load(c.pos, c.radius, c.speed, off, pxy)
+    dropped = np.zeros(n, bool)
+    for t in range(600):
+        rp_o, _ = ora.step(1)
+        rp_g, _ = sim.step(1)
+        for s in set(rp_o.tolist()) | set(rp_g.tolist()):  # location failures: drop on both sides
+            ora.destroy_agent(s)
+            sim.destroy_agent(s)
+            dropped[s] = True
+    a, b = sim.state(n), ora.state(n)
+    both = (a["active"] > 0) & (b["active"] > 0)
+    d = a["pos"][both] - b["pos"][both]
+    rms = float(np.sqrt((d ** 2).sum(axis=1).mean()))
+    same_active = float((a["active"] == b["active"]).mean())
+    print(f"trajectory RMS divergence over 600 ticks: {rms:.3e} m ({both.sum()} agents, {dropped.sum()} dropped, "
+          f"active flags equal {same_active:.4f})")
+    assert rms < 0.05
+    assert same_active > 0.995
+
+
+def test_sparse_crowd_uses_exhaustive_fallback_and_stays_exact():
+    """Fewer than 6 agents / far-apart agents: the ring search cannot terminate, the warp pass must."""
+    w = lattice_world([40] * 6, [40] * 6, 20.0)
+    c = S.sample_crowd(w, 40, 7)
+    off = np.arange(0, 2 * c.n + 1, 2, dtype=np.int32)
+    pxy = np.stack([c.pos, c.goal], axis=1).reshape(-1, 2)
+    for take in (3, 5, 6, 40):
+        sim = gpu.GpuSim(w, 64, 1 / 60, neighbor_cell=1.0)
+        ora = OracleSim(w, 64, 1 / 60, "exact-knn")
+        sim.bulk_load(c.pos[:take], c.radius[:take], c.speed[:take], off[: take + 1], pxy[: 2 * take])
+        ora.bulk_load(c.pos[:take], c.radius[:take], c.speed[:take], off[: take + 1], pxy[: 2 * take])
+        ig, cg = sim.query_neighbors(take)
+        io, co = ora.query_neighbors(take)
+        assert np.array_equal(ig, io) and np.array_equal(cg, co), take
+        sim.step(3)
+        ora.step(3)
+        assert np.abs(sim.read(gpu.VEL, 0, take) - ora.state(take)["vel"]).max() <= VEL_TOL
+        assert sim.stats()["knn_fallbacks"] > 0
+
+
+def test_ties_and_colocated_agents():
+    """Equal distances are ordered by slot id; co-located agents (sqDist <= 1e-4) are not neighbours."""
+    w = lattice_world([30, 30], [30, 30], 20.0)
+    # a 5 x 5 lattice of agents with spacing 1 inside the crossing: many exact distance ties
+    xs, ys = np.meshgrid(np.arange(5), np.arange(5))
+    pos = np.stack([xs.ravel() + 33.0, ys.ravel() + 33.0], axis=1).astype(np.float32)
+    pos = np.concatenate([pos, pos[:3] + np.float32(0.005)])  # three nearly co-located agents
+    n = len(pos)
+    goal = pos + np.float32([30.0, 0.0])
+    off = np.arange(0, 2 * n + 1, 2, dtype=np.int32)
+    pxy = np.stack([pos, goal], axis=1).reshape(-1, 2)
+    rad, spd = np.full(n, 0.3, np.float32), np.full(n, 1.4, np.float32)
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(n)  # slot order unrelated to geometry
+    sim = gpu.GpuSim(w, 64, 1 / 60, neighbor_cell=2.0)
+    ora = OracleSim(w, 64, 1 / 60, "exact-knn")
+    offp = np.arange(0, 2 * n + 1, 2, dtype=np.int32)
+    pxyp = np.stack([pos[perm], goal[perm]], axis=1).reshape(-1, 2)
+    sim.bulk_load(pos[perm], rad, spd, offp, pxyp)
+    ora.bulk_load(pos[perm], rad, spd, offp, pxyp)
+    ig, cg = sim.query_neighbors(n)
+    io, co = ora.query_neighbors(n)
+    assert np.array_equal(ig, io) and np.array_equal(cg, co)
+
+
+def test_arrival_destroy_and_replan_events():
+    g = Golden("c1_small")
+    n = 32
+    pos = g.crowd.pos[:n].copy()
+    goal = g.crowd.goal[:n].copy()
+    goal[:8] = pos[:8] + np.float32([0.5, 0.0])     # within the delete distance -> destroyed on tick 1
+    goal[8:16] = pos[8:16] + np.float32([6.0, 0.0])  # within the arrival radius -> attraction = goal
+    off = np.arange(0, 2 * n + 1, 2, dtype=np.int32)
+    pxy = np.stack([pos, goal], axis=1).reshape(-1, 2)
+    # agents 16..23: path far away from the agent -> no line hits the clearance disk -> replan request
+    pxy[2 * 16: 2 * 24] += np.float32([0.0, 500.0])
+    sim = gpu.GpuSim(g.world, 64, g.step)
+    ora = OracleSim(g.world, 64, g.step, "exact-knn")
+    sim.bulk_load(pos, g.crowd.radius[:n], g.crowd.speed[:n], off, pxy)
+    ora.bulk_load(pos, g.crowd.radius[:n], g.crowd.speed[:n], off, pxy)
+    rp_g, ds_g = sim.step(1)
+    rp_o, ds_o = ora.step(1)
+    assert np.array_equal(ds_g, ds_o) and set(ds_g.tolist()) == set(range(8))
+    assert np.array_equal(rp_g, rp_o) and len(rp_g) >= 1
+    st = sim.read(gpu.STATUS, 0, n)
+    assert (st[:8] & gpu.ST_DESTROYED).all() and (st[8:16] & gpu.ST_ARRIVING).all()
+    assert (st[rp_g] & gpu.ST_REPLAN).all()
+    a, b = sim.state(n), ora.state(n)
+    assert np.array_equal(a["active"], b["active"])
+    assert_bits_equal(a["attraction"], b["attraction"], "attraction")
+    # a pending replan is reported once, until the host supplies a path
+    rp2, _ = sim.step(1)
+    ora.step(1)
+    assert len(rp2) == 0
+    s0 = int(rp_g[0])
+    sim.set_path(s0, np.stack([pos[s0], goal[s0]]))
+    ora.set_path(s0, np.stack([pos[s0], goal[s0]]))
+    sim.step(1)
+    ora.step(1)
+    assert np.abs(sim.read(gpu.VEL, 0, n) - ora.state(n)["vel"]).max() <= VEL_TOL
+
+
+def test_outside_world_and_bin_fallback_paths():
+    """Points outside the static grid use the exhaustive scans; results must not change."""
+    g = Golden("c2_small")
+    sim = gpu.GpuSim(g.world, 8, g.step)
+    ora = OracleSim(g.world, 8, g.step, "exact-knn")
+    rng = np.random.default_rng(9)
+    bb = g.world.bbox
+    pts = rng.uniform([bb[0] - 300, bb[1] - 300], [bb[2] + 300, bb[3] + 300], size=(4000, 2)).astype(np.float32)
+    assert np.array_equal(sim.query_cells(pts), ora.query_cells(pts))
+    for bin_size in (1.5, 50.0):
+        sim2 = gpu.GpuSim(g.world, 8, g.step, static_bin=bin_size)
+        assert np.array_equal(sim2.query_cells(g.z["probe/xy"]), g.z["probe/cell"])
+
+
+def test_obstacle_lists_match_oracle():
+    g = Golden("c2_small")
+    sim, ora = _pair(g)
+    sim.step(5)
+    ora.step(5)
+    st = ora.state(g.n)
+    sim.write(gpu.POS, st["pos"])
+    for slot in range(0, g.n, 7):
+        assert np.array_equal(sim.query_obstacles(slot), ora.query_obstacles(slot)), slot
+    assert sim.stats()["obstacle_overflows"] == 0
+
+
+def test_large_crowd_properties():
+    """BASELINE-size check without an oracle run: invariants of one tick on a big crowd."""
+    w = S.world_c3()
+    n = 200_000
+    c = S.sample_crowd(w, n, 3, window=(0, 0, 1200, 1200))
+    off = np.arange(0, 2 * n + 1, 2, dtype=np.int32)
+    pxy = np.stack([c.pos, c.goal], axis=1).reshape(-1, 2)
+    sim = gpu.GpuSim(w, n, 1 / 60)
+    sim.bulk_load(c.pos, c.radius, c.speed, off, pxy)
+    ids, cnt = sim.query_neighbors(n)
+    assert (cnt == 5).all()
+    # neighbour lists are sorted by distance, contain no self and no duplicates
+    d = np.linalg.norm(c.pos[ids] - c.pos[:, None, :], axis=2)
+    assert (np.diff(d, axis=1) >= -1e-5).all()
+    assert (ids != np.arange(n)[:, None]).all()
+    assert all(len(set(row)) == 5 for row in ids[:: 997])
+    # symmetric sanity: the nearest neighbour's distance is what a brute-force block check finds
+    sub = np.arange(0, n, 4001)
+    for i in sub[:20]:
+        dd = np.linalg.norm(c.pos - c.pos[i], axis=1)
+        dd[i] = np.inf
+        assert abs(dd.min() - d[i, 0]) < 1e-4
+    sim.step(2)
+    st = sim.stats()
+    assert st["n_active"] == n and st["knn_fallbacks"] == 0
+    v = sim.read(gpu.VEL, 0, n)
+    assert np.isfinite(v).all() and np.linalg.norm(v, axis=1).max() <= 1.4 * 1.01
