@@ -224,7 +224,8 @@ def run_ours(args):
 
         sim = StripSim(w, c, off, pxy, rank, world, local)
     else:
-        sim = gpu.GpuSim(w, n, float(S.DT), device=local, record_neighbors=False)
+        sim = gpu.GpuSim(w, n, float(S.DT), device=local, record_neighbors=False,
+                         path_pool_points=int(off[-1] * 1.25) + 4096)
         sim.bulk_load(c.pos, c.radius, c.speed, off, pxy)
     mean_p = float(np.diff(off).mean())
 
