@@ -1,0 +1,181 @@
+// Multi-GPU strip decomposition: device side of the per-tick halo exchange and agent migration.
+//
+// The world is cut into vertical strips [lo, hi) along x, one per rank (one process per GPU).
+// Every rank holds the per-slot arrays for ALL global slots; static components (radius, speed,
+// path) are replicated at load time, `active[slot]` is 1 only on the rank that OWNS the agent.
+// All inter-agent coupling of the reference tick is the read of the k = 5 neighbours' pre-tick
+// position / velocity / radius (ORCA.cpp:342-344), so one exchange per tick suffices:
+//
+//   k_pack            owned agents near a strip border -> halo entries for that neighbour;
+//                     agents that left the strip -> migrant entries for the new owner, the old
+//                     owner keeps them as "self ghosts" for the coming tick
+//   NCCL send/recv    one fixed-size message per direction (header with the two counts)
+//   k_unpack_migrants received migrants become owned agents of this rank
+//   k_ghost_count / k_ghost_scatter   received halo entries + self ghosts join the neighbour grid
+//                     snapshot as ghosts (visible as neighbours, never updated here)
+//
+// Exactness: the grid holds every agent with x in [lo - halo, hi + halo).  After the neighbour
+// search an owned agent whose 5th distance reaches beyond that range raises ECMGPU_ST_HALO_MISS
+// (counted); with zero misses the result equals the single-GPU result bit for bit.
+#pragma once
+#include "tick.cuh"
+
+namespace ecm {
+
+struct HaloEntry {  // 20 B
+    int slot;
+    float x, y, vx, vy;
+};
+struct MigrantEntry {  // 48 B: every mutable per-slot component
+    int slot;
+    float x, y, vx, vy;
+    float ax, ay;    // attraction point (kept on IRM failure, Simulator.cpp:573-587)
+    float pvx, pvy;  // preferred velocity
+    float fx, fy;    // force
+    unsigned flags;  // bit 0: replan pending
+};
+struct MsgHeader {  // 16 B
+    int n_halo, n_migrants, pad0, pad1;
+};
+
+struct StripView {
+    int enabled;
+    int rank, n_ranks;
+    float lo, hi, halo;  // lo = -inf on rank 0, hi = +inf on the last rank
+    int cap_halo, cap_migr, cap_self;
+    // message = [MsgHeader][HaloEntry x cap_halo][MigrantEntry x cap_migr]; index 0 = left, 1 = right
+    unsigned char* send[2];
+    unsigned char* recv[2];
+    HaloEntry* self_ghost;
+    int* self_ghost_n;
+    int* g_key;   // [2*cap_halo + cap_self] cell key of ghost g
+    int* g_rank;
+    __device__ __forceinline__ MsgHeader* hdr(unsigned char* m) const { return (MsgHeader*)m; }
+    __device__ __forceinline__ HaloEntry* halo_of(unsigned char* m) const { return (HaloEntry*)(m + sizeof(MsgHeader)); }
+    __device__ __forceinline__ MigrantEntry* migr_of(unsigned char* m) const {
+        return (MigrantEntry*)(m + sizeof(MsgHeader) + sizeof(HaloEntry) * (size_t)cap_halo);
+    }
+};
+
+__host__ __device__ inline size_t strip_msg_bytes(int cap_halo, int cap_migr) {
+    return sizeof(MsgHeader) + sizeof(HaloEntry) * (size_t)cap_halo + sizeof(MigrantEntry) * (size_t)cap_migr;
+}
+
+// Ownership from position: used once when strips are installed.
+__global__ void __launch_bounds__(256) k_assign_owner(int n_slots, AgentArrays ag, StripView sv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots || !ag.active[i]) return;
+    float x = ag.pos[i].x;
+    if (!(x >= sv.lo && x < sv.hi)) ag.active[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_pack(int n_slots, AgentArrays ag, StripView sv, unsigned long long* counters) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots || !ag.active[i]) return;
+    const float2 p = ag.pos[i];
+    const int dir = p.x < sv.lo ? 0 : (p.x >= sv.hi ? 1 : -1);
+    if (dir >= 0) {  // left the strip: hand over, keep as a ghost for the coming tick
+        const float2 v = ag.vel[i];
+        unsigned char* m = sv.send[dir];
+        int e = atomicAdd(&sv.hdr(m)->n_migrants, 1);
+        if (e < sv.cap_migr) {
+            MigrantEntry me;
+            me.slot = i; me.x = p.x; me.y = p.y; me.vx = v.x; me.vy = v.y;
+            const float2 a = ag.attraction[i], pv = ag.prefvel[i], f = ag.force[i];
+            me.ax = a.x; me.ay = a.y; me.pvx = pv.x; me.pvy = pv.y; me.fx = f.x; me.fy = f.y;
+            me.flags = ag.replan_pending[i] ? 1u : 0u;
+            sv.migr_of(m)[e] = me;
+            ag.active[i] = 0;
+            int g = atomicAdd(sv.self_ghost_n, 1);
+            if (g < sv.cap_self) {
+                HaloEntry he; he.slot = i; he.x = p.x; he.y = p.y; he.vx = v.x; he.vy = v.y;
+                sv.self_ghost[g] = he;
+            } else atomicAdd(&counters[C_TOTAL_HALO_MISS], 1ull);
+        } else {
+            atomicAdd(&counters[C_TOTAL_HALO_MISS], 1ull);  // message full: the agent stays here this tick
+        }
+        return;
+    }
+#pragma unroll
+    for (int d = 0; d < 2; d++) {
+        const bool has = d == 0 ? sv.rank > 0 : sv.rank < sv.n_ranks - 1;
+        const bool near = d == 0 ? p.x < sv.lo + sv.halo : p.x >= sv.hi - sv.halo;
+        if (has && near) {
+            unsigned char* m = sv.send[d];
+            int e = atomicAdd(&sv.hdr(m)->n_halo, 1);
+            if (e < sv.cap_halo) {
+                const float2 v = ag.vel[i];
+                HaloEntry he; he.slot = i; he.x = p.x; he.y = p.y; he.vx = v.x; he.vy = v.y;
+                sv.halo_of(m)[e] = he;
+            } else atomicAdd(&counters[C_TOTAL_HALO_MISS], 1ull);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_unpack_migrants(AgentArrays ag, StripView sv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int d = 0; d < 2; d++) {
+        const unsigned char* m = sv.recv[d];
+        const int n = min(((const MsgHeader*)m)->n_migrants, sv.cap_migr);
+        if (i < n) {
+            const MigrantEntry me = ((const MigrantEntry*)(m + sizeof(MsgHeader) + sizeof(HaloEntry) * (size_t)sv.cap_halo))[i];
+            ag.pos[me.slot] = make_float2(me.x, me.y);
+            ag.vel[me.slot] = make_float2(me.vx, me.vy);
+            ag.attraction[me.slot] = make_float2(me.ax, me.ay);
+            ag.prefvel[me.slot] = make_float2(me.pvx, me.pvy);
+            ag.force[me.slot] = make_float2(me.fx, me.fy);
+            ag.replan_pending[me.slot] = (me.flags & 1u) ? 1 : 0;
+            ag.active[me.slot] = 1;
+        }
+    }
+}
+
+// ghost index space: [0, cap_halo) from the left neighbour, [cap_halo, 2 cap_halo) from the right,
+// [2 cap_halo, 2 cap_halo + cap_self) self ghosts
+__device__ __forceinline__ bool ghost_entry(const StripView& sv, int g, HaloEntry& out) {
+    if (g < 2 * sv.cap_halo) {
+        const int d = g >= sv.cap_halo ? 1 : 0;
+        const int k = g - d * sv.cap_halo;
+        const unsigned char* m = sv.recv[d];
+        if (k >= min(((const MsgHeader*)m)->n_halo, sv.cap_halo)) return false;
+        out = ((const HaloEntry*)(m + sizeof(MsgHeader)))[k];
+        return true;
+    }
+    const int k = g - 2 * sv.cap_halo;
+    if (k >= min(*sv.self_ghost_n, sv.cap_self)) return false;
+    out = sv.self_ghost[k];
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_ghost_count(StripView sv, GridParams gp, int* __restrict__ cell_count) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= 2 * sv.cap_halo + sv.cap_self) return;
+    HaloEntry he;
+    if (!ghost_entry(sv, g, he)) { sv.g_key[g] = -1; return; }
+    float fx = (he.x - gp.x0) * gp.inv_cell, fy = (he.y - gp.y0) * gp.inv_cell;
+    int cx = fx >= 0.0f ? (fx < (float)gp.w ? (int)fx : gp.w - 1) : 0;
+    int cy = fy >= 0.0f ? (fy < (float)gp.h ? (int)fy : gp.h - 1) : 0;
+    int k = cy * gp.w + cx;
+    sv.g_key[g] = k;
+    sv.g_rank[g] = atomicAdd(&cell_count[k], 1);
+}
+
+__global__ void __launch_bounds__(256) k_ghost_scatter(StripView sv, const int* __restrict__ cell_start, AgentArrays ag, TickScratch sc,
+                                                       unsigned char* __restrict__ s_ghost) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= 2 * sv.cap_halo + sv.cap_self) return;
+    const int k = sv.g_key[g];
+    if (k < 0) return;
+    HaloEntry he;
+    ghost_entry(sv, g, he);
+    const int p = cell_start[k] + sv.g_rank[g];
+    sc.s_pos[p] = make_float2(he.x, he.y);
+    sc.s_vel[p] = make_float2(he.vx, he.vy);
+    sc.s_rad[p] = ag.radius[he.slot];
+    sc.s_spd[p] = ag.speed[he.slot];
+    sc.s_slot[p] = he.slot;
+    s_ghost[p] = 1;
+}
+
+}  // namespace ecm

@@ -59,6 +59,7 @@ struct TickScratch {
     int* block_sums;
     float2* s_pos; float2* s_vel; float* s_rad; float* s_spd; int* s_slot;
     float2* s_pref; unsigned char* s_alive;
+    unsigned char* s_ghost;  // 1: halo / self ghost (multi-GPU): a neighbour candidate only
     int* fb_list;
     int* ev_replan; int* ev_destroyed;
     unsigned long long* counters;
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(256) k_scatter(int n_slots, const int* __restr
     sc.s_rad[p] = ag.radius[i];
     sc.s_spd[p] = ag.speed[i];
     sc.s_slot[p] = i;
+    sc.s_ghost[p] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -180,12 +182,15 @@ struct TickView {
     float step;
     int max_ring;
     int record_neighbors;
+    // multi-GPU strips (strips.cuh): the grid holds every agent with x in [cover_lo, cover_hi)
+    int strips;
+    float cover_lo, cover_hi;
 };
 
 __global__ void __launch_bounds__(128) k_attract(TickView t) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = *t.n_sorted_ptr;
-    const bool valid = p < n;
+    const bool valid = p < n && !t.sc.s_ghost[p];
     unsigned st = 0u;
     if (valid) {
         const int slot = t.sc.s_slot[p];
@@ -253,6 +258,11 @@ __device__ __forceinline__ unsigned finish_agent(const TickView& t, int p, const
     const v2 pos = t.sc.s_pos[p], vel = t.sc.s_vel[p];
     const float rad = t.sc.s_rad[p], spd = t.sc.s_spd[p];
     const int n_nb = k.count();
+    unsigned extra = 0u;
+    if (t.strips) {  // did the search ball stay inside what this rank can see?
+        const float r5 = n_nb == kK ? sqrtf(k.d[kK - 1]) * 1.001f : CUDART_INF_F;
+        if (pos.x - r5 < t.cover_lo || pos.x + r5 >= t.cover_hi) extra = 128u;
+    }
     OrcaResult r = orca_velocity(t.obst, t.bins, t.grid, pos, vel, rad, spd, t.sc.s_pref[p], n_nb, k.q, t.step);
     // force = v_orca - v (Simulator.cpp:676-677)
     const v2 f = V(r.velocity.x - vel.x, r.velocity.y - vel.y);
@@ -268,14 +278,14 @@ __device__ __forceinline__ unsigned finish_agent(const TickView& t, int p, const
         for (int j = 0; j < kK; j++) t.ag.nbr[kK * slot + j] = k.q[j] >= 0 ? t.sc.s_slot[k.q[j]] : -1;
         t.ag.nbr_cnt[slot] = n_nb;
     }
-    return r.status;
+    return r.status | extra;
 }
 
 __global__ void __launch_bounds__(128) k_orca(TickView t) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = *t.n_sorted_ptr;
     unsigned st = 0u;
-    if (p < n && t.sc.s_alive[p]) {
+    if (p < n && !t.sc.s_ghost[p] && t.sc.s_alive[p]) {
         Knn k;
         if (knn_grid(k, t.sc.s_pos[p], t.grid, t.max_ring)) {
             st = finish_agent(t, p, k);
@@ -289,7 +299,9 @@ __global__ void __launch_bounds__(128) k_orca(TickView t) {
     unsigned m_ovf = __ballot_sync(0xffffffffu, (st & 16u) != 0u);
     unsigned m_lp3 = __ballot_sync(0xffffffffu, (st & 64u) != 0u);
     unsigned m_fb = __ballot_sync(0xffffffffu, (st & 32u) != 0u);
+    unsigned m_hm = __ballot_sync(0xffffffffu, (st & 128u) != 0u);
     if ((threadIdx.x & 31) == 0) {
+        if (m_hm) atomicAdd(&t.sc.counters[C_TOTAL_HALO_MISS], (unsigned long long)__popc(m_hm));
         if (m_ovf) atomicAdd(&t.sc.counters[C_TOTAL_OBST_OVF], (unsigned long long)__popc(m_ovf));
         if (m_lp3) atomicAdd(&t.sc.counters[C_TOTAL_LP3D], (unsigned long long)__popc(m_lp3));
         if (m_fb) atomicAdd(&t.sc.counters[C_TOTAL_FALLBACK], (unsigned long long)__popc(m_fb));
@@ -313,6 +325,7 @@ __global__ void __launch_bounds__(128) k_fallback(TickView t, int mode) {
                 unsigned st = finish_agent(t, p, k);
                 if (st & 16u) atomicAdd(&t.sc.counters[C_TOTAL_OBST_OVF], 1ull);
                 if (st & 64u) atomicAdd(&t.sc.counters[C_TOTAL_LP3D], 1ull);
+                if (st & 128u) atomicAdd(&t.sc.counters[C_TOTAL_HALO_MISS], 1ull);
                 if (st) t.ag.status[t.sc.s_slot[p]] |= st;
             } else {
                 const int slot = t.sc.s_slot[p];
@@ -346,7 +359,7 @@ __global__ void k_retract(EcmView ecm, BinView bins, int n, const float2* __rest
 __global__ void __launch_bounds__(128) k_knn_query(TickView t) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = *t.n_sorted_ptr;
-    if (p >= n) return;
+    if (p >= n || t.sc.s_ghost[p]) return;
     Knn k;
     if (knn_grid(k, t.sc.s_pos[p], t.grid, t.max_ring)) {
         const int slot = t.sc.s_slot[p];

@@ -12,14 +12,13 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
-#include "device/tick.cuh"
+#include <dlfcn.h>
 
-#ifdef ECMGPU_WITH_NCCL
-#include <nccl.h>
-#endif
+#include "device/strips.cuh"
 
 using namespace ecm;
 
@@ -94,6 +93,19 @@ struct ecmgpu_sim {
     DevBuf<float> d_s_rad, d_s_spd;
     DevBuf<unsigned char> d_s_alive;
     DevBuf<unsigned long long> d_counters;
+
+    // ---- multi-GPU strips (device/strips.cuh)
+    bool strips_on = false;
+    int rank = 0, n_ranks = 1;
+    float strip_lo = 0, strip_hi = 0, halo = 0;
+    int cap_halo = 0, cap_migr = 0, cap_self = 0;
+    void* nccl_comm = nullptr;
+    ecmgpu_sim* peer[2] = {nullptr, nullptr};  // in-process transport: left / right neighbour handles
+    bool local_transport = false;
+    cudaEvent_t ev_packed = nullptr, ev_pulled = nullptr;
+    DevBuf<unsigned char> d_send[2], d_recv[2], d_s_ghost;
+    DevBuf<HaloEntry> d_self_ghost;
+    DevBuf<int> d_self_ghost_n, d_g_key, d_g_rank;
 
     // ---- bookkeeping
     uint64_t ticks = 0, launches = 0;
@@ -357,6 +369,7 @@ TickView make_view(ecmgpu_sim* s) {
     t.sc.s_slot = s->d_s_slot.p;
     t.sc.s_pref = s->d_s_pref.p;
     t.sc.s_alive = s->d_s_alive.p;
+    t.sc.s_ghost = s->d_s_ghost.p;
     t.sc.fb_list = s->d_fb_list.p;
     t.sc.ev_replan = s->d_ev_replan.p;
     t.sc.ev_destroyed = s->d_ev_destroyed.p;
@@ -365,6 +378,10 @@ TickView make_view(ecmgpu_sim* s) {
     t.step = s->prm.step;
     t.max_ring = s->max_ring;
     t.record_neighbors = s->prm.record_neighbors;
+    t.strips = s->strips_on ? 1 : 0;
+    const float inf = std::numeric_limits<float>::infinity();
+    t.cover_lo = s->strips_on && s->rank > 0 ? s->strip_lo - s->halo : -inf;
+    t.cover_hi = s->strips_on && s->rank < s->n_ranks - 1 ? s->strip_hi + s->halo : inf;
     return t;
 }
 
@@ -382,18 +399,146 @@ int ensure_ready(ecmgpu_sim* s) {
     return ECMGPU_OK;
 }
 
-// count + scan + scatter: the per-tick neighbour structure
+// ---- NCCL, loaded lazily so that single-GPU users need no NCCL at all ----------------------------
+struct UniqueId { char internal[128]; };  // ncclUniqueId
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+bool load_nccl(std::string& err) {
+    if (g_nccl.lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+    auto sym = [&](const char* n) { void* p = dlsym(h, n); if (!p) err = std::string("missing NCCL symbol ") + n; return p; };
+    g_nccl.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, UniqueId, int))sym("ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+    g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))sym("ncclSend");
+    g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))sym("ncclRecv");
+    g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    if (!err.empty()) return false;
+    g_nccl.lib = h;
+    return true;
+}
+
+#define NCCL_TRY(s, expr)                                                                                  \
+    do {                                                                                                   \
+        int _r = (expr);                                                                                   \
+        if (_r != 0) return fail((s), ECMGPU_ERR_COMM, std::string(#expr) + ": " + g_nccl.GetErrorString(_r)); \
+    } while (0)
+
+void comm_teardown(ecmgpu_sim* s) {
+    if (s->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->nccl_comm);
+    s->nccl_comm = nullptr;
+    if (s->ev_packed) cudaEventDestroy(s->ev_packed);
+    if (s->ev_pulled) cudaEventDestroy(s->ev_pulled);
+    s->ev_packed = s->ev_pulled = nullptr;
+    for (int d = 0; d < 2; d++) { s->d_send[d].free(); s->d_recv[d].free(); }
+    s->d_s_ghost.free(); s->d_self_ghost.free(); s->d_self_ghost_n.free(); s->d_g_key.free(); s->d_g_rank.free();
+}
+
+StripView make_strip_view(ecmgpu_sim* s) {
+    StripView v;
+    memset(&v, 0, sizeof(v));
+    v.enabled = s->strips_on ? 1 : 0;
+    v.rank = s->rank;
+    v.n_ranks = s->n_ranks;
+    v.lo = s->strip_lo;
+    v.hi = s->strip_hi;
+    v.halo = s->halo;
+    v.cap_halo = s->cap_halo;
+    v.cap_migr = s->cap_migr;
+    v.cap_self = s->cap_self;
+    for (int d = 0; d < 2; d++) { v.send[d] = s->d_send[d].p; v.recv[d] = s->d_recv[d].p; }
+    v.self_ghost = s->d_self_ghost.p;
+    v.self_ghost_n = s->d_self_ghost_n.p;
+    v.g_key = s->d_g_key.p;
+    v.g_rank = s->d_g_rank.p;
+    return v;
+}
+
+// phase 0: pack halo / migrant / self-ghost lists from the current state
+int enqueue_pack(ecmgpu_sim* s, const TickView& t) {
+    StripView sv = make_strip_view(s);
+    if (s->local_transport)  // neighbours must have pulled last tick's messages before we overwrite them
+        for (int d = 0; d < 2; d++)
+            if (s->peer[d]) CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->peer[d]->ev_pulled, 0));
+    for (int d = 0; d < 2; d++) CUDA_TRY(s, cudaMemsetAsync(s->d_send[d].p, 0, sizeof(MsgHeader), s->stream));
+    CUDA_TRY(s, cudaMemsetAsync(s->d_self_ghost_n.p, 0, sizeof(int), s->stream));
+    k_pack<<<div_up(s->n_slots, 256), 256, 0, s->stream>>>(s->n_slots, t.ag, sv, s->d_counters.p);
+    s->launches++;
+    if (s->local_transport) CUDA_TRY(s, cudaEventRecord(s->ev_packed, s->stream));
+    CUDA_TRY(s, cudaGetLastError());
+    return ECMGPU_OK;
+}
+
+// phase 1: one fixed-size message per direction (NCCL send/recv, or peer copies inside one process),
+// then received migrants become owned agents
+int enqueue_exchange(ecmgpu_sim* s, const TickView& t) {
+    StripView sv = make_strip_view(s);
+    const size_t msg = strip_msg_bytes(s->cap_halo, s->cap_migr);
+    if (s->local_transport) {
+        for (int d = 0; d < 2; d++) {
+            ecmgpu_sim* p = s->peer[d];
+            if (!p) continue;
+            CUDA_TRY(s, cudaStreamWaitEvent(s->stream, p->ev_packed, 0));
+            // my left neighbour's RIGHT message is my left inbox, and vice versa
+            CUDA_TRY(s, cudaMemcpyPeerAsync(s->d_recv[d].p, s->prm.device, p->d_send[1 - d].p, p->prm.device, msg, s->stream));
+        }
+        CUDA_TRY(s, cudaEventRecord(s->ev_pulled, s->stream));
+    } else if (s->n_ranks > 1) {
+        NCCL_TRY(s, g_nccl.GroupStart());
+        if (s->rank > 0) {
+            NCCL_TRY(s, g_nccl.Send(s->d_send[0].p, msg, /*ncclInt8*/ 0, s->rank - 1, s->nccl_comm, s->stream));
+            NCCL_TRY(s, g_nccl.Recv(s->d_recv[0].p, msg, 0, s->rank - 1, s->nccl_comm, s->stream));
+        }
+        if (s->rank < s->n_ranks - 1) {
+            NCCL_TRY(s, g_nccl.Send(s->d_send[1].p, msg, 0, s->rank + 1, s->nccl_comm, s->stream));
+            NCCL_TRY(s, g_nccl.Recv(s->d_recv[1].p, msg, 0, s->rank + 1, s->nccl_comm, s->stream));
+        }
+        NCCL_TRY(s, g_nccl.GroupEnd());
+    }
+    k_unpack_migrants<<<div_up(std::max(s->cap_migr, 1), 256), 256, 0, s->stream>>>(t.ag, sv);
+    s->launches++;
+    CUDA_TRY(s, cudaGetLastError());
+    return ECMGPU_OK;
+}
+
+// count + scan + scatter: the per-tick neighbour structure (owned agents, plus ghosts with strips)
 int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
     GridParams gp{s->gx0, s->gy0, s->cell, 1.0f / s->cell, s->gw, s->gh};
     CUDA_TRY(s, cudaMemsetAsync(s->d_cell_count.p, 0, sizeof(int) * s->ncells_padded, s->stream));
     CUDA_TRY(s, cudaMemsetAsync(s->d_counters.p + C_FALLBACK_N, 0, sizeof(unsigned long long), s->stream));
     const int nb = div_up(s->n_slots, 256);
     k_bin_count<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p);
+    StripView sv = make_strip_view(s);
+    const int ng = 2 * s->cap_halo + s->cap_self;
+    if (s->strips_on) {
+        k_ghost_count<<<div_up(ng, 256), 256, 0, s->stream>>>(sv, gp, s->d_cell_count.p);
+        s->launches++;
+    }
     const int tiles = s->ncells_padded / kScanTile;
     k_scan_tiles<<<tiles, kScanBlock, 0, s->stream>>>((int4*)s->d_cell_count.p, s->d_block_sums.p);
     k_scan_sums<<<1, kScanBlock, 0, s->stream>>>(s->d_block_sums.p, tiles);
     k_scan_add<<<tiles, kScanBlock, 0, s->stream>>>((int4*)s->d_cell_count.p, s->d_block_sums.p);
     k_scatter<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc);
+    if (s->strips_on) {
+        k_ghost_scatter<<<div_up(ng, 256), 256, 0, s->stream>>>(sv, s->d_cell_count.p, t.ag, t.sc, s->d_s_ghost.p);
+        s->launches++;
+    }
     s->launches += 5;
     CUDA_TRY(s, cudaGetLastError());
     return ECMGPU_OK;
@@ -499,7 +644,7 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
     TRY_ALLOC(s->d_key.alloc(n)); TRY_ALLOC(s->d_rank.alloc(n));
     TRY_ALLOC(s->d_s_pos.alloc(n)); TRY_ALLOC(s->d_s_vel.alloc(n)); TRY_ALLOC(s->d_s_pref.alloc(n));
     TRY_ALLOC(s->d_s_rad.alloc(n)); TRY_ALLOC(s->d_s_spd.alloc(n)); TRY_ALLOC(s->d_s_slot.alloc(n));
-    TRY_ALLOC(s->d_s_alive.alloc(n)); TRY_ALLOC(s->d_fb_list.alloc(n));
+    TRY_ALLOC(s->d_s_alive.alloc(n)); TRY_ALLOC(s->d_fb_list.alloc(n)); TRY_ALLOC(s->d_s_ghost.alloc(n));
     TRY_ALLOC(s->d_ev_replan.alloc(n)); TRY_ALLOC(s->d_ev_destroyed.alloc(n));
     TRY_ALLOC(s->d_counters.alloc(C_COUNT));
     TRY_ALLOC(cudaMemsetAsync(s->d_pos.p, 0, 8 * n, s->stream)); TRY_ALLOC(cudaMemsetAsync(s->d_vel.p, 0, 8 * n, s->stream));
@@ -535,6 +680,7 @@ void ecmgpu_destroy(ecmgpu_sim* s) {
     s->d_key.free(); s->d_rank.free(); s->d_cell_count.free(); s->d_block_sums.free(); s->d_s_slot.free();
     s->d_fb_list.free(); s->d_ev_replan.free(); s->d_ev_destroyed.free(); s->d_s_pos.free(); s->d_s_vel.free();
     s->d_s_pref.free(); s->d_s_rad.free(); s->d_s_spd.free(); s->d_s_alive.free(); s->d_counters.free();
+    comm_teardown(s);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -688,18 +834,23 @@ int ecmgpu_destroy_agent(ecmgpu_sim* s, int slot) {
     return ECMGPU_OK;
 }
 
-int ecmgpu_update(ecmgpu_sim* s) {
+int ecmgpu_update_phase(ecmgpu_sim* s, int phase) {
     if (!s) return ECMGPU_ERR_INVALID;
+    if (phase < 0 || phase > 2) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_update_phase: phase must be 0, 1 or 2");
     CUDA_TRY(s, cudaSetDevice(s->prm.device));
-    if (s->n_slots == 0) { s->ticks++; return ECMGPU_OK; }
+    if (s->n_slots == 0) { if (phase == 2) s->ticks++; return ECMGPU_OK; }
     int rc = ensure_ready(s);
     if (rc) return rc;
     TickView t = make_view(s);
-    if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[0], s->stream));
+    if (phase == 0) {
+        if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[0], s->stream));
+        return s->strips_on ? enqueue_pack(s, t) : ECMGPU_OK;
+    }
+    if (phase == 1) return s->strips_on ? enqueue_exchange(s, t) : ECMGPU_OK;
     rc = enqueue_grid_build(s, t);
     if (rc) return rc;
     if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[1], s->stream));
-    const int nb = div_up(s->n_slots, 128);
+    const int nb = div_up(s->n_slots + (s->strips_on ? 2 * s->cap_halo + s->cap_self : 0), 128);
     k_attract<<<nb, 128, 0, s->stream>>>(t);
     if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
     k_orca<<<nb, 128, 0, s->stream>>>(t);
@@ -708,6 +859,17 @@ int ecmgpu_update(ecmgpu_sim* s) {
     s->launches += 3;
     s->ticks++;
     CUDA_TRY(s, cudaGetLastError());
+    return ECMGPU_OK;
+}
+
+int ecmgpu_update(ecmgpu_sim* s) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (s->local_transport && s->n_ranks > 1)
+        return fail(s, ECMGPU_ERR_INVALID, "in-process strips: drive all handles with ecmgpu_update_phase(0), (1), (2)");
+    for (int phase = 0; phase < 3; phase++) {
+        int rc = ecmgpu_update_phase(s, phase);
+        if (rc) return rc;
+    }
     return ECMGPU_OK;
 }
 
@@ -822,11 +984,19 @@ int ecmgpu_find_neighbors(ecmgpu_sim* s, int count, int* out_ids5, int* out_coun
         int rc = ensure_ready(s);
         if (rc) return rc;
         TickView t = make_view(s);
+        if (s->strips_on) {
+            if (s->local_transport && s->n_ranks > 1)
+                return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_find_neighbors is not available with in-process strips");
+            rc = enqueue_pack(s, t);
+            if (rc) return rc;
+            rc = enqueue_exchange(s, t);
+            if (rc) return rc;
+        }
         rc = enqueue_grid_build(s, t);
         if (rc) return rc;
         CUDA_TRY(s, cudaMemsetAsync(s->d_nbr.p, 0xff, sizeof(int) * 5 * (size_t)s->n_slots, s->stream));
         CUDA_TRY(s, cudaMemsetAsync(s->d_nbr_cnt.p, 0xff, sizeof(int) * (size_t)s->n_slots, s->stream));
-        k_knn_query<<<div_up(s->n_slots, 128), 128, 0, s->stream>>>(t);
+        k_knn_query<<<div_up(s->n_slots + (s->strips_on ? 2 * s->cap_halo + s->cap_self : 0), 128), 128, 0, s->stream>>>(t);
         k_fallback<<<148, 128, 0, s->stream>>>(t, 1);
         s->launches += 2;
         CUDA_TRY(s, cudaGetLastError());
@@ -926,16 +1096,95 @@ int ecmgpu_mark_elapsed_ms(ecmgpu_sim* s, int a, int b, float* out_ms) {
 void* ecmgpu_stream(ecmgpu_sim* s) { return s ? (void*)s->stream : nullptr; }
 
 int ecmgpu_comm_unique_id(uint8_t out_id[128]) {
-    (void)out_id;
-    return ECMGPU_ERR_COMM;
+    std::string err;
+    if (!out_id) return ECMGPU_ERR_INVALID;
+    if (!load_nccl(err)) return fail(nullptr, ECMGPU_ERR_COMM, err);
+    UniqueId id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) return fail(nullptr, ECMGPU_ERR_COMM, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r));
+    memcpy(out_id, id.internal, 128);
+    return ECMGPU_OK;
 }
-int ecmgpu_comm_init(ecmgpu_sim* s, const uint8_t id[128], int rank, int n_ranks) {
-    (void)id; (void)rank; (void)n_ranks;
-    return fail(s, ECMGPU_ERR_COMM, "multi-GPU strips not built into this library yet");
+
+int ecmgpu_comm_init(ecmgpu_sim* s, const uint8_t nccl_unique_id[128], int rank, int n_ranks) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_comm_init: bad rank / n_ranks");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    s->rank = rank;
+    s->n_ranks = n_ranks;
+    if (n_ranks > 1) {
+        if (!nccl_unique_id) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_comm_init: null unique id");
+        std::string err;
+        if (!load_nccl(err)) return fail(s, ECMGPU_ERR_COMM, err);
+        UniqueId id;
+        memcpy(id.internal, nccl_unique_id, 128);
+        NCCL_TRY(s, g_nccl.CommInitRank(&s->nccl_comm, n_ranks, id, rank));
+    }
+    return ECMGPU_OK;
 }
+
+int ecmgpu_comm_init_local(ecmgpu_sim* s, int rank, int n_ranks, ecmgpu_sim* left, ecmgpu_sim* right) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_comm_init_local: bad rank / n_ranks");
+    if ((rank > 0) != (left != nullptr) || (rank < n_ranks - 1) != (right != nullptr))
+        return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_comm_init_local: neighbours must match the rank's position");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    s->rank = rank;
+    s->n_ranks = n_ranks;
+    s->peer[0] = left;
+    s->peer[1] = right;
+    s->local_transport = true;
+    if (!s->ev_packed) CUDA_TRY(s, cudaEventCreateWithFlags(&s->ev_packed, cudaEventDisableTiming));
+    if (!s->ev_pulled) CUDA_TRY(s, cudaEventCreateWithFlags(&s->ev_pulled, cudaEventDisableTiming));
+    CUDA_TRY(s, cudaEventRecord(s->ev_pulled, s->stream));
+    return ECMGPU_OK;
+}
+
 int ecmgpu_comm_set_strips(ecmgpu_sim* s, const float* bounds, float halo_width) {
-    (void)bounds; (void)halo_width;
-    return fail(s, ECMGPU_ERR_COMM, "multi-GPU strips not built into this library yet");
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (!bounds || !(halo_width > 0.0f)) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_comm_set_strips: bad arguments");
+    if (s->n_ranks > 1 && !s->nccl_comm && !s->local_transport) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_comm_set_strips: call ecmgpu_comm_init first");
+    for (int r = 0; r < s->n_ranks; r++) {
+        if (!(bounds[r] < bounds[r + 1])) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_comm_set_strips: bounds must ascend");
+        // ghosts come from the adjacent strips only: an interior strip narrower than the halo would hide agents two strips away
+        if (r > 0 && r < s->n_ranks - 1 && bounds[r + 1] - bounds[r] < halo_width)
+            return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_comm_set_strips: interior strip narrower than the halo");
+    }
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    const float inf = std::numeric_limits<float>::infinity();
+    s->strip_lo = s->rank == 0 ? -inf : bounds[s->rank];
+    s->strip_hi = s->rank == s->n_ranks - 1 ? inf : bounds[s->rank + 1];
+    s->halo = halo_width;
+    // capacities: generous fixed-size messages (counts travel in the header, no host round trip)
+    const int n = s->prm.max_agents;
+    s->cap_halo = std::max(1024, std::min(n, n / std::max(1, s->n_ranks) / 2 + 4096));
+    s->cap_migr = std::max(256, std::min(n, s->cap_halo / 8));
+    s->cap_self = 2 * s->cap_migr;
+    const size_t msg = strip_msg_bytes(s->cap_halo, s->cap_migr);
+    for (int d = 0; d < 2; d++) {
+        CUDA_TRY(s, s->d_send[d].alloc(msg));
+        CUDA_TRY(s, s->d_recv[d].alloc(msg));
+        CUDA_TRY(s, cudaMemsetAsync(s->d_send[d].p, 0, sizeof(MsgHeader), s->stream));
+        CUDA_TRY(s, cudaMemsetAsync(s->d_recv[d].p, 0, sizeof(MsgHeader), s->stream));
+    }
+    CUDA_TRY(s, s->d_self_ghost.alloc(s->cap_self));
+    CUDA_TRY(s, s->d_self_ghost_n.alloc(1));
+    CUDA_TRY(s, s->d_g_key.alloc(2 * (size_t)s->cap_halo + s->cap_self));
+    CUDA_TRY(s, s->d_g_rank.alloc(2 * (size_t)s->cap_halo + s->cap_self));
+    // snapshot arrays must hold owned agents + ghosts
+    const size_t cap = (size_t)n + 2 * (size_t)s->cap_halo + s->cap_self;
+    CUDA_TRY(s, s->d_s_pos.alloc(cap)); CUDA_TRY(s, s->d_s_vel.alloc(cap)); CUDA_TRY(s, s->d_s_pref.alloc(cap));
+    CUDA_TRY(s, s->d_s_rad.alloc(cap)); CUDA_TRY(s, s->d_s_spd.alloc(cap)); CUDA_TRY(s, s->d_s_slot.alloc(cap));
+    CUDA_TRY(s, s->d_s_alive.alloc(cap)); CUDA_TRY(s, s->d_s_ghost.alloc(cap)); CUDA_TRY(s, s->d_fb_list.alloc(cap));
+    s->strips_on = true;
+    if (s->n_slots > 0) {
+        TickView t = make_view(s);
+        k_assign_owner<<<div_up(s->n_slots, 256), 256, 0, s->stream>>>(s->n_slots, t.ag, make_strip_view(s));
+        s->launches++;
+        CUDA_TRY(s, cudaGetLastError());
+    }
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    return ECMGPU_OK;
 }
 
 }  // extern "C"

@@ -36,7 +36,7 @@ EXPORTS = [
     "ecmgpu_read", "ecmgpu_write", "ecmgpu_read_async", "ecmgpu_write_async", "ecmgpu_alloc_pinned", "ecmgpu_free_pinned",
     "ecmgpu_locate", "ecmgpu_retract", "ecmgpu_find_neighbors", "ecmgpu_find_obstacles", "ecmgpu_get_stats",
     "ecmgpu_last_tick_ms", "ecmgpu_set_profiling", "ecmgpu_mark", "ecmgpu_mark_elapsed_ms", "ecmgpu_stream", "ecmgpu_comm_unique_id", "ecmgpu_comm_init",
-    "ecmgpu_comm_set_strips",
+    "ecmgpu_comm_set_strips", "ecmgpu_comm_init_local", "ecmgpu_update_phase",
 ]
 
 
@@ -99,6 +99,8 @@ def lib() -> C.CDLL:
         L.ecmgpu_comm_unique_id.argtypes = [u8p]
         L.ecmgpu_comm_init.argtypes = [vp, u8p, C.c_int, C.c_int]
         L.ecmgpu_comm_set_strips.argtypes = [vp, f32p, C.c_float]
+        L.ecmgpu_comm_init_local.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+        L.ecmgpu_update_phase.argtypes = [vp, C.c_int]
         _lib = L
     return _lib
 
@@ -193,8 +195,32 @@ class GpuSim:
         for _ in range(int(n)):
             self._ck(self.L.ecmgpu_update(self.h))
 
+    def update_phase(self, phase: int):
+        self._ck(self.L.ecmgpu_update_phase(self.h, int(phase)))
+
     def sync(self):
         self._ck(self.L.ecmgpu_sync(self.h))
+
+    # -- multi-GPU strips
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = lib().ecmgpu_comm_unique_id(buf)
+        if rc != 0:
+            raise EcmGpuError(f"ecmgpu_comm_unique_id failed ({rc}): {lib().ecmgpu_last_error(None).decode()}")
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        self._ck(self.L.ecmgpu_comm_init(self.h, buf, int(rank), int(n_ranks)))
+
+    def comm_init_local(self, rank: int, n_ranks: int, left: "GpuSim | None", right: "GpuSim | None"):
+        self._ck(self.L.ecmgpu_comm_init_local(self.h, int(rank), int(n_ranks), left.h if left else None,
+                                               right.h if right else None))
+
+    def comm_set_strips(self, bounds, halo: float):
+        b = np.ascontiguousarray(bounds, np.float32)
+        self._ck(self.L.ecmgpu_comm_set_strips(self.h, _p(b, f32p), float(halo)))
 
     def poll_events(self):
         """(replan_slots, destroyed_slots) since the last poll, ascending."""

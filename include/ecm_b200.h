@@ -164,7 +164,18 @@ void* ecmgpu_stream(ecmgpu_sim* sim);
  * nccl_unique_id: 128 bytes from ecmgpu_comm_unique_id() on rank 0, distributed by the caller. */
 int ecmgpu_comm_unique_id(uint8_t out_id[128]);
 int ecmgpu_comm_init(ecmgpu_sim* sim, const uint8_t nccl_unique_id[128], int rank, int n_ranks);
-/* Strip boundaries along x: n_ranks+1 ascending values; rank r owns [bounds[r], bounds[r+1]). */
+/* In-process transport instead of NCCL: all strips are handles of ONE process (on one or several
+ * devices); messages move by peer copies.  left/right are the neighbouring handles (NULL at the rim).
+ * With this transport a tick is driven as: ecmgpu_update_phase(h, 0) on every handle, then phase 1
+ * on every handle, then phase 2 on every handle. */
+int ecmgpu_comm_init_local(ecmgpu_sim* sim, int rank, int n_ranks, ecmgpu_sim* left, ecmgpu_sim* right);
+/* One tick in three stream-ordered phases: 0 = pack halo / migrants, 1 = exchange + adopt migrants,
+ * 2 = neighbour grid, attraction, ORCA, integration.  ecmgpu_update() = phases 0, 1, 2. */
+int ecmgpu_update_phase(ecmgpu_sim* sim, int phase);
+/* Strip boundaries along x: n_ranks+1 ascending values; rank r owns [bounds[r], bounds[r+1])
+ * (the first and last strip extend to infinity).  halo_width: agents this close to a border are
+ * mirrored to the neighbour; interior strips must be at least this wide.  Agents outside this
+ * rank's strip are deactivated here (another rank owns them). */
 int ecmgpu_comm_set_strips(ecmgpu_sim* sim, const float* bounds, float halo_width);
 
 #ifdef __cplusplus

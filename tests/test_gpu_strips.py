@@ -1,0 +1,111 @@
+"""GPU (-m gpu): strip decomposition.  In-process strips on ONE device exercise pack / exchange /
+migration / ghosts exactly like the NCCL path (same kernels, peer copies instead of send/recv);
+the NCCL transport itself is tested with torchrun when the box has >= 2 GPUs."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from ecmgenerator_b200 import gpu
+from ecmgenerator_b200 import multigpu as M
+from ecmgenerator_b200 import scenarios as S
+from ecmgenerator_b200.host import plan_paths
+from tests.conftest import ROOT
+from tests.util import assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _crowd(n, seed):
+    w = S.world_c1()
+    c = S.crowd_c1(w, n=n, seed=seed)
+    off, pxy, ok = plan_paths(w, c.pos, c.goal, c.radius)
+    assert ok == n
+    return w, c, off, pxy
+
+
+@pytest.mark.parametrize("n_strips", [2, 3, 5])
+def test_in_process_strips_match_single_gpu_bitwise(n_strips):
+    n, ticks = 6000, 240
+    w, c, off, pxy = _crowd(n, 41)
+    single = gpu.GpuSim(w, n, float(S.DT), path_pool_points=int(off[-1] * 1.25) + 4096)
+    single.bulk_load(c.pos, c.radius, c.speed, off, pxy)
+    strips = M.LocalStrips(w, c, off, pxy, n_strips, devices=(0,))
+    own0 = M.owner_of(c.pos[:, 0], strips.bounds)
+    for t in range(ticks):
+        single.update(1)
+        strips.update(1)
+    single.sync()
+    strips.sync()
+    pos, owners = strips.gather(gpu.POS)
+    act = single.read(gpu.ACTIVE, 0, n)
+    assert np.array_equal(owners, act), "every active agent has exactly one owner"
+    a = act > 0
+    assert_bits_equal(pos[a], single.read(gpu.POS, 0, n)[a], "positions")
+    vel, _ = strips.gather(gpu.VEL)
+    assert_bits_equal(vel[a], single.read(gpu.VEL, 0, n)[a], "velocities")
+    att, _ = strips.gather(gpu.ATTRACTION)
+    assert_bits_equal(att[a], single.read(gpu.ATTRACTION, 0, n)[a], "attraction points")
+    st = strips.stats()
+    assert sum(s["halo_misses"] for s in st) == 0
+    # agents did cross strip borders, i.e. migration was exercised
+    own1 = M.owner_of(pos[:, 0], strips.bounds)
+    moved = int(((own0 != own1) & a).sum())
+    print(f"{n_strips} strips: {moved} agents changed owner in {ticks} ticks; halo {strips.halo:.2f}")
+    assert moved > 10
+    # each strip really only works on its share
+    per = [s["n_active"] for s in st]
+    assert max(per) < n  # n_active counts owned + ghosts of the last grid build
+    strips.close()
+    single.close()
+
+
+def test_halo_miss_is_detected_when_the_halo_is_too_small():
+    n = 3000
+    w, c, off, pxy = _crowd(n, 42)
+    strips = M.LocalStrips(w, c, off, pxy, 2, devices=(0,), halo=0.05)
+    strips.update(3)
+    strips.sync()
+    assert sum(s["halo_misses"] for s in strips.stats()) > 0
+    strips.close()
+
+
+def test_strip_validation_errors():
+    n = 500
+    w, c, off, pxy = _crowd(n, 43)
+    s = gpu.GpuSim(w, n, float(S.DT))
+    s.bulk_load(c.pos, c.radius, c.speed, off, pxy)
+    with pytest.raises(gpu.EcmGpuError, match="null unique id"):
+        s._ck(s.L.ecmgpu_comm_init(s.h, None, 0, 2))
+    with pytest.raises(gpu.EcmGpuError, match="comm_init first"):
+        s.comm_set_strips(np.array([-1.0, 0.0, 1.0], np.float32), 5.0)
+    s2 = gpu.GpuSim(w, n, float(S.DT))
+    s2.comm_init_local(0, 1, None, None)
+    with pytest.raises(gpu.EcmGpuError, match="ascend"):
+        s2.comm_set_strips(np.array([1.0, 0.0], np.float32), 5.0)
+    s2.comm_set_strips(np.array([-1000.0, 1000.0], np.float32), 5.0)  # a single strip is fine
+    s2.bulk_load(c.pos, c.radius, c.speed, off, pxy)
+    s2.update(2)
+    s.update(2)
+    assert_bits_equal(s2.read(gpu.POS, 0, n), s.read(gpu.POS, 0, n), "one strip == no strips")
+
+
+def test_nccl_strips_match_single_gpu_bitwise():
+    import torch
+
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    world = 2 if ngpu < 4 else 4
+    out = os.path.join(ROOT, "gpurun_out", "nccl_strips.json")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(ROOT, "tests", "nccl_strips_worker.py"), out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = json.load(open(out))
+    print(res)
+    assert res["pos_equal"] and res["vel_equal"] and res["halo_misses"] == 0 and res["owners_ok"] and res["moved"] > 10
