@@ -2,7 +2,7 @@
  *
  * The reference has no plugin/FFI mechanism; the seam this library sits behind is the C++ class
  * ECM::Simulation::Simulator (/root/reference/ECMAgentSimulator/Simulator.h:59-188).  A host-side
- * drop-in `Simulator` (ecmgenerator_b200/csrc/host/Simulator.h) keeps that class's public
+ * drop-in `Simulator` (ecmgenerator_b200/csrc/dropin/Simulator.h) keeps that class's public
  * signatures and forwards to the entry points below; INTEGRATION.md shows the binding.
  *
  * Conventions: plain C types, caller-owned host buffers, int status codes (0 = ECMGPU_OK),

@@ -57,6 +57,11 @@ def _load(mode):
         L.ecmref_query_neighbors.argtypes = [C.c_void_p, C.c_int, i32p, i32p]
         L.ecmref_query_obstacles.argtypes = [C.c_void_p, C.c_int, i32p, C.c_int]
         L.ecmref_orca_velocity.argtypes = [C.c_void_p, C.c_int, f32p]
+        L.ecmref_add_spawn_area.argtypes = [C.c_void_p] + [C.c_float] * 6
+        L.ecmref_add_goal_area.argtypes = [C.c_void_p] + [C.c_float] * 4
+        L.ecmref_connect_areas.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float]
+        L.ecmref_srand.argtypes = [C.c_uint]
+        L.ecmref_valid_spawn_location.argtypes = [C.c_void_p] + [C.c_float] * 3
         _LIBS[mode] = L
     return _LIBS[mode]
 
@@ -119,6 +124,21 @@ class RefSim:
     def spawn(self, start, goal, clearance, speed) -> int:
         return self.L.ecmref_spawn(self.h, float(start[0]), float(start[1]), float(goal[0]), float(goal[1]),
                                    float(clearance), float(speed))
+
+    def add_spawn_area(self, pos, half, clearance, speed) -> int:
+        return self.L.ecmref_add_spawn_area(self.h, float(pos[0]), float(pos[1]), float(half[0]), float(half[1]), float(clearance), float(speed))
+
+    def add_goal_area(self, pos, half) -> int:
+        return self.L.ecmref_add_goal_area(self.h, float(pos[0]), float(pos[1]), float(half[0]), float(half[1]))
+
+    def connect_areas(self, spawn_id, goal_id, rate):
+        self.L.ecmref_connect_areas(self.h, int(spawn_id), int(goal_id), float(rate))
+
+    def srand(self, seed: int):
+        self.L.ecmref_srand(int(seed))
+
+    def valid_spawn_location(self, p, clearance) -> bool:
+        return bool(self.L.ecmref_valid_spawn_location(self.h, float(p[0]), float(p[1]), float(clearance)))
 
     def set_kinematics(self, slot, pos, vel):
         self.L.ecmref_set_kinematics(self.h, int(slot), float(pos[0]), float(pos[1]), float(vel[0]), float(vel[1]))

@@ -229,6 +229,18 @@ int ecmref_spawn(void* h, float sx, float sy, float gx, float gy, float clearanc
     return ((RefSim*)h)->sim->SpawnAgent(Point(sx, sy), Point(gx, gy), clearance, speed);
 }
 
+// Area API as the editor uses it (Command.cpp:33-159): Simulator.cpp:336-381, :428-440.
+int ecmref_add_spawn_area(void* h, float x, float y, float hw, float hh, float clearance, float speed) {
+    SpawnConfiguration cfg;
+    cfg.clearanceMin = clearance;
+    cfg.preferredSpeedMin = speed;
+    return ((RefSim*)h)->sim->AddSpawnArea(Point(x, y), Vec2(hw, hh), cfg);
+}
+int ecmref_add_goal_area(void* h, float x, float y, float hw, float hh) { return ((RefSim*)h)->sim->AddGoalArea(Point(x, y), Vec2(hw, hh)); }
+void ecmref_connect_areas(void* h, int spawn_id, int goal_id, float rate) { ((RefSim*)h)->sim->ConnectSpawnGoalAreas(spawn_id, goal_id, rate); }
+void ecmref_srand(unsigned seed) { srand(seed); }
+int ecmref_valid_spawn_location(void* h, float x, float y, float c) { return ((RefSim*)h)->sim->ValidSpawnLocation(Point(x, y), c) ? 1 : 0; }
+
 void ecmref_set_kinematics(void* h, int slot, float x, float y, float vx, float vy) {
     Simulator* s = ((RefSim*)h)->sim;
     s->m_Positions[slot].x = x;

@@ -1,0 +1,104 @@
+"""GPU (-m gpu): the C++17 drop-in ECM::Simulation::Simulator (csrc/dropin) used through the
+reference's own call pattern - SpawnAgent / Update / getters / spawn areas - against the reference
+built with the exact-kNN KD-tree TU (oracle/_ref, when present) and against the C oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from ecmgenerator_b200 import dropin
+from ecmgenerator_b200 import scenarios as S
+from ecmgenerator_b200.host import plan_paths
+from oracle import pyref
+from oracle.pyoracle import OracleSim
+
+pytestmark = pytest.mark.gpu
+VEL_TOL = 1e-4
+needs_ref = pytest.mark.skipif(not pyref.available("exact-knn"), reason="oracle/_ref not built")
+
+
+@needs_ref
+def test_spawn_update_getters_match_reference():
+    w = S.world_c1()
+    c = S.crowd_c1(w, n=400, seed=61)
+    ref = pyref.RefSim(w, 512, 1 / 60, "exact-knn")
+    sim = dropin.Simulator(w, 512, 1 / 60)
+    slots_r, slots_s = [], []
+    for i in range(c.n):
+        # every 50th spawn is attempted on top of the previous agent: ValidSpawnLocation must refuse it (-1)
+        start = c.pos[i - 1] if (i % 50 == 49) else c.pos[i]
+        slots_r.append(ref.spawn(start, c.goal[i], c.radius[i], c.speed[i]))
+        slots_s.append(sim.spawn_agent(start, c.goal[i], c.radius[i], c.speed[i]))
+    assert slots_r == slots_s and -1 in slots_s
+    n = max(slots_s) + 1
+    for s in slots_s[::37]:
+        if s >= 0:
+            assert np.array_equal(sim.path(s), ref.path(s)), "planner parity through SpawnAgent"
+    assert sim.num_agents == ref.num_agents and sim.last_index == ref.last_index
+    for t in range(120):
+        ref.step(1)
+        sim.update(1 / 60)
+        if t == 40:  # destroy + respawn: LIFO slot reuse (Simulator.h:66-69)
+            for s in (5, 17, 3):
+                ref.destroy_agent(s)
+                sim.destroy_agent(s)
+            a = ref.spawn(c.pos[5], c.goal[6], 0.3, 1.4)
+            b = sim.spawn_agent(c.pos[5], c.goal[6], 0.3, 1.4)
+            assert a == b == 3
+    a, b = sim.state(n), ref.state(n)
+    assert np.array_equal(a["active"], b["active"])
+    act = b["active"] > 0
+    assert np.abs(a["vel"][act] - b["vel"][act]).max() <= 5e-3  # free-running for 120 ticks
+    assert np.abs(a["pos"][act] - b["pos"][act]).max() <= 5e-3
+    assert sim.num_agents == ref.num_agents
+    ids, cnt = sim.find_neighbors(10)
+    rid, rcnt = ref.query_neighbors(n)
+    assert cnt == rcnt[10] and np.array_equal(ids, rid[10]) or np.abs(a["pos"] - b["pos"]).max() > 0
+    sim.close()
+    ref.close()
+
+
+@needs_ref
+def test_spawn_areas_follow_the_same_rand_sequence():
+    w = S.world_c1()
+    res = []
+    for make in ("ref", "sim"):
+        libc = ctypes.CDLL(None)
+        libc.srand(777)
+        s = pyref.RefSim(w, 256, 1 / 60, "exact-knn") if make == "ref" else dropin.Simulator(w, 256, 1 / 60)
+        sp = s.add_spawn_area((-135.0, 0.0), (10.0, 10.0), 0.3, 1.4)
+        ga = s.add_goal_area((135.0, 0.0), (10.0, 10.0))
+        s.connect_areas(sp, ga, 30.0)  # 30 agents / s -> one every other tick
+        for _ in range(200):
+            s.step(1) if make == "ref" else s.update(1 / 60)
+        st = s.state(256)
+        res.append((s.num_agents, s.last_index, st["active"].copy(), st["pos"].copy()))
+        s.close()
+    assert res[0][0] == res[1][0] > 50 and res[0][1] == res[1][1]
+    assert np.array_equal(res[0][2], res[1][2])
+    act = res[0][2] > 0
+    assert np.abs(res[0][3][act] - res[1][3][act]).max() <= 5e-3
+
+
+def test_dropin_matches_c_oracle_with_host_planner():
+    """No /root/reference needed: same spawn sequence into the drop-in and (as bulk load) into the C oracle."""
+    w = S.world_c1()
+    c = S.crowd_c1(w, n=300, seed=62)
+    off, pxy, ok = plan_paths(w, c.pos, c.goal, c.radius)
+    assert ok == c.n
+    sim = dropin.Simulator(w, 320, 1 / 60)
+    for i in range(c.n):
+        assert sim.spawn_agent(c.pos[i], c.goal[i], c.radius[i], c.speed[i]) == i
+    ora = OracleSim(w, 320, 1 / 60, "exact-knn")
+    ora.bulk_load(c.pos, c.radius, c.speed, off, pxy)
+    for t in range(60):
+        sim.update(0.5)  # dt is ignored like in the reference (Simulator.cpp:314)
+        ora.step(1)
+    a, b = sim.state(c.n), ora.state(c.n)
+    assert np.array_equal(a["active"], b["active"])
+    assert np.abs(a["vel"] - b["vel"]).max() <= 1e-3
+    assert np.abs(a["attraction"] - b["attraction"]).max() <= 1e-3
+    assert not sim.valid_spawn_location(a["pos"][0], 0.3) and sim.valid_spawn_location((1e4, 1e4), 0.3)
+    sim.reset()
+    assert sim.num_agents == 0
+    sim.close()
