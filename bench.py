@@ -292,37 +292,55 @@ def run_ours(args):
                 "whole_tick": {"achieved": ach_tick, "frac": ach_tick / peak, "algorithmic_bytes_per_agent": alg["tick"]}}
     clk = clocks.stop()
 
-    # ---- end to end through the C ABI with host buffers
+    # ---- end to end through the C ABI with host buffers (every rank moves its full slot arrays)
     e2e = None
-    if world == 1:
+    if True:
+        raw = sim if world == 1 else sim.sim
         hp = gpu.PinnedArray((n, 2), np.float32)
         hv = gpu.PinnedArray((n, 2), np.float32)
         ha = gpu.PinnedArray((n,), np.uint8)
-        hp.array[:] = sim.read(gpu.POS, 0, n)
-        hv.array[:] = sim.read(gpu.VEL, 0, n)
+        hp.array[:] = raw.read(gpu.POS, 0, n)
+        hv.array[:] = raw.read(gpu.VEL, 0, n)
         k = max(3, min(args.steps, 20))
 
         def e2e_tick():
-            sim.write_async(gpu.POS, hp, 0, n)
-            sim.write_async(gpu.VEL, hv, 0, n)
-            sim.update(1)
-            sim.read_async(gpu.POS, hp, 0, n)
-            sim.read_async(gpu.VEL, hv, 0, n)
-            sim.read_async(gpu.ACTIVE, ha, 0, n)
-            sim.sync()  # the host consumes the result (getters) before the next tick
+            raw.write_async(gpu.POS, hp, 0, n)
+            raw.write_async(gpu.VEL, hv, 0, n)
+            raw.update(1)
+            raw.read_async(gpu.POS, hp, 0, n)
+            raw.read_async(gpu.VEL, hv, 0, n)
+            raw.read_async(gpu.ACTIVE, ha, 0, n)
+            raw.sync()  # the host consumes the result (getters) before the next tick
 
         for _ in range(2):
             e2e_tick()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(k):
             e2e_tick()
+        barrier()
         dt = time.perf_counter() - t0
         act = int((ha.array > 0).sum())
-        e2e = {"value": act * k / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 17 * n,
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([dt, float(act)], device="cuda", dtype=torch.float64)
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dt, act = float(tmax[0].item()), int(t[1].item())
+        e2e = {"value": act * k / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * n * world, "d2h_bytes_per_step": 17 * n * world,
                "ms_per_step": 1e3 * dt / k, "steps": k}
         for a in (hp, hv, ha):
             a.free()
 
+    global_active = int(active0)
+    if world > 1:
+        import torch.distributed as dist
+
+        global_active = sim.global_active()
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     cpu = None
@@ -334,7 +352,7 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: {n} agents, {w.n_obstacles} blocks, {w.n_cells} ECM cells, dt=1/60, mean path points {mean_p:.1f}",
-                       "agents": n, "active": int(active0), "dt": float(S.DT), "parallelism": f"strips{world}" if world > 1 else "1gpu",
+                       "agents": n, "active": global_active, "dt": float(S.DT), "parallelism": f"strips{world}" if world > 1 else "1gpu",
                        "l2": "working set (agent state + path pool + snapshot) exceeds the 126 MB L2", "neighbor_cell": st1["neighbor_cell"],
                        "static_bin": st1["static_bin"]},
             "gpu_launches": int(launches), "clocks": clk,

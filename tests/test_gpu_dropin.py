@@ -66,8 +66,8 @@ def test_spawn_areas_follow_the_same_rand_sequence():
         libc = ctypes.CDLL(None)
         libc.srand(777)
         s = pyref.RefSim(w, 256, 1 / 60, "exact-knn") if make == "ref" else dropin.Simulator(w, 256, 1 / 60)
-        sp = s.add_spawn_area((-135.0, 0.0), (10.0, 10.0), 0.3, 1.4)
-        ga = s.add_goal_area((135.0, 0.0), (10.0, 10.0))
+        sp = s.add_spawn_area((-55.0, -100.0), (10.0, 10.0), 0.3, 1.4)  # inside the west vertical street
+        ga = s.add_goal_area((55.0, 100.0), (10.0, 10.0))  # inside the east vertical street
         s.connect_areas(sp, ga, 30.0)  # 30 agents / s -> one every other tick
         for _ in range(200):
             s.step(1) if make == "ref" else s.update(1 / 60)
