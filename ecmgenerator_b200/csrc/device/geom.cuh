@@ -18,6 +18,21 @@ constexpr int kK = 5;                 // Simulator.cpp:55
 
 typedef float2 v2;
 
+// Warp-uniform trip count for loops whose per-lane bound differs: with kSync all 32 lanes of the
+// warp iterate max(bound) times and re-converge at the top of every iteration (__syncwarp), so the
+// lanes that have work in iteration i do it together instead of drifting apart (independent thread
+// scheduling re-converges an early-exit loop only at its exit: ncu showed 3 of 32 lanes active in
+// the LP loop, profiles/r01_v1_k_orca_source_hotspots.txt).  kSync requires a convergent call site.
+template <bool kSync>
+__device__ __forceinline__ int warp_max_trip(int n) {
+    if (kSync) return __reduce_max_sync(0xffffffffu, n);
+    return n;
+}
+template <bool kSync>
+__device__ __forceinline__ void warp_align() {
+    if (kSync) __syncwarp();
+}
+
 __device__ __forceinline__ v2 V(float x, float y) { return make_float2(x, y); }
 __device__ __forceinline__ v2 vadd(v2 a, v2 b) { return V(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ v2 vsub(v2 a, v2 b) { return V(a.x - b.x, a.y - b.y); }

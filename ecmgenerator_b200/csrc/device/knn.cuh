@@ -26,16 +26,35 @@ struct Knn {
         for (int j = 0; j < kK; j++) n += (q[j] >= 0);
         return n;
     }
-    // compare-exchange chain: the candidate sinks to its place, the displaced entry is carried on
-    __device__ __forceinline__ void insert(float cd, int cq, const int* __restrict__ s_slot) {
-#pragma unroll
+    // compare-exchange chain: the candidate sinks to its place, the displaced entry is carried on.
+    // Exact distance ties (ordered by slot id) take the out-of-line path: they are rare and keeping
+    // them out of the inlined chain keeps the hot loop small (the kernels are I-cache bound).
+    __device__ __noinline__ void insert_with_ties(float cd, int cq, const int* __restrict__ s_slot) {
+        bool placed = false;  // once the candidate sits, the displaced entries just shift down
         for (int j = 0; j < kK; j++) {
-            bool less = cd < d[j];
-            if (cd == d[j] && q[j] >= 0) less = __ldg(&s_slot[cq]) < __ldg(&s_slot[q[j]]);  // tie: lower slot id first
+            bool less = placed || cd < d[j];
+            if (!placed && cd == d[j] && q[j] >= 0) less = __ldg(&s_slot[cq]) < __ldg(&s_slot[q[j]]);  // tie: lower slot id first
+            placed = less;
             if (less) {
                 float td = d[j]; d[j] = cd; cd = td;
                 int tq = q[j]; q[j] = cq; cq = tq;
             }
+        }
+    }
+    __device__ __forceinline__ void insert(float cd, int cq, const int* __restrict__ s_slot) {
+        const bool tie = (cd == d[0]) | (cd == d[1]) | (cd == d[2]) | (cd == d[3]) | (cd == d[4]);
+        if (tie) { insert_with_ties(cd, cq, s_slot); return; }
+        bool placed = false;
+#pragma unroll
+        for (int j = 0; j < kK; j++) {
+            const bool less = placed | (cd < d[j]);
+            placed = less;
+            const float td = less ? d[j] : cd;
+            const int tq = less ? q[j] : cq;
+            d[j] = less ? cd : d[j];
+            q[j] = less ? cq : q[j];
+            cd = td;
+            cq = tq;
         }
     }
     __device__ __forceinline__ void consider(v2 self, int cand, const GridView& g) {
@@ -46,31 +65,34 @@ struct Knn {
     }
 };
 
-// Scans the sorted range of cells [cxa, cxb] of row cy.
-__device__ __forceinline__ void knn_scan_row(Knn& k, v2 self, const GridView& g, int cy, int cxa, int cxb) {
-    int a = __ldg(&g.cell_start[cy * g.w + cxa]);
-    int b = __ldg(&g.cell_start[cy * g.w + cxb + 1]);
-    for (int c = a; c < b; c++) k.consider(self, c, g);
-}
-
-// Returns true when the result is proven exact within `max_ring` rings.
+// Returns true when the result is proven exact within `max_ring` rings.  Ring r is walked as a list
+// of row pieces so that there is ONE candidate loop in the code: r = 1: the own row, the row below,
+// the row above (3 cells each); r > 1: the two full outer rows, then the two outer cells of every
+// row in between.
 __device__ __forceinline__ bool knn_grid(Knn& k, v2 self, const GridView& g, int max_ring) {
     int cx, cy;
     g.cell_of(self, cx, cy);
     k.init();
     for (int r = 1; r <= max_ring; r++) {
-        int xa = max(cx - r, 0), xb = min(cx + r, g.w - 1);
-        int ya = max(cy - r, 0), yb = min(cy + r, g.h - 1);
-        if (r == 1) {
-            for (int y = ya; y <= yb; y++) knn_scan_row(k, self, g, y, xa, xb);
-        } else {
-            if (cy - r >= 0) knn_scan_row(k, self, g, cy - r, xa, xb);
-            if (cy + r < g.h) knn_scan_row(k, self, g, cy + r, xa, xb);
-            int y0 = max(cy - r + 1, 0), y1 = min(cy + r - 1, g.h - 1);
-            for (int y = y0; y <= y1; y++) {
-                if (cx - r >= 0) knn_scan_row(k, self, g, y, cx - r, cx - r);
-                if (cx + r < g.w) knn_scan_row(k, self, g, y, cx + r, cx + r);
+        const int xa = max(cx - r, 0), xb = min(cx + r, g.w - 1);
+        const int ya = max(cy - r, 0), yb = min(cy + r, g.h - 1);
+        const int pieces = r == 1 ? 3 : 2 + 2 * (2 * r - 1);
+        for (int s = 0; s < pieces; s++) {
+            int y, x0, x1;
+            if (r == 1) {  // own row first: near candidates tighten the 5th distance early
+                y = s == 0 ? cy : (s == 1 ? cy - 1 : cy + 1);
+                x0 = xa; x1 = xb;
+            } else if (s < 2) {
+                y = s == 0 ? cy - r : cy + r;
+                x0 = xa; x1 = xb;
+            } else {
+                y = cy - r + 1 + ((s - 2) >> 1);
+                x0 = x1 = ((s - 2) & 1) ? cx + r : cx - r;
             }
+            if (y < 0 || y >= g.h || x0 < 0 || x1 >= g.w) continue;
+            const int a = __ldg(&g.cell_start[y * g.w + x0]);
+            const int b = __ldg(&g.cell_start[y * g.w + x1 + 1]);
+            for (int c = a; c < b; c++) k.consider(self, c, g);
         }
         // Every agent not scanned yet lies outside the block [xa..xb] x [ya..yb] (agents beyond the
         // grid are clamped into border cells, and a block side on the grid border extends to infinity),

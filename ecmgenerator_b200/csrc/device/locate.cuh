@@ -40,20 +40,29 @@ __device__ __forceinline__ bool cell_contains(const EcmView& ecm, int c, v2 p) {
 
 // ECMCellCollection::PointLocationQueryLinear (ECMCellCollection.cpp:57-90): lowest-index
 // containing cell, -1 if none.  The bin list is ascending and a superset of the cells that can
-// contain a point of the bin, so the first hit equals the linear scan's.
-__device__ __forceinline__ int find_cell(const EcmView& ecm, const BinView& bins, v2 p) {
-    int b = bins.bin_of(p);
-    if (b >= 0) {
-        int i0 = __ldg(&bins.cell_start[b]), i1 = __ldg(&bins.cell_start[b + 1]);
-        for (int i = i0; i < i1; i++) {
-            int c = __ldg(&bins.cell_items[i]);
-            if (cell_contains(ecm, c, p)) return c;
-        }
-        return -1;
+// contain a point of the bin, so the first hit equals the linear scan's.  kSync: see warp_max_trip.
+template <bool kSync>
+__device__ __forceinline__ int find_cell(const EcmView& ecm, const BinView& bins, v2 p, bool valid = true) {
+    int res = -1;
+    const int b = valid ? bins.bin_of(p) : 0;
+    int i0 = 0, cnt = 0;
+    if (valid && b >= 0) {
+        i0 = __ldg(&bins.cell_start[b]);
+        cnt = __ldg(&bins.cell_start[b + 1]) - i0;
     }
-    for (int c = 0; c < 2 * ecm.n_edges; c++)
-        if (cell_contains(ecm, c, p)) return c;
-    return -1;
+    const int trips = warp_max_trip<kSync>(cnt);
+    for (int k = 0; k < trips; k++) {
+        warp_align<kSync>();
+        if (k < cnt && res < 0) {
+            const int c = __ldg(&bins.cell_items[i0 + k]);
+            if (cell_contains(ecm, c, p)) res = c;
+        }
+    }
+    if (valid && b < 0) {  // outside the static grid: the reference's linear scan
+        for (int c = 0; c < 2 * ecm.n_edges && res < 0; c++)
+            if (cell_contains(ecm, c, p)) res = c;
+    }
+    return res;
 }
 
 // MathUtility::GetRayToLineSegmentIntersection (UtilityFunctions.cpp:323-349).
@@ -94,49 +103,114 @@ __device__ __forceinline__ bool retract_in_cell(const EcmView& ecm, int cell, v2
     return ray_segment(loc, ray, p1, p2, out);
 }
 
+// One path segment a -> b against the clearance disk (R, c2): IRMPathFollower.cpp:54-112.
+// Returns true if the reference would have written outPoint for this segment; line_hit is set when
+// the segment's infinite line meets the disk (`success = true`, IRMPathFollower.cpp:70).
+__device__ __forceinline__ bool irm_segment(v2 a, v2 b, v2 R, float c2, v2& out, bool& line_hit) {
+    v2 p1 = vsub(a, R), p2 = vsub(b, R);
+    v2 ed = vsub(p2, p1);
+    float el2 = vlen2(ed);
+    float det = vdet(p1, p2);
+    float disc = c2 * el2 - det * det;
+    if (disc < kEpsilon) return false;
+    line_hit = true;
+    float dys = ed.y < 0.0f ? -1.0f : 1.0f;
+    float sq = sqrtf(disc);
+    v2 i1 = V((det * ed.y + dys * ed.x * sq) / el2, (-det * ed.x + fabsf(ed.y) * sq) / el2);
+    v2 i2 = V((det * ed.y - dys * ed.x * sq) / el2, (-det * ed.x - fabsf(ed.y) * sq) / el2);
+    v2 g1 = vadd(p1, R), g2 = vadd(p2, R), gi1 = vadd(i1, R), gi2 = vadd(i2, R);
+    v2 edge = vsub(g2, g1);
+    float t1 = vdot(vsub(gi1, g1), edge) / el2;
+    float t2 = vdot(vsub(gi2, g1), edge) / el2;
+    float maxT = -1.0f;
+    bool has = false;
+    if (t1 >= 0.0f && t1 <= 1.0f) { out = gi1; maxT = t1; has = true; }
+    if (t2 >= 0.0f && t2 <= 1.0f) { if (t2 > maxT) out = gi2; has = true; }
+    return has;
+}
+
+constexpr int kPathBlock = 8;  // segments per bounding-box block (paths start on multiples of 8 points in the pool)
+
 // IRMPathFollower::FindAttractionPoint (IRMPathFollower.cpp:14-115).  `out` is written exactly
 // where the reference writes outPoint; `cell` receives the located cell (-1: location failed).
+//
+// The reference evaluates every path segment in order and lets later segments overwrite earlier
+// ones, i.e. the result is the output of the LAST segment that produces one.  We scan from the end
+// and stop at the first producing segment; blocks of 8 segments whose (padded) bounding box the
+// clearance disk does not touch cannot produce an output and are skipped unread.  Only if no
+// segment produces an output does `success` depend on the line tests of all segments, which a
+// plain second pass then evaluates (rare: the agent was pushed off its path).
+//
+// kSync: called by the whole warp (lanes without a query pass valid = false); the segment scan is
+// a warp-synchronous state machine: in every step each still-searching lane evaluates its next
+// candidate segment, so the expensive evaluation runs in lock-step instead of lane by lane.
+template <bool kSync>
 __device__ __forceinline__ bool find_attraction_point(const EcmView& ecm, const BinView& bins, v2 position,
-                                                      const float2* __restrict__ path, int np, v2& out, int& cell) {
-    cell = find_cell(ecm, bins, position);
-    if (cell < 0) return false;
-    v2 R;
-    if (!retract_in_cell(ecm, cell, position, R)) return false;
-    const float2* cl = ecm.edge_cl + 4 * (cell >> 1);
-    v2 obstA = __ldg(&cl[0]), obstB = __ldg(&cl[2]);  // always the LEFT pair (IRMPathFollower.cpp:31-34)
-    v2 closest = closest_on_segment(R, obstA, obstB);
-    float clearance = vlen(vsub(R, closest));
-    float c2 = clearance * clearance;
-    v2 goal = path[np - 1];
-    if (vlen2(vsub(goal, R)) < c2) {
-        out = goal;
-        return true;
+                                                      const float2* __restrict__ path, const float4* __restrict__ bbox, int np, v2 goal,
+                                                      v2& out, int& cell, bool valid = true) {
+    cell = find_cell<kSync>(ecm, bins, position, valid);
+    bool go = valid && cell >= 0;
+    bool result = false;
+    v2 R = V(0.0f, 0.0f);
+    float c2 = 0.0f;
+    if (go) go = retract_in_cell(ecm, cell, position, R);
+    if (go) {
+        const float2* cl = ecm.edge_cl + 4 * (cell >> 1);
+        v2 obstA = __ldg(&cl[0]), obstB = __ldg(&cl[2]);  // always the LEFT pair (IRMPathFollower.cpp:31-34)
+        v2 closest = closest_on_segment(R, obstA, obstB);
+        float clearance = vlen(vsub(R, closest));
+        c2 = clearance * clearance;
+        if (vlen2(vsub(goal, R)) < c2) {
+            out = goal;
+            result = true;
+            go = false;
+        }
     }
-    bool success = false;
-    v2 a = path[0];
-    for (int i = 0; i < np - 1; i++) {
-        v2 b = path[i + 1];
-        v2 p1 = vsub(a, R), p2 = vsub(b, R);
-        a = b;
-        v2 ed = vsub(p2, p1);
-        float el2 = vlen2(ed);
-        float det = vdet(p1, p2);
-        float disc = c2 * el2 - det * det;
-        if (disc < kEpsilon) continue;
-        success = true;
-        float dys = ed.y < 0.0f ? -1.0f : 1.0f;
-        float sq = sqrtf(disc);
-        v2 i1 = V((det * ed.y + dys * ed.x * sq) / el2, (-det * ed.x + fabsf(ed.y) * sq) / el2);
-        v2 i2 = V((det * ed.y - dys * ed.x * sq) / el2, (-det * ed.x - fabsf(ed.y) * sq) / el2);
-        v2 g1 = vadd(p1, R), g2 = vadd(p2, R), gi1 = vadd(i1, R), gi2 = vadd(i2, R);
-        v2 edge = vsub(g2, g1);
-        float t1 = vdot(vsub(gi1, g1), edge) / el2;
-        float t2 = vdot(vsub(gi2, g1), edge) / el2;
-        float maxT = -1.0f;
-        if (t1 >= 0.0f && t1 <= 1.0f) { out = gi1; maxT = t1; }
-        if (t2 >= 0.0f && t2 <= 1.0f) { if (t2 > maxT) out = gi2; }
+    const int nseg = np - 1;
+    int b = go ? (nseg + kPathBlock - 1) / kPathBlock : 0;  // blocks still to look at
+    int i = 0, i0 = 1;                                      // i < i0: fetch the next overlapping block
+    bool found = false, line_hit = false, active = go;
+    v2 pb = V(0.0f, 0.0f);
+    while (kSync ? __any_sync(0xffffffffu, active) : active) {
+        if (active) {
+            if (i < i0) {
+                for (;;) {
+                    if (--b < 0) break;
+                    const float4 bb = __ldg(&bbox[b]);
+                    const float dx = fmaxf(fmaxf(bb.x - R.x, R.x - bb.z), 0.0f), dy = fmaxf(fmaxf(bb.y - R.y, R.y - bb.w), 0.0f);
+                    if (!(dx * dx + dy * dy > c2)) break;  // bbox is padded on the host: conservative
+                }
+                if (b < 0) {
+                    active = false;
+                } else {
+                    i0 = b * kPathBlock;
+                    i = min(i0 + kPathBlock, nseg) - 1;
+                    pb = path[i + 1];
+                }
+            }
+            if (active) {
+                const v2 pa = path[i];
+                if (irm_segment(pa, pb, R, c2, out, line_hit)) { found = true; active = false; }
+                pb = pa;
+                i--;
+            }
+        }
     }
-    return success;
+    if (go) {
+        if (found || line_hit) {
+            result = true;  // line_hit without a point: outPoint stays untouched (Simulator.cpp:570-577)
+        } else {            // no output anywhere: `success` = any segment line meets the disk, over ALL segments
+            v2 pa = path[0];
+            for (int k = 0; k < nseg && !result; k++) {
+                const v2 pn = path[k + 1];
+                const v2 p1 = vsub(pa, R), p2 = vsub(pn, R);
+                const float el2 = vlen2(vsub(p2, p1)), det = vdet(p1, p2);
+                if (!(c2 * el2 - det * det < kEpsilon)) result = true;
+                pa = pn;
+            }
+        }
+    }
+    return result;
 }
 
 }  // namespace ecm

@@ -34,16 +34,24 @@ __device__ __forceinline__ bool obstacle_in_range(const ObstView& ob, int o, v2 
 
 // FindNearestObstacles through the static bins; ids in (obstacle, vertex) order.  Returns the
 // number found (may exceed cap: the excess is dropped and the caller flags OBST_OVERFLOW).
-__device__ __forceinline__ int find_obstacles(const ObstView& ob, const BinView& bins, v2 a, float range2, int* out, int cap) {
+template <bool kSync>
+__device__ __forceinline__ int find_obstacles(const ObstView& ob, const BinView& bins, v2 a, float range2, int* out, int cap, bool valid = true) {
     int n = 0;
-    int b = bins.bin_of(a);
-    if (b >= 0) {
-        int i0 = __ldg(&bins.obst_start[b]), i1 = __ldg(&bins.obst_start[b + 1]);
-        for (int i = i0; i < i1; i++) {
-            int o = __ldg(&bins.obst_items[i]);
+    const int b = valid ? bins.bin_of(a) : 0;
+    int i0 = 0, cnt = 0;
+    if (valid && b >= 0) {
+        i0 = __ldg(&bins.obst_start[b]);
+        cnt = __ldg(&bins.obst_start[b + 1]) - i0;
+    }
+    const int trips = warp_max_trip<kSync>(cnt);
+    for (int k = 0; k < trips; k++) {
+        warp_align<kSync>();
+        if (k < cnt) {
+            int o = __ldg(&bins.obst_items[i0 + k]);
             if (obstacle_in_range(ob, o, a, range2)) { if (n < cap) out[n] = o; n++; }
         }
-    } else {
+    }
+    if (valid && b < 0) {  // outside the static grid: exhaustive scan (exactness over speed)
         for (int o = 0; o < ob.n; o++)
             if (obstacle_in_range(ob, o, a, range2)) { if (n < cap) out[n] = o; n++; }
     }
@@ -189,45 +197,57 @@ __device__ __forceinline__ Cons agent_constraint(v2 position, v2 velocity, float
     return cmake(vadd(velocity, vmul(U, 0.5f)), vright(rn));
 }
 
-// ORCA::RandomizedLP (ORCA.cpp:428-587).  Returns n on success, else the failing index.
+// ORCA::RandomizedLP (ORCA.cpp:428-587).  Returns n on success, else the failing index.  The
+// arithmetic and its order are the reference's; only the control flow is flattened: a failure is
+// recorded in `result` instead of returning from inside the loops (outV stays untouched from then on).
+template <bool kSync>
 __device__ __forceinline__ int randomized_lp(const Cons* cs, int n, v2 opt, float maxSpeed, bool useDirOpt, v2& outV) {
     if (useDirOpt) outV = vmul(opt, maxSpeed);
     else if (vlen(opt) > maxSpeed) outV = vmul(vnormalized(opt), maxSpeed);
     else outV = opt;
-    for (int i = 0; i < n; i++) {
+    int result = n;
+    const int trips = warp_max_trip<kSync>(n);
+    for (int i = 0; i < trips; i++) {
+        warp_align<kSync>();
+        if (i >= n || result != n) continue;
         const Cons h = cs[i];
         if (ccontains(h, outV)) continue;
-        v2 dir = vright(cn(h));
-        float dpd = vdot(dir, cp(h));
-        float disc = dpd * dpd + maxSpeed * maxSpeed - vdot(cp(h), cp(h));
-        if (disc <= 0.0f) return i;
-        float dsq = sqrtf(disc);
-        float left = -dpd - dsq;
-        float right = -dpd + dsq;
-        for (int j = 0; j < i; j++) {
-            const Cons hj = cs[j];
-            float den = vdet(dir, vright(cn(hj)));
-            float num = vdet(vright(cn(hj)), vsub(cp(h), cp(hj)));
-            if (fabsf(den) <= kEpsilon) {
-                if (num < 0.0f) return i;
-                continue;
+        const v2 dir = vright(cn(h));
+        const float dpd = vdot(dir, cp(h));
+        const float disc = dpd * dpd + maxSpeed * maxSpeed - vdot(cp(h), cp(h));
+        bool bad = disc <= 0.0f;  // `return i` (ORCA.cpp:499-503)
+        float left = 0.0f, right = 0.0f;
+        if (!bad) {
+            const float dsq = sqrtf(disc);
+            left = -dpd - dsq;
+            right = -dpd + dsq;
+            for (int j = 0; j < i; j++) {  // same i for every lane in here: lock-step
+                const Cons hj = cs[j];
+                const float den = vdet(dir, vright(cn(hj)));
+                const float num = vdet(vright(cn(hj)), vsub(cp(h), cp(hj)));
+                if (fabsf(den) <= kEpsilon) {
+                    if (num < 0.0f) bad = true;  // `return i` (ORCA.cpp:526-533)
+                    continue;
+                }
+                const float t = num / den;
+                if (den >= 0.0f) right = (t < right) ? t : right;  // std::min(right, t)
+                else left = (left < t) ? t : left;                 // std::max(left, t)
+                if (left > right) bad = true;                      // `return i` (ORCA.cpp:546-548); monotone, so order-free
             }
-            const float t = num / den;
-            if (den >= 0.0f) right = (t < right) ? t : right;  // std::min(right, t)
-            else left = (left < t) ? t : left;                 // std::max(left, t)
-            if (left > right) return i;
         }
-        if (useDirOpt) {
+        if (bad) {
+            result = i;
+        } else if (useDirOpt) {
             if (vdot(opt, dir) > 0.0f) outV = vadd(cp(h), vmul(dir, right));
             else outV = vadd(cp(h), vmul(dir, left));
         } else {
-            float t = vdot(dir, vsub(opt, cp(h)));
+            const float t = vdot(dir, vsub(opt, cp(h)));
             if (t < left) outV = vadd(cp(h), vmul(dir, left));
             else if (t > right) outV = vadd(cp(h), vmul(dir, right));
             else outV = vadd(cp(h), vmul(dir, t));
         }
     }
-    return n;
+    return result;
 }
 
 // ORCA::RandomizedLP3D (ORCA.cpp:592-669).  `proj` is scratch for the projected constraints.
@@ -253,7 +273,7 @@ __device__ __forceinline__ void randomized_lp3d(int nObst, const Cons* cs, int t
             proj[np++] = cmake(pt, vnormalized(vsub(cn(cj), cn(ci))));
         }
         const v2 temp = outV;
-        if (randomized_lp(proj, np, cn(ci), maxSpeed, true, outV) < np) outV = temp;
+        if (randomized_lp<false>(proj, np, cn(ci), maxSpeed, true, outV) < np) outV = temp;
         maxPen = vdet(dir, vsub(cp(ci), outV));
     }
 }
@@ -264,29 +284,46 @@ struct OrcaResult {
 };
 
 // ORCA::GetVelocity after the neighbour query (ORCA.cpp:23-56).  nb_q[] are snapshot indices.
+// kSync: called by all 32 lanes of the warp (lanes without an agent pass valid = false).
+template <bool kSync>
 __device__ __forceinline__ OrcaResult orca_velocity(const ObstView& ob, const BinView& bins, const GridView& g, v2 position, v2 velocity,
-                                                    float clearance, float maxSpeed, v2 prefVel, int n_nb, const int* nb_q, float stepSize) {
+                                                    float clearance, float maxSpeed, v2 prefVel, int n_nb, const int* nb_q, float stepSize,
+                                                    bool valid = true) {
     OrcaResult res;
     res.status = 0u;
+    res.velocity = V(0.0f, 0.0f);
     Cons cs[kMaxCons];
-    Cons proj[kMaxCons];
     int on[kMaxObstNeighbors];
+    if (!valid) n_nb = 0;
     float range = kLookAhead * maxSpeed + clearance;  // ORCA.cpp:27
-    int n_on = find_obstacles(ob, bins, position, range * range, on, kMaxObstNeighbors);
+    int n_on = find_obstacles<kSync>(ob, bins, position, range * range, on, kMaxObstNeighbors, valid);
     if (n_on > kMaxObstNeighbors) { n_on = kMaxObstNeighbors; res.status |= 16u; }
     int nc = 0;
-    for (int i = 0; i < n_on; i++) {
-        Cons c;
-        if (obstacle_constraint(ob, on[i], position, velocity, clearance, c)) cs[nc++] = c;
+    {
+        const int trips = warp_max_trip<kSync>(n_on);
+        for (int i = 0; i < trips; i++) {
+            warp_align<kSync>();
+            if (i < n_on) {
+                Cons c;
+                if (obstacle_constraint(ob, on[i], position, velocity, clearance, c)) cs[nc++] = c;
+            }
+        }
     }
     const int nObst = nc;
-    for (int i = 0; i < n_nb; i++) {
-        int q = nb_q[i];
-        cs[nc++] = agent_constraint(position, velocity, clearance, __ldg(&g.s_pos[q]), __ldg(&g.s_vel[q]), __ldg(&g.s_rad[q]), stepSize);
+    {
+        const int trips = warp_max_trip<kSync>(n_nb);
+        for (int i = 0; i < trips; i++) {
+            warp_align<kSync>();
+            if (i < n_nb) {
+                int q = nb_q[i];
+                cs[nc++] = agent_constraint(position, velocity, clearance, __ldg(&g.s_pos[q]), __ldg(&g.s_vel[q]), __ldg(&g.s_rad[q]), stepSize);
+            }
+        }
     }
     v2 out = V(0.0f, 0.0f);
-    int failed = randomized_lp(cs, nc, prefVel, maxSpeed, false, out);
-    if (failed < nc) {
+    int failed = randomized_lp<kSync>(cs, nc, prefVel, maxSpeed, false, out);
+    if (failed < nc) {  // rare (dense crowds): stays per-lane
+        Cons proj[kMaxCons];
         res.status |= 64u;
         randomized_lp3d(nObst, cs, nc, maxSpeed, failed, out, proj);
     }

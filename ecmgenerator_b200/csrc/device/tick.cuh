@@ -33,6 +33,13 @@ enum Counter {
     C_COUNT = 16
 };
 
+// Path header of a slot: `off` is a multiple of 8 points (blocks of 8 segments share bbox index off/8 + b);
+// the goal (last point, Simulator.cpp:554) is duplicated here so the arrival test touches no polyline data.
+struct PathHdr {
+    int off, len;
+    float gx, gy;
+};
+
 // Mutable per-slot agent components (structure of arrays, indexed by slot = global agent id).
 struct AgentArrays {
     float2* pos;          // Simulator::m_Positions
@@ -48,8 +55,9 @@ struct AgentArrays {
     int* cell;            // located ECM cell of the last tick
     int* nbr;             // [5*slot] neighbour slot ids of the last tick (optional)
     int* nbr_cnt;
-    const int2* path_hdr;   // (offset, length) into path_pool
+    const PathHdr* path_hdr;  // (offset, length, goal) into path_pool
     const float2* path_pool;
+    const float4* path_bbox;  // [pool/8] padded bounding box of each block of 8 segments
 };
 
 struct TickScratch {
@@ -192,19 +200,22 @@ __global__ void __launch_bounds__(128) k_attract(TickView t) {
     const int n = *t.n_sorted_ptr;
     const bool valid = p < n && !t.sc.s_ghost[p];
     unsigned st = 0u;
+    int slot = 0, np = 2, cell = -2;
+    v2 pos = V(0.0f, 0.0f), goal = V(0.0f, 0.0f), attr = V(0.0f, 0.0f);
+    const float2* path = t.ag.path_pool;
+    const float4* bbox = t.ag.path_bbox;
+    bool have = false, alive = true, need_irm = false;
     if (valid) {
-        const int slot = t.sc.s_slot[p];
-        const v2 pos = t.sc.s_pos[p];
-        const int2 hdr = t.ag.path_hdr[slot];
-        const float2* path = t.ag.path_pool + hdr.x;
-        const int np = hdr.y;
-        const v2 goal = path[np - 1];
+        slot = t.sc.s_slot[p];
+        pos = t.sc.s_pos[p];
+        const PathHdr hdr = t.ag.path_hdr[slot];
+        path += hdr.off;
+        bbox += hdr.off >> 3;
+        np = hdr.len;
+        goal = V(hdr.gx, hdr.gy);
         // SquareDistance(float,float,float,float) (UtilityFunctions.cpp:43-49)
         const float ddx = pos.x - goal.x, ddy = pos.y - goal.y;
         const float dist = ddx * ddx + ddy * ddy;
-        int cell = -2;
-        v2 attr;
-        bool have = false, alive = true;
         if (dist < 20.0f * 20.0f) {  // arrival radius (Simulator.cpp:543, 557-562)
             attr = goal;
             have = true;
@@ -217,8 +228,15 @@ __global__ void __launch_bounds__(128) k_attract(TickView t) {
                 t.sc.ev_destroyed[e] = slot;
             }
         } else {
-            v2 ap = V(0.0f, 0.0f);  // `Point attractionPoint;` is (0,0) (Simulator.cpp:570)
-            if (find_attraction_point(t.ecm, t.bins, pos, path, np, ap, cell)) {
+            need_irm = true;
+        }
+    }
+    __syncwarp();
+    v2 ap = V(0.0f, 0.0f);  // `Point attractionPoint;` is (0,0) (Simulator.cpp:570)
+    const bool ok = find_attraction_point<true>(t.ecm, t.bins, pos, path, bbox, np, goal, ap, cell, need_irm);
+    if (valid) {
+        if (need_irm) {
+            if (ok) {
                 attr = ap;
                 have = true;
             } else {
@@ -230,6 +248,8 @@ __global__ void __launch_bounds__(128) k_attract(TickView t) {
                     t.sc.ev_replan[e] = slot;
                 }
             }
+        } else {
+            cell = -2;
         }
         if (have) t.ag.attraction[slot] = attr;
         else attr = t.ag.attraction[slot];  // previous attraction point is kept (Simulator.cpp:573-587)
@@ -252,18 +272,22 @@ __global__ void __launch_bounds__(128) k_attract(TickView t) {
     }
 }
 
-// ORCA + integration for one agent whose neighbour list is known.
-__device__ __forceinline__ unsigned finish_agent(const TickView& t, int p, const Knn& k) {
-    const int slot = t.sc.s_slot[p];
-    const v2 pos = t.sc.s_pos[p], vel = t.sc.s_vel[p];
-    const float rad = t.sc.s_rad[p], spd = t.sc.s_spd[p];
-    const int n_nb = k.count();
+// ORCA + integration for one agent whose neighbour list is known.  kSync: convergent call by the
+// whole warp, lanes without work pass valid = false.
+template <bool kSync>
+__device__ __forceinline__ unsigned finish_agent(const TickView& t, int p, const Knn& k, bool valid = true) {
+    const int slot = valid ? t.sc.s_slot[p] : 0;
+    const v2 pos = valid ? t.sc.s_pos[p] : V(0.0f, 0.0f), vel = valid ? t.sc.s_vel[p] : V(0.0f, 0.0f);
+    const float rad = valid ? t.sc.s_rad[p] : 0.0f, spd = valid ? t.sc.s_spd[p] : 0.0f;
+    const v2 pref = valid ? t.sc.s_pref[p] : V(0.0f, 0.0f);
+    const int n_nb = valid ? k.count() : 0;
     unsigned extra = 0u;
-    if (t.strips) {  // did the search ball stay inside what this rank can see?
+    if (valid && t.strips) {  // did the search ball stay inside what this rank can see?
         const float r5 = n_nb == kK ? sqrtf(k.d[kK - 1]) * 1.001f : CUDART_INF_F;
         if (pos.x - r5 < t.cover_lo || pos.x + r5 >= t.cover_hi) extra = 128u;
     }
-    OrcaResult r = orca_velocity(t.obst, t.bins, t.grid, pos, vel, rad, spd, t.sc.s_pref[p], n_nb, k.q, t.step);
+    OrcaResult r = orca_velocity<kSync>(t.obst, t.bins, t.grid, pos, vel, rad, spd, pref, n_nb, k.q, t.step, valid);
+    if (!valid) return 0u;
     // force = v_orca - v (Simulator.cpp:676-677)
     const v2 f = V(r.velocity.x - vel.x, r.velocity.y - vel.y);
     // v += force * (1/mass) * step (Simulator.cpp:622-633); p += v * step (Simulator.cpp:603-604)
@@ -285,17 +309,20 @@ __global__ void __launch_bounds__(128) k_orca(TickView t) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = *t.n_sorted_ptr;
     unsigned st = 0u;
-    if (p < n && !t.sc.s_ghost[p] && t.sc.s_alive[p]) {
-        Knn k;
-        if (knn_grid(k, t.sc.s_pos[p], t.grid, t.max_ring)) {
-            st = finish_agent(t, p, k);
-        } else {
+    const bool mine = p < n && !t.sc.s_ghost[p] && t.sc.s_alive[p];
+    Knn k;
+    bool found = false;
+    if (mine) {
+        found = knn_grid(k, t.sc.s_pos[p], t.grid, t.max_ring);
+        if (!found) {
             st = 32u;
             int e = (int)atomicAdd(&t.sc.counters[C_FALLBACK_N], 1ull);
             t.sc.fb_list[e] = p;
         }
-        if (st) t.ag.status[t.sc.s_slot[p]] |= st;
     }
+    __syncwarp();
+    st |= finish_agent<true>(t, p, k, mine && found);
+    if (st) t.ag.status[t.sc.s_slot[p]] |= st;
     unsigned m_ovf = __ballot_sync(0xffffffffu, (st & 16u) != 0u);
     unsigned m_lp3 = __ballot_sync(0xffffffffu, (st & 64u) != 0u);
     unsigned m_fb = __ballot_sync(0xffffffffu, (st & 32u) != 0u);
@@ -322,7 +349,7 @@ __global__ void __launch_bounds__(128) k_fallback(TickView t, int mode) {
         knn_exhaustive(k, t.sc.s_pos[p], g);
         if (lane == 0) {
             if (mode == 0) {
-                unsigned st = finish_agent(t, p, k);
+                unsigned st = finish_agent<false>(t, p, k);
                 if (st & 16u) atomicAdd(&t.sc.counters[C_TOTAL_OBST_OVF], 1ull);
                 if (st & 64u) atomicAdd(&t.sc.counters[C_TOTAL_LP3D], 1ull);
                 if (st & 128u) atomicAdd(&t.sc.counters[C_TOTAL_HALO_MISS], 1ull);
@@ -341,7 +368,7 @@ __global__ void __launch_bounds__(128) k_fallback(TickView t, int mode) {
 // Query kernels (ecmgpu_locate / ecmgpu_retract / ecmgpu_find_neighbors / ecmgpu_find_obstacles)
 __global__ void k_locate(EcmView ecm, BinView bins, int n, const float2* __restrict__ xy, int* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = find_cell(ecm, bins, xy[i]);
+    if (i < n) out[i] = find_cell<false>(ecm, bins, xy[i]);
 }
 
 __global__ void k_retract(EcmView ecm, BinView bins, int n, const float2* __restrict__ xy, unsigned char* __restrict__ ok,
@@ -349,7 +376,7 @@ __global__ void k_retract(EcmView ecm, BinView bins, int n, const float2* __rest
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     v2 p = xy[i], r = V(0.0f, 0.0f);
-    int c = find_cell(ecm, bins, p);
+    int c = find_cell<false>(ecm, bins, p);
     bool good = c >= 0 && retract_in_cell(ecm, c, p, r);
     ok[i] = good ? 1 : 0;
     out[i] = r;
@@ -373,7 +400,7 @@ __global__ void __launch_bounds__(128) k_knn_query(TickView t) {
 }
 
 __global__ void k_find_obstacles(ObstView ob, BinView bins, float2 pos, float range2, int* out, int cap, int* out_n) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *out_n = find_obstacles(ob, bins, pos, range2, out, cap);
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out_n = find_obstacles<false>(ob, bins, pos, range2, out, cap);
 }
 
 }  // namespace ecm

@@ -75,11 +75,13 @@ struct ecmgpu_sim {
     DevBuf<unsigned char> d_active, d_replan_pending;
     DevBuf<unsigned> d_status;
     DevBuf<int> d_cell, d_nbr, d_nbr_cnt;
-    DevBuf<int2> d_path_hdr;
+    DevBuf<PathHdr> d_path_hdr;
     DevBuf<float2> d_path_pool;
+    DevBuf<float4> d_path_bbox;
     // host mirror of the path pool (append-only, compacted on overflow)
-    std::vector<int2> h_path_hdr;
-    std::vector<float2> h_path_pool;
+    std::vector<PathHdr> h_path_hdr;
+    std::vector<float2> h_path_pool;  // every path starts on a multiple of 8 points
+    std::vector<float4> h_path_bbox;  // [h_path_pool.size()/8 rounded up]
     size_t pool_uploaded = 0;  // prefix of h_path_pool already resident on the device
     int n_slots = 0;
 
@@ -358,6 +360,7 @@ TickView make_view(ecmgpu_sim* s) {
     t.ag.nbr_cnt = s->d_nbr_cnt.p;
     t.ag.path_hdr = s->d_path_hdr.p;
     t.ag.path_pool = s->d_path_pool.p;
+    t.ag.path_bbox = s->d_path_bbox.p;
     t.sc.key = s->d_key.p;
     t.sc.rank = s->d_rank.p;
     t.sc.cell_count = s->d_cell_count.p;
@@ -544,30 +547,63 @@ int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
     return ECMGPU_OK;
 }
 
+// Appends a polyline to the host mirror of the pool (start aligned to 8 points) with the padded
+// bounding boxes of its blocks of 8 segments; compacts the pool when it is full.
+void append_path(ecmgpu_sim* s, int slot, const float2* pts, int n) {
+    while (s->h_path_pool.size() % kPathBlock) s->h_path_pool.push_back(make_float2(0.0f, 0.0f));
+    const int off = (int)s->h_path_pool.size();
+    s->h_path_pool.insert(s->h_path_pool.end(), pts, pts + n);
+    const int nseg = n - 1, nblk = (nseg + kPathBlock - 1) / kPathBlock;
+    s->h_path_bbox.resize((size_t)off / kPathBlock + std::max(nblk, 1), make_float4(0, 0, 0, 0));
+    const float pad = 0.05f;  // far above the rounding of the reference's intersection arithmetic
+    for (int b = 0; b < nblk; b++) {
+        float4 bb = make_float4(3e38f, 3e38f, -3e38f, -3e38f);
+        for (int i = b * kPathBlock; i <= std::min((b + 1) * kPathBlock, nseg); i++) {
+            bb.x = std::min(bb.x, pts[i].x); bb.y = std::min(bb.y, pts[i].y);
+            bb.z = std::max(bb.z, pts[i].x); bb.w = std::max(bb.w, pts[i].y);
+        }
+        bb.x -= pad; bb.y -= pad; bb.z += pad; bb.w += pad;
+        s->h_path_bbox[(size_t)off / kPathBlock + b] = bb;
+    }
+    s->h_path_hdr[slot] = PathHdr{off, n, pts[n - 1].x, pts[n - 1].y};
+}
+
 int upload_path(ecmgpu_sim* s, int slot, const float* xy, int n) {
     if (n < 1) return fail(s, ECMGPU_ERR_INVALID, "path needs at least 1 point");
     const size_t cap = s->d_path_pool.n;
-    if (s->h_path_pool.size() + n > cap) {
+    if (s->h_path_pool.size() + n + kPathBlock > cap) {
         // compact: rebuild the pool from the live headers
-        std::vector<float2> np;
-        np.reserve(cap);
+        std::vector<float2> old;
+        old.swap(s->h_path_pool);
+        s->h_path_bbox.clear();
         for (int i = 0; i < s->n_slots; i++) {
-            int2& h = s->h_path_hdr[i];
-            if (h.y <= 0 || i == slot) { if (i == slot) h = make_int2(0, 0); continue; }
-            int off = (int)np.size();
-            np.insert(np.end(), s->h_path_pool.begin() + h.x, s->h_path_pool.begin() + h.x + h.y);
-            h.x = off;
+            const PathHdr h = s->h_path_hdr[i];
+            if (h.len <= 0 || i == slot) { if (i == slot) s->h_path_hdr[i] = PathHdr{0, 0, 0.0f, 0.0f}; continue; }
+            std::vector<float2> tmp(old.begin() + h.off, old.begin() + h.off + h.len);
+            append_path(s, i, tmp.data(), h.len);
         }
-        if (np.size() + n > cap) return fail(s, ECMGPU_ERR_CAPACITY, "path pool full (raise ecmgpu_params.path_pool_points)");
-        s->h_path_pool.swap(np);
+        if (s->h_path_pool.size() + n + kPathBlock > cap) return fail(s, ECMGPU_ERR_CAPACITY, "path pool full (raise ecmgpu_params.path_pool_points)");
         CUDA_TRY(s, cudaMemcpyAsync(s->d_path_pool.p, s->h_path_pool.data(), sizeof(float2) * s->h_path_pool.size(), cudaMemcpyHostToDevice, s->stream));
-        CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p, s->h_path_hdr.data(), sizeof(int2) * s->n_slots, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_path_bbox.p, s->h_path_bbox.data(), sizeof(float4) * s->h_path_bbox.size(), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p, s->h_path_hdr.data(), sizeof(PathHdr) * s->n_slots, cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(s, cudaStreamSynchronize(s->stream));
         s->pool_uploaded = s->h_path_pool.size();
     }
-    const int off = (int)s->h_path_pool.size();
-    for (int j = 0; j < n; j++) s->h_path_pool.push_back(make_float2(xy[2 * j], xy[2 * j + 1]));
-    s->h_path_hdr[slot] = make_int2(off, n);
+    std::vector<float2> pts(n);
+    for (int j = 0; j < n; j++) pts[j] = make_float2(xy[2 * j], xy[2 * j + 1]);
+    append_path(s, slot, pts.data(), n);
+    return ECMGPU_OK;
+}
+
+// Uploads the part of the pool mirror (points + bboxes) appended since the last upload.
+int flush_pool(ecmgpu_sim* s) {
+    if (s->h_path_pool.size() > s->pool_uploaded) {
+        const size_t a = s->pool_uploaded - s->pool_uploaded % kPathBlock, e = s->h_path_pool.size();
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_path_pool.p + a, s->h_path_pool.data() + a, sizeof(float2) * (e - a), cudaMemcpyHostToDevice, s->stream));
+        const size_t ba = a / kPathBlock, be = s->h_path_bbox.size();
+        if (be > ba) CUDA_TRY(s, cudaMemcpyAsync(s->d_path_bbox.p + ba, s->h_path_bbox.data() + ba, sizeof(float4) * (be - ba), cudaMemcpyHostToDevice, s->stream));
+        s->pool_uploaded = e;
+    }
     return ECMGPU_OK;
 }
 
@@ -626,7 +662,8 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
     ecmgpu_sim* s = new ecmgpu_sim();
     s->prm = *params;
     const size_t n = (size_t)params->max_agents;
-    const size_t pool = params->path_pool_points > 0 ? (size_t)params->path_pool_points : 16 * n;
+    // payload capacity + room for aligning every path start to a block of 8 points
+    const size_t pool = (params->path_pool_points > 0 ? (size_t)params->path_pool_points : 16 * n) + 8 * n + 8;
     auto bad = [&](cudaError_t ce, const char* what) {
         fail(nullptr, ECMGPU_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
         ecmgpu_destroy(s);
@@ -640,7 +677,7 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
     TRY_ALLOC(s->d_active.alloc(n)); TRY_ALLOC(s->d_replan_pending.alloc(n));
     TRY_ALLOC(s->d_status.alloc(n)); TRY_ALLOC(s->d_cell.alloc(n));
     TRY_ALLOC(s->d_nbr.alloc(5 * n)); TRY_ALLOC(s->d_nbr_cnt.alloc(n));
-    TRY_ALLOC(s->d_path_hdr.alloc(n)); TRY_ALLOC(s->d_path_pool.alloc(pool));
+    TRY_ALLOC(s->d_path_hdr.alloc(n)); TRY_ALLOC(s->d_path_pool.alloc(pool)); TRY_ALLOC(s->d_path_bbox.alloc(pool / 8 + 1));
     TRY_ALLOC(s->d_key.alloc(n)); TRY_ALLOC(s->d_rank.alloc(n));
     TRY_ALLOC(s->d_s_pos.alloc(n)); TRY_ALLOC(s->d_s_vel.alloc(n)); TRY_ALLOC(s->d_s_pref.alloc(n));
     TRY_ALLOC(s->d_s_rad.alloc(n)); TRY_ALLOC(s->d_s_spd.alloc(n)); TRY_ALLOC(s->d_s_slot.alloc(n));
@@ -654,13 +691,13 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
     TRY_ALLOC(cudaMemsetAsync(s->d_active.p, 0, n, s->stream)); TRY_ALLOC(cudaMemsetAsync(s->d_replan_pending.p, 0, n, s->stream));
     TRY_ALLOC(cudaMemsetAsync(s->d_status.p, 0, 4 * n, s->stream)); TRY_ALLOC(cudaMemsetAsync(s->d_cell.p, 0xff, 4 * n, s->stream));
     TRY_ALLOC(cudaMemsetAsync(s->d_nbr.p, 0xff, 20 * n, s->stream)); TRY_ALLOC(cudaMemsetAsync(s->d_nbr_cnt.p, 0, 4 * n, s->stream));
-    TRY_ALLOC(cudaMemsetAsync(s->d_path_hdr.p, 0, 8 * n, s->stream));
+    TRY_ALLOC(cudaMemsetAsync(s->d_path_hdr.p, 0, sizeof(PathHdr) * n, s->stream));
     TRY_ALLOC(cudaMemsetAsync(s->d_counters.p, 0, sizeof(unsigned long long) * C_COUNT, s->stream));
     for (auto& ev : s->ev) TRY_ALLOC(cudaEventCreate(&ev));
     for (auto& ev : s->marks) TRY_ALLOC(cudaEventCreate(&ev));
     TRY_ALLOC(cudaStreamSynchronize(s->stream));
 #undef TRY_ALLOC
-    s->h_path_hdr.assign(n, make_int2(0, 0));
+    s->h_path_hdr.assign(n, PathHdr{0, 0, 0.0f, 0.0f});
     s->h_path_pool.reserve(std::min<size_t>(pool, 1 << 20));
     *out = s;
     return ECMGPU_OK;
@@ -676,7 +713,7 @@ void ecmgpu_destroy(ecmgpu_sim* s) {
     s->d_bin_cell_start.free(); s->d_bin_cell_items.free(); s->d_bin_obst_start.free(); s->d_bin_obst_items.free();
     s->d_pos.free(); s->d_vel.free(); s->d_prefvel.free(); s->d_attraction.free(); s->d_force.free();
     s->d_radius.free(); s->d_speed.free(); s->d_active.free(); s->d_replan_pending.free(); s->d_status.free();
-    s->d_cell.free(); s->d_nbr.free(); s->d_nbr_cnt.free(); s->d_path_hdr.free(); s->d_path_pool.free();
+    s->d_cell.free(); s->d_nbr.free(); s->d_nbr_cnt.free(); s->d_path_hdr.free(); s->d_path_pool.free(); s->d_path_bbox.free();
     s->d_key.free(); s->d_rank.free(); s->d_cell_count.free(); s->d_block_sums.free(); s->d_s_slot.free();
     s->d_fb_list.free(); s->d_ev_replan.free(); s->d_ev_destroyed.free(); s->d_s_pos.free(); s->d_s_vel.free();
     s->d_s_pref.free(); s->d_s_rad.free(); s->d_s_spd.free(); s->d_s_alive.free(); s->d_counters.free();
@@ -789,16 +826,12 @@ int ecmgpu_bulk_load(ecmgpu_sim* s, int n, const int* slots, const float* pos_xy
         }
     }
     // path pool tail + touched headers
-    if (s->h_path_pool.size() > s->pool_uploaded) {
-        CUDA_TRY(s, cudaMemcpyAsync(s->d_path_pool.p + s->pool_uploaded, s->h_path_pool.data() + s->pool_uploaded,
-                                    sizeof(float2) * (s->h_path_pool.size() - s->pool_uploaded), cudaMemcpyHostToDevice, s->stream));
-        s->pool_uploaded = s->h_path_pool.size();
-    }
+    { int rc = flush_pool(s); if (rc) return rc; }
     if (contiguous && n > 0) {
-        CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p + first, s->h_path_hdr.data() + first, sizeof(int2) * n, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p + first, s->h_path_hdr.data() + first, sizeof(PathHdr) * n, cudaMemcpyHostToDevice, s->stream));
     } else {
         for (int i = 0; i < n; i++)
-            CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p + slots[i], &s->h_path_hdr[slots[i]], sizeof(int2), cudaMemcpyHostToDevice, s->stream));
+            CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p + slots[i], &s->h_path_hdr[slots[i]], sizeof(PathHdr), cudaMemcpyHostToDevice, s->stream));
     }
     CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     return ECMGPU_OK;
@@ -816,11 +849,9 @@ int ecmgpu_set_path(ecmgpu_sim* s, int slot, const float* path_xy, int n_points)
     CUDA_TRY(s, cudaSetDevice(s->prm.device));
     int rc = upload_path(s, slot, path_xy, n_points);
     if (rc) return rc;
-    const int2 h = s->h_path_hdr[slot];
     const unsigned char zero = 0;
-    CUDA_TRY(s, cudaMemcpyAsync(s->d_path_pool.p + h.x, s->h_path_pool.data() + h.x, sizeof(float2) * h.y, cudaMemcpyHostToDevice, s->stream));
-    s->pool_uploaded = std::max(s->pool_uploaded, (size_t)(h.x + h.y));
-    CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p + slot, &s->h_path_hdr[slot], sizeof(int2), cudaMemcpyHostToDevice, s->stream));
+    { int rc2 = flush_pool(s); if (rc2) return rc2; }
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p + slot, &s->h_path_hdr[slot], sizeof(PathHdr), cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(s, cudaMemcpyAsync(s->d_replan_pending.p + slot, &zero, 1, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     return ECMGPU_OK;
