@@ -32,21 +32,30 @@ template <bool kSync>
 __device__ __forceinline__ void warp_align() {
     if (kSync) __syncwarp();
 }
+// Block-wide phase barrier (kSync kernels only): keeps all warps of a CTA in the same phase of a
+// long kernel so that the CTA's instruction working set is one phase, not the whole kernel
+// (k_orca was instruction-fetch bound: stall_no_instruction 4.9-14.7 per issue, profiles/).
+template <bool kSync>
+__device__ __forceinline__ void phase_barrier() {
+    if (kSync) __syncthreads();
+}
 
 __device__ __forceinline__ v2 V(float x, float y) { return make_float2(x, y); }
 __device__ __forceinline__ v2 vadd(v2 a, v2 b) { return V(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ v2 vsub(v2 a, v2 b) { return V(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ v2 vmul(v2 a, float s) { return V(a.x * s, a.y * s); }
-__device__ __forceinline__ v2 vdiv(v2 a, float s) { return V(a.x / s, a.y / s); }
+// IEEE division / sqrt expand to ~10-instruction sequences each; the three helpers built on them are
+// kept out of line so that their ~40 call sites do not multiply that code (instruction-cache footprint).
+__device__ __noinline__ v2 vdiv(v2 a, float s) { return V(a.x / s, a.y / s); }
 __device__ __forceinline__ float vdot(v2 a, v2 b) { return a.x * b.x + a.y * b.y; }   // UtilityFunctions.cpp:172
 __device__ __forceinline__ float vdet(v2 a, v2 b) { return a.x * b.y - a.y * b.x; }   // UtilityFunctions.cpp:182
 __device__ __forceinline__ float vlen2(v2 a) { return a.x * a.x + a.y * a.y; }        // ECMDataTypes.h:38
-__device__ __forceinline__ float vlen(v2 a) { return sqrtf(a.x * a.x + a.y * a.y); }  // ECMDataTypes.h:33
+__device__ __noinline__ float vlen(v2 a) { return sqrtf(a.x * a.x + a.y * a.y); }  // ECMDataTypes.h:33
 __device__ __forceinline__ v2 vright(v2 a) { return V(a.y, -a.x); }                   // UtilityFunctions.cpp:213
 __device__ __forceinline__ v2 vleft(v2 a) { return V(-a.y, a.x); }                    // UtilityFunctions.cpp:223
 // Vec2::Normalize / Normalized (ECMDataTypes.h:45-60): a zero vector stays zero.
-__device__ __forceinline__ v2 vnormalized(v2 a) {
-    float l = vlen(a);
+__device__ __noinline__ v2 vnormalized(v2 a) {
+    float l = sqrtf(a.x * a.x + a.y * a.y);
     if (l == 0.0f) return a;
     return V(a.x / l, a.y / l);
 }

@@ -251,7 +251,7 @@ __device__ __forceinline__ int randomized_lp(const Cons* cs, int n, v2 opt, floa
 }
 
 // ORCA::RandomizedLP3D (ORCA.cpp:592-669).  `proj` is scratch for the projected constraints.
-__device__ __forceinline__ void randomized_lp3d(int nObst, const Cons* cs, int total, float maxSpeed, int failed, v2& outV, Cons* proj) {
+__device__ __noinline__ void randomized_lp3d(int nObst, const Cons* cs, int total, float maxSpeed, int failed, v2& outV, Cons* proj) {
     float maxPen = 0.0f;
     for (int i = failed; i < total; i++) {
         const Cons ci = cs[i];
@@ -299,6 +299,7 @@ __device__ __forceinline__ OrcaResult orca_velocity(const ObstView& ob, const Bi
     int n_on = find_obstacles<kSync>(ob, bins, position, range * range, on, kMaxObstNeighbors, valid);
     if (n_on > kMaxObstNeighbors) { n_on = kMaxObstNeighbors; res.status |= 16u; }
     int nc = 0;
+    phase_barrier<kSync>();
     {
         const int trips = warp_max_trip<kSync>(n_on);
         for (int i = 0; i < trips; i++) {
@@ -310,6 +311,7 @@ __device__ __forceinline__ OrcaResult orca_velocity(const ObstView& ob, const Bi
         }
     }
     const int nObst = nc;
+    phase_barrier<kSync>();
     {
         const int trips = warp_max_trip<kSync>(n_nb);
         for (int i = 0; i < trips; i++) {
@@ -321,6 +323,7 @@ __device__ __forceinline__ OrcaResult orca_velocity(const ObstView& ob, const Bi
         }
     }
     v2 out = V(0.0f, 0.0f);
+    phase_barrier<kSync>();
     int failed = randomized_lp<kSync>(cs, nc, prefVel, maxSpeed, false, out);
     if (failed < nc) {  // rare (dense crowds): stays per-lane
         Cons proj[kMaxCons];

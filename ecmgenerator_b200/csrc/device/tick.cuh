@@ -305,7 +305,7 @@ __device__ __forceinline__ unsigned finish_agent(const TickView& t, int p, const
     return r.status | extra;
 }
 
-__global__ void __launch_bounds__(128) k_orca(TickView t) {
+__global__ void __launch_bounds__(512) k_orca(TickView t) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = *t.n_sorted_ptr;
     unsigned st = 0u;
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(128) k_orca(TickView t) {
             t.sc.fb_list[e] = p;
         }
     }
-    __syncwarp();
+    __syncthreads();  // phase barrier: neighbour search | constraints + LP
     st |= finish_agent<true>(t, p, k, mine && found);
     if (st) t.ag.status[t.sc.s_slot[p]] |= st;
     unsigned m_ovf = __ballot_sync(0xffffffffu, (st & 16u) != 0u);

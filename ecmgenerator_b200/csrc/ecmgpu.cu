@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -116,6 +117,7 @@ struct ecmgpu_sim {
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
     int max_ring = 8;
+    int orca_block = 256;  // CTA size of k_orca (env ECMGPU_ORCA_BLOCK for experiments)
 };
 
 namespace {
@@ -698,6 +700,7 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
     TRY_ALLOC(cudaStreamSynchronize(s->stream));
 #undef TRY_ALLOC
     s->h_path_hdr.assign(n, PathHdr{0, 0, 0.0f, 0.0f});
+    if (const char* e = getenv("ECMGPU_ORCA_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= 512 && v % 32 == 0) s->orca_block = v; }
     s->h_path_pool.reserve(std::min<size_t>(pool, 1 << 20));
     *out = s;
     return ECMGPU_OK;
@@ -884,7 +887,10 @@ int ecmgpu_update_phase(ecmgpu_sim* s, int phase) {
     const int nb = div_up(s->n_slots + (s->strips_on ? 2 * s->cap_halo + s->cap_self : 0), 128);
     k_attract<<<nb, 128, 0, s->stream>>>(t);
     if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
-    k_orca<<<nb, 128, 0, s->stream>>>(t);
+    {
+        const int ob = s->orca_block;
+        k_orca<<<div_up(nb * 128, ob), ob, 0, s->stream>>>(t);
+    }
     k_fallback<<<148, 128, 0, s->stream>>>(t, 0);
     if (s->profiling) { CUDA_TRY(s, cudaEventRecord(s->ev[3], s->stream)); s->ev_valid = true; }
     s->launches += 3;

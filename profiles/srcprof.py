@@ -6,7 +6,7 @@ rows = list(csv.reader(out.splitlines()))
 cur_file="?"; agg=[]
 hdr=None
 for r in rows:
-    if len(r)>=2 and r[0].strip()=="File Name": cur_file=r[1].split('/')[-1]; continue
+    if len(r)>=2 and r[0].strip()=="File Path": cur_file=r[1].split('/')[-1]; continue
     if len(r)>5 and r[0]=="Line No": hdr=r; continue
     if hdr and len(r)>10 and r[0] not in ("",):
         try: ln=int(r[0])
