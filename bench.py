@@ -44,13 +44,33 @@ def log(*a):
 
 
 # ------------------------------------------------------------------------------------------------
-def build_workload(config: str, agents: int | None, seed_offset: int = 0):
+def _plan_sharded(w, c, rank: int, world: int):
+    """Every rank plans 1/world of the paths (host threads are shared by the ranks), then all-gather."""
+    import torch.distributed as dist
+
+    n = c.n
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    threads = max(1, (os.cpu_count() or 8) // world)
+    off, pxy, _ = host.plan_paths(w, c.pos[lo:hi], c.goal[lo:hi], c.radius[lo:hi], threads=threads)
+    parts = [None] * world
+    dist.all_gather_object(parts, (np.diff(off).astype(np.int32), pxy))
+    lens = np.concatenate([p[0] for p in parts])
+    pts = np.concatenate([p[1] for p in parts])
+    out_off = np.zeros(n + 1, np.int32)
+    np.cumsum(lens, out=out_off[1:])
+    return out_off, pts
+
+
+def build_workload(config: str, agents: int | None, rank: int = 0, world: int = 1):
     world_fn, crowd_fn = S.CONFIGS[config]
     w = world_fn()
     t = time.time()
     c = crowd_fn(w, n=agents) if agents else crowd_fn(w)
     t1 = time.time()
-    off, pxy, ok = host.plan_paths(w, c.pos, c.goal, c.radius, threads=0)
+    if world > 1:
+        off, pxy = _plan_sharded(w, c, rank, world)
+    else:
+        off, pxy, _ = host.plan_paths(w, c.pos, c.goal, c.radius, threads=0)
     lens = np.diff(off)
     good = lens >= 2
     if not good.all():  # drop agents the planner could not serve (start or goal level with a cell corner)
@@ -139,6 +159,22 @@ class _silence_stdout:
         return False
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the newest committed ncu --set full
+    capture (profiles/*_traffic.json); bench.py itself never runs under a profiler."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None, None
+    try:
+        d = json.load(open(files[-1]))
+        k = d["kernels"][kernel]
+        return (k["dram_read_mbytes"] + k["dram_write_mbytes"]) * 1e6, os.path.basename(files[-1])
+    except Exception:
+        return None, None
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -217,7 +253,7 @@ def run_ours(args):
 
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    w, c, off, pxy = build_workload(args.config, args.agents)
+    w, c, off, pxy = build_workload(args.config, args.agents, rank, world)
     n = c.n
     if world > 1:
         from ecmgenerator_b200.multigpu import StripSim
@@ -286,12 +322,11 @@ def run_ours(args):
         dom = "orca" if acc["orca"] >= acc["attract"] else "attract"
         ach = alg[dom] * active0 / (acc[dom] * 1e-3) / 1e9
         ach_tick = alg["tick"] * active0 / (acc["tick"] * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic("k_" + dom)
         roof = {"bound": "hbm", "kernel": "k_" + dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_agent": alg[dom],
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_agent": alg[dom],
                 "kernel_ms": acc[dom], "phase_ms": acc,
                 "whole_tick": {"achieved": ach_tick, "frac": ach_tick / peak, "algorithmic_bytes_per_agent": alg["tick"]}}
-    clk = clocks.stop()
-
     # ---- end to end through the C ABI with host buffers (every rank moves its full slot arrays)
     e2e = None
     if True:
@@ -333,6 +368,7 @@ def run_ours(args):
                "ms_per_step": 1e3 * dt / k, "steps": k}
         for a in (hp, hv, ha):
             a.free()
+    clk = clocks.stop()  # sampled over all timed regions (resident ticks, per-phase pass, end-to-end ticks)
 
     global_active = int(active0)
     if world > 1:
