@@ -115,6 +115,16 @@ struct ecmgpu_sim {
     bool profiling = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // ---- pipelined host I/O (ecmgpu_update_io): two copy streams, double-buffered device staging
+    struct IoPipe {
+        bool ready = false;
+        int cap = 0;
+        cudaStream_t s_in = nullptr, s_out = nullptr;
+        float2 *in_pos[2] = {nullptr, nullptr}, *in_vel[2] = {nullptr, nullptr}, *out_pos[2] = {nullptr, nullptr}, *out_vel[2] = {nullptr, nullptr};
+        unsigned char* out_act[2] = {nullptr, nullptr};
+        cudaEvent_t in_done[2] = {nullptr, nullptr}, in_consumed[2] = {nullptr, nullptr}, tick_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+        uint64_t calls = 0;
+    } io;
     bool ev_valid = false;
     int max_ring = 8;
     int orca_block = 256;  // CTA size of k_orca (env ECMGPU_ORCA_BLOCK for experiments)
@@ -721,6 +731,16 @@ void ecmgpu_destroy(ecmgpu_sim* s) {
     s->d_fb_list.free(); s->d_ev_replan.free(); s->d_ev_destroyed.free(); s->d_s_pos.free(); s->d_s_vel.free();
     s->d_s_pref.free(); s->d_s_rad.free(); s->d_s_spd.free(); s->d_s_alive.free(); s->d_counters.free();
     comm_teardown(s);
+    if (s->io.ready) {
+        cudaStreamSynchronize(s->io.s_in);
+        cudaStreamSynchronize(s->io.s_out);
+        for (int b = 0; b < 2; b++) {
+            cudaFree(s->io.in_pos[b]); cudaFree(s->io.in_vel[b]); cudaFree(s->io.out_pos[b]); cudaFree(s->io.out_vel[b]); cudaFree(s->io.out_act[b]);
+            cudaEventDestroy(s->io.in_done[b]); cudaEventDestroy(s->io.in_consumed[b]); cudaEventDestroy(s->io.tick_done[b]); cudaEventDestroy(s->io.out_done[b]);
+        }
+        cudaStreamDestroy(s->io.s_in);
+        cudaStreamDestroy(s->io.s_out);
+    }
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -966,6 +986,73 @@ int ecmgpu_write(ecmgpu_sim* s, int which, const void* src, int first, int count
 int ecmgpu_read_async(ecmgpu_sim* s, int which, void* dst, int first, int count) { return xfer(s, which, dst, first, count, true, false); }
 int ecmgpu_write_async(ecmgpu_sim* s, int which, const void* src, int first, int count) { return xfer(s, which, (void*)src, first, count, false, false); }
 
+// One tick with host I/O, pipelined: upload (copy stream A) -> tick (main stream) -> download (copy
+// stream B).  Consecutive calls overlap: while tick k computes, the inputs of k+1 are already on
+// their way and the results of k-1 are still draining.  Device staging is double-buffered.
+int ecmgpu_update_io(ecmgpu_sim* s, int count, const float* in_pos, const float* in_vel, float* out_pos, float* out_vel,
+                     uint8_t* out_active, uint64_t* ticket) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (count < 0 || count > s->prm.max_agents) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_update_io: bad count");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    auto& io = s->io;
+    if (!io.ready) {
+        const size_t n = (size_t)s->prm.max_agents;
+        CUDA_TRY(s, cudaStreamCreateWithFlags(&io.s_in, cudaStreamNonBlocking));
+        CUDA_TRY(s, cudaStreamCreateWithFlags(&io.s_out, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            CUDA_TRY(s, cudaMalloc((void**)&io.in_pos[b], sizeof(float2) * n));
+            CUDA_TRY(s, cudaMalloc((void**)&io.in_vel[b], sizeof(float2) * n));
+            CUDA_TRY(s, cudaMalloc((void**)&io.out_pos[b], sizeof(float2) * n));
+            CUDA_TRY(s, cudaMalloc((void**)&io.out_vel[b], sizeof(float2) * n));
+            CUDA_TRY(s, cudaMalloc((void**)&io.out_act[b], n));
+            CUDA_TRY(s, cudaEventCreateWithFlags(&io.in_done[b], cudaEventDisableTiming));
+            CUDA_TRY(s, cudaEventCreateWithFlags(&io.in_consumed[b], cudaEventDisableTiming));
+            CUDA_TRY(s, cudaEventCreateWithFlags(&io.tick_done[b], cudaEventDisableTiming));
+            CUDA_TRY(s, cudaEventCreateWithFlags(&io.out_done[b], cudaEventDisableTiming));
+            CUDA_TRY(s, cudaEventRecord(io.in_consumed[b], s->stream));
+            CUDA_TRY(s, cudaEventRecord(io.out_done[b], io.s_out));
+        }
+        io.ready = true;
+    }
+    const int b = (int)(io.calls & 1);
+    const size_t c = (size_t)count;
+    // upload into staging b once the tick that last used it has consumed it
+    CUDA_TRY(s, cudaStreamWaitEvent(io.s_in, io.in_consumed[b], 0));
+    if (in_pos) CUDA_TRY(s, cudaMemcpyAsync(io.in_pos[b], in_pos, sizeof(float2) * c, cudaMemcpyHostToDevice, io.s_in));
+    if (in_vel) CUDA_TRY(s, cudaMemcpyAsync(io.in_vel[b], in_vel, sizeof(float2) * c, cudaMemcpyHostToDevice, io.s_in));
+    CUDA_TRY(s, cudaEventRecord(io.in_done[b], io.s_in));
+    // main stream: adopt the inputs, tick, publish the results
+    CUDA_TRY(s, cudaStreamWaitEvent(s->stream, io.in_done[b], 0));
+    if (in_pos) CUDA_TRY(s, cudaMemcpyAsync(s->d_pos.p, io.in_pos[b], sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
+    if (in_vel) CUDA_TRY(s, cudaMemcpyAsync(s->d_vel.p, io.in_vel[b], sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
+    CUDA_TRY(s, cudaEventRecord(io.in_consumed[b], s->stream));
+    int rc = ecmgpu_update(s);
+    if (rc) return rc;
+    CUDA_TRY(s, cudaStreamWaitEvent(s->stream, io.out_done[b], 0));  // the download that last read staging b is over
+    if (out_pos) CUDA_TRY(s, cudaMemcpyAsync(io.out_pos[b], s->d_pos.p, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
+    if (out_vel) CUDA_TRY(s, cudaMemcpyAsync(io.out_vel[b], s->d_vel.p, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
+    if (out_active) CUDA_TRY(s, cudaMemcpyAsync(io.out_act[b], s->d_active.p, c, cudaMemcpyDeviceToDevice, s->stream));
+    CUDA_TRY(s, cudaEventRecord(io.tick_done[b], s->stream));
+    // download
+    CUDA_TRY(s, cudaStreamWaitEvent(io.s_out, io.tick_done[b], 0));
+    if (out_pos) CUDA_TRY(s, cudaMemcpyAsync(out_pos, io.out_pos[b], sizeof(float2) * c, cudaMemcpyDeviceToHost, io.s_out));
+    if (out_vel) CUDA_TRY(s, cudaMemcpyAsync(out_vel, io.out_vel[b], sizeof(float2) * c, cudaMemcpyDeviceToHost, io.s_out));
+    if (out_active) CUDA_TRY(s, cudaMemcpyAsync(out_active, io.out_act[b], c, cudaMemcpyDeviceToHost, io.s_out));
+    CUDA_TRY(s, cudaEventRecord(io.out_done[b], io.s_out));
+    if (ticket) *ticket = io.calls;
+    io.calls++;
+    return ECMGPU_OK;
+}
+
+int ecmgpu_io_wait(ecmgpu_sim* s, uint64_t ticket) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    auto& io = s->io;
+    if (!io.ready || ticket >= io.calls) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_io_wait: unknown ticket");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    CUDA_TRY(s, cudaEventSynchronize(io.out_done[ticket & 1]));
+    return ECMGPU_OK;
+}
+
 void* ecmgpu_alloc_pinned(uint64_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
@@ -1192,10 +1279,26 @@ int ecmgpu_comm_set_strips(ecmgpu_sim* s, const float* bounds, float halo_width)
     s->strip_lo = s->rank == 0 ? -inf : bounds[s->rank];
     s->strip_hi = s->rank == s->n_ranks - 1 ? inf : bounds[s->rank + 1];
     s->halo = halo_width;
-    // capacities: generous fixed-size messages (counts travel in the header, no host round trip)
+    // capacities of the fixed-size messages (counts travel in the header, no host round trip): four times
+    // what the current crowd puts within the halo of this rank's borders, never less than 4096 entries
     const int n = s->prm.max_agents;
-    s->cap_halo = std::max(1024, std::min(n, n / std::max(1, s->n_ranks) / 2 + 4096));
-    s->cap_migr = std::max(256, std::min(n, s->cap_halo / 8));
+    int near = 0;
+    if (s->n_slots > 0) {
+        std::vector<float2> pos(s->n_slots);
+        std::vector<unsigned char> act(s->n_slots);
+        CUDA_TRY(s, cudaMemcpyAsync(pos.data(), s->d_pos.p, sizeof(float2) * s->n_slots, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(act.data(), s->d_active.p, s->n_slots, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        int cnt[2] = {0, 0};
+        for (int i = 0; i < s->n_slots; i++) {
+            if (!act[i]) continue;
+            if (std::fabs(pos[i].x - s->strip_lo) < halo_width) cnt[0]++;
+            if (std::fabs(pos[i].x - s->strip_hi) < halo_width) cnt[1]++;
+        }
+        near = std::max(cnt[0], cnt[1]);
+    }
+    s->cap_halo = std::min(n, std::max(4096, 4 * near));
+    s->cap_migr = std::min(n, std::max(1024, s->cap_halo / 4));
     s->cap_self = 2 * s->cap_migr;
     const size_t msg = strip_msg_bytes(s->cap_halo, s->cap_migr);
     for (int d = 0; d < 2; d++) {

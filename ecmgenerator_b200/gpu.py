@@ -36,7 +36,7 @@ EXPORTS = [
     "ecmgpu_read", "ecmgpu_write", "ecmgpu_read_async", "ecmgpu_write_async", "ecmgpu_alloc_pinned", "ecmgpu_free_pinned",
     "ecmgpu_locate", "ecmgpu_retract", "ecmgpu_find_neighbors", "ecmgpu_find_obstacles", "ecmgpu_get_stats",
     "ecmgpu_last_tick_ms", "ecmgpu_set_profiling", "ecmgpu_mark", "ecmgpu_mark_elapsed_ms", "ecmgpu_stream", "ecmgpu_comm_unique_id", "ecmgpu_comm_init",
-    "ecmgpu_comm_set_strips", "ecmgpu_comm_init_local", "ecmgpu_update_phase",
+    "ecmgpu_comm_set_strips", "ecmgpu_comm_init_local", "ecmgpu_update_phase", "ecmgpu_update_io", "ecmgpu_io_wait",
 ]
 
 
@@ -101,6 +101,8 @@ def lib() -> C.CDLL:
         L.ecmgpu_comm_set_strips.argtypes = [vp, f32p, C.c_float]
         L.ecmgpu_comm_init_local.argtypes = [vp, C.c_int, C.c_int, vp, vp]
         L.ecmgpu_update_phase.argtypes = [vp, C.c_int]
+        L.ecmgpu_update_io.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(C.c_uint64)]
+        L.ecmgpu_io_wait.argtypes = [vp, C.c_uint64]
         _lib = L
     return _lib
 
@@ -194,6 +196,17 @@ class GpuSim:
     def update(self, n: int = 1):
         for _ in range(int(n)):
             self._ck(self.L.ecmgpu_update(self.h))
+
+    def update_io(self, count, in_pos, in_vel, out_pos, out_vel, out_active) -> int:
+        """Pipelined tick with host I/O; arguments are PinnedArray (or None).  Returns the ticket."""
+        ptr = lambda a: C.c_void_p(a.ptr) if a is not None else None  # noqa: E731
+        t = C.c_uint64(0)
+        self._ck(self.L.ecmgpu_update_io(self.h, int(count), ptr(in_pos), ptr(in_vel), ptr(out_pos), ptr(out_vel), ptr(out_active),
+                                         C.byref(t)))
+        return int(t.value)
+
+    def io_wait(self, ticket: int):
+        self._ck(self.L.ecmgpu_io_wait(self.h, int(ticket)))
 
     def update_phase(self, phase: int):
         self._ck(self.L.ecmgpu_update_phase(self.h, int(phase)))

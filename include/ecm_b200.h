@@ -119,6 +119,17 @@ int ecmgpu_write(ecmgpu_sim* sim, int which, const void* src, int first, int cou
 /* Asynchronous variants on the handle's stream for pinned host memory (end-to-end pipelines). */
 int ecmgpu_read_async(ecmgpu_sim* sim, int which, void* dst_pinned, int first, int count);
 int ecmgpu_write_async(ecmgpu_sim* sim, int which, const void* src_pinned, int first, int count);
+/* One tick with host I/O, pipelined over two copy streams and double-buffered device staging:
+ * uploads positions / velocities of slots [0,count) from PINNED host memory (NULL = keep the device
+ * values), runs ecmgpu_update, downloads positions / velocities / active flags into PINNED host
+ * memory (NULL = skip).  Returns at once; the outputs of the call that returned `ticket` are complete
+ * after ecmgpu_io_wait(ticket).  Consecutive calls overlap (upload of k+1 | tick k | download of k-1),
+ * so use two sets of host buffers and wait for ticket k-1 after issuing call k.
+ * Replaces the per-frame pattern Update() + GetPositionData()/GetVelocityData()/GetActiveFlags()
+ * (Application.cpp:137-144, ECMRenderer.cpp:836-884) for hosts that keep the state on their side. */
+int ecmgpu_update_io(ecmgpu_sim* sim, int count, const float* in_pos, const float* in_vel, float* out_pos, float* out_vel,
+                     uint8_t* out_active, uint64_t* ticket);
+int ecmgpu_io_wait(ecmgpu_sim* sim, uint64_t ticket);
 /* cudaHostAlloc / cudaFreeHost pass-through so non-CUDA hosts can get pinned staging memory. */
 void* ecmgpu_alloc_pinned(uint64_t bytes);
 void  ecmgpu_free_pinned(void* p);

@@ -291,3 +291,35 @@ def test_large_crowd_properties():
     assert st["n_active"] == n and st["knn_fallbacks"] == 0
     v = sim.read(gpu.VEL, 0, n)
     assert np.isfinite(v).all() and np.linalg.norm(v, axis=1).max() <= 1.4 * 1.01
+
+
+def test_update_io_pipeline_matches_plain_update():
+    """ecmgpu_update_io (overlapped upload | tick | download) gives the same state as write + update + read."""
+    g = Golden("c2_small")
+    n = g.n
+    a = gpu.GpuSim(g.world, n, g.step)
+    b = gpu.GpuSim(g.world, n, g.step)
+    for s in (a, b):
+        s.bulk_load(g.crowd.pos, g.crowd.radius, g.crowd.speed, g.path_off, g.path_xy)
+    hp = [gpu.PinnedArray((n, 2), np.float32) for _ in range(2)]
+    hv = [gpu.PinnedArray((n, 2), np.float32) for _ in range(2)]
+    op = [gpu.PinnedArray((n, 2), np.float32) for _ in range(2)]
+    ov = [gpu.PinnedArray((n, 2), np.float32) for _ in range(2)]
+    oa = [gpu.PinnedArray((n,), np.uint8) for _ in range(2)]
+    pos, vel = g.crowd.pos.copy(), np.zeros((n, 2), np.float32)
+    for t in range(12):
+        k = t & 1
+        hp[k].array[:] = pos
+        hv[k].array[:] = vel
+        tk = b.update_io(n, hp[k], hv[k], op[k], ov[k], oa[k])
+        a.write(gpu.POS, pos)
+        a.write(gpu.VEL, vel)
+        a.update(1)
+        b.io_wait(tk)
+        pa, va = a.read(gpu.POS, 0, n), a.read(gpu.VEL, 0, n)
+        assert_bits_equal(op[k].array, pa, f"pos tick {t}")
+        assert_bits_equal(ov[k].array, va, f"vel tick {t}")
+        assert np.array_equal(oa[k].array, a.read(gpu.ACTIVE, 0, n))
+        pos, vel = pa.copy(), va.copy()
+    for x in hp + hv + op + ov + oa:
+        x.free()
