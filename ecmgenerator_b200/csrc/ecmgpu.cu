@@ -128,6 +128,14 @@ struct ecmgpu_sim {
     bool ev_valid = false;
     int max_ring = 8;
     int orca_block = 256;  // CTA size of k_orca (env ECMGPU_ORCA_BLOCK for experiments)
+    // ---- the tick as a CUDA graph (one launch instead of ~15 kernel / memset / NCCL submissions)
+    bool use_graph = true;         // env ECMGPU_GRAPH=0 disables
+    uint64_t config_epoch = 1;     // bumped whenever something the captured tick depends on changes
+    uint64_t graph_epoch = 0;
+    int graph_n_slots = -1;
+    uint64_t graph_launches = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
 };
 
 namespace {
@@ -282,6 +290,7 @@ int build_bins(ecmgpu_sim* s) {
     CUDA_TRY(s, cudaStreamSynchronize(s->stream));  // the host vectors die here
     s->built_range = (float)range;
     s->bins_dirty = false;
+    s->config_epoch++;
     return ECMGPU_OK;
 }
 
@@ -321,6 +330,7 @@ int build_grid(ecmgpu_sim* s) {
     CUDA_TRY(s, s->d_cell_count.alloc(s->ncells_padded));
     CUDA_TRY(s, s->d_block_sums.alloc(s->ncells_padded / kScanTile));
     s->grid_dirty = false;
+    s->config_epoch++;
     return ECMGPU_OK;
 }
 
@@ -710,6 +720,7 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
     TRY_ALLOC(cudaStreamSynchronize(s->stream));
 #undef TRY_ALLOC
     s->h_path_hdr.assign(n, PathHdr{0, 0, 0.0f, 0.0f});
+    if (const char* e = getenv("ECMGPU_GRAPH")) s->use_graph = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_ORCA_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= 512 && v % 32 == 0) s->orca_block = v; }
     s->h_path_pool.reserve(std::min<size_t>(pool, 1 << 20));
     *out = s;
@@ -731,6 +742,8 @@ void ecmgpu_destroy(ecmgpu_sim* s) {
     s->d_fb_list.free(); s->d_ev_replan.free(); s->d_ev_destroyed.free(); s->d_s_pos.free(); s->d_s_vel.free();
     s->d_s_pref.free(); s->d_s_rad.free(); s->d_s_spd.free(); s->d_s_alive.free(); s->d_counters.free();
     comm_teardown(s);
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    if (s->graph) cudaGraphDestroy(s->graph);
     if (s->io.ready) {
         cudaStreamSynchronize(s->io.s_in);
         cudaStreamSynchronize(s->io.s_out);
@@ -923,6 +936,31 @@ int ecmgpu_update(ecmgpu_sim* s) {
     if (!s) return ECMGPU_ERR_INVALID;
     if (s->local_transport && s->n_ranks > 1)
         return fail(s, ECMGPU_ERR_INVALID, "in-process strips: drive all handles with ecmgpu_update_phase(0), (1), (2)");
+    if (s->use_graph && !s->profiling && s->n_slots > 0) {
+        CUDA_TRY(s, cudaSetDevice(s->prm.device));
+        int rc = ensure_ready(s);  // host-side (re)builds happen outside the capture
+        if (rc) return rc;
+        if (!s->graph_exec || s->graph_epoch != s->config_epoch || s->graph_n_slots != s->n_slots) {
+            if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+            if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
+            const uint64_t l0 = s->launches, t0 = s->ticks;
+            CUDA_TRY(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeRelaxed));
+            for (int phase = 0; phase < 3 && rc == ECMGPU_OK; phase++) rc = ecmgpu_update_phase(s, phase);
+            cudaError_t ce = cudaStreamEndCapture(s->stream, &s->graph);
+            s->graph_launches = s->launches - l0;
+            s->launches = l0;
+            s->ticks = t0;
+            if (rc) return rc;
+            if (ce != cudaSuccess) return fail(s, ECMGPU_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+            CUDA_TRY(s, cudaGraphInstantiate(&s->graph_exec, s->graph, 0));
+            s->graph_epoch = s->config_epoch;
+            s->graph_n_slots = s->n_slots;
+        }
+        CUDA_TRY(s, cudaGraphLaunch(s->graph_exec, s->stream));
+        s->launches += s->graph_launches;
+        s->ticks++;
+        return ECMGPU_OK;
+    }
     for (int phase = 0; phase < 3; phase++) {
         int rc = ecmgpu_update_phase(s, phase);
         if (rc) return rc;
@@ -1289,13 +1327,15 @@ int ecmgpu_comm_set_strips(ecmgpu_sim* s, const float* bounds, float halo_width)
         CUDA_TRY(s, cudaMemcpyAsync(pos.data(), s->d_pos.p, sizeof(float2) * s->n_slots, cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(s, cudaMemcpyAsync(act.data(), s->d_active.p, s->n_slots, cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(s, cudaStreamSynchronize(s->stream));
-        int cnt[2] = {0, 0};
+        // every rank still sees the whole crowd here and counts at EVERY border, so that all ranks agree
+        // on the message layout (neighbours must use the same capacities)
+        std::vector<int> cnt(s->n_ranks + 1, 0);
         for (int i = 0; i < s->n_slots; i++) {
             if (!act[i]) continue;
-            if (std::fabs(pos[i].x - s->strip_lo) < halo_width) cnt[0]++;
-            if (std::fabs(pos[i].x - s->strip_hi) < halo_width) cnt[1]++;
+            for (int r = 1; r < s->n_ranks; r++)
+                if (std::fabs(pos[i].x - bounds[r]) < halo_width) cnt[r]++;
         }
-        near = std::max(cnt[0], cnt[1]);
+        for (int r = 1; r < s->n_ranks; r++) near = std::max(near, cnt[r]);
     }
     s->cap_halo = std::min(n, std::max(4096, 4 * near));
     s->cap_migr = std::min(n, std::max(1024, s->cap_halo / 4));
@@ -1317,6 +1357,7 @@ int ecmgpu_comm_set_strips(ecmgpu_sim* s, const float* bounds, float halo_width)
     CUDA_TRY(s, s->d_s_rad.alloc(cap)); CUDA_TRY(s, s->d_s_spd.alloc(cap)); CUDA_TRY(s, s->d_s_slot.alloc(cap));
     CUDA_TRY(s, s->d_s_alive.alloc(cap)); CUDA_TRY(s, s->d_s_ghost.alloc(cap)); CUDA_TRY(s, s->d_fb_list.alloc(cap));
     s->strips_on = true;
+    s->config_epoch++;
     if (s->n_slots > 0) {
         TickView t = make_view(s);
         k_assign_owner<<<div_up(s->n_slots, 256), 256, 0, s->stream>>>(s->n_slots, t.ag, make_strip_view(s));
