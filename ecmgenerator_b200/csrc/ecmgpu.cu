@@ -936,7 +936,10 @@ int ecmgpu_update(ecmgpu_sim* s) {
     if (!s) return ECMGPU_ERR_INVALID;
     if (s->local_transport && s->n_ranks > 1)
         return fail(s, ECMGPU_ERR_INVALID, "in-process strips: drive all handles with ecmgpu_update_phase(0), (1), (2)");
-    if (s->use_graph && !s->profiling && s->n_slots > 0) {
+    // NCCL send/recv are kept out of graph capture (capturing them hung on 4 x B200 with NCCL 2.28): with the
+    // NCCL transport the tick is submitted launch by launch
+    const bool nccl_tick = s->strips_on && !s->local_transport && s->n_ranks > 1;
+    if (s->use_graph && !nccl_tick && !s->profiling && s->n_slots > 0) {
         CUDA_TRY(s, cudaSetDevice(s->prm.device));
         int rc = ensure_ready(s);  // host-side (re)builds happen outside the capture
         if (rc) return rc;
