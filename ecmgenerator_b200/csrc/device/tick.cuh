@@ -305,7 +305,12 @@ __device__ __forceinline__ unsigned finish_agent(const TickView& t, int p, const
     return r.status | extra;
 }
 
-__global__ void __launch_bounds__(512) k_orca(TickView t) {
+// 5 CTAs of 256 threads per SM (48 registers): measured 6 % faster than the 64-register build (4 CTAs);
+// the few spilled values stay in L1 (A/B on one B200, 1M agents: 0.467 -> 0.439 ms)
+#ifndef ECM_ORCA_MINBLOCKS
+#define ECM_ORCA_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(256, ECM_ORCA_MINBLOCKS) k_orca(TickView t) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = *t.n_sorted_ptr;
     unsigned st = 0u;

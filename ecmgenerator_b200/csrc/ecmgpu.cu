@@ -721,7 +721,7 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
 #undef TRY_ALLOC
     s->h_path_hdr.assign(n, PathHdr{0, 0, 0.0f, 0.0f});
     if (const char* e = getenv("ECMGPU_GRAPH")) s->use_graph = atoi(e) != 0;
-    if (const char* e = getenv("ECMGPU_ORCA_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= 512 && v % 32 == 0) s->orca_block = v; }
+    if (const char* e = getenv("ECMGPU_ORCA_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) s->orca_block = v; }
     s->h_path_pool.reserve(std::min<size_t>(pool, 1 << 20));
     *out = s;
     return ECMGPU_OK;

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libecmgpu.so")
+LIB_PATH = os.environ.get("ECMGPU_LIB") or os.path.join(_HERE, "libecmgpu.so")  # ECMGPU_LIB: build variants for experiments
 _lib = None
 
 f32p = C.POINTER(C.c_float)
