@@ -102,3 +102,19 @@ def test_dropin_matches_c_oracle_with_host_planner():
     sim.reset()
     assert sim.num_agents == 0
     sim.close()
+
+
+def test_headless_cpp_program_runs():
+    """examples/headless_main.cpp: a C++17 host program over the drop-in class (no Python in the loop)."""
+    import os
+    import subprocess
+
+    from tests.conftest import ROOT
+
+    exe = os.path.join(ROOT, "ecmgenerator_b200", "ecm_headless")
+    r = subprocess.run([exe, "120", "300"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("ticks ")][-1]
+    print(line)
+    agents = int(line.split()[3])
+    assert agents > 500
