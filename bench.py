@@ -260,7 +260,7 @@ def run_ours(args):
 
         sim = StripSim(w, c, off, pxy, rank, world, local)
     else:
-        sim = gpu.GpuSim(w, n, float(S.DT), device=local, record_neighbors=False,
+        sim = gpu.GpuSim(w, n, float(S.DT), device=local, record_neighbors=False, neighbor_cell=args.cell, static_bin=args.bin,
                          path_pool_points=int(off[-1] * 1.25) + 4096)
         sim.bulk_load(c.pos, c.radius, c.speed, off, pxy)
     mean_p = float(np.diff(off).mean())
@@ -418,6 +418,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4096, help="agents in the CPU baseline sample")
     ap.add_argument("--cpu-ticks", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cell", type=float, default=0.0, help="neighbour grid cell (0 = from crowd density)")
+    ap.add_argument("--bin", type=float, default=0.0, help="static bin edge (0 = from the ECM)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -68,14 +68,14 @@ __device__ __forceinline__ bool obstacle_constraint(const ObstView& ob, int oL, 
     const float sp = vdot(vmul(rp1, -1.0f), segDir) / vlen2(segDir);
     const float distSqLine = vlen2(vsub(vmul(rp1, -1.0f), vmul(segDir, sp)));
     const float distSq1 = vlen2(rp1), distSq2 = vlen2(rp2);
-    segDir = vnormalized(segDir);
+    segDir = __ldg(&ob.dir[oL]);  // = Normalize(segDir)
     const float radiusSq = clearance * clearance;
 
     if (sp < 0.0f && distSq1 <= radiusSq) {  // collision with the left vertex (ORCA.cpp:92-105)
         if (cvxL) { c = cmake(V(0.0f, 0.0f), vnormalized(vmul(rp1, -1.0f))); return true; }
         return false;
     } else if (sp > 1.0f && distSq2 <= radiusSq) {  // collision with the right vertex (ORCA.cpp:108-121)
-        v2 rnd = vnormalized(vsub(__ldg(&ob.xy[__ldg(&ob.next[oR])]), pR));
+        v2 rnd = __ldg(&ob.dir[oR]);  // = Normalize(next(R).p - R.p)
         if (cvxR && vdet(rp2, rnd) >= 0.0f) { c = cmake(V(0.0f, 0.0f), vnormalized(vmul(rp2, -1.0f))); return true; }
         return false;
     } else if (sp >= 0.0f && sp < 1.0f && distSqLine <= radiusSq) {  // collision with the segment (ORCA.cpp:124-135)
@@ -113,9 +113,9 @@ __device__ __forceinline__ bool obstacle_constraint(const ObstView& ob, int oL, 
 
     // foreign legs (ORCA.cpp:218-239)
     bool leftForeign = false, rightForeign = false;
-    v2 lnd = vnormalized(vsub(pL, __ldg(&ob.xy[__ldg(&ob.prev[oL])])));
+    v2 lnd = __ldg(&ob.dir[__ldg(&ob.prev[oL])]);  // = Normalize(L.p - prev(L).p)
     if (cvxL && vdet(leftLeg, vmul(lnd, -1.0f)) >= 0.0f) { leftLeg = vmul(lnd, -1.0f); leftForeign = true; }
-    v2 rnd = vnormalized(vsub(__ldg(&ob.xy[__ldg(&ob.next[oR])]), pR));
+    v2 rnd = __ldg(&ob.dir[oR]);  // = Normalize(next(R).p - R.p)
     if (cvxR && vdet(rightLeg, rnd) <= 0.0f) { rightLeg = rnd; rightForeign = true; }
 
     const float recip = 1.0f / kLookAhead;  // ORCA.cpp:241
@@ -174,8 +174,11 @@ __device__ __forceinline__ Cons agent_constraint(v2 position, v2 velocity, float
         return cmake(vadd(velocity, vmul(U, 0.5f)), unitW);
     }
     float tanHalfAngle = atanf(VORadius / VOPosLength);  // atan, not asin (ORCA.cpp:375-376)
-    v2 VOLeftLeg = rotate(VOPos, tanHalfAngle);
-    v2 VORightLeg = rotate(VOPos, -tanHalfAngle);
+    // RotateVector(VOPos, +a) and RotateVector(VOPos, -a): one sincosf serves both (sin is odd, cos even, exactly)
+    float sn, cs;
+    sincosf(tanHalfAngle, &sn, &cs);
+    v2 VOLeftLeg = V(VOPos.x * cs - VOPos.y * sn, VOPos.x * sn + VOPos.y * cs);
+    v2 VORightLeg = V(VOPos.x * cs + VOPos.y * sn, VOPos.y * cs - VOPos.x * sn);
     float sqDistFromCircleCentre = sqdist(VOPos, relVel);
     v2 base = vsub(VOLeftLeg, VOPos), chk = vsub(relVel, VOPos);
     bool liesBelow = base.x * chk.y - base.y * chk.x > 0.0f;  // IsLeftOfVector (UtilityFunctions.cpp:198-201)

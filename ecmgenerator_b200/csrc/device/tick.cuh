@@ -163,13 +163,19 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_add(int4* __restrict__ data
 }
 
 // ------------------------------------------------------------------------------------------------
+// slots_only: write just the slot id; k_attract then GATHERS the agent's components by slot (random
+// reads that hit L2) and writes the snapshot rows coalesced, instead of six scattered writes here.
 __global__ void __launch_bounds__(256) k_scatter(int n_slots, const int* __restrict__ key, const int* __restrict__ rank,
-                                                 const int* __restrict__ cell_start, AgentArrays ag, TickScratch sc) {
+                                                 const int* __restrict__ cell_start, AgentArrays ag, TickScratch sc, int slots_only) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_slots) return;
     int k = key[i];
     if (k < 0) return;
     int p = cell_start[k] + rank[i];
+    if (slots_only) {
+        sc.s_slot[p] = i;
+        return;
+    }
     sc.s_pos[p] = ag.pos[i];
     sc.s_vel[p] = ag.vel[i];
     sc.s_rad[p] = ag.radius[i];
@@ -190,6 +196,7 @@ struct TickView {
     float step;
     int max_ring;
     int record_neighbors;
+    int gather;  // 1: k_scatter wrote only s_slot; k_attract fills the snapshot rows of owned agents
     // multi-GPU strips (strips.cuh): the grid holds every agent with x in [cover_lo, cover_hi)
     int strips;
     float cover_lo, cover_hi;
@@ -201,13 +208,24 @@ __global__ void __launch_bounds__(128) k_attract(TickView t) {
     const bool valid = p < n && !t.sc.s_ghost[p];
     unsigned st = 0u;
     int slot = 0, np = 2, cell = -2;
+    float spd = 0.0f;
     v2 pos = V(0.0f, 0.0f), goal = V(0.0f, 0.0f), attr = V(0.0f, 0.0f);
     const float2* path = t.ag.path_pool;
     const float4* bbox = t.ag.path_bbox;
     bool have = false, alive = true, need_irm = false;
     if (valid) {
         slot = t.sc.s_slot[p];
-        pos = t.sc.s_pos[p];
+        if (t.gather) {  // build this agent's snapshot row: gathers hit L2, the stores are coalesced
+            pos = t.ag.pos[slot];
+            t.sc.s_pos[p] = pos;
+            t.sc.s_vel[p] = t.ag.vel[slot];
+            t.sc.s_rad[p] = t.ag.radius[slot];
+            spd = t.ag.speed[slot];
+            t.sc.s_spd[p] = spd;
+        } else {
+            pos = t.sc.s_pos[p];
+            spd = t.sc.s_spd[p];
+        }
         const PathHdr hdr = t.ag.path_hdr[slot];
         path += hdr.off;
         bbox += hdr.off >> 3;
@@ -255,7 +273,7 @@ __global__ void __launch_bounds__(128) k_attract(TickView t) {
         else attr = t.ag.attraction[slot];  // previous attraction point is kept (Simulator.cpp:573-587)
         if (alive) {  // ApplySteeringForce (Simulator.cpp:638-657)
             v2 d = vnormalized(vsub(attr, pos));
-            v2 pv = vmul(d, t.sc.s_spd[p]);
+            v2 pv = vmul(d, spd);
             t.ag.prefvel[slot] = pv;
             t.sc.s_pref[p] = pv;
         }

@@ -21,6 +21,9 @@ struct ObstView {
     const int* next;
     const int* prev;
     const unsigned char* convex;
+    // unit direction of segment i -> next[i], precomputed on the host with the same IEEE sqrt / divide as
+    // Vec2::Normalize (bit-identical to normalising on the fly; ORCA.cpp:88, :111-112, :226-227, :234-235)
+    const float2* dir;
 };
 
 // Uniform bins over the walkable-area bbox (+margin).  Per bin two ascending id lists (CSR):

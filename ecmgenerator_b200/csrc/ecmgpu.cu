@@ -67,6 +67,7 @@ struct ecmgpu_sim {
     DevBuf<int2> d_edge_v;
     DevBuf<int> d_obst_next, d_obst_prev;
     DevBuf<unsigned char> d_obst_convex;
+    DevBuf<float2> d_obst_dir;
     DevBuf<int> d_bin_cell_start, d_bin_cell_items, d_bin_obst_start, d_bin_obst_items;
     int n_vertices = 0, n_edges = 0, n_obst = 0;
 
@@ -128,6 +129,7 @@ struct ecmgpu_sim {
     bool ev_valid = false;
     int max_ring = 8;
     int orca_block = 256;  // CTA size of k_orca (env ECMGPU_ORCA_BLOCK for experiments)
+    bool gather = false;   // snapshot rows built by k_attract (gather) instead of k_scatter: measured neutral (profiles/r01_experiments.md); env ECMGPU_GATHER=1
     // ---- the tick as a CUDA graph (one launch instead of ~15 kernel / memset / NCCL submissions)
     bool use_graph = true;         // env ECMGPU_GRAPH=0 disables
     uint64_t config_epoch = 1;     // bumped whenever something the captured tick depends on changes
@@ -346,6 +348,7 @@ TickView make_view(ecmgpu_sim* s) {
     t.obst.next = s->d_obst_next.p;
     t.obst.prev = s->d_obst_prev.p;
     t.obst.convex = s->d_obst_convex.p;
+    t.obst.dir = s->d_obst_dir.p;
     t.bins.x0 = s->bins_x0;
     t.bins.y0 = s->bins_y0;
     t.bins.inv_bin = 1.0f / s->static_bin;
@@ -403,6 +406,7 @@ TickView make_view(ecmgpu_sim* s) {
     t.step = s->prm.step;
     t.max_ring = s->max_ring;
     t.record_neighbors = s->prm.record_neighbors;
+    t.gather = s->gather ? 1 : 0;
     t.strips = s->strips_on ? 1 : 0;
     const float inf = std::numeric_limits<float>::infinity();
     t.cover_lo = s->strips_on && s->rank > 0 ? s->strip_lo - s->halo : -inf;
@@ -559,7 +563,8 @@ int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
     k_scan_tiles<<<tiles, kScanBlock, 0, s->stream>>>((int4*)s->d_cell_count.p, s->d_block_sums.p);
     k_scan_sums<<<1, kScanBlock, 0, s->stream>>>(s->d_block_sums.p, tiles);
     k_scan_add<<<tiles, kScanBlock, 0, s->stream>>>((int4*)s->d_cell_count.p, s->d_block_sums.p);
-    k_scatter<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc);
+    if (t.gather && s->strips_on) CUDA_TRY(s, cudaMemsetAsync(s->d_s_ghost.p, 0, s->d_s_ghost.n, s->stream));
+    k_scatter<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc, t.gather);
     if (s->strips_on) {
         k_ghost_scatter<<<div_up(ng, 256), 256, 0, s->stream>>>(sv, s->d_cell_count.p, t.ag, t.sc, s->d_s_ghost.p);
         s->launches++;
@@ -721,6 +726,7 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
 #undef TRY_ALLOC
     s->h_path_hdr.assign(n, PathHdr{0, 0, 0.0f, 0.0f});
     if (const char* e = getenv("ECMGPU_GRAPH")) s->use_graph = atoi(e) != 0;
+    if (const char* e = getenv("ECMGPU_GATHER")) s->gather = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_ORCA_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) s->orca_block = v; }
     s->h_path_pool.reserve(std::min<size_t>(pool, 1 << 20));
     *out = s;
@@ -733,7 +739,7 @@ void ecmgpu_destroy(ecmgpu_sim* s) {
     for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : s->marks) if (ev) cudaEventDestroy(ev);
     s->d_vert_xy.free(); s->d_edge_cl.free(); s->d_obst_xy.free(); s->d_edge_v.free();
-    s->d_obst_next.free(); s->d_obst_prev.free(); s->d_obst_convex.free();
+    s->d_obst_next.free(); s->d_obst_prev.free(); s->d_obst_convex.free(); s->d_obst_dir.free();
     s->d_bin_cell_start.free(); s->d_bin_cell_items.free(); s->d_bin_obst_start.free(); s->d_bin_obst_items.free();
     s->d_pos.free(); s->d_vel.free(); s->d_prefvel.free(); s->d_attraction.free(); s->d_force.free();
     s->d_radius.free(); s->d_speed.free(); s->d_active.free(); s->d_replan_pending.free(); s->d_status.free();
@@ -798,11 +804,20 @@ int ecmgpu_set_obstacles(ecmgpu_sim* s, int n, const float* xy, const int* next,
     CUDA_TRY(s, s->d_obst_next.alloc(std::max(n, 1)));
     CUDA_TRY(s, s->d_obst_prev.alloc(std::max(n, 1)));
     CUDA_TRY(s, s->d_obst_convex.alloc(std::max(n, 1)));
+    CUDA_TRY(s, s->d_obst_dir.alloc(std::max(n, 1)));
+    std::vector<float2> dir(std::max(n, 1), make_float2(0.0f, 0.0f));
+    for (int i = 0; i < n; i++) {  // Vec2::Normalize (ECMDataTypes.h:45-52) in IEEE float, no contraction
+        volatile float dx = xy[2 * next[i]] - xy[2 * i], dy = xy[2 * next[i] + 1] - xy[2 * i + 1];
+        volatile float xx = dx * dx, yy = dy * dy;
+        volatile float l = sqrtf(xx + yy);
+        dir[i] = l == 0.0f ? make_float2(dx, dy) : make_float2(dx / l, dy / l);
+    }
     if (n > 0) {
         CUDA_TRY(s, cudaMemcpyAsync(s->d_obst_xy.p, xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(s, cudaMemcpyAsync(s->d_obst_next.p, next, sizeof(int) * n, cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(s, cudaMemcpyAsync(s->d_obst_prev.p, prev, sizeof(int) * n, cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(s, cudaMemcpyAsync(s->d_obst_convex.p, convex, n, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_obst_dir.p, dir.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     }
     s->have_obst = true;
@@ -1149,6 +1164,7 @@ int ecmgpu_find_neighbors(ecmgpu_sim* s, int count, int* out_ids5, int* out_coun
         int rc = ensure_ready(s);
         if (rc) return rc;
         TickView t = make_view(s);
+        t.gather = 0;  // no k_attract in this path: k_scatter writes the full snapshot rows
         if (s->strips_on) {
             if (s->local_transport && s->n_ranks > 1)
                 return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_find_neighbors is not available with in-process strips");
