@@ -44,8 +44,10 @@ struct StripView {
     float lo, hi, halo;  // lo = -inf on rank 0, hi = +inf on the last rank
     int cap_halo, cap_migr, cap_self;
     // message = [MsgHeader][HaloEntry x cap_halo][MigrantEntry x cap_migr]; index 0 = left, 1 = right
-    unsigned char* send[2];
+    unsigned char* send[2];   // where the entries of the outgoing message are written: a local staging buffer (NCCL /
+                              // in-process transports) or the neighbour's inbox itself, mapped over NVLink (peer transport)
     unsigned char* recv[2];
+    MsgHeader* send_hdr[2];   // local header the pack kernel counts in (== send[d] unless the peer transport is on)
     HaloEntry* self_ghost;
     int* self_ghost_n;
     int* g_key;   // [2*cap_halo + cap_self] cell key of ghost g
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(256) k_pack(int n_slots, AgentArrays ag, Strip
     if (dir >= 0) {  // left the strip: hand over, keep as a ghost for the coming tick
         const float2 v = ag.vel[i];
         unsigned char* m = sv.send[dir];
-        int e = atomicAdd(&sv.hdr(m)->n_migrants, 1);
+        int e = atomicAdd(&sv.send_hdr[dir]->n_migrants, 1);
         if (e < sv.cap_migr) {
             MigrantEntry me;
             me.slot = i; me.x = p.x; me.y = p.y; me.vx = v.x; me.vy = v.y;
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(256) k_pack(int n_slots, AgentArrays ag, Strip
         const bool near = d == 0 ? p.x < sv.lo + sv.halo : p.x >= sv.hi - sv.halo;
         if (has && near) {
             unsigned char* m = sv.send[d];
-            int e = atomicAdd(&sv.hdr(m)->n_halo, 1);
+            int e = atomicAdd(&sv.send_hdr[d]->n_halo, 1);
             if (e < sv.cap_halo) {
                 const float2 v = ag.vel[i];
                 HaloEntry he; he.slot = i; he.x = p.x; he.y = p.y; he.vx = v.x; he.vy = v.y;
@@ -110,6 +112,34 @@ __global__ void __launch_bounds__(256) k_pack(int n_slots, AgentArrays ag, Strip
             } else atomicAdd(&counters[C_TOTAL_HALO_MISS], 1ull);
         }
     }
+}
+
+// Peer transport: the entries were stored straight into the neighbour's inbox by k_pack (NVLink
+// peer stores).  k_publish completes the message: counts, then - after a system-scope fence - the
+// sequence number the neighbour's k_await spins on.  Inboxes are double-buffered by sequence parity;
+// having seen the neighbour's message s-1 implies it has consumed our message s-2, so writing
+// generation s & 1 never races with its reader.
+__global__ void k_publish(StripView sv, int seq) {
+    const int d = threadIdx.x;
+    if (d >= 2) return;
+    const bool has = d == 0 ? sv.rank > 0 : sv.rank < sv.n_ranks - 1;
+    if (!has) return;
+    MsgHeader* dst = (MsgHeader*)sv.send[d];
+    const MsgHeader h = *sv.send_hdr[d];
+    dst->n_halo = h.n_halo;
+    dst->n_migrants = h.n_migrants;
+    __threadfence_system();
+    *(volatile int*)&dst->pad0 = seq;
+}
+
+__global__ void k_await(StripView sv, int seq) {
+    const int d = threadIdx.x;
+    if (d >= 2) return;
+    const bool has = d == 0 ? sv.rank > 0 : sv.rank < sv.n_ranks - 1;
+    if (!has) return;
+    volatile int* flag = &((MsgHeader*)sv.recv[d])->pad0;
+    while (*flag != seq) __nanosleep(100);
+    __threadfence_system();
 }
 
 __global__ void __launch_bounds__(256) k_unpack_migrants(AgentArrays ag, StripView sv) {

@@ -202,9 +202,8 @@ struct TickView {
     float cover_lo, cover_hi;
 };
 
-__global__ void __launch_bounds__(128) k_attract(TickView t) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = *t.n_sorted_ptr;
+// UpdateAttractionPointSystem + ApplySteeringForce for snapshot row p; convergent call (whole warp).
+__device__ __forceinline__ void attract_agent(const TickView& t, const int p, const int n) {
     const bool valid = p < n && !t.sc.s_ghost[p];
     unsigned st = 0u;
     int slot = 0, np = 2, cell = -2;
@@ -290,6 +289,10 @@ __global__ void __launch_bounds__(128) k_attract(TickView t) {
     }
 }
 
+__global__ void __launch_bounds__(128) k_attract(TickView t) {
+    attract_agent(t, blockIdx.x * blockDim.x + threadIdx.x, *t.n_sorted_ptr);
+}
+
 // ORCA + integration for one agent whose neighbour list is known.  kSync: convergent call by the
 // whole warp, lanes without work pass valid = false.
 template <bool kSync>
@@ -328,9 +331,7 @@ __device__ __forceinline__ unsigned finish_agent(const TickView& t, int p, const
 #ifndef ECM_ORCA_MINBLOCKS
 #define ECM_ORCA_MINBLOCKS 5
 #endif
-__global__ void __launch_bounds__(256, ECM_ORCA_MINBLOCKS) k_orca(TickView t) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = *t.n_sorted_ptr;
+__device__ __forceinline__ void orca_agent(const TickView& t, const int p, const int n) {
     unsigned st = 0u;
     const bool mine = p < n && !t.sc.s_ghost[p] && t.sc.s_alive[p];
     Knn k;
@@ -356,6 +357,21 @@ __global__ void __launch_bounds__(256, ECM_ORCA_MINBLOCKS) k_orca(TickView t) {
         if (m_lp3) atomicAdd(&t.sc.counters[C_TOTAL_LP3D], (unsigned long long)__popc(m_lp3));
         if (m_fb) atomicAdd(&t.sc.counters[C_TOTAL_FALLBACK], (unsigned long long)__popc(m_fb));
     }
+}
+
+__global__ void __launch_bounds__(256, ECM_ORCA_MINBLOCKS) k_orca(TickView t) {
+    orca_agent(t, blockIdx.x * blockDim.x + threadIdx.x, *t.n_sorted_ptr);
+}
+
+// The whole per-agent tick in one kernel: the attraction phase is memory-latency bound (polyline
+// and header gathers), the ORCA phases are issue bound; with CTAs of one SM sitting in different
+// phases the two overlap instead of running back to back as k_attract + k_orca.
+__global__ void __launch_bounds__(256, ECM_ORCA_MINBLOCKS) k_tick(TickView t) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *t.n_sorted_ptr;
+    attract_agent(t, p, n);  // writes s_pref[p] / s_alive[p], read back by the same thread below
+    __syncthreads();         // phase barrier
+    orca_agent(t, p, n);
 }
 
 // mode 0: full tick for the listed agents; mode 1: neighbour query only (ecmgpu_find_neighbors)

@@ -107,7 +107,13 @@ struct ecmgpu_sim {
     ecmgpu_sim* peer[2] = {nullptr, nullptr};  // in-process transport: left / right neighbour handles
     bool local_transport = false;
     cudaEvent_t ev_packed = nullptr, ev_pulled = nullptr;
-    DevBuf<unsigned char> d_send[2], d_recv[2], d_s_ghost;
+    DevBuf<unsigned char> d_send[2], d_recv[2], d_s_ghost;  // d_recv holds two generations (peer transport)
+    // peer transport: neighbours' inboxes mapped through CUDA IPC, messages written in place over NVLink
+    bool p2p = false;
+    unsigned char* peer_inbox[2] = {nullptr, nullptr};  // [0] = left neighbour's recv[1], [1] = right neighbour's recv[0]
+    DevBuf<MsgHeader> d_send_hdr;
+    unsigned comm_seq = 1;   // sequence number of the next exchange
+    unsigned cur_gen = 0;    // inbox generation of the exchange in flight / last completed (fixed at pack time)
     DevBuf<HaloEntry> d_self_ghost;
     DevBuf<int> d_self_ghost_n, d_g_key, d_g_rank;
 
@@ -129,6 +135,7 @@ struct ecmgpu_sim {
     bool ev_valid = false;
     int max_ring = 8;
     int orca_block = 256;  // CTA size of k_orca (env ECMGPU_ORCA_BLOCK for experiments)
+    bool fused = false;    // k_tick (attraction + ORCA in one kernel); profiling mode times k_attract / k_orca separately; env ECMGPU_FUSED=0
     bool gather = false;   // snapshot rows built by k_attract (gather) instead of k_scatter: measured neutral (profiles/r01_experiments.md); env ECMGPU_GATHER=1
     // ---- the tick as a CUDA graph (one launch instead of ~15 kernel / memset / NCCL submissions)
     bool use_graph = true;         // env ECMGPU_GRAPH=0 disables
@@ -475,7 +482,14 @@ void comm_teardown(ecmgpu_sim* s) {
     if (s->ev_packed) cudaEventDestroy(s->ev_packed);
     if (s->ev_pulled) cudaEventDestroy(s->ev_pulled);
     s->ev_packed = s->ev_pulled = nullptr;
-    for (int d = 0; d < 2; d++) { s->d_send[d].free(); s->d_recv[d].free(); }
+    for (int d = 0; d < 2; d++) {
+        if (s->peer_inbox[d]) cudaIpcCloseMemHandle(s->peer_inbox[d]);
+        s->peer_inbox[d] = nullptr;
+        s->d_send[d].free();
+        s->d_recv[d].free();
+    }
+    s->d_send_hdr.free();
+    s->p2p = false;
     s->d_s_ghost.free(); s->d_self_ghost.free(); s->d_self_ghost_n.free(); s->d_g_key.free(); s->d_g_rank.free();
 }
 
@@ -491,7 +505,18 @@ StripView make_strip_view(ecmgpu_sim* s) {
     v.cap_halo = s->cap_halo;
     v.cap_migr = s->cap_migr;
     v.cap_self = s->cap_self;
-    for (int d = 0; d < 2; d++) { v.send[d] = s->d_send[d].p; v.recv[d] = s->d_recv[d].p; }
+    const size_t msg = strip_msg_bytes(s->cap_halo, s->cap_migr);
+    const size_t gen = s->p2p ? (size_t)s->cur_gen * msg : 0;
+    for (int d = 0; d < 2; d++) {
+        v.recv[d] = s->d_recv[d].p ? s->d_recv[d].p + gen : nullptr;
+        if (s->p2p) {
+            v.send[d] = s->peer_inbox[d] ? s->peer_inbox[d] + gen : s->d_send[d].p;
+            v.send_hdr[d] = s->d_send_hdr.p + d;
+        } else {
+            v.send[d] = s->d_send[d].p;
+            v.send_hdr[d] = (MsgHeader*)s->d_send[d].p;
+        }
+    }
     v.self_ghost = s->d_self_ghost.p;
     v.self_ghost_n = s->d_self_ghost_n.p;
     v.g_key = s->d_g_key.p;
@@ -501,11 +526,13 @@ StripView make_strip_view(ecmgpu_sim* s) {
 
 // phase 0: pack halo / migrant / self-ghost lists from the current state
 int enqueue_pack(ecmgpu_sim* s, const TickView& t) {
+    s->cur_gen = s->comm_seq & 1u;
     StripView sv = make_strip_view(s);
     if (s->local_transport)  // neighbours must have pulled last tick's messages before we overwrite them
         for (int d = 0; d < 2; d++)
             if (s->peer[d]) CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->peer[d]->ev_pulled, 0));
-    for (int d = 0; d < 2; d++) CUDA_TRY(s, cudaMemsetAsync(s->d_send[d].p, 0, sizeof(MsgHeader), s->stream));
+    if (s->p2p) CUDA_TRY(s, cudaMemsetAsync(s->d_send_hdr.p, 0, 2 * sizeof(MsgHeader), s->stream));
+    else for (int d = 0; d < 2; d++) CUDA_TRY(s, cudaMemsetAsync(s->d_send[d].p, 0, sizeof(MsgHeader), s->stream));
     CUDA_TRY(s, cudaMemsetAsync(s->d_self_ghost_n.p, 0, sizeof(int), s->stream));
     k_pack<<<div_up(s->n_slots, 256), 256, 0, s->stream>>>(s->n_slots, t.ag, sv, s->d_counters.p);
     s->launches++;
@@ -528,6 +555,10 @@ int enqueue_exchange(ecmgpu_sim* s, const TickView& t) {
             CUDA_TRY(s, cudaMemcpyPeerAsync(s->d_recv[d].p, s->prm.device, p->d_send[1 - d].p, p->prm.device, msg, s->stream));
         }
         CUDA_TRY(s, cudaEventRecord(s->ev_pulled, s->stream));
+    } else if (s->p2p) {
+        k_publish<<<1, 32, 0, s->stream>>>(sv, (int)s->comm_seq);
+        k_await<<<1, 32, 0, s->stream>>>(sv, (int)s->comm_seq);
+        s->launches += 2;
     } else if (s->n_ranks > 1) {
         NCCL_TRY(s, g_nccl.GroupStart());
         if (s->rank > 0) {
@@ -542,6 +573,7 @@ int enqueue_exchange(ecmgpu_sim* s, const TickView& t) {
     }
     k_unpack_migrants<<<div_up(std::max(s->cap_migr, 1), 256), 256, 0, s->stream>>>(t.ag, sv);
     s->launches++;
+    s->comm_seq++;  // the next exchange uses the other inbox generation
     CUDA_TRY(s, cudaGetLastError());
     return ECMGPU_OK;
 }
@@ -727,6 +759,7 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
     s->h_path_hdr.assign(n, PathHdr{0, 0, 0.0f, 0.0f});
     if (const char* e = getenv("ECMGPU_GRAPH")) s->use_graph = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_GATHER")) s->gather = atoi(e) != 0;
+    if (const char* e = getenv("ECMGPU_FUSED")) s->fused = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_ORCA_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) s->orca_block = v; }
     s->h_path_pool.reserve(std::min<size_t>(pool, 1 << 20));
     *out = s;
@@ -933,10 +966,14 @@ int ecmgpu_update_phase(ecmgpu_sim* s, int phase) {
     if (rc) return rc;
     if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[1], s->stream));
     const int nb = div_up(s->n_slots + (s->strips_on ? 2 * s->cap_halo + s->cap_self : 0), 128);
-    k_attract<<<nb, 128, 0, s->stream>>>(t);
-    if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
-    {
-        const int ob = s->orca_block;
+    const int ob = s->orca_block;
+    if (s->fused) {
+        if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));  // "attract" phase is empty: all of it is k_tick
+        k_tick<<<div_up(nb * 128, ob), ob, 0, s->stream>>>(t);
+        s->launches -= 1;  // one kernel instead of two (3 are added below)
+    } else {
+        k_attract<<<nb, 128, 0, s->stream>>>(t);
+        if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
         k_orca<<<div_up(nb * 128, ob), ob, 0, s->stream>>>(t);
     }
     k_fallback<<<148, 128, 0, s->stream>>>(t, 0);
@@ -953,7 +990,7 @@ int ecmgpu_update(ecmgpu_sim* s) {
         return fail(s, ECMGPU_ERR_INVALID, "in-process strips: drive all handles with ecmgpu_update_phase(0), (1), (2)");
     // NCCL send/recv are kept out of graph capture (capturing them hung on 4 x B200 with NCCL 2.28): with the
     // NCCL transport the tick is submitted launch by launch
-    const bool nccl_tick = s->strips_on && !s->local_transport && s->n_ranks > 1;
+    const bool nccl_tick = s->strips_on && !s->local_transport && s->n_ranks > 1;  // also the peer transport: its sequence number changes per tick
     if (s->use_graph && !nccl_tick && !s->profiling && s->n_slots > 0) {
         CUDA_TRY(s, cudaSetDevice(s->prm.device));
         int rc = ensure_ready(s);  // host-side (re)builds happen outside the capture
@@ -1321,6 +1358,43 @@ int ecmgpu_comm_init_local(ecmgpu_sim* s, int rank, int n_ranks, ecmgpu_sim* lef
     return ECMGPU_OK;
 }
 
+int ecmgpu_comm_p2p_export(ecmgpu_sim* s, uint8_t out_handles[128]) {
+    if (!s || !out_handles) return ECMGPU_ERR_INVALID;
+    if (!s->strips_on || !s->d_recv[0].p) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_comm_p2p_export: call ecmgpu_comm_set_strips first");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    for (int d = 0; d < 2; d++) {
+        cudaIpcMemHandle_t h;
+        CUDA_TRY(s, cudaIpcGetMemHandle(&h, s->d_recv[d].p));
+        memcpy(out_handles + 64 * d, &h, 64);
+    }
+    return ECMGPU_OK;
+}
+
+int ecmgpu_comm_p2p_connect(ecmgpu_sim* s, const uint8_t* left_handles, const uint8_t* right_handles) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (!s->strips_on) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_comm_p2p_connect: call ecmgpu_comm_set_strips first");
+    if ((s->rank > 0) != (left_handles != nullptr) || (s->rank < s->n_ranks - 1) != (right_handles != nullptr))
+        return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_comm_p2p_connect: handles must match the rank's neighbours");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    const uint8_t* src[2] = {left_handles ? left_handles + 64 : nullptr,   // left neighbour's RIGHT inbox
+                             right_handles ? right_handles : nullptr};     // right neighbour's LEFT inbox
+    for (int d = 0; d < 2; d++) {
+        if (!src[d]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, src[d], 64);
+        void* p = nullptr;
+        CUDA_TRY(s, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_inbox[d] = (unsigned char*)p;
+    }
+    CUDA_TRY(s, s->d_send_hdr.alloc(2));
+    CUDA_TRY(s, cudaMemsetAsync(s->d_send_hdr.p, 0, 2 * sizeof(MsgHeader), s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    s->p2p = true;
+    s->config_epoch++;
+    return ECMGPU_OK;
+}
+
 int ecmgpu_comm_set_strips(ecmgpu_sim* s, const float* bounds, float halo_width) {
     if (!s) return ECMGPU_ERR_INVALID;
     if (!bounds || !(halo_width > 0.0f)) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_comm_set_strips: bad arguments");
@@ -1362,9 +1436,9 @@ int ecmgpu_comm_set_strips(ecmgpu_sim* s, const float* bounds, float halo_width)
     const size_t msg = strip_msg_bytes(s->cap_halo, s->cap_migr);
     for (int d = 0; d < 2; d++) {
         CUDA_TRY(s, s->d_send[d].alloc(msg));
-        CUDA_TRY(s, s->d_recv[d].alloc(msg));
+        CUDA_TRY(s, s->d_recv[d].alloc(2 * msg));  // two generations for the peer transport
         CUDA_TRY(s, cudaMemsetAsync(s->d_send[d].p, 0, sizeof(MsgHeader), s->stream));
-        CUDA_TRY(s, cudaMemsetAsync(s->d_recv[d].p, 0, sizeof(MsgHeader), s->stream));
+        CUDA_TRY(s, cudaMemsetAsync(s->d_recv[d].p, 0, 2 * msg, s->stream));
     }
     CUDA_TRY(s, s->d_self_ghost.alloc(s->cap_self));
     CUDA_TRY(s, s->d_self_ghost_n.alloc(1));

@@ -36,7 +36,7 @@ EXPORTS = [
     "ecmgpu_read", "ecmgpu_write", "ecmgpu_read_async", "ecmgpu_write_async", "ecmgpu_alloc_pinned", "ecmgpu_free_pinned",
     "ecmgpu_locate", "ecmgpu_retract", "ecmgpu_find_neighbors", "ecmgpu_find_obstacles", "ecmgpu_get_stats",
     "ecmgpu_last_tick_ms", "ecmgpu_set_profiling", "ecmgpu_mark", "ecmgpu_mark_elapsed_ms", "ecmgpu_stream", "ecmgpu_comm_unique_id", "ecmgpu_comm_init",
-    "ecmgpu_comm_set_strips", "ecmgpu_comm_init_local", "ecmgpu_update_phase", "ecmgpu_update_io", "ecmgpu_io_wait",
+    "ecmgpu_comm_set_strips", "ecmgpu_comm_init_local", "ecmgpu_update_phase", "ecmgpu_update_io", "ecmgpu_io_wait", "ecmgpu_comm_p2p_export", "ecmgpu_comm_p2p_connect",
 ]
 
 
@@ -101,6 +101,8 @@ def lib() -> C.CDLL:
         L.ecmgpu_comm_set_strips.argtypes = [vp, f32p, C.c_float]
         L.ecmgpu_comm_init_local.argtypes = [vp, C.c_int, C.c_int, vp, vp]
         L.ecmgpu_update_phase.argtypes = [vp, C.c_int]
+        L.ecmgpu_comm_p2p_export.argtypes = [vp, u8p]
+        L.ecmgpu_comm_p2p_connect.argtypes = [vp, u8p, u8p]
         L.ecmgpu_update_io.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(C.c_uint64)]
         L.ecmgpu_io_wait.argtypes = [vp, C.c_uint64]
         _lib = L
@@ -230,6 +232,16 @@ class GpuSim:
     def comm_init_local(self, rank: int, n_ranks: int, left: "GpuSim | None", right: "GpuSim | None"):
         self._ck(self.L.ecmgpu_comm_init_local(self.h, int(rank), int(n_ranks), left.h if left else None,
                                                right.h if right else None))
+
+    def comm_p2p_export(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        self._ck(self.L.ecmgpu_comm_p2p_export(self.h, buf))
+        return bytes(buf)
+
+    def comm_p2p_connect(self, left: bytes | None, right: bytes | None):
+        lb = (C.c_uint8 * 128).from_buffer_copy(left) if left is not None else None
+        rb = (C.c_uint8 * 128).from_buffer_copy(right) if right is not None else None
+        self._ck(self.L.ecmgpu_comm_p2p_connect(self.h, lb, rb))
 
     def comm_set_strips(self, bounds, halo: float):
         b = np.ascontiguousarray(bounds, np.float32)

@@ -16,6 +16,8 @@ Two transports:
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import gpu
@@ -146,6 +148,14 @@ class StripSim:
         dist.broadcast_object_list(box, src=0)
         self.sim.comm_init(box[0], rank, n_ranks)
         self.sim.comm_set_strips(self.bounds, self.halo)
+        # peer transport: halo / migrant entries are stored straight into the neighbours' inboxes over
+        # NVLink (CUDA IPC); NCCL stays initialised as the fallback transport (ECMGPU_P2P=0)
+        self.p2p = os.environ.get("ECMGPU_P2P", "1") != "0" and n_ranks > 1
+        if self.p2p:
+            blobs = [None] * n_ranks
+            dist.all_gather_object(blobs, self.sim.comm_p2p_export())
+            self.sim.comm_p2p_connect(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank < n_ranks - 1 else None)
+            dist.barrier()
 
     # the bench / tests drive a StripSim like a GpuSim
     def update(self, n: int = 1):

@@ -175,6 +175,13 @@ void* ecmgpu_stream(ecmgpu_sim* sim);
  * nccl_unique_id: 128 bytes from ecmgpu_comm_unique_id() on rank 0, distributed by the caller. */
 int ecmgpu_comm_unique_id(uint8_t out_id[128]);
 int ecmgpu_comm_init(ecmgpu_sim* sim, const uint8_t nccl_unique_id[128], int rank, int n_ranks);
+/* Peer transport (one process per GPU, same node): after ecmgpu_comm_set_strips every rank exports the
+ * CUDA-IPC handles of its two inboxes, the caller hands each rank its neighbours' 128 bytes, and from
+ * then on k_pack stores halo / migrant entries straight into the neighbour's inbox over NVLink; a
+ * sequence number written after a system-scope fence replaces the NCCL send/recv pair.
+ * left/right = the neighbour's exported bytes, NULL at the rim. */
+int ecmgpu_comm_p2p_export(ecmgpu_sim* sim, uint8_t out_handles[128]);
+int ecmgpu_comm_p2p_connect(ecmgpu_sim* sim, const uint8_t* left_handles, const uint8_t* right_handles);
 /* In-process transport instead of NCCL: all strips are handles of ONE process (on one or several
  * devices); messages move by peer copies.  left/right are the neighbouring handles (NULL at the rim).
  * With this transport a tick is driven as: ecmgpu_update_phase(h, 0) on every handle, then phase 1
