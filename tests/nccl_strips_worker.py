@@ -45,7 +45,7 @@ def main():
                "pos_equal": bool(np.array_equal(pos[a].view(np.uint32), sp[a].view(np.uint32))),
                "vel_equal": bool(np.array_equal(vel[a].view(np.uint32), sv[a].view(np.uint32))),
                "owners_ok": bool(np.array_equal(owners, act)), "halo_misses": gs["halo_misses"],
-               "moved": int(((own0 != own1) & a).sum()), "halo": strips.halo}
+               "moved": int(((own0 != own1) & a).sum()), "halo": strips.halo, "p2p": bool(strips.p2p)}
         json.dump(res, open(sys.argv[1], "w"))
     dist.barrier()
     strips.close()

@@ -93,19 +93,24 @@ def test_strip_validation_errors():
     assert_bits_equal(s2.read(gpu.POS, 0, n), s.read(gpu.POS, 0, n), "one strip == no strips")
 
 
-def test_nccl_strips_match_single_gpu_bitwise():
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_multi_process_strips_match_single_gpu_bitwise(transport):
+    """One process per GPU under torchrun.  transport = peer: entries stored into the neighbour's inbox over
+    NVLink (CUDA IPC); nccl: ncclSend/ncclRecv of the staged message."""
     import torch
 
     ngpu = torch.cuda.device_count()
     if ngpu < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     world = 2 if ngpu < 4 else 4
-    out = os.path.join(ROOT, "gpurun_out", "nccl_strips.json")
+    out = os.path.join(ROOT, "gpurun_out", f"strips_{transport}.json")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(ROOT, "tests", "nccl_strips_worker.py"), out]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+           "--master-port", "29517" if transport == "peer" else "29518", os.path.join(ROOT, "tests", "nccl_strips_worker.py"), out]
+    env = dict(os.environ, ECMGPU_P2P="1" if transport == "peer" else "0")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = json.load(open(out))
     print(res)
     assert res["pos_equal"] and res["vel_equal"] and res["halo_misses"] == 0 and res["owners_ok"] and res["moved"] > 10
+    assert res["p2p"] == (transport == "peer")
