@@ -324,7 +324,7 @@ def run_ours(args):
         if fused:
             alg["orca"] = alg["tick"]
         ach = alg[dom] * active0 / (acc[dom] * 1e-3) / 1e9
-        ach_tick = alg["tick"] * active0 / (acc["tick"] * 1e-3) / 1e9
+        ach_tick = alg["tick"] * active0 / ((ms / args.steps) * 1e-3) / 1e9  # whole tick: the timed region itself (graph launch)
         kname = "k_tick" if fused else "k_" + dom
         traffic, traffic_src = ncu_traffic(kname)
         roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
