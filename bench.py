@@ -10,7 +10,9 @@ One JSON line on stdout (rank 0).  Workload at N=1: C3, 1M agents in the 2025-bl
                simulator's stream, max over ranks)
   e2e          same metric through the C ABI with HOST buffers (ecmgpu_update_io): every tick uploads
                positions and velocities from pinned memory, runs the tick and downloads positions,
-               velocities and active flags; transfers of consecutive ticks overlap with compute
+               velocities and active flags; transfers of consecutive ticks overlap with compute.
+               With strips (N > 1) every rank moves the (slot, position, velocity) records of the
+               agents it owns (ecmgpu_update_io_owned), so the bytes per tick do not grow with N
   roofline     dominant kernel (by measured phase time) against the measured HBM copy bandwidth
   cpu_baseline the unmodified reference (oracle/_ref) on one host core, bounded sample
 
@@ -331,52 +333,92 @@ def run_ours(args):
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_agent": alg[dom],
                 "kernel_ms": acc[dom], "phase_ms": acc,
                 "whole_tick": {"achieved": ach_tick, "frac": ach_tick / peak, "algorithmic_bytes_per_agent": alg["tick"]}}
-    # ---- end to end through the C ABI with host buffers (every rank moves its full slot arrays)
+    # ---- end to end through the C ABI with host buffers.  One GPU: whole slot arrays (ecmgpu_update_io);
+    # strips: every rank moves the records of the agents it owns (ecmgpu_update_io_owned)
     e2e = None
-    if True:
-        raw = sim if world == 1 else sim.sim
+    raw = sim if world == 1 else sim.sim
+    k = max(3, min(args.steps, 50))
+    if world == 1:
         # two generations of pinned host buffers: call k uses set k & 1 while set (k-1) & 1 is still draining
         hp = [gpu.PinnedArray((n, 2), np.float32) for _ in range(2)]
         hv = [gpu.PinnedArray((n, 2), np.float32) for _ in range(2)]
         op = [gpu.PinnedArray((n, 2), np.float32) for _ in range(2)]
         ov = [gpu.PinnedArray((n, 2), np.float32) for _ in range(2)]
         oa = [gpu.PinnedArray((n,), np.uint8) for _ in range(2)]
+        bufs = hp + hv + op + ov + oa
         p0, v0 = raw.read(gpu.POS, 0, n), raw.read(gpu.VEL, 0, n)
         for g in range(2):
             hp[g].array[:] = p0
             hv[g].array[:] = v0
-        k = max(3, min(args.steps, 50))
-        ha = oa[(k - 1) & 1]
+        moved = [0, 0]
 
-        def e2e_run(steps):
-            last = None
-            for i in range(steps):
-                g = i & 1
-                tk = raw.update_io(n, hp[g], hv[g], op[g], ov[g], oa[g])  # H2D pos+vel | tick | D2H pos+vel+active
-                if last is not None:
-                    raw.io_wait(last)  # the host consumes tick i-1's results while tick i is in flight
-                last = tk
-            raw.io_wait(last)
+        def io_call(i):
+            g = i & 1
+            moved[0] += 16 * n
+            moved[1] += 17 * n
+            return raw.update_io(n, hp[g], hv[g], op[g], ov[g], oa[g])  # H2D pos+vel | tick | D2H pos+vel+active
 
-        e2e_run(2)
-        barrier()
-        t0 = time.perf_counter()
-        e2e_run(k)
-        barrier()
-        dt = time.perf_counter() - t0
-        act = int((ha.array > 0).sum())
-        if world > 1:
-            import torch.distributed as dist
+        def io_result(i):
+            return int((oa[i & 1].array > 0).sum())
+    else:
+        act_now = raw.read(gpu.ACTIVE, 0, n) > 0
+        ids = np.flatnonzero(act_now)
+        p0, v0 = raw.read(gpu.POS, 0, n), raw.read(gpu.VEL, 0, n)
+        cap = n
+        rin = [gpu.PinnedArray((cap,), gpu.AGENT_REC) for _ in range(2)]
+        rout = [gpu.PinnedArray((cap,), gpu.AGENT_REC) for _ in range(2)]
+        cnt = [gpu.PinnedArray((1,), np.int32) for _ in range(2)]
+        bufs = rin + rout + cnt
+        for g in range(2):
+            r = rin[g].array
+            r["slot"][: len(ids)] = ids
+            r["x"][: len(ids)], r["y"][: len(ids)] = p0[ids, 0], p0[ids, 1]
+            r["vx"][: len(ids)], r["vy"][: len(ids)] = v0[ids, 0], v0[ids, 1]
+        moved = [0, 0]
+        rec_b = gpu.AGENT_REC.itemsize
 
-            t = torch.tensor([dt, float(act)], device="cuda", dtype=torch.float64)
-            tmax = t.clone()
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            dt, act = float(tmax[0].item()), int(t[1].item())
-        e2e = {"value": act * k / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * n * world, "d2h_bytes_per_step": 17 * n * world,
-               "ms_per_step": 1e3 * dt / k, "steps": k}
-        for a in hp + hv + op + ov + oa:
-            a.free()
+        def io_call(i):
+            g = i & 1
+            moved[0] += rec_b * len(ids)
+            return raw.update_io_owned(len(ids), rin[g], rout[g], cnt[g])  # H2D owned records | tick | D2H owned records
+
+        def io_result(i):
+            m = int(cnt[i & 1].array[0])
+            moved[1] += rec_b * m + 4  # lower bound: the copy is sized from the last confirmed count plus migrant room
+            return m
+
+    def e2e_run(steps):
+        last, res = None, 0
+        for i in range(steps):
+            tk = io_call(i)
+            if last is not None:
+                raw.io_wait(last)  # the host consumes tick i-1's results while tick i is in flight
+                res = io_result(i - 1)
+            last = tk
+        raw.io_wait(last)
+        return io_result(steps - 1)
+
+    e2e_run(4)
+    moved[0] = moved[1] = 0
+    barrier()
+    t0 = time.perf_counter()
+    act = e2e_run(k)
+    barrier()
+    dt = time.perf_counter() - t0
+    h2d, d2h = moved[0] / k, moved[1] / k
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([dt, float(act), h2d, d2h], device="cuda", dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dt, act, h2d, d2h = float(tmax[0].item()), int(t[1].item()), float(t[2].item()), float(t[3].item())
+    e2e = {"value": act * k / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": 1e3 * dt / k, "steps": k,
+           "api": "ecmgpu_update_io (whole slot arrays)" if world == 1 else "ecmgpu_update_io_owned (records of the agents each rank owns)"}
+    for a in bufs:
+        a.free()
     clk = clocks.stop()  # sampled over all timed regions (resident ticks, per-phase pass, end-to-end ticks)
 
     global_active = int(active0)

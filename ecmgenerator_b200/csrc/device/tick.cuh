@@ -442,4 +442,39 @@ __global__ void k_find_obstacles(ObstView ob, BinView bins, float2 pos, float ra
     if (threadIdx.x == 0 && blockIdx.x == 0) *out_n = find_obstacles<false>(ob, bins, pos, range2, out, cap);
 }
 
+// ---- host I/O as records of owned agents (ecmgpu_update_io_owned) --------------------------------
+struct AgentRec {  // == ecmgpu_agent_rec (include/ecm_b200.h)
+    int slot;
+    float x, y, vx, vy;
+};
+
+// Host-provided state: position and velocity of the listed slots, where this handle owns them.
+__global__ void __launch_bounds__(256) k_apply_records(int n, const AgentRec* __restrict__ rec, int max_slots, const unsigned char* __restrict__ active,
+                                                       float2* __restrict__ pos, float2* __restrict__ vel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const AgentRec r = rec[i];
+    if (r.slot < 0 || r.slot >= max_slots || !active[r.slot]) return;
+    pos[r.slot] = make_float2(r.x, r.y);
+    vel[r.slot] = make_float2(r.vx, r.vy);
+}
+
+// Compacts the owned agents into records (one atomic per warp; ascending slots within a warp).
+__global__ void __launch_bounds__(256) k_collect_owned(int n_slots, const unsigned char* __restrict__ active, const float2* __restrict__ pos,
+                                                       const float2* __restrict__ vel, AgentRec* __restrict__ out, int* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool mine = i < n_slots && active[i];
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    if (m == 0u) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (!mine) return;
+    const float2 p = pos[i], v = vel[i];
+    AgentRec r;
+    r.slot = i; r.x = p.x; r.y = p.y; r.vx = v.x; r.vy = v.y;
+    out[base + __popc(m & ((1u << lane) - 1u))] = r;
+}
+
 }  // namespace ecm

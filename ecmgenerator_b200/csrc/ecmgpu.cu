@@ -127,8 +127,17 @@ struct ecmgpu_sim {
         bool ready = false;
         int cap = 0;
         cudaStream_t s_in = nullptr, s_out = nullptr;
-        float2 *in_pos[2] = {nullptr, nullptr}, *in_vel[2] = {nullptr, nullptr}, *out_pos[2] = {nullptr, nullptr}, *out_vel[2] = {nullptr, nullptr};
-        unsigned char* out_act[2] = {nullptr, nullptr};
+        // staging, two generations each.  Dense calls: in = [pos 8n | vel 8n], out = [pos 8n | vel 8n | active n];
+        // owned calls: in = records, out = [32 B header with the count | records]
+        unsigned char *in_buf[2] = {nullptr, nullptr}, *out_buf[2] = {nullptr, nullptr};
+        // owned calls: where the count of generation b lands on the host, how many records were copied for it
+        const int32_t* owned_count[2] = {nullptr, nullptr};
+        int owned_copied[2] = {0, 0};
+        // upper bound of the number of agents this handle owns, as far as the host can know it without a
+        // synchronisation: the count confirmed by the last ecmgpu_io_wait plus the migrants every tick
+        // enqueued since may have brought in; < 0 = unknown (everything is copied)
+        long long owned_confirmed = -1;
+        uint64_t owned_confirmed_ticket = 0;
         cudaEvent_t in_done[2] = {nullptr, nullptr}, in_consumed[2] = {nullptr, nullptr}, tick_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
         uint64_t calls = 0;
     } io;
@@ -787,7 +796,7 @@ void ecmgpu_destroy(ecmgpu_sim* s) {
         cudaStreamSynchronize(s->io.s_in);
         cudaStreamSynchronize(s->io.s_out);
         for (int b = 0; b < 2; b++) {
-            cudaFree(s->io.in_pos[b]); cudaFree(s->io.in_vel[b]); cudaFree(s->io.out_pos[b]); cudaFree(s->io.out_vel[b]); cudaFree(s->io.out_act[b]);
+            cudaFree(s->io.in_buf[b]); cudaFree(s->io.out_buf[b]);
             cudaEventDestroy(s->io.in_done[b]); cudaEventDestroy(s->io.in_consumed[b]); cudaEventDestroy(s->io.tick_done[b]); cudaEventDestroy(s->io.out_done[b]);
         }
         cudaStreamDestroy(s->io.s_in);
@@ -871,6 +880,7 @@ int ecmgpu_bulk_load(ecmgpu_sim* s, int n, const int* slots, const float* pos_xy
         hi = std::max(hi, slot + 1);
     }
     s->n_slots = hi;
+    s->io.owned_confirmed = -1;
     // host staging in slot order when contiguous, otherwise per-element copies
     const bool contiguous = [&] {
         if (!slots) return true;
@@ -1072,6 +1082,7 @@ static int xfer(ecmgpu_sim* s, int which, void* host, int first, int count, bool
     if (wait) CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     if (!to_host && (which == ECMGPU_RADIUS || which == ECMGPU_SPEED)) s->bins_dirty = true;  // ranges may have grown
     if (!to_host) s->n_slots = std::max(s->n_slots, which == ECMGPU_ACTIVE ? first + count : s->n_slots);
+    if (!to_host && which == ECMGPU_ACTIVE) s->io.owned_confirmed = -1;
     return ECMGPU_OK;
 }
 int ecmgpu_read(ecmgpu_sim* s, int which, void* dst, int first, int count) { return xfer(s, which, dst, first, count, true, true); }
@@ -1082,56 +1093,113 @@ int ecmgpu_write_async(ecmgpu_sim* s, int which, const void* src, int first, int
 // One tick with host I/O, pipelined: upload (copy stream A) -> tick (main stream) -> download (copy
 // stream B).  Consecutive calls overlap: while tick k computes, the inputs of k+1 are already on
 // their way and the results of k-1 are still draining.  Device staging is double-buffered.
+static int io_prepare(ecmgpu_sim* s) {
+    auto& io = s->io;
+    if (io.ready) return ECMGPU_OK;
+    const size_t n = (size_t)s->prm.max_agents;
+    CUDA_TRY(s, cudaStreamCreateWithFlags(&io.s_in, cudaStreamNonBlocking));
+    CUDA_TRY(s, cudaStreamCreateWithFlags(&io.s_out, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+        CUDA_TRY(s, cudaMalloc((void**)&io.in_buf[b], sizeof(ecmgpu_agent_rec) * n + 32));
+        CUDA_TRY(s, cudaMalloc((void**)&io.out_buf[b], sizeof(ecmgpu_agent_rec) * n + 32));
+        CUDA_TRY(s, cudaEventCreateWithFlags(&io.in_done[b], cudaEventDisableTiming));
+        CUDA_TRY(s, cudaEventCreateWithFlags(&io.in_consumed[b], cudaEventDisableTiming));
+        CUDA_TRY(s, cudaEventCreateWithFlags(&io.tick_done[b], cudaEventDisableTiming));
+        CUDA_TRY(s, cudaEventCreateWithFlags(&io.out_done[b], cudaEventDisableTiming));
+        CUDA_TRY(s, cudaEventRecord(io.in_consumed[b], s->stream));
+        CUDA_TRY(s, cudaEventRecord(io.out_done[b], io.s_out));
+    }
+    io.ready = true;
+    return ECMGPU_OK;
+}
+
 int ecmgpu_update_io(ecmgpu_sim* s, int count, const float* in_pos, const float* in_vel, float* out_pos, float* out_vel,
                      uint8_t* out_active, uint64_t* ticket) {
     if (!s) return ECMGPU_ERR_INVALID;
     if (count < 0 || count > s->prm.max_agents) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_update_io: bad count");
     CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    int rc = io_prepare(s);
+    if (rc) return rc;
     auto& io = s->io;
-    if (!io.ready) {
-        const size_t n = (size_t)s->prm.max_agents;
-        CUDA_TRY(s, cudaStreamCreateWithFlags(&io.s_in, cudaStreamNonBlocking));
-        CUDA_TRY(s, cudaStreamCreateWithFlags(&io.s_out, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; b++) {
-            CUDA_TRY(s, cudaMalloc((void**)&io.in_pos[b], sizeof(float2) * n));
-            CUDA_TRY(s, cudaMalloc((void**)&io.in_vel[b], sizeof(float2) * n));
-            CUDA_TRY(s, cudaMalloc((void**)&io.out_pos[b], sizeof(float2) * n));
-            CUDA_TRY(s, cudaMalloc((void**)&io.out_vel[b], sizeof(float2) * n));
-            CUDA_TRY(s, cudaMalloc((void**)&io.out_act[b], n));
-            CUDA_TRY(s, cudaEventCreateWithFlags(&io.in_done[b], cudaEventDisableTiming));
-            CUDA_TRY(s, cudaEventCreateWithFlags(&io.in_consumed[b], cudaEventDisableTiming));
-            CUDA_TRY(s, cudaEventCreateWithFlags(&io.tick_done[b], cudaEventDisableTiming));
-            CUDA_TRY(s, cudaEventCreateWithFlags(&io.out_done[b], cudaEventDisableTiming));
-            CUDA_TRY(s, cudaEventRecord(io.in_consumed[b], s->stream));
-            CUDA_TRY(s, cudaEventRecord(io.out_done[b], io.s_out));
-        }
-        io.ready = true;
-    }
     const int b = (int)(io.calls & 1);
-    const size_t c = (size_t)count;
+    const size_t c = (size_t)count, n8 = sizeof(float2) * (size_t)s->prm.max_agents;
+    unsigned char *si = io.in_buf[b], *so = io.out_buf[b];
     // upload into staging b once the tick that last used it has consumed it
     CUDA_TRY(s, cudaStreamWaitEvent(io.s_in, io.in_consumed[b], 0));
-    if (in_pos) CUDA_TRY(s, cudaMemcpyAsync(io.in_pos[b], in_pos, sizeof(float2) * c, cudaMemcpyHostToDevice, io.s_in));
-    if (in_vel) CUDA_TRY(s, cudaMemcpyAsync(io.in_vel[b], in_vel, sizeof(float2) * c, cudaMemcpyHostToDevice, io.s_in));
+    if (in_pos) CUDA_TRY(s, cudaMemcpyAsync(si, in_pos, sizeof(float2) * c, cudaMemcpyHostToDevice, io.s_in));
+    if (in_vel) CUDA_TRY(s, cudaMemcpyAsync(si + n8, in_vel, sizeof(float2) * c, cudaMemcpyHostToDevice, io.s_in));
     CUDA_TRY(s, cudaEventRecord(io.in_done[b], io.s_in));
     // main stream: adopt the inputs, tick, publish the results
     CUDA_TRY(s, cudaStreamWaitEvent(s->stream, io.in_done[b], 0));
-    if (in_pos) CUDA_TRY(s, cudaMemcpyAsync(s->d_pos.p, io.in_pos[b], sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
-    if (in_vel) CUDA_TRY(s, cudaMemcpyAsync(s->d_vel.p, io.in_vel[b], sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
+    if (in_pos) CUDA_TRY(s, cudaMemcpyAsync(s->d_pos.p, si, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
+    if (in_vel) CUDA_TRY(s, cudaMemcpyAsync(s->d_vel.p, si + n8, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
     CUDA_TRY(s, cudaEventRecord(io.in_consumed[b], s->stream));
-    int rc = ecmgpu_update(s);
+    rc = ecmgpu_update(s);
     if (rc) return rc;
     CUDA_TRY(s, cudaStreamWaitEvent(s->stream, io.out_done[b], 0));  // the download that last read staging b is over
-    if (out_pos) CUDA_TRY(s, cudaMemcpyAsync(io.out_pos[b], s->d_pos.p, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
-    if (out_vel) CUDA_TRY(s, cudaMemcpyAsync(io.out_vel[b], s->d_vel.p, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
-    if (out_active) CUDA_TRY(s, cudaMemcpyAsync(io.out_act[b], s->d_active.p, c, cudaMemcpyDeviceToDevice, s->stream));
+    if (out_pos) CUDA_TRY(s, cudaMemcpyAsync(so, s->d_pos.p, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
+    if (out_vel) CUDA_TRY(s, cudaMemcpyAsync(so + n8, s->d_vel.p, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
+    if (out_active) CUDA_TRY(s, cudaMemcpyAsync(so + 2 * n8, s->d_active.p, c, cudaMemcpyDeviceToDevice, s->stream));
     CUDA_TRY(s, cudaEventRecord(io.tick_done[b], s->stream));
     // download
     CUDA_TRY(s, cudaStreamWaitEvent(io.s_out, io.tick_done[b], 0));
-    if (out_pos) CUDA_TRY(s, cudaMemcpyAsync(out_pos, io.out_pos[b], sizeof(float2) * c, cudaMemcpyDeviceToHost, io.s_out));
-    if (out_vel) CUDA_TRY(s, cudaMemcpyAsync(out_vel, io.out_vel[b], sizeof(float2) * c, cudaMemcpyDeviceToHost, io.s_out));
-    if (out_active) CUDA_TRY(s, cudaMemcpyAsync(out_active, io.out_act[b], c, cudaMemcpyDeviceToHost, io.s_out));
+    if (out_pos) CUDA_TRY(s, cudaMemcpyAsync(out_pos, so, sizeof(float2) * c, cudaMemcpyDeviceToHost, io.s_out));
+    if (out_vel) CUDA_TRY(s, cudaMemcpyAsync(out_vel, so + n8, sizeof(float2) * c, cudaMemcpyDeviceToHost, io.s_out));
+    if (out_active) CUDA_TRY(s, cudaMemcpyAsync(out_active, so + 2 * n8, c, cudaMemcpyDeviceToHost, io.s_out));
     CUDA_TRY(s, cudaEventRecord(io.out_done[b], io.s_out));
+    io.owned_count[b] = nullptr;
+    if (ticket) *ticket = io.calls;
+    io.calls++;
+    return ECMGPU_OK;
+}
+
+// The same pipeline moving only the agents this handle owns, as (slot, position, velocity) records:
+// with strips every rank transfers its share of the crowd instead of all slots.
+int ecmgpu_update_io_owned(ecmgpu_sim* s, int n_in, const ecmgpu_agent_rec* in, ecmgpu_agent_rec* out, int out_cap, int32_t* out_count,
+                           uint64_t* ticket) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (n_in < 0 || n_in > s->prm.max_agents || (n_in > 0 && !in)) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_update_io_owned: bad input records");
+    if (!out || !out_count || out_cap < 0) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_update_io_owned: bad output buffer");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    int rc = io_prepare(s);
+    if (rc) return rc;
+    auto& io = s->io;
+    const int b = (int)(io.calls & 1);
+    static_assert(sizeof(AgentRec) == sizeof(ecmgpu_agent_rec), "record layout");
+    AgentRec* si = (AgentRec*)io.in_buf[b];
+    int* so_count = (int*)io.out_buf[b];
+    AgentRec* so = (AgentRec*)(io.out_buf[b] + 32);
+    CUDA_TRY(s, cudaStreamWaitEvent(io.s_in, io.in_consumed[b], 0));
+    if (n_in) CUDA_TRY(s, cudaMemcpyAsync(si, in, sizeof(ecmgpu_agent_rec) * (size_t)n_in, cudaMemcpyHostToDevice, io.s_in));
+    CUDA_TRY(s, cudaEventRecord(io.in_done[b], io.s_in));
+    CUDA_TRY(s, cudaStreamWaitEvent(s->stream, io.in_done[b], 0));
+    if (n_in) {
+        k_apply_records<<<div_up(n_in, 256), 256, 0, s->stream>>>(n_in, si, s->prm.max_agents, s->d_active.p, s->d_pos.p, s->d_vel.p);
+        s->launches++;
+    }
+    CUDA_TRY(s, cudaEventRecord(io.in_consumed[b], s->stream));
+    rc = ecmgpu_update(s);
+    if (rc) return rc;
+    CUDA_TRY(s, cudaStreamWaitEvent(s->stream, io.out_done[b], 0));
+    CUDA_TRY(s, cudaMemsetAsync(so_count, 0, sizeof(int), s->stream));
+    if (s->n_slots > 0) {
+        k_collect_owned<<<div_up(s->n_slots, 256), 256, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, s->d_vel.p, so, so_count);
+        s->launches++;
+    }
+    CUDA_TRY(s, cudaEventRecord(io.tick_done[b], s->stream));
+    // how many records to bring back: the host cannot know the count of this tick yet
+    long long bound = s->n_slots;
+    if (io.owned_confirmed >= 0) {
+        const long long per_tick = s->strips_on ? 2ll * s->cap_migr : 0ll;
+        bound = std::min(bound, io.owned_confirmed + per_tick * (long long)(io.calls - io.owned_confirmed_ticket));
+    }
+    const int copied = (int)std::min<long long>(bound, out_cap);
+    CUDA_TRY(s, cudaStreamWaitEvent(io.s_out, io.tick_done[b], 0));
+    CUDA_TRY(s, cudaMemcpyAsync(out_count, so_count, sizeof(int), cudaMemcpyDeviceToHost, io.s_out));
+    if (copied) CUDA_TRY(s, cudaMemcpyAsync(out, so, sizeof(ecmgpu_agent_rec) * (size_t)copied, cudaMemcpyDeviceToHost, io.s_out));
+    CUDA_TRY(s, cudaEventRecord(io.out_done[b], io.s_out));
+    io.owned_count[b] = out_count;
+    io.owned_copied[b] = copied;
     if (ticket) *ticket = io.calls;
     io.calls++;
     return ECMGPU_OK;
@@ -1141,8 +1209,21 @@ int ecmgpu_io_wait(ecmgpu_sim* s, uint64_t ticket) {
     if (!s) return ECMGPU_ERR_INVALID;
     auto& io = s->io;
     if (!io.ready || ticket >= io.calls) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_io_wait: unknown ticket");
+    // a generation that has been reused since: waiting for its latest user also covers the older ticket
+    while (ticket + 2 < io.calls) ticket += 2;
     CUDA_TRY(s, cudaSetDevice(s->prm.device));
-    CUDA_TRY(s, cudaEventSynchronize(io.out_done[ticket & 1]));
+    const int b = (int)(ticket & 1);
+    CUDA_TRY(s, cudaEventSynchronize(io.out_done[b]));
+    if (io.owned_count[b]) {
+        const int have = *io.owned_count[b];
+        if (io.owned_confirmed < 0 || ticket >= io.owned_confirmed_ticket) {
+            io.owned_confirmed = have;
+            io.owned_confirmed_ticket = ticket;
+        }
+        if (have > io.owned_copied[b])
+            return fail(s, ECMGPU_ERR_CAPACITY, "ecmgpu_update_io_owned: " + std::to_string(have) + " owned agents, room for " +
+                        std::to_string(io.owned_copied[b]) + " records");
+    }
     return ECMGPU_OK;
 }
 

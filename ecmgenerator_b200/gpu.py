@@ -36,7 +36,7 @@ EXPORTS = [
     "ecmgpu_read", "ecmgpu_write", "ecmgpu_read_async", "ecmgpu_write_async", "ecmgpu_alloc_pinned", "ecmgpu_free_pinned",
     "ecmgpu_locate", "ecmgpu_retract", "ecmgpu_find_neighbors", "ecmgpu_find_obstacles", "ecmgpu_get_stats",
     "ecmgpu_last_tick_ms", "ecmgpu_set_profiling", "ecmgpu_mark", "ecmgpu_mark_elapsed_ms", "ecmgpu_stream", "ecmgpu_comm_unique_id", "ecmgpu_comm_init",
-    "ecmgpu_comm_set_strips", "ecmgpu_comm_init_local", "ecmgpu_update_phase", "ecmgpu_update_io", "ecmgpu_io_wait", "ecmgpu_comm_p2p_export", "ecmgpu_comm_p2p_connect",
+    "ecmgpu_comm_set_strips", "ecmgpu_comm_init_local", "ecmgpu_update_phase", "ecmgpu_update_io", "ecmgpu_update_io_owned", "ecmgpu_io_wait", "ecmgpu_comm_p2p_export", "ecmgpu_comm_p2p_connect",
 ]
 
 
@@ -105,12 +105,17 @@ def lib() -> C.CDLL:
         L.ecmgpu_comm_p2p_connect.argtypes = [vp, u8p, u8p]
         L.ecmgpu_update_io.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(C.c_uint64)]
         L.ecmgpu_io_wait.argtypes = [vp, C.c_uint64]
+        L.ecmgpu_update_io_owned.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
 
 def _p(a, t):
     return None if a is None else a.ctypes.data_as(t)
+
+
+# ecmgpu_agent_rec (include/ecm_b200.h): 20-byte record of one owned agent
+AGENT_REC = np.dtype([("slot", np.int32), ("x", np.float32), ("y", np.float32), ("vx", np.float32), ("vy", np.float32)])
 
 
 class PinnedArray:
@@ -205,6 +210,14 @@ class GpuSim:
         t = C.c_uint64(0)
         self._ck(self.L.ecmgpu_update_io(self.h, int(count), ptr(in_pos), ptr(in_vel), ptr(out_pos), ptr(out_vel), ptr(out_active),
                                          C.byref(t)))
+        return int(t.value)
+
+    def update_io_owned(self, n_in, in_rec, out_rec, out_count) -> int:
+        """Pipelined tick moving only the owned agents as AGENT_REC records (PinnedArray arguments; in_rec may be None)."""
+        ptr = lambda a: C.c_void_p(a.ptr) if a is not None else None  # noqa: E731
+        t = C.c_uint64(0)
+        self._ck(self.L.ecmgpu_update_io_owned(self.h, int(n_in), ptr(in_rec), ptr(out_rec), int(out_rec.array.shape[0]), ptr(out_count),
+                                               C.byref(t)))
         return int(t.value)
 
     def io_wait(self, ticket: int):

@@ -130,6 +130,21 @@ int ecmgpu_write_async(ecmgpu_sim* sim, int which, const void* src_pinned, int f
 int ecmgpu_update_io(ecmgpu_sim* sim, int count, const float* in_pos, const float* in_vel, float* out_pos, float* out_vel,
                      uint8_t* out_active, uint64_t* ticket);
 int ecmgpu_io_wait(ecmgpu_sim* sim, uint64_t ticket);
+/* The same pipeline for strips (and for hosts that only track live agents): moves (slot, position,
+ * velocity) records of the agents THIS handle owns instead of whole slot arrays, so that with N ranks
+ * every rank transfers its share of the crowd.  `in` (PINNED, may be NULL with n_in = 0): records whose
+ * slot this handle owns overwrite position and velocity before the tick, other records are ignored.
+ * After the tick `out` (PINNED, room for out_cap records) receives one record per owned agent, in no
+ * particular order, and *out_count (PINNED) their number.  The copy is sized from the count confirmed by
+ * the last ecmgpu_io_wait plus the migrants that may have arrived since, so the first calls after a
+ * spawn / bulk load move max_agents records and later ones only the owned share; ecmgpu_io_wait fails
+ * with ECMGPU_ERR_CAPACITY when out_cap was too small for the tick's count. */
+typedef struct ecmgpu_agent_rec {
+    int32_t slot;
+    float x, y, vx, vy;
+} ecmgpu_agent_rec; /* 20 bytes */
+int ecmgpu_update_io_owned(ecmgpu_sim* sim, int n_in, const ecmgpu_agent_rec* in, ecmgpu_agent_rec* out, int out_cap,
+                           int32_t* out_count, uint64_t* ticket);
 /* cudaHostAlloc / cudaFreeHost pass-through so non-CUDA hosts can get pinned staging memory. */
 void* ecmgpu_alloc_pinned(uint64_t bytes);
 void  ecmgpu_free_pinned(void* p);

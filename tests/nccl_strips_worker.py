@@ -33,21 +33,52 @@ def main():
     pos, owners = strips.gather(gpu.POS)
     vel, _ = strips.gather(gpu.VEL)
     gs = strips.global_stats()
+    # 24 more ticks through ecmgpu_update_io_owned (two deep): every rank moves only its share; the union of
+    # the records must be the whole crowd and equal the single-GPU state after ticks + 24
+    raw = strips.sim
+    rout = [gpu.PinnedArray((n,), gpu.AGENT_REC) for _ in range(2)]
+    cnt = [gpu.PinnedArray((1,), np.int32) for _ in range(2)]
+    last, copied = None, []
+    for t in range(24):
+        tk = raw.update_io_owned(0, None, rout[t & 1], cnt[t & 1])
+        if last is not None:
+            raw.io_wait(last)
+        last = tk
+    raw.io_wait(last)
+    m = int(cnt[1].array[0])
+    rec = rout[1].array[:m].copy()
+    counts = [None] * world
+    dist.all_gather_object(counts, m)
+    recs = [None] * world
+    dist.all_gather_object(recs, rec)
     if rank == 0:
         single = gpu.GpuSim(w, n, float(S.DT), device=local, record_neighbors=False, path_pool_points=int(off[-1] * 1.25) + 4096)
         single.bulk_load(c.pos, c.radius, c.speed, off, pxy)
         single.update(ticks)
         act = single.read(gpu.ACTIVE, 0, n)
+        snap_p, snap_v = single.read(gpu.POS, 0, n), single.read(gpu.VEL, 0, n)
+        single.update(24)
+        act2 = single.read(gpu.ACTIVE, 0, n) > 0
+        p2, v2 = single.read(gpu.POS, 0, n), single.read(gpu.VEL, 0, n)
+        allrec = np.concatenate(recs)
+        o = np.argsort(allrec["slot"])
+        sl = allrec["slot"][o]
+        io_ok = bool(np.array_equal(sl, np.flatnonzero(act2))
+                     and np.array_equal(np.stack([allrec["x"][o], allrec["y"][o]], 1).view(np.uint32), p2[sl].view(np.uint32))
+                     and np.array_equal(np.stack([allrec["vx"][o], allrec["vy"][o]], 1).view(np.uint32), v2[sl].view(np.uint32)))
         a = act > 0
-        sp, sv = single.read(gpu.POS, 0, n), single.read(gpu.VEL, 0, n)
+        sp, sv = snap_p, snap_v
         own1 = M.owner_of(pos[:, 0], strips.bounds)
         res = {"world": world, "agents": n, "ticks": ticks,
                "pos_equal": bool(np.array_equal(pos[a].view(np.uint32), sp[a].view(np.uint32))),
                "vel_equal": bool(np.array_equal(vel[a].view(np.uint32), sv[a].view(np.uint32))),
                "owners_ok": bool(np.array_equal(owners, act)), "halo_misses": gs["halo_misses"],
-               "moved": int(((own0 != own1) & a).sum()), "halo": strips.halo, "p2p": bool(strips.p2p)}
+               "moved": int(((own0 != own1) & a).sum()), "halo": strips.halo, "p2p": bool(strips.p2p),
+               "io_owned_ok": io_ok, "io_owned_counts": [int(x) for x in counts]}
         json.dump(res, open(sys.argv[1], "w"))
     dist.barrier()
+    for x in rout + cnt:
+        x.free()
     strips.close()
     dist.destroy_process_group()
 

@@ -325,6 +325,56 @@ def test_update_io_pipeline_matches_plain_update():
         x.free()
 
 
+def test_update_io_owned_records_match_plain_update():
+    """ecmgpu_update_io_owned: records in -> tick -> records of the live agents out, pipelined two deep, equals
+    write + update + read; agents that arrive drop out of the records; the copy shrinks to the confirmed count."""
+    g = Golden("c2_small")
+    n = g.n
+    a = gpu.GpuSim(g.world, n + 5, g.step)
+    b = gpu.GpuSim(g.world, n + 5, g.step)
+    for s in (a, b):
+        s.bulk_load(g.crowd.pos, g.crowd.radius, g.crowd.speed, g.path_off, g.path_xy)
+        s.write(gpu.ACTIVE, np.zeros(3, np.uint8), first=4)  # holes in the slot range
+    live = np.ones(n, bool)
+    live[4:7] = False
+    rin = [gpu.PinnedArray((n + 5,), gpu.AGENT_REC) for _ in range(2)]
+    rout = [gpu.PinnedArray((n + 5,), gpu.AGENT_REC) for _ in range(2)]
+    cnt = [gpu.PinnedArray((1,), np.int32) for _ in range(2)]
+    pos, vel = g.crowd.pos.copy(), np.zeros((n, 2), np.float32)
+    for t in range(10):
+        k = t & 1
+        ids = np.flatnonzero(live)[::-1]  # any order
+        r = rin[k].array
+        r["slot"][: len(ids)] = ids
+        r["x"][: len(ids)], r["y"][: len(ids)] = pos[ids, 0], pos[ids, 1]
+        r["vx"][: len(ids)], r["vy"][: len(ids)] = vel[ids, 0], vel[ids, 1]
+        r["slot"][len(ids)] = 5  # a record for a slot that is not live must be ignored
+        r["x"][len(ids)] = 1e6
+        tk = b.update_io_owned(len(ids) + 1, rin[k], rout[k], cnt[k])
+        a.write(gpu.POS, pos)
+        a.write(gpu.VEL, vel)
+        a.update(1)
+        b.io_wait(tk)
+        pa, va, act = a.read(gpu.POS, 0, n), a.read(gpu.VEL, 0, n), a.read(gpu.ACTIVE, 0, n)
+        m = int(cnt[k].array[0])
+        out = rout[k].array[:m]
+        order = np.argsort(out["slot"])
+        assert np.array_equal(out["slot"][order], np.flatnonzero(act)), f"owned slots tick {t}"
+        sl = out["slot"][order]
+        assert_bits_equal(np.stack([out["x"][order], out["y"][order]], 1), pa[sl], f"pos tick {t}")
+        assert_bits_equal(np.stack([out["vx"][order], out["vy"][order]], 1), va[sl], f"vel tick {t}")
+        assert b.read(gpu.POS, 5, 1)[0, 0] != 1e6
+        live = act > 0
+        pos, vel = pa.copy(), va.copy()
+    # too small an output buffer is reported, not silently truncated
+    small = gpu.PinnedArray((8,), gpu.AGENT_REC)
+    tk = b.update_io_owned(0, None, small, cnt[0])
+    with pytest.raises(gpu.EcmGpuError):
+        b.io_wait(tk)
+    for x in rin + rout + cnt + [small]:
+        x.free()
+
+
 def _lockstep(sim, ora, n, ticks):
     worst = 0.0
     for t in range(ticks):

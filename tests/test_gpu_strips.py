@@ -114,3 +114,4 @@ def test_multi_process_strips_match_single_gpu_bitwise(transport):
     print(res)
     assert res["pos_equal"] and res["vel_equal"] and res["halo_misses"] == 0 and res["owners_ok"] and res["moved"] > 10
     assert res["p2p"] == (transport == "peer")
+    assert res["io_owned_ok"] and sum(res["io_owned_counts"]) > 0
