@@ -280,6 +280,10 @@ def run_ours(args):
     sim.sync()
     st0 = sim.stats()
     active0 = st0["n_active"]
+    # the state the timed ticks start from: the end-to-end loop below replays it, so that `value` and `e2e` time the
+    # same phase of the simulation (the tick gets dearer as the crowd congests, see "steady_state")
+    raw0 = sim if world == 1 else sim.sim
+    pos_w, vel_w, act_w = raw0.read(gpu.POS, 0, n), raw0.read(gpu.VEL, 0, n), raw0.read(gpu.ACTIVE, 0, n) > 0
 
     # ---- timed: K ticks, state resident in HBM
     clocks = ClockSampler(local)
@@ -336,40 +340,42 @@ def run_ours(args):
     # ---- end to end through the C ABI with host buffers.  One GPU: whole slot arrays (ecmgpu_update_io);
     # strips: every rank moves the records of the agents it owns (ecmgpu_update_io_owned)
     e2e = None
+    DEPTH = 3
     raw = sim if world == 1 else sim.sim
     k = max(3, min(args.steps, 50))
     if world == 1:
-        # two generations of pinned host buffers: call k uses set k & 1 while set (k-1) & 1 is still draining
-        hp = [gpu.PinnedArray((n, 2), np.float32) for _ in range(2)]
-        hv = [gpu.PinnedArray((n, 2), np.float32) for _ in range(2)]
-        op = [gpu.PinnedArray((n, 2), np.float32) for _ in range(2)]
-        ov = [gpu.PinnedArray((n, 2), np.float32) for _ in range(2)]
-        oa = [gpu.PinnedArray((n,), np.uint8) for _ in range(2)]
+        # DEPTH generations of pinned host buffers: call i uses set i % DEPTH while the sets of i-1 and i-2 are still in flight
+        hp = [gpu.PinnedArray((n, 2), np.float32) for _ in range(DEPTH)]
+        hv = [gpu.PinnedArray((n, 2), np.float32) for _ in range(DEPTH)]
+        op = [gpu.PinnedArray((n, 2), np.float32) for _ in range(DEPTH)]
+        ov = [gpu.PinnedArray((n, 2), np.float32) for _ in range(DEPTH)]
+        oa = [gpu.PinnedArray((n,), np.uint8) for _ in range(DEPTH)]
         bufs = hp + hv + op + ov + oa
-        p0, v0 = raw.read(gpu.POS, 0, n), raw.read(gpu.VEL, 0, n)
-        for g in range(2):
-            hp[g].array[:] = p0
-            hv[g].array[:] = v0
+        for g in range(DEPTH):
+            hp[g].array[:] = pos_w
+            hv[g].array[:] = vel_w
         moved = [0, 0]
 
         def io_call(i):
-            g = i & 1
+            g = i % DEPTH
             moved[0] += 16 * n
             moved[1] += 17 * n
             return raw.update_io(n, hp[g], hv[g], op[g], ov[g], oa[g])  # H2D pos+vel | tick | D2H pos+vel+active
 
         def io_result(i):
-            return int((oa[i & 1].array > 0).sum())
+            return int((oa[i % DEPTH].array > 0).sum())
     else:
         act_now = raw.read(gpu.ACTIVE, 0, n) > 0
         ids = np.flatnonzero(act_now)
         p0, v0 = raw.read(gpu.POS, 0, n), raw.read(gpu.VEL, 0, n)
+        keep_w = act_now & act_w  # owned at the start of the timed ticks too: their state of that moment is replayed
+        p0[keep_w], v0[keep_w] = pos_w[keep_w], vel_w[keep_w]
         cap = n
-        rin = [gpu.PinnedArray((cap,), gpu.AGENT_REC) for _ in range(2)]
-        rout = [gpu.PinnedArray((cap,), gpu.AGENT_REC) for _ in range(2)]
-        cnt = [gpu.PinnedArray((1,), np.int32) for _ in range(2)]
+        rin = [gpu.PinnedArray((cap,), gpu.AGENT_REC) for _ in range(DEPTH)]
+        rout = [gpu.PinnedArray((cap,), gpu.AGENT_REC) for _ in range(DEPTH)]
+        cnt = [gpu.PinnedArray((1,), np.int32) for _ in range(DEPTH)]
         bufs = rin + rout + cnt
-        for g in range(2):
+        for g in range(DEPTH):
             r = rin[g].array
             r["slot"][: len(ids)] = ids
             r["x"][: len(ids)], r["y"][: len(ids)] = p0[ids, 0], p0[ids, 1]
@@ -378,25 +384,28 @@ def run_ours(args):
         rec_b = gpu.AGENT_REC.itemsize
 
         def io_call(i):
-            g = i & 1
+            g = i % DEPTH
             moved[0] += rec_b * len(ids)
             return raw.update_io_owned(len(ids), rin[g], rout[g], cnt[g])  # H2D owned records | tick | D2H owned records
 
         def io_result(i):
-            m = int(cnt[i & 1].array[0])
+            m = int(cnt[i % DEPTH].array[0])
             moved[1] += rec_b * m + 4  # lower bound: the copy is sized from the last confirmed count plus migrant room
             return m
 
     def e2e_run(steps):
-        last, res = None, 0
+        # the host keeps DEPTH - 1 calls in flight: it issues call i, then consumes the results of call i - (DEPTH - 1)
+        tickets, res = [], 0
         for i in range(steps):
-            tk = io_call(i)
-            if last is not None:
-                raw.io_wait(last)  # the host consumes tick i-1's results while tick i is in flight
-                res = io_result(i - 1)
-            last = tk
-        raw.io_wait(last)
-        return io_result(steps - 1)
+            tickets.append(io_call(i))
+            j = i - (DEPTH - 1)
+            if j >= 0:
+                raw.io_wait(tickets[j])
+                res = io_result(j)
+        for j in range(max(0, steps - (DEPTH - 1)), steps):
+            raw.io_wait(tickets[j])
+            res = io_result(j)
+        return res
 
     e2e_run(4)
     moved[0] = moved[1] = 0
@@ -415,11 +424,52 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         dt, act, h2d, d2h = float(tmax[0].item()), int(t[1].item()), float(t[2].item()), float(t[3].item())
     e2e = {"value": act * k / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "ms_per_step": 1e3 * dt / k, "steps": k,
+           "ms_per_step": 1e3 * dt / k, "steps": k, "calls_in_flight": DEPTH - 1,
            "api": "ecmgpu_update_io (whole slot arrays)" if world == 1 else "ecmgpu_update_io_owned (records of the agents each rank owns)"}
     for a in bufs:
         a.free()
-    clk = clocks.stop()  # sampled over all timed regions (resident ticks, per-phase pass, end-to-end ticks)
+    # the host link as this box gives it (pinned memory, one direction at a time): context for the e2e number
+    lk = gpu.PinnedArray((n, 2), np.float32)
+    raw.read_async(gpu.POS, lk, 0, n)
+    raw.sync()
+    raw.mark(0)
+    for _ in range(4):
+        raw.read_async(gpu.POS, lk, 0, n)
+    raw.mark(1)
+    for _ in range(4):
+        raw.write_async(gpu.POS, lk, 0, n)  # the values just read: the state does not change
+    raw.mark(2)
+    raw.sync()
+    e2e["link"] = {"d2h_GBps": 4 * 8 * n / (raw.elapsed_ms(0, 1) * 1e6), "h2d_GBps": 4 * 8 * n / (raw.elapsed_ms(1, 2) * 1e6)}
+    lk.free()
+    clk = clocks.stop()
+    # ---- disclosure: the same K ticks once the crowd has congested (the tick cost levels off after ~400 ticks)
+    steady = None
+    if args.steady_tick > 0:
+        done = max(args.warmup, 3) + 1  # the end-to-end loop replayed the post-warm-up state: the crowd is one tick past it
+        while done < args.steady_tick:
+            sim.update(min(50, args.steady_tick - done))
+            done += min(50, args.steady_tick - done)
+        st_a = sim.stats()
+        barrier()
+        sim.mark(0)
+        for _ in range(args.steps):
+            sim.update(1)
+        sim.mark(1)
+        barrier()
+        ms_s = sim.elapsed_ms(0, 1)
+        st_b = sim.stats()
+        act_s = float(st_b["n_active"]) if world == 1 else float(sim.global_active())
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([ms_s], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_s = float(t.item())
+        steady = {"from_tick": int(done), "ms_per_step": ms_s / args.steps, "value": act_s * args.steps / (ms_s * 1e-3), "unit": UNIT,
+                  "lp3d_runs_per_tick_rank0": (st_b["lp3d_runs"] - st_a["lp3d_runs"]) / args.steps,
+                  "note": "the headline is timed on ticks [warmup, warmup+steps) from the crowd at rest; this is the same measurement on the congested crowd"}
+  # sampled over all timed regions (resident ticks, per-phase pass, end-to-end ticks)
 
     global_active = int(active0)
     if world > 1:
@@ -448,6 +498,8 @@ def run_ours(args):
         line["roofline"] = roof
     if e2e:
         line["e2e"] = e2e
+    if steady:
+        line["steady_state"] = steady
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
@@ -458,6 +510,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steady-tick", type=int, default=600, help="also time K ticks from this tick on (0 = skip)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3_1m", choices=sorted(S.CONFIGS))
     ap.add_argument("--agents", type=int, default=None)

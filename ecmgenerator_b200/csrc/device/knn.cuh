@@ -61,7 +61,29 @@ struct Knn {
         v2 pj = __ldg(&g.s_pos[cand]);
         float dx = pj.x - self.x, dy = pj.y - self.y;
         float dd = dx * dx + dy * dy;
+#ifdef ECM_KNN_BRANCHLESS
+        // every lane runs the chain on every candidate (a rejected one carries +inf and changes nothing): with 32
+        // lanes almost every iteration has SOME lane inserting, so the branch saved nothing and cost its divergence
+        const bool ok = dd > kEpsilon && dd <= d[kK - 1];
+        float cd = ok ? dd : CUDART_INF_F;
+        const bool tie = ok & ((cd == d[0]) | (cd == d[1]) | (cd == d[2]) | (cd == d[3]) | (cd == d[4]));
+        if (tie) { insert_with_ties(cd, cand, g.s_slot); return; }
+        int cq = cand;
+        bool placed = false;
+#pragma unroll
+        for (int j = 0; j < kK; j++) {
+            const bool less = placed | (cd < d[j]);
+            placed = less;
+            const float td = less ? d[j] : cd;
+            const int tq = less ? q[j] : cq;
+            d[j] = less ? cd : d[j];
+            q[j] = less ? cq : q[j];
+            cd = td;
+            cq = tq;
+        }
+#else
         if (dd > kEpsilon && dd <= d[kK - 1]) insert(dd, cand, g.s_slot);
+#endif
     }
 };
 

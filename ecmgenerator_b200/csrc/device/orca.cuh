@@ -283,15 +283,30 @@ __device__ __noinline__ void randomized_lp3d(int nObst, const Cons* cs, int tota
 
 struct OrcaResult {
     v2 velocity;
-    unsigned status;  // ECMGPU_ST_OBST_OVERFLOW | ECMGPU_ST_LP3D
+    unsigned status;  // ECMGPU_ST_OBST_OVERFLOW | ECMGPU_ST_LP3D | kLp3dDeferred
+};
+
+// Agents whose 2-D program is infeasible need RandomizedLP3D: a few per warp in a congested crowd (13 % of
+// the agents of the 1 M city crowd after 600 ticks), so run inline almost every warp pays the whole LP3D
+// with 4 of 32 lanes working - and k_orca carries its code and its 512-byte scratch array.  k_orca instead
+// parks such an agent here - constraints, failing index and the velocity reached so far - and k_lp3d
+// finishes the parked agents with every lane busy.  Same functions on the same values: results are
+// bit-identical to the inline path (kept for the warp-per-agent fallback kernel).
+constexpr unsigned kLp3dDeferred = 0x80000000u;  // internal: never stored in the status array
+struct Lp3dQueue {
+    int cap;                    // one row per slot
+    unsigned long long* count;  // entries this tick (may run past cap: readers clamp)
+    int4* hdr;                  // (snapshot row p, nObst, nc, failed)
+    float4* out;                // (velocity so far, maxSpeed, unused)
+    Cons* cs;                   // constraint i of entry e at [i * cap + e]
 };
 
 // ORCA::GetVelocity after the neighbour query (ORCA.cpp:23-56).  nb_q[] are snapshot indices.
 // kSync: called by all 32 lanes of the warp (lanes without an agent pass valid = false).
-template <bool kSync>
+template <bool kSync, bool kDefer>
 __device__ __forceinline__ OrcaResult orca_velocity(const ObstView& ob, const BinView& bins, const GridView& g, v2 position, v2 velocity,
                                                     float clearance, float maxSpeed, v2 prefVel, int n_nb, const int* nb_q, float stepSize,
-                                                    bool valid = true) {
+                                                    bool valid, const Lp3dQueue& dq, int p) {
     OrcaResult res;
     res.status = 0u;
     res.velocity = V(0.0f, 0.0f);
@@ -328,10 +343,21 @@ __device__ __forceinline__ OrcaResult orca_velocity(const ObstView& ob, const Bi
     v2 out = V(0.0f, 0.0f);
     phase_barrier<kSync>();
     int failed = randomized_lp<kSync>(cs, nc, prefVel, maxSpeed, false, out);
-    if (failed < nc) {  // rare (dense crowds): stays per-lane
-        Cons proj[kMaxCons];
+    if (failed < nc) {
         res.status |= 64u;
-        randomized_lp3d(nObst, cs, nc, maxSpeed, failed, out, proj);
+        if constexpr (kDefer) {
+            // the queue has a row for every slot and an agent parks at most once per tick: e < cap always holds
+            const int e = (int)atomicAdd(dq.count, 1ull);
+            if (e < dq.cap) {
+                res.status |= kLp3dDeferred;
+                dq.hdr[e] = make_int4(p, nObst, nc, failed);
+                dq.out[e] = make_float4(out.x, out.y, maxSpeed, 0.0f);
+                for (int i = 0; i < nc; i++) dq.cs[(size_t)i * dq.cap + e] = cs[i];
+            }
+        } else {  // per-lane (k_fallback, queries)
+            Cons proj[kMaxCons];
+            randomized_lp3d(nObst, cs, nc, maxSpeed, failed, out, proj);
+        }
     }
     res.velocity = out;
     return res;

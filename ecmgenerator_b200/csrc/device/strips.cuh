@@ -71,13 +71,17 @@ __global__ void __launch_bounds__(256) k_assign_owner(int n_slots, AgentArrays a
     if (!(x >= sv.lo && x < sv.hi)) ag.active[i] = 0;
 }
 
-__global__ void __launch_bounds__(256) k_pack(int n_slots, AgentArrays ag, StripView sv, unsigned long long* counters) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots || !ag.active[i]) return;
-    const float2 p = ag.pos[i];
-    const int dir = p.x < sv.lo ? 0 : (p.x >= sv.hi ? 1 : -1);
-    if (dir >= 0) {  // left the strip: hand over, keep as a ghost for the coming tick
-        const float2 v = ag.vel[i];
+constexpr int kPackBlock = 1024;
+
+__global__ void __launch_bounds__(kPackBlock) k_pack(int n_slots, AgentArrays ag, StripView sv, unsigned long long* counters) {
+    __shared__ int s_warp[33];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool owned = i < n_slots && ag.active[i];
+    float2 p = make_float2(0.0f, 0.0f), v = p;
+    if (owned) p = ag.pos[i];
+    const int dir = !owned ? -1 : (p.x < sv.lo ? 0 : (p.x >= sv.hi ? 1 : -1));
+    if (dir >= 0) {  // left the strip (rare: per-entry atomics): hand over, keep as a ghost for the coming tick
+        v = ag.vel[i];
         unsigned char* m = sv.send[dir];
         int e = atomicAdd(&sv.send_hdr[dir]->n_migrants, 1);
         if (e < sv.cap_migr) {
@@ -96,50 +100,79 @@ __global__ void __launch_bounds__(256) k_pack(int n_slots, AgentArrays ag, Strip
         } else {
             atomicAdd(&counters[C_TOTAL_HALO_MISS], 1ull);  // message full: the agent stays here this tick
         }
-        return;
     }
+    const bool stays = owned && dir < 0;
 #pragma unroll
     for (int d = 0; d < 2; d++) {
         const bool has = d == 0 ? sv.rank > 0 : sv.rank < sv.n_ranks - 1;
-        const bool near = d == 0 ? p.x < sv.lo + sv.halo : p.x >= sv.hi - sv.halo;
-        if (has && near) {
-            unsigned char* m = sv.send[d];
-            int e = atomicAdd(&sv.send_hdr[d]->n_halo, 1);
+        if (!has) continue;  // uniform over the grid
+        const bool near = stays && (d == 0 ? p.x < sv.lo + sv.halo : p.x >= sv.hi - sv.halo);
+        const int e = cta_reserve(near, &sv.send_hdr[d]->n_halo, s_warp);
+        if (near) {
             if (e < sv.cap_halo) {
-                const float2 v = ag.vel[i];
+                v = ag.vel[i];
                 HaloEntry he; he.slot = i; he.x = p.x; he.y = p.y; he.vx = v.x; he.vy = v.y;
-                sv.halo_of(m)[e] = he;
+                sv.halo_of(sv.send[d])[e] = he;
             } else atomicAdd(&counters[C_TOTAL_HALO_MISS], 1ull);
         }
     }
 }
 
-// Peer transport: the entries were stored straight into the neighbour's inbox by k_pack (NVLink
-// peer stores).  k_publish completes the message: counts, then - after a system-scope fence - the
-// sequence number the neighbour's k_await spins on.  Inboxes are double-buffered by sequence parity;
-// having seen the neighbour's message s-1 implies it has consumed our message s-2, so writing
-// generation s & 1 never races with its reader.
-__global__ void k_publish(StripView sv, int seq) {
-    const int d = threadIdx.x;
-    if (d >= 2) return;
-    const bool has = d == 0 ? sv.rank > 0 : sv.rank < sv.n_ranks - 1;
-    if (!has) return;
-    MsgHeader* dst = (MsgHeader*)sv.send[d];
-    const MsgHeader h = *sv.send_hdr[d];
-    dst->n_halo = h.n_halo;
-    dst->n_migrants = h.n_migrants;
-    __threadfence_system();
-    *(volatile int*)&dst->pad0 = seq;
+__device__ __forceinline__ void adopt_migrant(AgentArrays& ag, const MigrantEntry& me) {
+    ag.pos[me.slot] = make_float2(me.x, me.y);
+    ag.vel[me.slot] = make_float2(me.vx, me.vy);
+    ag.attraction[me.slot] = make_float2(me.ax, me.ay);
+    ag.prefvel[me.slot] = make_float2(me.pvx, me.pvy);
+    ag.force[me.slot] = make_float2(me.fx, me.fy);
+    ag.replan_pending[me.slot] = (me.flags & 1u) ? 1 : 0;
+    ag.active[me.slot] = 1;
 }
 
-__global__ void k_await(StripView sv, int seq) {
+// Peer transport: the entries were stored straight into the neighbour's inbox by k_pack (NVLink
+// peer stores).  This single-CTA kernel completes the exchange:
+//   publish  counts, then - after a system-scope fence - the sequence number the neighbour spins on;
+//   await    spin until both neighbours' messages carry this tick's sequence number;
+//   adopt    received migrants become owned agents of this rank (k_unpack_migrants of the other transports).
+// Inboxes are double-buffered by sequence parity; having seen the neighbour's message s-1 implies it
+// has consumed our message s-2, so writing generation s & 1 never races with its reader.  The sequence
+// number lives in device memory and is advanced here, so the tick can be replayed as a CUDA graph.
+__global__ void __launch_bounds__(256) k_exchange_p2p(StripView sv, AgentArrays ag, int* seq_counter) {
+    __shared__ int s_seq;
+    if (threadIdx.x == 0) s_seq = *seq_counter;
+    __syncthreads();
+    const int seq = s_seq;
     const int d = threadIdx.x;
-    if (d >= 2) return;
-    const bool has = d == 0 ? sv.rank > 0 : sv.rank < sv.n_ranks - 1;
-    if (!has) return;
-    volatile int* flag = &((MsgHeader*)sv.recv[d])->pad0;
-    while (*flag != seq) __nanosleep(100);
-    __threadfence_system();
+    const bool mine = d < 2 && (d == 0 ? sv.rank > 0 : sv.rank < sv.n_ranks - 1);
+    if (mine) {
+        MsgHeader* dst = (MsgHeader*)sv.send[d];
+        const MsgHeader h = *sv.send_hdr[d];
+        dst->n_halo = h.n_halo;
+        dst->n_migrants = h.n_migrants;
+        __threadfence_system();
+        *(volatile int*)&dst->pad0 = seq;
+    }
+    __syncwarp();  // both messages are out before either lane starts to wait
+    if (mine) {
+        volatile int* flag = &((MsgHeader*)sv.recv[d])->pad0;
+        while (*flag != seq) __nanosleep(100);
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *seq_counter = seq + 1;
+    for (int dd = 0; dd < 2; dd++) {
+        const bool has = dd == 0 ? sv.rank > 0 : sv.rank < sv.n_ranks - 1;
+        if (!has) continue;
+        const unsigned char* m = sv.recv[dd];
+        // the inbox was written by another GPU while this kernel ran: read it past the L1 (ld.cg)
+        const int n = min(__ldcg(&((const MsgHeader*)m)->n_migrants), sv.cap_migr);
+        const int* src = (const int*)(m + sizeof(MsgHeader) + sizeof(HaloEntry) * (size_t)sv.cap_halo);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            union { MigrantEntry me; int w[sizeof(MigrantEntry) / 4]; } u;
+#pragma unroll
+            for (int k = 0; k < (int)(sizeof(MigrantEntry) / 4); k++) u.w[k] = __ldcg(src + (size_t)i * (sizeof(MigrantEntry) / 4) + k);
+            adopt_migrant(ag, u.me);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) k_unpack_migrants(AgentArrays ag, StripView sv) {
@@ -150,13 +183,7 @@ __global__ void __launch_bounds__(256) k_unpack_migrants(AgentArrays ag, StripVi
         const int n = min(((const MsgHeader*)m)->n_migrants, sv.cap_migr);
         if (i < n) {
             const MigrantEntry me = ((const MigrantEntry*)(m + sizeof(MsgHeader) + sizeof(HaloEntry) * (size_t)sv.cap_halo))[i];
-            ag.pos[me.slot] = make_float2(me.x, me.y);
-            ag.vel[me.slot] = make_float2(me.vx, me.vy);
-            ag.attraction[me.slot] = make_float2(me.ax, me.ay);
-            ag.prefvel[me.slot] = make_float2(me.pvx, me.pvy);
-            ag.force[me.slot] = make_float2(me.fx, me.fy);
-            ag.replan_pending[me.slot] = (me.flags & 1u) ? 1 : 0;
-            ag.active[me.slot] = 1;
+            adopt_migrant(ag, me);
         }
     }
 }

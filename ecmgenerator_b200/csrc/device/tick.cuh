@@ -8,7 +8,8 @@
 //   k_orca        exact 5-NN, obstacle gather, ORCA half-planes, LP / LP3D, velocity and position
 //                 integration (ApplyObstacleAvoidanceForce, UpdateVelocitySystem, UpdatePositionSystem,
 //                 Simulator.cpp:659-686, 619-635, 592-606)
-//   k_fallback    warp-per-agent exhaustive neighbour search for agents whose ring budget ran out
+//   k_fallback    the stragglers: warp-per-agent exhaustive neighbour search for agents whose ring budget ran
+//                 out, and RandomizedLP3D + integration for the agents k_orca parked (orca.cuh Lp3dQueue)
 //
 // The snapshot makes the tick Jacobi-style exactly like the reference: every agent reads its
 // neighbours' PRE-tick position / velocity / radius (ORCA.cpp:342-344) while new values are written
@@ -24,12 +25,13 @@ enum Counter {
     C_REPLAN_N = 0,     // entries in ev_replan since the last poll
     C_DESTROYED_N = 1,  // entries in ev_destroyed since the last poll
     C_FALLBACK_N = 2,   // entries in fb_list this tick (reset every tick)
-    C_TOTAL_FALLBACK = 3,
-    C_TOTAL_OBST_OVF = 4,
-    C_TOTAL_LP3D = 5,
-    C_TOTAL_LOCFAIL = 6,
-    C_TOTAL_REPLAN = 7,
-    C_TOTAL_HALO_MISS = 8,
+    C_LP3D_N = 3,       // entries in the LP3D queue this tick (reset every tick, together with C_FALLBACK_N)
+    C_TOTAL_FALLBACK = 4,
+    C_TOTAL_OBST_OVF = 5,
+    C_TOTAL_LP3D = 6,
+    C_TOTAL_LOCFAIL = 7,
+    C_TOTAL_REPLAN = 8,
+    C_TOTAL_HALO_MISS = 9,
     C_COUNT = 16
 };
 
@@ -200,6 +202,7 @@ struct TickView {
     // multi-GPU strips (strips.cuh): the grid holds every agent with x in [cover_lo, cover_hi)
     int strips;
     float cover_lo, cover_hi;
+    Lp3dQueue lp3d;
 };
 
 // UpdateAttractionPointSystem + ApplySteeringForce for snapshot row p; convergent call (whole warp).
@@ -289,13 +292,30 @@ __device__ __forceinline__ void attract_agent(const TickView& t, const int p, co
     }
 }
 
-__global__ void __launch_bounds__(128) k_attract(TickView t) {
+// k_attract waits on dependent gathers (header -> block boxes -> polyline block): resident warps hide them
+#ifndef ECM_ATTRACT_MINBLOCKS
+#define ECM_ATTRACT_MINBLOCKS 9  // 56 registers; 12 / 16 CTAs (40 / 32 registers, spills) measured 1 % / 8 % slower
+#endif
+__global__ void __launch_bounds__(128, ECM_ATTRACT_MINBLOCKS) k_attract(TickView t) {
     attract_agent(t, blockIdx.x * blockDim.x + threadIdx.x, *t.n_sorted_ptr);
 }
 
+// force = v_orca - v (Simulator.cpp:676-677); v += force * (1/mass) * step (Simulator.cpp:622-633);
+// p += v * step (Simulator.cpp:603-604)
+__device__ __forceinline__ void integrate_agent(const TickView& t, int slot, v2 pos, v2 vel, v2 velocity) {
+    const v2 f = V(velocity.x - vel.x, velocity.y - vel.y);
+    const float massRecip = 1.0f / 0.8f;
+    const v2 nv = V(vel.x + f.x * massRecip * t.step, vel.y + f.y * massRecip * t.step);
+    const v2 np = V(pos.x + (nv.x * t.step), pos.y + (nv.y * t.step));
+    t.ag.force[slot] = f;
+    t.ag.vel[slot] = nv;
+    t.ag.pos[slot] = np;
+}
+
 // ORCA + integration for one agent whose neighbour list is known.  kSync: convergent call by the
-// whole warp, lanes without work pass valid = false.
-template <bool kSync>
+// whole warp, lanes without work pass valid = false.  With kDefer an agent that needs LP3D may be
+// parked in t.lp3d instead (k_lp3d integrates it).
+template <bool kSync, bool kDefer>
 __device__ __forceinline__ unsigned finish_agent(const TickView& t, int p, const Knn& k, bool valid = true) {
     const int slot = valid ? t.sc.s_slot[p] : 0;
     const v2 pos = valid ? t.sc.s_pos[p] : V(0.0f, 0.0f), vel = valid ? t.sc.s_vel[p] : V(0.0f, 0.0f);
@@ -307,23 +327,30 @@ __device__ __forceinline__ unsigned finish_agent(const TickView& t, int p, const
         const float r5 = n_nb == kK ? sqrtf(k.d[kK - 1]) * 1.001f : CUDART_INF_F;
         if (pos.x - r5 < t.cover_lo || pos.x + r5 >= t.cover_hi) extra = 128u;
     }
-    OrcaResult r = orca_velocity<kSync>(t.obst, t.bins, t.grid, pos, vel, rad, spd, pref, n_nb, k.q, t.step, valid);
+    OrcaResult r = orca_velocity<kSync, kDefer>(t.obst, t.bins, t.grid, pos, vel, rad, spd, pref, n_nb, k.q, t.step, valid, t.lp3d, p);
     if (!valid) return 0u;
-    // force = v_orca - v (Simulator.cpp:676-677)
-    const v2 f = V(r.velocity.x - vel.x, r.velocity.y - vel.y);
-    // v += force * (1/mass) * step (Simulator.cpp:622-633); p += v * step (Simulator.cpp:603-604)
-    const float massRecip = 1.0f / 0.8f;
-    const v2 nv = V(vel.x + f.x * massRecip * t.step, vel.y + f.y * massRecip * t.step);
-    const v2 np = V(pos.x + (nv.x * t.step), pos.y + (nv.y * t.step));
-    t.ag.force[slot] = f;
-    t.ag.vel[slot] = nv;
-    t.ag.pos[slot] = np;
+    if (!(r.status & kLp3dDeferred)) integrate_agent(t, slot, pos, vel, r.velocity);
     if (t.record_neighbors) {
 #pragma unroll
         for (int j = 0; j < kK; j++) t.ag.nbr[kK * slot + j] = k.q[j] >= 0 ? t.sc.s_slot[k.q[j]] : -1;
         t.ag.nbr_cnt[slot] = n_nb;
     }
-    return r.status | extra;
+    return (r.status & ~kLp3dDeferred) | extra;
+}
+
+// RandomizedLP3D + integration for the agents k_orca parked, one thread per entry (second half of k_fallback).
+__device__ __forceinline__ void lp3d_parked(const TickView& t) {
+    const Lp3dQueue dq = t.lp3d;
+    const int n = (int)min(*dq.count, (unsigned long long)dq.cap);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int4 h = dq.hdr[e];  // (p, nObst, nc, failed)
+        const float4 o = dq.out[e];
+        Cons cs[kMaxCons], proj[kMaxCons];
+        for (int i = 0; i < h.z; i++) cs[i] = dq.cs[(size_t)i * dq.cap + e];
+        v2 out = V(o.x, o.y);
+        randomized_lp3d(h.y, cs, h.z, o.z, h.w, out, proj);
+        integrate_agent(t, t.sc.s_slot[h.x], t.sc.s_pos[h.x], t.sc.s_vel[h.x], out);
+    }
 }
 
 // 5 CTAs of 256 threads per SM (48 registers): measured 6 % faster than the 64-register build (4 CTAs);
@@ -345,7 +372,7 @@ __device__ __forceinline__ void orca_agent(const TickView& t, const int p, const
         }
     }
     __syncthreads();  // phase barrier: neighbour search | constraints + LP
-    st |= finish_agent<true>(t, p, k, mine && found);
+    st |= finish_agent<true, true>(t, p, k, mine && found);
     if (st) t.ag.status[t.sc.s_slot[p]] |= st;
     unsigned m_ovf = __ballot_sync(0xffffffffu, (st & 16u) != 0u);
     unsigned m_lp3 = __ballot_sync(0xffffffffu, (st & 64u) != 0u);
@@ -374,7 +401,9 @@ __global__ void __launch_bounds__(256, ECM_ORCA_MINBLOCKS) k_tick(TickView t) {
     orca_agent(t, p, n);
 }
 
-// mode 0: full tick for the listed agents; mode 1: neighbour query only (ecmgpu_find_neighbors)
+// The stragglers of a tick, one kernel: (a) warp-per-agent exhaustive neighbour search + ORCA for agents
+// whose ring budget ran out, (b) LP3D + integration for the agents k_orca parked.
+// mode 0: full tick; mode 1: neighbour query only (ecmgpu_find_neighbors)
 __global__ void __launch_bounds__(128) k_fallback(TickView t, int mode) {
     const int warps_total = (gridDim.x * blockDim.x) >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -388,7 +417,7 @@ __global__ void __launch_bounds__(128) k_fallback(TickView t, int mode) {
         knn_exhaustive(k, t.sc.s_pos[p], g);
         if (lane == 0) {
             if (mode == 0) {
-                unsigned st = finish_agent<false>(t, p, k);
+                unsigned st = finish_agent<false, false>(t, p, k);
                 if (st & 16u) atomicAdd(&t.sc.counters[C_TOTAL_OBST_OVF], 1ull);
                 if (st & 64u) atomicAdd(&t.sc.counters[C_TOTAL_LP3D], 1ull);
                 if (st & 128u) atomicAdd(&t.sc.counters[C_TOTAL_HALO_MISS], 1ull);
@@ -401,6 +430,7 @@ __global__ void __launch_bounds__(128) k_fallback(TickView t, int mode) {
         }
         __syncwarp();
     }
+    if (mode == 0) lp3d_parked(t);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -442,6 +472,33 @@ __global__ void k_find_obstacles(ObstView ob, BinView bins, float2 pos, float ra
     if (threadIdx.x == 0 && blockIdx.x == 0) *out_n = find_obstacles<false>(ob, bins, pos, range2, out, cap);
 }
 
+// CTA-wide reservation in a list whose length lives in global memory: one atomicAdd per CTA instead of
+// one per entry (all entries of a list hit ONE address; 20 k serialised atomics cost ~20 us per tick).
+// Returns this thread's index (valid where `want`).  All threads of the CTA must call it.
+__device__ __forceinline__ int cta_reserve(bool want, int* counter, int* s_warp /* [33] */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (lane == 0) s_warp[wid] = __popc(m);
+    __syncthreads();
+    if (wid == 0) {
+        int c = lane < nw ? s_warp[lane] : 0, incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int base = 0;
+        if (lane == 0 && total > 0) base = atomicAdd(counter, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < nw) s_warp[lane] = base + incl - c;
+    }
+    __syncthreads();
+    const int idx = s_warp[wid] + __popc(m & ((1u << lane) - 1u));
+    __syncthreads();  // s_warp is reused by the next reservation
+    return idx;
+}
+
 // ---- host I/O as records of owned agents (ecmgpu_update_io_owned) --------------------------------
 struct AgentRec {  // == ecmgpu_agent_rec (include/ecm_b200.h)
     int slot;
@@ -459,22 +516,19 @@ __global__ void __launch_bounds__(256) k_apply_records(int n, const AgentRec* __
     vel[r.slot] = make_float2(r.vx, r.vy);
 }
 
-// Compacts the owned agents into records (one atomic per warp; ascending slots within a warp).
-__global__ void __launch_bounds__(256) k_collect_owned(int n_slots, const unsigned char* __restrict__ active, const float2* __restrict__ pos,
-                                                       const float2* __restrict__ vel, AgentRec* __restrict__ out, int* __restrict__ count) {
+// Compacts the owned agents into records (one atomic per CTA; ascending slots within a CTA).
+constexpr int kCollectBlock = 1024;
+__global__ void __launch_bounds__(kCollectBlock) k_collect_owned(int n_slots, const unsigned char* __restrict__ active, const float2* __restrict__ pos,
+                                                                 const float2* __restrict__ vel, AgentRec* __restrict__ out, int* __restrict__ count) {
+    __shared__ int s_warp[33];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool mine = i < n_slots && active[i];
-    const unsigned m = __ballot_sync(0xffffffffu, mine);
-    if (m == 0u) return;
-    const int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == __ffs(m) - 1) base = atomicAdd(count, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    const int e = cta_reserve(mine, count, s_warp);
     if (!mine) return;
     const float2 p = pos[i], v = vel[i];
     AgentRec r;
     r.slot = i; r.x = p.x; r.y = p.y; r.vx = v.x; r.vy = v.y;
-    out[base + __popc(m & ((1u << lane) - 1u))] = r;
+    out[e] = r;
 }
 
 }  // namespace ecm

@@ -93,6 +93,10 @@ struct ecmgpu_sim {
     float gx0 = 0, gy0 = 0;
     bool grid_dirty = true;
     DevBuf<int> d_key, d_rank, d_cell_count, d_block_sums, d_s_slot, d_fb_list, d_ev_replan, d_ev_destroyed;
+    // LP3D queue (orca.cuh Lp3dQueue): one row per slot, 32 + 16 * kMaxCons bytes each
+    DevBuf<int4> d_lp3d_hdr;
+    DevBuf<float4> d_lp3d_out, d_lp3d_cs;
+    int lp3d_cap = 0;
     DevBuf<float2> d_s_pos, d_s_vel, d_s_pref;
     DevBuf<float> d_s_rad, d_s_spd;
     DevBuf<unsigned char> d_s_alive;
@@ -112,6 +116,7 @@ struct ecmgpu_sim {
     bool p2p = false;
     unsigned char* peer_inbox[2] = {nullptr, nullptr};  // [0] = left neighbour's recv[1], [1] = right neighbour's recv[0]
     DevBuf<MsgHeader> d_send_hdr;
+    DevBuf<int> d_seq;       // peer transport: device copy of comm_seq, advanced by k_exchange_p2p itself (graph replay)
     unsigned comm_seq = 1;   // sequence number of the next exchange
     unsigned cur_gen = 0;    // inbox generation of the exchange in flight / last completed (fixed at pack time)
     DevBuf<HaloEntry> d_self_ghost;
@@ -131,8 +136,10 @@ struct ecmgpu_sim {
         // owned calls: in = records, out = [32 B header with the count | records]
         unsigned char *in_buf[2] = {nullptr, nullptr}, *out_buf[2] = {nullptr, nullptr};
         // owned calls: where the count of generation b lands on the host, how many records were copied for it
-        const int32_t* owned_count[2] = {nullptr, nullptr};
-        int owned_copied[2] = {0, 0};
+        static constexpr int kTickets = 8;  // calls whose completion can be waited for individually (host pipelines > 2 deep)
+        cudaEvent_t ticket_done[kTickets] = {};
+        const int32_t* owned_count[kTickets] = {};
+        int owned_copied[kTickets] = {};
         // upper bound of the number of agents this handle owns, as far as the host can know it without a
         // synchronisation: the count confirmed by the last ecmgpu_io_wait plus the migrants every tick
         // enqueued since may have brought in; < 0 = unknown (everything is copied)
@@ -149,11 +156,13 @@ struct ecmgpu_sim {
     // ---- the tick as a CUDA graph (one launch instead of ~15 kernel / memset / NCCL submissions)
     bool use_graph = true;         // env ECMGPU_GRAPH=0 disables
     uint64_t config_epoch = 1;     // bumped whenever something the captured tick depends on changes
-    uint64_t graph_epoch = 0;
-    int graph_n_slots = -1;
-    uint64_t graph_launches = 0;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t graph_exec = nullptr;
+    // one graph per inbox generation: the peer transport alternates between two message buffers, everything else
+    // in the tick is the same from tick to tick (the exchange sequence number lives in device memory, d_seq)
+    uint64_t graph_epoch[2] = {0, 0};
+    int graph_n_slots[2] = {-1, -1};
+    uint64_t graph_launches[2] = {0, 0};
+    cudaGraph_t graph[2] = {nullptr, nullptr};
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -427,6 +436,11 @@ TickView make_view(ecmgpu_sim* s) {
     const float inf = std::numeric_limits<float>::infinity();
     t.cover_lo = s->strips_on && s->rank > 0 ? s->strip_lo - s->halo : -inf;
     t.cover_hi = s->strips_on && s->rank < s->n_ranks - 1 ? s->strip_hi + s->halo : inf;
+    t.lp3d.cap = s->lp3d_cap;
+    t.lp3d.count = s->d_counters.p + C_LP3D_N;
+    t.lp3d.hdr = s->d_lp3d_hdr.p;
+    t.lp3d.out = s->d_lp3d_out.p;
+    t.lp3d.cs = s->d_lp3d_cs.p;
     return t;
 }
 
@@ -498,6 +512,7 @@ void comm_teardown(ecmgpu_sim* s) {
         s->d_recv[d].free();
     }
     s->d_send_hdr.free();
+    s->d_seq.free();
     s->p2p = false;
     s->d_s_ghost.free(); s->d_self_ghost.free(); s->d_self_ghost_n.free(); s->d_g_key.free(); s->d_g_rank.free();
 }
@@ -543,7 +558,7 @@ int enqueue_pack(ecmgpu_sim* s, const TickView& t) {
     if (s->p2p) CUDA_TRY(s, cudaMemsetAsync(s->d_send_hdr.p, 0, 2 * sizeof(MsgHeader), s->stream));
     else for (int d = 0; d < 2; d++) CUDA_TRY(s, cudaMemsetAsync(s->d_send[d].p, 0, sizeof(MsgHeader), s->stream));
     CUDA_TRY(s, cudaMemsetAsync(s->d_self_ghost_n.p, 0, sizeof(int), s->stream));
-    k_pack<<<div_up(s->n_slots, 256), 256, 0, s->stream>>>(s->n_slots, t.ag, sv, s->d_counters.p);
+    k_pack<<<div_up(s->n_slots, kPackBlock), kPackBlock, 0, s->stream>>>(s->n_slots, t.ag, sv, s->d_counters.p);
     s->launches++;
     if (s->local_transport) CUDA_TRY(s, cudaEventRecord(s->ev_packed, s->stream));
     CUDA_TRY(s, cudaGetLastError());
@@ -565,9 +580,8 @@ int enqueue_exchange(ecmgpu_sim* s, const TickView& t) {
         }
         CUDA_TRY(s, cudaEventRecord(s->ev_pulled, s->stream));
     } else if (s->p2p) {
-        k_publish<<<1, 32, 0, s->stream>>>(sv, (int)s->comm_seq);
-        k_await<<<1, 32, 0, s->stream>>>(sv, (int)s->comm_seq);
-        s->launches += 2;
+        k_exchange_p2p<<<1, 256, 0, s->stream>>>(sv, t.ag, s->d_seq.p);  // publish, await, adopt the migrants
+        s->launches++;
     } else if (s->n_ranks > 1) {
         NCCL_TRY(s, g_nccl.GroupStart());
         if (s->rank > 0) {
@@ -580,8 +594,10 @@ int enqueue_exchange(ecmgpu_sim* s, const TickView& t) {
         }
         NCCL_TRY(s, g_nccl.GroupEnd());
     }
-    k_unpack_migrants<<<div_up(std::max(s->cap_migr, 1), 256), 256, 0, s->stream>>>(t.ag, sv);
-    s->launches++;
+    if (!s->p2p) {
+        k_unpack_migrants<<<div_up(std::max(s->cap_migr, 1), 256), 256, 0, s->stream>>>(t.ag, sv);
+        s->launches++;
+    }
     s->comm_seq++;  // the next exchange uses the other inbox generation
     CUDA_TRY(s, cudaGetLastError());
     return ECMGPU_OK;
@@ -591,7 +607,8 @@ int enqueue_exchange(ecmgpu_sim* s, const TickView& t) {
 int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
     GridParams gp{s->gx0, s->gy0, s->cell, 1.0f / s->cell, s->gw, s->gh};
     CUDA_TRY(s, cudaMemsetAsync(s->d_cell_count.p, 0, sizeof(int) * s->ncells_padded, s->stream));
-    CUDA_TRY(s, cudaMemsetAsync(s->d_counters.p + C_FALLBACK_N, 0, sizeof(unsigned long long), s->stream));
+    static_assert(C_LP3D_N == C_FALLBACK_N + 1, "the two per-tick counters are cleared by one memset");
+    CUDA_TRY(s, cudaMemsetAsync(s->d_counters.p + C_FALLBACK_N, 0, 2 * sizeof(unsigned long long), s->stream));
     const int nb = div_up(s->n_slots, 256);
     k_bin_count<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p);
     StripView sv = make_strip_view(s);
@@ -750,6 +767,9 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
     TRY_ALLOC(s->d_s_pos.alloc(n)); TRY_ALLOC(s->d_s_vel.alloc(n)); TRY_ALLOC(s->d_s_pref.alloc(n));
     TRY_ALLOC(s->d_s_rad.alloc(n)); TRY_ALLOC(s->d_s_spd.alloc(n)); TRY_ALLOC(s->d_s_slot.alloc(n));
     TRY_ALLOC(s->d_s_alive.alloc(n)); TRY_ALLOC(s->d_fb_list.alloc(n)); TRY_ALLOC(s->d_s_ghost.alloc(n));
+    s->lp3d_cap = (int)n;
+    TRY_ALLOC(s->d_lp3d_hdr.alloc(s->lp3d_cap)); TRY_ALLOC(s->d_lp3d_out.alloc(s->lp3d_cap));
+    TRY_ALLOC(s->d_lp3d_cs.alloc((size_t)s->lp3d_cap * kMaxCons));
     TRY_ALLOC(s->d_ev_replan.alloc(n)); TRY_ALLOC(s->d_ev_destroyed.alloc(n));
     TRY_ALLOC(s->d_counters.alloc(C_COUNT));
     TRY_ALLOC(cudaMemsetAsync(s->d_pos.p, 0, 8 * n, s->stream)); TRY_ALLOC(cudaMemsetAsync(s->d_vel.p, 0, 8 * n, s->stream));
@@ -787,17 +807,23 @@ void ecmgpu_destroy(ecmgpu_sim* s) {
     s->d_radius.free(); s->d_speed.free(); s->d_active.free(); s->d_replan_pending.free(); s->d_status.free();
     s->d_cell.free(); s->d_nbr.free(); s->d_nbr_cnt.free(); s->d_path_hdr.free(); s->d_path_pool.free(); s->d_path_bbox.free();
     s->d_key.free(); s->d_rank.free(); s->d_cell_count.free(); s->d_block_sums.free(); s->d_s_slot.free();
+    s->d_lp3d_hdr.free(); s->d_lp3d_out.free(); s->d_lp3d_cs.free();
     s->d_fb_list.free(); s->d_ev_replan.free(); s->d_ev_destroyed.free(); s->d_s_pos.free(); s->d_s_vel.free();
     s->d_s_pref.free(); s->d_s_rad.free(); s->d_s_spd.free(); s->d_s_alive.free(); s->d_counters.free();
     comm_teardown(s);
-    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
-    if (s->graph) cudaGraphDestroy(s->graph);
+    for (int g = 0; g < 2; g++) {
+        if (s->graph_exec[g]) cudaGraphExecDestroy(s->graph_exec[g]);
+        if (s->graph[g]) cudaGraphDestroy(s->graph[g]);
+    }
     if (s->io.ready) {
         cudaStreamSynchronize(s->io.s_in);
         cudaStreamSynchronize(s->io.s_out);
         for (int b = 0; b < 2; b++) {
             cudaFree(s->io.in_buf[b]); cudaFree(s->io.out_buf[b]);
             cudaEventDestroy(s->io.in_done[b]); cudaEventDestroy(s->io.in_consumed[b]); cudaEventDestroy(s->io.tick_done[b]); cudaEventDestroy(s->io.out_done[b]);
+        }
+        for (int k = 0; k < s->io.kTickets; k++) {
+            if (s->io.ticket_done[k]) cudaEventDestroy(s->io.ticket_done[k]);
         }
         cudaStreamDestroy(s->io.s_in);
         cudaStreamDestroy(s->io.s_out);
@@ -986,7 +1012,7 @@ int ecmgpu_update_phase(ecmgpu_sim* s, int phase) {
         if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
         k_orca<<<div_up(nb * 128, ob), ob, 0, s->stream>>>(t);
     }
-    k_fallback<<<148, 128, 0, s->stream>>>(t, 0);
+    k_fallback<<<148 * 4, 128, 0, s->stream>>>(t, 0);
     if (s->profiling) { CUDA_TRY(s, cudaEventRecord(s->ev[3], s->stream)); s->ev_valid = true; }
     s->launches += 3;
     s->ticks++;
@@ -999,31 +1025,38 @@ int ecmgpu_update(ecmgpu_sim* s) {
     if (s->local_transport && s->n_ranks > 1)
         return fail(s, ECMGPU_ERR_INVALID, "in-process strips: drive all handles with ecmgpu_update_phase(0), (1), (2)");
     // NCCL send/recv are kept out of graph capture (capturing them hung on 4 x B200 with NCCL 2.28): with the
-    // NCCL transport the tick is submitted launch by launch
-    const bool nccl_tick = s->strips_on && !s->local_transport && s->n_ranks > 1;  // also the peer transport: its sequence number changes per tick
+    // NCCL transport the tick is submitted launch by launch.  The peer transport is plain kernels and memsets.
+    const bool nccl_tick = s->strips_on && !s->local_transport && s->n_ranks > 1 && !s->p2p;
     if (s->use_graph && !nccl_tick && !s->profiling && s->n_slots > 0) {
         CUDA_TRY(s, cudaSetDevice(s->prm.device));
         int rc = ensure_ready(s);  // host-side (re)builds happen outside the capture
         if (rc) return rc;
-        if (!s->graph_exec || s->graph_epoch != s->config_epoch || s->graph_n_slots != s->n_slots) {
-            if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
-            if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
+        const int g = (int)(s->comm_seq & 1u);
+        if (!s->graph_exec[g] || s->graph_epoch[g] != s->config_epoch || s->graph_n_slots[g] != s->n_slots) {
+            if (s->graph_exec[g]) { cudaGraphExecDestroy(s->graph_exec[g]); s->graph_exec[g] = nullptr; }
+            if (s->graph[g]) { cudaGraphDestroy(s->graph[g]); s->graph[g] = nullptr; }
             const uint64_t l0 = s->launches, t0 = s->ticks;
+            const unsigned seq0 = s->comm_seq;
             CUDA_TRY(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeRelaxed));
             for (int phase = 0; phase < 3 && rc == ECMGPU_OK; phase++) rc = ecmgpu_update_phase(s, phase);
-            cudaError_t ce = cudaStreamEndCapture(s->stream, &s->graph);
-            s->graph_launches = s->launches - l0;
+            cudaError_t ce = cudaStreamEndCapture(s->stream, &s->graph[g]);
+            s->graph_launches[g] = s->launches - l0;
             s->launches = l0;
             s->ticks = t0;
+            s->comm_seq = seq0;
             if (rc) return rc;
             if (ce != cudaSuccess) return fail(s, ECMGPU_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
-            CUDA_TRY(s, cudaGraphInstantiate(&s->graph_exec, s->graph, 0));
-            s->graph_epoch = s->config_epoch;
-            s->graph_n_slots = s->n_slots;
+            CUDA_TRY(s, cudaGraphInstantiate(&s->graph_exec[g], s->graph[g], 0));
+            s->graph_epoch[g] = s->config_epoch;
+            s->graph_n_slots[g] = s->n_slots;
         }
-        CUDA_TRY(s, cudaGraphLaunch(s->graph_exec, s->stream));
-        s->launches += s->graph_launches;
+        CUDA_TRY(s, cudaGraphLaunch(s->graph_exec[g], s->stream));
+        s->launches += s->graph_launches[g];
         s->ticks++;
+        if (s->strips_on && s->n_ranks > 1) {  // what enqueue_pack / enqueue_exchange do to the host-side state
+            s->cur_gen = s->comm_seq & 1u;
+            s->comm_seq++;
+        }
         return ECMGPU_OK;
     }
     for (int phase = 0; phase < 3; phase++) {
@@ -1109,6 +1142,7 @@ static int io_prepare(ecmgpu_sim* s) {
         CUDA_TRY(s, cudaEventRecord(io.in_consumed[b], s->stream));
         CUDA_TRY(s, cudaEventRecord(io.out_done[b], io.s_out));
     }
+    for (int k = 0; k < io.kTickets; k++) CUDA_TRY(s, cudaEventCreateWithFlags(&io.ticket_done[k], cudaEventDisableTiming));
     io.ready = true;
     return ECMGPU_OK;
 }
@@ -1147,7 +1181,8 @@ int ecmgpu_update_io(ecmgpu_sim* s, int count, const float* in_pos, const float*
     if (out_vel) CUDA_TRY(s, cudaMemcpyAsync(out_vel, so + n8, sizeof(float2) * c, cudaMemcpyDeviceToHost, io.s_out));
     if (out_active) CUDA_TRY(s, cudaMemcpyAsync(out_active, so + 2 * n8, c, cudaMemcpyDeviceToHost, io.s_out));
     CUDA_TRY(s, cudaEventRecord(io.out_done[b], io.s_out));
-    io.owned_count[b] = nullptr;
+    CUDA_TRY(s, cudaEventRecord(io.ticket_done[io.calls % io.kTickets], io.s_out));
+    io.owned_count[io.calls % io.kTickets] = nullptr;
     if (ticket) *ticket = io.calls;
     io.calls++;
     return ECMGPU_OK;
@@ -1183,7 +1218,7 @@ int ecmgpu_update_io_owned(ecmgpu_sim* s, int n_in, const ecmgpu_agent_rec* in, 
     CUDA_TRY(s, cudaStreamWaitEvent(s->stream, io.out_done[b], 0));
     CUDA_TRY(s, cudaMemsetAsync(so_count, 0, sizeof(int), s->stream));
     if (s->n_slots > 0) {
-        k_collect_owned<<<div_up(s->n_slots, 256), 256, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, s->d_vel.p, so, so_count);
+        k_collect_owned<<<div_up(s->n_slots, kCollectBlock), kCollectBlock, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, s->d_vel.p, so, so_count);
         s->launches++;
     }
     CUDA_TRY(s, cudaEventRecord(io.tick_done[b], s->stream));
@@ -1198,8 +1233,9 @@ int ecmgpu_update_io_owned(ecmgpu_sim* s, int n_in, const ecmgpu_agent_rec* in, 
     CUDA_TRY(s, cudaMemcpyAsync(out_count, so_count, sizeof(int), cudaMemcpyDeviceToHost, io.s_out));
     if (copied) CUDA_TRY(s, cudaMemcpyAsync(out, so, sizeof(ecmgpu_agent_rec) * (size_t)copied, cudaMemcpyDeviceToHost, io.s_out));
     CUDA_TRY(s, cudaEventRecord(io.out_done[b], io.s_out));
-    io.owned_count[b] = out_count;
-    io.owned_copied[b] = copied;
+    CUDA_TRY(s, cudaEventRecord(io.ticket_done[io.calls % io.kTickets], io.s_out));
+    io.owned_count[io.calls % io.kTickets] = out_count;
+    io.owned_copied[io.calls % io.kTickets] = copied;
     if (ticket) *ticket = io.calls;
     io.calls++;
     return ECMGPU_OK;
@@ -1209,20 +1245,20 @@ int ecmgpu_io_wait(ecmgpu_sim* s, uint64_t ticket) {
     if (!s) return ECMGPU_ERR_INVALID;
     auto& io = s->io;
     if (!io.ready || ticket >= io.calls) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_io_wait: unknown ticket");
-    // a generation that has been reused since: waiting for its latest user also covers the older ticket
-    while (ticket + 2 < io.calls) ticket += 2;
+    // a ticket slot that has been reused since: waiting for its latest user also covers the older call
+    while (ticket + io.kTickets < io.calls) ticket += io.kTickets;
     CUDA_TRY(s, cudaSetDevice(s->prm.device));
-    const int b = (int)(ticket & 1);
-    CUDA_TRY(s, cudaEventSynchronize(io.out_done[b]));
-    if (io.owned_count[b]) {
-        const int have = *io.owned_count[b];
+    const int k = (int)(ticket % io.kTickets);
+    CUDA_TRY(s, cudaEventSynchronize(io.ticket_done[k]));
+    if (io.owned_count[k]) {
+        const int have = *io.owned_count[k];
         if (io.owned_confirmed < 0 || ticket >= io.owned_confirmed_ticket) {
             io.owned_confirmed = have;
             io.owned_confirmed_ticket = ticket;
         }
-        if (have > io.owned_copied[b])
+        if (have > io.owned_copied[k])
             return fail(s, ECMGPU_ERR_CAPACITY, "ecmgpu_update_io_owned: " + std::to_string(have) + " owned agents, room for " +
-                        std::to_string(io.owned_copied[b]) + " records");
+                        std::to_string(io.owned_copied[k]) + " records");
     }
     return ECMGPU_OK;
 }
@@ -1470,6 +1506,9 @@ int ecmgpu_comm_p2p_connect(ecmgpu_sim* s, const uint8_t* left_handles, const ui
     }
     CUDA_TRY(s, s->d_send_hdr.alloc(2));
     CUDA_TRY(s, cudaMemsetAsync(s->d_send_hdr.p, 0, 2 * sizeof(MsgHeader), s->stream));
+    CUDA_TRY(s, s->d_seq.alloc(1));
+    const int seq = (int)s->comm_seq;
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_seq.p, &seq, sizeof(int), cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     s->p2p = true;
     s->config_epoch++;

@@ -123,8 +123,11 @@ int ecmgpu_write_async(ecmgpu_sim* sim, int which, const void* src_pinned, int f
  * uploads positions / velocities of slots [0,count) from PINNED host memory (NULL = keep the device
  * values), runs ecmgpu_update, downloads positions / velocities / active flags into PINNED host
  * memory (NULL = skip).  Returns at once; the outputs of the call that returned `ticket` are complete
- * after ecmgpu_io_wait(ticket).  Consecutive calls overlap (upload of k+1 | tick k | download of k-1),
- * so use two sets of host buffers and wait for ticket k-1 after issuing call k.
+ * after ecmgpu_io_wait(ticket).  Consecutive calls overlap (upload of k+1 | tick k | download of k-1):
+ * give every call in flight its own set of host buffers.  Two sets (wait for ticket k-1 after issuing
+ * call k) already hide the tick behind the copies; three sets (wait for k-2) also let the download of
+ * k-1 and the upload of k+1 share the link in both directions.  The last 8 tickets can be waited for
+ * individually; an older ticket waits for the newest call that reused its slot.
  * Replaces the per-frame pattern Update() + GetPositionData()/GetVelocityData()/GetActiveFlags()
  * (Application.cpp:137-144, ECMRenderer.cpp:836-884) for hosts that keep the state on their side. */
 int ecmgpu_update_io(ecmgpu_sim* sim, int count, const float* in_pos, const float* in_vel, float* out_pos, float* out_vel,
