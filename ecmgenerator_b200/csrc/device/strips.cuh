@@ -11,6 +11,8 @@
 //                     owner keeps them as "self ghosts" for the coming tick
 //   NCCL send/recv    one fixed-size message per direction (header with the two counts)
 //   k_unpack_migrants received migrants become owned agents of this rank
+//   (peer transport: k_pack stores into the neighbour's inbox over NVLink, k_exchange_p2p publishes the
+//    counts + sequence number, waits for both neighbours and adopts the migrants - no NCCL call)
 //   k_ghost_count / k_ghost_scatter   received halo entries + self ghosts join the neighbour grid
 //                     snapshot as ghosts (visible as neighbours, never updated here)
 //
