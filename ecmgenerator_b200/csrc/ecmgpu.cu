@@ -140,11 +140,12 @@ struct ecmgpu_sim {
         cudaEvent_t ticket_done[kTickets] = {};
         const int32_t* owned_count[kTickets] = {};
         int owned_copied[kTickets] = {};
+        uint64_t owned_tick[kTickets] = {};  // ecmgpu_sim::ticks after the call's tick
         // upper bound of the number of agents this handle owns, as far as the host can know it without a
         // synchronisation: the count confirmed by the last ecmgpu_io_wait plus the migrants every tick
         // enqueued since may have brought in; < 0 = unknown (everything is copied)
         long long owned_confirmed = -1;
-        uint64_t owned_confirmed_ticket = 0;
+        uint64_t owned_confirmed_ticket = 0, owned_confirmed_tick = 0;
         cudaEvent_t in_done[2] = {nullptr, nullptr}, in_consumed[2] = {nullptr, nullptr}, tick_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
         uint64_t calls = 0;
     } io;
@@ -696,7 +697,7 @@ size_t elem_size(int which) {
     switch (which) {
         case ECMGPU_POS: case ECMGPU_VEL: case ECMGPU_PREFVEL: case ECMGPU_ATTRACTION: case ECMGPU_FORCE: return 8;
         case ECMGPU_RADIUS: case ECMGPU_SPEED: case ECMGPU_CELL: case ECMGPU_NEIGHBOR_COUNT: case ECMGPU_STATUS: return 4;
-        case ECMGPU_ACTIVE: return 1;
+        case ECMGPU_ACTIVE: case ECMGPU_REPLAN_PENDING: return 1;
         case ECMGPU_NEIGHBORS: return 20;
         default: return 0;
     }
@@ -715,6 +716,7 @@ void* dev_array(ecmgpu_sim* s, int which) {
         case ECMGPU_NEIGHBORS: return s->d_nbr.p;
         case ECMGPU_NEIGHBOR_COUNT: return s->d_nbr_cnt.p;
         case ECMGPU_STATUS: return s->d_status.p;
+        case ECMGPU_REPLAN_PENDING: return s->d_replan_pending.p;
         default: return nullptr;
     }
 }
@@ -1226,7 +1228,8 @@ int ecmgpu_update_io_owned(ecmgpu_sim* s, int n_in, const ecmgpu_agent_rec* in, 
     long long bound = s->n_slots;
     if (io.owned_confirmed >= 0) {
         const long long per_tick = s->strips_on ? 2ll * s->cap_migr : 0ll;
-        bound = std::min(bound, io.owned_confirmed + per_tick * (long long)(io.calls - io.owned_confirmed_ticket));
+        // every tick since the confirmed one - through this call or plain ecmgpu_update - may have brought migrants in
+        bound = std::min(bound, io.owned_confirmed + per_tick * (long long)(s->ticks - io.owned_confirmed_tick));
     }
     const int copied = (int)std::min<long long>(bound, out_cap);
     CUDA_TRY(s, cudaStreamWaitEvent(io.s_out, io.tick_done[b], 0));
@@ -1236,6 +1239,7 @@ int ecmgpu_update_io_owned(ecmgpu_sim* s, int n_in, const ecmgpu_agent_rec* in, 
     CUDA_TRY(s, cudaEventRecord(io.ticket_done[io.calls % io.kTickets], io.s_out));
     io.owned_count[io.calls % io.kTickets] = out_count;
     io.owned_copied[io.calls % io.kTickets] = copied;
+    io.owned_tick[io.calls % io.kTickets] = s->ticks;
     if (ticket) *ticket = io.calls;
     io.calls++;
     return ECMGPU_OK;
@@ -1255,6 +1259,7 @@ int ecmgpu_io_wait(ecmgpu_sim* s, uint64_t ticket) {
         if (io.owned_confirmed < 0 || ticket >= io.owned_confirmed_ticket) {
             io.owned_confirmed = have;
             io.owned_confirmed_ticket = ticket;
+            io.owned_confirmed_tick = io.owned_tick[k];
         }
         if (have > io.owned_copied[k])
             return fail(s, ECMGPU_ERR_CAPACITY, "ecmgpu_update_io_owned: " + std::to_string(have) + " owned agents, room for " +
@@ -1550,26 +1555,37 @@ int ecmgpu_comm_set_strips(ecmgpu_sim* s, const float* bounds, float halo_width)
         }
         for (int r = 1; r < s->n_ranks; r++) near = std::max(near, cnt[r]);
     }
-    s->cap_halo = std::min(n, std::max(4096, 4 * near));
-    s->cap_migr = std::min(n, std::max(1024, s->cap_halo / 4));
-    s->cap_self = 2 * s->cap_migr;
-    const size_t msg = strip_msg_bytes(s->cap_halo, s->cap_migr);
-    for (int d = 0; d < 2; d++) {
-        CUDA_TRY(s, s->d_send[d].alloc(msg));
-        CUDA_TRY(s, s->d_recv[d].alloc(2 * msg));  // two generations for the peer transport
-        CUDA_TRY(s, cudaMemsetAsync(s->d_send[d].p, 0, sizeof(MsgHeader), s->stream));
-        CUDA_TRY(s, cudaMemsetAsync(s->d_recv[d].p, 0, 2 * msg, s->stream));
+    const int want_halo = std::min(n, std::max(4096, 4 * near));
+    if (s->strips_on) {
+        // Re-balance: new borders for a crowd whose global state the caller has just written to every rank's slot
+        // arrays.  The message buffers stay (peer-transport mappings and sequence numbers with them), so the
+        // capacities chosen at the first call must still do.
+        if (want_halo > s->cap_halo)
+            return fail(s, ECMGPU_ERR_CAPACITY, "ecmgpu_comm_set_strips: the crowd near the new borders needs larger messages than "
+                        "the first call allocated; create the strips on a fresh handle");
+    } else {
+        s->cap_halo = want_halo;
+        s->cap_migr = std::min(n, std::max(1024, s->cap_halo / 4));
+        s->cap_self = 2 * s->cap_migr;
+        const size_t msg = strip_msg_bytes(s->cap_halo, s->cap_migr);
+        for (int d = 0; d < 2; d++) {
+            CUDA_TRY(s, s->d_send[d].alloc(msg));
+            CUDA_TRY(s, s->d_recv[d].alloc(2 * msg));  // two generations for the peer transport
+            CUDA_TRY(s, cudaMemsetAsync(s->d_send[d].p, 0, sizeof(MsgHeader), s->stream));
+            CUDA_TRY(s, cudaMemsetAsync(s->d_recv[d].p, 0, 2 * msg, s->stream));
+        }
+        CUDA_TRY(s, s->d_self_ghost.alloc(s->cap_self));
+        CUDA_TRY(s, s->d_self_ghost_n.alloc(1));
+        CUDA_TRY(s, s->d_g_key.alloc(2 * (size_t)s->cap_halo + s->cap_self));
+        CUDA_TRY(s, s->d_g_rank.alloc(2 * (size_t)s->cap_halo + s->cap_self));
+        // snapshot arrays must hold owned agents + ghosts
+        const size_t cap = (size_t)n + 2 * (size_t)s->cap_halo + s->cap_self;
+        CUDA_TRY(s, s->d_s_pos.alloc(cap)); CUDA_TRY(s, s->d_s_vel.alloc(cap)); CUDA_TRY(s, s->d_s_pref.alloc(cap));
+        CUDA_TRY(s, s->d_s_rad.alloc(cap)); CUDA_TRY(s, s->d_s_spd.alloc(cap)); CUDA_TRY(s, s->d_s_slot.alloc(cap));
+        CUDA_TRY(s, s->d_s_alive.alloc(cap)); CUDA_TRY(s, s->d_s_ghost.alloc(cap)); CUDA_TRY(s, s->d_fb_list.alloc(cap));
     }
-    CUDA_TRY(s, s->d_self_ghost.alloc(s->cap_self));
-    CUDA_TRY(s, s->d_self_ghost_n.alloc(1));
-    CUDA_TRY(s, s->d_g_key.alloc(2 * (size_t)s->cap_halo + s->cap_self));
-    CUDA_TRY(s, s->d_g_rank.alloc(2 * (size_t)s->cap_halo + s->cap_self));
-    // snapshot arrays must hold owned agents + ghosts
-    const size_t cap = (size_t)n + 2 * (size_t)s->cap_halo + s->cap_self;
-    CUDA_TRY(s, s->d_s_pos.alloc(cap)); CUDA_TRY(s, s->d_s_vel.alloc(cap)); CUDA_TRY(s, s->d_s_pref.alloc(cap));
-    CUDA_TRY(s, s->d_s_rad.alloc(cap)); CUDA_TRY(s, s->d_s_spd.alloc(cap)); CUDA_TRY(s, s->d_s_slot.alloc(cap));
-    CUDA_TRY(s, s->d_s_alive.alloc(cap)); CUDA_TRY(s, s->d_s_ghost.alloc(cap)); CUDA_TRY(s, s->d_fb_list.alloc(cap));
     s->strips_on = true;
+    s->io.owned_confirmed = -1;
     s->config_epoch++;
     if (s->n_slots > 0) {
         TickView t = make_view(s);

@@ -20,7 +20,7 @@ i32p = C.POINTER(C.c_int)
 u8p = C.POINTER(C.c_uint8)
 
 # selectors (include/ecm_b200.h)
-POS, VEL, PREFVEL, ATTRACTION, FORCE, RADIUS, SPEED, ACTIVE, CELL, NEIGHBORS, NEIGHBOR_COUNT, STATUS = range(12)
+POS, VEL, PREFVEL, ATTRACTION, FORCE, RADIUS, SPEED, ACTIVE, CELL, NEIGHBORS, NEIGHBOR_COUNT, STATUS, REPLAN_PENDING = range(13)
 ST_NO_CELL, ST_REPLAN, ST_ARRIVING, ST_DESTROYED, ST_OBST_OVERFLOW, ST_KNN_FALLBACK, ST_LP3D, ST_HALO_MISS = (
     1, 2, 4, 8, 16, 32, 64, 128)
 
@@ -28,6 +28,7 @@ _DTYPES = {
     POS: (np.float32, 2), VEL: (np.float32, 2), PREFVEL: (np.float32, 2), ATTRACTION: (np.float32, 2),
     FORCE: (np.float32, 2), RADIUS: (np.float32, 1), SPEED: (np.float32, 1), ACTIVE: (np.uint8, 1),
     CELL: (np.int32, 1), NEIGHBORS: (np.int32, 5), NEIGHBOR_COUNT: (np.int32, 1), STATUS: (np.uint32, 1),
+    REPLAN_PENDING: (np.uint8, 1),
 }
 
 EXPORTS = [

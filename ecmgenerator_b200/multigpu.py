@@ -69,6 +69,10 @@ def merge_owned(local: np.ndarray, owned: np.ndarray, all_reduce_sum) -> np.ndar
     return out.astype(np.uint8).reshape(a.shape[0], -1).view(a.dtype).reshape(a.shape)
 
 
+# per-slot state that travels with an agent when the borders move (the static components are replicated)
+REBALANCE_STATE = (gpu.POS, gpu.VEL, gpu.PREFVEL, gpu.ATTRACTION, gpu.FORCE, gpu.REPLAN_PENDING)
+
+
 def default_halo(neighbor_cell: float) -> float:
     return 4.0 * float(neighbor_cell)
 
@@ -77,10 +81,10 @@ class LocalStrips:
     """n strips inside one process; strips r lives on devices[r % len(devices)]."""
 
     def __init__(self, world, crowd, path_off, path_xy, n_strips: int, devices=(0,), halo: float | None = None,
-                 neighbor_cell: float = 0.0, record_neighbors: bool = True, step: float = float(DT)):
+                 neighbor_cell: float = 0.0, record_neighbors: bool = True, step: float = float(DT), bounds=None):
         n = crowd.n
         self.n = n
-        self.bounds = strip_bounds(crowd.pos[:, 0], n_strips)
+        self.bounds = strip_bounds(crowd.pos[:, 0], n_strips) if bounds is None else np.asarray(bounds, np.float32)
         self.sims = []
         pool = int(path_off[-1] * 1.25) + 4096
         for r in range(n_strips):
@@ -119,6 +123,18 @@ class LocalStrips:
                 out = np.zeros_like(loc)
             out[a > 0] = loc[a > 0]
         return out, owners.astype(np.uint8)
+
+    def rebalance(self):
+        """New equal-count borders from the current crowd: every strip gets the global state, then re-derives ownership."""
+        self.sync()
+        state = {w: self.gather(w)[0] for w in REBALANCE_STATE}
+        owners = self.gather(gpu.ACTIVE)[1]
+        self.bounds = strip_bounds(state[gpu.POS][owners > 0, 0], len(self.sims))
+        for s in self.sims:
+            for w, a in state.items():
+                s.write(w, a)
+            s.write(gpu.ACTIVE, owners)
+            s.comm_set_strips(self.bounds, self.halo)
 
     def stats(self):
         return [s.stats() for s in self.sims]
@@ -201,6 +217,22 @@ class StripSim:
         owners = self._all_reduce_sum(act.astype(np.int64))
         loc = self.sim.read(which, 0, self.n)
         return merge_owned(loc, act, self._all_reduce_sum), owners.astype(np.uint8)
+
+    def rebalance(self):
+        """New equal-count borders from the current crowd (collective: every rank calls it).  The global state is
+        merged through torch.distributed, written to every rank, and ownership re-derived; message buffers,
+        peer mappings and sequence numbers stay (ecmgpu_comm_set_strips, re-balancing clause)."""
+        import torch.distributed as dist
+
+        self.sim.sync()
+        state = {w: self.gather(w)[0] for w in REBALANCE_STATE}
+        owners = self.gather(gpu.ACTIVE)[1]
+        self.bounds = strip_bounds(state[gpu.POS][owners > 0, 0], self.n_ranks)
+        for w, a in state.items():
+            self.sim.write(w, a)
+        self.sim.write(gpu.ACTIVE, owners)
+        self.sim.comm_set_strips(self.bounds, self.halo)
+        dist.barrier()
 
     def close(self):
         self.sim.close()

@@ -57,7 +57,9 @@ enum {
     ECMGPU_CELL = 8,         /* [1 i32] ECM cell located this tick (2*edge+side), -1 none, -2 not evaluated (ECM.cpp:220-223) */
     ECMGPU_NEIGHBORS = 9,    /* [5 i32] neighbour slot ids of this tick, (sqDist, slot) ascending, -1 padding (KDTree.cpp:85-96) */
     ECMGPU_NEIGHBOR_COUNT = 10, /* [1 i32] */
-    ECMGPU_STATUS = 11       /* [1 u32] ECMGPU_ST_* bits of the last tick */
+    ECMGPU_STATUS = 11,      /* [1 u32] ECMGPU_ST_* bits of the last tick */
+    ECMGPU_REPLAN_PENDING = 12 /* [1 u8]  a replan event was raised and ecmgpu_set_path has not answered it yet
+                                *         (state a strip re-balance has to carry along with the agent) */
 };
 
 /* per-agent status bits (ECMGPU_STATUS) */
@@ -211,7 +213,11 @@ int ecmgpu_update_phase(ecmgpu_sim* sim, int phase);
 /* Strip boundaries along x: n_ranks+1 ascending values; rank r owns [bounds[r], bounds[r+1])
  * (the first and last strip extend to infinity).  halo_width: agents this close to a border are
  * mirrored to the neighbour; interior strips must be at least this wide.  Agents outside this
- * rank's strip are deactivated here (another rank owns them). */
+ * rank's strip are deactivated here (another rank owns them).
+ * Re-balancing: call it again with new borders after writing the GLOBAL state (positions, velocities,
+ * preferred velocities, attraction points, forces, active flags, replan-pending flags of every agent) to
+ * the slot arrays of every rank; message buffers, peer mappings and sequence numbers are kept, and the call
+ * fails with ECMGPU_ERR_CAPACITY if the new borders need larger messages than the first call allocated. */
 int ecmgpu_comm_set_strips(ecmgpu_sim* sim, const float* bounds, float halo_width);
 
 #ifdef __cplusplus

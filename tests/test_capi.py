@@ -42,6 +42,26 @@ def test_param_struct_layout_matches_header():
     assert gpu.Stats.ticks.offset % 8 == 0
 
 
+def test_agent_record_layout_matches_header():
+    """ecmgpu_agent_rec (ecmgpu_update_io_owned) is five 4-byte fields, slot first, as the numpy dtype says."""
+    from ecmgenerator_b200 import gpu
+
+    text = open(os.path.join(ROOT, "include", "ecm_b200.h")).read()
+    m = re.search(r"typedef struct ecmgpu_agent_rec \{(.*?)\} ecmgpu_agent_rec;", text, flags=re.S)
+    assert m, "ecmgpu_agent_rec not declared"
+    fields = [f.strip() for f in m.group(1).replace("\n", " ").split(";") if f.strip()]
+    assert fields == ["int32_t slot", "float x, y, vx, vy"]
+    assert gpu.AGENT_REC.itemsize == 20 and gpu.AGENT_REC.names == ("slot", "x", "y", "vx", "vy")
+    assert [gpu.AGENT_REC.fields[n][1] for n in gpu.AGENT_REC.names] == [0, 4, 8, 12, 16]
+
+
+def test_tools_and_bench_compile():
+    import py_compile
+
+    for rel in ["bench.py", "__graft_entry__.py"] + [os.path.join("tools", f) for f in sorted(os.listdir(os.path.join(ROOT, "tools"))) if f.endswith(".py")]:
+        py_compile.compile(os.path.join(ROOT, rel), doraise=True)
+
+
 @pytest.mark.skipif(has_cuda(), reason="only meaningful without a CUDA device")
 def test_no_cpu_fallback_without_gpu():
     from ecmgenerator_b200 import gpu

@@ -63,6 +63,37 @@ def test_in_process_strips_match_single_gpu_bitwise(n_strips):
     single.close()
 
 
+def test_rebalance_moves_the_borders_and_keeps_results_bitwise():
+    """Strips that start badly balanced (20 % / 30 % / 50 % of the crowd) are re-balanced mid-run: ownership moves
+    wholesale, the trajectory does not change by a bit."""
+    n, ticks = 6000, 90
+    w, c, off, pxy = _crowd(n, 44)
+    xs = np.sort(c.pos[:, 0])
+    skew = np.array([xs[0] - 1.0, xs[int(0.2 * n)], xs[int(0.5 * n)], xs[-1] + 1.0], np.float32)
+    single = gpu.GpuSim(w, n, float(S.DT), path_pool_points=int(off[-1] * 1.25) + 4096)
+    single.bulk_load(c.pos, c.radius, c.speed, off, pxy)
+    strips = M.LocalStrips(w, c, off, pxy, 3, devices=(0,), bounds=skew)
+    single.update(2 * ticks)
+    strips.update(ticks)
+    before = [int(s.read(gpu.ACTIVE, 0, n).sum()) for s in strips.sims]
+    strips.rebalance()
+    after = [int(s.read(gpu.ACTIVE, 0, n).sum()) for s in strips.sims]
+    assert max(before) > 0.45 * n and max(after) < 0.36 * n, (before, after)
+    assert sum(before) == sum(after)
+    strips.update(ticks)
+    strips.sync()
+    pos, owners = strips.gather(gpu.POS)
+    act = single.read(gpu.ACTIVE, 0, n)
+    assert np.array_equal(owners, act)
+    a = act > 0
+    assert_bits_equal(pos[a], single.read(gpu.POS, 0, n)[a], "positions")
+    assert_bits_equal(strips.gather(gpu.VEL)[0][a], single.read(gpu.VEL, 0, n)[a], "velocities")
+    assert_bits_equal(strips.gather(gpu.ATTRACTION)[0][a], single.read(gpu.ATTRACTION, 0, n)[a], "attraction points")
+    assert sum(s["halo_misses"] for s in strips.stats()) == 0
+    strips.close()
+    single.close()
+
+
 def test_halo_miss_is_detected_when_the_halo_is_too_small():
     n = 3000
     w, c, off, pxy = _crowd(n, 42)
