@@ -1536,7 +1536,9 @@ int ecmgpu_comm_set_strips(ecmgpu_sim* s, const float* bounds, float halo_width)
     s->strip_hi = s->rank == s->n_ranks - 1 ? inf : bounds[s->rank + 1];
     s->halo = halo_width;
     // capacities of the fixed-size messages (counts travel in the header, no host round trip): four times
-    // what the current crowd puts within the halo of this rank's borders, never less than 4096 entries
+    // what the current crowd puts within the halo of ANY vertical line, never less than 4096 entries.  Taking the
+    // worst line instead of today's borders makes the layout the same on every rank (every rank still sees
+    // the whole crowd here) and keeps it valid when the borders move (re-balancing) or the crowd drifts.
     const int n = s->prm.max_agents;
     int near = 0;
     if (s->n_slots > 0) {
@@ -1545,15 +1547,16 @@ int ecmgpu_comm_set_strips(ecmgpu_sim* s, const float* bounds, float halo_width)
         CUDA_TRY(s, cudaMemcpyAsync(pos.data(), s->d_pos.p, sizeof(float2) * s->n_slots, cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(s, cudaMemcpyAsync(act.data(), s->d_active.p, s->n_slots, cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(s, cudaStreamSynchronize(s->stream));
-        // every rank still sees the whole crowd here and counts at EVERY border, so that all ranks agree
-        // on the message layout (neighbours must use the same capacities)
-        std::vector<int> cnt(s->n_ranks + 1, 0);
-        for (int i = 0; i < s->n_slots; i++) {
-            if (!act[i]) continue;
-            for (int r = 1; r < s->n_ranks; r++)
-                if (std::fabs(pos[i].x - bounds[r]) < halo_width) cnt[r]++;
+        std::vector<float> xs;
+        xs.reserve(s->n_slots);
+        for (int i = 0; i < s->n_slots; i++)
+            if (act[i]) xs.push_back(pos[i].x);
+        std::sort(xs.begin(), xs.end());
+        size_t j = 0;
+        for (size_t i = 0; i < xs.size(); i++) {  // agents with x in [xs[i] - 2 halo, xs[i]]: within the halo of the line in the middle
+            while (xs[i] - xs[j] > 2.0f * halo_width) j++;
+            near = std::max(near, (int)(i - j + 1));
         }
-        for (int r = 1; r < s->n_ranks; r++) near = std::max(near, cnt[r]);
     }
     const int want_halo = std::min(n, std::max(4096, 4 * near));
     if (s->strips_on) {
