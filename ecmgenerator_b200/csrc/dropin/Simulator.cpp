@@ -72,7 +72,8 @@ void Simulator::Initialize() {  // Simulator.cpp:21-60
     const auto& e = m_World->ecm;
     Check(ecmgpu_set_ecm(m_Gpu, m_World->bbox, e.num_vertices(), e.vert_xy.data(), e.vert_clear.data(), e.num_edges(),
                          e.edge_v.data(), e.edge_cl.data()), "ecmgpu_set_ecm");
-    const auto& o = m_World->obst;
+    m_Obst = m_World->obst;
+    const auto& o = m_Obst;
     Check(ecmgpu_set_obstacles(m_Gpu, o.num_vertices(), o.xy.data(), o.next.data(), o.prev.data(), o.convex.data()), "ecmgpu_set_obstacles");
     printf("SIMULATOR: Data for %d agents was created.\n", n);
 }
@@ -360,8 +361,38 @@ void Simulator::FindNNearestNeighbors(const Entity& agent, int n, std::vector<En
 }
 
 // Simulator::FindNearestObstacles (Simulator.cpp:259-292) on the host mirror; a query API, not the hot path.
+void Simulator::FindNNearestNeighborsDeprecated(const Entity& agent, int n, std::vector<Entity>& outNeighbors, int& outNNeighbors) {
+    outNeighbors.clear();
+    outNeighbors.resize(n);  // Simulator.cpp:230-231
+    FindNNearestNeighbors(agent, n, outNeighbors, outNNeighbors);
+}
+
+void KDTree::KNearestAgents(Simulator* simulation, int agent, int k, std::vector<Entity>& outAgents, int& outNumNeighbors) {
+    simulation->FindNNearestNeighbors(agent, k, outAgents, outNumNeighbors);
+}
+
+int Simulator::AddObstacleArea(const Point& position, const Vec2& halfSize, bool updateECM) {  // Simulator.cpp:383-412
+    ObstacleArea oa;
+    oa.ID = m_ObstacleAreas.size() == 0 ? 0 : m_ObstacleAreas[m_ObstacleAreas.size() - 1].ID + 1;
+    oa.Position = position;
+    oa.HalfHeight = halfSize.y;
+    oa.HalfWidth = halfSize.x;
+    oa.obstacleVerts.push_back(Point(position.x + halfSize.x, position.y + halfSize.y));
+    oa.obstacleVerts.push_back(Point(position.x - halfSize.x, position.y + halfSize.y));
+    oa.obstacleVerts.push_back(Point(position.x - halfSize.x, position.y - halfSize.y));
+    oa.obstacleVerts.push_back(Point(position.x + halfSize.x, position.y - halfSize.y));
+    // Environment::AddObstacle (Environment.cpp:198-229): the obstacle joins the list FindNearestObstacles scans
+    float xy[8];
+    for (int i = 0; i < 4; i++) { xy[2 * i] = oa.obstacleVerts[i].x; xy[2 * i + 1] = oa.obstacleVerts[i].y; }
+    ecmb200::AppendObstacle(m_Obst, xy, 4);
+    const auto& o = m_Obst;
+    Check(ecmgpu_set_obstacles(m_Gpu, o.num_vertices(), o.xy.data(), o.next.data(), o.prev.data(), o.convex.data()), "ecmgpu_set_obstacles");
+    if (updateECM) m_Error = "AddObstacleArea: updateECM needs the host-side ECM generator (not part of this library); the ECM and the planned paths are unchanged";
+    return oa.ID;
+}
+
 void Simulator::FindNearestObstacles(const Entity& agent, float rangeSquared, std::vector<int>& outObstacles) const {
-    const auto& o = m_World->obst;
+    const auto& o = m_Obst;
     const float ax = m_Positions[agent].x, ay = m_Positions[agent].y;
     auto approx = [](float px, float py, float qx, float qy) {
         const float E = 0.0001f;

@@ -72,6 +72,23 @@ struct SpawnArea : public Area {
     std::vector<float> timeSinceLastSpawn;
 };
 
+struct ObstacleArea : public Area {  // Area.h:101-105
+    ObstacleArea() { Type = OBSTACLE; }
+    std::vector<Point> obstacleVerts;
+};
+
+class Simulator;
+
+// Stand-in for the reference's KDTree (KDTree.h:57-80) behind Simulator::GetKDTree(): there is no tree on this
+// side - the neighbour structure is the per-tick uniform grid in HBM - so Construct / Clear are no-ops and
+// KNearestAgents answers with the exact 5-NN of the CURRENT state (Simulator::FindNNearestNeighbors).
+class KDTree {
+public:
+    void Construct(Simulator*) {}
+    void Clear() {}
+    void KNearestAgents(Simulator* simulation, int agent, int k, std::vector<Entity>& outAgents, int& outNumNeighbors);
+};
+
 class Simulator {
 public:
     // `world` and `planner` are borrowed, like ECM* / ECMPathPlanner* / Environment* in the reference.
@@ -89,6 +106,11 @@ public:
 
     int AddSpawnArea(const Point& position, const Vec2& halfSize, const SpawnConfiguration& config, int ID = -1);
     int AddGoalArea(const Point& position, const Vec2& halfSize, int ID = -1);
+    // Simulator.cpp:383-412: a box obstacle for FindNearestObstacles / ORCA.  Like the reference the area itself is
+    // not recorded (GetObstacleAreas() stays empty, the returned ID is 0) and paths are not replanned; updateECM = true
+    // would need the host-side ECM generator (out of scope here): the obstacle is added, LastError() says so.
+    int AddObstacleArea(const Point& position, const Vec2& halfSize, bool updateECM = false);
+    std::vector<ObstacleArea>& GetObstacleAreas() { return m_ObstacleAreas; }
     void RemoveArea(SimAreaType areaType, int ID);
     void ConnectSpawnGoalAreas(int spawnID, int goalID, float spawnRate = 0.0f);
     void DeconnectSpawnGoalAreas(int spawnID, int goalID);
@@ -100,6 +122,8 @@ public:
 
     // exact 5-NN (DESIGN.md "Neighbour contract"); outNeighbors must have size n == 5
     void FindNNearestNeighbors(const Entity& agent, int n, std::vector<Entity>& outNeighbors, int& outNNeighbors);
+    // the reference's unused brute-force variant (Simulator.cpp:228-257): same exact answer here, resizes outNeighbors
+    void FindNNearestNeighborsDeprecated(const Entity& agent, int n, std::vector<Entity>& outNeighbors, int& outNNeighbors);
     // flat obstacle-vertex indices in (obstacle, vertex) order instead of ObstacleVertex*
     void FindNearestObstacles(const Entity& agent, float rangeSquared, std::vector<int>& outObstacles) const;
     bool ValidSpawnLocation(const Point& location, float clearance) const;
@@ -116,6 +140,9 @@ public:
     PositionComponent* GetAttractionPointData() const { return m_AttractionPoints; }
     bool* GetActiveFlags() const { return m_ActiveAgents; }
     ecmb200::PathPlanner* GetECMPathPlanner() { return m_Planner; }
+    KDTree* GetKDTree() const { return const_cast<KDTree*>(&m_KDTree); }
+    const ecmb200::FlatWorld* GetEnvironment() const { return m_World; }  // the flattened Environment + ECM
+    const ecmb200::FlatObstacles& GetObstacles() const { return m_Obst; } // world obstacles + AddObstacleArea boxes
     float GetSimulationStepTime() const { return m_SimStepTime; }
     const std::string& LastError() const { return m_Error; }
     ecmgpu_sim* GetGpuHandle() const { return m_Gpu; }
@@ -144,6 +171,9 @@ private:
 
     std::map<int, SpawnArea> m_SpawnAreas;
     std::map<int, GoalArea> m_GoalAreas;
+    std::vector<ObstacleArea> m_ObstacleAreas;
+    ecmb200::FlatObstacles m_Obst;  // what the GPU holds: the world's obstacles, then the boxes added at run time
+    KDTree m_KDTree;
     int m_NextSpawnID = 0;
     int m_NextGoalID = 0;
 

@@ -111,5 +111,18 @@ int ecmsim_add_spawn_area(void* h, float x, float y, float hw, float hh, float c
 }
 int ecmsim_add_goal_area(void* h, float x, float y, float hw, float hh) { return ((SimBox*)h)->sim->AddGoalArea(Point(x, y), Vec2(hw, hh)); }
 void ecmsim_connect_areas(void* h, int spawn_id, int goal_id, float rate) { ((SimBox*)h)->sim->ConnectSpawnGoalAreas(spawn_id, goal_id, rate); }
+int ecmsim_add_obstacle_area(void* h, float x, float y, float hw, float hh, int update_ecm) {
+    GUARD(return ((SimBox*)h)->sim->AddObstacleArea(Point(x, y), Vec2(hw, hh), update_ecm != 0), -2)
+}
+int ecmsim_num_obstacle_vertices(void* h) { return ((SimBox*)h)->sim->GetObstacles().num_vertices(); }
+// the reference's other routes to the neighbour query: GetKDTree()->KNearestAgents and the deprecated brute force
+int ecmsim_find_neighbors_via(void* h, int agent, int route, int* out5) {
+    std::vector<int> nb(5, -1);
+    int n = 0;
+    auto* sim = ((SimBox*)h)->sim;
+    GUARD(if (route == 0) sim->GetKDTree()->KNearestAgents(sim, agent, 5, nb, n); else sim->FindNNearestNeighborsDeprecated(agent, 5, nb, n), -2)
+    for (int k = 0; k < 5; k++) out5[k] = nb[k];
+    return n;
+}
 
 }  // extern "C"

@@ -50,6 +50,9 @@ def lib():
         L.ecmsim_add_spawn_area.argtypes = [vp] + [C.c_float] * 6
         L.ecmsim_add_goal_area.argtypes = [vp] + [C.c_float] * 4
         L.ecmsim_connect_areas.argtypes = [vp, C.c_int, C.c_int, C.c_float]
+        L.ecmsim_add_obstacle_area.argtypes = [vp] + [C.c_float] * 4 + [C.c_int]
+        L.ecmsim_num_obstacle_vertices.argtypes = [vp]
+        L.ecmsim_find_neighbors_via.argtypes = [vp, C.c_int, C.c_int, i32p]
         # the same library also carries the ecmhost_* entry points (one FlatWorld layout)
         L.ecmhost_world_from_arrays.restype = vp
         L.ecmhost_world_from_arrays.argtypes = [C.POINTER(host._WorldView)]
@@ -140,6 +143,24 @@ class Simulator:
 
     def connect_areas(self, spawn_id, goal_id, rate):
         self.L.ecmsim_connect_areas(self.h, int(spawn_id), int(goal_id), float(rate))
+
+    def find_obstacles(self, agent, range_squared: float, cap: int = 256):
+        """Simulator::FindNearestObstacles: flat obstacle-vertex indices in (obstacle, vertex) order."""
+        out = np.full(cap, -1, np.int32)
+        n = self.L.ecmsim_find_obstacles(self.h, int(agent), float(range_squared), out.ctypes.data_as(i32p), cap)
+        return out[: min(n, cap)].copy()
+
+    def add_obstacle_area(self, pos, half, update_ecm: bool = False) -> int:
+        return self._ck(self.L.ecmsim_add_obstacle_area(self.h, float(pos[0]), float(pos[1]), float(half[0]), float(half[1]), int(update_ecm)))
+
+    def num_obstacle_vertices(self) -> int:
+        return int(self.L.ecmsim_num_obstacle_vertices(self.h))
+
+    def find_neighbors_via(self, agent, route: str):
+        """route 'kdtree': GetKDTree()->KNearestAgents; 'deprecated': FindNNearestNeighborsDeprecated."""
+        out = np.full(5, -1, np.int32)
+        n = self._ck(self.L.ecmsim_find_neighbors_via(self.h, int(agent), 0 if route == "kdtree" else 1, out.ctypes.data_as(i32p)))
+        return out, n
 
 
 def _world_in(L, w):

@@ -106,6 +106,27 @@ class World:
     blocks_x: np.ndarray | None = None
     blocks_y: np.ndarray | None = None
 
+    def with_box_obstacle(self, pos, half) -> "World":
+        """Copy of the world with one more box obstacle, vertices in the order of Simulator::AddObstacleArea
+        (Simulator.cpp:404-407: ++, -+, --, +-; counter-clockwise) and the links / convexity flags of
+        Obstacle::Initialize (ECMDataTypes.cpp:36-59).  The ECM is unchanged, as with updateECM = false."""
+        import dataclasses
+
+        x, y, hx, hy = (np.float32(v) for v in (pos[0], pos[1], half[0], half[1]))
+        box = np.array([[x + hx, y + hy], [x - hx, y + hy], [x - hx, y - hy], [x + hx, y - hy]], np.float32)
+        base = int(self.obst_next.shape[0])
+        nxt = base + np.array([1, 2, 3, 0], np.int32)
+        prv = base + np.array([3, 0, 1, 2], np.int32)
+        conv = np.zeros(4, np.uint8)
+        for i in range(4):
+            p, q, c = box[prv[i] - base], box[nxt[i] - base], box[i]
+            a, b = p - q, c - p  # isConvex = det(prev - next, p - prev) >= 0, float arithmetic
+            conv[i] = 1 if np.float32(a[0] * b[1]) - np.float32(a[1] * b[0]) >= 0 else 0
+        return dataclasses.replace(
+            self, obst_xy=np.concatenate([self.obst_xy, box]), obst_next=np.concatenate([self.obst_next, nxt]),
+            obst_prev=np.concatenate([self.obst_prev, prv]), obst_convex=np.concatenate([self.obst_convex, conv]),
+            obst_first=np.concatenate([self.obst_first, [base + 4]]).astype(np.int32))
+
     @property
     def n_vertices(self) -> int:
         return int(self.vert_clear.shape[0])

@@ -60,6 +60,7 @@ def _load(mode):
         L.ecmref_add_spawn_area.argtypes = [C.c_void_p] + [C.c_float] * 6
         L.ecmref_add_goal_area.argtypes = [C.c_void_p] + [C.c_float] * 4
         L.ecmref_connect_areas.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float]
+        L.ecmref_add_obstacle_area.argtypes = [C.c_void_p] + [C.c_float] * 4
         L.ecmref_srand.argtypes = [C.c_uint]
         L.ecmref_valid_spawn_location.argtypes = [C.c_void_p] + [C.c_float] * 3
         _LIBS[mode] = L
@@ -133,6 +134,9 @@ class RefSim:
 
     def connect_areas(self, spawn_id, goal_id, rate):
         self.L.ecmref_connect_areas(self.h, int(spawn_id), int(goal_id), float(rate))
+
+    def add_obstacle_area(self, pos, half) -> int:
+        return self.L.ecmref_add_obstacle_area(self.h, float(pos[0]), float(pos[1]), float(half[0]), float(half[1]))
 
     def srand(self, seed: int):
         self.L.ecmref_srand(int(seed))

@@ -238,6 +238,8 @@ int ecmref_add_spawn_area(void* h, float x, float y, float hw, float hh, float c
 }
 int ecmref_add_goal_area(void* h, float x, float y, float hw, float hh) { return ((RefSim*)h)->sim->AddGoalArea(Point(x, y), Vec2(hw, hh)); }
 void ecmref_connect_areas(void* h, int spawn_id, int goal_id, float rate) { ((RefSim*)h)->sim->ConnectSpawnGoalAreas(spawn_id, goal_id, rate); }
+// Simulator::AddObstacleArea (Simulator.cpp:383-412) -> Environment::AddObstacle (Environment.cpp:198-229), updateECM = false
+int ecmref_add_obstacle_area(void* h, float x, float y, float hw, float hh) { return ((RefSim*)h)->sim->AddObstacleArea(Point(x, y), Vec2(hw, hh), false); }
 void ecmref_srand(unsigned seed) { srand(seed); }
 int ecmref_valid_spawn_location(void* h, float x, float y, float c) { return ((RefSim*)h)->sim->ValidSpawnLocation(Point(x, y), c) ? 1 : 0; }
 

@@ -104,6 +104,53 @@ def test_dropin_matches_c_oracle_with_host_planner():
     sim.close()
 
 
+def test_add_obstacle_area_equals_a_world_that_had_the_box_all_along():
+    """Simulator::AddObstacleArea (updateECM = false) feeds FindNearestObstacles / ORCA only: the drop-in with the box
+    added through the API must walk like the C oracle on a world whose obstacle list already ends with that box
+    (the unmodified reference does, bit for bit: checked when this test was written).  A second simulator gets the
+    box mid-run."""
+    w = S.world_c1()
+    c = S.crowd_c1(w, n=300, seed=62)
+    off, pxy, ok = plan_paths(w, c.pos, c.goal, c.radius)
+    assert ok == c.n
+    box_pos, box_half = (-63.449421, -50.712929), (1.0, 1.5)  # 6 m ahead of agent 14, 23 agents pass within reach of it
+    n_world = w.obst_next.shape[0]
+    sim = dropin.Simulator(w, 320, 1 / 60)
+    late = dropin.Simulator(w, 320, 1 / 60)
+    for s in (sim, late):
+        for i in range(c.n):
+            assert s.spawn_agent(c.pos[i], c.goal[i], c.radius[i], c.speed[i]) == i
+    assert sim.add_obstacle_area(box_pos, box_half) == 0  # the reference never records the area: every call returns 0
+    assert sim.num_obstacle_vertices() == n_world + 4 and late.num_obstacle_vertices() == n_world
+    ora = OracleSim(w.with_box_obstacle(box_pos, box_half), 320, 1 / 60, "exact-knn")
+    ora.bulk_load(c.pos, c.radius, c.speed, off, pxy)
+    bare = OracleSim(w, 320, 1 / 60, "exact-knn")
+    bare.bulk_load(c.pos, c.radius, c.speed, off, pxy)
+    for t in range(90):
+        sim.update(1 / 60)
+        late.update(1 / 60)
+        ora.step(1)
+        bare.step(1)
+        if t == 29:
+            a, z = late.state(c.n), bare.state(c.n)
+            assert np.abs(a["vel"] - z["vel"]).max() <= 1e-3, "before its box arrives the second simulator walks the bare world"
+            late.add_obstacle_area(box_pos, box_half)
+            assert late.num_obstacle_vertices() == n_world + 4
+    a, b, z = sim.state(c.n), ora.state(c.n), bare.state(c.n)
+    assert np.array_equal(a["active"], b["active"])
+    assert np.abs(a["vel"] - b["vel"]).max() <= 1e-3 and np.abs(a["pos"] - b["pos"]).max() <= 1e-3
+    moved = np.abs(b["pos"] - z["pos"]).max(axis=1) > 1e-3
+    assert moved.sum() >= 3, "the box must matter in this scene"
+    seen = sim.find_obstacles(14, (10.0 * float(c.speed[14]) + float(c.radius[14])) ** 2)
+    assert (seen >= n_world).any(), "FindNearestObstacles reports the new vertices"
+    l = late.state(c.n)
+    assert np.isfinite(l["pos"]).all() and np.abs(l["pos"] - z["pos"])[moved].max() > 1e-3, "the late box deflects the same agents"
+    assert np.array_equal(sim.find_neighbors_via(14, "kdtree")[0], sim.find_neighbors(14)[0])
+    assert np.array_equal(sim.find_neighbors_via(14, "deprecated")[0], sim.find_neighbors(14)[0])
+    sim.close()
+    late.close()
+
+
 def test_headless_cpp_program_runs():
     """examples/headless_main.cpp: a C++17 host program over the drop-in class (no Python in the loop)."""
     import os
