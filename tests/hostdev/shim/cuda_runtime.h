@@ -1,0 +1,58 @@
+// TEST INFRASTRUCTURE: just enough of the CUDA C++ surface to compile csrc/device/*.cuh with g++ for ONE
+// thread, so that the device algorithms can be checked on the CPU against the golden vectors
+// (tests/test_hostdev.py).  Nothing in the product includes this; the product path is nvcc + a GPU.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
+#define __launch_bounds__(...)
+
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+
+using std::max;
+using std::min;
+
+template <class T>
+static inline T __ldg(const T* p) { return *p; }
+template <class T>
+static inline T __ldcg(const T* p) { return *p; }
+
+// one thread == one "warp": the warp-collective operations degenerate to identities
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+static inline void __syncthreads() {}
+static inline int __reduce_max_sync(unsigned, int v) { return v; }
+static inline bool __any_sync(unsigned, bool p) { return p; }
+static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int) { return v; }
+template <class T>
+static inline T __shfl_up_sync(unsigned, T v, int) { return v; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline void __threadfence_system() {}
+static inline void __nanosleep(unsigned) {}
+
+template <class T, class U>
+static inline T atomicAdd(T* p, U v) { T old = *p; *p = (T)(old + (T)v); return old; }
+
+struct HdDim3 { int x, y, z; };
+static const HdDim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
+
+// RotateVector / the VO half angle use the C library's sinf / cosf (UtilityFunctions.cpp:233-242) and so does
+// the oracle: route the device code's single sincosf call to the same two functions
+static inline void hd_sincosf(float a, float* s, float* c) { *s = sinf(a); *c = cosf(a); }
+#define sincosf hd_sincosf
