@@ -58,6 +58,9 @@ struct Knn {
         }
     }
     __device__ __forceinline__ void consider(v2 self, int cand, const GridView& g) {
+#ifdef ECM_KNN_STATS  // host test build only (tests/hostdev): counts the candidates visited
+        ECM_KNN_STATS;
+#endif
         v2 pj = __ldg(&g.s_pos[cand]);
         float dx = pj.x - self.x, dy = pj.y - self.y;
         float dd = dx * dx + dy * dy;
@@ -91,10 +94,31 @@ struct Knn {
 // of row pieces so that there is ONE candidate loop in the code: r = 1: the own row, the row below,
 // the row above (3 cells each); r > 1: the two full outer rows, then the two outer cells of every
 // row in between.
+#ifdef ECM_KNN_PRUNE
+// Squared distance from `self` to the column span [x0 .. x1] / to row y of the grid (0 inside).  Border cells
+// also hold the agents clamped into them from outside the grid, so they extend to infinity outwards.
+__device__ __forceinline__ float knn_span_dx2(const GridView& g, v2 self, int x0, int x1) {
+    const float lo = x0 <= 0 ? -CUDART_INF_F : g.x0 + (float)x0 * g.cell;
+    const float hi = x1 >= g.w - 1 ? CUDART_INF_F : g.x0 + (float)(x1 + 1) * g.cell;
+    const float d = fmaxf(fmaxf(lo - self.x, self.x - hi), 0.0f);
+    return d * d;
+}
+__device__ __forceinline__ float knn_row_dy2(const GridView& g, v2 self, int y) {
+    const float lo = y <= 0 ? -CUDART_INF_F : g.y0 + (float)y * g.cell;
+    const float hi = y >= g.h - 1 ? CUDART_INF_F : g.y0 + (float)(y + 1) * g.cell;
+    const float d = fmaxf(fmaxf(lo - self.y, self.y - hi), 0.0f);
+    return d * d;
+}
+#endif
+
 __device__ __forceinline__ bool knn_grid(Knn& k, v2 self, const GridView& g, int max_ring) {
     int cx, cy;
     g.cell_of(self, cx, cy);
     k.init();
+#ifdef ECM_KNN_PRUNE
+    // of the two neighbouring rows take the nearer one first: it tightens the 5th distance before the farther one is judged
+    const bool low_first = (self.y - (g.y0 + (float)cy * g.cell)) * 2.0f <= g.cell;
+#endif
     for (int r = 1; r <= max_ring; r++) {
         const int xa = max(cx - r, 0), xb = min(cx + r, g.w - 1);
         const int ya = max(cy - r, 0), yb = min(cy + r, g.h - 1);
@@ -102,7 +126,11 @@ __device__ __forceinline__ bool knn_grid(Knn& k, v2 self, const GridView& g, int
         for (int s = 0; s < pieces; s++) {
             int y, x0, x1;
             if (r == 1) {  // own row first: near candidates tighten the 5th distance early
+#ifdef ECM_KNN_PRUNE
+                y = s == 0 ? cy : ((s == 1) == low_first ? cy - 1 : cy + 1);
+#else
                 y = s == 0 ? cy : (s == 1 ? cy - 1 : cy + 1);
+#endif
                 x0 = xa; x1 = xb;
             } else if (s < 2) {
                 y = s == 0 ? cy - r : cy + r;
@@ -112,6 +140,17 @@ __device__ __forceinline__ bool knn_grid(Knn& k, v2 self, const GridView& g, int
                 x0 = x1 = ((s - 2) & 1) ? cx + r : cx - r;
             }
             if (y < 0 || y >= g.h || x0 < 0 || x1 >= g.w) continue;
+#ifdef ECM_KNN_PRUNE
+            // A cell farther away than the current 5th distance cannot contribute (distances only shrink, and a tie
+            // needs d == d5): drop such end cells of the piece, or the whole piece.  1.001: rounding of both sides.
+            if (k.q[kK - 1] >= 0) {
+                const float lim = k.d[kK - 1] * 1.001f;
+                const float dy2 = knn_row_dy2(g, self, y);
+                if (x0 < x1 && dy2 + knn_span_dx2(g, self, x0, x0) > lim) x0++;
+                if (x0 < x1 && dy2 + knn_span_dx2(g, self, x1, x1) > lim) x1--;
+                if (dy2 + knn_span_dx2(g, self, x0, x1) > lim) continue;
+            }
+#endif
             const int a = __ldg(&g.cell_start[y * g.w + x0]);
             const int b = __ldg(&g.cell_start[y * g.w + x1 + 1]);
             for (int c = a; c < b; c++) k.consider(self, c, g);

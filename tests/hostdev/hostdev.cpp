@@ -11,10 +11,22 @@
 // finish_agent, integrate_agent, and ecmgpu.cu's append_path (block bounding boxes of the polylines).
 #include <vector>
 
+static long long g_hd_considered = 0;  // neighbour candidates visited (Knn::consider), see hd_considered()
+#define ECM_KNN_STATS (g_hd_considered++)
+
 #include "../../ecmgenerator_b200/csrc/device/locate.cuh"
 #include "../../ecmgenerator_b200/csrc/device/orca.cuh"
 
 using namespace ecm;
+
+// -DHD_SYNC: take the warp-synchronous instantiations the kernels use (kSync = true: warp-uniform trip counts,
+// flags instead of early returns).  With one thread per "warp" the collectives are identities, so this checks
+// the flattened control flow, not the lock-step itself.
+#ifdef HD_SYNC
+constexpr bool kHdSync = true;
+#else
+constexpr bool kHdSync = false;
+#endif
 
 namespace {
 
@@ -69,17 +81,18 @@ void* hd_world(int nV, const float* vert_xy, int nE, const int* edge_v, const fl
     return w;
 }
 void hd_world_free(void* h) { delete (HdWorld*)h; }
+long long hd_considered(int reset) { long long v = g_hd_considered; if (reset) g_hd_considered = 0; return v; }
 
 void hd_locate(void* h, int n, const float* xy, int* out_cell) {
     HdWorld* w = (HdWorld*)h;
-    for (int i = 0; i < n; i++) out_cell[i] = find_cell<false>(w->ecm, w->bins, V(xy[2 * i], xy[2 * i + 1]));
+    for (int i = 0; i < n; i++) out_cell[i] = find_cell<kHdSync>(w->ecm, w->bins, V(xy[2 * i], xy[2 * i + 1]));
 }
 
 void hd_retract(void* h, int n, const float* xy, unsigned char* ok, float* out_xy, int* out_edge) {  // k_retract
     HdWorld* w = (HdWorld*)h;
     for (int i = 0; i < n; i++) {
         v2 p = V(xy[2 * i], xy[2 * i + 1]), r = V(0.0f, 0.0f);
-        int c = find_cell<false>(w->ecm, w->bins, p);
+        int c = find_cell<kHdSync>(w->ecm, w->bins, p);
         bool good = c >= 0 && retract_in_cell(w->ecm, c, p, r);
         ok[i] = good ? 1 : 0;
         out_xy[2 * i] = r.x; out_xy[2 * i + 1] = r.y;
@@ -154,7 +167,7 @@ int hd_tick(void* h, int n, float step, float cell, int max_ring, float* pos_io,
         }
         v2 ap = V(0.0f, 0.0f);
         int cellid = -2;
-        const bool ok = find_attraction_point<false>(w->ecm, w->bins, P, poly.data(), boxes.data(), np, goal, ap, cellid, need_irm);
+        const bool ok = find_attraction_point<kHdSync>(w->ecm, w->bins, P, poly.data(), boxes.data(), np, goal, ap, cellid, need_irm);
         if (need_irm) {
             if (ok) { a = ap; have = true; }
             else { st |= 2u; if (cellid == -1) st |= 1u; replans.push_back(slot); }
@@ -184,7 +197,7 @@ int hd_tick(void* h, int n, float step, float cell, int max_ring, float* pos_io,
             for (int c = 0; c < n_act; c++) k.consider(s_pos[p], c, g);
         }
         const int n_nb = k.count();
-        OrcaResult r = orca_velocity<false, false>(w->obst, w->bins, g, s_pos[p], s_vel[p], s_rad[p], s_spd[p], s_pref[p], n_nb, k.q, step, true, none, p);
+        OrcaResult r = orca_velocity<kHdSync, false>(w->obst, w->bins, g, s_pos[p], s_vel[p], s_rad[p], s_spd[p], s_pref[p], n_nb, k.q, step, true, none, p);
         const v2 f = V(r.velocity.x - s_vel[p].x, r.velocity.y - s_vel[p].y);
         const float massRecip = 1.0f / 0.8f;
         const v2 nv = V(s_vel[p].x + f.x * massRecip * step, s_vel[p].y + f.y * massRecip * step);

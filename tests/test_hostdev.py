@@ -22,9 +22,16 @@ def _p(a, t):
     return a.ctypes.data_as(t)
 
 
-@pytest.fixture(scope="session")
-def hd():
-    so = os.path.join(HD, "_build", "libhostdev.so")
+# build variants of the device code that must ALL be bit-exact: the default build and the switches kept for A/B
+VARIANTS = {"default": [], "knn_prune": ["-DECM_KNN_PRUNE"], "knn_branchless": ["-DECM_KNN_BRANCHLESS"],
+            "knn_prune_branchless": ["-DECM_KNN_PRUNE", "-DECM_KNN_BRANCHLESS"],
+            # the warp-synchronous instantiations the kernels run (flattened control flow), one lane per "warp"
+            "sync": ["-DHD_SYNC"]}
+
+
+@pytest.fixture(scope="session", params=list(VARIANTS))
+def hd(request):
+    so = os.path.join(HD, "_build", f"libhostdev_{request.param}.so")
     src = os.path.join(HD, "hostdev.cpp")
     dev = os.path.join(ROOT, "ecmgenerator_b200", "csrc", "device")
     deps = [src] + [os.path.join(HD, "shim", f) for f in os.listdir(os.path.join(HD, "shim"))] + \
@@ -33,7 +40,7 @@ def hd():
         os.makedirs(os.path.dirname(so), exist_ok=True)
         # -ffp-contract=off == nvcc -fmad=false: IEEE mul / add without contraction; div / sqrt are IEEE on both sides
         subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HD, "shim"),
-                               "-o", so, src])
+                               "-o", so, src] + VARIANTS[request.param])
     L = C.CDLL(so)
     L.hd_world.restype = C.c_void_p
     L.hd_world.argtypes = [C.c_int, f32p, C.c_int, i32p, f32p, C.c_int, f32p, i32p, i32p, u8p]
@@ -43,6 +50,9 @@ def hd():
     L.hd_tick.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, f32p, f32p, f32p, f32p, f32p, f32p, f32p, u8p, i32p, f32p,
                           i32p, i32p, i32p, i32p, i32p, i32p, u32p]
     L.hd_neighbors.argtypes = [C.c_int, C.c_float, C.c_int, f32p, u8p, i32p, i32p]
+    L.hd_considered.restype = C.c_longlong
+    L.hd_considered.argtypes = [C.c_int]
+    L.variant = request.param
     return L
 
 
@@ -147,4 +157,51 @@ def test_device_point_location_and_retraction(hd, name):
     good = ok > 0
     assert np.array_equal(edge[good], g.z["probe/retract_edge"][good])
     assert_bits_equal(xy[good], g.z["probe/retract_xy"][good], "retracted points")
+    s.close()
+
+
+def _brute_knn(pos, active):
+    """The neighbour contract in numpy: float32 sqDist = fl(fl(dx*dx) + fl(dy*dy)), keep > 1e-4, 5 smallest by (sqDist, slot)."""
+    n = len(pos)
+    ids, cnt = np.full((n, 5), -1, np.int32), np.zeros(n, np.int32)
+    act = np.flatnonzero(active)
+    for i in act:
+        dx = (pos[act, 0] - pos[i, 0]).astype(np.float32)
+        dy = (pos[act, 1] - pos[i, 1]).astype(np.float32)
+        d = (dx * dx).astype(np.float32) + (dy * dy).astype(np.float32)
+        keep = d > np.float32(1e-4)
+        order = np.lexsort((act[keep], d[keep]))[:5]
+        ids[i, : len(order)] = act[keep][order]
+        cnt[i] = len(order)
+    return ids, cnt
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_device_knn_equals_brute_force_on_hostile_inputs(hd, seed):
+    """Clusters, exact ties (points on an integer lattice), duplicates, sparse outliers far outside the bulk, inactive
+    slots - for several grid cell sizes, including cells far smaller and far larger than the spacing."""
+    rng = np.random.default_rng(seed)
+    parts = [rng.integers(-6, 7, size=(300, 2)).astype(np.float32),                    # lattice: many exact ties and duplicates
+             rng.normal(0, 0.4, size=(200, 2)).astype(np.float32) + np.float32(20.0),    # a tight cluster
+             rng.uniform(-40, 40, size=(200, 2)).astype(np.float32),                     # background
+             np.array([[500.0, -300.0], [-800.0, 10.0], [0.0, 900.0]], np.float32)]       # far outliers: many empty rings
+    pos = np.ascontiguousarray(np.concatenate(parts))
+    n = len(pos)
+    active = (rng.uniform(size=n) > 0.1).astype(np.uint8)
+    want_ids, want_cnt = _brute_knn(pos, active)
+    for cell in (0.3, 1.0, 2.5, 9.0, 150.0):
+        ids, cnt = np.full((n, 5), -1, np.int32), np.zeros(n, np.int32)
+        hd.hd_neighbors(n, np.float32(cell), 8, _p(pos, f32p), _p(active, u8p), _p(ids, i32p), _p(cnt, i32p))
+        a = active > 0
+        assert np.array_equal(cnt[a], want_cnt[a]), f"counts, cell {cell}"
+        assert np.array_equal(ids[a], want_ids[a]), f"ids, cell {cell}"
+
+
+def test_report_candidates_visited(hd):
+    """Not a check: prints how many neighbour candidates the variant visits on the dense golden crowd."""
+    g = Golden("c2_small")
+    s = HostDevSim(hd, g, 1.7 / np.sqrt(g.n / 6000.0))
+    hd.hd_considered(1)
+    s.neighbors()
+    print(f"[{hd.variant}] candidates per agent: {hd.hd_considered(1) / g.n:.1f}")
     s.close()
