@@ -16,7 +16,9 @@ One JSON line on stdout (rank 0).  Workload at N=1: C3, 1M agents in the 2025-bl
   roofline     dominant kernel (by measured phase time) against the measured HBM copy bandwidth
   cpu_baseline the unmodified reference (oracle/_ref) on one host core, bounded sample
 
---impl reference times the reference's own CPU Simulator::Update (single-threaded, as shipped).
+--impl reference times the reference's own CPU Simulator::Update (single-threaded, as shipped) on a sample of the
+same workload sized to --cpu-budget seconds; `cpu_baseline.replica_farm` adds what one such process per host core
+delivers together (a labelled upper bound: the reference cannot spread ONE crowd over cores).
 """
 from __future__ import annotations
 
@@ -188,10 +190,8 @@ def measured_hbm_peak():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(w, c, off, pxy, sample_agents: int, ticks: int, warm: int):
-    """The reference's Simulator::Update on a window of the same workload, one host core."""
-    n = min(sample_agents, c.n)
-    # spatially compact sample: the n agents closest to the crowd's centroid keep the local density
+def _cpu_sample(w, c, off, pxy, n):
+    """Spatially compact sample: the n agents closest to the crowd's centroid keep the local density."""
     ctr = c.pos.mean(axis=0)
     idx = np.argsort(((c.pos - ctr) ** 2).sum(axis=1), kind="stable")[:n]
     idx.sort()
@@ -199,9 +199,14 @@ def cpu_reference_run(w, c, off, pxy, sample_agents: int, ticks: int, warm: int)
     sub_off = np.zeros(n + 1, np.int32)
     lens = (off[1:] - off[:-1])[idx]
     np.cumsum(lens, out=sub_off[1:])
-    sub_xy = _gather(pxy, off, idx)
+    return sub, sub_off, _gather(pxy, off, idx)
+
+
+def _cpu_run(w, sub, sub_off, sub_xy, ticks, warm):
+    """(seconds for `ticks` ticks, kind): the unmodified reference (oracle/_ref) if it was built, else the C port."""
     from oracle import pyref
 
+    n = sub.n
     with _silence_stdout():  # the reference prints banners and timing tables to stdout
         if pyref.available("ref-kdtree"):
             kind = "reference"
@@ -220,9 +225,41 @@ def cpu_reference_run(w, c, off, pxy, sample_agents: int, ticks: int, warm: int)
             sim.step(1)
         dt = time.perf_counter() - t0
         sim.close()
-    return {"value": n * ticks / dt, "unit": UNIT, "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
-            "sample": f"{n} agents nearest the crowd centroid of the same world ({w.n_cells} ECM cells, {w.n_obst_vertices} obstacle segments), "
-                      f"{ticks} ticks after {warm} warm-up", "ms_per_tick_sample": 1e3 * dt / ticks}
+    return dt, kind
+
+
+def _cpu_replica(args):
+    return _cpu_run(*args)[0]
+
+
+def cpu_reference_run(w, c, off, pxy, sample_agents: int, ticks: int, warm: int, budget_s: float | None = None, replicas: int = 0):
+    """The reference's Simulator::Update on a window of the same workload, one host core (it has no threading).
+
+    budget_s: shrink the sample so that warm + ticks ticks take about that long (the reference scans all ECM cells
+    and all obstacle segments per agent: its cost per agent-update is flat in the sample size).
+    replicas > 0: additionally run that many independent copies of the same sample side by side, one per core -
+    what a farm of reference processes would deliver on this box (labelled upper bound)."""
+    n = min(sample_agents, c.n)
+    if budget_s is not None:
+        probe = _cpu_sample(w, c, off, pxy, min(256, n))
+        per_agent = _cpu_run(w, *probe, 1, 0)[0] / probe[0].n
+        n = int(max(64, min(n, budget_s / ((ticks + warm) * per_agent))))
+    sub, sub_off, sub_xy = _cpu_sample(w, c, off, pxy, n)
+    dt, kind = _cpu_run(w, sub, sub_off, sub_xy, ticks, warm)
+    res = {"value": n * ticks / dt, "unit": UNIT, "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
+           "sample": f"{n} agents nearest the crowd centroid of the same world ({w.n_cells} ECM cells, {w.n_obst_vertices} obstacle segments), "
+                     f"{ticks} ticks after {warm} warm-up", "ms_per_tick_sample": 1e3 * dt / ticks}
+    if replicas > 1:
+        import multiprocessing as mp
+
+        with mp.get_context("fork").Pool(replicas) as pool:  # no CUDA context in this process (reference arm only)
+            t0 = time.perf_counter()
+            dts = pool.map(_cpu_replica, [(w, sub, sub_off, sub_xy, ticks, warm)] * replicas)
+            wall = time.perf_counter() - t0
+        res["replica_farm"] = {"replicas": replicas, "value": replicas * n * ticks / max(dts), "unit": UNIT, "wall_s": wall,
+                               "note": "independent single-threaded copies of the sample, one per core: an upper bound for this box, "
+                                       "not something the reference can do for ONE crowd"}
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
@@ -231,7 +268,9 @@ def run_reference_arm(args):
     if rank != 0:
         return
     w, c, off, pxy = build_workload(args.config, args.agents)
-    res = cpu_reference_run(w, c, off, pxy, args.cpu_sample, max(1, args.steps), max(0, min(args.warmup, 2)))
+    # sized so that the whole run stays near a minute whatever --steps asks for; then the same once more on every core
+    res = cpu_reference_run(w, c, off, pxy, args.cpu_sample, max(1, args.steps), max(0, min(args.warmup, 2)), budget_s=args.cpu_budget,
+                            replicas=os.cpu_count() or 1)
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": res["ms_per_tick_sample"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
@@ -510,6 +549,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--cpu-budget", type=float, default=45.0, help="--impl reference: seconds of CPU time the timed sample may take")
     ap.add_argument("--steady-tick", type=int, default=600, help="also time K ticks from this tick on (0 = skip)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3_1m", choices=sorted(S.CONFIGS))
