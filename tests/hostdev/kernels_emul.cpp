@@ -1,0 +1,288 @@
+// TEST INFRASTRUCTURE - not part of the product, never linked into it.
+//
+// The KERNELS of csrc/device/tick.cuh and csrc/device/strips.cuh compiled for the host and "launched" as plain
+// loops with ONE thread per block (blockIdx.x walks the grid; a one-lane warp makes every warp collective an
+// identity).  The sequence of launches is that of ecmgpu_update_phase (csrc/ecmgpu.cu): pack -> exchange ->
+// adopt migrants -> bin count (+ ghosts) -> scan -> scatter (+ ghosts) -> k_attract -> k_orca -> k_fallback,
+// with the in-process transport's message copy between strips.  What this adds to hostdev.cpp (which calls the
+// device FUNCTIONS): the kernels' own glue - snapshot rows, ghosts, ownership hand-over, the LP3D queue and
+// its finisher, the event lists, the record compaction of ecmgpu_update_io_owned - checked on the CPU, bit for
+// bit, against the reference's golden trajectories and against the un-stripped run (tests/test_hostdev_kernels.py).
+// Not emulated: the three scan kernels (a host prefix sum stands in) and the warp-per-agent half of k_fallback
+// (needs 32 co-operating lanes; the scenes used never exhaust the ring budget, which the harness asserts).
+#include <vector>
+
+#include "../../ecmgenerator_b200/csrc/device/strips.cuh"
+
+using namespace ecm;
+
+namespace {
+
+template <class F>
+void launch(int threads, F&& body) {
+    gridDim.x = threads; blockDim.x = 1; threadIdx.x = 0;
+    for (int b = 0; b < threads; b++) { blockIdx.x = b; body(); }
+    blockIdx.x = 0; gridDim.x = 1;
+}
+
+struct Emu {
+    // world (one bin over everything, like hostdev.cpp)
+    std::vector<float2> vert_xy, edge_cl, obst_xy, obst_dir;
+    std::vector<int2> edge_v;
+    std::vector<int> obst_next, obst_prev, cell_items, obst_items, bin_cell_start, bin_obst_start;
+    std::vector<unsigned char> obst_convex;
+    // slots
+    int n = 0, n_slots = 0;
+    float step = 0;
+    std::vector<float2> pos, vel, prefvel, attraction, force;
+    std::vector<float> radius, speed;
+    std::vector<unsigned char> active, replan_pending;
+    std::vector<unsigned> status;
+    std::vector<int> cell, nbr, nbr_cnt;
+    std::vector<PathHdr> path_hdr;
+    std::vector<float2> path_pool;
+    std::vector<float4> path_bbox;
+    // grid + snapshot + scratch
+    float gx0 = 0, gy0 = 0, gcell = 1;
+    int gw = 1, gh = 1;
+    std::vector<int> key, rank, cell_count, s_slot, fb_list, ev_replan, ev_destroyed;
+    std::vector<float2> s_pos, s_vel, s_pref;
+    std::vector<float> s_rad, s_spd;
+    std::vector<unsigned char> s_alive, s_ghost;
+    std::vector<unsigned long long> counters;
+    std::vector<int4> lp3d_hdr;
+    std::vector<float4> lp3d_out, lp3d_cs;
+    // strips
+    bool strips = false;
+    int rank_id = 0, n_ranks = 1, cap_halo = 0, cap_migr = 0, cap_self = 0;
+    float lo = 0, hi = 0, halo = 0;
+    std::vector<unsigned char> send[2], recv[2];
+    std::vector<HaloEntry> self_ghost;
+    std::vector<int> self_ghost_n, g_key, g_rank;
+
+    TickView view() {
+        TickView t;
+        memset(&t, 0, sizeof(t));
+        t.ecm = EcmView{(int)vert_xy.size(), (int)edge_v.size(), vert_xy.data(), edge_v.data(), edge_cl.data()};
+        t.obst = ObstView{(int)obst_xy.size(), obst_xy.data(), obst_next.data(), obst_prev.data(), obst_convex.data(), obst_dir.data()};
+        t.bins.x0 = -1.0e9f; t.bins.y0 = -1.0e9f; t.bins.inv_bin = 1.0e-12f; t.bins.w = 1; t.bins.h = 1;
+        t.bins.cell_start = bin_cell_start.data(); t.bins.cell_items = cell_items.data();
+        t.bins.obst_start = bin_obst_start.data(); t.bins.obst_items = obst_items.data();
+        t.grid.x0 = gx0; t.grid.y0 = gy0; t.grid.cell = gcell; t.grid.inv_cell = 1.0f / gcell; t.grid.w = gw; t.grid.h = gh;
+        t.grid.n_sorted = 0; t.grid.cell_start = cell_count.data();
+        t.grid.s_pos = s_pos.data(); t.grid.s_vel = s_vel.data(); t.grid.s_rad = s_rad.data(); t.grid.s_slot = s_slot.data();
+        t.ag.pos = pos.data(); t.ag.vel = vel.data(); t.ag.prefvel = prefvel.data(); t.ag.attraction = attraction.data();
+        t.ag.force = force.data(); t.ag.radius = radius.data(); t.ag.speed = speed.data(); t.ag.active = active.data();
+        t.ag.replan_pending = replan_pending.data(); t.ag.status = status.data(); t.ag.cell = cell.data();
+        t.ag.nbr = nbr.data(); t.ag.nbr_cnt = nbr_cnt.data();
+        t.ag.path_hdr = path_hdr.data(); t.ag.path_pool = path_pool.data(); t.ag.path_bbox = path_bbox.data();
+        t.sc.key = key.data(); t.sc.rank = rank.data(); t.sc.cell_count = cell_count.data(); t.sc.block_sums = nullptr;
+        t.sc.s_pos = s_pos.data(); t.sc.s_vel = s_vel.data(); t.sc.s_rad = s_rad.data(); t.sc.s_spd = s_spd.data();
+        t.sc.s_slot = s_slot.data(); t.sc.s_pref = s_pref.data(); t.sc.s_alive = s_alive.data(); t.sc.s_ghost = s_ghost.data();
+        t.sc.fb_list = fb_list.data(); t.sc.ev_replan = ev_replan.data(); t.sc.ev_destroyed = ev_destroyed.data();
+        t.sc.counters = counters.data();
+        t.n_sorted_ptr = cell_count.data() + (size_t)gw * gh;
+        t.step = step; t.max_ring = 8; t.record_neighbors = 1; t.gather = 0;
+        t.strips = strips ? 1 : 0;
+        const float inf = CUDART_INF_F;
+        t.cover_lo = strips && rank_id > 0 ? lo - halo : -inf;
+        t.cover_hi = strips && rank_id < n_ranks - 1 ? hi + halo : inf;
+        t.lp3d.cap = n; t.lp3d.count = counters.data() + C_LP3D_N;
+        t.lp3d.hdr = lp3d_hdr.data(); t.lp3d.out = lp3d_out.data(); t.lp3d.cs = lp3d_cs.data();
+        return t;
+    }
+    StripView sview() {
+        StripView v;
+        memset(&v, 0, sizeof(v));
+        v.enabled = strips ? 1 : 0; v.rank = rank_id; v.n_ranks = n_ranks; v.lo = lo; v.hi = hi; v.halo = halo;
+        v.cap_halo = cap_halo; v.cap_migr = cap_migr; v.cap_self = cap_self;
+        for (int d = 0; d < 2; d++) { v.send[d] = send[d].data(); v.recv[d] = recv[d].data(); v.send_hdr[d] = (MsgHeader*)send[d].data(); }
+        v.self_ghost = self_ghost.data(); v.self_ghost_n = self_ghost_n.data(); v.g_key = g_key.data(); v.g_rank = g_rank.data();
+        return v;
+    }
+    void append_path(int slot, const float2* pts, int np) {  // ecmgpu.cu append_path
+        while (path_pool.size() % kPathBlock) path_pool.push_back(make_float2(0.0f, 0.0f));
+        const int off = (int)path_pool.size();
+        path_pool.insert(path_pool.end(), pts, pts + np);
+        const int nseg = np - 1, nblk = (nseg + kPathBlock - 1) / kPathBlock;
+        path_bbox.resize((size_t)off / kPathBlock + std::max(nblk, 1), make_float4(0, 0, 0, 0));
+        const float pad = 0.05f;
+        for (int b = 0; b < nblk; b++) {
+            float4 bb = make_float4(3e38f, 3e38f, -3e38f, -3e38f);
+            for (int i = b * kPathBlock; i <= std::min((b + 1) * kPathBlock, nseg); i++) {
+                bb.x = std::min(bb.x, pts[i].x); bb.y = std::min(bb.y, pts[i].y);
+                bb.z = std::max(bb.z, pts[i].x); bb.w = std::max(bb.w, pts[i].y);
+            }
+            bb.x -= pad; bb.y -= pad; bb.z += pad; bb.w += pad;
+            path_bbox[(size_t)off / kPathBlock + b] = bb;
+        }
+        path_hdr[slot] = PathHdr{off, np, pts[np - 1].x, pts[np - 1].y};
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+void* emu_create(int nV, const float* vert_xy, int nE, const int* edge_v, const float* edge_cl, int nO, const float* obst_xy,
+                 const int* obst_next, const int* obst_prev, const unsigned char* obst_convex, int max_agents, float step,
+                 float gx0, float gy0, float cell, int gw, int gh) {
+    Emu* e = new Emu;
+    e->vert_xy.resize(nV);
+    for (int i = 0; i < nV; i++) e->vert_xy[i] = make_float2(vert_xy[2 * i], vert_xy[2 * i + 1]);
+    e->edge_v.resize(nE);
+    e->edge_cl.resize(4 * (size_t)nE);
+    for (int i = 0; i < nE; i++) e->edge_v[i] = make_int2(edge_v[2 * i], edge_v[2 * i + 1]);
+    for (int i = 0; i < 4 * nE; i++) e->edge_cl[i] = make_float2(edge_cl[2 * i], edge_cl[2 * i + 1]);
+    e->obst_xy.resize(nO); e->obst_dir.resize(nO);
+    e->obst_next.assign(obst_next, obst_next + nO); e->obst_prev.assign(obst_prev, obst_prev + nO);
+    e->obst_convex.assign(obst_convex, obst_convex + nO);
+    for (int i = 0; i < nO; i++) e->obst_xy[i] = make_float2(obst_xy[2 * i], obst_xy[2 * i + 1]);
+    for (int i = 0; i < nO; i++) {
+        volatile float dx = obst_xy[2 * obst_next[i]] - obst_xy[2 * i], dy = obst_xy[2 * obst_next[i] + 1] - obst_xy[2 * i + 1];
+        volatile float xx = dx * dx, yy = dy * dy;
+        volatile float l = sqrtf(xx + yy);
+        e->obst_dir[i] = l == 0.0f ? make_float2(dx, dy) : make_float2(dx / l, dy / l);
+    }
+    for (int c = 0; c < 2 * nE; c++) e->cell_items.push_back(c);
+    for (int o = 0; o < nO; o++) e->obst_items.push_back(o);
+    e->bin_cell_start = {0, 2 * nE};
+    e->bin_obst_start = {0, nO};
+    const int n = max_agents;
+    e->n = n; e->step = step; e->gx0 = gx0; e->gy0 = gy0; e->gcell = cell; e->gw = gw; e->gh = gh;
+    e->pos.assign(n, make_float2(0, 0)); e->vel = e->prefvel = e->attraction = e->force = e->pos;
+    e->radius.assign(n, 0); e->speed.assign(n, 0); e->active.assign(n, 0); e->replan_pending.assign(n, 0);
+    e->status.assign(n, 0); e->cell.assign(n, -2); e->nbr.assign(5 * (size_t)n, -1); e->nbr_cnt.assign(n, 0);
+    e->path_hdr.assign(n, PathHdr{0, 0, 0.0f, 0.0f});
+    e->key.assign(n, -1); e->rank.assign(n, 0); e->cell_count.assign((size_t)gw * gh + 2, 0);
+    e->counters.assign(C_COUNT, 0ull);
+    e->ev_replan.assign(n, 0); e->ev_destroyed.assign(n, 0);
+    e->lp3d_hdr.resize(n); e->lp3d_out.resize(n); e->lp3d_cs.resize((size_t)n * kMaxCons);
+    const size_t cap = n;  // grows in emu_set_strips
+    e->s_pos.resize(cap); e->s_vel.resize(cap); e->s_pref.resize(cap); e->s_rad.resize(cap); e->s_spd.resize(cap);
+    e->s_slot.resize(cap); e->s_alive.resize(cap); e->s_ghost.assign(cap, 0); e->fb_list.resize(cap);
+    return e;
+}
+void emu_destroy(void* h) { delete (Emu*)h; }
+
+void emu_load(void* h, int n, const float* pos, const float* radius, const float* speed, const int* path_off, const float* path_xy) {
+    Emu* e = (Emu*)h;
+    for (int i = 0; i < n; i++) {
+        e->pos[i] = make_float2(pos[2 * i], pos[2 * i + 1]);
+        e->vel[i] = e->prefvel[i] = e->attraction[i] = e->force[i] = make_float2(0, 0);
+        e->radius[i] = radius[i]; e->speed[i] = speed[i]; e->active[i] = 1; e->replan_pending[i] = 0;
+        e->append_path(i, (const float2*)path_xy + path_off[i], path_off[i + 1] - path_off[i]);
+    }
+    e->n_slots = std::max(e->n_slots, n);
+}
+void emu_set_path(void* h, int slot, const float* xy, int np) {
+    Emu* e = (Emu*)h;
+    e->append_path(slot, (const float2*)xy, np);
+    e->replan_pending[slot] = 0;
+}
+void emu_destroy_agent(void* h, int slot) { ((Emu*)h)->active[slot] = 0; }
+
+// ecmgpu_comm_set_strips (fixed capacities given by the caller) + k_assign_owner
+void emu_set_strips(void* h, int rank, int n_ranks, float lo, float hi, float halo, int cap_halo, int cap_migr) {
+    Emu* e = (Emu*)h;
+    e->strips = true; e->rank_id = rank; e->n_ranks = n_ranks; e->lo = lo; e->hi = hi; e->halo = halo;
+    e->cap_halo = cap_halo; e->cap_migr = cap_migr; e->cap_self = 2 * cap_migr;
+    const size_t msg = strip_msg_bytes(cap_halo, cap_migr);
+    for (int d = 0; d < 2; d++) { e->send[d].assign(msg, 0); e->recv[d].assign(msg, 0); }
+    e->self_ghost.resize(e->cap_self); e->self_ghost_n.assign(1, 0);
+    const size_t ng = 2 * (size_t)cap_halo + e->cap_self;
+    e->g_key.assign(ng, -1); e->g_rank.assign(ng, 0);
+    const size_t cap = e->n + ng;
+    e->s_pos.resize(cap); e->s_vel.resize(cap); e->s_pref.resize(cap); e->s_rad.resize(cap); e->s_spd.resize(cap);
+    e->s_slot.resize(cap); e->s_alive.resize(cap); e->s_ghost.assign(cap, 0); e->fb_list.resize(cap);
+    TickView t = e->view();
+    StripView sv = e->sview();
+    launch(e->n_slots, [&] { k_assign_owner(e->n_slots, t.ag, sv); });
+}
+
+// phase 0: enqueue_pack
+void emu_pack(void* h) {
+    Emu* e = (Emu*)h;
+    if (!e->strips) return;
+    for (int d = 0; d < 2; d++) memset(e->send[d].data(), 0, sizeof(MsgHeader));
+    e->self_ghost_n[0] = 0;
+    TickView t = e->view();
+    StripView sv = e->sview();
+    launch(e->n_slots, [&] { k_pack(e->n_slots, t.ag, sv, e->counters.data()); });
+}
+// phase 1: enqueue_exchange with the in-process transport: my left neighbour's RIGHT message is my left inbox
+void emu_exchange(void* h, void* left, void* right) {
+    Emu* e = (Emu*)h;
+    if (!e->strips) return;
+    if (left) e->recv[0] = ((Emu*)left)->send[1];
+    if (right) e->recv[1] = ((Emu*)right)->send[0];
+    TickView t = e->view();
+    StripView sv = e->sview();
+    launch(std::max(e->cap_migr, 1), [&] { k_unpack_migrants(t.ag, sv); });
+}
+// phase 2: enqueue_grid_build + k_attract + k_orca + k_fallback.  Returns the number of ring-budget fallbacks (must be 0).
+int emu_tick(void* h) {
+    Emu* e = (Emu*)h;
+    TickView t = e->view();
+    StripView sv = e->sview();
+    GridParams gp{e->gx0, e->gy0, e->gcell, 1.0f / e->gcell, e->gw, e->gh};
+    std::fill(e->cell_count.begin(), e->cell_count.end(), 0);
+    e->counters[C_FALLBACK_N] = 0; e->counters[C_LP3D_N] = 0;
+    launch(e->n_slots, [&] { k_bin_count(e->n_slots, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data()); });
+    const int ng = 2 * e->cap_halo + e->cap_self;
+    if (e->strips) launch(ng, [&] { k_ghost_count(sv, gp, e->cell_count.data()); });
+    {   // k_scan_tiles / k_scan_sums / k_scan_add: exclusive scan in place, total behind the last cell
+        int run = 0;
+        for (size_t c = 0; c < (size_t)e->gw * e->gh + 1; c++) { int v = e->cell_count[c]; e->cell_count[c] = run; run += v; }
+    }
+    launch(e->n_slots, [&] { k_scatter(e->n_slots, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc, 0); });
+    if (e->strips) launch(ng, [&] { k_ghost_scatter(sv, e->cell_count.data(), t.ag, t.sc, e->s_ghost.data()); });
+    const int rows = e->n_slots + (e->strips ? ng : 0);
+    launch(rows, [&] { k_attract(t); });
+    launch(rows, [&] { k_orca(t); });
+    const int fb = (int)e->counters[C_FALLBACK_N];
+    if (fb == 0) launch(64, [&] { k_fallback(t, 0); });  // the parked LP3D agents (its warp-per-agent half needs real warps)
+    return fb;
+}
+
+void emu_read(void* h, float* pos, float* vel, float* pref, float* attr, float* force, unsigned char* active, int* nbr, int* nbr_cnt,
+              unsigned* status, int* cell) {
+    Emu* e = (Emu*)h;
+    const size_t n = e->n;
+    if (pos) memcpy(pos, e->pos.data(), 8 * n);
+    if (vel) memcpy(vel, e->vel.data(), 8 * n);
+    if (pref) memcpy(pref, e->prefvel.data(), 8 * n);
+    if (attr) memcpy(attr, e->attraction.data(), 8 * n);
+    if (force) memcpy(force, e->force.data(), 8 * n);
+    if (active) memcpy(active, e->active.data(), n);
+    if (nbr) memcpy(nbr, e->nbr.data(), 20 * n);
+    if (nbr_cnt) memcpy(nbr_cnt, e->nbr_cnt.data(), 4 * n);
+    if (status) memcpy(status, e->status.data(), 4 * n);
+    if (cell) memcpy(cell, e->cell.data(), 4 * n);
+}
+// counters: out[0..C_COUNT)
+void emu_counters(void* h, unsigned long long* out) { memcpy(out, ((Emu*)h)->counters.data(), sizeof(unsigned long long) * C_COUNT); }
+// ecmgpu_poll_events: replans / destroyed since the last poll, ascending slots
+void emu_poll(void* h, int* replans, int* n_replans, int* destroyed, int* n_destroyed) {
+    Emu* e = (Emu*)h;
+    const int nr = (int)e->counters[C_REPLAN_N], nd = (int)e->counters[C_DESTROYED_N];
+    std::copy(e->ev_replan.begin(), e->ev_replan.begin() + nr, replans);
+    std::copy(e->ev_destroyed.begin(), e->ev_destroyed.begin() + nd, destroyed);
+    std::sort(replans, replans + nr);
+    std::sort(destroyed, destroyed + nd);
+    *n_replans = nr; *n_destroyed = nd;
+    e->counters[C_REPLAN_N] = 0; e->counters[C_DESTROYED_N] = 0;
+}
+// ecmgpu_update_io_owned's two kernels
+int emu_collect_owned(void* h, AgentRec* out) {
+    Emu* e = (Emu*)h;
+    int count = 0;
+    launch(e->n_slots, [&] { k_collect_owned(e->n_slots, e->active.data(), e->pos.data(), e->vel.data(), out, &count); });
+    return count;
+}
+void emu_apply_records(void* h, int n, const AgentRec* rec) {
+    Emu* e = (Emu*)h;
+    launch(n, [&] { k_apply_records(n, rec, e->n, e->active.data(), e->pos.data(), e->vel.data()); });
+}
+
+}  // extern "C"

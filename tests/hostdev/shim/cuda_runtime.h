@@ -49,8 +49,10 @@ static inline void __nanosleep(unsigned) {}
 template <class T, class U>
 static inline T atomicAdd(T* p, U v) { T old = *p; *p = (T)(old + (T)v); return old; }
 
+// launch geometry: one thread per block (kernels_emul.cpp walks blockIdx.x over the grid)
 struct HdDim3 { int x, y, z; };
-static const HdDim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
+static HdDim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
+#define __shared__ static
 
 // RotateVector / the VO half angle use the C library's sinf / cosf (UtilityFunctions.cpp:233-242) and so does
 // the oracle: route the device code's single sincosf call to the same two functions
