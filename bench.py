@@ -515,6 +515,9 @@ def run_ours(args):
         import torch.distributed as dist
 
         global_active = sim.global_active()
+        # whole-job counters; zero halo misses = every owned agent's 5-NN ball stayed inside what its rank sees,
+        # i.e. the strips computed exactly what one GPU computes (DESIGN.md "Multi-GPU")
+        job_counters = sim.global_stats(("halo_misses", "knn_fallbacks", "obstacle_overflows", "lp3d_runs", "location_failures", "replans"))
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
@@ -533,6 +536,9 @@ def run_ours(args):
                        "static_bin": st1["static_bin"]},
             "gpu_launches": int(launches), "clocks": clk,
             "counters": {k: int(st1[k]) for k in ("knn_fallbacks", "obstacle_overflows", "lp3d_runs", "location_failures", "replans")}}
+    if world > 1:
+        line["counters"] = dict(job_counters, scope="all ranks, whole run")
+        line["config"]["halo_m"] = float(sim.halo)
     if roof:
         line["roofline"] = roof
     if e2e:
