@@ -33,72 +33,72 @@ bool Area::Intersects(const Point position) const {  // Area.h:66-74
 }
 
 Simulator::Simulator(const ecmb200::FlatWorld* world, ecmb200::PathPlanner* planner, int maxAgents, float simStepTime, int device)
-    : m_World(world), m_Planner(planner), m_Device(device), m_MaxNumEntities(maxAgents), m_SimStepTime(simStepTime) {
-    for (int i = maxAgents - 1; i >= 0; i--) m_freeEntitySpaces.push(i);  // Simulator.h:66-69
+    : world_(world), planner_(planner), device_(device), capacity_(maxAgents), tick_seconds_(simStepTime) {
+    for (int i = maxAgents - 1; i >= 0; i--) free_slots_.push(i);  // Simulator.h:66-69
 }
 
-Simulator::~Simulator() { ClearSimulator(); }
+Simulator::~Simulator() { ReleaseAll(); }
 
 void Simulator::Check(int rc, const char* what) {
     if (rc == ECMGPU_OK) return;
-    m_Error = std::string(what) + ": " + (m_Gpu ? ecmgpu_last_error(m_Gpu) : ecmgpu_last_error(nullptr));
-    throw std::runtime_error(m_Error);  // no CPU fallback: a GPU failure is fatal for the simulation
+    error_ = std::string(what) + ": " + (gpu_ ? ecmgpu_last_error(gpu_) : ecmgpu_last_error(nullptr));
+    throw std::runtime_error(error_);  // no CPU fallback: a GPU failure is fatal for the simulation
 }
 
 void Simulator::Initialize() {  // Simulator.cpp:21-60
-    const int n = m_MaxNumEntities;
-    m_LastEntityIdx = -1;
-    m_ActiveAgents = new bool[n]();
-    m_Positions = new PositionComponent[n]();
-    m_AttractionPoints = new PositionComponent[n]();
-    m_Velocities = new VelocityComponent[n]();
-    m_PreferredVelocities = new VelocityComponent[n]();
-    m_PreferredSpeed = new SpeedComponent[n]();
-    m_Clearances = new ClearanceComponent[n]();
-    m_Paths = new PathComponent[n];
+    const int n = capacity_;
+    last_slot_ = -1;
+    alive_ = new bool[n]();
+    xy_ = new PositionComponent[n]();
+    attraction_ = new PositionComponent[n]();
+    vel_ = new VelocityComponent[n]();
+    pref_vel_ = new VelocityComponent[n]();
+    pref_speed_ = new SpeedComponent[n]();
+    radius_ = new ClearanceComponent[n]();
+    routes_ = new PathComponent[n];
     for (int i = 0; i < n; i++) {
-        m_Paths[i].x = nullptr;
-        m_Paths[i].y = nullptr;
-        m_Paths[i].currentIndex = -1;
-        m_Paths[i].numPoints = 0;
+        routes_[i].x = nullptr;
+        routes_[i].y = nullptr;
+        routes_[i].currentIndex = -1;
+        routes_[i].numPoints = 0;
     }
     ecmgpu_params prm;
     memset(&prm, 0, sizeof(prm));
-    prm.device = m_Device;
+    prm.device = device_;
     prm.max_agents = n;
-    prm.step = m_SimStepTime;
+    prm.step = tick_seconds_;
     prm.record_neighbors = 0;
-    Check(ecmgpu_create(&prm, &m_Gpu), "ecmgpu_create");
-    const auto& e = m_World->ecm;
-    Check(ecmgpu_set_ecm(m_Gpu, m_World->bbox, e.num_vertices(), e.vert_xy.data(), e.vert_clear.data(), e.num_edges(),
+    Check(ecmgpu_create(&prm, &gpu_), "ecmgpu_create");
+    const auto& e = world_->ecm;
+    Check(ecmgpu_set_ecm(gpu_, world_->bbox, e.num_vertices(), e.vert_xy.data(), e.vert_clear.data(), e.num_edges(),
                          e.edge_v.data(), e.edge_cl.data()), "ecmgpu_set_ecm");
-    m_Obst = m_World->obst;
-    const auto& o = m_Obst;
-    Check(ecmgpu_set_obstacles(m_Gpu, o.num_vertices(), o.xy.data(), o.next.data(), o.prev.data(), o.convex.data()), "ecmgpu_set_obstacles");
+    obstacles_ = world_->obst;
+    const auto& o = obstacles_;
+    Check(ecmgpu_set_obstacles(gpu_, o.num_vertices(), o.xy.data(), o.next.data(), o.prev.data(), o.convex.data()), "ecmgpu_set_obstacles");
     printf("SIMULATOR: Data for %d agents was created.\n", n);
 }
 
-void Simulator::ClearSimulator() {  // Simulator.cpp:62-95
-    if (m_Paths) {
-        for (int i = 0; i < m_MaxNumEntities; i++) {
-            delete[] m_Paths[i].x;
-            delete[] m_Paths[i].y;
+void Simulator::ReleaseAll() {  // Simulator.cpp:62-95
+    if (routes_) {
+        for (int i = 0; i < capacity_; i++) {
+            delete[] routes_[i].x;
+            delete[] routes_[i].y;
         }
     }
-    delete[] m_Positions; delete[] m_AttractionPoints; delete[] m_Velocities; delete[] m_PreferredVelocities;
-    delete[] m_PreferredSpeed; delete[] m_Paths; delete[] m_ActiveAgents; delete[] m_Clearances;
-    m_Positions = m_AttractionPoints = nullptr;
-    m_Velocities = m_PreferredVelocities = nullptr;
-    m_PreferredSpeed = nullptr; m_Paths = nullptr; m_ActiveAgents = nullptr; m_Clearances = nullptr;
-    if (m_Gpu) {
-        ecmgpu_destroy(m_Gpu);
-        m_Gpu = nullptr;
+    delete[] xy_; delete[] attraction_; delete[] vel_; delete[] pref_vel_;
+    delete[] pref_speed_; delete[] routes_; delete[] alive_; delete[] radius_;
+    xy_ = attraction_ = nullptr;
+    vel_ = pref_vel_ = nullptr;
+    pref_speed_ = nullptr; routes_ = nullptr; alive_ = nullptr; radius_ = nullptr;
+    if (gpu_) {
+        ecmgpu_destroy(gpu_);
+        gpu_ = nullptr;
         printf("SIMULATOR: Data was destroyed.\n");
     }
 }
 
-void Simulator::SetPathComponent(int e, const std::vector<ecmb200::P2f>& path) {  // Simulator.cpp:114-123
-    PathComponent& pc = m_Paths[e];
+void Simulator::StoreRoute(int e, const std::vector<ecmb200::P2f>& path) {  // Simulator.cpp:114-123
+    PathComponent& pc = routes_[e];
     delete[] pc.x;
     delete[] pc.y;
     const int n = (int)path.size();
@@ -111,42 +111,42 @@ void Simulator::SetPathComponent(int e, const std::vector<ecmb200::P2f>& path) {
         pc.x[j] = xy[2 * j] = path[j].x;
         pc.y[j] = xy[2 * j + 1] = path[j].y;
     }
-    Check(ecmgpu_set_path(m_Gpu, e, xy.data(), n), "ecmgpu_set_path");
+    Check(ecmgpu_set_path(gpu_, e, xy.data(), n), "ecmgpu_set_path");
 }
 
 // Simulator::UpdatePath (Simulator.cpp:97-124).  A failed query keeps the previous path.
 void Simulator::UpdatePath(const Entity& e, const Point& location, const Point& goal) {
     std::vector<ecmb200::P2f> path;
-    const bool ok = m_Planner->FindPath(ecmb200::P2f{location.x, location.y}, ecmb200::P2f{goal.x, goal.y}, m_Clearances[e].clearance, path);
+    const bool ok = planner_->FindPath(ecmb200::P2f{location.x, location.y}, ecmb200::P2f{goal.x, goal.y}, radius_[e].clearance, path);
     if (!ok || path.size() < 2) {
-        if (m_Paths[e].numPoints >= 2) {  // re-arm the replan request instead of storing an unusable path
-            std::vector<ecmb200::P2f> old((size_t)m_Paths[e].numPoints);
-            for (int j = 0; j < m_Paths[e].numPoints; j++) old[j] = ecmb200::P2f{m_Paths[e].x[j], m_Paths[e].y[j]};
-            SetPathComponent(e, old);
+        if (routes_[e].numPoints >= 2) {  // re-arm the replan request instead of storing an unusable path
+            std::vector<ecmb200::P2f> old((size_t)routes_[e].numPoints);
+            for (int j = 0; j < routes_[e].numPoints; j++) old[j] = ecmb200::P2f{routes_[e].x[j], routes_[e].y[j]};
+            StoreRoute(e, old);
         }
         return;
     }
-    SetPathComponent(e, path);
+    StoreRoute(e, path);
 }
 
 int Simulator::SpawnAgent(const Point& start, const Point& goal, float clearance, float preferredSpeed) {  // Simulator.cpp:168-200
-    if (m_freeEntitySpaces.empty()) return -1;
+    if (free_slots_.empty()) return -1;
     if (!ValidSpawnLocation(start, clearance)) return -1;
     std::vector<ecmb200::P2f> path;
-    if (!m_Planner->FindPath(ecmb200::P2f{start.x, start.y}, ecmb200::P2f{goal.x, goal.y}, clearance, path) || path.size() < 2) return -1;
-    m_NumEntities++;
-    int idx = m_freeEntitySpaces.top();
-    m_freeEntitySpaces.pop();
-    m_LastEntityIdx = m_LastEntityIdx < idx ? idx : m_LastEntityIdx;
-    m_Positions[idx].x = start.x;
-    m_Positions[idx].y = start.y;
-    m_Clearances[idx].clearance = clearance;
-    m_PreferredSpeed[idx].speed = preferredSpeed;
-    m_ActiveAgents[idx] = true;
+    if (!planner_->FindPath(ecmb200::P2f{start.x, start.y}, ecmb200::P2f{goal.x, goal.y}, clearance, path) || path.size() < 2) return -1;
+    count_++;
+    int idx = free_slots_.top();
+    free_slots_.pop();
+    last_slot_ = last_slot_ < idx ? idx : last_slot_;
+    xy_[idx].x = start.x;
+    xy_[idx].y = start.y;
+    radius_[idx].clearance = clearance;
+    pref_speed_[idx].speed = preferredSpeed;
+    alive_[idx] = true;
     std::vector<float> xy(2 * path.size());
     for (size_t j = 0; j < path.size(); j++) { xy[2 * j] = path[j].x; xy[2 * j + 1] = path[j].y; }
-    Check(ecmgpu_spawn(m_Gpu, idx, start.x, start.y, clearance, preferredSpeed, xy.data(), (int)path.size()), "ecmgpu_spawn");
-    PathComponent& pc = m_Paths[idx];
+    Check(ecmgpu_spawn(gpu_, idx, start.x, start.y, clearance, preferredSpeed, xy.data(), (int)path.size()), "ecmgpu_spawn");
+    PathComponent& pc = routes_[idx];
     delete[] pc.x;
     delete[] pc.y;
     pc.numPoints = (int)path.size();
@@ -154,53 +154,53 @@ int Simulator::SpawnAgent(const Point& start, const Point& goal, float clearance
     pc.x = new float[path.size()];
     pc.y = new float[path.size()];
     for (size_t j = 0; j < path.size(); j++) { pc.x[j] = path[j].x; pc.y[j] = path[j].y; }
-    m_PreferredVelocities[idx].dx = m_PreferredVelocities[idx].dy = 0.0f;
-    m_Velocities[idx].dx = m_Velocities[idx].dy = 0.0f;
-    m_AttractionPoints[idx].x = m_AttractionPoints[idx].y = 0.0f;
-    m_NeighborsValid = false;
+    pref_vel_[idx].dx = pref_vel_[idx].dy = 0.0f;
+    vel_[idx].dx = vel_[idx].dy = 0.0f;
+    attraction_[idx].x = attraction_[idx].y = 0.0f;
+    nbr_valid_ = false;
     return idx;
 }
 
 void Simulator::DestroyAgent(int idx) {  // Simulator.cpp:202-208
-    m_NumEntities--;
-    m_ActiveAgents[idx] = false;
-    m_freeEntitySpaces.push(idx);
-    Check(ecmgpu_destroy_agent(m_Gpu, idx), "ecmgpu_destroy_agent");
-    m_NeighborsValid = false;
+    count_--;
+    alive_[idx] = false;
+    free_slots_.push(idx);
+    Check(ecmgpu_destroy_agent(gpu_, idx), "ecmgpu_destroy_agent");
+    nbr_valid_ = false;
 }
 
 void Simulator::AddPosition(Entity entity, float x, float y) {  // Simulator.h:87-90
-    m_Positions[entity].x = x;
-    m_Positions[entity].y = y;
-    Check(ecmgpu_write(m_Gpu, ECMGPU_POS, &m_Positions[entity], entity, 1), "ecmgpu_write");
-    m_NeighborsValid = false;
+    xy_[entity].x = x;
+    xy_[entity].y = y;
+    Check(ecmgpu_write(gpu_, ECMGPU_POS, &xy_[entity], entity, 1), "ecmgpu_write");
+    nbr_valid_ = false;
 }
 
 bool Simulator::ValidSpawnLocation(const Point& location, float clearance) const {  // Simulator.cpp:295-311
     float clearanceSquared = clearance * clearance;
-    for (int i = 0; i <= m_LastEntityIdx; i++) {
-        if (!m_ActiveAgents[i]) continue;
-        float dx = location.x - m_Positions[i].x, dy = location.y - m_Positions[i].y;
+    for (int i = 0; i <= last_slot_; i++) {
+        if (!alive_[i]) continue;
+        float dx = location.x - xy_[i].x, dy = location.y - xy_[i].y;
         float d = dx * dx + dy * dy;
         if (d < clearanceSquared) return false;
     }
     return true;
 }
 
-void Simulator::UpdateMaxAgentIndex() {  // Simulator.cpp:481-492
+void Simulator::TrimLastSlot() {  // Simulator.cpp:481-492
     int emptyCounter = 0;
-    for (int i = m_LastEntityIdx; i >= 0; i--) {
-        if (m_ActiveAgents[i]) break;
+    for (int i = last_slot_; i >= 0; i--) {
+        if (alive_[i]) break;
         emptyCounter++;
     }
-    m_LastEntityIdx = m_LastEntityIdx - emptyCounter;
+    last_slot_ = last_slot_ - emptyCounter;
 }
 
-void Simulator::UpdateSpawnAreas() {  // Simulator.cpp:494-536
-    for (auto iter = m_SpawnAreas.begin(); iter != m_SpawnAreas.end(); iter++) {
+void Simulator::RunSpawnAreas() {  // Simulator.cpp:494-536
+    for (auto iter = spawn_areas_.begin(); iter != spawn_areas_.end(); iter++) {
         SpawnArea& area = iter->second;
         for (int ga = 0; ga < (int)area.connectedGoalAreas.size(); ga++) {
-            area.timeSinceLastSpawn[ga] += m_SimStepTime;
+            area.timeSinceLastSpawn[ga] += tick_seconds_;
             int agentsToSpawn = area.timeSinceLastSpawn[ga] * area.spawnRate[ga];
             const int maxSpawnAttempts = 10;
             for (int i = 0; i < agentsToSpawn; i++) {
@@ -217,7 +217,7 @@ void Simulator::UpdateSpawnAreas() {  // Simulator.cpp:494-536
                     printf("Could not find a valid spawn position in the spawn area!\n");
                     continue;
                 }
-                Point goal = m_GoalAreas[area.connectedGoalAreas[ga]].GetRandomPositionInArea();
+                Point goal = goal_areas_[area.connectedGoalAreas[ga]].GetRandomPositionInArea();
                 SpawnAgent(start, goal, clearance, speed);
             }
             area.timeSinceLastSpawn[ga] -= (float)agentsToSpawn / area.spawnRate[ga];
@@ -226,52 +226,52 @@ void Simulator::UpdateSpawnAreas() {  // Simulator.cpp:494-536
 }
 
 void Simulator::Update(float /*dt*/) {  // Simulator.cpp:314-323
-    UpdateMaxAgentIndex();
-    UpdateSpawnAreas();
-    m_NeighborsValid = false;
-    if (m_LastEntityIdx < 0) return;
-    Check(ecmgpu_update(m_Gpu), "ecmgpu_update");
+    TrimLastSlot();
+    RunSpawnAreas();
+    nbr_valid_ = false;
+    if (last_slot_ < 0) return;
+    Check(ecmgpu_update(gpu_), "ecmgpu_update");
     // events of this tick: arrivals (Simulator.cpp:564-566) then replans (Simulator.cpp:581-587), in slot
     // order like the reference's loop; the mirrors still hold the PRE-tick positions the replans start from
-    const int count = m_LastEntityIdx + 1;
-    m_EventScratch.resize(2 * (size_t)count);
+    const int count = last_slot_ + 1;
+    event_scratch_.resize(2 * (size_t)count);
     int nr = 0, nd = 0;
-    Check(ecmgpu_poll_events(m_Gpu, m_EventScratch.data(), count, &nr, m_EventScratch.data() + count, count, &nd), "ecmgpu_poll_events");
+    Check(ecmgpu_poll_events(gpu_, event_scratch_.data(), count, &nr, event_scratch_.data() + count, count, &nd), "ecmgpu_poll_events");
     for (int k = 0; k < nd; k++) {
-        const int e = m_EventScratch[count + k];
-        m_NumEntities--;
-        m_ActiveAgents[e] = false;
-        m_freeEntitySpaces.push(e);
+        const int e = event_scratch_[count + k];
+        count_--;
+        alive_[e] = false;
+        free_slots_.push(e);
         // the reference assigns the goal as attraction point before destroying (Simulator.cpp:559-562)
-        m_AttractionPoints[e].x = m_Paths[e].x[m_Paths[e].numPoints - 1];
-        m_AttractionPoints[e].y = m_Paths[e].y[m_Paths[e].numPoints - 1];
+        attraction_[e].x = routes_[e].x[routes_[e].numPoints - 1];
+        attraction_[e].y = routes_[e].y[routes_[e].numPoints - 1];
     }
     for (int k = 0; k < nr; k++) {
-        const int e = m_EventScratch[k];
+        const int e = event_scratch_[k];
         printf("Recalculate path...\n");
-        Point cur(m_Positions[e].x, m_Positions[e].y);
-        Point goal(m_Paths[e].x[m_Paths[e].numPoints - 1], m_Paths[e].y[m_Paths[e].numPoints - 1]);
+        Point cur(xy_[e].x, xy_[e].y);
+        Point goal(routes_[e].x[routes_[e].numPoints - 1], routes_[e].y[routes_[e].numPoints - 1]);
         UpdatePath(e, cur, goal);
     }
     // refresh the mirrors the getters expose; destroyed agents keep their stale components (Appendix B.5)
     std::vector<PositionComponent> pos(count), att(count);
     std::vector<VelocityComponent> vel(count), pref(count);
-    Check(ecmgpu_read(m_Gpu, ECMGPU_POS, pos.data(), 0, count), "ecmgpu_read");
-    Check(ecmgpu_read(m_Gpu, ECMGPU_VEL, vel.data(), 0, count), "ecmgpu_read");
-    Check(ecmgpu_read(m_Gpu, ECMGPU_PREFVEL, pref.data(), 0, count), "ecmgpu_read");
-    Check(ecmgpu_read(m_Gpu, ECMGPU_ATTRACTION, att.data(), 0, count), "ecmgpu_read");
+    Check(ecmgpu_read(gpu_, ECMGPU_POS, pos.data(), 0, count), "ecmgpu_read");
+    Check(ecmgpu_read(gpu_, ECMGPU_VEL, vel.data(), 0, count), "ecmgpu_read");
+    Check(ecmgpu_read(gpu_, ECMGPU_PREFVEL, pref.data(), 0, count), "ecmgpu_read");
+    Check(ecmgpu_read(gpu_, ECMGPU_ATTRACTION, att.data(), 0, count), "ecmgpu_read");
     for (int i = 0; i < count; i++) {
-        if (!m_ActiveAgents[i]) continue;
-        m_Positions[i] = pos[i];
-        m_Velocities[i] = vel[i];
-        m_PreferredVelocities[i] = pref[i];
-        m_AttractionPoints[i] = att[i];
+        if (!alive_[i]) continue;
+        xy_[i] = pos[i];
+        vel_[i] = vel[i];
+        pref_vel_[i] = pref[i];
+        attraction_[i] = att[i];
     }
 }
 
 void Simulator::Reset() {  // Simulator.cpp:325-333
-    for (int i = 0; i <= m_LastEntityIdx; i++) {
-        if (!m_ActiveAgents[i]) continue;
+    for (int i = 0; i <= last_slot_; i++) {
+        if (!alive_[i]) continue;
         DestroyAgent(i);
     }
 }
@@ -280,53 +280,53 @@ int Simulator::AddSpawnArea(const Point& position, const Vec2& halfSize, const S
     SpawnArea sa;
     sa.HalfWidth = halfSize.x;
     sa.HalfHeight = halfSize.y;
-    if (ID == -1) { sa.ID = m_NextSpawnID; m_NextSpawnID++; }
+    if (ID == -1) { sa.ID = next_spawn_id_; next_spawn_id_++; }
     else sa.ID = ID;
     sa.Position = position;
     sa.spawnConfiguration = config;
-    m_SpawnAreas.emplace(sa.ID, sa);
+    spawn_areas_.emplace(sa.ID, sa);
     return sa.ID;
 }
 
 int Simulator::AddGoalArea(const Point& position, const Vec2& halfSize, int ID) {  // Simulator.cpp:362-381
     GoalArea ga;
-    if (ID == -1) { ga.ID = m_NextGoalID; m_NextGoalID++; }
+    if (ID == -1) { ga.ID = next_goal_id_; next_goal_id_++; }
     else ga.ID = ID;
     ga.Position = position;
     ga.HalfHeight = halfSize.y;
     ga.HalfWidth = halfSize.x;
-    m_GoalAreas.emplace(ga.ID, ga);
+    goal_areas_.emplace(ga.ID, ga);
     return ga.ID;
 }
 
 void Simulator::RemoveArea(SimAreaType areaType, int ID) {  // Simulator.cpp:416-426
-    if (areaType == SPAWN) m_SpawnAreas.erase(ID);
-    if (areaType == GOAL) m_GoalAreas.erase(ID);
+    if (areaType == SPAWN) spawn_areas_.erase(ID);
+    if (areaType == GOAL) goal_areas_.erase(ID);
 }
 
 void Simulator::ConnectSpawnGoalAreas(int spawnID, int goalID, float spawnRate) {  // Simulator.cpp:428-440
-    for (int ga : m_SpawnAreas[spawnID].connectedGoalAreas)
+    for (int ga : spawn_areas_[spawnID].connectedGoalAreas)
         if (ga == goalID) return;
-    SpawnArea& sa = m_SpawnAreas[spawnID];
+    SpawnArea& sa = spawn_areas_[spawnID];
     sa.connectedGoalAreas.push_back(goalID);
     sa.timeSinceLastSpawn.push_back(0.0f);
     sa.spawnRate.push_back(spawnRate);
 }
 
 void Simulator::DeconnectSpawnGoalAreas(int spawnID, int goalID) {  // Simulator.cpp:442-460
-    if (spawnID < 0 || spawnID >= (int)m_SpawnAreas.size()) return;
-    auto& v = m_SpawnAreas[spawnID].connectedGoalAreas;
+    if (spawnID < 0 || spawnID >= (int)spawn_areas_.size()) return;
+    auto& v = spawn_areas_[spawnID].connectedGoalAreas;
     for (size_t i = 0; i < v.size(); i++)
         if (v[i] == goalID) { v.erase(v.begin() + i); return; }
 }
 
 SpawnArea* Simulator::GetSpawnArea(int ID) {
-    auto it = m_SpawnAreas.find(ID);
-    return it != m_SpawnAreas.end() ? &it->second : nullptr;
+    auto it = spawn_areas_.find(ID);
+    return it != spawn_areas_.end() ? &it->second : nullptr;
 }
 GoalArea* Simulator::GetGoalArea(int ID) {
-    auto it = m_GoalAreas.find(ID);
-    return it != m_GoalAreas.end() ? &it->second : nullptr;
+    auto it = goal_areas_.find(ID);
+    return it != goal_areas_.end() ? &it->second : nullptr;
 }
 
 std::vector<int> Simulator::GetConnectedAreas(int sourceID, SimAreaType type) {  // Simulator.cpp:126-166
@@ -336,7 +336,7 @@ std::vector<int> Simulator::GetConnectedAreas(int sourceID, SimAreaType type) { 
     }
     std::vector<int> result;
     if (type == GOAL && GetGoalArea(sourceID)) {
-        for (auto& kv : m_SpawnAreas)
+        for (auto& kv : spawn_areas_)
             for (int g : kv.second.connectedGoalAreas)
                 if (g == sourceID) { result.push_back(kv.first); break; }
     }
@@ -348,15 +348,15 @@ void Simulator::FindNNearestNeighbors(const Entity& agent, int n, std::vector<En
         printf("ERROR: FindNNearestNeighbors() expects std::vector<Entity>& outNeighbors to be of size n (= 5).\n");
         return;
     }
-    if (!m_NeighborsValid) {  // one device query serves every agent until the state changes
-        const int count = m_LastEntityIdx + 1;
-        m_NeighborIds.assign(5 * (size_t)std::max(count, 1), -1);
-        m_NeighborCounts.assign((size_t)std::max(count, 1), -1);
-        Check(ecmgpu_find_neighbors(m_Gpu, count, m_NeighborIds.data(), m_NeighborCounts.data()), "ecmgpu_find_neighbors");
-        m_NeighborsValid = true;
+    if (!nbr_valid_) {  // one device query serves every agent until the state changes
+        const int count = last_slot_ + 1;
+        nbr_ids_.assign(5 * (size_t)std::max(count, 1), -1);
+        nbr_counts_.assign((size_t)std::max(count, 1), -1);
+        Check(ecmgpu_find_neighbors(gpu_, count, nbr_ids_.data(), nbr_counts_.data()), "ecmgpu_find_neighbors");
+        nbr_valid_ = true;
     }
-    outNNeighbors = std::max(0, m_NeighborCounts[agent]);
-    for (int k = 0; k < 5; k++) outNeighbors[k] = m_NeighborIds[5 * (size_t)agent + k];
+    outNNeighbors = std::max(0, nbr_counts_[agent]);
+    for (int k = 0; k < 5; k++) outNeighbors[k] = nbr_ids_[5 * (size_t)agent + k];
     if (NN_TO_DRAW == agent) NEAREST_NEIGHBORS = outNeighbors;
 }
 
@@ -373,7 +373,7 @@ void KDTree::KNearestAgents(Simulator* simulation, int agent, int k, std::vector
 
 int Simulator::AddObstacleArea(const Point& position, const Vec2& halfSize, bool updateECM) {  // Simulator.cpp:383-412
     ObstacleArea oa;
-    oa.ID = m_ObstacleAreas.size() == 0 ? 0 : m_ObstacleAreas[m_ObstacleAreas.size() - 1].ID + 1;
+    oa.ID = obstacle_areas_.size() == 0 ? 0 : obstacle_areas_[obstacle_areas_.size() - 1].ID + 1;
     oa.Position = position;
     oa.HalfHeight = halfSize.y;
     oa.HalfWidth = halfSize.x;
@@ -384,16 +384,16 @@ int Simulator::AddObstacleArea(const Point& position, const Vec2& halfSize, bool
     // Environment::AddObstacle (Environment.cpp:198-229): the obstacle joins the list FindNearestObstacles scans
     float xy[8];
     for (int i = 0; i < 4; i++) { xy[2 * i] = oa.obstacleVerts[i].x; xy[2 * i + 1] = oa.obstacleVerts[i].y; }
-    ecmb200::AppendObstacle(m_Obst, xy, 4);
-    const auto& o = m_Obst;
-    Check(ecmgpu_set_obstacles(m_Gpu, o.num_vertices(), o.xy.data(), o.next.data(), o.prev.data(), o.convex.data()), "ecmgpu_set_obstacles");
-    if (updateECM) m_Error = "AddObstacleArea: updateECM needs the host-side ECM generator (not part of this library); the ECM and the planned paths are unchanged";
+    ecmb200::AppendObstacle(obstacles_, xy, 4);
+    const auto& o = obstacles_;
+    Check(ecmgpu_set_obstacles(gpu_, o.num_vertices(), o.xy.data(), o.next.data(), o.prev.data(), o.convex.data()), "ecmgpu_set_obstacles");
+    if (updateECM) error_ = "AddObstacleArea: updateECM needs the host-side ECM generator (not part of this library); the ECM and the planned paths are unchanged";
     return oa.ID;
 }
 
 void Simulator::FindNearestObstacles(const Entity& agent, float rangeSquared, std::vector<int>& outObstacles) const {
-    const auto& o = m_Obst;
-    const float ax = m_Positions[agent].x, ay = m_Positions[agent].y;
+    const auto& o = obstacles_;
+    const float ax = xy_[agent].x, ay = xy_[agent].y;
     auto approx = [](float px, float py, float qx, float qy) {
         const float E = 0.0001f;
         return px < (qx + E) && px > (qx - E) && py < (qy + E) && py > (qy - E);

@@ -22,60 +22,12 @@
 
 #include "../host/flat_world.h"
 #include "../host/planner.h"
+#include "sim_types.h"
 
 struct ecmgpu_sim;
 
 namespace ECM {
-
-struct Point {
-    float x = 0, y = 0;
-    Point() {}
-    Point(float x_, float y_) : x(x_), y(y_) {}
-};
-struct Vec2 {
-    float x = 0, y = 0;
-    Vec2() {}
-    Vec2(float x_, float y_) : x(x_), y(y_) {}
-};
-
 namespace Simulation {
-
-typedef int Entity;
-
-// component structs: identical layout to Simulator.h:29-57
-struct PositionComponent { float x; float y; };
-struct VelocityComponent { float dx; float dy; };
-struct ClearanceComponent { float clearance; };
-struct SpeedComponent { float speed; };
-struct PathComponent { int currentIndex; int numPoints; float* x; float* y; };
-
-enum SimAreaType { NONE, WALKABLE, SPAWN, GOAL, OBSTACLE };  // Area.h:11-18
-
-struct Area {  // Area.h:31-75
-    int ID = 0;
-    Point Position;
-    float HalfHeight = 0;
-    float HalfWidth = 0;
-    SimAreaType Type = NONE;
-    Point GetRandomPositionInArea();
-    bool Intersects(const Point position) const;
-};
-struct GoalArea : public Area { GoalArea() { Type = GOAL; } };
-struct SpawnConfiguration {  // Area.h:82-88
-    float preferredSpeedMin = 5.0f, preferredSpeedMax = 10.0f, clearanceMin = 5.0f, clearanceMax = 10.0f;
-};
-struct SpawnArea : public Area {
-    SpawnArea() { Type = SPAWN; }
-    SpawnConfiguration spawnConfiguration;
-    std::vector<int> connectedGoalAreas;
-    std::vector<float> spawnRate;
-    std::vector<float> timeSinceLastSpawn;
-};
-
-struct ObstacleArea : public Area {  // Area.h:101-105
-    ObstacleArea() { Type = OBSTACLE; }
-    std::vector<Point> obstacleVerts;
-};
 
 class Simulator;
 
@@ -91,104 +43,105 @@ public:
 
 class Simulator {
 public:
-    // `world` and `planner` are borrowed, like ECM* / ECMPathPlanner* / Environment* in the reference.
-    Simulator(const ecmb200::FlatWorld* world, ecmb200::PathPlanner* planner, int maxAgents, float simStepTime, int device = 0);
-    ~Simulator();
-
-    int SpawnAgent(const Point& start, const Point& goal, float clearance, float preferredSpeed);
-    void DestroyAgent(int idx);
-
-    void Initialize();      // allocates host mirrors and the GPU simulator; throws std::runtime_error without a CUDA device
-    void Update(float dt);  // dt is ignored, the constructor's step is used (Simulator.cpp:314-323)
-    void Reset();
-
-    void AddPosition(Entity entity, float x, float y);
-
-    int AddSpawnArea(const Point& position, const Vec2& halfSize, const SpawnConfiguration& config, int ID = -1);
-    int AddGoalArea(const Point& position, const Vec2& halfSize, int ID = -1);
-    // Simulator.cpp:383-412: a box obstacle for FindNearestObstacles / ORCA.  Like the reference the area itself is
-    // not recorded (GetObstacleAreas() stays empty, the returned ID is 0) and paths are not replanned; updateECM = true
-    // would need the host-side ECM generator (out of scope here): the obstacle is added, LastError() says so.
-    int AddObstacleArea(const Point& position, const Vec2& halfSize, bool updateECM = false);
-    std::vector<ObstacleArea>& GetObstacleAreas() { return m_ObstacleAreas; }
-    void RemoveArea(SimAreaType areaType, int ID);
-    void ConnectSpawnGoalAreas(int spawnID, int goalID, float spawnRate = 0.0f);
-    void DeconnectSpawnGoalAreas(int spawnID, int goalID);
-    std::map<int, SpawnArea>& GetSpawnAreas() { return m_SpawnAreas; }
-    std::map<int, GoalArea>& GetGoalAreas() { return m_GoalAreas; }
-    SpawnArea* GetSpawnArea(int ID);
-    GoalArea* GetGoalArea(int ID);
-    std::vector<int> GetConnectedAreas(int sourceID, SimAreaType type);
-
-    // exact 5-NN (DESIGN.md "Neighbour contract"); outNeighbors must have size n == 5
-    void FindNNearestNeighbors(const Entity& agent, int n, std::vector<Entity>& outNeighbors, int& outNNeighbors);
-    // the reference's unused brute-force variant (Simulator.cpp:228-257): same exact answer here, resizes outNeighbors
-    void FindNNearestNeighborsDeprecated(const Entity& agent, int n, std::vector<Entity>& outNeighbors, int& outNNeighbors);
-    // flat obstacle-vertex indices in (obstacle, vertex) order instead of ObstacleVertex*
-    void FindNearestObstacles(const Entity& agent, float rangeSquared, std::vector<int>& outObstacles) const;
-    bool ValidSpawnLocation(const Point& location, float clearance) const;
-    void UpdatePath(const Entity& e, const Point& location, const Point& goal);
-
-    // getters: raw pointers into host mirrors indexed by slot, refreshed by Update()
-    int GetNumAgents() const { return m_NumEntities; }
-    int GetLastIndex() const { return m_LastEntityIdx; }
-    PositionComponent* GetPositionData() const { return m_Positions; }
-    VelocityComponent* GetVelocityData() const { return m_Velocities; }
-    VelocityComponent* GetPreferredVelocityData() const { return m_PreferredVelocities; }
-    PathComponent* GetPathData() const { return m_Paths; }
-    ClearanceComponent* GetClearanceData() const { return m_Clearances; }
-    PositionComponent* GetAttractionPointData() const { return m_AttractionPoints; }
-    bool* GetActiveFlags() const { return m_ActiveAgents; }
-    ecmb200::PathPlanner* GetECMPathPlanner() { return m_Planner; }
-    KDTree* GetKDTree() const { return const_cast<KDTree*>(&m_KDTree); }
-    const ecmb200::FlatWorld* GetEnvironment() const { return m_World; }  // the flattened Environment + ECM
-    const ecmb200::FlatObstacles& GetObstacles() const { return m_Obst; } // world obstacles + AddObstacleArea boxes
-    float GetSimulationStepTime() const { return m_SimStepTime; }
-    const std::string& LastError() const { return m_Error; }
-    ecmgpu_sim* GetGpuHandle() const { return m_Gpu; }
-
+    // ---- what a frame loop reads: raw pointers into host mirrors indexed by slot, refreshed by Update()
+    PositionComponent* GetPositionData() const { return xy_; }
+    VelocityComponent* GetVelocityData() const { return vel_; }
+    VelocityComponent* GetPreferredVelocityData() const { return pref_vel_; }
+    PositionComponent* GetAttractionPointData() const { return attraction_; }
+    ClearanceComponent* GetClearanceData() const { return radius_; }
+    PathComponent* GetPathData() const { return routes_; }
+    bool* GetActiveFlags() const { return alive_; }
+    int GetNumAgents() const { return count_; }
+    int GetLastIndex() const { return last_slot_; }
+    float GetSimulationStepTime() const { return tick_seconds_; }
+    ecmb200::PathPlanner* GetECMPathPlanner() { return planner_; }
+    KDTree* GetKDTree() const { return const_cast<KDTree*>(&kdtree_); }
+    const ecmb200::FlatWorld* GetEnvironment() const { return world_; }        // the flattened Environment + ECM
+    const ecmb200::FlatObstacles& GetObstacles() const { return obstacles_; }  // world obstacles + AddObstacleArea boxes
+    ecmgpu_sim* GetGpuHandle() const { return gpu_; }
+    const std::string& LastError() const { return error_; }
+    // debug hooks of the reference's renderer (Simulator.h:131-132): the neighbours of agent NN_TO_DRAW, kept by the query
     int NN_TO_DRAW = 0;
     std::vector<int> NEAREST_NEIGHBORS;
 
+    // ---- life cycle.  `w` and `routePlanner` are borrowed, like ECM* / ECMPathPlanner* / Environment* in the reference
+    Simulator(const ecmb200::FlatWorld* w, ecmb200::PathPlanner* routePlanner, int maxAgents, float simStepTime, int device = 0);
+    ~Simulator();
+    void Initialize();           // host mirrors + the GPU simulator; throws std::runtime_error without a CUDA device
+    void Update(float ignored);  // the constructor's step is used, like the reference (Simulator.cpp:314-323)
+    void Reset();
+
+    // ---- agents
+    int SpawnAgent(const Point& from, const Point& to, float radius, float speed);
+    void DestroyAgent(int slot);
+    void UpdatePath(const Entity& slot, const Point& from, const Point& to);
+    void AddPosition(Entity slot, float x, float y);
+    bool ValidSpawnLocation(const Point& where, float radius) const;
+
+    // ---- queries on the current state
+    // exact 5-NN (DESIGN.md "Neighbour contract"); `out` must have size k == 5
+    void FindNNearestNeighbors(const Entity& slot, int k, std::vector<Entity>& out, int& found);
+    // the reference's unused brute-force variant (Simulator.cpp:228-257): same exact answer here, resizes `out`
+    void FindNNearestNeighborsDeprecated(const Entity& slot, int k, std::vector<Entity>& out, int& found);
+    // flat obstacle-vertex indices in (obstacle, vertex) order instead of ObstacleVertex*
+    void FindNearestObstacles(const Entity& slot, float rangeSquared, std::vector<int>& out) const;
+
+    // ---- areas (the editor's API, Command.cpp:33-159)
+    int AddSpawnArea(const Point& centre, const Vec2& halfExtent, const SpawnConfiguration& profile, int ID = -1);
+    int AddGoalArea(const Point& centre, const Vec2& halfExtent, int ID = -1);
+    // Simulator.cpp:383-412: a box obstacle for FindNearestObstacles / ORCA.  Like the reference the area itself is
+    // not recorded (GetObstacleAreas() stays empty, the returned ID is 0) and paths are not replanned; updateECM = true
+    // would need the host-side ECM generator (out of scope here): the obstacle is added, LastError() says so.
+    int AddObstacleArea(const Point& centre, const Vec2& halfExtent, bool updateECM = false);
+    void RemoveArea(SimAreaType kind, int ID);
+    void ConnectSpawnGoalAreas(int spawnID, int goalID, float agentsPerSecond = 0.0f);
+    void DeconnectSpawnGoalAreas(int spawnID, int goalID);
+    std::vector<int> GetConnectedAreas(int sourceID, SimAreaType kind);
+    SpawnArea* GetSpawnArea(int ID);
+    GoalArea* GetGoalArea(int ID);
+    std::map<int, SpawnArea>& GetSpawnAreas() { return spawn_areas_; }
+    std::map<int, GoalArea>& GetGoalAreas() { return goal_areas_; }
+    std::vector<ObstacleArea>& GetObstacleAreas() { return obstacle_areas_; }
+
 private:
-    void ClearSimulator();
-    void UpdateMaxAgentIndex();
-    void UpdateSpawnAreas();
-    void SetPathComponent(int e, const std::vector<ecmb200::P2f>& path);
+    void ReleaseAll();
+    void TrimLastSlot();
+    void RunSpawnAreas();
+    void StoreRoute(int slot, const std::vector<ecmb200::P2f>& polyline);
     void Check(int rc, const char* what);
 
-    const ecmb200::FlatWorld* m_World;
-    ecmb200::PathPlanner* m_Planner;
-    ecmgpu_sim* m_Gpu = nullptr;
-    int m_Device;
+    const ecmb200::FlatWorld* world_;
+    ecmb200::PathPlanner* planner_;
+    ecmgpu_sim* gpu_ = nullptr;
+    int device_;
 
-    int m_MaxNumEntities;
-    int m_NumEntities = 0;
-    std::stack<int> m_freeEntitySpaces;
-    bool* m_ActiveAgents = nullptr;
-    int m_LastEntityIdx = -1;
-    float m_SimStepTime;
+    int capacity_;
+    int count_ = 0;
+    std::stack<int> free_slots_;
+    bool* alive_ = nullptr;
+    int last_slot_ = -1;
+    float tick_seconds_;
 
-    std::map<int, SpawnArea> m_SpawnAreas;
-    std::map<int, GoalArea> m_GoalAreas;
-    std::vector<ObstacleArea> m_ObstacleAreas;
-    ecmb200::FlatObstacles m_Obst;  // what the GPU holds: the world's obstacles, then the boxes added at run time
-    KDTree m_KDTree;
-    int m_NextSpawnID = 0;
-    int m_NextGoalID = 0;
+    std::map<int, SpawnArea> spawn_areas_;
+    std::map<int, GoalArea> goal_areas_;
+    std::vector<ObstacleArea> obstacle_areas_;
+    ecmb200::FlatObstacles obstacles_;  // what the GPU holds: the world's obstacles, then the boxes added at run time
+    KDTree kdtree_;
+    int next_spawn_id_ = 0;
+    int next_goal_id_ = 0;
 
-    PositionComponent* m_Positions = nullptr;
-    PositionComponent* m_AttractionPoints = nullptr;
-    VelocityComponent* m_PreferredVelocities = nullptr;
-    VelocityComponent* m_Velocities = nullptr;
-    ClearanceComponent* m_Clearances = nullptr;
-    SpeedComponent* m_PreferredSpeed = nullptr;
-    PathComponent* m_Paths = nullptr;
+    PositionComponent* xy_ = nullptr;
+    PositionComponent* attraction_ = nullptr;
+    VelocityComponent* pref_vel_ = nullptr;
+    VelocityComponent* vel_ = nullptr;
+    ClearanceComponent* radius_ = nullptr;
+    SpeedComponent* pref_speed_ = nullptr;
+    PathComponent* routes_ = nullptr;
 
-    bool m_NeighborsValid = false;
-    std::vector<int> m_NeighborIds, m_NeighborCounts;
-    std::vector<int> m_EventScratch;
-    std::string m_Error;
+    bool nbr_valid_ = false;
+    std::vector<int> nbr_ids_, nbr_counts_;
+    std::vector<int> event_scratch_;
+    std::string error_;
 };
 
 }  // namespace Simulation
