@@ -70,3 +70,14 @@ def test_no_cpu_fallback_without_gpu():
     w = lattice_world([20, 20], [20, 20], 6.0)
     with pytest.raises(gpu.EcmGpuError, match="no CUDA device"):
         gpu.GpuSim(w, 16, 1 / 60)
+
+
+@pytest.mark.skipif(has_cuda(), reason="only meaningful without a CUDA device")
+def test_dropin_fails_loudly_without_gpu():
+    """libecmsim.so (the C++17 drop-in Simulator) loads, plans on the host, and refuses to run without a device."""
+    from ecmgenerator_b200 import dropin
+    from ecmgenerator_b200.host import lattice_world
+
+    w = lattice_world([20, 20], [20, 20], 6.0)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        dropin.Simulator(w, 16, 1 / 60)
