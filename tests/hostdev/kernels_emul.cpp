@@ -220,6 +220,17 @@ void emu_exchange(void* h, void* left, void* right) {
     StripView sv = e->sview();
     launch(std::max(e->cap_migr, 1), [&] { k_unpack_migrants(t.ag, sv); });
 }
+// The same exchange for strips that live in DIFFERENT processes (tests: torch.distributed / gloo carries the bytes
+// the way NCCL send/recv does on the GPUs): the outgoing message of direction d, the incoming one, then adopt.
+int emu_msg_bytes(void* h) { Emu* e = (Emu*)h; return (int)strip_msg_bytes(e->cap_halo, e->cap_migr); }
+void emu_get_send(void* h, int d, unsigned char* out) { Emu* e = (Emu*)h; memcpy(out, e->send[d].data(), e->send[d].size()); }
+void emu_set_recv(void* h, int d, const unsigned char* in) { Emu* e = (Emu*)h; memcpy(e->recv[d].data(), in, e->recv[d].size()); }
+void emu_adopt(void* h) {
+    Emu* e = (Emu*)h;
+    TickView t = e->view();
+    StripView sv = e->sview();
+    launch(std::max(e->cap_migr, 1), [&] { k_unpack_migrants(t.ag, sv); });
+}
 // phase 2: enqueue_grid_build + k_attract + k_orca + k_fallback.  Returns the number of ring-budget fallbacks (must be 0).
 int emu_tick(void* h) {
     Emu* e = (Emu*)h;

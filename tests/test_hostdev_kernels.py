@@ -28,6 +28,10 @@ def _p(a, t):
 
 @pytest.fixture(scope="session")
 def emu():
+    return load_emu()
+
+
+def load_emu():
     so = os.path.join(HD, "_build", "libkernels_emul.so")
     src = os.path.join(HD, "kernels_emul.cpp")
     dev = os.path.join(ROOT, "ecmgenerator_b200", "csrc", "device")
@@ -52,6 +56,10 @@ def emu():
     L.emu_read.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, u8p, i32p, i32p, u32p, i32p]
     L.emu_counters.argtypes = [vp, u64p]
     L.emu_poll.argtypes = [vp, i32p, i32p, i32p, i32p]
+    L.emu_msg_bytes.argtypes = [vp]
+    L.emu_get_send.argtypes = [vp, C.c_int, u8p]
+    L.emu_set_recv.argtypes = [vp, C.c_int, u8p]
+    L.emu_adopt.argtypes = [vp]
     L.emu_collect_owned.argtypes = [vp, vp]
     L.emu_apply_records.argtypes = [vp, C.c_int, vp]
     return L
@@ -239,3 +247,85 @@ def test_owned_record_kernels(emu):
     assert_bits_equal(st2["pos"][r["slot"], 0], st["pos"][r["slot"], 0] + np.float32(1.0), "applied x")
     assert st2["pos"][7, 0] == st["pos"][7, 0]
     d.close()
+
+
+def _gloo_strip_worker(rank, world, port, name, q):
+    """One strip per PROCESS: k_pack fills the fixed-size messages, gloo send / recv carries them to the neighbours
+    (what ncclSend / ncclRecv do between the GPUs), k_unpack_migrants adopts, then the tick."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    from tests.util import apply_events
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = load_emu()
+        g = Golden(name)
+        mode = "exact-knn"
+        bounds = M.strip_bounds(g.crowd.pos[:, 0], world)
+        widths = np.diff(bounds)
+        halo = float(min(2.0 * _r5_max(g) + 2.0, widths.max()))
+        d = EmuDevice(L, g, _cell_for(g))
+        lo = -np.inf if rank == 0 else bounds[rank]
+        hi = np.inf if rank == world - 1 else bounds[rank + 1]
+        L.emu_set_strips(d.h, rank, world, np.float32(lo), np.float32(hi), np.float32(halo), 512, 128)
+        nbytes = L.emu_msg_bytes(d.h)
+        ok, owned_max = True, 0
+        for t in range(g.ticks(mode)):
+            L.emu_pack(d.h)
+            ops, inbox = [], {}
+            for dr, peer in ((0, rank - 1), (1, rank + 1)):
+                if 0 <= peer < world:
+                    out = np.zeros(nbytes, np.uint8)
+                    L.emu_get_send(d.h, dr, _p(out, u8p))
+                    inbox[dr] = torch.zeros(nbytes, dtype=torch.uint8)
+                    ops += [dist.P2POp(dist.isend, torch.from_numpy(out), peer), dist.P2POp(dist.irecv, inbox[dr], peer)]
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            for dr, buf in inbox.items():
+                L.emu_set_recv(d.h, dr, _p(np.ascontiguousarray(buf.numpy()), u8p))
+            L.emu_adopt(d.h)
+            assert L.emu_tick(d.h) == 0
+            st = d.state()
+            mine = st["active"] > 0
+            owned_max = max(owned_max, int(mine.sum()))
+            # every rank checks its own agents against the golden trajectory; ownership is checked globally
+            ok &= bool(np.array_equal(st["pos"][mine].view(np.uint32), g.z[f"{mode}/pos"][t][mine].view(np.uint32)))
+            ok &= bool(np.array_equal(st["vel"][mine].view(np.uint32), g.z[f"{mode}/vel"][t][mine].view(np.uint32)))
+            owners = torch.from_numpy(mine.astype(np.int64))
+            dist.all_reduce(owners)
+            ok &= bool(np.array_equal(owners.numpy() > 0, g.z[f"{mode}/active"][t] > 0)) and int(owners.max()) <= 1
+            apply_events(d, g.events_at(mode, t))
+        own0 = M.owner_of(g.crowd.pos[:, 0], bounds) == rank
+        arrived = int((mine & ~own0).sum())
+        q.put((rank, ok, int(d.counters()[C_TOTAL_HALO_MISS]), arrived, owned_max))
+        d.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["jam_small"])
+def test_two_process_strips_over_gloo_equal_the_reference_bitwise(emu, name):
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_strip_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    print(res)
+    for rank, ok, misses, arrived, owned_max in res:
+        assert ok, f"rank {rank}: trajectory or ownership differs from the reference"
+        assert misses == 0
+        assert owned_max < Golden(name).n, "each rank works on its share only"
+    assert sum(r[3] for r in res) >= 1, "agents must have migrated between the processes"
