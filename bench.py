@@ -270,7 +270,7 @@ def run_reference_arm(args):
     w, c, off, pxy = build_workload(args.config, args.agents)
     # sized so that the whole run stays near a minute whatever --steps asks for; then the same once more on every core
     res = cpu_reference_run(w, c, off, pxy, args.cpu_sample, max(1, args.steps), max(0, min(args.warmup, 2)), budget_s=args.cpu_budget,
-                            replicas=os.cpu_count() or 1)
+                            replicas=min(os.cpu_count() or 1, 128))
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": res["ms_per_tick_sample"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
