@@ -111,7 +111,14 @@ __device__ __forceinline__ float knn_row_dy2(const GridView& g, v2 self, int y) 
 }
 #endif
 
+#ifdef ECM_KNN_TWOPASS
+__device__ __forceinline__ bool knn_grid_twopass(Knn& k, v2 self, const GridView& g, int max_ring);
+#endif
+
 __device__ __forceinline__ bool knn_grid(Knn& k, v2 self, const GridView& g, int max_ring) {
+#ifdef ECM_KNN_TWOPASS
+    return knn_grid_twopass(k, self, g, max_ring);
+#endif
     int cx, cy;
     g.cell_of(self, cx, cy);
     k.init();
@@ -169,6 +176,125 @@ __device__ __forceinline__ bool knn_grid(Knn& k, v2 self, const GridView& g, int
     }
     return false;
 }
+
+#ifdef ECM_KNN_TWOPASS
+// Two-pass variant of knn_grid (same contract, same result).  While the rings expand only the five smallest
+// DISTANCES are tracked - a branch-free min / max chain, every lane busy on every candidate; once the 5th distance
+// is proven minimal one more sweep over the scanned block collects the candidates with dd <= d5 (normally exactly
+// five) and orders them by (distance, slot id).  More than five means exact ties at d5: the ordered insert decides.
+__device__ __forceinline__ bool knn_grid_twopass(Knn& k, v2 self, const GridView& g, int max_ring) {
+    int cx, cy;
+    g.cell_of(self, cx, cy);
+    float t0 = CUDART_INF_F, t1 = t0, t2 = t0, t3 = t0, t4 = t0;
+    int r = 1;
+    bool done = false;
+    for (; r <= max_ring; r++) {
+        const int xa = max(cx - r, 0), xb = min(cx + r, g.w - 1);
+        const int ya = max(cy - r, 0), yb = min(cy + r, g.h - 1);
+        const int pieces = r == 1 ? 3 : 2 + 2 * (2 * r - 1);
+        for (int s = 0; s < pieces; s++) {
+            int y, x0, x1;
+            if (r == 1) { y = s == 0 ? cy : (s == 1 ? cy - 1 : cy + 1); x0 = xa; x1 = xb; }
+            else if (s < 2) { y = s == 0 ? cy - r : cy + r; x0 = xa; x1 = xb; }
+            else { y = cy - r + 1 + ((s - 2) >> 1); x0 = x1 = ((s - 2) & 1) ? cx + r : cx - r; }
+            if (y < 0 || y >= g.h || x0 < 0 || x1 >= g.w) continue;
+#ifdef ECM_KNN_PRUNE
+            if (t4 < CUDART_INF_F) {  // same pruning as knn_grid: cells beyond the current 5th distance cannot contribute
+                const float lim = t4 * 1.001f;
+                const float dy2 = knn_row_dy2(g, self, y);
+                if (x0 < x1 && dy2 + knn_span_dx2(g, self, x0, x0) > lim) x0++;
+                if (x0 < x1 && dy2 + knn_span_dx2(g, self, x1, x1) > lim) x1--;
+                if (dy2 + knn_span_dx2(g, self, x0, x1) > lim) continue;
+            }
+#endif
+            const int a = __ldg(&g.cell_start[y * g.w + x0]);
+            const int b = __ldg(&g.cell_start[y * g.w + x1 + 1]);
+            for (int c = a; c < b; c++) {
+#ifdef ECM_KNN_STATS
+                ECM_KNN_STATS;
+#endif
+                const v2 pj = __ldg(&g.s_pos[c]);
+                const float dx = pj.x - self.x, dy = pj.y - self.y;
+                float dd = dx * dx + dy * dy;
+                dd = dd > kEpsilon ? dd : CUDART_INF_F;
+                float lo;
+                lo = fminf(t0, dd); dd = fmaxf(t0, dd); t0 = lo;
+                lo = fminf(t1, dd); dd = fmaxf(t1, dd); t1 = lo;
+                lo = fminf(t2, dd); dd = fmaxf(t2, dd); t2 = lo;
+                lo = fminf(t3, dd); dd = fmaxf(t3, dd); t3 = lo;
+                t4 = fminf(t4, dd);
+            }
+        }
+        float cover = CUDART_INF_F;
+        if (xa > 0) cover = fminf(cover, self.x - (g.x0 + (float)xa * g.cell));
+        if (xb < g.w - 1) cover = fminf(cover, (g.x0 + (float)(xb + 1) * g.cell) - self.x);
+        if (ya > 0) cover = fminf(cover, self.y - (g.y0 + (float)ya * g.cell));
+        if (yb < g.h - 1) cover = fminf(cover, (g.y0 + (float)(yb + 1) * g.cell) - self.y);
+        if (cover == CUDART_INF_F) { done = true; break; }
+        if (t4 < CUDART_INF_F && cover > 0.0f && t4 < cover * cover * 0.999f) { done = true; break; }
+    }
+    if (!done) return false;
+    // collecting sweep over the scanned block, row by row (each row is one contiguous range of the snapshot)
+    k.init();
+    const int xa = max(cx - r, 0), xb = min(cx + r, g.w - 1);
+    const int ya = max(cy - r, 0), yb = min(cy + r, g.h - 1);
+    int cnt = 0;
+    bool overflow = false;
+    for (int y = ya; y <= yb; y++) {
+        int x0 = xa, x1 = xb;
+#ifdef ECM_KNN_PRUNE
+        {   // only cells that reach into the final ball can hold a result
+            const float lim = t4 * 1.001f;
+            const float dy2 = knn_row_dy2(g, self, y);
+            if (dy2 > lim) continue;
+            while (x0 < x1 && dy2 + knn_span_dx2(g, self, x0, x0) > lim) x0++;
+            while (x0 < x1 && dy2 + knn_span_dx2(g, self, x1, x1) > lim) x1--;
+        }
+#endif
+        const int a = __ldg(&g.cell_start[y * g.w + x0]);
+        const int b = __ldg(&g.cell_start[y * g.w + x1 + 1]);
+        for (int c = a; c < b; c++) {
+            const v2 pj = __ldg(&g.s_pos[c]);
+            const float dx = pj.x - self.x, dy = pj.y - self.y;
+            const float dd = dx * dx + dy * dy;
+            if (dd > kEpsilon && dd <= t4) {
+                if (cnt < kK) {  // newest first; ordered below
+                    k.d[4] = k.d[3]; k.q[4] = k.q[3]; k.d[3] = k.d[2]; k.q[3] = k.q[2];
+                    k.d[2] = k.d[1]; k.q[2] = k.q[1]; k.d[1] = k.d[0]; k.q[1] = k.q[0];
+                    k.d[0] = dd; k.q[0] = c;
+                } else overflow = true;
+                cnt++;
+            }
+        }
+    }
+    if (overflow) {  // exact ties at the 5th distance: the slot id decides, in the ordered insert
+        k.init();
+        for (int y = ya; y <= yb; y++) {
+            const int a = __ldg(&g.cell_start[y * g.w + xa]);
+            const int b = __ldg(&g.cell_start[y * g.w + xb + 1]);
+            for (int c = a; c < b; c++) {
+                const v2 pj = __ldg(&g.s_pos[c]);
+                const float dx = pj.x - self.x, dy = pj.y - self.y;
+                const float dd = dx * dx + dy * dy;
+                if (dd > kEpsilon && dd <= k.d[kK - 1]) k.insert(dd, c, g.s_slot);
+            }
+        }
+        return true;
+    }
+    // insertion sort of the <= 5 collected entries by (distance, slot id); empty places hold (+inf, -1) and stay last
+    for (int i = 1; i < kK; i++) {
+        for (int j = i; j > 0; j--) {
+            const bool swap = k.q[j] >= 0 && (k.q[j - 1] < 0 || k.d[j] < k.d[j - 1] ||
+                                              (k.d[j] == k.d[j - 1] && __ldg(&g.s_slot[k.q[j]]) < __ldg(&g.s_slot[k.q[j - 1]])));
+            if (swap) {
+                const float td = k.d[j]; k.d[j] = k.d[j - 1]; k.d[j - 1] = td;
+                const int tq = k.q[j]; k.q[j] = k.q[j - 1]; k.q[j - 1] = tq;
+            }
+        }
+    }
+    return true;
+}
+#endif
 
 // Exhaustive variant, one WARP per agent: every lane scans a stride of the snapshot, then the 32
 // partial lists are merged through shuffles.  All lanes return the same result.
