@@ -32,6 +32,7 @@ enum Counter {
     C_TOTAL_LOCFAIL = 7,
     C_TOTAL_REPLAN = 8,
     C_TOTAL_HALO_MISS = 9,
+    C_TOTAL_KD_TIES = 10,  // kdtree.cuh: tree segments whose median tied on the split axis
     C_COUNT = 16
 };
 

@@ -20,6 +20,9 @@
 #include <dlfcn.h>
 
 #include "device/strips.cuh"
+#include "device/kdtree.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
 
 using namespace ecm;
 
@@ -121,6 +124,16 @@ struct ecmgpu_sim {
     unsigned cur_gen = 0;    // inbox generation of the exchange in flight / last completed (fixed at pack time)
     DevBuf<HaloEntry> d_self_ghost;
     DevBuf<int> d_self_ghost_n, d_g_key, d_g_rank;
+
+    // ---- faithful KD-tree neighbour mode (device/kdtree.cuh), allocated when the mode is first selected
+    int neighbor_mode = ECMGPU_NEIGHBORS_EXACT;
+    DevBuf<unsigned long long> d_kd_keys[2];
+    DevBuf<int> d_kd_vals[2], d_kd_seg_r[2], d_kd_seg_node[2], d_kd_raw, d_kd_raw_cnt, d_kd_cache, d_kd_meta;
+    DevBuf<float4> d_kd_tree;
+    DevBuf<float2> d_kd_pre_pos, d_kd_pre_vel;
+    DevBuf<unsigned char> d_kd_sort_tmp;
+    size_t kd_sort_tmp_bytes = 0;
+    int kd_cap = 0;
 
     // ---- bookkeeping
     uint64_t ticks = 0, launches = 0;
@@ -633,6 +646,116 @@ int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
     return ECMGPU_OK;
 }
 
+// ---- faithful KD-tree neighbour mode (device/kdtree.cuh) -----------------------------------------
+// Levels of a median-split tree over n agents: the smallest L with 2^L - 1 >= n.
+int kd_levels(int n) {
+    int L = 0;
+    while (((1ll << L) - 1) < (long long)n) L++;
+    return L;
+}
+
+int kd_alloc(ecmgpu_sim* s) {
+    if (s->d_kd_raw.p) return ECMGPU_OK;
+    const size_t n = (size_t)s->prm.max_agents;
+    for (int b = 0; b < 2; b++) {
+        CUDA_TRY(s, s->d_kd_keys[b].alloc(n)); CUDA_TRY(s, s->d_kd_vals[b].alloc(n));
+        CUDA_TRY(s, s->d_kd_seg_r[b].alloc(n + 1)); CUDA_TRY(s, s->d_kd_seg_node[b].alloc(n + 1));
+    }
+    s->kd_cap = (int)((1ll << kd_levels((int)n)) - 1);
+    CUDA_TRY(s, s->d_kd_tree.alloc((size_t)s->kd_cap));
+    CUDA_TRY(s, s->d_kd_raw.alloc(5 * n)); CUDA_TRY(s, s->d_kd_raw_cnt.alloc(n));
+    CUDA_TRY(s, s->d_kd_cache.alloc(10));  // [0,5): carried from tick to tick; [5,10): zeros for ecmgpu_find_neighbors
+    CUDA_TRY(s, s->d_kd_meta.alloc(4));
+    CUDA_TRY(s, s->d_kd_pre_pos.alloc(n)); CUDA_TRY(s, s->d_kd_pre_vel.alloc(n));
+    cub::DoubleBuffer<unsigned long long> dk(s->d_kd_keys[0].p, s->d_kd_keys[1].p);
+    cub::DoubleBuffer<int> dv(s->d_kd_vals[0].p, s->d_kd_vals[1].p);
+    size_t bytes = 0;
+    CUDA_TRY(s, cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (int)n, 0, 64, s->stream));
+    s->kd_sort_tmp_bytes = bytes;
+    CUDA_TRY(s, s->d_kd_sort_tmp.alloc(std::max<size_t>(bytes, 16)));
+    CUDA_TRY(s, cudaMemsetAsync(s->d_kd_meta.p, 0, sizeof(int) * 4, s->stream));
+    return ECMGPU_OK;
+}
+
+void kd_free(ecmgpu_sim* s) {
+    for (int b = 0; b < 2; b++) { s->d_kd_keys[b].free(); s->d_kd_vals[b].free(); s->d_kd_seg_r[b].free(); s->d_kd_seg_node[b].free(); }
+    s->d_kd_tree.free(); s->d_kd_raw.free(); s->d_kd_raw_cnt.free(); s->d_kd_cache.free(); s->d_kd_meta.free();
+    s->d_kd_pre_pos.free(); s->d_kd_pre_vel.free(); s->d_kd_sort_tmp.free();
+}
+
+// KDTree::Construct (KDTree.cpp:22-57) on the pre-tick positions: one segmented sort + one split kernel per level.
+// Needs the snapshot's slot list (enqueue_grid_build) for the agents active at the start of the tick.
+int enqueue_kd_build(ecmgpu_sim* s, const TickView& t) {
+    const int n = s->n_slots;
+    KdBuild b;
+    b.n_slots = n;
+    b.n_active_ptr = t.n_sorted_ptr;
+    b.s_slot = s->d_s_slot.p;
+    b.pos = s->d_pos.p;
+    b.tree = s->d_kd_tree.p;
+    b.cap = s->kd_cap;
+    b.meta = s->d_kd_meta.p;
+    b.ties = s->d_counters.p + C_TOTAL_KD_TIES;
+    const int levels = kd_levels(n);
+    const size_t used_nodes = (size_t)((1ll << levels) - 1);
+    CUDA_TRY(s, cudaMemsetAsync(s->d_kd_tree.p, 0xff, sizeof(float4) * used_nodes, s->stream));  // KDTREE_NULL_NODE everywhere (KDTree.cpp:50-51)
+    const int nb = div_up(n, 256);
+    unsigned long long* k_in = s->d_kd_keys[0].p; unsigned long long* k_alt = s->d_kd_keys[1].p;
+    int* v_in = s->d_kd_vals[0].p; int* v_alt = s->d_kd_vals[1].p;
+    k_kd_init<<<nb, 256, 0, s->stream>>>(b, k_in, v_in, s->d_kd_seg_r[0].p, s->d_kd_seg_node[0].p);
+    s->launches++;
+    int seg_bits = 1;
+    while ((1ll << seg_bits) < (long long)n) seg_bits++;
+    for (int d = 0; d < levels; d++) {
+        cub::DoubleBuffer<unsigned long long> dk(k_in, k_alt);
+        cub::DoubleBuffer<int> dv(v_in, v_alt);
+        size_t bytes = s->kd_sort_tmp_bytes;
+        CUDA_TRY(s, cub::DeviceRadixSort::SortPairs(s->d_kd_sort_tmp.p, bytes, dk, dv, n, 0, 32 + seg_bits, s->stream));
+        k_kd_split<<<nb, 256, 0, s->stream>>>(b, d, dk.Current(), dv.Current(), dk.Alternate(), dv.Alternate(), s->d_kd_seg_r[d & 1].p,
+                                              s->d_kd_seg_node[d & 1].p, s->d_kd_seg_r[(d + 1) & 1].p, s->d_kd_seg_node[(d + 1) & 1].p);
+        k_in = dk.Alternate(); k_alt = dk.Current();
+        v_in = dv.Alternate(); v_alt = dv.Current();
+        s->launches++;  // ours; the library's sort passes are not counted
+    }
+    CUDA_TRY(s, cudaGetLastError());
+    return ECMGPU_OK;
+}
+
+KdQuery make_kd_query(ecmgpu_sim* s, bool carried) {
+    KdQuery q;
+    q.tree = s->d_kd_tree.p;
+    q.cap = s->kd_cap;
+    q.meta = s->d_kd_meta.p;
+    q.raw = s->d_kd_raw.p;
+    q.raw_cnt = s->d_kd_raw_cnt.p;
+    q.cache = s->d_kd_cache.p + (carried ? 0 : 5);
+    return q;
+}
+
+// The ORCA phase of a tick in KD-tree mode: tree, lists, token resolution, carried list, k_orca_kd.
+int enqueue_kd_orca(ecmgpu_sim* s, const TickView& t, int rows) {
+    int rc = enqueue_kd_build(s, t);
+    if (rc) return rc;
+    const size_t n = (size_t)s->n_slots;
+    // neighbours are read by slot from the pre-tick state while k_orca_kd integrates in place
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_kd_pre_pos.p, s->d_pos.p, sizeof(float2) * n, cudaMemcpyDeviceToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_kd_pre_vel.p, s->d_vel.p, sizeof(float2) * n, cudaMemcpyDeviceToDevice, s->stream));
+    const KdQuery q = make_kd_query(s, true);
+    k_kd_query<<<div_up(rows, 128), 128, 0, s->stream>>>(t, q, 1);
+    k_kd_resolve<<<div_up(s->n_slots, 256), 256, 0, s->stream>>>(s->n_slots, s->d_active.p, q, s->d_nbr.p, s->d_nbr_cnt.p);
+    k_kd_cache<<<1, 256, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_nbr.p, q.cache);
+    TickView t2 = t;
+    t2.grid.s_pos = s->d_kd_pre_pos.p;
+    t2.grid.s_vel = s->d_kd_pre_vel.p;
+    t2.grid.s_rad = s->d_radius.p;
+    t2.record_neighbors = 0;  // ECMGPU_NEIGHBORS already holds the lists
+    k_orca_kd<<<div_up(rows, 256), 256, 0, s->stream>>>(t2);
+    s->launches += 4;
+    CUDA_TRY(s, cudaGetLastError());
+    return ECMGPU_OK;
+}
+
+
 // Appends a polyline to the host mirror of the pool (start aligned to 8 points) with the padded
 // bounding boxes of its blocks of 8 segments; compacts the pool when it is full.
 void append_path(ecmgpu_sim* s, int slot, const float2* pts, int n) {
@@ -812,6 +935,7 @@ void ecmgpu_destroy(ecmgpu_sim* s) {
     s->d_lp3d_hdr.free(); s->d_lp3d_out.free(); s->d_lp3d_cs.free();
     s->d_fb_list.free(); s->d_ev_replan.free(); s->d_ev_destroyed.free(); s->d_s_pos.free(); s->d_s_vel.free();
     s->d_s_pref.free(); s->d_s_rad.free(); s->d_s_spd.free(); s->d_s_alive.free(); s->d_counters.free();
+    kd_free(s);
     comm_teardown(s);
     for (int g = 0; g < 2; g++) {
         if (s->graph_exec[g]) cudaGraphExecDestroy(s->graph_exec[g]);
@@ -1005,7 +1129,15 @@ int ecmgpu_update_phase(ecmgpu_sim* s, int phase) {
     if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[1], s->stream));
     const int nb = div_up(s->n_slots + (s->strips_on ? 2 * s->cap_halo + s->cap_self : 0), 128);
     const int ob = s->orca_block;
-    if (s->fused) {
+    if (s->neighbor_mode == ECMGPU_NEIGHBORS_KDTREE) {
+        if (s->strips_on) return fail(s, ECMGPU_ERR_INVALID, "the KD-tree neighbour mode runs on a single handle (no strips)");
+        k_attract<<<nb, 128, 0, s->stream>>>(t);
+        s->launches++;
+        if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
+        rc = enqueue_kd_orca(s, t, nb * 128);
+        if (rc) return rc;
+        s->launches -= 2;  // k_attract and k_orca_kd are counted above (3 are added below)
+    } else if (s->fused) {
         if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));  // "attract" phase is empty: all of it is k_tick
         k_tick<<<div_up(nb * 128, ob), ob, 0, s->stream>>>(t);
         s->launches -= 1;  // one kernel instead of two (3 are added below)
@@ -1029,7 +1161,8 @@ int ecmgpu_update(ecmgpu_sim* s) {
     // NCCL send/recv are kept out of graph capture (capturing them hung on 4 x B200 with NCCL 2.28): with the
     // NCCL transport the tick is submitted launch by launch.  The peer transport is plain kernels and memsets.
     const bool nccl_tick = s->strips_on && !s->local_transport && s->n_ranks > 1 && !s->p2p;
-    if (s->use_graph && !nccl_tick && !s->profiling && s->n_slots > 0) {
+    // the KD-tree mode submits a library sort per tree level: launch by launch as well
+    if (s->use_graph && !nccl_tick && !s->profiling && s->n_slots > 0 && s->neighbor_mode == ECMGPU_NEIGHBORS_EXACT) {
         CUDA_TRY(s, cudaSetDevice(s->prm.device));
         int rc = ensure_ready(s);  // host-side (re)builds happen outside the capture
         if (rc) return rc;
@@ -1336,8 +1469,19 @@ int ecmgpu_find_neighbors(ecmgpu_sim* s, int count, int* out_ids5, int* out_coun
         if (rc) return rc;
         CUDA_TRY(s, cudaMemsetAsync(s->d_nbr.p, 0xff, sizeof(int) * 5 * (size_t)s->n_slots, s->stream));
         CUDA_TRY(s, cudaMemsetAsync(s->d_nbr_cnt.p, 0xff, sizeof(int) * (size_t)s->n_slots, s->stream));
-        k_knn_query<<<div_up(s->n_slots + (s->strips_on ? 2 * s->cap_halo + s->cap_self : 0), 128), 128, 0, s->stream>>>(t);
-        k_fallback<<<148, 128, 0, s->stream>>>(t, 1);
+        if (s->neighbor_mode == ECMGPU_NEIGHBORS_KDTREE) {
+            // every active slot in ascending order with ONE shared, zero-filled output vector
+            // (Simulator::FindNNearestNeighbors, Simulator.cpp:211-227, called the way ORCA::GetVelocity calls it)
+            rc = enqueue_kd_build(s, t);
+            if (rc) return rc;
+            const KdQuery q = make_kd_query(s, false);
+            CUDA_TRY(s, cudaMemsetAsync(q.cache, 0, sizeof(int) * 5, s->stream));
+            k_kd_query<<<div_up(s->n_slots, 128), 128, 0, s->stream>>>(t, q, 0);
+            k_kd_resolve<<<div_up(s->n_slots, 256), 256, 0, s->stream>>>(s->n_slots, s->d_active.p, q, s->d_nbr.p, s->d_nbr_cnt.p);
+        } else {
+            k_knn_query<<<div_up(s->n_slots + (s->strips_on ? 2 * s->cap_halo + s->cap_self : 0), 128), 128, 0, s->stream>>>(t);
+            k_fallback<<<148, 128, 0, s->stream>>>(t, 1);
+        }
         s->launches += 2;
         CUDA_TRY(s, cudaGetLastError());
     }
@@ -1376,6 +1520,21 @@ int ecmgpu_find_obstacles(ecmgpu_sim* s, int slot, int* out_ids, int cap, int* o
     return ECMGPU_OK;
 }
 
+int ecmgpu_set_neighbor_mode(ecmgpu_sim* s, int mode) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (mode != ECMGPU_NEIGHBORS_EXACT && mode != ECMGPU_NEIGHBORS_KDTREE) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_neighbor_mode: unknown mode");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    if (mode == ECMGPU_NEIGHBORS_KDTREE) {
+        if (s->strips_on) return fail(s, ECMGPU_ERR_INVALID, "the KD-tree neighbour mode runs on a single handle (no strips)");
+        int rc = kd_alloc(s);
+        if (rc) return rc;
+        CUDA_TRY(s, cudaMemsetAsync(s->d_kd_cache.p, 0, sizeof(int) * 10, s->stream));  // a fresh ORCA object (ORCA.h:87)
+    }
+    s->neighbor_mode = mode;
+    s->config_epoch++;
+    return ECMGPU_OK;
+}
+
 int ecmgpu_get_stats(ecmgpu_sim* s, ecmgpu_stats* o) {
     if (!s || !o) return ECMGPU_ERR_INVALID;
     CUDA_TRY(s, cudaSetDevice(s->prm.device));
@@ -1394,6 +1553,7 @@ int ecmgpu_get_stats(ecmgpu_sim* s, ecmgpu_stats* o) {
     o->ticks = s->ticks; o->kernel_launches = s->launches;
     o->knn_fallbacks = c[C_TOTAL_FALLBACK]; o->obstacle_overflows = c[C_TOTAL_OBST_OVF]; o->lp3d_runs = c[C_TOTAL_LP3D];
     o->location_failures = c[C_TOTAL_LOCFAIL]; o->replans = c[C_TOTAL_REPLAN]; o->halo_misses = c[C_TOTAL_HALO_MISS];
+    o->kd_median_ties = c[C_TOTAL_KD_TIES];
     return ECMGPU_OK;
 }
 
@@ -1523,6 +1683,7 @@ int ecmgpu_comm_p2p_connect(ecmgpu_sim* s, const uint8_t* left_handles, const ui
 int ecmgpu_comm_set_strips(ecmgpu_sim* s, const float* bounds, float halo_width) {
     if (!s) return ECMGPU_ERR_INVALID;
     if (!bounds || !(halo_width > 0.0f)) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_comm_set_strips: bad arguments");
+    if (s->neighbor_mode != ECMGPU_NEIGHBORS_EXACT) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_comm_set_strips: the KD-tree neighbour mode runs on a single handle (no strips)");
     if (s->n_ranks > 1 && !s->nccl_comm && !s->local_transport) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_comm_set_strips: call ecmgpu_comm_init first");
     for (int r = 0; r < s->n_ranks; r++) {
         if (!(bounds[r] < bounds[r + 1])) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_comm_set_strips: bounds must ascend");

@@ -21,6 +21,7 @@ u8p = C.POINTER(C.c_uint8)
 
 # selectors (include/ecm_b200.h)
 POS, VEL, PREFVEL, ATTRACTION, FORCE, RADIUS, SPEED, ACTIVE, CELL, NEIGHBORS, NEIGHBOR_COUNT, STATUS, REPLAN_PENDING = range(13)
+NEIGHBORS_EXACT, NEIGHBORS_KDTREE = 0, 1
 ST_NO_CELL, ST_REPLAN, ST_ARRIVING, ST_DESTROYED, ST_OBST_OVERFLOW, ST_KNN_FALLBACK, ST_LP3D, ST_HALO_MISS = (
     1, 2, 4, 8, 16, 32, 64, 128)
 
@@ -38,6 +39,7 @@ EXPORTS = [
     "ecmgpu_locate", "ecmgpu_retract", "ecmgpu_find_neighbors", "ecmgpu_find_obstacles", "ecmgpu_get_stats",
     "ecmgpu_last_tick_ms", "ecmgpu_set_profiling", "ecmgpu_mark", "ecmgpu_mark_elapsed_ms", "ecmgpu_stream", "ecmgpu_comm_unique_id", "ecmgpu_comm_init",
     "ecmgpu_comm_set_strips", "ecmgpu_comm_init_local", "ecmgpu_update_phase", "ecmgpu_update_io", "ecmgpu_update_io_owned", "ecmgpu_io_wait", "ecmgpu_comm_p2p_export", "ecmgpu_comm_p2p_connect",
+    "ecmgpu_set_neighbor_mode",
 ]
 
 
@@ -53,7 +55,8 @@ class Stats(C.Structure):
                 ("max_cell_list", C.c_int), ("max_obstacle_list", C.c_int), ("ticks", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("knn_fallbacks", C.c_uint64), ("obstacle_overflows", C.c_uint64),
                 ("lp3d_runs", C.c_uint64), ("location_failures", C.c_uint64), ("replans", C.c_uint64),
-                ("halo_misses", C.c_uint64)]
+                ("halo_misses", C.c_uint64),
+                ("kd_median_ties", C.c_uint64)]
 
 
 class EcmGpuError(RuntimeError):
@@ -106,6 +109,7 @@ def lib() -> C.CDLL:
         L.ecmgpu_comm_p2p_connect.argtypes = [vp, u8p, u8p]
         L.ecmgpu_update_io.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(C.c_uint64)]
         L.ecmgpu_io_wait.argtypes = [vp, C.c_uint64]
+        L.ecmgpu_set_neighbor_mode.argtypes = [vp, C.c_int]
         L.ecmgpu_update_io_owned.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
@@ -329,6 +333,10 @@ class GpuSim:
         cnt = np.full(n, -1, np.int32)
         self._ck(self.L.ecmgpu_find_neighbors(self.h, n, _p(ids, i32p), _p(cnt, i32p)))
         return ids, cnt
+
+    def set_neighbor_mode(self, mode: int):
+        """NEIGHBORS_EXACT (default) or NEIGHBORS_KDTREE: the reference's own KD-tree lists (parity mode)."""
+        self._ck(self.L.ecmgpu_set_neighbor_mode(self.h, int(mode)))
 
     def query_obstacles(self, slot, cap=256):
         out = np.zeros(cap, np.int32)

@@ -165,6 +165,18 @@ int ecmgpu_find_neighbors(ecmgpu_sim* sim, int count, int* out_ids5, int* out_co
 /* Simulator::FindNearestObstacles with ORCA's range for one slot; returns the number found. */
 int ecmgpu_find_obstacles(ecmgpu_sim* sim, int slot, int* out_ids, int cap, int* out_n);
 
+/* -- neighbour mode ---------------------------------------------------------------------------
+ * ECMGPU_NEIGHBORS_EXACT (default): the exact 5-NN contract of DESIGN.md on the per-tick uniform grid.
+ * ECMGPU_NEIGHBORS_KDTREE: the reference's own lists - a median-split tree built like KDTree::Construct
+ * (KDTree.cpp:22-83) and searched like KDTree::KNearestAgents_R (KDTree.cpp:98-202) with its pruning and
+ * fill rules and the ids ORCA::m_NeighborCache (ORCA.h:100) carries from one query to the next, so that
+ * trajectories can be compared with the UNMODIFIED reference.  A parity mode: single handle (no strips),
+ * several times the cost of the default.  Switching modes resets the carried-over list to zeros, the
+ * state of a fresh ORCA object (ORCA.h:87).  ECMGPU_NEIGHBORS then holds the tick's lists in the
+ * reference's order (place 0 = farthest), ecmgpu_find_neighbors answers in the same mode. */
+enum { ECMGPU_NEIGHBORS_EXACT = 0, ECMGPU_NEIGHBORS_KDTREE = 1 };
+int ecmgpu_set_neighbor_mode(ecmgpu_sim* sim, int mode);
+
 /* -- introspection ----------------------------------------------------------------------------*/
 typedef struct ecmgpu_stats {
     int   n_slots;            /* highest loaded slot + 1 (what the kernels iterate over) */
@@ -177,6 +189,7 @@ typedef struct ecmgpu_stats {
     uint64_t ticks;           /* ticks enqueued so far */
     uint64_t kernel_launches; /* kernels launched by this handle so far */
     uint64_t knn_fallbacks, obstacle_overflows, lp3d_runs, location_failures, replans, halo_misses;
+    uint64_t kd_median_ties;  /* ECMGPU_NEIGHBORS_KDTREE: tree segments whose median tied on the split axis (0 = the tree is unique) */
 } ecmgpu_stats;
 int ecmgpu_get_stats(ecmgpu_sim* sim, ecmgpu_stats* out);
 /* CUDA-event time of each phase of the LAST completed tick, milliseconds.

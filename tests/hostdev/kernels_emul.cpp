@@ -12,7 +12,10 @@
 // (needs 32 co-operating lanes; the scenes used never exhaust the ring budget, which the harness asserts).
 #include <vector>
 
+#include <numeric>
+
 #include "../../ecmgenerator_b200/csrc/device/strips.cuh"
+#include "../../ecmgenerator_b200/csrc/device/kdtree.cuh"
 
 using namespace ecm;
 
@@ -59,6 +62,12 @@ struct Emu {
     std::vector<unsigned char> send[2], recv[2];
     std::vector<HaloEntry> self_ghost;
     std::vector<int> self_ghost_n, g_key, g_rank;
+    // faithful KD-tree mode (kdtree.cuh)
+    std::vector<unsigned long long> kd_keys[2];
+    std::vector<int> kd_vals[2], kd_seg_r[2], kd_seg_node[2], kd_raw, kd_raw_cnt, kd_cache, kd_meta;
+    std::vector<float4> kd_tree;
+    std::vector<float2> kd_pre_pos, kd_pre_vel;
+    int kd_cap = 0;
 
     TickView view() {
         TickView t;
@@ -254,6 +263,107 @@ int emu_tick(void* h) {
     const int fb = (int)e->counters[C_FALLBACK_N];
     if (fb == 0) launch(64, [&] { k_fallback(t, 0); });  // the parked LP3D agents (its warp-per-agent half needs real warps)
     return fb;
+}
+
+// ---- the tick in KD-tree neighbour mode: enqueue_grid_build + k_attract + enqueue_kd_orca + k_fallback (ecmgpu.cu).
+// The library radix sort of every tree level is stood in for by std::stable_sort on the same keys.
+static int kd_levels(int n) { int L = 0; while (((1ll << L) - 1) < (long long)n) L++; return L; }
+
+static void emu_kd_alloc(Emu* e) {
+    if (!e->kd_raw.empty()) return;
+    const size_t n = e->n;
+    for (int b = 0; b < 2; b++) { e->kd_keys[b].assign(n, 0); e->kd_vals[b].assign(n, -1); e->kd_seg_r[b].assign(n + 1, 0); e->kd_seg_node[b].assign(n + 1, 0); }
+    e->kd_cap = (int)((1ll << kd_levels((int)n)) - 1);
+    e->kd_tree.resize(e->kd_cap);
+    e->kd_raw.assign(5 * n, -1); e->kd_raw_cnt.assign(n, 0); e->kd_cache.assign(10, 0); e->kd_meta.assign(4, 0);
+    e->kd_pre_pos.resize(n); e->kd_pre_vel.resize(n);
+}
+
+static void emu_kd_build(Emu* e, const TickView& t) {
+    const int n = e->n_slots;
+    KdBuild b;
+    b.n_slots = n; b.n_active_ptr = t.n_sorted_ptr; b.s_slot = e->s_slot.data(); b.pos = e->pos.data();
+    b.tree = e->kd_tree.data(); b.cap = e->kd_cap; b.meta = e->kd_meta.data(); b.ties = e->counters.data() + C_TOTAL_KD_TIES;
+    memset(e->kd_tree.data(), 0xff, sizeof(float4) * e->kd_tree.size());
+    int in = 0;
+    launch(n, [&] { k_kd_init(b, e->kd_keys[0].data(), e->kd_vals[0].data(), e->kd_seg_r[0].data(), e->kd_seg_node[0].data()); });
+    const int levels = kd_levels(n);
+    std::vector<int> perm(n);
+    for (int d = 0; d < levels; d++) {
+        std::iota(perm.begin(), perm.end(), 0);
+        const unsigned long long* k = e->kd_keys[in].data();
+        std::stable_sort(perm.begin(), perm.end(), [k](int a, int c) { return k[a] < k[c]; });
+        std::vector<unsigned long long> sk(n);
+        std::vector<int> sv(n);
+        for (int i = 0; i < n; i++) { sk[i] = k[perm[i]]; sv[i] = e->kd_vals[in][perm[i]]; }
+        const int out = in ^ 1;
+        launch(n, [&] {
+            k_kd_split(b, d, sk.data(), sv.data(), e->kd_keys[out].data(), e->kd_vals[out].data(), e->kd_seg_r[d & 1].data(), e->kd_seg_node[d & 1].data(),
+                       e->kd_seg_r[(d + 1) & 1].data(), e->kd_seg_node[(d + 1) & 1].data());
+        });
+        in = out;
+    }
+}
+
+static KdQuery emu_kd_query(Emu* e, bool carried) {
+    KdQuery q;
+    q.tree = e->kd_tree.data(); q.cap = e->kd_cap; q.meta = e->kd_meta.data(); q.raw = e->kd_raw.data(); q.raw_cnt = e->kd_raw_cnt.data();
+    q.cache = e->kd_cache.data() + (carried ? 0 : 5);
+    return q;
+}
+
+void emu_kd_reset(void* h) {  // ecmgpu_set_neighbor_mode(KDTREE)
+    Emu* e = (Emu*)h;
+    emu_kd_alloc(e);
+    std::fill(e->kd_cache.begin(), e->kd_cache.end(), 0);
+}
+
+static void emu_grid_build(Emu* e, const TickView& t) {
+    GridParams gp{e->gx0, e->gy0, e->gcell, 1.0f / e->gcell, e->gw, e->gh};
+    std::fill(e->cell_count.begin(), e->cell_count.end(), 0);
+    e->counters[C_FALLBACK_N] = 0; e->counters[C_LP3D_N] = 0;
+    launch(e->n_slots, [&] { k_bin_count(e->n_slots, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data()); });
+    int run = 0;
+    for (size_t c = 0; c < (size_t)e->gw * e->gh + 1; c++) { int v = e->cell_count[c]; e->cell_count[c] = run; run += v; }
+    launch(e->n_slots, [&] { k_scatter(e->n_slots, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc, 0); });
+}
+
+void emu_tick_kd(void* h) {
+    Emu* e = (Emu*)h;
+    emu_kd_alloc(e);
+    TickView t = e->view();
+    emu_grid_build(e, t);
+    const int rows = e->n_slots;
+    launch(rows, [&] { k_attract(t); });
+    emu_kd_build(e, t);
+    std::copy(e->pos.begin(), e->pos.begin() + e->n_slots, e->kd_pre_pos.begin());
+    std::copy(e->vel.begin(), e->vel.begin() + e->n_slots, e->kd_pre_vel.begin());
+    const KdQuery q = emu_kd_query(e, true);
+    launch(rows, [&] { k_kd_query(t, q, 1); });
+    launch(e->n_slots, [&] { k_kd_resolve(e->n_slots, e->active.data(), q, e->nbr.data(), e->nbr_cnt.data()); });
+    launch(1, [&] { k_kd_cache(e->n_slots, e->active.data(), e->nbr.data(), q.cache); });
+    TickView t2 = t;
+    t2.grid.s_pos = e->kd_pre_pos.data(); t2.grid.s_vel = e->kd_pre_vel.data(); t2.grid.s_rad = e->radius.data();
+    t2.record_neighbors = 0;
+    launch(rows, [&] { k_orca_kd(t2); });
+    launch(64, [&] { k_fallback(t, 0); });
+}
+
+// ecmgpu_find_neighbors in KD-tree mode
+void emu_query_neighbors_kd(void* h, int* ids, int* cnt) {
+    Emu* e = (Emu*)h;
+    emu_kd_alloc(e);
+    TickView t = e->view();
+    emu_grid_build(e, t);
+    emu_kd_build(e, t);
+    std::fill(e->nbr.begin(), e->nbr.end(), -1);
+    std::fill(e->nbr_cnt.begin(), e->nbr_cnt.end(), -1);
+    const KdQuery q = emu_kd_query(e, false);
+    std::fill(q.cache, q.cache + 5, 0);
+    launch(e->n_slots, [&] { k_kd_query(t, q, 0); });
+    launch(e->n_slots, [&] { k_kd_resolve(e->n_slots, e->active.data(), q, e->nbr.data(), e->nbr_cnt.data()); });
+    memcpy(ids, e->nbr.data(), 20 * (size_t)e->n);
+    memcpy(cnt, e->nbr_cnt.data(), 4 * (size_t)e->n);
 }
 
 void emu_read(void* h, float* pos, float* vel, float* pref, float* attr, float* force, unsigned char* active, int* nbr, int* nbr_cnt,

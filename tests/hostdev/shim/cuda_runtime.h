@@ -48,6 +48,11 @@ static inline void __nanosleep(unsigned) {}
 
 template <class T, class U>
 static inline T atomicAdd(T* p, U v) { T old = *p; *p = (T)(old + (T)v); return old; }
+static inline int atomicMax(int* p, int v) { int old = *p; if (v > old) *p = v; return old; }
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 
 // launch geometry: one thread per block (kernels_emul.cpp walks blockIdx.x over the grid)
 struct HdDim3 { int x, y, z; };

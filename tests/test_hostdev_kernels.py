@@ -53,6 +53,9 @@ def load_emu():
     L.emu_pack.argtypes = [vp]
     L.emu_exchange.argtypes = [vp, vp, vp]
     L.emu_tick.argtypes = [vp]
+    L.emu_tick_kd.argtypes = [vp]
+    L.emu_kd_reset.argtypes = [vp]
+    L.emu_query_neighbors_kd.argtypes = [vp, i32p, i32p]
     L.emu_read.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, u8p, i32p, i32p, u32p, i32p]
     L.emu_counters.argtypes = [vp, u64p]
     L.emu_poll.argtypes = [vp, i32p, i32p, i32p, i32p]
@@ -166,10 +169,9 @@ def _cell_for(g):
     return max(2.0, _r5_max(g) / 2.0)  # 8 rings then reach 4 x the largest 5th-neighbour distance
 
 
-def _run_against_golden(sim, g, step, state, label):
+def _run_against_golden(sim, g, step, state, label, mode="exact-knn"):
     from tests.util import apply_events
 
-    mode = "exact-knn"
     full_at = set(int(t) for t in g.z[f"{mode}/full_at"])
     prev_active = np.ones(g.n, bool)
     for t in range(g.ticks(mode)):
