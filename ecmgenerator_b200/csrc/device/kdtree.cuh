@@ -22,8 +22,13 @@
 //                            not active any more; the reference reads its slot all the same)
 //
 // std::sort leaves the order of agents with EQUAL coordinates implementation-defined.  The tree is unique exactly
-// when no agent of a segment ties with the segment's median on the split axis; k_kd_split counts such ties
-// (ecmgpu_stats.kd_median_ties) - with zero ties the tree equals the reference's whatever its std::sort does.
+// when no agent of a segment ties with the segment's median on the split axis.  Where one does, the reference's
+// tree depends on its standard library: libstdc++ (the oracle's build) sorts ranges of up to 16 elements by plain
+// insertion - a STABLE sort, whose input order is the parent segment's sorted order - and so does the radix sort
+// here (stable, elements start in ascending slot order like KDTree.cpp:34-41), hence such ties resolve identically
+// (counted in ecmgpu_stats.kd_small_ties, for information).  A median tie in a LARGER segment goes through
+// introsort's unstable partitioning and cannot be followed by a parallel sort: k_kd_split counts those in
+// ecmgpu_stats.kd_median_ties - with zero of them the tree equals the reference's.
 #pragma once
 #include "tick.cuh"
 
@@ -44,15 +49,18 @@ __device__ __forceinline__ float kd_from_orderable(unsigned k) {
 struct KdBuild {
     int n_slots;                 // elements sorted per level (live agents first, then one dead element per spare place)
     const int* n_active_ptr;     // device: number of agents active at the start of the tick (= rows of the snapshot)
-    const int* s_slot;           // snapshot: the active agents (any order; ties are reported, not ordered)
+    const int* cell_key;         // [slot] grid cell key of the tick, -1 = not active at the start of the tick (k_bin_count)
     const float2* pos;           // per slot, pre-tick
     float4* tree;                // [cap] (x, y, slot bits, -) per node of the implicit heap (KDTree.cpp:12-20); slot -1 = KDTREE_NULL_NODE
     int cap;
     int* meta;                   // [0] m_MaxDepth (KDTree.cpp:47)
-    unsigned long long* ties;    // counter: segments whose median ties with a neighbour on the split axis
+    unsigned long long* ties;    // counter: segments of more than kKdStableRange elements whose median ties on the split axis
+    unsigned long long* small_ties;  // counter: the same in smaller segments (resolved like libstdc++'s insertion sort)
 };
+constexpr int kKdStableRange = 16;  // libstdc++ std::sort: _S_threshold, ranges up to this size are insertion-sorted
 
-// Level 0: the root segment [0, n_active) sorted by x next; every other place is dead.
+// Level 0: element i is slot i (ascending slot order, KDTree.cpp:34-41); the agents active at the start of the tick
+// form the root segment [0, n_active) once the first sort (by x) has moved the dead elements behind them.
 __global__ void __launch_bounds__(256) k_kd_init(KdBuild b, unsigned long long* __restrict__ keys, int* __restrict__ vals, int* __restrict__ seg_r,
                                                  int* __restrict__ seg_node) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,12 +74,11 @@ __global__ void __launch_bounds__(256) k_kd_init(KdBuild b, unsigned long long* 
         while ((2ll << h) < (long long)n + 1) h++;
         b.meta[0] = h;
     }
-    if (i < n) {
-        const int slot = b.s_slot[i];
-        keys[i] = (unsigned long long)kd_orderable(b.pos[slot].x);  // segment start 0 in the high half
-        vals[i] = slot;
+    if (b.cell_key[i] >= 0) {
+        keys[i] = (unsigned long long)kd_orderable(b.pos[i].x);  // segment start 0 in the high half
+        vals[i] = i;
     } else {
-        keys[i] = (unsigned long long)(unsigned)i << 32;
+        keys[i] = (unsigned long long)(unsigned)b.n_slots << 32;  // behind every segment start
         vals[i] = kKdDead;
     }
 }
@@ -100,7 +107,7 @@ __global__ void __launch_bounds__(256) k_kd_split(KdBuild b, int depth, const un
         if (node < b.cap) b.tree[node] = make_float4(p.x, p.y, __int_as_float(slot), 0.0f);
         const float c = kd_from_orderable((unsigned)key);
         const bool tie = (i > l && kd_from_orderable((unsigned)keys_in[i - 1]) == c) || (i + 1 < r && kd_from_orderable((unsigned)keys_in[i + 1]) == c);
-        if (tie) atomicAdd(b.ties, 1ull);
+        if (tie) atomicAdd(r - l > kKdStableRange ? b.ties : b.small_ties, 1ull);
         keys_out[i] = (unsigned long long)(unsigned)i << 32;
         vals_out[i] = kKdDead;
         return;

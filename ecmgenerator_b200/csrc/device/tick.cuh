@@ -32,7 +32,8 @@ enum Counter {
     C_TOTAL_LOCFAIL = 7,
     C_TOTAL_REPLAN = 8,
     C_TOTAL_HALO_MISS = 9,
-    C_TOTAL_KD_TIES = 10,  // kdtree.cuh: tree segments whose median tied on the split axis
+    C_TOTAL_KD_TIES = 10,  // kdtree.cuh: tree segments (> 16 elements) whose median tied on the split axis
+    C_TOTAL_KD_SMALL_TIES = 11,  // the same in segments of up to 16 elements (resolved like libstdc++)
     C_COUNT = 16
 };
 

@@ -690,12 +690,13 @@ int enqueue_kd_build(ecmgpu_sim* s, const TickView& t) {
     KdBuild b;
     b.n_slots = n;
     b.n_active_ptr = t.n_sorted_ptr;
-    b.s_slot = s->d_s_slot.p;
+    b.cell_key = s->d_key.p;
     b.pos = s->d_pos.p;
     b.tree = s->d_kd_tree.p;
     b.cap = s->kd_cap;
     b.meta = s->d_kd_meta.p;
     b.ties = s->d_counters.p + C_TOTAL_KD_TIES;
+    b.small_ties = s->d_counters.p + C_TOTAL_KD_SMALL_TIES;
     const int levels = kd_levels(n);
     const size_t used_nodes = (size_t)((1ll << levels) - 1);
     CUDA_TRY(s, cudaMemsetAsync(s->d_kd_tree.p, 0xff, sizeof(float4) * used_nodes, s->stream));  // KDTREE_NULL_NODE everywhere (KDTree.cpp:50-51)
@@ -704,8 +705,8 @@ int enqueue_kd_build(ecmgpu_sim* s, const TickView& t) {
     int* v_in = s->d_kd_vals[0].p; int* v_alt = s->d_kd_vals[1].p;
     k_kd_init<<<nb, 256, 0, s->stream>>>(b, k_in, v_in, s->d_kd_seg_r[0].p, s->d_kd_seg_node[0].p);
     s->launches++;
-    int seg_bits = 1;
-    while ((1ll << seg_bits) < (long long)n) seg_bits++;
+    int seg_bits = 1;  // segment starts are < n, the dead elements of level 0 carry n itself
+    while ((1ll << seg_bits) <= (long long)n) seg_bits++;
     for (int d = 0; d < levels; d++) {
         cub::DoubleBuffer<unsigned long long> dk(k_in, k_alt);
         cub::DoubleBuffer<int> dv(v_in, v_alt);
@@ -1554,6 +1555,7 @@ int ecmgpu_get_stats(ecmgpu_sim* s, ecmgpu_stats* o) {
     o->knn_fallbacks = c[C_TOTAL_FALLBACK]; o->obstacle_overflows = c[C_TOTAL_OBST_OVF]; o->lp3d_runs = c[C_TOTAL_LP3D];
     o->location_failures = c[C_TOTAL_LOCFAIL]; o->replans = c[C_TOTAL_REPLAN]; o->halo_misses = c[C_TOTAL_HALO_MISS];
     o->kd_median_ties = c[C_TOTAL_KD_TIES];
+    o->kd_small_ties = c[C_TOTAL_KD_SMALL_TIES];
     return ECMGPU_OK;
 }
 

@@ -189,7 +189,10 @@ typedef struct ecmgpu_stats {
     uint64_t ticks;           /* ticks enqueued so far */
     uint64_t kernel_launches; /* kernels launched by this handle so far */
     uint64_t knn_fallbacks, obstacle_overflows, lp3d_runs, location_failures, replans, halo_misses;
-    uint64_t kd_median_ties;  /* ECMGPU_NEIGHBORS_KDTREE: tree segments whose median tied on the split axis (0 = the tree is unique) */
+    /* ECMGPU_NEIGHBORS_KDTREE: tree segments whose median tied with another agent on the split axis.  In segments of
+     * up to 16 agents (kd_small_ties) the tie resolves like libstdc++'s std::sort does (insertion sort, stable);
+     * in larger ones (kd_median_ties) the reference's tree is std::sort-defined: 0 = the tree equals the reference's */
+    uint64_t kd_median_ties, kd_small_ties;
 } ecmgpu_stats;
 int ecmgpu_get_stats(ecmgpu_sim* sim, ecmgpu_stats* out);
 /* CUDA-event time of each phase of the LAST completed tick, milliseconds.

@@ -282,8 +282,9 @@ static void emu_kd_alloc(Emu* e) {
 static void emu_kd_build(Emu* e, const TickView& t) {
     const int n = e->n_slots;
     KdBuild b;
-    b.n_slots = n; b.n_active_ptr = t.n_sorted_ptr; b.s_slot = e->s_slot.data(); b.pos = e->pos.data();
+    b.n_slots = n; b.n_active_ptr = t.n_sorted_ptr; b.cell_key = e->key.data(); b.pos = e->pos.data();
     b.tree = e->kd_tree.data(); b.cap = e->kd_cap; b.meta = e->kd_meta.data(); b.ties = e->counters.data() + C_TOTAL_KD_TIES;
+    b.small_ties = e->counters.data() + C_TOTAL_KD_SMALL_TIES;
     memset(e->kd_tree.data(), 0xff, sizeof(float4) * e->kd_tree.size());
     int in = 0;
     launch(n, [&] { k_kd_init(b, e->kd_keys[0].data(), e->kd_vals[0].data(), e->kd_seg_r[0].data(), e->kd_seg_node[0].data()); });

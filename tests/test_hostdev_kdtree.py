@@ -70,3 +70,66 @@ def test_kd_mode_differs_from_exact_mode():
     """The two golden trajectories are different (otherwise the test above would prove nothing about the quirks)."""
     g = Golden("c2_small")
     assert not np.array_equal(g.z["ref-kdtree/final_pos"], g.z["exact-knn/final_pos"])
+
+
+def test_kd_small_segment_ties_resolve_like_the_reference():
+    """Agents with EQUAL coordinates: where the tie sits at the median of a segment of up to 16 agents, libstdc++'s
+    std::sort is an insertion sort (stable) and the stable radix sort of the build resolves it the same way - the
+    lists must still equal the reference's (C oracle with its std::sort restatement, and the compiled reference
+    itself where it is available).  Ties at the median of larger segments are the ones reported as ambiguous."""
+    import copy
+
+    from oracle import pyref
+    from oracle.pyoracle import OracleSim
+    from tests.test_hostdev_kernels import load_emu
+
+    L = load_emu()
+    g = Golden("c2_small")
+    rng = np.random.default_rng(11)
+    pos = g.crowd.pos.copy()
+    d2 = ((pos[:, None, :] - pos[None, :, :]) ** 2).sum(-1)
+    np.fill_diagonal(d2, np.inf)
+
+    def probe(p):
+        g2 = copy.copy(g)
+        g2.crowd = copy.copy(g.crowd)
+        g2.crowd.pos = p
+        dev = EmuDevice(L, g2, _cell_for(g))
+        L.emu_kd_reset(dev.h)
+        ids, cnt = _query(L, dev)
+        c = dev.counters()
+        dev.close()
+        return ids, cnt, int(c[C_TOTAL_KD_TIES + 1]), int(c[C_TOTAL_KD_TIES])
+
+    # tie nearest neighbours on x or y, one pair at a time; keep a pair unless it puts a tie on the median of a LARGE segment
+    used = np.zeros(g.n, bool)
+    pairs = 0
+    for a in rng.permutation(g.n):
+        b = int(np.argmin(d2[a]))
+        if used[a] or used[b]:
+            continue
+        trial = pos.copy()
+        trial[b, pairs & 1] = trial[a, pairs & 1]
+        if probe(trial)[3] > 0:
+            continue
+        pos = trial
+        used[a] = used[b] = True
+        pairs += 1
+        if pairs == 60:
+            break
+    ids, cnt, small, big = probe(pos)
+    print(f"{pairs} tied pairs: {small} median ties in segments of up to 16 agents, {big} in larger ones")
+    assert small >= 5, "the scene must put ties on medians of small segments"
+    assert big == 0
+    ora = OracleSim(g.world, g.n + 8, g.step, "ref-kdtree")
+    ora.bulk_load(pos, g.crowd.radius, g.crowd.speed, g.path_off, g.path_xy)
+    io, co = ora.query_neighbors(g.n)
+    assert_bits_equal(cnt, co, "counts vs the C oracle")
+    assert_bits_equal(ids, io, "ids vs the C oracle (std::sort restated)")
+    if pyref.available("ref-kdtree"):
+        r = pyref.RefSim(g.world, g.n + 8, g.step, "ref-kdtree")
+        r.bulk_load_paths(pos, g.crowd.radius, g.crowd.speed, g.path_off, g.path_xy) if hasattr(r, "bulk_load_paths") else \
+            r.bulk_load(pos, g.crowd.goal, g.crowd.radius, g.crowd.speed)
+        ir, cr = r.query_neighbors(g.n)
+        r.close()
+        assert_bits_equal(ids, ir, "ids vs the compiled reference")
