@@ -59,6 +59,36 @@ __device__ __noinline__ v2 vnormalized(v2 a) {
     if (l == 0.0f) return a;
     return V(a.x / l, a.y / l);
 }
+// Arithmetic of the ORCA half-planes and linear programs only (orca.cuh).  Their contract is "new velocities within
+// 1e-4 m/s", not bit-exactness, so a build with -DECM_ORCA_FAST may use the SFU approximations (division 2 ulp,
+// square root 1 ulp, sine / cosine 2^-21 absolute) instead of the ~10-instruction IEEE sequences, which are a quarter
+// of k_orca's instructions (profiles/r01_v8_k_orca_by_function.txt).  Off by default: an A/B on the GPU has to show
+// both the gain and the parity statistics (tools/build_variants.py).  Everything that feeds a bit-exact decision
+// (cells, neighbour order, the obstacle range filter, preferred velocities) stays IEEE in either build.
+#ifdef ECM_ORCA_FAST
+__device__ __forceinline__ float odiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float osqrt(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void osincos(float a, float* sn, float* cs) { __sincosf(a, sn, cs); }
+__device__ __forceinline__ v2 ovdiv(v2 a, float s) { return V(odiv(a.x, s), odiv(a.y, s)); }
+__device__ __forceinline__ float ovlen(v2 a) { return osqrt(a.x * a.x + a.y * a.y); }
+__device__ __forceinline__ v2 ovnormalized(v2 a) {
+    const float l2 = a.x * a.x + a.y * a.y;
+    if (l2 == 0.0f) return a;
+    const float inv = rsqrtf(l2);
+    return V(a.x * inv, a.y * inv);
+}
+#else
+__device__ __forceinline__ float odiv(float a, float b) { return a / b; }
+__device__ __forceinline__ float osqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ void osincos(float a, float* sn, float* cs) { sincosf(a, sn, cs); }
+__device__ __forceinline__ v2 ovdiv(v2 a, float s) { return vdiv(a, s); }
+__device__ __forceinline__ float ovlen(v2 a) { return vlen(a); }
+__device__ __forceinline__ v2 ovnormalized(v2 a) { return vnormalized(a); }
+#endif
 // Point::Approximate (ECMDataTypes.cpp:97-100): open +-EPSILON box.
 __device__ __forceinline__ bool approx(v2 a, v2 b) {
     return a.x < (b.x + kEpsilon) && a.x > (b.x - kEpsilon) && a.y < (b.y + kEpsilon) && a.y > (b.y - kEpsilon);

@@ -65,18 +65,18 @@ __device__ __forceinline__ bool obstacle_constraint(const ObstView& ob, int oL, 
     bool cvxL = __ldg(&ob.convex[oL]) != 0, cvxR = __ldg(&ob.convex[oR]) != 0;
     v2 rp1 = vsub(pL, position), rp2 = vsub(pR, position);
     v2 segDir = vsub(pR, pL);
-    const float sp = vdot(vmul(rp1, -1.0f), segDir) / vlen2(segDir);
+    const float sp = odiv(vdot(vmul(rp1, -1.0f), segDir), vlen2(segDir));
     const float distSqLine = vlen2(vsub(vmul(rp1, -1.0f), vmul(segDir, sp)));
     const float distSq1 = vlen2(rp1), distSq2 = vlen2(rp2);
     segDir = __ldg(&ob.dir[oL]);  // = Normalize(segDir)
     const float radiusSq = clearance * clearance;
 
     if (sp < 0.0f && distSq1 <= radiusSq) {  // collision with the left vertex (ORCA.cpp:92-105)
-        if (cvxL) { c = cmake(V(0.0f, 0.0f), vnormalized(vmul(rp1, -1.0f))); return true; }
+        if (cvxL) { c = cmake(V(0.0f, 0.0f), ovnormalized(vmul(rp1, -1.0f))); return true; }
         return false;
     } else if (sp > 1.0f && distSq2 <= radiusSq) {  // collision with the right vertex (ORCA.cpp:108-121)
         v2 rnd = __ldg(&ob.dir[oR]);  // = Normalize(next(R).p - R.p)
-        if (cvxR && vdet(rp2, rnd) >= 0.0f) { c = cmake(V(0.0f, 0.0f), vnormalized(vmul(rp2, -1.0f))); return true; }
+        if (cvxR && vdet(rp2, rnd) >= 0.0f) { c = cmake(V(0.0f, 0.0f), ovnormalized(vmul(rp2, -1.0f))); return true; }
         return false;
     } else if (sp >= 0.0f && sp < 1.0f && distSqLine <= radiusSq) {  // collision with the segment (ORCA.cpp:124-135)
         c = cmake(V(0.0f, 0.0f), vright(segDir));
@@ -87,25 +87,25 @@ __device__ __forceinline__ bool obstacle_constraint(const ObstView& ob, int oL, 
     if (sp < 0.0f && distSqLine <= radiusSq) {  // ORCA.cpp:146-169
         if (!cvxL) return false;
         oR = oL; pR = pL; cvxR = cvxL;
-        const float leg1 = sqrtf(distSq1 - radiusSq);
-        leftLeg = vdiv(V(rp1.x * leg1 - rp1.y * clearance, rp1.x * clearance + rp1.y * leg1), distSq1);
-        rightLeg = vdiv(V(rp1.x * leg1 + rp1.y * clearance, -rp1.x * clearance + rp1.y * leg1), distSq1);
+        const float leg1 = osqrt(distSq1 - radiusSq);
+        leftLeg = ovdiv(V(rp1.x * leg1 - rp1.y * clearance, rp1.x * clearance + rp1.y * leg1), distSq1);
+        rightLeg = ovdiv(V(rp1.x * leg1 + rp1.y * clearance, -rp1.x * clearance + rp1.y * leg1), distSq1);
     } else if (sp > 1.0f && distSqLine <= radiusSq) {  // ORCA.cpp:171-183
         if (!cvxR) return false;
         oL = oR; pL = pR; cvxL = cvxR;
-        const float leg2 = sqrtf(distSq2 - radiusSq);
-        leftLeg = vdiv(V(rp2.x * leg2 - rp2.y * clearance, rp2.x * clearance + rp2.y * leg2), distSq2);
-        rightLeg = vdiv(V(rp2.x * leg2 + rp2.y * clearance, -rp2.x * clearance + rp2.y * leg2), distSq2);
+        const float leg2 = osqrt(distSq2 - radiusSq);
+        leftLeg = ovdiv(V(rp2.x * leg2 - rp2.y * clearance, rp2.x * clearance + rp2.y * leg2), distSq2);
+        rightLeg = ovdiv(V(rp2.x * leg2 + rp2.y * clearance, -rp2.x * clearance + rp2.y * leg2), distSq2);
     } else {  // ORCA.cpp:186-212
         if (cvxL) {
-            const float leg1 = sqrtf(distSq1 - radiusSq);
-            leftLeg = vdiv(V(rp1.x * leg1 - rp1.y * clearance, rp1.x * clearance + rp1.y * leg1), distSq1);
+            const float leg1 = osqrt(distSq1 - radiusSq);
+            leftLeg = ovdiv(V(rp1.x * leg1 - rp1.y * clearance, rp1.x * clearance + rp1.y * leg1), distSq1);
         } else {
             leftLeg = vmul(segDir, -1.0f);
         }
         if (cvxR) {
-            const float leg2 = sqrtf(distSq2 - radiusSq);
-            rightLeg = vdiv(V(rp2.x * leg2 + rp2.y * clearance, -rp2.x * clearance + rp2.y * leg2), distSq2);
+            const float leg2 = osqrt(distSq2 - radiusSq);
+            rightLeg = ovdiv(V(rp2.x * leg2 + rp2.y * clearance, -rp2.x * clearance + rp2.y * leg2), distSq2);
         } else {
             rightLeg = segDir;
         }
@@ -123,16 +123,16 @@ __device__ __forceinline__ bool obstacle_constraint(const ObstView& ob, int oL, 
     const v2 rightCutoff = vmul(vsub(pR, position), recip);
     const v2 cutoffVec = vsub(rightCutoff, leftCutoff);
     const bool same = (oL == oR);
-    const float t = same ? 0.5f : vdot(vsub(velocity, leftCutoff), cutoffVec) / vlen2(cutoffVec);
+    const float t = same ? 0.5f : odiv(vdot(vsub(velocity, leftCutoff), cutoffVec), vlen2(cutoffVec));
     const float tLeft = vdot(vsub(velocity, leftCutoff), leftLeg);
     const float tRight = vdot(vsub(velocity, rightCutoff), rightLeg);
 
     if ((t < 0.0f && tLeft < 0.0f) || (same && tLeft < 0.0f && tRight < 0.0f)) {  // ORCA.cpp:259-268
-        v2 unitW = vnormalized(vsub(velocity, leftCutoff));
+        v2 unitW = ovnormalized(vsub(velocity, leftCutoff));
         c = cmake(vadd(leftCutoff, vmul(vmul(unitW, recip), clearance)), unitW);
         return true;
     } else if (t > 1.0f && tRight < 0.0f) {  // ORCA.cpp:270-280
-        v2 unitW = vnormalized(vsub(velocity, rightCutoff));
+        v2 unitW = ovnormalized(vsub(velocity, rightCutoff));
         c = cmake(vadd(rightCutoff, vmul(vmul(unitW, recip), clearance)), unitW);
         return true;
     }
@@ -159,42 +159,42 @@ __device__ __forceinline__ bool obstacle_constraint(const ObstView& ob, int oL, 
 
 // One agent neighbour -> exactly one constraint (ORCA.cpp:339-423).
 __device__ __forceinline__ Cons agent_constraint(v2 position, v2 velocity, float clearance, v2 npos, v2 nvel, float nclear, float stepSize) {
-    v2 VOPos = V((npos.x - position.x) / kLookAhead, (npos.y - position.y) / kLookAhead);
-    float VOPosLength = vlen(VOPos);
+    v2 VOPos = V(odiv(npos.x - position.x, kLookAhead), odiv(npos.y - position.y, kLookAhead));
+    float VOPosLength = ovlen(VOPos);
     float combinedRadius = nclear + clearance;
-    float VORadius = combinedRadius / kLookAhead;
+    float VORadius = odiv(combinedRadius, kLookAhead);
     v2 relVel = V(velocity.x - nvel.x, velocity.y - nvel.y);
     v2 relPos = V(npos.x - position.x, npos.y - position.y);
-    float relPosLength = vlen(relPos);
+    float relPosLength = ovlen(relPos);
     if (relPosLength < combinedRadius) {  // colliding (ORCA.cpp:356-372): uses the sim step, not the look-ahead
-        v2 w = vsub(relVel, vdiv(relPos, stepSize));
-        float wLength = vlen(w);
-        v2 unitW = vdiv(w, wLength);
-        v2 U = vmul(unitW, (combinedRadius / stepSize - wLength));
+        v2 w = vsub(relVel, ovdiv(relPos, stepSize));
+        float wLength = ovlen(w);
+        v2 unitW = ovdiv(w, wLength);
+        v2 U = vmul(unitW, (odiv(combinedRadius, stepSize) - wLength));
         return cmake(vadd(velocity, vmul(U, 0.5f)), unitW);
     }
-    float tanHalfAngle = atanf(VORadius / VOPosLength);  // atan, not asin (ORCA.cpp:375-376)
+    float tanHalfAngle = atanf(odiv(VORadius, VOPosLength));  // atan, not asin (ORCA.cpp:375-376)
     // RotateVector(VOPos, +a) and RotateVector(VOPos, -a): one sincosf serves both (sin is odd, cos even, exactly)
     float sn, cs;
-    sincosf(tanHalfAngle, &sn, &cs);
+    osincos(tanHalfAngle, &sn, &cs);
     v2 VOLeftLeg = V(VOPos.x * cs - VOPos.y * sn, VOPos.x * sn + VOPos.y * cs);
     v2 VORightLeg = V(VOPos.x * cs + VOPos.y * sn, VOPos.y * cs - VOPos.x * sn);
     float sqDistFromCircleCentre = sqdist(VOPos, relVel);
     v2 base = vsub(VOLeftLeg, VOPos), chk = vsub(relVel, VOPos);
     bool liesBelow = base.x * chk.y - base.y * chk.x > 0.0f;  // IsLeftOfVector (UtilityFunctions.cpp:198-201)
     if (liesBelow) {  // ORCA.cpp:385-397
-        float distToEdge = VORadius - sqrtf(sqDistFromCircleCentre);
-        v2 lineNormal = vnormalized(vsub(relVel, VOPos));
+        float distToEdge = VORadius - osqrt(sqDistFromCircleCentre);
+        v2 lineNormal = ovnormalized(vsub(relVel, VOPos));
         return cmake(vadd(velocity, vmul(vmul(lineNormal, distToEdge), 0.5f)), lineNormal);
     }
-    v2 leftPerp = vdiv(vleft(VOPos), VOPosLength);
+    v2 leftPerp = ovdiv(vleft(VOPos), VOPosLength);
     if (vdot(leftPerp, relVel) >= 0.0f) {  // closer to the left leg (ORCA.cpp:403-412)
-        v2 ln = vnormalized(VOLeftLeg);
+        v2 ln = ovnormalized(VOLeftLeg);
         float l = vdot(relVel, ln);  // GetClosestPointOnLineThroughOrigin (UtilityFunctions.cpp:316-320)
         v2 U = vsub(vmul(ln, l), relVel);
         return cmake(vadd(velocity, vmul(U, 0.5f)), vleft(ln));
     }
-    v2 rn = vnormalized(VORightLeg);
+    v2 rn = ovnormalized(VORightLeg);
     float l = vdot(relVel, rn);
     v2 U = vsub(vmul(rn, l), relVel);
     return cmake(vadd(velocity, vmul(U, 0.5f)), vright(rn));
@@ -206,7 +206,7 @@ __device__ __forceinline__ Cons agent_constraint(v2 position, v2 velocity, float
 template <bool kSync>
 __device__ __forceinline__ int randomized_lp(const Cons* cs, int n, v2 opt, float maxSpeed, bool useDirOpt, v2& outV) {
     if (useDirOpt) outV = vmul(opt, maxSpeed);
-    else if (vlen(opt) > maxSpeed) outV = vmul(vnormalized(opt), maxSpeed);
+    else if (ovlen(opt) > maxSpeed) outV = vmul(ovnormalized(opt), maxSpeed);
     else outV = opt;
     int result = n;
     const int trips = warp_max_trip<kSync>(n);
@@ -221,7 +221,7 @@ __device__ __forceinline__ int randomized_lp(const Cons* cs, int n, v2 opt, floa
         bool bad = disc <= 0.0f;  // `return i` (ORCA.cpp:499-503)
         float left = 0.0f, right = 0.0f;
         if (!bad) {
-            const float dsq = sqrtf(disc);
+            const float dsq = osqrt(disc);
             left = -dpd - dsq;
             right = -dpd + dsq;
             for (int j = 0; j < i; j++) {  // same i for every lane in here: lock-step
@@ -232,7 +232,7 @@ __device__ __forceinline__ int randomized_lp(const Cons* cs, int n, v2 opt, floa
                     if (num < 0.0f) bad = true;  // `return i` (ORCA.cpp:526-533)
                     continue;
                 }
-                const float t = num / den;
+                const float t = odiv(num, den);
                 if (den >= 0.0f) right = (t < right) ? t : right;  // std::min(right, t)
                 else left = (left < t) ? t : left;                 // std::max(left, t)
                 if (left > right) bad = true;                      // `return i` (ORCA.cpp:546-548); monotone, so order-free
@@ -270,10 +270,10 @@ __device__ __noinline__ void randomized_lp3d(int nObst, const Cons* cs, int tota
                 if (vdot(cn(ci), cn(cj)) > 0.0f) continue;
                 pt = vmul(vadd(cp(ci), cp(cj)), 0.5f);
             } else {
-                float t = vdet(vright(cn(cj)), vsub(cp(ci), cp(cj))) / det;
+                float t = odiv(vdet(vright(cn(cj)), vsub(cp(ci), cp(cj))), det);
                 pt = vadd(cp(ci), vmul(dir, t));
             }
-            proj[np++] = cmake(pt, vnormalized(vsub(cn(cj), cn(ci))));
+            proj[np++] = cmake(pt, ovnormalized(vsub(cn(cj), cn(ci))));
         }
         const v2 temp = outV;
         if (randomized_lp<false>(proj, np, cn(ci), maxSpeed, true, outV) < np) outV = temp;
