@@ -56,3 +56,60 @@ def apply_events(sim, events):
             sim.destroy_agent(slot)
         else:
             sim.set_path(slot, path)
+
+
+def check_window_against_oracle(world, step, before, after, radius, speed, path_off, path_xy, window, margin, vel_tol, label=""):
+    """Locality check that scales to any crowd size: one tick of the agents inside `window` = (x0, y0, x1, y1) depends
+    only on the agents within their 5-NN reach, so the C oracle stepping the SUB-crowd `window + margin` must reproduce
+    what the device computed for the window's agents in the full crowd - neighbour lists, cells, attraction points and
+    preferred velocities bit for bit, velocities within `vel_tol`.
+
+    before: pos, vel, attraction, active of every slot before the tick; after: pos, vel, prefvel, attraction, active,
+    nbr, nbr_cnt, cell after it.  Returns statistics."""
+    from oracle.pyoracle import OracleSim
+
+    x0, y0, x1, y1 = window
+    p = before["pos"]
+    act = before["active"] > 0
+    member = act & (p[:, 0] >= x0 - margin) & (p[:, 0] < x1 + margin) & (p[:, 1] >= y0 - margin) & (p[:, 1] < y1 + margin)
+    members = np.flatnonzero(member)  # ascending slots: the (distance, slot id) tie-break keeps its meaning
+    inner_l = np.flatnonzero((p[members, 0] >= x0) & (p[members, 0] < x1) & (p[members, 1] >= y0) & (p[members, 1] < y1))
+    inner = members[inner_l]
+    assert len(inner) >= 50, f"{label}: window holds only {len(inner)} agents"
+    m = len(members)
+    local = np.full(len(p), -1, np.int64)
+    local[members] = np.arange(m)
+    nb = after["nbr"][inner]
+    cnt = after["nbr_cnt"][inner]
+    assert (cnt == 5).all()
+    assert (local[nb] >= 0).all(), f"{label}: margin {margin} m does not cover the 5-NN reach of the window"
+    lens = (path_off[1:] - path_off[:-1])[members]
+    off = np.zeros(m + 1, np.int32)
+    np.cumsum(lens, out=off[1:])
+    idx = np.repeat(path_off[:-1][members].astype(np.int64), lens) + (np.arange(int(lens.sum())) - np.repeat(off[:-1].astype(np.int64), lens))
+    ora = OracleSim(world, m + 8, step, "exact-knn")
+    ora.bulk_load(p[members], radius[members], speed[members], off, path_xy[idx])
+    for k, s in enumerate(members):
+        ora.set_kinematics(k, p[s], before["vel"][s])
+        ora.set_attraction(k, before["attraction"][s])
+    ids_o, cnt_o = ora.query_neighbors(m)
+    cells_o = ora.query_cells(p[inner])
+    ora.step(1)
+    st = ora.state(m)
+    ora.close()
+    assert np.array_equal(cnt_o[inner_l], cnt), f"{label}: neighbour counts"
+    assert np.array_equal(members[ids_o[inner_l]], nb), f"{label}: neighbour lists"
+    assert np.array_equal(st["active"][inner_l] > 0, after["active"][inner] > 0), f"{label}: active flags"
+    alive = st["active"][inner_l] > 0
+    cell = after["cell"][inner]
+    evaluated = cell != -2
+    assert np.array_equal(cell[evaluated], cells_o[evaluated]), f"{label}: ECM cells"
+    assert_bits_equal(after["attraction"][inner], st["attraction"][inner_l], f"{label}: attraction points")
+    assert_bits_equal(after["prefvel"][inner][alive], st["prefvel"][inner_l][alive], f"{label}: preferred velocities")
+    dv = np.abs(after["vel"][inner][alive] - st["vel"][inner_l][alive])
+    assert dv.max() <= vel_tol, f"{label}: max |dv| = {dv.max()}"
+    dp = np.abs(after["pos"][inner][alive] - st["pos"][inner_l][alive])
+    assert dp.max() <= vel_tol, f"{label}: max |dp| = {dp.max()}"
+    same = (after["vel"][inner][alive].view(np.uint32) == st["vel"][inner_l][alive].view(np.uint32)).all(axis=1)
+    return {"members": m, "inner": int(len(inner)), "evaluated_cells": int(evaluated.sum()), "max_dv": float(dv.max()),
+            "velocity_rows_bit_identical": float(same.mean()), "moving": float((np.linalg.norm(before["vel"][inner], axis=1) > 0.1).mean())}
