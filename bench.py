@@ -304,6 +304,10 @@ def run_ours(args):
         sim = gpu.GpuSim(w, n, float(S.DT), device=local, record_neighbors=False, neighbor_cell=args.cell, static_bin=args.bin,
                          path_pool_points=int(off[-1] * 1.25) + 4096)
         sim.bulk_load(c.pos, c.radius, c.speed, off, pxy)
+        if args.neighbors == "kdtree":
+            sim.set_neighbor_mode(gpu.NEIGHBORS_KDTREE)
+    if args.neighbors == "kdtree" and world > 1:
+        raise SystemExit("--neighbors kdtree runs on one GPU")
     mean_p = float(np.diff(off).mean())
 
     def barrier():
@@ -536,6 +540,9 @@ def run_ours(args):
                        "static_bin": st1["static_bin"]},
             "gpu_launches": int(launches), "clocks": clk,
             "counters": {k: int(st1[k]) for k in ("knn_fallbacks", "obstacle_overflows", "lp3d_runs", "location_failures", "replans")}}
+    if args.neighbors == "kdtree":
+        line["config"]["neighbors"] = "kdtree (the reference's own lists; parity mode)"
+        line["counters"].update({k: int(st1[k]) for k in ("kd_median_ties", "kd_small_ties")})
     if world > 1:
         line["counters"] = dict(job_counters, scope="all ranks, whole run")
         line["config"]["halo_m"] = float(sim.halo)
@@ -565,6 +572,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cell", type=float, default=0.0, help="neighbour grid cell (0 = from crowd density)")
     ap.add_argument("--bin", type=float, default=0.0, help="static bin edge (0 = from the ECM)")
+    ap.add_argument("--neighbors", default="exact", choices=["exact", "kdtree"],
+                    help="kdtree: the reference's own KD-tree lists (parity mode, single GPU; DESIGN.md 5a) - a cost figure, not the headline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
