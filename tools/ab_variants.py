@@ -35,7 +35,9 @@ def main():
         os.environ.update(env)
         gpu._lib = None
         gpu.LIB_PATH = os.path.abspath(path) if path else os.path.join(os.path.dirname(gpu.__file__), "libecmgpu.so")
-        sim = gpu.GpuSim(w, n, float(S.DT), device=0, record_neighbors=False, path_pool_points=int(off[-1]) + 8 * n + 4096)
+        # AB_CELL: neighbour-grid cell edge in metres (default: chosen from the crowd's density)
+        sim = gpu.GpuSim(w, n, float(S.DT), device=0, record_neighbors=False, path_pool_points=int(off[-1]) + 8 * n + 4096,
+                         neighbor_cell=float(os.environ.get("AB_CELL", "0")))
         sim.bulk_load(c.pos, c.radius, c.speed, off, pxy)
         sim.update(5 + int(os.environ.get("AB_PREROLL", "0")))  # AB_PREROLL: let the crowd congest first (tick cost drifts)
         sim.sync()
@@ -64,7 +66,7 @@ def main():
             d = (pos.astype(np.float64) - ref.astype(np.float64))
             gap = {"rms_m": float(np.sqrt((d ** 2).sum(axis=1).mean())), "max_m": float(np.abs(d).max()),
                    "rows_bit_identical": float((pos.view(np.uint32) == ref.view(np.uint32)).all(axis=1).mean())}
-        print(json.dumps({"variant": name, "env": env, "ms_per_tick": round(best, 4), "grid": round(acc["grid"], 4),
+        print(json.dumps({"variant": name, "env": env, "cell": sim.stats()["neighbor_cell"], "ms_per_tick": round(best, 4), "grid": round(acc["grid"], 4),
                           "attract": round(acc["attract"], 4), "orca": round(acc["orca"], 4), "tick_profiled": round(acc["tick"], 4),
                           "same_state_as_first": same, "position_gap_vs_first": gap}), flush=True)
         sim.close()

@@ -1,0 +1,60 @@
+#!/usr/bin/env bash
+# One gpurun call that measures everything prepared on the CPU (run from the repo root on a B200 box):
+#
+#   gpurun --timeout 2400 -- 'bash tools/gpu_session.sh r02a'
+#
+# Steps (each under its own timeout, all output under gpurun_out/<tag>_*):
+#   1. pytest -m gpu                      the parity suite incl. the KD-tree mode and the full-size windows
+#   2. bench.py                           the headline line (1 GPU, c3_1m)
+#   3. tools/ab_variants.py               base vs the prepared build variants, one process, same box
+#   4. the same on the congested crowd    (AB_PREROLL=400)
+#   5. cell-size sweep for the pruning variants (smaller cells pay only with pruning)
+#   6. parity statistics of the orca_fast variant (NOT bit-exact by design)
+#   7. bench.py --neighbors kdtree        cost of the parity mode
+#   8. ncu launch list + one --set full capture of k_orca / k_attract of the default build
+# Nothing here changes GPU clocks.  Numbers printed under ncu are never bench values.
+set -u
+TAG=${1:-session}
+OUT=gpurun_out
+mkdir -p "$OUT"
+export PYTHONUNBUFFERED=1
+step() { echo "=== $1 ($(date +%T))" | tee -a "$OUT/${TAG}_session.log"; }
+
+step "build"
+python -c "import __graft_entry__ as g; g.build()" >>"$OUT/${TAG}_session.log" 2>&1
+python tools/build_variants.py >"$OUT/${TAG}_variants_build.log" 2>&1
+
+step "pytest -m gpu"
+timeout 1500 python -m pytest tests -m gpu -q -s -x >"$OUT/${TAG}_gpu_tests.log" 2>&1
+echo "pytest exit $?" | tee -a "$OUT/${TAG}_session.log"
+
+step "bench"
+timeout 600 python bench.py >"$OUT/${TAG}_bench.json" 2>"$OUT/${TAG}_bench.err"
+
+V="base knn_prune=variants/libecmgpu_knn_prune.so knn_twopass=variants/libecmgpu_knn_twopass.so knn_twopass_prune=variants/libecmgpu_knn_twopass_prune.so orca_fast=variants/libecmgpu_orca_fast.so"
+step "A/B from rest"
+timeout 900 python tools/ab_variants.py $V >"$OUT/${TAG}_ab_rest.jsonl" 2>"$OUT/${TAG}_ab_rest.err"
+step "A/B congested (400 ticks of pre-roll)"
+AB_PREROLL=400 timeout 1200 python tools/ab_variants.py $V >"$OUT/${TAG}_ab_congested.jsonl" 2>"$OUT/${TAG}_ab_congested.err"
+
+step "cell sweep with pruning"
+: >"$OUT/${TAG}_ab_cells.jsonl"
+for cell in 2.0 2.4 2.8; do
+  AB_CELL=$cell timeout 600 python tools/ab_variants.py base knn_prune=variants/libecmgpu_knn_prune.so knn_twopass_prune=variants/libecmgpu_knn_twopass_prune.so \
+      >>"$OUT/${TAG}_ab_cells.jsonl" 2>>"$OUT/${TAG}_ab_cells.err"
+done
+
+step "orca_fast parity statistics"
+ECMGPU_LIB=$PWD/variants/libecmgpu_orca_fast.so timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -s \
+    -k "lockstep or free_running or rms_600" >"$OUT/${TAG}_orca_fast_parity.log" 2>&1
+
+step "bench --neighbors kdtree"
+timeout 600 python bench.py --neighbors kdtree --no-cpu --steady-tick 0 --steps 20 >"$OUT/${TAG}_bench_kdtree.json" 2>"$OUT/${TAG}_bench_kdtree.err"
+
+step "ncu launch list"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/${TAG}_launches.csv" \
+    python bench.py --steps 2 --warmup 3 --no-cpu --steady-tick 0 >"$OUT/${TAG}_ncu_launch_bench.log" 2>&1
+step "ncu --set full (k_orca, k_attract)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_orca|k_attract|k_scatter" --launch-skip 30 -c 6 \
+    -o "$OUT/${TAG}_full" -f python bench.py --steps 4 --warmup 5 --no-cpu --steady-tick 0 >"$OUT/${TAG}_ncu_full_bench.log" 2>&1
+step "done"
