@@ -470,6 +470,37 @@ __global__ void __launch_bounds__(128) k_knn_query(TickView t) {
     }
 }
 
+// Simulator::ValidSpawnLocation (Simulator.cpp:295-311) for a batch of candidate points on the grid of the CURRENT
+// positions: valid iff no active agent centre lies strictly closer than the clearance, with the
+// reference's expression fl(fl(dx*dx) + fl(dy*dy)) < fl(c*c), dx = location.x - position.x.  Only the cells the
+// clearance box touches (plus one cell of slack for the rounding of the box corners) are scanned; agents beyond the
+// grid sit in the border cells of their clamped coordinates, which the clamped box then covers too.
+__global__ void __launch_bounds__(128) k_valid_spawn(GridView g, int n, const float2* __restrict__ xy, const float* __restrict__ clearance,
+                                                      unsigned char* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const v2 loc = xy[i];
+    const float c = clearance[i];
+    const float c2 = c * c;
+    int xa, ya, xb, yb;
+    g.cell_of(V(loc.x - c, loc.y - c), xa, ya);
+    g.cell_of(V(loc.x + c, loc.y + c), xb, yb);
+    if (!(c == c) || !(loc.x == loc.x) || !(loc.y == loc.y)) { xa = 0; ya = 0; xb = g.w - 1; yb = g.h - 1; }  // NaN: scan everything
+    xa = max(xa - 1, 0); ya = max(ya - 1, 0);
+    xb = min(xb + 1, g.w - 1); yb = min(yb + 1, g.h - 1);
+    bool ok = true;
+    for (int y = ya; y <= yb && ok; y++) {
+        const int a = __ldg(&g.cell_start[y * g.w + xa]);
+        const int b = __ldg(&g.cell_start[y * g.w + xb + 1]);
+        for (int k = a; k < b; k++) {
+            const v2 pj = __ldg(&g.s_pos[k]);
+            const float dx = loc.x - pj.x, dy = loc.y - pj.y;
+            if (dx * dx + dy * dy < c2) { ok = false; break; }
+        }
+    }
+    out[i] = ok ? 1 : 0;
+}
+
 __global__ void k_find_obstacles(ObstView ob, BinView bins, float2 pos, float range2, int* out, int cap, int* out_n) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *out_n = find_obstacles<false>(ob, bins, pos, range2, out, cap);
 }

@@ -1521,6 +1521,44 @@ int ecmgpu_find_obstacles(ecmgpu_sim* s, int slot, int* out_ids, int cap, int* o
     return ECMGPU_OK;
 }
 
+int ecmgpu_valid_spawn_locations(ecmgpu_sim* s, int n, const float* xy, const float* clearance, uint8_t* out_valid) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!xy || !clearance || !out_valid))) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_valid_spawn_locations: bad arguments");
+    if (n == 0) return ECMGPU_OK;
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    if (s->n_slots == 0) {  // nobody to collide with (ensure_ready may have no crowd to size the grid from yet)
+        memset(out_valid, 1, (size_t)n);
+        return ECMGPU_OK;
+    }
+    if (s->strips_on && s->local_transport && s->n_ranks > 1)
+        return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_valid_spawn_locations is not available with in-process strips");
+    int rc = ensure_ready(s);
+    if (rc) return rc;
+    TickView t = make_view(s);
+    t.gather = 0;  // k_scatter writes the full snapshot rows
+    if (s->strips_on) {
+        rc = enqueue_pack(s, t);
+        if (rc) return rc;
+        rc = enqueue_exchange(s, t);
+        if (rc) return rc;
+    }
+    rc = enqueue_grid_build(s, t);
+    if (rc) return rc;
+    DevBuf<float2> d_xy;
+    DevBuf<float> d_c;
+    DevBuf<unsigned char> d_out;
+    CUDA_TRY(s, d_xy.alloc(n)); CUDA_TRY(s, d_c.alloc(n)); CUDA_TRY(s, d_out.alloc(n));
+    CUDA_TRY(s, cudaMemcpyAsync(d_xy.p, xy, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(d_c.p, clearance, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+    k_valid_spawn<<<div_up(n, 128), 128, 0, s->stream>>>(t.grid, n, d_xy.p, d_c.p, d_out.p);
+    s->launches++;
+    CUDA_TRY(s, cudaGetLastError());
+    CUDA_TRY(s, cudaMemcpyAsync(out_valid, d_out.p, (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    d_xy.free(); d_c.free(); d_out.free();
+    return ECMGPU_OK;
+}
+
 int ecmgpu_set_neighbor_mode(ecmgpu_sim* s, int mode) {
     if (!s) return ECMGPU_ERR_INVALID;
     if (mode != ECMGPU_NEIGHBORS_EXACT && mode != ECMGPU_NEIGHBORS_KDTREE) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_neighbor_mode: unknown mode");

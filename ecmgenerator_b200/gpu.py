@@ -39,7 +39,7 @@ EXPORTS = [
     "ecmgpu_locate", "ecmgpu_retract", "ecmgpu_find_neighbors", "ecmgpu_find_obstacles", "ecmgpu_get_stats",
     "ecmgpu_last_tick_ms", "ecmgpu_set_profiling", "ecmgpu_mark", "ecmgpu_mark_elapsed_ms", "ecmgpu_stream", "ecmgpu_comm_unique_id", "ecmgpu_comm_init",
     "ecmgpu_comm_set_strips", "ecmgpu_comm_init_local", "ecmgpu_update_phase", "ecmgpu_update_io", "ecmgpu_update_io_owned", "ecmgpu_io_wait", "ecmgpu_comm_p2p_export", "ecmgpu_comm_p2p_connect",
-    "ecmgpu_set_neighbor_mode",
+    "ecmgpu_set_neighbor_mode", "ecmgpu_valid_spawn_locations",
 ]
 
 
@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
         L.ecmgpu_update_io.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(C.c_uint64)]
         L.ecmgpu_io_wait.argtypes = [vp, C.c_uint64]
         L.ecmgpu_set_neighbor_mode.argtypes = [vp, C.c_int]
+        L.ecmgpu_valid_spawn_locations.argtypes = [vp, C.c_int, f32p, f32p, u8p]
         L.ecmgpu_update_io_owned.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
@@ -333,6 +334,14 @@ class GpuSim:
         cnt = np.full(n, -1, np.int32)
         self._ck(self.L.ecmgpu_find_neighbors(self.h, n, _p(ids, i32p), _p(cnt, i32p)))
         return ids, cnt
+
+    def valid_spawn_locations(self, xy, clearance):
+        """Simulator::ValidSpawnLocation for a batch of points on the current positions (uint8 flags)."""
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        cl = np.ascontiguousarray(np.broadcast_to(np.asarray(clearance, np.float32), (len(xy),)))
+        out = np.zeros(len(xy), np.uint8)
+        self._ck(self.L.ecmgpu_valid_spawn_locations(self.h, len(xy), _p(xy, f32p), _p(cl, f32p), _p(out, u8p)))
+        return out
 
     def set_neighbor_mode(self, mode: int):
         """NEIGHBORS_EXACT (default) or NEIGHBORS_KDTREE: the reference's own KD-tree lists (parity mode)."""

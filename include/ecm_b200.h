@@ -165,6 +165,14 @@ int ecmgpu_find_neighbors(ecmgpu_sim* sim, int count, int* out_ids5, int* out_co
 /* Simulator::FindNearestObstacles with ORCA's range for one slot; returns the number found. */
 int ecmgpu_find_obstacles(ecmgpu_sim* sim, int slot, int* out_ids, int cap, int* out_n);
 
+/* Simulator::ValidSpawnLocation (Simulator.cpp:295-311) for n candidate points at once, on the CURRENT positions:
+ * out_valid[i] = 1 iff no active agent centre lies strictly closer to xy[i] than clearance[i] (the reference's float
+ * expression).  Uses the neighbour grid instead of the reference's scan over every agent; candidates of one batch do
+ * not see each other (a host that spawns several agents per tick checks those few against each other itself, as
+ * UpdateSpawnAreas does one by one, Simulator.cpp:494-536).  With strips: against the agents this handle holds
+ * (owned + halo), and - like ecmgpu_find_neighbors - a collective call: every rank runs the halo exchange. */
+int ecmgpu_valid_spawn_locations(ecmgpu_sim* sim, int n, const float* xy, const float* clearance, uint8_t* out_valid);
+
 /* -- neighbour mode ---------------------------------------------------------------------------
  * ECMGPU_NEIGHBORS_EXACT (default): the exact 5-NN contract of DESIGN.md on the per-tick uniform grid.
  * ECMGPU_NEIGHBORS_KDTREE: the reference's own lists - a median-split tree built like KDTree::Construct

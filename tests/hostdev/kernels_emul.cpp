@@ -367,6 +367,14 @@ void emu_query_neighbors_kd(void* h, int* ids, int* cnt) {
     memcpy(cnt, e->nbr_cnt.data(), 4 * (size_t)e->n);
 }
 
+// ecmgpu_valid_spawn_locations
+void emu_valid_spawn(void* h, int n, const float* xy, const float* clearance, unsigned char* out) {
+    Emu* e = (Emu*)h;
+    TickView t = e->view();
+    emu_grid_build(e, t);
+    launch(n, [&] { k_valid_spawn(t.grid, n, (const float2*)xy, clearance, out); });
+}
+
 void emu_read(void* h, float* pos, float* vel, float* pref, float* attr, float* force, unsigned char* active, int* nbr, int* nbr_cnt,
               unsigned* status, int* cell) {
     Emu* e = (Emu*)h;

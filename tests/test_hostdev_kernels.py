@@ -54,6 +54,7 @@ def load_emu():
     L.emu_exchange.argtypes = [vp, vp, vp]
     L.emu_tick.argtypes = [vp]
     L.emu_tick_kd.argtypes = [vp]
+    L.emu_valid_spawn.argtypes = [vp, C.c_int, f32p, f32p, u8p]
     L.emu_kd_reset.argtypes = [vp]
     L.emu_query_neighbors_kd.argtypes = [vp, i32p, i32p]
     L.emu_read.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, u8p, i32p, i32p, u32p, i32p]
@@ -249,6 +250,37 @@ def test_owned_record_kernels(emu):
     assert_bits_equal(st2["pos"][r["slot"], 0], st["pos"][r["slot"], 0] + np.float32(1.0), "applied x")
     assert st2["pos"][7, 0] == st["pos"][7, 0]
     d.close()
+
+
+def test_valid_spawn_kernel_equals_the_reference_scan(emu):
+    """k_valid_spawn (grid) against Simulator::ValidSpawnLocation's scan over every agent, restated in float32."""
+    g = Golden("c2_small")
+    rng = np.random.default_rng(21)
+    pos = g.crowd.pos
+    for cell in (0.6, 3.0, 40.0):
+        d = EmuDevice(emu, g, cell)
+        d.destroy_agent(5)  # an inactive agent must not block a spawn
+        act = np.ones(g.n, bool)
+        act[5] = False
+        x0, y0, x1, y1 = (float(v) for v in g.world.bbox)
+        q = np.concatenate([
+            rng.uniform([x0 - 30, y0 - 30], [x1 + 30, y1 + 30], size=(3000, 2)),          # anywhere, also outside the grid
+            pos[rng.integers(0, g.n, 1500)] + rng.normal(0, 0.4, size=(1500, 2)),          # close to agents
+            pos[:200] + np.float32([0.5, 0.0]), pos[:200] - np.float32([0.0, 0.25]),       # at (about) the clearance exactly
+            pos[5:6],                                                                       # on top of the inactive agent
+        ]).astype(np.float32)
+        cl = rng.choice(np.float32([0.25, 0.5, 1.0, 7.5]), size=len(q)).astype(np.float32)
+        cl[-1] = 0.5
+        out = np.zeros(len(q), np.uint8)
+        emu.emu_valid_spawn(d.h, len(q), _p(q, f32p), _p(cl, f32p), _p(out, u8p))
+        dx = q[:, None, 0] - pos[None, act, 0]
+        dy = q[:, None, 1] - pos[None, act, 1]
+        d2 = dx * dx + dy * dy  # float32 throughout: fl(fl(dx*dx) + fl(dy*dy))
+        assert d2.dtype == np.float32
+        want = ~(d2 < (cl * cl)[:, None]).any(axis=1)
+        assert np.array_equal(out > 0, want), f"cell {cell}: {int((want != (out > 0)).sum())} of {len(q)} answers differ"
+        assert 0.2 < want.mean() < 0.95
+        d.close()
 
 
 def _gloo_strip_worker(rank, world, port, name, q):
