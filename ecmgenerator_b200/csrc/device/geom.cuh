@@ -13,6 +13,7 @@
 namespace ecm {
 
 constexpr float kEpsilon = 0.0001f;   // Configuration.h:14
+constexpr float kMaxFloat = 3.402823466e+38f;  // Utility::MAX_FLOAT (Configuration.h:11)
 constexpr float kLookAhead = 10.0f;   // ORCA.h:102-103 (agents and obstacles)
 constexpr int kK = 5;                 // Simulator.cpp:55
 

@@ -34,7 +34,6 @@
 
 namespace ecm {
 
-constexpr float kMaxFloat = 3.402823466e+38f;  // Utility::MAX_FLOAT (Configuration.h:11)
 constexpr int kKdDead = -1;
 
 // float -> unsigned with the same order (negative values reversed below the positive ones)

@@ -21,6 +21,7 @@
 
 #include "device/strips.cuh"
 #include "device/kdtree.cuh"
+#include "device/planner.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -134,6 +135,17 @@ struct ecmgpu_sim {
     DevBuf<unsigned char> d_kd_sort_tmp;
     size_t kd_sort_tmp_bytes = 0;
     int kd_cap = 0;
+
+    // ---- batched path planning on the device (device/planner.cuh): topology + per-worker scratch, allocated on first use
+    DevBuf<float> d_vert_clear;
+    DevBuf<int> d_vert_he, d_he_next;
+    bool have_topology = false;
+    DevBuf<float> d_pl_g, d_pl_f;
+    DevBuf<int> d_pl_parent, d_pl_heap, d_pl_touched, d_pl_vpath, d_pl_epath;
+    DevBuf<unsigned char> d_pl_visited;
+    DevBuf<float4> d_pl_portals;
+    DevBuf<float2> d_pl_out;
+    int pl_workers = 0, pl_cap_push = 0, pl_cap_path = 0, pl_cap_portals = 0, pl_cap_out = 0;
 
     // ---- bookkeeping
     uint64_t ticks = 0, launches = 0;
@@ -646,6 +658,57 @@ int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
     return ECMGPU_OK;
 }
 
+// ---- batched path planning (device/planner.cuh) ----------------------------------------------------
+void plan_free(ecmgpu_sim* s) {
+    s->d_pl_g.free(); s->d_pl_f.free(); s->d_pl_parent.free(); s->d_pl_heap.free(); s->d_pl_touched.free(); s->d_pl_vpath.free();
+    s->d_pl_epath.free(); s->d_pl_visited.free(); s->d_pl_portals.free(); s->d_pl_out.free();
+    s->pl_workers = 0;
+}
+
+PlanScratch make_plan_scratch(ecmgpu_sim* s) {
+    PlanScratch sc;
+    sc.n_workers = s->pl_workers;
+    sc.cap_push = s->pl_cap_push; sc.cap_path = s->pl_cap_path; sc.cap_portals = s->pl_cap_portals; sc.cap_out = s->pl_cap_out;
+    sc.g = s->d_pl_g.p; sc.f = s->d_pl_f.p; sc.parent = s->d_pl_parent.p; sc.visited = s->d_pl_visited.p;
+    sc.heap = s->d_pl_heap.p; sc.touched = s->d_pl_touched.p; sc.vpath = s->d_pl_vpath.p; sc.epath = s->d_pl_epath.p;
+    sc.portals = s->d_pl_portals.p; sc.out = s->d_pl_out.p;
+    return sc;
+}
+
+// Per-worker scratch for `want` concurrent queries, within a memory budget (env ECMGPU_PLAN_MB, default 12 GB).
+int plan_alloc(ecmgpu_sim* s, int want) {
+    const size_t nV = (size_t)s->n_vertices, nE = (size_t)s->n_edges;
+    const int cap_push = (int)(2 * nE + 4);                    // a query pushes at most once per directed edge, plus the two start vertices
+    const int cap_path = (int)std::min<size_t>(nV + 2, 2048);  // vertices of one A* path
+    const int cap_portals = 8192, cap_out = 1024;
+    const size_t per_worker = nV * 13 + (size_t)cap_push * 8 + (size_t)cap_path * 8 + (size_t)cap_portals * 16 + (size_t)cap_out * 8;
+    size_t budget = (size_t)12 << 30;
+    if (const char* e = getenv("ECMGPU_PLAN_MB")) budget = (size_t)std::max(16, atoi(e)) << 20;
+    int workers = (int)std::min<size_t>({(size_t)want, (size_t)148 * 128, std::max<size_t>(budget / per_worker, 32)});
+    workers = div_up(workers, 32) * 32;
+    if (s->pl_workers >= workers) return ECMGPU_OK;
+    plan_free(s);
+    const size_t w = (size_t)workers;
+    CUDA_TRY(s, s->d_pl_g.alloc(w * nV)); CUDA_TRY(s, s->d_pl_f.alloc(w * nV)); CUDA_TRY(s, s->d_pl_parent.alloc(w * nV));
+    CUDA_TRY(s, s->d_pl_visited.alloc(w * nV));
+    CUDA_TRY(s, s->d_pl_heap.alloc(w * cap_push)); CUDA_TRY(s, s->d_pl_touched.alloc(w * cap_push));
+    CUDA_TRY(s, s->d_pl_vpath.alloc(w * cap_path)); CUDA_TRY(s, s->d_pl_epath.alloc(w * cap_path));
+    CUDA_TRY(s, s->d_pl_portals.alloc(w * cap_portals)); CUDA_TRY(s, s->d_pl_out.alloc(w * cap_out));
+    s->pl_workers = workers;
+    s->pl_cap_push = cap_push; s->pl_cap_path = cap_path; s->pl_cap_portals = cap_portals; s->pl_cap_out = cap_out;
+    k_plan_init<<<148 * 8, 256, 0, s->stream>>>(make_plan_scratch(s), (int)nV);
+    s->launches++;
+    CUDA_TRY(s, cudaGetLastError());
+    return ECMGPU_OK;
+}
+
+int ensure_bins(ecmgpu_sim* s) {
+    if (!s->have_ecm) return fail(s, ECMGPU_ERR_INVALID, "no ECM: call ecmgpu_set_ecm first");
+    const float want = std::max(s->prm.max_obstacle_range > 0 ? s->prm.max_obstacle_range : 0.0f, s->tracked_range);
+    if (s->bins_dirty || want > s->built_range) return build_bins(s);
+    return ECMGPU_OK;
+}
+
 // ---- faithful KD-tree neighbour mode (device/kdtree.cuh) -----------------------------------------
 // Levels of a median-split tree over n agents: the smallest L with 2^L - 1 >= n.
 int kd_levels(int n) {
@@ -937,6 +1000,8 @@ void ecmgpu_destroy(ecmgpu_sim* s) {
     s->d_fb_list.free(); s->d_ev_replan.free(); s->d_ev_destroyed.free(); s->d_s_pos.free(); s->d_s_vel.free();
     s->d_s_pref.free(); s->d_s_rad.free(); s->d_s_spd.free(); s->d_s_alive.free(); s->d_counters.free();
     kd_free(s);
+    plan_free(s);
+    s->d_vert_clear.free(); s->d_vert_he.free(); s->d_he_next.free();
     comm_teardown(s);
     for (int g = 0; g < 2; g++) {
         if (s->graph_exec[g]) cudaGraphExecDestroy(s->graph_exec[g]);
@@ -963,7 +1028,7 @@ int ecmgpu_set_ecm(ecmgpu_sim* s, const float bbox[4], int nV, const float* vert
                    const int* edge_v, const float* edge_cl) {
     if (!s) return ECMGPU_ERR_INVALID;
     if (!bbox || nV <= 0 || nE <= 0 || !vert_xy || !edge_v || !edge_cl) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_ecm: bad arguments");
-    (void)vert_clear;  // vertex clearance is used by the planner (host) only
+    // vertex clearance is used by the planners only (the host's, and ecmgpu_plan_paths)
     for (int e = 0; e < 2 * nE; e++)
         if (edge_v[e] < 0 || edge_v[e] >= nV) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_ecm: edge vertex index out of range");
     CUDA_TRY(s, cudaSetDevice(s->prm.device));
@@ -979,6 +1044,13 @@ int ecmgpu_set_ecm(ecmgpu_sim* s, const float bbox[4], int nV, const float* vert
     CUDA_TRY(s, cudaMemcpyAsync(s->d_vert_xy.p, vert_xy, sizeof(float) * 2 * nV, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(s, cudaMemcpyAsync(s->d_edge_v.p, edge_v, sizeof(int) * 2 * nE, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(s, cudaMemcpyAsync(s->d_edge_cl.p, edge_cl, sizeof(float) * 8 * nE, cudaMemcpyHostToDevice, s->stream));
+    s->d_vert_clear.free();
+    if (vert_clear) {
+        CUDA_TRY(s, s->d_vert_clear.alloc(nV));
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_vert_clear.p, vert_clear, sizeof(float) * nV, cudaMemcpyHostToDevice, s->stream));
+    }
+    s->have_topology = false;  // belongs to the previous graph
+    plan_free(s);
     CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     s->have_ecm = true;
     s->bins_dirty = true;
@@ -1518,6 +1590,76 @@ int ecmgpu_find_obstacles(ecmgpu_sim* s, int slot, int* out_ids, int cap, int* o
     const int m = std::min(*out_n, cap);
     if (m > 0) CUDA_TRY(s, cudaMemcpy(out_ids, dout.p, sizeof(int) * m, cudaMemcpyDeviceToHost));
     dout.free(); dn.free();
+    return ECMGPU_OK;
+}
+
+int ecmgpu_set_ecm_topology(ecmgpu_sim* s, const int* vert_he, const int* he_next) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (!s->have_ecm) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_ecm_topology: call ecmgpu_set_ecm first");
+    if (!vert_he || !he_next) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_ecm_topology: null argument");
+    const int nV = s->n_vertices, nH = 2 * s->n_edges;
+    auto source = [&](int he) { return (he & 1) ? s->h_edge_v[2 * (he >> 1) + 1] : s->h_edge_v[2 * (he >> 1)]; };
+    for (int v = 0; v < nV; v++)
+        if (vert_he[v] < 0 || vert_he[v] >= nH || source(vert_he[v]) != v)
+            return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_ecm_topology: vert_he[v] must be a half-edge leaving v");
+    for (int h = 0; h < nH; h++)
+        if (he_next[h] < 0 || he_next[h] >= nH || source(he_next[h]) != source(h))
+            return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_ecm_topology: he_next must stay on the half-edge's source vertex");
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    CUDA_TRY(s, s->d_vert_he.alloc(nV)); CUDA_TRY(s, s->d_he_next.alloc(nH));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_vert_he.p, vert_he, sizeof(int) * nV, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_he_next.p, he_next, sizeof(int) * nH, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    s->have_topology = true;
+    return ECMGPU_OK;
+}
+
+int ecmgpu_plan_paths(ecmgpu_sim* s, int n, const float* start_xy, const float* goal_xy, const float* clearance, int* out_off, int* out_len,
+                      uint8_t* out_status, float* out_xy, int cap_points, int* out_points) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (n < 0 || cap_points < 0 || (n > 0 && (!start_xy || !goal_xy || !clearance || !out_off || !out_len || (cap_points > 0 && !out_xy))))
+        return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_plan_paths: bad arguments");
+    if (!s->have_topology || !s->d_vert_clear.p)
+        return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_plan_paths: needs vertex clearances (ecmgpu_set_ecm) and ecmgpu_set_ecm_topology");
+    if (out_points) *out_points = 0;
+    if (n == 0) return ECMGPU_OK;
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    int rc = ensure_bins(s);
+    if (rc) return rc;
+    rc = plan_alloc(s, n);
+    if (rc) return rc;
+    const TickView t = make_view(s);
+    PlanView w;
+    w.ecm = t.ecm;
+    w.bins = t.bins;
+    w.vert_clear = s->d_vert_clear.p;
+    w.vert_he = s->d_vert_he.p;
+    w.he_next = s->d_he_next.p;
+    DevBuf<float2> d_start, d_goal, d_pool;
+    DevBuf<float> d_cl;
+    DevBuf<int> d_off, d_len, d_cursor;
+    DevBuf<unsigned char> d_st;
+    CUDA_TRY(s, d_start.alloc(n)); CUDA_TRY(s, d_goal.alloc(n)); CUDA_TRY(s, d_cl.alloc(n)); CUDA_TRY(s, d_off.alloc(n));
+    CUDA_TRY(s, d_len.alloc(n)); CUDA_TRY(s, d_st.alloc(n)); CUDA_TRY(s, d_cursor.alloc(1)); CUDA_TRY(s, d_pool.alloc(std::max(cap_points, 1)));
+    CUDA_TRY(s, cudaMemcpyAsync(d_start.p, start_xy, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(d_goal.p, goal_xy, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(d_cl.p, clearance, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemsetAsync(d_cursor.p, 0, sizeof(int), s->stream));
+    const PlanScratch sc = make_plan_scratch(s);
+    k_plan_paths<<<div_up(sc.n_workers, 128), 128, 0, s->stream>>>(w, sc, n, d_start.p, d_goal.p, d_cl.p, d_off.p, d_len.p, d_st.p, d_pool.p,
+                                                                   cap_points, d_cursor.p);
+    s->launches++;
+    CUDA_TRY(s, cudaGetLastError());
+    int used = 0;
+    CUDA_TRY(s, cudaMemcpyAsync(&used, d_cursor.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(out_off, d_off.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(out_len, d_len.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    if (out_status) CUDA_TRY(s, cudaMemcpyAsync(out_status, d_st.p, (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    const int have = std::min(used, cap_points);
+    if (have > 0) CUDA_TRY(s, cudaMemcpy(out_xy, d_pool.p, sizeof(float2) * (size_t)have, cudaMemcpyDeviceToHost));
+    if (out_points) *out_points = used;
+    d_start.free(); d_goal.free(); d_pool.free(); d_cl.free(); d_off.free(); d_len.free(); d_cursor.free(); d_st.free();
     return ECMGPU_OK;
 }
 

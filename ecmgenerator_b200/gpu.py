@@ -39,7 +39,7 @@ EXPORTS = [
     "ecmgpu_locate", "ecmgpu_retract", "ecmgpu_find_neighbors", "ecmgpu_find_obstacles", "ecmgpu_get_stats",
     "ecmgpu_last_tick_ms", "ecmgpu_set_profiling", "ecmgpu_mark", "ecmgpu_mark_elapsed_ms", "ecmgpu_stream", "ecmgpu_comm_unique_id", "ecmgpu_comm_init",
     "ecmgpu_comm_set_strips", "ecmgpu_comm_init_local", "ecmgpu_update_phase", "ecmgpu_update_io", "ecmgpu_update_io_owned", "ecmgpu_io_wait", "ecmgpu_comm_p2p_export", "ecmgpu_comm_p2p_connect",
-    "ecmgpu_set_neighbor_mode", "ecmgpu_valid_spawn_locations",
+    "ecmgpu_set_neighbor_mode", "ecmgpu_valid_spawn_locations", "ecmgpu_set_ecm_topology", "ecmgpu_plan_paths",
 ]
 
 
@@ -111,6 +111,8 @@ def lib() -> C.CDLL:
         L.ecmgpu_io_wait.argtypes = [vp, C.c_uint64]
         L.ecmgpu_set_neighbor_mode.argtypes = [vp, C.c_int]
         L.ecmgpu_valid_spawn_locations.argtypes = [vp, C.c_int, f32p, f32p, u8p]
+        L.ecmgpu_set_ecm_topology.argtypes = [vp, i32p, i32p]
+        L.ecmgpu_plan_paths.argtypes = [vp, C.c_int, f32p, f32p, f32p, i32p, i32p, u8p, f32p, C.c_int, i32p]
         L.ecmgpu_update_io_owned.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
@@ -165,6 +167,11 @@ class GpuSim:
         b = [np.ascontiguousarray(x) for x in (w.obst_xy, w.obst_next, w.obst_prev, w.obst_convex)]
         self._ck(self.L.ecmgpu_set_obstacles(self.h, w.n_obst_vertices, _p(b[0], f32p), _p(b[1], i32p), _p(b[2], i32p),
                                              _p(b[3], u8p)))
+        if getattr(w, "vert_he", None) is not None and getattr(w, "he_next", None) is not None:  # half-edge rings: device planner
+            t = [np.ascontiguousarray(x, np.int32) for x in (w.vert_he, w.he_next)]
+            rc = self.L.ecmgpu_set_ecm_topology(self.h, _p(t[0], i32p), _p(t[1], i32p))
+            # the tick does not need the rings: a graph they do not describe only makes plan_paths unavailable
+            self.topology_error = None if rc == 0 else self.L.ecmgpu_last_error(self.h).decode()
 
     def _ck(self, rc):
         if rc != 0:
@@ -334,6 +341,31 @@ class GpuSim:
         cnt = np.full(n, -1, np.int32)
         self._ck(self.L.ecmgpu_find_neighbors(self.h, n, _p(ids, i32p), _p(cnt, i32p)))
         return ids, cnt
+
+    def plan_paths(self, start, goal, clearance, points_per_path: int = 32):
+        """Batched ECMPathPlanner::FindPath on the device.  Same return shape as host.plan_paths:
+        (path_off[n+1], path_xy[total, 2], n_ok), paths in query order; a failed query contributes zero points."""
+        start = np.ascontiguousarray(start, np.float32).reshape(-1, 2)
+        goal = np.ascontiguousarray(goal, np.float32).reshape(-1, 2)
+        n = len(start)
+        cl = np.ascontiguousarray(np.broadcast_to(np.asarray(clearance, np.float32), (n,)))
+        off, ln, st = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint8)
+        cap = max(64, int(points_per_path) * n)
+        while True:
+            pool = np.zeros((cap, 2), np.float32)
+            used = C.c_int(0)
+            self._ck(self.L.ecmgpu_plan_paths(self.h, n, _p(start, f32p), _p(goal, f32p), _p(cl, f32p), _p(off, i32p), _p(ln, i32p),
+                                              _p(st, u8p), _p(pool, f32p), cap, C.byref(used)))
+            if used.value <= cap:
+                break
+            cap = used.value + 64  # the pool was too small: now its size is known
+        if (st == 2).any():
+            raise EcmGpuError(f"ecmgpu_plan_paths: {int((st == 2).sum())} queries exceeded a planner capacity")
+        out_off = np.zeros(n + 1, np.int32)
+        np.cumsum(ln, out=out_off[1:])
+        total = int(out_off[-1])
+        idx = np.repeat(off.astype(np.int64), ln) + (np.arange(total) - np.repeat(out_off[:-1].astype(np.int64), ln))
+        return out_off, pool[idx], int((ln > 0).sum())
 
     def valid_spawn_locations(self, xy, clearance):
         """Simulator::ValidSpawnLocation for a batch of points on the current positions (uint8 flags)."""

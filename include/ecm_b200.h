@@ -173,6 +173,23 @@ int ecmgpu_find_obstacles(ecmgpu_sim* sim, int slot, int* out_ids, int cap, int*
  * (owned + halo), and - like ecmgpu_find_neighbors - a collective call: every rank runs the halo exchange. */
 int ecmgpu_valid_spawn_locations(ecmgpu_sim* sim, int n, const float* xy, const float* clearance, uint8_t* out_valid);
 
+/* -- batched path planning on the device -------------------------------------
+ * The half-edge rings of the ECM graph, needed by the planner only: vert_he[v] = one half-edge leaving vertex v
+ * (ECMVertex::half_edge_idx, ECM.h:41-47), he_next[h] = the next half-edge around h's source vertex
+ * (ECMHalfEdge::next_idx, ECM.h:20-26); half-edge 2e runs edge e from v0 to v1, 2e+1 back (ECM.h:69).
+ * ecmgpu_set_ecm must have been given the vertex clearances.  A new ecmgpu_set_ecm drops the topology. */
+int ecmgpu_set_ecm_topology(ecmgpu_sim* sim, const int* vert_he, const int* he_next);
+/* ECMPathPlanner::FindPath (ECMPathPlanner.cpp:22-136, preferredAdditionalClearance = 0 as in Simulator.cpp:108-112)
+ * for n queries at once, one device thread per query: point location, retraction, A* on the medial axis with the
+ * reference's open-list behaviour, corridor, portals, funnel - the polylines equal the reference's bit for bit
+ * (tests/test_hostdev_planner.py).  The polyline of query i is out_xy[2*out_off[i] .. 2*(out_off[i]+out_len[i]));
+ * paths are packed in order of completion, so out_off is NOT ascending in i.  out_len[i] = 0 where the reference
+ * returns false.  out_status (may be NULL): 0 path, 1 no path, 2 a capacity was exceeded (path longer than 1024
+ * points / 2048 graph vertices / 8192 portals, or the pool: *out_points > cap_points - call again with a larger
+ * pool).  Waits for the result. */
+int ecmgpu_plan_paths(ecmgpu_sim* sim, int n, const float* start_xy, const float* goal_xy, const float* clearance, int* out_off,
+                      int* out_len, uint8_t* out_status, float* out_xy, int cap_points, int* out_points);
+
 /* -- neighbour mode ---------------------------------------------------------------------------
  * ECMGPU_NEIGHBORS_EXACT (default): the exact 5-NN contract of DESIGN.md on the per-tick uniform grid.
  * ECMGPU_NEIGHBORS_KDTREE: the reference's own lists - a median-split tree built like KDTree::Construct

@@ -16,6 +16,7 @@
 
 #include "../../ecmgenerator_b200/csrc/device/strips.cuh"
 #include "../../ecmgenerator_b200/csrc/device/kdtree.cuh"
+#include "../../ecmgenerator_b200/csrc/device/planner.cuh"
 
 using namespace ecm;
 
@@ -68,6 +69,9 @@ struct Emu {
     std::vector<float4> kd_tree;
     std::vector<float2> kd_pre_pos, kd_pre_vel;
     int kd_cap = 0;
+    // device planner (planner.cuh)
+    std::vector<float> vert_clear;
+    std::vector<int> vert_he, he_next;
 
     TickView view() {
         TickView t;
@@ -365,6 +369,42 @@ void emu_query_neighbors_kd(void* h, int* ids, int* cnt) {
     launch(e->n_slots, [&] { k_kd_resolve(e->n_slots, e->active.data(), q, e->nbr.data(), e->nbr_cnt.data()); });
     memcpy(ids, e->nbr.data(), 20 * (size_t)e->n);
     memcpy(cnt, e->nbr_cnt.data(), 4 * (size_t)e->n);
+}
+
+// ecmgpu_set_ecm_topology + ecmgpu_plan_paths with `workers` workers (queries in a grid-stride loop, like the kernel)
+void emu_set_topology(void* h, const float* vert_clear, const int* vert_he, const int* he_next) {
+    Emu* e = (Emu*)h;
+    e->vert_clear.assign(vert_clear, vert_clear + e->vert_xy.size());
+    e->vert_he.assign(vert_he, vert_he + e->vert_xy.size());
+    e->he_next.assign(he_next, he_next + 2 * e->edge_v.size());
+}
+int emu_plan_paths(void* h, int workers, int n, const float* start, const float* goal, const float* clearance, int* out_off, int* out_len,
+                   unsigned char* out_status, float* pool, int pool_cap, int cap_path, int cap_portals, int cap_out) {
+    Emu* e = (Emu*)h;
+    TickView t = e->view();
+    PlanView w;
+    w.ecm = t.ecm; w.bins = t.bins;
+    w.vert_clear = e->vert_clear.data(); w.vert_he = e->vert_he.data(); w.he_next = e->he_next.data();
+    const int nV = (int)e->vert_xy.size(), nE = (int)e->edge_v.size();
+    PlanScratch sc;
+    sc.n_workers = workers; sc.cap_push = 2 * nE + 4; sc.cap_path = cap_path; sc.cap_portals = cap_portals; sc.cap_out = cap_out;
+    std::vector<float> g((size_t)workers * nV), f((size_t)workers * nV);
+    std::vector<int> parent((size_t)workers * nV), heap((size_t)workers * sc.cap_push), touched((size_t)workers * sc.cap_push),
+        vpath((size_t)workers * cap_path), epath((size_t)workers * cap_path);
+    std::vector<unsigned char> visited((size_t)workers * nV);
+    std::vector<float4> portals((size_t)workers * cap_portals);
+    std::vector<float2> out((size_t)workers * cap_out);
+    sc.g = g.data(); sc.f = f.data(); sc.parent = parent.data(); sc.visited = visited.data(); sc.heap = heap.data(); sc.touched = touched.data();
+    sc.vpath = vpath.data(); sc.epath = epath.data(); sc.portals = portals.data(); sc.out = out.data();
+    launch(64, [&] { k_plan_init(sc, nV); });
+    int cursor = 0;
+    launch(workers, [&] {
+        k_plan_paths(w, sc, n, (const float2*)start, (const float2*)goal, clearance, out_off, out_len, out_status, (float2*)pool, pool_cap, &cursor);
+    });
+    // every query must leave the A* arrays idle again (CleanRequestData through the touched list)
+    for (size_t i = 0; i < g.size(); i++)
+        if (g[i] != kMaxFloat || f[i] != kMaxFloat || parent[i] != nV || visited[i]) return -1;
+    return cursor;
 }
 
 // ecmgpu_valid_spawn_locations
