@@ -48,14 +48,28 @@ def log(*a):
 
 
 # ------------------------------------------------------------------------------------------------
-def _plan_sharded(w, c, rank: int, world: int):
+def _plan(w, start, goal, radius, threads: int, planner: str, device: int):
+    """planner "host": csrc/host/planner.cpp on `threads` cores; "device": ecmgpu_plan_paths on this rank's GPU
+    (same polylines bit for bit, tests/test_zz_gpu_planner.py)."""
+    if planner == "device":
+        from ecmgenerator_b200 import gpu
+
+        sim = gpu.GpuSim(w, 8, float(S.DT), device=device)
+        try:
+            return sim.plan_paths(start, goal, radius)
+        finally:
+            sim.close()
+    return host.plan_paths(w, start, goal, radius, threads=threads)
+
+
+def _plan_sharded(w, c, rank: int, world: int, planner: str = "host", device: int = 0):
     """Every rank plans 1/world of the paths (host threads are shared by the ranks), then all-gather."""
     import torch.distributed as dist
 
     n = c.n
     lo, hi = n * rank // world, n * (rank + 1) // world
     threads = max(1, (os.cpu_count() or 8) // world)
-    off, pxy, _ = host.plan_paths(w, c.pos[lo:hi], c.goal[lo:hi], c.radius[lo:hi], threads=threads)
+    off, pxy, _ = _plan(w, c.pos[lo:hi], c.goal[lo:hi], c.radius[lo:hi], threads, planner, device)
     parts = [None] * world
     dist.all_gather_object(parts, (np.diff(off).astype(np.int32), pxy))
     lens = np.concatenate([p[0] for p in parts])
@@ -65,16 +79,16 @@ def _plan_sharded(w, c, rank: int, world: int):
     return out_off, pts
 
 
-def build_workload(config: str, agents: int | None, rank: int = 0, world: int = 1):
+def build_workload(config: str, agents: int | None, rank: int = 0, world: int = 1, planner: str = "host", device: int = 0):
     world_fn, crowd_fn = S.CONFIGS[config]
     w = world_fn()
     t = time.time()
     c = crowd_fn(w, n=agents) if agents else crowd_fn(w)
     t1 = time.time()
     if world > 1:
-        off, pxy = _plan_sharded(w, c, rank, world)
+        off, pxy = _plan_sharded(w, c, rank, world, planner, device)
     else:
-        off, pxy, _ = host.plan_paths(w, c.pos, c.goal, c.radius, threads=0)
+        off, pxy, _ = _plan(w, c.pos, c.goal, c.radius, 0, planner, device)
     lens = np.diff(off)
     good = lens >= 2
     if not good.all():  # drop agents the planner could not serve (start or goal level with a cell corner)
@@ -84,7 +98,7 @@ def build_workload(config: str, agents: int | None, rank: int = 0, world: int = 
         np.cumsum(lens[keep], out=new_off[1:])
         pxy = np.concatenate([pxy[off[i]:off[i + 1]] for i in keep]) if len(keep) < 200_000 else _gather(pxy, off, keep)
         off = new_off
-    log(f"[bench] {config}: {c.n} agents sampled in {t1 - t:.1f}s, paths planned in {time.time() - t1:.1f}s "
+    log(f"[bench] {config}: {c.n} agents sampled in {t1 - t:.1f}s, paths planned on the {planner} in {time.time() - t1:.1f}s "
         f"(mean {np.diff(off).mean():.1f} points, {int((~good).sum())} dropped)")
     return w, c, off, pxy
 
@@ -294,7 +308,7 @@ def run_ours(args):
 
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    w, c, off, pxy = build_workload(args.config, args.agents, rank, world)
+    w, c, off, pxy = build_workload(args.config, args.agents, rank, world, args.planner, local)
     n = c.n
     if world > 1:
         from ecmgenerator_b200.multigpu import StripSim
@@ -572,6 +586,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cell", type=float, default=0.0, help="neighbour grid cell (0 = from crowd density)")
     ap.add_argument("--bin", type=float, default=0.0, help="static bin edge (0 = from the ECM)")
+    ap.add_argument("--planner", default="host", choices=["host", "device"],
+                    help="who plans the agents' routes during set-up (outside the timed region): the host planner on all cores or "
+                         "ecmgpu_plan_paths on the GPU - identical polylines")
     ap.add_argument("--neighbors", default="exact", choices=["exact", "kdtree"],
                     help="kdtree: the reference's own KD-tree lists (parity mode, single GPU; DESIGN.md 5a) - a cost figure, not the headline")
     args = ap.parse_args()

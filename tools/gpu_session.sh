@@ -11,6 +11,7 @@
 #   5. cell-size sweep for the pruning variants (smaller cells pay only with pruning)
 #   6. parity statistics of the orca_fast variant (NOT bit-exact by design)
 #   7. bench.py --neighbors kdtree        cost of the parity mode
+#   7b. bench.py --planner device         set-up with ecmgpu_plan_paths instead of the host planner
 #   8. ncu launch list + one --set full capture of k_orca / k_attract of the default build
 # Nothing here changes GPU clocks.  Numbers printed under ncu are never bench values.
 set -u
@@ -50,6 +51,9 @@ ECMGPU_LIB=$PWD/variants/libecmgpu_orca_fast.so timeout 900 python -m pytest tes
 
 step "bench --neighbors kdtree"
 timeout 600 python bench.py --neighbors kdtree --no-cpu --steady-tick 0 --steps 20 >"$OUT/${TAG}_bench_kdtree.json" 2>"$OUT/${TAG}_bench_kdtree.err"
+
+step "bench --planner device (set-up time on stderr)"
+timeout 900 python bench.py --planner device --no-cpu --steady-tick 0 --steps 20 >"$OUT/${TAG}_bench_devplan.json" 2>"$OUT/${TAG}_bench_devplan.err"
 
 step "ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/${TAG}_launches.csv" \
