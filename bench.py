@@ -50,7 +50,7 @@ def log(*a):
 # ------------------------------------------------------------------------------------------------
 def _plan(w, start, goal, radius, threads: int, planner: str, device: int):
     """planner "host": csrc/host/planner.cpp on `threads` cores; "device": ecmgpu_plan_paths on this rank's GPU
-    (same polylines bit for bit, tests/test_zz_gpu_planner.py)."""
+    (same polylines bit for bit, tests/test_zz4_gpu_planner.py)."""
     if planner == "device":
         from ecmgenerator_b200 import gpu
 

@@ -1602,9 +1602,13 @@ int ecmgpu_set_ecm_topology(ecmgpu_sim* s, const int* vert_he, const int* he_nex
     for (int v = 0; v < nV; v++)
         if (vert_he[v] < 0 || vert_he[v] >= nH || source(vert_he[v]) != v)
             return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_ecm_topology: vert_he[v] must be a half-edge leaving v");
-    for (int h = 0; h < nH; h++)
+    std::vector<unsigned char> seen(nH, 0);
+    for (int h = 0; h < nH; h++) {
         if (he_next[h] < 0 || he_next[h] >= nH || source(he_next[h]) != source(h))
             return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_ecm_topology: he_next must stay on the half-edge's source vertex");
+        // rings must close: the planner walks he_next until it is back where it started (AStar.cpp:104-152)
+        if (seen[he_next[h]]++) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_ecm_topology: he_next must be a permutation (closed rings)");
+    }
     CUDA_TRY(s, cudaSetDevice(s->prm.device));
     CUDA_TRY(s, s->d_vert_he.alloc(nV)); CUDA_TRY(s, s->d_he_next.alloc(nH));
     CUDA_TRY(s, cudaMemcpyAsync(s->d_vert_he.p, vert_he, sizeof(int) * nV, cudaMemcpyHostToDevice, s->stream));

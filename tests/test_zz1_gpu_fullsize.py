@@ -15,7 +15,8 @@ from ecmgenerator_b200 import gpu, host
 from ecmgenerator_b200 import scenarios as S
 from tests.util import check_window_against_oracle
 
-pytestmark = pytest.mark.gpu
+# a kernel that never returns must not hang the box: the watchdog thread ends the run instead
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900, method="thread")]
 
 VEL_TOL = 1e-4  # m/s absolute per step (north_star)
 

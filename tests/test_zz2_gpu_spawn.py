@@ -6,7 +6,8 @@ import pytest
 from ecmgenerator_b200 import gpu
 from tests.util import Golden
 
-pytestmark = pytest.mark.gpu
+# a kernel that never returns must not hang the box: the watchdog thread ends the run instead
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
 
 
 @pytest.mark.parametrize("cell", [0.0, 0.6, 40.0])

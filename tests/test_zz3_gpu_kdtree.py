@@ -14,7 +14,8 @@ from ecmgenerator_b200 import gpu
 from oracle.pyoracle import OracleSim
 from tests.util import GOLDEN, Golden, apply_events, assert_bits_equal
 
-pytestmark = pytest.mark.gpu
+# a kernel that never returns must not hang the box: the watchdog thread ends the run instead
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]
 
 VEL_TOL = 1e-4  # m/s absolute per step (north_star)
 MODE = "ref-kdtree"

@@ -10,7 +10,8 @@ from ecmgenerator_b200 import gpu, host
 from ecmgenerator_b200 import scenarios as S
 from tests.util import GOLDEN, Golden, assert_bits_equal
 
-pytestmark = pytest.mark.gpu
+# a kernel that never returns must not hang the box: the watchdog thread ends the run instead
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]
 
 
 @pytest.mark.parametrize("name", GOLDEN)
