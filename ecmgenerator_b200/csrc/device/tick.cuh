@@ -73,6 +73,7 @@ struct TickScratch {
     float2* s_pref; unsigned char* s_alive;
     unsigned char* s_ghost;  // 1: halo / self ghost (multi-GPU): a neighbour candidate only
     int* fb_list;
+    int* nbr_q;  // split tick only (k_knn_rows -> k_orca_rows): [6 * cap] neighbour rows j-major, then the count / flag word
     int* ev_replan; int* ev_destroyed;
     unsigned long long* counters;
 };
@@ -390,6 +391,72 @@ __device__ __forceinline__ void orca_agent(const TickView& t, const int p, const
 
 __global__ void __launch_bounds__(256, ECM_ORCA_MINBLOCKS) k_orca(TickView t) {
     orca_agent(t, blockIdx.x * blockDim.x + threadIdx.x, *t.n_sorted_ptr);
+}
+
+// Split variant of k_orca (ECMGPU_SPLIT=1, off by default, same results): the neighbour search as a kernel of its own
+// at 8 CTAs per SM (32 registers, every warp slot filled: the search waits on L1 / L2 loads, long scoreboard was
+// k_orca's top stall at 62 % occupancy), its five snapshot rows handed over through `nbr_q` (24 B per agent each way);
+// the half-planes and the LP then run without the search's registers and code.
+#ifndef ECM_KNN_MINBLOCKS
+#define ECM_KNN_MINBLOCKS 8
+#endif
+constexpr int kSplitHaloMiss = 0x100;  // flag in the count word
+__global__ void __launch_bounds__(256, ECM_KNN_MINBLOCKS) k_knn_rows(TickView t, int cap) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *t.n_sorted_ptr;
+    const bool mine = p < n && !t.sc.s_ghost[p] && t.sc.s_alive[p];
+    Knn k;
+    k.init();
+    int word = -1;  // no work for k_orca_rows
+    bool fb = false;
+    if (mine) {
+        const v2 pos = t.sc.s_pos[p];
+        if (knn_grid(k, pos, t.grid, t.max_ring)) {
+            word = k.count();
+            if (t.strips) {  // finish_agent's check, made where the 5th distance is at hand
+                const float r5 = word == kK ? sqrtf(k.d[kK - 1]) * 1.001f : CUDART_INF_F;
+                if (pos.x - r5 < t.cover_lo || pos.x + r5 >= t.cover_hi) word |= kSplitHaloMiss;
+            }
+        } else {
+            fb = true;
+            const int e = (int)atomicAdd(&t.sc.counters[C_FALLBACK_N], 1ull);
+            t.sc.fb_list[e] = p;
+            t.ag.status[t.sc.s_slot[p]] |= 32u;
+        }
+    }
+    if (p < cap) {
+#pragma unroll
+        for (int j = 0; j < kK; j++) t.sc.nbr_q[(size_t)j * cap + p] = k.q[j];
+        t.sc.nbr_q[(size_t)kK * cap + p] = word;
+    }
+    const unsigned m_fb = __ballot_sync(0xffffffffu, fb);
+    if ((threadIdx.x & 31) == 0 && m_fb) atomicAdd(&t.sc.counters[C_TOTAL_FALLBACK], (unsigned long long)__popc(m_fb));
+}
+
+// `t.strips` must be 0 here (the halo check travelled in the count word).
+__global__ void __launch_bounds__(256, ECM_ORCA_MINBLOCKS) k_orca_rows(TickView t, int cap) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *t.n_sorted_ptr;
+    const int word = p < n && p < cap ? t.sc.nbr_q[(size_t)kK * cap + p] : -1;
+    const bool valid = word >= 0;
+    Knn k;
+    k.init();
+    if (valid) {
+#pragma unroll
+        for (int j = 0; j < kK; j++) k.q[j] = t.sc.nbr_q[(size_t)j * cap + p];
+    }
+    __syncthreads();
+    unsigned st = finish_agent<true, true>(t, p, k, valid);
+    if (valid && (word & kSplitHaloMiss)) st |= 128u;
+    if (st) t.ag.status[t.sc.s_slot[p]] |= st;
+    const unsigned m_ovf = __ballot_sync(0xffffffffu, (st & 16u) != 0u);
+    const unsigned m_lp3 = __ballot_sync(0xffffffffu, (st & 64u) != 0u);
+    const unsigned m_hm = __ballot_sync(0xffffffffu, (st & 128u) != 0u);
+    if ((threadIdx.x & 31) == 0) {
+        if (m_hm) atomicAdd(&t.sc.counters[C_TOTAL_HALO_MISS], (unsigned long long)__popc(m_hm));
+        if (m_ovf) atomicAdd(&t.sc.counters[C_TOTAL_OBST_OVF], (unsigned long long)__popc(m_ovf));
+        if (m_lp3) atomicAdd(&t.sc.counters[C_TOTAL_LP3D], (unsigned long long)__popc(m_lp3));
+    }
 }
 
 // The whole per-agent tick in one kernel: the attraction phase is memory-latency bound (polyline

@@ -178,6 +178,8 @@ struct ecmgpu_sim {
     int max_ring = 8;
     int orca_block = 256;  // CTA size of k_orca (env ECMGPU_ORCA_BLOCK for experiments)
     bool fused = false;    // k_tick (attraction + ORCA in one kernel); profiling mode times k_attract / k_orca separately; env ECMGPU_FUSED=0
+    bool split = false;    // k_knn_rows + k_orca_rows instead of k_orca (same results; an A/B candidate, not measured yet); env ECMGPU_SPLIT=1
+    DevBuf<int> d_nbr_q;   // split tick: [6 * rows] neighbour rows + count word
     bool gather = false;   // snapshot rows built by k_attract (gather) instead of k_scatter: measured neutral (profiles/r01_experiments.md); env ECMGPU_GATHER=1
     // ---- the tick as a CUDA graph (one launch instead of ~15 kernel / memset / NCCL submissions)
     bool use_graph = true;         // env ECMGPU_GRAPH=0 disables
@@ -450,6 +452,7 @@ TickView make_view(ecmgpu_sim* s) {
     t.sc.s_alive = s->d_s_alive.p;
     t.sc.s_ghost = s->d_s_ghost.p;
     t.sc.fb_list = s->d_fb_list.p;
+    t.sc.nbr_q = s->d_nbr_q.p;
     t.sc.ev_replan = s->d_ev_replan.p;
     t.sc.ev_destroyed = s->d_ev_destroyed.p;
     t.sc.counters = s->d_counters.p;
@@ -699,6 +702,14 @@ int plan_alloc(ecmgpu_sim* s, int want) {
     k_plan_init<<<148 * 8, 256, 0, s->stream>>>(make_plan_scratch(s), (int)nV);
     s->launches++;
     CUDA_TRY(s, cudaGetLastError());
+    return ECMGPU_OK;
+}
+
+// Split tick: room for 6 ints per snapshot row the kernels cover (same row count as ecmgpu_update_phase computes).
+int ensure_split_buffer(ecmgpu_sim* s) {
+    if (!s->split) return ECMGPU_OK;
+    const size_t cap = (size_t)div_up(s->n_slots + (s->strips_on ? 2 * s->cap_halo + s->cap_self : 0), 128) * 128;
+    if (s->d_nbr_q.n < 6 * cap) CUDA_TRY(s, s->d_nbr_q.alloc(6 * cap));
     return ECMGPU_OK;
 }
 
@@ -978,6 +989,7 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
     if (const char* e = getenv("ECMGPU_GRAPH")) s->use_graph = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_GATHER")) s->gather = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_FUSED")) s->fused = atoi(e) != 0;
+    if (const char* e = getenv("ECMGPU_SPLIT")) s->split = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_ORCA_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) s->orca_block = v; }
     s->h_path_pool.reserve(std::min<size_t>(pool, 1 << 20));
     *out = s;
@@ -998,7 +1010,7 @@ void ecmgpu_destroy(ecmgpu_sim* s) {
     s->d_key.free(); s->d_rank.free(); s->d_cell_count.free(); s->d_block_sums.free(); s->d_s_slot.free();
     s->d_lp3d_hdr.free(); s->d_lp3d_out.free(); s->d_lp3d_cs.free();
     s->d_fb_list.free(); s->d_ev_replan.free(); s->d_ev_destroyed.free(); s->d_s_pos.free(); s->d_s_vel.free();
-    s->d_s_pref.free(); s->d_s_rad.free(); s->d_s_spd.free(); s->d_s_alive.free(); s->d_counters.free();
+    s->d_s_pref.free(); s->d_s_rad.free(); s->d_s_spd.free(); s->d_s_alive.free(); s->d_counters.free(); s->d_nbr_q.free();
     kd_free(s);
     plan_free(s);
     s->d_vert_clear.free(); s->d_vert_he.free(); s->d_he_next.free();
@@ -1210,6 +1222,18 @@ int ecmgpu_update_phase(ecmgpu_sim* s, int phase) {
         rc = enqueue_kd_orca(s, t, nb * 128);
         if (rc) return rc;
         s->launches -= 2;  // k_attract and k_orca_kd are counted above (3 are added below)
+    } else if (s->split) {
+        const int cap = nb * 128;  // rows the kernels cover
+        rc = ensure_split_buffer(s);  // normally done by ecmgpu_update before a capture starts
+        if (rc) return rc;
+        t.sc.nbr_q = s->d_nbr_q.p;
+        k_attract<<<nb, 128, 0, s->stream>>>(t);
+        if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
+        k_knn_rows<<<div_up(cap, 256), 256, 0, s->stream>>>(t, cap);
+        TickView t2 = t;
+        t2.strips = 0;  // the halo check travels in the count word
+        k_orca_rows<<<div_up(cap, 256), 256, 0, s->stream>>>(t2, cap);
+        s->launches += 1;  // three kernels instead of two (3 are added below)
     } else if (s->fused) {
         if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));  // "attract" phase is empty: all of it is k_tick
         k_tick<<<div_up(nb * 128, ob), ob, 0, s->stream>>>(t);
@@ -1238,6 +1262,8 @@ int ecmgpu_update(ecmgpu_sim* s) {
     if (s->use_graph && !nccl_tick && !s->profiling && s->n_slots > 0 && s->neighbor_mode == ECMGPU_NEIGHBORS_EXACT) {
         CUDA_TRY(s, cudaSetDevice(s->prm.device));
         int rc = ensure_ready(s);  // host-side (re)builds happen outside the capture
+        if (rc) return rc;
+        rc = ensure_split_buffer(s);
         if (rc) return rc;
         const int g = (int)(s->comm_seq & 1u);
         if (!s->graph_exec[g] || s->graph_epoch[g] != s->config_epoch || s->graph_n_slots[g] != s->n_slots) {

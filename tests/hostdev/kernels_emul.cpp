@@ -49,7 +49,8 @@ struct Emu {
     // grid + snapshot + scratch
     float gx0 = 0, gy0 = 0, gcell = 1;
     int gw = 1, gh = 1;
-    std::vector<int> key, rank, cell_count, s_slot, fb_list, ev_replan, ev_destroyed;
+    std::vector<int> key, rank, cell_count, s_slot, fb_list, ev_replan, ev_destroyed, nbr_q;
+    bool split = false;  // ECMGPU_SPLIT: k_knn_rows + k_orca_rows instead of k_orca
     std::vector<float2> s_pos, s_vel, s_pref;
     std::vector<float> s_rad, s_spd;
     std::vector<unsigned char> s_alive, s_ghost;
@@ -92,7 +93,7 @@ struct Emu {
         t.sc.key = key.data(); t.sc.rank = rank.data(); t.sc.cell_count = cell_count.data(); t.sc.block_sums = nullptr;
         t.sc.s_pos = s_pos.data(); t.sc.s_vel = s_vel.data(); t.sc.s_rad = s_rad.data(); t.sc.s_spd = s_spd.data();
         t.sc.s_slot = s_slot.data(); t.sc.s_pref = s_pref.data(); t.sc.s_alive = s_alive.data(); t.sc.s_ghost = s_ghost.data();
-        t.sc.fb_list = fb_list.data(); t.sc.ev_replan = ev_replan.data(); t.sc.ev_destroyed = ev_destroyed.data();
+        t.sc.fb_list = fb_list.data(); t.sc.nbr_q = nbr_q.data(); t.sc.ev_replan = ev_replan.data(); t.sc.ev_destroyed = ev_destroyed.data();
         t.sc.counters = counters.data();
         t.n_sorted_ptr = cell_count.data() + (size_t)gw * gh;
         t.step = step; t.max_ring = 8; t.record_neighbors = 1; t.gather = 0;
@@ -177,6 +178,7 @@ void* emu_create(int nV, const float* vert_xy, int nE, const int* edge_v, const 
     return e;
 }
 void emu_destroy(void* h) { delete (Emu*)h; }
+void emu_set_split(void* h, int on) { ((Emu*)h)->split = on != 0; }
 
 void emu_load(void* h, int n, const float* pos, const float* radius, const float* speed, const int* path_off, const float* path_xy) {
     Emu* e = (Emu*)h;
@@ -263,7 +265,16 @@ int emu_tick(void* h) {
     if (e->strips) launch(ng, [&] { k_ghost_scatter(sv, e->cell_count.data(), t.ag, t.sc, e->s_ghost.data()); });
     const int rows = e->n_slots + (e->strips ? ng : 0);
     launch(rows, [&] { k_attract(t); });
-    launch(rows, [&] { k_orca(t); });
+    if (e->split) {
+        e->nbr_q.assign(6 * (size_t)rows, -7);
+        t.sc.nbr_q = e->nbr_q.data();
+        launch(rows, [&] { k_knn_rows(t, rows); });
+        TickView t2 = t;
+        t2.strips = 0;
+        launch(rows, [&] { k_orca_rows(t2, rows); });
+    } else {
+        launch(rows, [&] { k_orca(t); });
+    }
     const int fb = (int)e->counters[C_FALLBACK_N];
     if (fb == 0) launch(64, [&] { k_fallback(t, 0); });  // the parked LP3D agents (its warp-per-agent half needs real warps)
     return fb;

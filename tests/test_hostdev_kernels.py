@@ -54,6 +54,7 @@ def load_emu():
     L.emu_exchange.argtypes = [vp, vp, vp]
     L.emu_tick.argtypes = [vp]
     L.emu_tick_kd.argtypes = [vp]
+    L.emu_set_split.argtypes = [vp, C.c_int]
     L.emu_valid_spawn.argtypes = [vp, C.c_int, f32p, f32p, u8p]
     L.emu_kd_reset.argtypes = [vp]
     L.emu_query_neighbors_kd.argtypes = [vp, i32p, i32p]
@@ -205,14 +206,26 @@ def test_kernels_reproduce_reference_trajectories_bitwise(emu, name):
     d.close()
 
 
-@pytest.mark.parametrize("name", ["c2_small", "jam_small"])
-def test_three_strips_equal_one_device_bitwise(emu, name):
+@pytest.mark.parametrize("name", GOLDEN)
+def test_split_tick_reproduces_reference_trajectories_bitwise(emu, name):
+    """ECMGPU_SPLIT: k_knn_rows + k_orca_rows instead of k_orca."""
+    g = Golden(name)
+    d = EmuDevice(emu, g, _cell_for(g))
+    emu.emu_set_split(d.h, 1)
+    _run_against_golden(d, g, lambda: emu.emu_tick(d.h), d.state, f"{name} / split")
+    d.close()
+
+
+@pytest.mark.parametrize("name,split", [("c2_small", 0), ("jam_small", 0), ("jam_small", 1)])
+def test_three_strips_equal_one_device_bitwise(emu, name, split):
     g = Golden(name)
     # halo: comfortably more than any agent's 5th-neighbour distance at the start
     r5 = _r5_max(g)
     widths = np.diff(M.strip_bounds(g.crowd.pos[:, 0], 3))[1:-1]
     halo = float(min(2.0 * r5 + 2.0, widths.min()))
     s = EmuStrips(emu, g, _cell_for(g), 3, halo)
+    for dev in s.devs:
+        emu.emu_set_split(dev.h, split)
     own0 = M.owner_of(g.crowd.pos[:, 0], s.bounds)
     st = _run_against_golden(s, g, s.step, s.state, f"{name} / 3 strips")
     assert st["owners"].max() == 1, "every live agent has exactly one owner"

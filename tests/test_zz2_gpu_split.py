@@ -1,0 +1,65 @@
+"""GPU (-m gpu): the split tick (ECMGPU_SPLIT=1: k_knn_rows + k_orca_rows instead of k_orca) gives the default tick's
+state bit for bit - single device and in-process strips.  tests/test_hostdev_kernels.py pins it on the CPU."""
+import os
+
+import numpy as np
+import pytest
+
+from ecmgenerator_b200 import gpu
+from ecmgenerator_b200 import multigpu as M
+from tests.util import GOLDEN, Golden
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
+
+
+def _run(g, split, ticks):
+    old = os.environ.pop("ECMGPU_SPLIT", None)
+    if split:
+        os.environ["ECMGPU_SPLIT"] = "1"  # read by ecmgpu_create
+    try:
+        sim = gpu.GpuSim(g.world, g.n + 8, g.step)
+    finally:
+        os.environ.pop("ECMGPU_SPLIT", None)
+        if old is not None:
+            os.environ["ECMGPU_SPLIT"] = old
+    sim.bulk_load(g.crowd.pos, g.crowd.radius, g.crowd.speed, g.path_off, g.path_xy)
+    sim.update(ticks)
+    st = sim.state(g.n)
+    st["nbr"] = sim.read(gpu.NEIGHBORS, 0, g.n)
+    st["status"] = sim.read(gpu.STATUS, 0, g.n)
+    stats = sim.stats()
+    sim.close()
+    return st, stats
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_split_tick_equals_default_tick_bitwise(name):
+    g = Golden(name)
+    ticks = min(g.ticks("exact-knn"), 120)
+    a, sa = _run(g, False, ticks)
+    b, sb = _run(g, True, ticks)
+    for k in a:
+        assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), f"{name}: {k} differs"
+    assert sa["lp3d_runs"] == sb["lp3d_runs"] and sa["knn_fallbacks"] == sb["knn_fallbacks"]
+    assert sb["kernel_launches"] > sa["kernel_launches"]  # one more kernel per tick: the switch was on
+
+
+def test_split_tick_with_strips_equals_single_device():
+    g = Golden("jam_small")
+    single, _ = _run(g, False, 60)
+    os.environ["ECMGPU_SPLIT"] = "1"
+    try:
+        strips = M.LocalStrips(g.world, g.crowd, g.path_off, g.path_xy, 3, step=g.step)
+    finally:
+        os.environ.pop("ECMGPU_SPLIT", None)
+    strips.update(60)
+    strips.sync()
+    pos, owners = strips.gather(gpu.POS)
+    vel, _ = strips.gather(gpu.VEL)
+    live = single["active"] > 0
+    assert np.array_equal(owners > 0, live)
+    pos, vel = pos[live], vel[live]
+    single = {k: v[live] for k, v in single.items()}
+    assert np.array_equal(pos.view(np.uint32), single["pos"].view(np.uint32))
+    assert np.array_equal(vel.view(np.uint32), single["vel"].view(np.uint32))
+    assert sum(s["halo_misses"] for s in strips.stats()) == 0
