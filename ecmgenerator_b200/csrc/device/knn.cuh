@@ -126,7 +126,36 @@ __device__ __forceinline__ bool knn_grid(Knn& k, v2 self, const GridView& g, int
     // of the two neighbouring rows take the nearer one first: it tightens the 5th distance before the farther one is judged
     const bool low_first = (self.y - (g.y0 + (float)cy * g.cell)) * 2.0f <= g.cell;
 #endif
-    for (int r = 1; r <= max_ring; r++) {
+    int r_first = 1;
+#ifdef ECM_KNN_FLAT
+    // Ring 1 (the 3 x 3 block, where most searches end) as ONE loop over its three row ranges: the six range bounds
+    // are loaded up front (independent loads instead of three load -> loop -> load chains), and a warp runs
+    // max-over-lanes(n0 + n1 + n2) iterations instead of max(n0) + max(n1) + max(n2).  Same candidates in the same
+    // order (own row, row below, row above), hence the same result.
+    {
+        const int xa = max(cx - 1, 0), xb = min(cx + 1, g.w - 1);
+        const int ya = max(cy - 1, 0), yb = min(cy + 1, g.h - 1);
+        const int a0 = __ldg(&g.cell_start[cy * g.w + xa]), b0 = __ldg(&g.cell_start[cy * g.w + xb + 1]);
+        int a1 = 0, b1 = 0, a2 = 0, b2 = 0;
+        if (cy - 1 >= 0) { a1 = __ldg(&g.cell_start[(cy - 1) * g.w + xa]); b1 = __ldg(&g.cell_start[(cy - 1) * g.w + xb + 1]); }
+        if (cy + 1 < g.h) { a2 = __ldg(&g.cell_start[(cy + 1) * g.w + xa]); b2 = __ldg(&g.cell_start[(cy + 1) * g.w + xb + 1]); }
+        const int n0 = b0 - a0, n01 = n0 + (b1 - a1), total = n01 + (b2 - a2);
+        for (int i = 0; i < total; i++) {
+            const int c = i < n0 ? a0 + i : (i < n01 ? a1 + (i - n0) : a2 + (i - n01));
+            k.consider(self, c, g);
+        }
+        float cover = CUDART_INF_F;
+        if (xa > 0) cover = fminf(cover, self.x - (g.x0 + (float)xa * g.cell));
+        if (xb < g.w - 1) cover = fminf(cover, (g.x0 + (float)(xb + 1) * g.cell) - self.x);
+        if (ya > 0) cover = fminf(cover, self.y - (g.y0 + (float)ya * g.cell));
+        if (yb < g.h - 1) cover = fminf(cover, (g.y0 + (float)(yb + 1) * g.cell) - self.y);
+        if (cover == CUDART_INF_F) return true;
+        if (k.q[kK - 1] >= 0 && cover > 0.0f && k.d[kK - 1] < cover * cover * 0.999f) return true;
+        if (max_ring < 2) return false;
+        r_first = 2;
+    }
+#endif
+    for (int r = r_first; r <= max_ring; r++) {
         const int xa = max(cx - r, 0), xb = min(cx + r, g.w - 1);
         const int ya = max(cy - r, 0), yb = min(cy + r, g.h - 1);
         const int pieces = r == 1 ? 3 : 2 + 2 * (2 * r - 1);
