@@ -19,6 +19,7 @@ TAG=${1:-session}
 OUT=gpurun_out
 mkdir -p "$OUT"
 export PYTHONUNBUFFERED=1
+export ECM_WORKLOAD_CACHE=/tmp/ecm_workloads   # the 1 M crowd's routes are planned once per session, not once per step
 step() { echo "=== $1 ($(date +%T))" | tee -a "$OUT/${TAG}_session.log"; }
 
 step "build"
@@ -54,7 +55,7 @@ step "bench --neighbors kdtree"
 timeout 600 python bench.py --neighbors kdtree --no-cpu --steady-tick 0 --steps 20 >"$OUT/${TAG}_bench_kdtree.json" 2>"$OUT/${TAG}_bench_kdtree.err"
 
 step "bench --planner device (set-up time on stderr)"
-timeout 900 python bench.py --planner device --no-cpu --steady-tick 0 --steps 20 >"$OUT/${TAG}_bench_devplan.json" 2>"$OUT/${TAG}_bench_devplan.err"
+ECM_WORKLOAD_CACHE= timeout 900 python bench.py --planner device --no-cpu --steady-tick 0 --steps 20 >"$OUT/${TAG}_bench_devplan.json" 2>"$OUT/${TAG}_bench_devplan.err"
 
 step "ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/${TAG}_launches.csv" \
