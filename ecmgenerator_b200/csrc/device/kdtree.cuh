@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(256) k_kd_cache(int n_slots, const unsigned ch
         __syncthreads();
     }
     const int last = s_last;
-    if (last >= 0 && threadIdx.x < kK) cache[threadIdx.x] = nbr[kK * last + (int)threadIdx.x];
+    if (last >= 0)
+        for (int j = (int)threadIdx.x; j < kK; j += (int)blockDim.x) cache[j] = nbr[kK * last + j];
 }
 
 // k_orca with the reference's neighbour lists.  `t.grid.s_pos / s_vel / s_rad` point at SLOT-indexed pre-tick

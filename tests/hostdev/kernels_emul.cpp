@@ -365,6 +365,15 @@ void emu_tick_kd(void* h) {
     launch(64, [&] { k_fallback(t, 0); });
 }
 
+// k_kd_resolve + k_kd_cache on hand-made search results (ids or tokens -2 - place), for tests of the token chains
+void emu_kd_resolve(int n_slots, const unsigned char* active, const int* raw, const int* raw_cnt, int* cache, int* nbr, int* nbr_cnt) {
+    KdQuery q;
+    memset(&q, 0, sizeof(q));
+    q.raw = (int*)raw; q.raw_cnt = (int*)raw_cnt; q.cache = cache;
+    launch(n_slots, [&] { k_kd_resolve(n_slots, active, q, nbr, nbr_cnt); });
+    launch(1, [&] { k_kd_cache(n_slots, active, nbr, cache); });
+}
+
 // ecmgpu_find_neighbors in KD-tree mode
 void emu_query_neighbors_kd(void* h, int* ids, int* cnt) {
     Emu* e = (Emu*)h;
