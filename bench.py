@@ -300,7 +300,7 @@ def run_reference_arm(args):
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": res["ms_per_tick_sample"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"{args.config}: {c.n} agents, C3 city lattice; each step = one tick of a bounded sample",
+            "config": {"workload": f"{args.config}: {c.n} agents, {w.n_obstacles} blocks, {w.n_cells} ECM cells; each step = one tick of a bounded sample",
                        "agents": c.n, "dt": float(S.DT)},
             "cpu_baseline": res,
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
