@@ -25,7 +25,8 @@ class _Scene:
         self.crowd.pos[:] = self.path_xy[::2]
 
 
-def _emu_plan(emu, world, start, goal, clearance, workers=7, cap_path=512, cap_portals=4096, cap_out=512, pool_cap=None, dev=None):
+def _emu_plan(emu, world, start, goal, clearance, workers=7, cap_path=2048, cap_portals=8192, cap_out=1024, pool_cap=None, dev=None):
+    """Capacities default to ecmgpu.cu's plan_alloc."""
     own = dev is None
     if own:
         dev = EmuDevice(emu, _Scene(world), 4.0)
