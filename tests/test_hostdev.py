@@ -26,6 +26,7 @@ def _p(a, t):
 VARIANTS = {"default": [], "knn_prune": ["-DECM_KNN_PRUNE"], "knn_branchless": ["-DECM_KNN_BRANCHLESS"],
             "knn_prune_branchless": ["-DECM_KNN_PRUNE", "-DECM_KNN_BRANCHLESS"],
             "knn_flat": ["-DECM_KNN_FLAT"], "knn_flat_prune": ["-DECM_KNN_FLAT", "-DECM_KNN_PRUNE"],
+            "attract_bbox4": ["-DECM_ATTRACT_BBOX4"],
             "knn_twopass": ["-DECM_KNN_TWOPASS"], "knn_twopass_prune": ["-DECM_KNN_TWOPASS", "-DECM_KNN_PRUNE"],
             # the warp-synchronous instantiations the kernels run (flattened control flow), one lane per "warp"
             "sync": ["-DHD_SYNC"]}

@@ -17,6 +17,7 @@ STANDARD = {
     "knn_prune": ["-DECM_KNN_PRUNE"],
     "knn_flat": ["-DECM_KNN_FLAT"],
     "knn_flat_prune": ["-DECM_KNN_FLAT", "-DECM_KNN_PRUNE"],
+    "attract_bbox4": ["-DECM_ATTRACT_BBOX4"],
     "knn_twopass": ["-DECM_KNN_TWOPASS"],
     "knn_twopass_prune": ["-DECM_KNN_TWOPASS", "-DECM_KNN_PRUNE"],
     # NOT bit-exact (SFU division / square root / sine in the ORCA half-planes and LP only, geom.cuh): its bar is the

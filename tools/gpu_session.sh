@@ -34,7 +34,7 @@ step "bench"
 timeout 600 python bench.py >"$OUT/${TAG}_bench.json" 2>"$OUT/${TAG}_bench.err"
 
 # name[=library][,ENV=VALUE]: the split tick is a run-time switch of the default library (and of any variant)
-V="base split,ECMGPU_SPLIT=1 split_fast=variants/libecmgpu_orca_fast.so,ECMGPU_SPLIT=1 split_twopass=variants/libecmgpu_knn_twopass.so,ECMGPU_SPLIT=1 knn_flat=variants/libecmgpu_knn_flat.so split_flat=variants/libecmgpu_knn_flat.so,ECMGPU_SPLIT=1 knn_flat_prune=variants/libecmgpu_knn_flat_prune.so knn_prune=variants/libecmgpu_knn_prune.so knn_twopass=variants/libecmgpu_knn_twopass.so knn_twopass_prune=variants/libecmgpu_knn_twopass_prune.so orca_fast=variants/libecmgpu_orca_fast.so"
+V="base attract_bbox4=variants/libecmgpu_attract_bbox4.so split,ECMGPU_SPLIT=1 split_fast=variants/libecmgpu_orca_fast.so,ECMGPU_SPLIT=1 split_twopass=variants/libecmgpu_knn_twopass.so,ECMGPU_SPLIT=1 knn_flat=variants/libecmgpu_knn_flat.so split_flat=variants/libecmgpu_knn_flat.so,ECMGPU_SPLIT=1 knn_flat_prune=variants/libecmgpu_knn_flat_prune.so knn_prune=variants/libecmgpu_knn_prune.so knn_twopass=variants/libecmgpu_knn_twopass.so knn_twopass_prune=variants/libecmgpu_knn_twopass_prune.so orca_fast=variants/libecmgpu_orca_fast.so"
 step "A/B from rest"
 timeout 900 python tools/ab_variants.py $V >"$OUT/${TAG}_ab_rest.jsonl" 2>"$OUT/${TAG}_ab_rest.err"
 step "A/B congested (400 ticks of pre-roll)"
