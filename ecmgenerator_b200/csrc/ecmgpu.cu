@@ -35,6 +35,10 @@ template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;  // owns its allocation: temporaries release it on every return path
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { free(); }
     cudaError_t alloc(size_t count) {
         free();
         n = count;
