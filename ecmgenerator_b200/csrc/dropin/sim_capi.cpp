@@ -6,6 +6,7 @@
 #include <exception>
 #include <string>
 
+#include "../../../include/ecm_b200.h"
 #include "../../../include/ecm_b200_host.h"
 #include "Simulator.h"
 
@@ -123,6 +124,13 @@ int ecmsim_find_neighbors_via(void* h, int agent, int route, int* out5) {
     GUARD(if (route == 0) sim->GetKDTree()->KNearestAgents(sim, agent, 5, nb, n); else sim->FindNNearestNeighborsDeprecated(agent, 5, nb, n), -2)
     for (int k = 0; k < 5; k++) out5[k] = nb[k];
     return n;
+}
+// parity runs against the UNMODIFIED reference: the GPU tick with the reference's own KD-tree lists (ecm_b200.h)
+int ecmsim_set_neighbor_mode(void* h, int mode) {
+    auto* sim = ((SimBox*)h)->sim;
+    const int rc = ecmgpu_set_neighbor_mode(sim->GetGpuHandle(), mode);
+    if (rc) g_err = ecmgpu_last_error(sim->GetGpuHandle());
+    return rc;
 }
 
 }  // extern "C"

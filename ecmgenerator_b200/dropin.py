@@ -53,6 +53,7 @@ def lib():
         L.ecmsim_add_obstacle_area.argtypes = [vp] + [C.c_float] * 4 + [C.c_int]
         L.ecmsim_num_obstacle_vertices.argtypes = [vp]
         L.ecmsim_find_neighbors_via.argtypes = [vp, C.c_int, C.c_int, i32p]
+        L.ecmsim_set_neighbor_mode.argtypes = [vp, C.c_int]
         # the same library also carries the ecmhost_* entry points (one FlatWorld layout)
         L.ecmhost_world_from_arrays.restype = vp
         L.ecmhost_world_from_arrays.argtypes = [C.POINTER(host._WorldView)]
@@ -155,6 +156,11 @@ class Simulator:
 
     def num_obstacle_vertices(self) -> int:
         return int(self.L.ecmsim_num_obstacle_vertices(self.h))
+
+    def set_neighbor_mode(self, mode: int):
+        """gpu.NEIGHBORS_KDTREE: the tick uses the reference's own KD-tree lists (parity runs against the unmodified reference)."""
+        if self.L.ecmsim_set_neighbor_mode(self.h, int(mode)) != 0:
+            raise RuntimeError(self.L.ecmsim_last_error().decode())
 
     def find_neighbors_via(self, agent, route: str):
         """route 'kdtree': GetKDTree()->KNearestAgents; 'deprecated': FindNNearestNeighborsDeprecated."""

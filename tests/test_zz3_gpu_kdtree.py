@@ -114,3 +114,47 @@ def test_kd_mode_refuses_strips():
     strips = M.LocalStrips(g.world, g.crowd, g.path_off, g.path_xy, 2, step=g.step)
     with pytest.raises(gpu.EcmGpuError):
         strips.sims[0].set_neighbor_mode(gpu.NEIGHBORS_KDTREE)
+
+
+def test_dropin_in_kd_mode_walks_like_the_unmodified_reference():
+    """The C++ drop-in Simulator against the UNMODIFIED reference Simulator (its own KDTree.cpp, ORCA.cpp, ...), both
+    driven through the same calls - SpawnAgent, Update, DestroyAgent, the getters - for 120 free-running ticks."""
+    from ecmgenerator_b200 import dropin
+    from ecmgenerator_b200 import scenarios as S
+    from oracle import pyref
+
+    if not pyref.available(MODE):
+        pytest.skip("oracle/_ref not built")
+    w = S.world_c1()
+    c = S.crowd_c1(w, n=400, seed=61)
+    ref = pyref.RefSim(w, 512, 1 / 60, MODE)
+    sim = dropin.Simulator(w, 512, 1 / 60)
+    sim.set_neighbor_mode(gpu.NEIGHBORS_KDTREE)
+    slots_r, slots_s = [], []
+    for i in range(c.n):
+        start = c.pos[i - 1] if (i % 50 == 49) else c.pos[i]  # some spawns land on an agent: ValidSpawnLocation refuses
+        slots_r.append(ref.spawn(start, c.goal[i], c.radius[i], c.speed[i]))
+        slots_s.append(sim.spawn_agent(start, c.goal[i], c.radius[i], c.speed[i]))
+    assert slots_r == slots_s and -1 in slots_s
+    n = max(slots_s) + 1
+    worst = 0.0
+    for t in range(120):
+        ref.step(1)
+        sim.update(1 / 60)
+        if t == 40:
+            for s in (5, 17, 3):
+                ref.destroy_agent(s)
+                sim.destroy_agent(s)
+            assert ref.spawn(c.pos[5], c.goal[6], 0.3, 1.4) == sim.spawn_agent(c.pos[5], c.goal[6], 0.3, 1.4) == 3
+        if t % 20 == 19:
+            a, b = sim.state(n), ref.state(n)
+            assert np.array_equal(a["active"], b["active"])
+            act = b["active"] > 0
+            worst = max(worst, float(np.abs(a["pos"][act] - b["pos"][act]).max()))
+    a, b = sim.state(n), ref.state(n)
+    act = b["active"] > 0
+    print(f"drop-in (KD-tree mode) vs the unmodified reference after 120 ticks: max |dp| {worst:.3e}, "
+          f"max |dv| {float(np.abs(a['vel'][act] - b['vel'][act]).max()):.3e}")
+    assert np.abs(a["vel"][act] - b["vel"][act]).max() <= 5e-3 and worst <= 5e-3
+    sim.close()
+    ref.close()
