@@ -39,6 +39,7 @@ sys.path.insert(0, ROOT)
 from ecmgenerator_b200 import scenarios as S  # noqa: E402
 from ecmgenerator_b200 import host  # noqa: E402
 
+LAST_SETUP = {}  # filled by build_workload: who planned the routes and how long it took (reported, not timed as the metric)
 METRIC = "agent_updates_per_s"
 UNIT = "agent-updates/s"
 
@@ -107,6 +108,7 @@ def build_workload(config: str, agents: int | None, rank: int = 0, world: int = 
         np.cumsum(lens[keep], out=new_off[1:])
         pxy = np.concatenate([pxy[off[i]:off[i + 1]] for i in keep]) if len(keep) < 200_000 else _gather(pxy, off, keep)
         off = new_off
+    LAST_SETUP.update(planner=planner, plan_seconds=round(time.time() - t1, 2), queries=int(len(lens)))
     log(f"[bench] {config}: {c.n} agents sampled in {t1 - t:.1f}s, paths planned on the {planner} in {time.time() - t1:.1f}s "
         f"(mean {np.diff(off).mean():.1f} points, {int((~good).sum())} dropped)")
     if cache_file:
@@ -566,6 +568,8 @@ def run_ours(args):
                        "static_bin": st1["static_bin"]},
             "gpu_launches": int(launches), "clocks": clk,
             "counters": {k: int(st1[k]) for k in ("knn_fallbacks", "obstacle_overflows", "lp3d_runs", "location_failures", "replans")}}
+    if LAST_SETUP:
+        line["setup"] = dict(LAST_SETUP, note="route planning before the run; outside every timed region")
     if args.neighbors == "kdtree":
         line["config"]["neighbors"] = "kdtree (the reference's own lists; parity mode)"
         line["counters"].update({k: int(st1[k]) for k in ("kd_median_ties", "kd_small_ties")})
