@@ -12,6 +12,7 @@
 #   6. parity statistics of the orca_fast variant (NOT bit-exact by design)
 #   7. bench.py --neighbors kdtree        cost of the parity mode
 #   7b. bench.py --planner device         set-up with ecmgpu_plan_paths instead of the host planner
+#   7c. bench.py at 5 k / 50 k / 250 k / 4 M agents on one GPU
 #   8. ncu launch list + one --set full capture of k_orca / k_attract of the default build
 # Nothing here changes GPU clocks.  Numbers printed under ncu are never bench values.
 set -u
@@ -56,6 +57,13 @@ timeout 600 python bench.py --neighbors kdtree --no-cpu --steady-tick 0 --steps 
 
 step "bench --planner device (set-up time on stderr)"
 ECM_WORKLOAD_CACHE= timeout 900 python bench.py --planner device --no-cpu --steady-tick 0 --steps 20 >"$OUT/${TAG}_bench_devplan.json" 2>"$OUT/${TAG}_bench_devplan.err"
+
+step "bench at the other BASELINE sizes (SURVEY.md 8d: 5 k, 50 k, 250 k on one GPU; 4 M with device-planned routes)"
+for cfg in c1_5k c2_50k c5_250k; do
+  ECM_WORKLOAD_CACHE= timeout 600 python bench.py --config $cfg --no-cpu --steady-tick 0 >"$OUT/${TAG}_bench_${cfg}.json" 2>"$OUT/${TAG}_bench_${cfg}.err"
+done
+ECM_WORKLOAD_CACHE= timeout 1200 python bench.py --config c4_4m --planner device --no-cpu --steady-tick 0 --steps 50 \
+    >"$OUT/${TAG}_bench_c4_4m.json" 2>"$OUT/${TAG}_bench_c4_4m.err"
 
 step "ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/${TAG}_launches.csv" \
