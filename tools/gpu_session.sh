@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # One gpurun call that measures everything prepared on the CPU (run from the repo root on a B200 box):
 #
-#   gpurun --timeout 2400 -- 'bash tools/gpu_session.sh r02a'
+#   gpurun --timeout 3600 -- 'bash tools/gpu_session.sh r02a'      (about 40 GPU-minutes; every step has its own timeout)
 #
 # Steps (each under its own timeout, all output under gpurun_out/<tag>_*):
 #   1. pytest -m gpu                      the parity suite incl. the KD-tree mode and the full-size windows
