@@ -40,6 +40,16 @@ struct MsgHeader {  // 16 B
     int n_halo, n_migrants, pad0, pad1;
 };
 
+// Compact walk (ECMGPU_COMPACT=1, off by default): the slots this rank may own, so that the per-slot kernels of a tick
+// (pack, cell count, scatter) walk the owned share instead of every slot of the global crowd.  No slot is listed twice
+// (`in_list`), inactive entries are skipped; adopted migrants are appended, agents that left stay listed (inactive) until
+// the next rebuild.  list == nullptr: off.
+struct WalkView {
+    int* list;               // [max_agents]
+    int* n;                  // entries
+    unsigned char* in_list;  // [max_agents]
+};
+
 struct StripView {
     int enabled;
     int rank, n_ranks;
@@ -54,6 +64,7 @@ struct StripView {
     int* self_ghost_n;
     int* g_key;   // [2*cap_halo + cap_self] cell key of ghost g
     int* g_rank;
+    WalkView walk;
     __device__ __forceinline__ MsgHeader* hdr(unsigned char* m) const { return (MsgHeader*)m; }
     __device__ __forceinline__ HaloEntry* halo_of(unsigned char* m) const { return (HaloEntry*)(m + sizeof(MsgHeader)); }
     __device__ __forceinline__ MigrantEntry* migr_of(unsigned char* m) const {
@@ -75,10 +86,8 @@ __global__ void __launch_bounds__(256) k_assign_owner(int n_slots, AgentArrays a
 
 constexpr int kPackBlock = 1024;
 
-__global__ void __launch_bounds__(kPackBlock) k_pack(int n_slots, AgentArrays ag, StripView sv, unsigned long long* counters) {
-    __shared__ int s_warp[33];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool owned = i < n_slots && ag.active[i];
+// One slot of k_pack (`owned` false: a thread without an agent - it still takes part in the CTA-wide reservations).
+__device__ __forceinline__ void pack_slot(bool owned, int i, AgentArrays& ag, const StripView& sv, unsigned long long* counters, int* s_warp) {
     float2 p = make_float2(0.0f, 0.0f), v = p;
     if (owned) p = ag.pos[i];
     const int dir = !owned ? -1 : (p.x < sv.lo ? 0 : (p.x >= sv.hi ? 1 : -1));
@@ -120,7 +129,80 @@ __global__ void __launch_bounds__(kPackBlock) k_pack(int n_slots, AgentArrays ag
     }
 }
 
-__device__ __forceinline__ void adopt_migrant(AgentArrays& ag, const MigrantEntry& me) {
+__global__ void __launch_bounds__(kPackBlock) k_pack(int n_slots, AgentArrays ag, StripView sv, unsigned long long* counters) {
+    __shared__ int s_warp[33];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pack_slot(i < n_slots && ag.active[i], i, ag, sv, counters, s_warp);
+}
+
+// ---- compact walk -----------------------------------------------------------------------------------------------
+// (Re)builds the list from the active flags: after host-side changes of ownership (loads, spawns, writes of the
+// active flags, new strip borders).  `*walk.n` and `in_list` are cleared by the caller.
+__global__ void __launch_bounds__(kPackBlock) k_walk_rebuild(int n_slots, const unsigned char* __restrict__ active, WalkView walk) {
+    __shared__ int s_warp[33];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool mine = i < n_slots && active[i];
+    const int e = cta_reserve(mine, walk.n, s_warp);
+    if (mine) {
+        walk.list[e] = i;
+        walk.in_list[i] = 1;
+    }
+}
+
+// Fixed grid, every CTA makes the same number of trips (the CTA-wide reservations need all threads): the launch does
+// not depend on the list length, so the tick still replays as a CUDA graph.
+__global__ void __launch_bounds__(kPackBlock) k_pack_walk(AgentArrays ag, StripView sv, unsigned long long* counters) {
+    __shared__ int s_warp[33];
+    const int n = *sv.walk.n;
+    const int stride = gridDim.x * blockDim.x;
+    const int trips = (n + stride - 1) / stride;
+    for (int it = 0; it < trips; it++) {
+        const int idx = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const int i = idx < n ? sv.walk.list[idx] : 0;
+        pack_slot(idx < n && ag.active[i], i, ag, sv, counters, s_warp);
+    }
+}
+
+// k_bin_count / k_scatter over the list (tick.cuh has the all-slots versions).
+__global__ void __launch_bounds__(256) k_bin_count_walk(WalkView walk, const unsigned char* __restrict__ active, const float2* __restrict__ pos, GridParams gp,
+                                                        int* __restrict__ cell_count, int* __restrict__ key, int* __restrict__ rank) {
+    const int n = *walk.n;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int i = walk.list[idx];
+        if (!active[i]) { key[i] = -1; continue; }
+        const float2 p = pos[i];
+        const float fx = (p.x - gp.x0) * gp.inv_cell, fy = (p.y - gp.y0) * gp.inv_cell;
+        const int cx = fx >= 0.0f ? (fx < (float)gp.w ? (int)fx : gp.w - 1) : 0;
+        const int cy = fy >= 0.0f ? (fy < (float)gp.h ? (int)fy : gp.h - 1) : 0;
+        const int k = cy * gp.w + cx;
+        key[i] = k;
+        rank[i] = atomicAdd(&cell_count[k], 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scatter_walk(WalkView walk, const int* __restrict__ key, const int* __restrict__ rank,
+                                                      const int* __restrict__ cell_start, AgentArrays ag, TickScratch sc, int slots_only) {
+    const int n = *walk.n;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int i = walk.list[idx];
+        const int k = key[i];
+        if (k < 0) continue;
+        const int p = cell_start[k] + rank[i];
+        sc.s_slot[p] = i;
+        if (slots_only) continue;
+        sc.s_pos[p] = ag.pos[i];
+        sc.s_vel[p] = ag.vel[i];
+        sc.s_rad[p] = ag.radius[i];
+        sc.s_spd[p] = ag.speed[i];
+        sc.s_ghost[p] = 0;
+    }
+}
+
+__device__ __forceinline__ void adopt_migrant(AgentArrays& ag, const MigrantEntry& me, const WalkView& walk) {
+    if (walk.list && !walk.in_list[me.slot]) {  // one thread per migrant, one migrant per slot and tick: no race on the flag
+        walk.in_list[me.slot] = 1;
+        walk.list[atomicAdd(walk.n, 1)] = me.slot;
+    }
     ag.pos[me.slot] = make_float2(me.x, me.y);
     ag.vel[me.slot] = make_float2(me.vx, me.vy);
     ag.attraction[me.slot] = make_float2(me.ax, me.ay);
@@ -172,7 +254,7 @@ __global__ void __launch_bounds__(256) k_exchange_p2p(StripView sv, AgentArrays 
             union { MigrantEntry me; int w[sizeof(MigrantEntry) / 4]; } u;
 #pragma unroll
             for (int k = 0; k < (int)(sizeof(MigrantEntry) / 4); k++) u.w[k] = __ldcg(src + (size_t)i * (sizeof(MigrantEntry) / 4) + k);
-            adopt_migrant(ag, u.me);
+            adopt_migrant(ag, u.me, sv.walk);
         }
     }
 }
@@ -185,7 +267,7 @@ __global__ void __launch_bounds__(256) k_unpack_migrants(AgentArrays ag, StripVi
         const int n = min(((const MsgHeader*)m)->n_migrants, sv.cap_migr);
         if (i < n) {
             const MigrantEntry me = ((const MigrantEntry*)(m + sizeof(MsgHeader) + sizeof(HaloEntry) * (size_t)sv.cap_halo))[i];
-            adopt_migrant(ag, me);
+            adopt_migrant(ag, me, sv.walk);
         }
     }
 }

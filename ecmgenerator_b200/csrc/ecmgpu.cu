@@ -182,6 +182,10 @@ struct ecmgpu_sim {
     int max_ring = 8;
     int orca_block = 256;  // CTA size of k_orca (env ECMGPU_ORCA_BLOCK for experiments)
     bool fused = false;    // k_tick (attraction + ORCA in one kernel); profiling mode times k_attract / k_orca separately; env ECMGPU_FUSED=0
+    // compact walk for strips (device/strips.cuh WalkView): pack / cell count / scatter walk the owned share; env ECMGPU_COMPACT=1
+    bool compact = false, walk_dirty = true;
+    DevBuf<int> d_walk, d_walk_n;
+    DevBuf<unsigned char> d_in_walk;
     bool split = false;    // k_knn_rows + k_orca_rows instead of k_orca (same results; an A/B candidate, not measured yet); env ECMGPU_SPLIT=1
     DevBuf<int> d_nbr_q;   // split tick: [6 * rows] neighbour rows + count word
     bool gather = false;   // snapshot rows built by k_attract (gather) instead of k_scatter: measured neutral (profiles/r01_experiments.md); env ECMGPU_GATHER=1
@@ -578,11 +582,39 @@ StripView make_strip_view(ecmgpu_sim* s) {
     v.self_ghost_n = s->d_self_ghost_n.p;
     v.g_key = s->d_g_key.p;
     v.g_rank = s->d_g_rank.p;
+    const bool walk = s->compact && s->strips_on && s->d_walk.p;
+    v.walk.list = walk ? s->d_walk.p : nullptr;
+    v.walk.n = s->d_walk_n.p;
+    v.walk.in_list = s->d_in_walk.p;
     return v;
+}
+
+// Compact walk: (re)built from the active flags whenever the host changed who owns what (loads, spawns, writes of the
+// active flags, new strip borders); between rebuilds the device keeps it current (adopted migrants are appended).
+int ensure_walk(ecmgpu_sim* s) {
+    if (!s->compact || !s->strips_on) return ECMGPU_OK;
+    if (!s->d_walk.p) {
+        const size_t n = (size_t)s->prm.max_agents;
+        CUDA_TRY(s, s->d_walk.alloc(n)); CUDA_TRY(s, s->d_walk_n.alloc(1)); CUDA_TRY(s, s->d_in_walk.alloc(n));
+        s->walk_dirty = true;
+    }
+    if (!s->walk_dirty) return ECMGPU_OK;
+    CUDA_TRY(s, cudaMemsetAsync(s->d_walk_n.p, 0, sizeof(int), s->stream));
+    CUDA_TRY(s, cudaMemsetAsync(s->d_in_walk.p, 0, (size_t)s->prm.max_agents, s->stream));
+    if (s->n_slots > 0) {
+        WalkView w{s->d_walk.p, s->d_walk_n.p, s->d_in_walk.p};
+        k_walk_rebuild<<<div_up(s->n_slots, kPackBlock), kPackBlock, 0, s->stream>>>(s->n_slots, s->d_active.p, w);
+        s->launches++;
+        CUDA_TRY(s, cudaGetLastError());
+    }
+    s->walk_dirty = false;
+    return ECMGPU_OK;
 }
 
 // phase 0: pack halo / migrant / self-ghost lists from the current state
 int enqueue_pack(ecmgpu_sim* s, const TickView& t) {
+    int rc = ensure_walk(s);  // a no-op inside a graph capture: ecmgpu_update has done it before the capture began
+    if (rc) return rc;
     s->cur_gen = s->comm_seq & 1u;
     StripView sv = make_strip_view(s);
     if (s->local_transport)  // neighbours must have pulled last tick's messages before we overwrite them
@@ -591,7 +623,8 @@ int enqueue_pack(ecmgpu_sim* s, const TickView& t) {
     if (s->p2p) CUDA_TRY(s, cudaMemsetAsync(s->d_send_hdr.p, 0, 2 * sizeof(MsgHeader), s->stream));
     else for (int d = 0; d < 2; d++) CUDA_TRY(s, cudaMemsetAsync(s->d_send[d].p, 0, sizeof(MsgHeader), s->stream));
     CUDA_TRY(s, cudaMemsetAsync(s->d_self_ghost_n.p, 0, sizeof(int), s->stream));
-    k_pack<<<div_up(s->n_slots, kPackBlock), kPackBlock, 0, s->stream>>>(s->n_slots, t.ag, sv, s->d_counters.p);
+    if (sv.walk.list) k_pack_walk<<<148 * 2, kPackBlock, 0, s->stream>>>(t.ag, sv, s->d_counters.p);
+    else k_pack<<<div_up(s->n_slots, kPackBlock), kPackBlock, 0, s->stream>>>(s->n_slots, t.ag, sv, s->d_counters.p);
     s->launches++;
     if (s->local_transport) CUDA_TRY(s, cudaEventRecord(s->ev_packed, s->stream));
     CUDA_TRY(s, cudaGetLastError());
@@ -643,8 +676,9 @@ int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
     static_assert(C_LP3D_N == C_FALLBACK_N + 1, "the two per-tick counters are cleared by one memset");
     CUDA_TRY(s, cudaMemsetAsync(s->d_counters.p + C_FALLBACK_N, 0, 2 * sizeof(unsigned long long), s->stream));
     const int nb = div_up(s->n_slots, 256);
-    k_bin_count<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p);
     StripView sv = make_strip_view(s);
+    if (sv.walk.list) k_bin_count_walk<<<148 * 8, 256, 0, s->stream>>>(sv.walk, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p);
+    else k_bin_count<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p);
     const int ng = 2 * s->cap_halo + s->cap_self;
     if (s->strips_on) {
         k_ghost_count<<<div_up(ng, 256), 256, 0, s->stream>>>(sv, gp, s->d_cell_count.p);
@@ -655,7 +689,8 @@ int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
     k_scan_sums<<<1, kScanBlock, 0, s->stream>>>(s->d_block_sums.p, tiles);
     k_scan_add<<<tiles, kScanBlock, 0, s->stream>>>((int4*)s->d_cell_count.p, s->d_block_sums.p);
     if (t.gather && s->strips_on) CUDA_TRY(s, cudaMemsetAsync(s->d_s_ghost.p, 0, s->d_s_ghost.n, s->stream));
-    k_scatter<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc, t.gather);
+    if (sv.walk.list) k_scatter_walk<<<148 * 8, 256, 0, s->stream>>>(sv.walk, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc, t.gather);
+    else k_scatter<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc, t.gather);
     if (s->strips_on) {
         k_ghost_scatter<<<div_up(ng, 256), 256, 0, s->stream>>>(sv, s->d_cell_count.p, t.ag, t.sc, s->d_s_ghost.p);
         s->launches++;
@@ -994,6 +1029,7 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
     if (const char* e = getenv("ECMGPU_GATHER")) s->gather = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_FUSED")) s->fused = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_SPLIT")) s->split = atoi(e) != 0;
+    if (const char* e = getenv("ECMGPU_COMPACT")) s->compact = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_ORCA_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) s->orca_block = v; }
     s->h_path_pool.reserve(std::min<size_t>(pool, 1 << 20));
     *out = s;
@@ -1015,6 +1051,7 @@ void ecmgpu_destroy(ecmgpu_sim* s) {
     s->d_lp3d_hdr.free(); s->d_lp3d_out.free(); s->d_lp3d_cs.free();
     s->d_fb_list.free(); s->d_ev_replan.free(); s->d_ev_destroyed.free(); s->d_s_pos.free(); s->d_s_vel.free();
     s->d_s_pref.free(); s->d_s_rad.free(); s->d_s_spd.free(); s->d_s_alive.free(); s->d_counters.free(); s->d_nbr_q.free();
+    s->d_walk.free(); s->d_walk_n.free(); s->d_in_walk.free();
     kd_free(s);
     plan_free(s);
     s->d_vert_clear.free(); s->d_vert_he.free(); s->d_he_next.free();
@@ -1122,6 +1159,7 @@ int ecmgpu_bulk_load(ecmgpu_sim* s, int n, const int* slots, const float* pos_xy
     }
     s->n_slots = hi;
     s->io.owned_confirmed = -1;
+    s->walk_dirty = true;
     // host staging in slot order when contiguous, otherwise per-element copies
     const bool contiguous = [&] {
         if (!slots) return true;
@@ -1269,6 +1307,8 @@ int ecmgpu_update(ecmgpu_sim* s) {
         if (rc) return rc;
         rc = ensure_split_buffer(s);
         if (rc) return rc;
+        rc = ensure_walk(s);
+        if (rc) return rc;
         const int g = (int)(s->comm_seq & 1u);
         if (!s->graph_exec[g] || s->graph_epoch[g] != s->config_epoch || s->graph_n_slots[g] != s->n_slots) {
             if (s->graph_exec[g]) { cudaGraphExecDestroy(s->graph_exec[g]); s->graph_exec[g] = nullptr; }
@@ -1353,7 +1393,7 @@ static int xfer(ecmgpu_sim* s, int which, void* host, int first, int count, bool
     if (wait) CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     if (!to_host && (which == ECMGPU_RADIUS || which == ECMGPU_SPEED)) s->bins_dirty = true;  // ranges may have grown
     if (!to_host) s->n_slots = std::max(s->n_slots, which == ECMGPU_ACTIVE ? first + count : s->n_slots);
-    if (!to_host && which == ECMGPU_ACTIVE) s->io.owned_confirmed = -1;
+    if (!to_host && which == ECMGPU_ACTIVE) { s->io.owned_confirmed = -1; s->walk_dirty = true; }
     return ECMGPU_OK;
 }
 int ecmgpu_read(ecmgpu_sim* s, int which, void* dst, int first, int count) { return xfer(s, which, dst, first, count, true, true); }
@@ -1966,6 +2006,7 @@ int ecmgpu_comm_set_strips(ecmgpu_sim* s, const float* bounds, float halo_width)
     }
     s->strips_on = true;
     s->io.owned_confirmed = -1;
+    s->walk_dirty = true;  // ownership is re-derived below
     s->config_epoch++;
     if (s->n_slots > 0) {
         TickView t = make_view(s);

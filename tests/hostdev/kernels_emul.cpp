@@ -64,6 +64,10 @@ struct Emu {
     std::vector<unsigned char> send[2], recv[2];
     std::vector<HaloEntry> self_ghost;
     std::vector<int> self_ghost_n, g_key, g_rank;
+    // compact walk (ECMGPU_COMPACT): ecmgpu.cu ensure_walk
+    bool compact = false, walk_dirty = true;
+    std::vector<int> walk, walk_n;
+    std::vector<unsigned char> in_walk;
     // faithful KD-tree mode (kdtree.cuh)
     std::vector<unsigned long long> kd_keys[2];
     std::vector<int> kd_vals[2], kd_seg_r[2], kd_seg_node[2], kd_raw, kd_raw_cnt, kd_cache, kd_meta;
@@ -112,6 +116,8 @@ struct Emu {
         v.cap_halo = cap_halo; v.cap_migr = cap_migr; v.cap_self = cap_self;
         for (int d = 0; d < 2; d++) { v.send[d] = send[d].data(); v.recv[d] = recv[d].data(); v.send_hdr[d] = (MsgHeader*)send[d].data(); }
         v.self_ghost = self_ghost.data(); v.self_ghost_n = self_ghost_n.data(); v.g_key = g_key.data(); v.g_rank = g_rank.data();
+        const bool w = compact && strips && !walk.empty();
+        v.walk.list = w ? walk.data() : nullptr; v.walk.n = walk_n.data(); v.walk.in_list = in_walk.data();
         return v;
     }
     void append_path(int slot, const float2* pts, int np) {  // ecmgpu.cu append_path
@@ -179,6 +185,19 @@ void* emu_create(int nV, const float* vert_xy, int nE, const int* edge_v, const 
 }
 void emu_destroy(void* h) { delete (Emu*)h; }
 void emu_set_split(void* h, int on) { ((Emu*)h)->split = on != 0; }
+void emu_set_compact(void* h, int on) { Emu* e = (Emu*)h; e->compact = on != 0; e->walk_dirty = true; }
+int emu_walk_len(void* h) { Emu* e = (Emu*)h; return e->walk_n.empty() ? -1 : e->walk_n[0]; }
+// ecmgpu.cu ensure_walk
+static void emu_ensure_walk(Emu* e) {
+    if (!e->compact || !e->strips) return;
+    if (e->walk.empty()) { e->walk.assign(e->n, 0); e->walk_n.assign(1, 0); e->in_walk.assign(e->n, 0); e->walk_dirty = true; }
+    if (!e->walk_dirty) return;
+    e->walk_n[0] = 0;
+    std::fill(e->in_walk.begin(), e->in_walk.end(), 0);
+    WalkView w{e->walk.data(), e->walk_n.data(), e->in_walk.data()};
+    launch(e->n_slots, [&] { k_walk_rebuild(e->n_slots, e->active.data(), w); });
+    e->walk_dirty = false;
+}
 
 void emu_load(void* h, int n, const float* pos, const float* radius, const float* speed, const int* path_off, const float* path_xy) {
     Emu* e = (Emu*)h;
@@ -189,6 +208,7 @@ void emu_load(void* h, int n, const float* pos, const float* radius, const float
         e->append_path(i, (const float2*)path_xy + path_off[i], path_off[i + 1] - path_off[i]);
     }
     e->n_slots = std::max(e->n_slots, n);
+    e->walk_dirty = true;
 }
 void emu_set_path(void* h, int slot, const float* xy, int np) {
     Emu* e = (Emu*)h;
@@ -210,6 +230,7 @@ void emu_set_strips(void* h, int rank, int n_ranks, float lo, float hi, float ha
     const size_t cap = e->n + ng;
     e->s_pos.resize(cap); e->s_vel.resize(cap); e->s_pref.resize(cap); e->s_rad.resize(cap); e->s_spd.resize(cap);
     e->s_slot.resize(cap); e->s_alive.resize(cap); e->s_ghost.assign(cap, 0); e->fb_list.resize(cap);
+    e->walk_dirty = true;
     TickView t = e->view();
     StripView sv = e->sview();
     launch(e->n_slots, [&] { k_assign_owner(e->n_slots, t.ag, sv); });
@@ -221,9 +242,11 @@ void emu_pack(void* h) {
     if (!e->strips) return;
     for (int d = 0; d < 2; d++) memset(e->send[d].data(), 0, sizeof(MsgHeader));
     e->self_ghost_n[0] = 0;
+    emu_ensure_walk(e);
     TickView t = e->view();
     StripView sv = e->sview();
-    launch(e->n_slots, [&] { k_pack(e->n_slots, t.ag, sv, e->counters.data()); });
+    if (sv.walk.list) launch(37, [&] { k_pack_walk(t.ag, sv, e->counters.data()); });  // a fixed grid, several trips
+    else launch(e->n_slots, [&] { k_pack(e->n_slots, t.ag, sv, e->counters.data()); });
 }
 // phase 1: enqueue_exchange with the in-process transport: my left neighbour's RIGHT message is my left inbox
 void emu_exchange(void* h, void* left, void* right) {
@@ -254,14 +277,16 @@ int emu_tick(void* h) {
     GridParams gp{e->gx0, e->gy0, e->gcell, 1.0f / e->gcell, e->gw, e->gh};
     std::fill(e->cell_count.begin(), e->cell_count.end(), 0);
     e->counters[C_FALLBACK_N] = 0; e->counters[C_LP3D_N] = 0;
-    launch(e->n_slots, [&] { k_bin_count(e->n_slots, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data()); });
+    if (sv.walk.list) launch(53, [&] { k_bin_count_walk(sv.walk, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data()); });
+    else launch(e->n_slots, [&] { k_bin_count(e->n_slots, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data()); });
     const int ng = 2 * e->cap_halo + e->cap_self;
     if (e->strips) launch(ng, [&] { k_ghost_count(sv, gp, e->cell_count.data()); });
     {   // k_scan_tiles / k_scan_sums / k_scan_add: exclusive scan in place, total behind the last cell
         int run = 0;
         for (size_t c = 0; c < (size_t)e->gw * e->gh + 1; c++) { int v = e->cell_count[c]; e->cell_count[c] = run; run += v; }
     }
-    launch(e->n_slots, [&] { k_scatter(e->n_slots, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc, 0); });
+    if (sv.walk.list) launch(53, [&] { k_scatter_walk(sv.walk, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc, 0); });
+    else launch(e->n_slots, [&] { k_scatter(e->n_slots, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc, 0); });
     if (e->strips) launch(ng, [&] { k_ghost_scatter(sv, e->cell_count.data(), t.ag, t.sc, e->s_ghost.data()); });
     const int rows = e->n_slots + (e->strips ? ng : 0);
     launch(rows, [&] { k_attract(t); });

@@ -56,6 +56,8 @@ def load_emu(flags=(), tag=""):
     L.emu_tick.argtypes = [vp]
     L.emu_tick_kd.argtypes = [vp]
     L.emu_set_split.argtypes = [vp, C.c_int]
+    L.emu_set_compact.argtypes = [vp, C.c_int]
+    L.emu_walk_len.argtypes = [vp]
     L.emu_valid_spawn.argtypes = [vp, C.c_int, f32p, f32p, u8p]
     L.emu_kd_reset.argtypes = [vp]
     L.emu_query_neighbors_kd.argtypes = [vp, i32p, i32p]
@@ -236,6 +238,32 @@ def test_three_strips_equal_one_device_bitwise(emu, name, split):
     moved = int(((own0 != own1) & (st["active"] > 0)).sum())
     print(f"{name}: halo {halo:.1f} m, {moved} agents changed owner")
     assert moved >= 1, "migration must be exercised"
+    s.close()
+
+
+@pytest.mark.parametrize("name", ["c2_small", "jam_small"])
+def test_three_strips_with_compact_walk_equal_one_device_bitwise(emu, name):
+    """ECMGPU_COMPACT: pack / cell count / scatter walk a list of the slots a strip may own instead of every slot;
+    adopted migrants are appended, nobody is listed twice."""
+    g = Golden(name)
+    r5 = _r5_max(g)
+    widths = np.diff(M.strip_bounds(g.crowd.pos[:, 0], 3))[1:-1]
+    halo = float(min(2.0 * r5 + 2.0, widths.min()))
+    s = EmuStrips(emu, g, _cell_for(g), 3, halo)
+    for dev in s.devs:
+        emu.emu_set_compact(dev.h, 1)
+    own0 = M.owner_of(g.crowd.pos[:, 0], s.bounds)
+    st = _run_against_golden(s, g, s.step, s.state, f"{name} / 3 strips, compact walk")
+    assert st["owners"].max() == 1
+    assert sum(int(d.counters()[C_TOTAL_HALO_MISS]) for d in s.devs) == 0
+    own1 = M.owner_of(st["pos"][:, 0], s.bounds)
+    lens = [emu.emu_walk_len(d.h) for d in s.devs]
+    owned0 = [int((own0 == r).sum()) for r in range(3)]
+    arrived = [int(((own1 == r) & (own0 != r) & (st["active"] > 0)).sum()) for r in range(3)]
+    print(f"{name}: list lengths {lens}, owned at the start {owned0}, arrived since {arrived}")
+    assert sum(arrived) >= 1, "migration must be exercised"
+    for r in range(3):
+        assert owned0[r] + arrived[r] <= lens[r] < g.n, "a strip lists its own share plus who came, not the whole crowd"
     s.close()
 
 

@@ -63,3 +63,27 @@ def test_split_tick_with_strips_equals_single_device():
     assert np.array_equal(pos.view(np.uint32), single["pos"].view(np.uint32))
     assert np.array_equal(vel.view(np.uint32), single["vel"].view(np.uint32))
     assert sum(s["halo_misses"] for s in strips.stats()) == 0
+
+
+@pytest.mark.parametrize("name", ["c2_small", "jam_small"])
+def test_compact_walk_strips_equal_single_device(name):
+    """ECMGPU_COMPACT=1: pack / cell count / scatter walk the owned share (device/strips.cuh WalkView)."""
+    g = Golden(name)
+    ticks = min(g.ticks("exact-knn"), 120)
+    single, _ = _run(g, False, ticks)
+    os.environ["ECMGPU_COMPACT"] = "1"
+    try:
+        strips = M.LocalStrips(g.world, g.crowd, g.path_off, g.path_xy, 3, step=g.step)
+    finally:
+        os.environ.pop("ECMGPU_COMPACT", None)
+    strips.update(ticks // 2)
+    strips.rebalance()  # new borders: the lists are rebuilt
+    strips.update(ticks - ticks // 2)
+    strips.sync()
+    pos, owners = strips.gather(gpu.POS)
+    vel, _ = strips.gather(gpu.VEL)
+    live = single["active"] > 0
+    assert np.array_equal(owners > 0, live)
+    assert np.array_equal(pos[live].view(np.uint32), single["pos"][live].view(np.uint32))
+    assert np.array_equal(vel[live].view(np.uint32), single["vel"][live].view(np.uint32))
+    assert sum(s["halo_misses"] for s in strips.stats()) == 0

@@ -13,6 +13,7 @@
 #   7. bench.py --neighbors kdtree        cost of the parity mode
 #   7b. bench.py --planner device         set-up with ecmgpu_plan_paths instead of the host planner
 #   7c. bench.py at 5 k / 50 k / 250 k / 4 M agents on one GPU
+#   7d. per-kernel cost of a strip tick (8 in-process strips) with and without the compact walk
 #   8. ncu launch list + one --set full capture of k_orca / k_attract of the default build
 # Nothing here changes GPU clocks.  Numbers printed under ncu are never bench values.
 set -u
@@ -64,6 +65,13 @@ for cfg in c1_5k c2_50k c5_250k; do
 done
 ECM_WORKLOAD_CACHE= timeout 1200 python bench.py --config c4_4m --planner device --no-cpu --steady-tick 0 --steps 50 \
     >"$OUT/${TAG}_bench_c4_4m.json" 2>"$OUT/${TAG}_bench_c4_4m.err"
+
+step "strip-scale launch lists on one GPU: 8 in-process strips, all-slots walk vs ECMGPU_COMPACT=1"
+for c in 0 1; do
+  ECMGPU_COMPACT=$c timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+      --log-file "$OUT/${TAG}_strips8_compact${c}_launches.csv" python tools/strip_profile.py --strips 8 --ticks 2 \
+      >"$OUT/${TAG}_strips8_compact${c}.log" 2>&1
+done
 
 step "ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/${TAG}_launches.csv" \
