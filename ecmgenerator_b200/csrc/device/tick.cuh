@@ -459,6 +459,21 @@ __global__ void __launch_bounds__(256, ECM_ORCA_MINBLOCKS) k_orca_rows(TickView 
     }
 }
 
+// Fixed-grid versions for strips with the compact walk (ECMGPU_COMPACT=1): a rank holds n_slots = the GLOBAL crowd but
+// its snapshot has only the rows of its share (+ ghosts); launching one CTA per possible row tile would start thousands
+// of CTAs that find nothing to do.  One resident wave of CTAs walks the row tiles that exist instead.
+__global__ void __launch_bounds__(128, ECM_ATTRACT_MINBLOCKS) k_attract_tiles(TickView t) {
+    const int n = *t.n_sorted_ptr;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) attract_agent(t, base + threadIdx.x, n);
+}
+__global__ void __launch_bounds__(256, ECM_ORCA_MINBLOCKS) k_orca_tiles(TickView t) {
+    const int n = *t.n_sorted_ptr;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {  // uniform per CTA: the phase barriers stay legal
+        orca_agent(t, base + threadIdx.x, n);
+        __syncthreads();
+    }
+}
+
 // The whole per-agent tick in one kernel: the attraction phase is memory-latency bound (polyline
 // and header gathers), the ORCA phases are issue bound; with CTAs of one SM sitting in different
 // phases the two overlap instead of running back to back as k_attract + k_orca.

@@ -1280,6 +1280,10 @@ int ecmgpu_update_phase(ecmgpu_sim* s, int phase) {
         if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));  // "attract" phase is empty: all of it is k_tick
         k_tick<<<div_up(nb * 128, ob), ob, 0, s->stream>>>(t);
         s->launches -= 1;  // one kernel instead of two (3 are added below)
+    } else if (s->compact && s->strips_on && ob == 256) {  // one resident wave over the row tiles that exist (tick.cuh)
+        k_attract_tiles<<<148 * ECM_ATTRACT_MINBLOCKS, 128, 0, s->stream>>>(t);
+        if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
+        k_orca_tiles<<<148 * ECM_ORCA_MINBLOCKS, 256, 0, s->stream>>>(t);
     } else {
         k_attract<<<nb, 128, 0, s->stream>>>(t);
         if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));

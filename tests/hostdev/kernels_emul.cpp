@@ -289,16 +289,21 @@ int emu_tick(void* h) {
     else launch(e->n_slots, [&] { k_scatter(e->n_slots, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc, 0); });
     if (e->strips) launch(ng, [&] { k_ghost_scatter(sv, e->cell_count.data(), t.ag, t.sc, e->s_ghost.data()); });
     const int rows = e->n_slots + (e->strips ? ng : 0);
-    launch(rows, [&] { k_attract(t); });
-    if (e->split) {
-        e->nbr_q.assign(6 * (size_t)rows, -7);
-        t.sc.nbr_q = e->nbr_q.data();
-        launch(rows, [&] { k_knn_rows(t, rows); });
-        TickView t2 = t;
-        t2.strips = 0;
-        launch(rows, [&] { k_orca_rows(t2, rows); });
+    if (sv.walk.list && !e->split) {  // ecmgpu_update_phase: compact strips run the fixed-grid versions
+        launch(41, [&] { k_attract_tiles(t); });
+        launch(29, [&] { k_orca_tiles(t); });
     } else {
-        launch(rows, [&] { k_orca(t); });
+        launch(rows, [&] { k_attract(t); });
+        if (e->split) {
+            e->nbr_q.assign(6 * (size_t)rows, -7);
+            t.sc.nbr_q = e->nbr_q.data();
+            launch(rows, [&] { k_knn_rows(t, rows); });
+            TickView t2 = t;
+            t2.strips = 0;
+            launch(rows, [&] { k_orca_rows(t2, rows); });
+        } else {
+            launch(rows, [&] { k_orca(t); });
+        }
     }
     const int fb = (int)e->counters[C_FALLBACK_N];
     if (fb == 0) launch(64, [&] { k_fallback(t, 0); });  // the parked LP3D agents (its warp-per-agent half needs real warps)
