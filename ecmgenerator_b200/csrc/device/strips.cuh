@@ -198,6 +198,27 @@ __global__ void __launch_bounds__(256) k_scatter_walk(WalkView walk, const int* 
     }
 }
 
+// k_collect_owned (tick.cuh) over the list: the records of ecmgpu_update_io_owned.
+__global__ void __launch_bounds__(kCollectBlock) k_collect_owned_walk(WalkView walk, const unsigned char* __restrict__ active, const float2* __restrict__ pos,
+                                                                      const float2* __restrict__ vel, AgentRec* __restrict__ out, int* __restrict__ count) {
+    __shared__ int s_warp[33];
+    const int n = *walk.n;
+    const int stride = gridDim.x * blockDim.x;
+    const int trips = (n + stride - 1) / stride;
+    for (int it = 0; it < trips; it++) {
+        const int idx = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const int i = idx < n ? walk.list[idx] : 0;
+        const bool mine = idx < n && active[i];
+        const int e = cta_reserve(mine, count, s_warp);
+        if (mine) {
+            const float2 p = pos[i], v = vel[i];
+            AgentRec r;
+            r.slot = i; r.x = p.x; r.y = p.y; r.vx = v.x; r.vy = v.y;
+            out[e] = r;
+        }
+    }
+}
+
 __device__ __forceinline__ void adopt_migrant(AgentArrays& ag, const MigrantEntry& me, const WalkView& walk) {
     if (walk.list && !walk.in_list[me.slot]) {  // one thread per migrant, one migrant per slot and tick: no race on the flag
         walk.in_list[me.slot] = 1;

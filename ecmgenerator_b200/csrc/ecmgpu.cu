@@ -1500,7 +1500,9 @@ int ecmgpu_update_io_owned(ecmgpu_sim* s, int n_in, const ecmgpu_agent_rec* in, 
     CUDA_TRY(s, cudaStreamWaitEvent(s->stream, io.out_done[b], 0));
     CUDA_TRY(s, cudaMemsetAsync(so_count, 0, sizeof(int), s->stream));
     if (s->n_slots > 0) {
-        k_collect_owned<<<div_up(s->n_slots, kCollectBlock), kCollectBlock, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, s->d_vel.p, so, so_count);
+        const StripView sv = make_strip_view(s);
+        if (sv.walk.list && !s->walk_dirty) k_collect_owned_walk<<<148 * 2, kCollectBlock, 0, s->stream>>>(sv.walk, s->d_active.p, s->d_pos.p, s->d_vel.p, so, so_count);
+        else k_collect_owned<<<div_up(s->n_slots, kCollectBlock), kCollectBlock, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, s->d_vel.p, so, so_count);
         s->launches++;
     }
     CUDA_TRY(s, cudaEventRecord(io.tick_done[b], s->stream));

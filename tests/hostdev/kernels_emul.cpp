@@ -497,7 +497,9 @@ void emu_poll(void* h, int* replans, int* n_replans, int* destroyed, int* n_dest
 int emu_collect_owned(void* h, AgentRec* out) {
     Emu* e = (Emu*)h;
     int count = 0;
-    launch(e->n_slots, [&] { k_collect_owned(e->n_slots, e->active.data(), e->pos.data(), e->vel.data(), out, &count); });
+    StripView sv = e->sview();
+    if (sv.walk.list && !e->walk_dirty) launch(19, [&] { k_collect_owned_walk(sv.walk, e->active.data(), e->pos.data(), e->vel.data(), out, &count); });
+    else launch(e->n_slots, [&] { k_collect_owned(e->n_slots, e->active.data(), e->pos.data(), e->vel.data(), out, &count); });
     return count;
 }
 void emu_apply_records(void* h, int n, const AgentRec* rec) {

@@ -264,6 +264,15 @@ def test_three_strips_with_compact_walk_equal_one_device_bitwise(emu, name):
     assert sum(arrived) >= 1, "migration must be exercised"
     for r in range(3):
         assert owned0[r] + arrived[r] <= lens[r] < g.n, "a strip lists its own share plus who came, not the whole crowd"
+    # the records of ecmgpu_update_io_owned, collected over the lists: every live agent exactly once, with its state
+    seen = np.zeros(g.n, np.int32)
+    for d in s.devs:
+        rec = np.zeros(g.n, AGENT_REC)
+        m = emu.emu_collect_owned(d.h, rec.ctypes.data_as(C.c_void_p))
+        r = rec[:m]
+        seen[r["slot"]] += 1
+        assert_bits_equal(np.stack([r["x"], r["y"]], 1), st["pos"][r["slot"]], "record positions")
+    assert np.array_equal(seen, (st["active"] > 0).astype(np.int32))
     s.close()
 
 
