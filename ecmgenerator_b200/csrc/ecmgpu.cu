@@ -361,6 +361,7 @@ int build_bins(ecmgpu_sim* s) {
 int build_grid(ecmgpu_sim* s) {
     double cell = s->prm.neighbor_cell;
     const double W = (double)s->bbox[2] - s->bbox[0], H = (double)s->bbox[3] - s->bbox[1];
+    if (!(cell > 0) && s->compact && s->strips_on && s->cell > 0) cell = s->cell;  // keep what the whole crowd chose before it was cut into strips
     if (!(cell > 0)) {
         // local density = agents per occupied 4x4 patch
         std::vector<float2> pos(s->n_slots);
@@ -384,9 +385,18 @@ int build_grid(ecmgpu_sim* s) {
     }
     while ((W / cell + 3) * (H / cell + 3) > 32.0e6) cell *= 1.5;
     s->cell = (float)cell;
-    s->gx0 = (float)(s->bbox[0] - cell);
+    // Compact strips: the rank's grid covers its strip and halo only, so clearing and scanning the cell table costs the
+    // rank's share too.  Exactness does not depend on where the grid lies: agents beyond it are clamped into the border
+    // cells and the search treats block sides on the grid border as unbounded (device/knn.cuh).
+    double x_lo = s->bbox[0], x_hi = s->bbox[2];
+    if (s->compact && s->strips_on) {
+        if (s->rank > 0) x_lo = std::max(x_lo, (double)s->strip_lo - s->halo);
+        if (s->rank < s->n_ranks - 1) x_hi = std::min(x_hi, (double)s->strip_hi + s->halo);
+        if (!(x_hi > x_lo)) { x_lo = s->bbox[0]; x_hi = s->bbox[2]; }
+    }
+    s->gx0 = (float)(x_lo - cell);
     s->gy0 = (float)(s->bbox[1] - cell);
-    s->gw = (int)std::ceil((W + 2 * cell) / cell) + 1;
+    s->gw = (int)std::ceil((x_hi - x_lo + 2 * cell) / cell) + 1;
     s->gh = (int)std::ceil((H + 2 * cell) / cell) + 1;
     const int ncells = s->gw * s->gh;
     s->ncells_padded = div_up(ncells + 1, kScanTile) * kScanTile;
@@ -2013,6 +2023,7 @@ int ecmgpu_comm_set_strips(ecmgpu_sim* s, const float* bounds, float halo_width)
     s->strips_on = true;
     s->io.owned_confirmed = -1;
     s->walk_dirty = true;  // ownership is re-derived below
+    if (s->compact) s->grid_dirty = true;  // the rank's grid follows its strip (build_grid)
     s->config_epoch++;
     if (s->n_slots > 0) {
         TickView t = make_view(s);

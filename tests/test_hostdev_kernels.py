@@ -74,10 +74,13 @@ def load_emu(flags=(), tag=""):
 
 
 class EmuDevice:
-    def __init__(self, L, g: Golden, cell: float):
+    def __init__(self, L, g: Golden, cell: float, x_range=None):
+        """x_range: the grid covers only this part of the world along x (compact strips, ecmgpu.cu build_grid)."""
         w = g.world
         self.L, self.n = L, g.n
         x0, y0, x1, y1 = (float(v) for v in w.bbox)
+        if x_range is not None:
+            x0, x1 = max(x0, float(x_range[0])), min(x1, float(x_range[1]))
         gw, gh = int((x1 - x0 + 2 * cell) / cell) + 1, int((y1 - y0 + 2 * cell) / cell) + 1
         keep = [np.ascontiguousarray(a) for a in (w.vert_xy, w.edge_v, w.edge_cl, w.obst_xy, w.obst_next, w.obst_prev, w.obst_convex)]
         self.h = L.emu_create(w.n_vertices, _p(keep[0], f32p), w.n_edges, _p(keep[1], i32p), _p(keep[2], f32p), int(w.obst_next.shape[0]),
@@ -122,10 +125,16 @@ class EmuDevice:
 class EmuStrips:
     """n strips, each an EmuDevice holding all slots and owning its share (the layout of multigpu.LocalStrips)."""
 
-    def __init__(self, L, g: Golden, cell: float, n_strips: int, halo: float):
+    def __init__(self, L, g: Golden, cell: float, n_strips: int, halo: float, narrow_grid: bool = False):
         self.L, self.n = L, g.n
         self.bounds = M.strip_bounds(g.crowd.pos[:, 0], n_strips)
-        self.devs = [EmuDevice(L, g, cell) for _ in range(n_strips)]
+
+        def x_range(r):  # what build_grid gives a rank of compact strips: its strip and halo
+            if not narrow_grid:
+                return None
+            return (-np.inf if r == 0 else self.bounds[r] - halo, np.inf if r == n_strips - 1 else self.bounds[r + 1] + halo)
+
+        self.devs = [EmuDevice(L, g, cell, x_range(r)) for r in range(n_strips)]
         for r, d in enumerate(self.devs):
             lo = -np.inf if r == 0 else self.bounds[r]
             hi = np.inf if r == n_strips - 1 else self.bounds[r + 1]
@@ -249,7 +258,7 @@ def test_three_strips_with_compact_walk_equal_one_device_bitwise(emu, name):
     r5 = _r5_max(g)
     widths = np.diff(M.strip_bounds(g.crowd.pos[:, 0], 3))[1:-1]
     halo = float(min(2.0 * r5 + 2.0, widths.min()))
-    s = EmuStrips(emu, g, _cell_for(g), 3, halo)
+    s = EmuStrips(emu, g, _cell_for(g), 3, halo, narrow_grid=True)
     for dev in s.devs:
         emu.emu_set_compact(dev.h, 1)
     own0 = M.owner_of(g.crowd.pos[:, 0], s.bounds)
