@@ -77,6 +77,6 @@ step "ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/${TAG}_launches.csv" \
     python bench.py --steps 2 --warmup 3 --no-cpu --steady-tick 0 >"$OUT/${TAG}_ncu_launch_bench.log" 2>&1
 step "ncu --set full (k_orca, k_attract)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_orca|k_attract|k_scatter" --launch-skip 30 -c 6 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_orca|k_attract|k_scatter" --launch-skip 15 -c 6 \
     -o "$OUT/${TAG}_full" -f python bench.py --steps 4 --warmup 5 --no-cpu --steady-tick 0 >"$OUT/${TAG}_ncu_full_bench.log" 2>&1
 step "done"
