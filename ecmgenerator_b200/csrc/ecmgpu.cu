@@ -727,16 +727,20 @@ PlanScratch make_plan_scratch(ecmgpu_sim* s) {
     return sc;
 }
 
-// Per-worker scratch for `want` concurrent queries, within a memory budget (env ECMGPU_PLAN_MB, default 12 GB).
+// Per-worker scratch for `want` concurrent queries, within a memory budget (env ECMGPU_PLAN_MB overrides it).
 int plan_alloc(ecmgpu_sim* s, int want) {
     const size_t nV = (size_t)s->n_vertices, nE = (size_t)s->n_edges;
     const int cap_push = (int)(2 * nE + 4);                    // a query pushes at most once per directed edge, plus the two start vertices
     const int cap_path = (int)std::min<size_t>(nV + 2, 2048);  // vertices of one A* path
     const int cap_portals = 8192, cap_out = 1024;
     const size_t per_worker = nV * 13 + (size_t)cap_push * 8 + (size_t)cap_path * 8 + (size_t)cap_portals * 16 + (size_t)cap_out * 8;
-    size_t budget = (size_t)12 << 30;
+    // The kernel is latency-bound pointer chasing: the more queries in flight the better, up to what the SMs can hold
+    // (80 registers: 768 threads per SM).  Scratch budget: a quarter of the free device memory, at most 48 GB.
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(s, cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = std::min<size_t>(free_b / 4, (size_t)48 << 30);
     if (const char* e = getenv("ECMGPU_PLAN_MB")) budget = (size_t)std::max(16, atoi(e)) << 20;
-    int workers = (int)std::min<size_t>({(size_t)want, (size_t)148 * 128, std::max<size_t>(budget / per_worker, 32)});
+    int workers = (int)std::min<size_t>({(size_t)want, (size_t)148 * 768, std::max<size_t>(budget / per_worker, 32)});
     workers = div_up(workers, 32) * 32;
     if (s->pl_workers >= workers) return ECMGPU_OK;
     plan_free(s);
