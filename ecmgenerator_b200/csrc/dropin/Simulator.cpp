@@ -72,6 +72,10 @@ void Simulator::Initialize() {  // Simulator.cpp:21-60
     const auto& e = world_->ecm;
     Check(ecmgpu_set_ecm(gpu_, world_->bbox, e.num_vertices(), e.vert_xy.data(), e.vert_clear.data(), e.num_edges(),
                          e.edge_v.data(), e.edge_cl.data()), "ecmgpu_set_ecm");
+    // the half-edge rings let ecmgpu_plan_paths(GetGpuHandle(), ...) plan routes in batches on the device; the tick does
+    // not need them, so a graph they do not describe only leaves that entry point unavailable
+    if ((int)e.vert_he.size() == e.num_vertices() && (int)e.he_next.size() == 2 * e.num_edges())
+        (void)ecmgpu_set_ecm_topology(gpu_, e.vert_he.data(), e.he_next.data());
     obstacles_ = world_->obst;
     const auto& o = obstacles_;
     Check(ecmgpu_set_obstacles(gpu_, o.num_vertices(), o.xy.data(), o.next.data(), o.prev.data(), o.convex.data()), "ecmgpu_set_obstacles");
