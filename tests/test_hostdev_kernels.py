@@ -343,7 +343,7 @@ def test_valid_spawn_kernel_equals_the_reference_scan(emu):
         d.close()
 
 
-def _gloo_strip_worker(rank, world, port, name, q):
+def _gloo_strip_worker(rank, world, port, name, q, compact=0):
     """One strip per PROCESS: k_pack fills the fixed-size messages, gloo send / recv carries them to the neighbours
     (what ncclSend / ncclRecv do between the GPUs), k_unpack_migrants adopts, then the tick."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -364,6 +364,7 @@ def _gloo_strip_worker(rank, world, port, name, q):
         lo = -np.inf if rank == 0 else bounds[rank]
         hi = np.inf if rank == world - 1 else bounds[rank + 1]
         L.emu_set_strips(d.h, rank, world, np.float32(lo), np.float32(hi), np.float32(halo), 512, 128)
+        L.emu_set_compact(d.h, compact)
         nbytes = L.emu_msg_bytes(d.h)
         ok, owned_max = True, 0
         for t in range(g.ticks(mode)):
@@ -399,8 +400,8 @@ def _gloo_strip_worker(rank, world, port, name, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["jam_small"])
-def test_two_process_strips_over_gloo_equal_the_reference_bitwise(emu, name):
+@pytest.mark.parametrize("name,compact", [("jam_small", 0), ("jam_small", 1)])
+def test_two_process_strips_over_gloo_equal_the_reference_bitwise(emu, name, compact):
     import socket
 
     import torch.multiprocessing as mp
@@ -410,7 +411,7 @@ def test_two_process_strips_over_gloo_equal_the_reference_bitwise(emu, name):
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_gloo_strip_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    procs = [ctx.Process(target=_gloo_strip_worker, args=(r, 2, port, name, q, compact)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=300) for _ in procs)
