@@ -250,8 +250,8 @@ def test_three_strips_equal_one_device_bitwise(emu, name, split):
     s.close()
 
 
-@pytest.mark.parametrize("name", ["c2_small", "jam_small"])
-def test_three_strips_with_compact_walk_equal_one_device_bitwise(emu, name):
+@pytest.mark.parametrize("name,split", [("c2_small", 0), ("jam_small", 0), ("jam_small", 1)])
+def test_three_strips_with_compact_walk_equal_one_device_bitwise(emu, name, split):
     """ECMGPU_COMPACT: pack / cell count / scatter walk a list of the slots a strip may own instead of every slot;
     adopted migrants are appended, nobody is listed twice."""
     g = Golden(name)
@@ -261,6 +261,7 @@ def test_three_strips_with_compact_walk_equal_one_device_bitwise(emu, name):
     s = EmuStrips(emu, g, _cell_for(g), 3, halo, narrow_grid=True)
     for dev in s.devs:
         emu.emu_set_compact(dev.h, 1)
+        emu.emu_set_split(dev.h, split)
     own0 = M.owner_of(g.crowd.pos[:, 0], s.bounds)
     st = _run_against_golden(s, g, s.step, s.state, f"{name} / 3 strips, compact walk")
     assert st["owners"].max() == 1
