@@ -1833,6 +1833,14 @@ int ecmgpu_get_stats(ecmgpu_sim* s, ecmgpu_stats* o) {
     return ECMGPU_OK;
 }
 
+void ecmgpu_abi_sizes(int32_t out[4]) {
+    out[0] = (int32_t)sizeof(ecmgpu_params);
+    out[1] = (int32_t)sizeof(ecmgpu_stats);
+    out[2] = (int32_t)sizeof(ecmgpu_agent_rec);
+    out[3] = 20;  // members of ecmgpu_stats
+    static_assert(sizeof(ecmgpu_stats) == 10 * 4 + 10 * 8, "ecmgpu_stats changed: update out[3] and the bindings");
+}
+
 int ecmgpu_set_profiling(ecmgpu_sim* s, int on) {
     if (!s) return ECMGPU_ERR_INVALID;
     s->profiling = on != 0;

@@ -40,6 +40,7 @@ EXPORTS = [
     "ecmgpu_last_tick_ms", "ecmgpu_set_profiling", "ecmgpu_mark", "ecmgpu_mark_elapsed_ms", "ecmgpu_stream", "ecmgpu_comm_unique_id", "ecmgpu_comm_init",
     "ecmgpu_comm_set_strips", "ecmgpu_comm_init_local", "ecmgpu_update_phase", "ecmgpu_update_io", "ecmgpu_update_io_owned", "ecmgpu_io_wait", "ecmgpu_comm_p2p_export", "ecmgpu_comm_p2p_connect",
     "ecmgpu_set_neighbor_mode", "ecmgpu_valid_spawn_locations", "ecmgpu_set_ecm_topology", "ecmgpu_plan_paths",
+    "ecmgpu_abi_sizes",
 ]
 
 
@@ -112,6 +113,13 @@ def lib() -> C.CDLL:
         L.ecmgpu_set_neighbor_mode.argtypes = [vp, C.c_int]
         L.ecmgpu_valid_spawn_locations.argtypes = [vp, C.c_int, f32p, f32p, u8p]
         L.ecmgpu_set_ecm_topology.argtypes = [vp, i32p, i32p]
+        L.ecmgpu_abi_sizes.argtypes = [i32p]
+        L.ecmgpu_abi_sizes.restype = None
+        sizes = (C.c_int32 * 4)()
+        L.ecmgpu_abi_sizes(sizes)
+        mine = (C.sizeof(Params), C.sizeof(Stats), AGENT_REC.itemsize, len(Stats._fields_))
+        if tuple(sizes) != mine:  # a stale mirror would corrupt memory in ecmgpu_get_stats / ecmgpu_create
+            raise EcmGpuError(f"struct layouts of {LIB_PATH} {tuple(sizes)} differ from this binding's {mine}")
         L.ecmgpu_plan_paths.argtypes = [vp, C.c_int, f32p, f32p, f32p, i32p, i32p, u8p, f32p, C.c_int, i32p]
         L.ecmgpu_update_io_owned.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.POINTER(C.c_uint64)]
         _lib = L

@@ -220,6 +220,9 @@ typedef struct ecmgpu_stats {
     uint64_t kd_median_ties, kd_small_ties;
 } ecmgpu_stats;
 int ecmgpu_get_stats(ecmgpu_sim* sim, ecmgpu_stats* out);
+/* sizeof(ecmgpu_params), sizeof(ecmgpu_stats), sizeof(ecmgpu_agent_rec), number of ecmgpu_stats members: lets a binding in
+ * another language check its mirrors of the structs against THIS build (needs no device). */
+void ecmgpu_abi_sizes(int32_t out[4]);
 /* CUDA-event time of each phase of the LAST completed tick, milliseconds.
  * phases: 0 whole tick, 1 grid build (count+scan+scatter), 2 attraction (locate+IRM+steer), 3 ORCA (kNN+obstacles+LP+integrate) */
 int ecmgpu_last_tick_ms(ecmgpu_sim* sim, float out_ms[4]);
