@@ -350,7 +350,7 @@ class GpuSim:
         self._ck(self.L.ecmgpu_find_neighbors(self.h, n, _p(ids, i32p), _p(cnt, i32p)))
         return ids, cnt
 
-    def plan_paths(self, start, goal, clearance, points_per_path: int = 32):
+    def plan_paths(self, start, goal, clearance, points_per_path: int = 48):
         """Batched ECMPathPlanner::FindPath on the device.  Same return shape as host.plan_paths:
         (path_off[n+1], path_xy[total, 2], n_ok), paths in query order; a failed query contributes zero points."""
         start = np.ascontiguousarray(start, np.float32).reshape(-1, 2)
