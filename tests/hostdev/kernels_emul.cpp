@@ -22,12 +22,23 @@ using namespace ecm;
 
 namespace {
 
+// `block`: the CTA size the product launches the kernel with.  The plain build ignores it (one thread per block);
+// the -DHD_SIMT build (shim/simt.h) runs real blocks of co-operating threads.
 template <class F>
-void launch(int threads, F&& body) {
+void launch(int threads, F&& body, int block = 1) {
+#ifdef HD_SIMT
+    if (threads <= 0) return;
+    hd_simt_launch((threads + block - 1) / block, block, std::function<void()>(body));
+#else
+    (void)block;
     gridDim.x = threads; blockDim.x = 1; threadIdx.x = 0;
     for (int b = 0; b < threads; b++) { blockIdx.x = b; body(); }
     blockIdx.x = 0; gridDim.x = 1;
+#endif
 }
+
+struct Emu;
+static void emu_scan_cells(Emu* e);
 
 struct Emu {
     // world (one bin over everything, like hostdev.cpp)
@@ -49,7 +60,7 @@ struct Emu {
     // grid + snapshot + scratch
     float gx0 = 0, gy0 = 0, gcell = 1;
     int gw = 1, gh = 1;
-    std::vector<int> key, rank, cell_count, s_slot, fb_list, ev_replan, ev_destroyed, nbr_q;
+    std::vector<int> key, rank, cell_count, block_sums, s_slot, fb_list, ev_replan, ev_destroyed, nbr_q;
     bool split = false;  // ECMGPU_SPLIT: k_knn_rows + k_orca_rows instead of k_orca
     std::vector<float2> s_pos, s_vel, s_pref;
     std::vector<float> s_rad, s_spd;
@@ -140,6 +151,20 @@ struct Emu {
     }
 };
 
+// Exclusive scan of the cell counts in place, total behind the last cell.  SIMT build: the three scan kernels
+// themselves (tick.cuh), launched like enqueue_grid_build does; plain build: a host prefix sum stands in.
+static void emu_scan_cells(Emu* e) {
+#ifdef HD_SIMT
+    const int tiles = (int)(e->cell_count.size() / kScanTile);
+    launch(tiles * kScanBlock, [&] { k_scan_tiles((int4*)e->cell_count.data(), e->block_sums.data()); }, kScanBlock);
+    launch(kScanBlock, [&] { k_scan_sums(e->block_sums.data(), tiles); }, kScanBlock);
+    launch(tiles * kScanBlock, [&] { k_scan_add((int4*)e->cell_count.data(), e->block_sums.data()); }, kScanBlock);
+#else
+    int run = 0;
+    for (size_t c = 0; c < (size_t)e->gw * e->gh + 1; c++) { int v = e->cell_count[c]; e->cell_count[c] = run; run += v; }
+#endif
+}
+
 }  // namespace
 
 extern "C" {
@@ -174,7 +199,9 @@ void* emu_create(int nV, const float* vert_xy, int nE, const int* edge_v, const 
     e->radius.assign(n, 0); e->speed.assign(n, 0); e->active.assign(n, 0); e->replan_pending.assign(n, 0);
     e->status.assign(n, 0); e->cell.assign(n, -2); e->nbr.assign(5 * (size_t)n, -1); e->nbr_cnt.assign(n, 0);
     e->path_hdr.assign(n, PathHdr{0, 0, 0.0f, 0.0f});
-    e->key.assign(n, -1); e->rank.assign(n, 0); e->cell_count.assign((size_t)gw * gh + 2, 0);
+    e->key.assign(n, -1); e->rank.assign(n, 0);
+    const size_t padded = (((size_t)gw * gh + 1 + kScanTile - 1) / kScanTile) * kScanTile;  // ecmgpu.cu build_grid: ncells_padded
+    e->cell_count.assign(padded, 0); e->block_sums.assign(padded / kScanTile, 0);
     e->counters.assign(C_COUNT, 0ull);
     e->ev_replan.assign(n, 0); e->ev_destroyed.assign(n, 0);
     e->lp3d_hdr.resize(n); e->lp3d_out.resize(n); e->lp3d_cs.resize((size_t)n * kMaxCons);
@@ -195,7 +222,7 @@ static void emu_ensure_walk(Emu* e) {
     e->walk_n[0] = 0;
     std::fill(e->in_walk.begin(), e->in_walk.end(), 0);
     WalkView w{e->walk.data(), e->walk_n.data(), e->in_walk.data()};
-    launch(e->n_slots, [&] { k_walk_rebuild(e->n_slots, e->active.data(), w); });
+    launch(e->n_slots, [&] { k_walk_rebuild(e->n_slots, e->active.data(), w); }, kPackBlock);
     e->walk_dirty = false;
 }
 
@@ -233,7 +260,7 @@ void emu_set_strips(void* h, int rank, int n_ranks, float lo, float hi, float ha
     e->walk_dirty = true;
     TickView t = e->view();
     StripView sv = e->sview();
-    launch(e->n_slots, [&] { k_assign_owner(e->n_slots, t.ag, sv); });
+    launch(e->n_slots, [&] { k_assign_owner(e->n_slots, t.ag, sv); }, 256);
 }
 
 // phase 0: enqueue_pack
@@ -245,8 +272,8 @@ void emu_pack(void* h) {
     emu_ensure_walk(e);
     TickView t = e->view();
     StripView sv = e->sview();
-    if (sv.walk.list) launch(37, [&] { k_pack_walk(t.ag, sv, e->counters.data()); });  // a fixed grid, several trips
-    else launch(e->n_slots, [&] { k_pack(e->n_slots, t.ag, sv, e->counters.data()); });
+    if (sv.walk.list) launch(37, [&] { k_pack_walk(t.ag, sv, e->counters.data()); }, kPackBlock);  // a fixed grid, several trips
+    else launch(e->n_slots, [&] { k_pack(e->n_slots, t.ag, sv, e->counters.data()); }, kPackBlock);
 }
 // phase 1: enqueue_exchange with the in-process transport: my left neighbour's RIGHT message is my left inbox
 void emu_exchange(void* h, void* left, void* right) {
@@ -256,7 +283,7 @@ void emu_exchange(void* h, void* left, void* right) {
     if (right) e->recv[1] = ((Emu*)right)->send[0];
     TickView t = e->view();
     StripView sv = e->sview();
-    launch(std::max(e->cap_migr, 1), [&] { k_unpack_migrants(t.ag, sv); });
+    launch(std::max(e->cap_migr, 1), [&] { k_unpack_migrants(t.ag, sv); }, 256);
 }
 // The same exchange for strips that live in DIFFERENT processes (tests: torch.distributed / gloo carries the bytes
 // the way NCCL send/recv does on the GPUs): the outgoing message of direction d, the incoming one, then adopt.
@@ -267,7 +294,7 @@ void emu_adopt(void* h) {
     Emu* e = (Emu*)h;
     TickView t = e->view();
     StripView sv = e->sview();
-    launch(std::max(e->cap_migr, 1), [&] { k_unpack_migrants(t.ag, sv); });
+    launch(std::max(e->cap_migr, 1), [&] { k_unpack_migrants(t.ag, sv); }, 256);
 }
 // phase 2: enqueue_grid_build + k_attract + k_orca + k_fallback.  Returns the number of ring-budget fallbacks (must be 0).
 int emu_tick(void* h) {
@@ -277,36 +304,37 @@ int emu_tick(void* h) {
     GridParams gp{e->gx0, e->gy0, e->gcell, 1.0f / e->gcell, e->gw, e->gh};
     std::fill(e->cell_count.begin(), e->cell_count.end(), 0);
     e->counters[C_FALLBACK_N] = 0; e->counters[C_LP3D_N] = 0;
-    if (sv.walk.list) launch(53, [&] { k_bin_count_walk(sv.walk, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data()); });
-    else launch(e->n_slots, [&] { k_bin_count(e->n_slots, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data()); });
+    if (sv.walk.list) launch(53, [&] { k_bin_count_walk(sv.walk, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data()); }, 256);
+    else launch(e->n_slots, [&] { k_bin_count(e->n_slots, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data()); }, 256);
     const int ng = 2 * e->cap_halo + e->cap_self;
-    if (e->strips) launch(ng, [&] { k_ghost_count(sv, gp, e->cell_count.data()); });
-    {   // k_scan_tiles / k_scan_sums / k_scan_add: exclusive scan in place, total behind the last cell
-        int run = 0;
-        for (size_t c = 0; c < (size_t)e->gw * e->gh + 1; c++) { int v = e->cell_count[c]; e->cell_count[c] = run; run += v; }
-    }
-    if (sv.walk.list) launch(53, [&] { k_scatter_walk(sv.walk, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc, 0); });
-    else launch(e->n_slots, [&] { k_scatter(e->n_slots, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc, 0); });
-    if (e->strips) launch(ng, [&] { k_ghost_scatter(sv, e->cell_count.data(), t.ag, t.sc, e->s_ghost.data()); });
+    if (e->strips) launch(ng, [&] { k_ghost_count(sv, gp, e->cell_count.data()); }, 256);
+    emu_scan_cells(e);
+    if (sv.walk.list) launch(53, [&] { k_scatter_walk(sv.walk, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc, 0); }, 256);
+    else launch(e->n_slots, [&] { k_scatter(e->n_slots, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc, 0); }, 256);
+    if (e->strips) launch(ng, [&] { k_ghost_scatter(sv, e->cell_count.data(), t.ag, t.sc, e->s_ghost.data()); }, 256);
     const int rows = e->n_slots + (e->strips ? ng : 0);
     if (sv.walk.list && !e->split) {  // ecmgpu_update_phase: compact strips run the fixed-grid versions
-        launch(41, [&] { k_attract_tiles(t); });
-        launch(29, [&] { k_orca_tiles(t); });
+        launch(41, [&] { k_attract_tiles(t); }, 128);
+        launch(29, [&] { k_orca_tiles(t); }, 256);
     } else {
-        launch(rows, [&] { k_attract(t); });
+        launch(rows, [&] { k_attract(t); }, 128);
         if (e->split) {
             e->nbr_q.assign(6 * (size_t)rows, -7);
             t.sc.nbr_q = e->nbr_q.data();
-            launch(rows, [&] { k_knn_rows(t, rows); });
+            launch(rows, [&] { k_knn_rows(t, rows); }, 256);
             TickView t2 = t;
             t2.strips = 0;
-            launch(rows, [&] { k_orca_rows(t2, rows); });
+            launch(rows, [&] { k_orca_rows(t2, rows); }, 256);
         } else {
-            launch(rows, [&] { k_orca(t); });
+            launch(rows, [&] { k_orca(t); }, 256);
         }
     }
     const int fb = (int)e->counters[C_FALLBACK_N];
-    if (fb == 0) launch(64, [&] { k_fallback(t, 0); });  // the parked LP3D agents (its warp-per-agent half needs real warps)
+#ifdef HD_SIMT
+    launch(4 * 128, [&] { k_fallback(t, 0); }, 128);  // real warps: the exhaustive warp-per-agent search too
+#else
+    if (fb == 0) launch(64, [&] { k_fallback(t, 0); }, 128);  // the parked LP3D agents (its warp-per-agent half needs real warps)
+#endif
     return fb;
 }
 
@@ -332,7 +360,7 @@ static void emu_kd_build(Emu* e, const TickView& t) {
     b.small_ties = e->counters.data() + C_TOTAL_KD_SMALL_TIES;
     memset(e->kd_tree.data(), 0xff, sizeof(float4) * e->kd_tree.size());
     int in = 0;
-    launch(n, [&] { k_kd_init(b, e->kd_keys[0].data(), e->kd_vals[0].data(), e->kd_seg_r[0].data(), e->kd_seg_node[0].data()); });
+    launch(n, [&] { k_kd_init(b, e->kd_keys[0].data(), e->kd_vals[0].data(), e->kd_seg_r[0].data(), e->kd_seg_node[0].data()); }, 256);
     const int levels = kd_levels(n);
     std::vector<int> perm(n);
     for (int d = 0; d < levels; d++) {
@@ -346,7 +374,7 @@ static void emu_kd_build(Emu* e, const TickView& t) {
         launch(n, [&] {
             k_kd_split(b, d, sk.data(), sv.data(), e->kd_keys[out].data(), e->kd_vals[out].data(), e->kd_seg_r[d & 1].data(), e->kd_seg_node[d & 1].data(),
                        e->kd_seg_r[(d + 1) & 1].data(), e->kd_seg_node[(d + 1) & 1].data());
-        });
+        }, 256);
         in = out;
     }
 }
@@ -368,10 +396,9 @@ static void emu_grid_build(Emu* e, const TickView& t) {
     GridParams gp{e->gx0, e->gy0, e->gcell, 1.0f / e->gcell, e->gw, e->gh};
     std::fill(e->cell_count.begin(), e->cell_count.end(), 0);
     e->counters[C_FALLBACK_N] = 0; e->counters[C_LP3D_N] = 0;
-    launch(e->n_slots, [&] { k_bin_count(e->n_slots, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data()); });
-    int run = 0;
-    for (size_t c = 0; c < (size_t)e->gw * e->gh + 1; c++) { int v = e->cell_count[c]; e->cell_count[c] = run; run += v; }
-    launch(e->n_slots, [&] { k_scatter(e->n_slots, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc, 0); });
+    launch(e->n_slots, [&] { k_bin_count(e->n_slots, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data()); }, 256);
+    emu_scan_cells(e);
+    launch(e->n_slots, [&] { k_scatter(e->n_slots, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc, 0); }, 256);
 }
 
 void emu_tick_kd(void* h) {
@@ -380,19 +407,19 @@ void emu_tick_kd(void* h) {
     TickView t = e->view();
     emu_grid_build(e, t);
     const int rows = e->n_slots;
-    launch(rows, [&] { k_attract(t); });
+    launch(rows, [&] { k_attract(t); }, 128);
     emu_kd_build(e, t);
     std::copy(e->pos.begin(), e->pos.begin() + e->n_slots, e->kd_pre_pos.begin());
     std::copy(e->vel.begin(), e->vel.begin() + e->n_slots, e->kd_pre_vel.begin());
     const KdQuery q = emu_kd_query(e, true);
-    launch(rows, [&] { k_kd_query(t, q, 1); });
-    launch(e->n_slots, [&] { k_kd_resolve(e->n_slots, e->active.data(), q, e->nbr.data(), e->nbr_cnt.data()); });
-    launch(1, [&] { k_kd_cache(e->n_slots, e->active.data(), e->nbr.data(), q.cache); });
+    launch(rows, [&] { k_kd_query(t, q, 1); }, 128);
+    launch(e->n_slots, [&] { k_kd_resolve(e->n_slots, e->active.data(), q, e->nbr.data(), e->nbr_cnt.data()); }, 256);
+    launch(1, [&] { k_kd_cache(e->n_slots, e->active.data(), e->nbr.data(), q.cache); }, 256);
     TickView t2 = t;
     t2.grid.s_pos = e->kd_pre_pos.data(); t2.grid.s_vel = e->kd_pre_vel.data(); t2.grid.s_rad = e->radius.data();
     t2.record_neighbors = 0;
-    launch(rows, [&] { k_orca_kd(t2); });
-    launch(64, [&] { k_fallback(t, 0); });
+    launch(rows, [&] { k_orca_kd(t2); }, 256);
+    launch(64, [&] { k_fallback(t, 0); }, 128);
 }
 
 // k_kd_resolve + k_kd_cache on hand-made search results (ids or tokens -2 - place), for tests of the token chains
@@ -400,8 +427,8 @@ void emu_kd_resolve(int n_slots, const unsigned char* active, const int* raw, co
     KdQuery q;
     memset(&q, 0, sizeof(q));
     q.raw = (int*)raw; q.raw_cnt = (int*)raw_cnt; q.cache = cache;
-    launch(n_slots, [&] { k_kd_resolve(n_slots, active, q, nbr, nbr_cnt); });
-    launch(1, [&] { k_kd_cache(n_slots, active, nbr, cache); });
+    launch(n_slots, [&] { k_kd_resolve(n_slots, active, q, nbr, nbr_cnt); }, 256);
+    launch(1, [&] { k_kd_cache(n_slots, active, nbr, cache); }, 256);
 }
 
 // ecmgpu_find_neighbors in KD-tree mode
@@ -415,8 +442,8 @@ void emu_query_neighbors_kd(void* h, int* ids, int* cnt) {
     std::fill(e->nbr_cnt.begin(), e->nbr_cnt.end(), -1);
     const KdQuery q = emu_kd_query(e, false);
     std::fill(q.cache, q.cache + 5, 0);
-    launch(e->n_slots, [&] { k_kd_query(t, q, 0); });
-    launch(e->n_slots, [&] { k_kd_resolve(e->n_slots, e->active.data(), q, e->nbr.data(), e->nbr_cnt.data()); });
+    launch(e->n_slots, [&] { k_kd_query(t, q, 0); }, 128);
+    launch(e->n_slots, [&] { k_kd_resolve(e->n_slots, e->active.data(), q, e->nbr.data(), e->nbr_cnt.data()); }, 256);
     memcpy(ids, e->nbr.data(), 20 * (size_t)e->n);
     memcpy(cnt, e->nbr_cnt.data(), 4 * (size_t)e->n);
 }
@@ -446,11 +473,11 @@ int emu_plan_paths(void* h, int workers, int n, const float* start, const float*
     std::vector<float2> out((size_t)workers * cap_out);
     sc.g = g.data(); sc.f = f.data(); sc.parent = parent.data(); sc.visited = visited.data(); sc.heap = heap.data(); sc.touched = touched.data();
     sc.vpath = vpath.data(); sc.epath = epath.data(); sc.portals = portals.data(); sc.out = out.data();
-    launch(64, [&] { k_plan_init(sc, nV); });
+    launch(64, [&] { k_plan_init(sc, nV); }, 256);
     int cursor = 0;
     launch(workers, [&] {
         k_plan_paths(w, sc, n, (const float2*)start, (const float2*)goal, clearance, out_off, out_len, out_status, (float2*)pool, pool_cap, &cursor);
-    });
+    }, 128);
     // every query must leave the A* arrays idle again (CleanRequestData through the touched list)
     for (size_t i = 0; i < g.size(); i++)
         if (g[i] != kMaxFloat || f[i] != kMaxFloat || parent[i] != nV || visited[i]) return -1;
@@ -462,7 +489,7 @@ void emu_valid_spawn(void* h, int n, const float* xy, const float* clearance, un
     Emu* e = (Emu*)h;
     TickView t = e->view();
     emu_grid_build(e, t);
-    launch(n, [&] { k_valid_spawn(t.grid, n, (const float2*)xy, clearance, out); });
+    launch(n, [&] { k_valid_spawn(t.grid, n, (const float2*)xy, clearance, out); }, 128);
 }
 
 void emu_read(void* h, float* pos, float* vel, float* pref, float* attr, float* force, unsigned char* active, int* nbr, int* nbr_cnt,
@@ -498,13 +525,13 @@ int emu_collect_owned(void* h, AgentRec* out) {
     Emu* e = (Emu*)h;
     int count = 0;
     StripView sv = e->sview();
-    if (sv.walk.list && !e->walk_dirty) launch(19, [&] { k_collect_owned_walk(sv.walk, e->active.data(), e->pos.data(), e->vel.data(), out, &count); });
-    else launch(e->n_slots, [&] { k_collect_owned(e->n_slots, e->active.data(), e->pos.data(), e->vel.data(), out, &count); });
+    if (sv.walk.list && !e->walk_dirty) launch(19, [&] { k_collect_owned_walk(sv.walk, e->active.data(), e->pos.data(), e->vel.data(), out, &count); }, kCollectBlock);
+    else launch(e->n_slots, [&] { k_collect_owned(e->n_slots, e->active.data(), e->pos.data(), e->vel.data(), out, &count); }, kCollectBlock);
     return count;
 }
 void emu_apply_records(void* h, int n, const AgentRec* rec) {
     Emu* e = (Emu*)h;
-    launch(n, [&] { k_apply_records(n, rec, e->n, e->active.data(), e->pos.data(), e->vel.data()); });
+    launch(n, [&] { k_apply_records(n, rec, e->n, e->active.data(), e->pos.data(), e->vel.data()); }, 256);
 }
 
 }  // extern "C"

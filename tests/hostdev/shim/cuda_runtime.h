@@ -31,6 +31,7 @@ static inline T __ldg(const T* p) { return *p; }
 template <class T>
 static inline T __ldcg(const T* p) { return *p; }
 
+#ifndef HD_SIMT
 // one thread == one "warp": the warp-collective operations degenerate to identities
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline void __syncthreads() {}
@@ -41,6 +42,7 @@ template <class T>
 static inline T __shfl_sync(unsigned, T v, int) { return v; }
 template <class T>
 static inline T __shfl_up_sync(unsigned, T v, int) { return v; }
+#endif
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline void __threadfence_system() {}
@@ -54,9 +56,13 @@ static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); re
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 
+#ifdef HD_SIMT
+#include "simt.h"  // real blocks of co-operating threads (fibers) with working collectives
+#else
 // launch geometry: one thread per block (kernels_emul.cpp walks blockIdx.x over the grid)
 struct HdDim3 { int x, y, z; };
 static HdDim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
+#endif
 #define __shared__ static
 
 // RotateVector / the VO half angle use the C library's sinf / cosf (UtilityFunctions.cpp:233-242) and so does
