@@ -114,3 +114,15 @@ def test_simt_carried_list_kernel(simt):
         nbr, nbr_cnt = np.full((n, 5), -9, np.int32), np.full(n, -9, np.int32)
         simt.emu_kd_resolve(n, _p(active, u8p), _p(raw, i32p), _p(cnt, i32p), _p(cache, i32p), _p(nbr, i32p), _p(nbr_cnt, i32p))
         assert np.array_equal(cache, raw[last]), (n, last)
+
+
+@pytest.mark.parametrize("tag,flags", [("flat_prune", ["-DECM_KNN_FLAT", "-DECM_KNN_PRUNE"]), ("twopass_prune", ["-DECM_KNN_TWOPASS", "-DECM_KNN_PRUNE"]),
+                                       ("bbox4", ["-DECM_ATTRACT_BBOX4"])])
+def test_simt_build_variants(tag, flags):
+    """The switches kept for A/B, compiled INTO the kernels and run with real warps (tests/test_hostdev.py pins the same
+    switches function by function)."""
+    lib = load_emu(["-DHD_SIMT"] + flags, "_simt_" + tag)
+    g = Golden("jam_small")
+    d = EmuDevice(lib, g, _cell_for(g))
+    _run_against_golden(d, g, lambda: lib.emu_tick(d.h), d.state, f"jam_small / simt {tag}", max_ticks=24)
+    d.close()
