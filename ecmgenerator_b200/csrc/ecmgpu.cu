@@ -217,6 +217,12 @@ int fail(ecmgpu_sim* s, int code, const std::string& msg) {
     } while (0)
 
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
+// SMs of a B200: fixed-size grids are multiples of it.  (The host-side test build of this file shrinks it so that its
+// thread emulator does not have to start hundreds of thousands of idle threads per launch.)
+#ifndef ECM_SM_COUNT
+#define ECM_SM_COUNT 148
+#endif
+constexpr int kSMs = ECM_SM_COUNT;
 
 // ---- host geometry for the static bins --------------------------------------------------------
 struct Rect { double x0, y0, x1, y1; };
@@ -633,7 +639,7 @@ int enqueue_pack(ecmgpu_sim* s, const TickView& t) {
     if (s->p2p) CUDA_TRY(s, cudaMemsetAsync(s->d_send_hdr.p, 0, 2 * sizeof(MsgHeader), s->stream));
     else for (int d = 0; d < 2; d++) CUDA_TRY(s, cudaMemsetAsync(s->d_send[d].p, 0, sizeof(MsgHeader), s->stream));
     CUDA_TRY(s, cudaMemsetAsync(s->d_self_ghost_n.p, 0, sizeof(int), s->stream));
-    if (sv.walk.list) k_pack_walk<<<148 * 2, kPackBlock, 0, s->stream>>>(t.ag, sv, s->d_counters.p);
+    if (sv.walk.list) k_pack_walk<<<kSMs * 2, kPackBlock, 0, s->stream>>>(t.ag, sv, s->d_counters.p);
     else k_pack<<<div_up(s->n_slots, kPackBlock), kPackBlock, 0, s->stream>>>(s->n_slots, t.ag, sv, s->d_counters.p);
     s->launches++;
     if (s->local_transport) CUDA_TRY(s, cudaEventRecord(s->ev_packed, s->stream));
@@ -687,7 +693,7 @@ int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
     CUDA_TRY(s, cudaMemsetAsync(s->d_counters.p + C_FALLBACK_N, 0, 2 * sizeof(unsigned long long), s->stream));
     const int nb = div_up(s->n_slots, 256);
     StripView sv = make_strip_view(s);
-    if (sv.walk.list) k_bin_count_walk<<<148 * 8, 256, 0, s->stream>>>(sv.walk, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p);
+    if (sv.walk.list) k_bin_count_walk<<<kSMs * 8, 256, 0, s->stream>>>(sv.walk, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p);
     else k_bin_count<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p);
     const int ng = 2 * s->cap_halo + s->cap_self;
     if (s->strips_on) {
@@ -699,7 +705,7 @@ int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
     k_scan_sums<<<1, kScanBlock, 0, s->stream>>>(s->d_block_sums.p, tiles);
     k_scan_add<<<tiles, kScanBlock, 0, s->stream>>>((int4*)s->d_cell_count.p, s->d_block_sums.p);
     if (t.gather && s->strips_on) CUDA_TRY(s, cudaMemsetAsync(s->d_s_ghost.p, 0, s->d_s_ghost.n, s->stream));
-    if (sv.walk.list) k_scatter_walk<<<148 * 8, 256, 0, s->stream>>>(sv.walk, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc, t.gather);
+    if (sv.walk.list) k_scatter_walk<<<kSMs * 8, 256, 0, s->stream>>>(sv.walk, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc, t.gather);
     else k_scatter<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc, t.gather);
     if (s->strips_on) {
         k_ghost_scatter<<<div_up(ng, 256), 256, 0, s->stream>>>(sv, s->d_cell_count.p, t.ag, t.sc, s->d_s_ghost.p);
@@ -740,7 +746,7 @@ int plan_alloc(ecmgpu_sim* s, int want) {
     CUDA_TRY(s, cudaMemGetInfo(&free_b, &total_b));
     size_t budget = std::min<size_t>(free_b / 4, (size_t)48 << 30);
     if (const char* e = getenv("ECMGPU_PLAN_MB")) budget = (size_t)std::max(16, atoi(e)) << 20;
-    int workers = (int)std::min<size_t>({(size_t)want, (size_t)148 * 768, std::max<size_t>(budget / per_worker, 32)});
+    int workers = (int)std::min<size_t>({(size_t)want, (size_t)kSMs * 768, std::max<size_t>(budget / per_worker, 32)});
     workers = div_up(workers, 32) * 32;
     if (s->pl_workers >= workers) return ECMGPU_OK;
     plan_free(s);
@@ -752,7 +758,7 @@ int plan_alloc(ecmgpu_sim* s, int want) {
     CUDA_TRY(s, s->d_pl_portals.alloc(w * cap_portals)); CUDA_TRY(s, s->d_pl_out.alloc(w * cap_out));
     s->pl_workers = workers;
     s->pl_cap_push = cap_push; s->pl_cap_path = cap_path; s->pl_cap_portals = cap_portals; s->pl_cap_out = cap_out;
-    k_plan_init<<<148 * 8, 256, 0, s->stream>>>(make_plan_scratch(s), (int)nV);
+    k_plan_init<<<kSMs * 8, 256, 0, s->stream>>>(make_plan_scratch(s), (int)nV);
     s->launches++;
     CUDA_TRY(s, cudaGetLastError());
     return ECMGPU_OK;
@@ -1295,15 +1301,15 @@ int ecmgpu_update_phase(ecmgpu_sim* s, int phase) {
         k_tick<<<div_up(nb * 128, ob), ob, 0, s->stream>>>(t);
         s->launches -= 1;  // one kernel instead of two (3 are added below)
     } else if (s->compact && s->strips_on && ob == 256) {  // one resident wave over the row tiles that exist (tick.cuh)
-        k_attract_tiles<<<148 * ECM_ATTRACT_MINBLOCKS, 128, 0, s->stream>>>(t);
+        k_attract_tiles<<<kSMs * ECM_ATTRACT_MINBLOCKS, 128, 0, s->stream>>>(t);
         if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
-        k_orca_tiles<<<148 * ECM_ORCA_MINBLOCKS, 256, 0, s->stream>>>(t);
+        k_orca_tiles<<<kSMs * ECM_ORCA_MINBLOCKS, 256, 0, s->stream>>>(t);
     } else {
         k_attract<<<nb, 128, 0, s->stream>>>(t);
         if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
         k_orca<<<div_up(nb * 128, ob), ob, 0, s->stream>>>(t);
     }
-    k_fallback<<<148 * 4, 128, 0, s->stream>>>(t, 0);
+    k_fallback<<<kSMs * 4, 128, 0, s->stream>>>(t, 0);
     if (s->profiling) { CUDA_TRY(s, cudaEventRecord(s->ev[3], s->stream)); s->ev_valid = true; }
     s->launches += 3;
     s->ticks++;
@@ -1515,7 +1521,7 @@ int ecmgpu_update_io_owned(ecmgpu_sim* s, int n_in, const ecmgpu_agent_rec* in, 
     CUDA_TRY(s, cudaMemsetAsync(so_count, 0, sizeof(int), s->stream));
     if (s->n_slots > 0) {
         const StripView sv = make_strip_view(s);
-        if (sv.walk.list && !s->walk_dirty) k_collect_owned_walk<<<148 * 2, kCollectBlock, 0, s->stream>>>(sv.walk, s->d_active.p, s->d_pos.p, s->d_vel.p, so, so_count);
+        if (sv.walk.list && !s->walk_dirty) k_collect_owned_walk<<<kSMs * 2, kCollectBlock, 0, s->stream>>>(sv.walk, s->d_active.p, s->d_pos.p, s->d_vel.p, so, so_count);
         else k_collect_owned<<<div_up(s->n_slots, kCollectBlock), kCollectBlock, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, s->d_vel.p, so, so_count);
         s->launches++;
     }
@@ -1643,7 +1649,7 @@ int ecmgpu_find_neighbors(ecmgpu_sim* s, int count, int* out_ids5, int* out_coun
             k_kd_resolve<<<div_up(s->n_slots, 256), 256, 0, s->stream>>>(s->n_slots, s->d_active.p, q, s->d_nbr.p, s->d_nbr_cnt.p);
         } else {
             k_knn_query<<<div_up(s->n_slots + (s->strips_on ? 2 * s->cap_halo + s->cap_self : 0), 128), 128, 0, s->stream>>>(t);
-            k_fallback<<<148, 128, 0, s->stream>>>(t, 1);
+            k_fallback<<<kSMs, 128, 0, s->stream>>>(t, 1);
         }
         s->launches += 2;
         CUDA_TRY(s, cudaGetLastError());

@@ -1,0 +1,64 @@
+// TEST INFRASTRUCTURE - not part of the product, never linked into it, never loaded unless a test names it.
+//
+// A synchronous stand-in for the CUDA runtime API that csrc/ecmgpu.cu (the host side of the C ABI) uses, so that the
+// REAL host glue - buffer sizing, launch order, mode switches, the strip phases, the query and planning entry points -
+// can be driven through the real C ABI on a machine without a GPU: device memory is host memory, every "asynchronous"
+// call completes before it returns, streams and events are tokens, kernels run at once under the SIMT emulator
+// (simt.h) with the grid and block sizes the glue asked for.  tests/hostdev/mock_cuda/make_mock.py rewrites the
+// `kernel<<<grid, block, shmem, stream>>>(args)` launches of ecmgpu.cu into hd_mock_launch(grid, block, [&]{ kernel(args); }).
+// What this CANNOT show: anything about timing, overlap, CUDA graphs (refused: run with ECMGPU_GRAPH=0), peer / IPC
+// transports, or the real library sort.  The product library itself has no CPU path: without a device it refuses to run.
+#pragma once
+#include <cstdlib>
+#include <cstring>
+
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801 };
+typedef struct HdStream* cudaStream_t;
+typedef struct HdEvent* cudaEvent_t;
+typedef struct HdGraph* cudaGraph_t;
+typedef struct HdGraphExec* cudaGraphExec_t;
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0, cudaStreamCaptureModeRelaxed = 2, cudaIpcMemLazyEnablePeerAccess = 1 };
+
+static inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : (e == cudaErrorNotSupported ? "not supported by the mock runtime" : "mock runtime error"); }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaMemGetInfo(size_t* free_b, size_t* total_b) { *free_b = (size_t)2 << 30; *total_b = (size_t)4 << 30; return cudaSuccess; }
+static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)malloc(8); return cudaSuccess; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)malloc(8); return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
+// graphs: a capture would have to record work for later replays - the mock runs everything at once, so it refuses
+static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return cudaErrorNotSupported; }
+static inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t, unsigned long long) { *e = nullptr; return cudaErrorNotSupported; }
+static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+static inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+
+// kernel<<<grid, block, shmem, stream>>>(args) after make_mock.py
+template <class F>
+static inline void hd_mock_launch(int grid, int block, F&& body) {
+    if (grid <= 0 || block <= 0) return;
+    hd_simt_launch(grid, block, std::function<void()>(body));
+}

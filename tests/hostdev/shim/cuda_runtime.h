@@ -2,10 +2,19 @@
 // thread, so that the device algorithms can be checked on the CPU against the golden vectors
 // (tests/test_hostdev.py).  Nothing in the product includes this; the product path is nvcc + a GPU.
 #pragma once
+// every standard header the including files use comes FIRST: libstdc++ spells __attribute__((__noinline__)), which the
+// __noinline__ macro below would mangle if those headers were read after it
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <limits>
+#include <numeric>
+#include <string>
+#include <vector>
 
 #define __device__
 #define __host__
@@ -64,6 +73,9 @@ struct HdDim3 { int x, y, z; };
 static HdDim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
 #endif
 #define __shared__ static
+#ifdef HD_MOCK_RUNTIME
+#include "mock_runtime.h"  // tests/hostdev/mock_cuda: the host side of the runtime API, synchronous (needs HD_SIMT)
+#endif
 
 // RotateVector / the VO half angle use the C library's sinf / cosf (UtilityFunctions.cpp:233-242) and so does
 // the oracle: route the device code's single sincosf call to the same two functions

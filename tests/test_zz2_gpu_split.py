@@ -12,6 +12,16 @@ from tests.util import GOLDEN, Golden
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
 
 
+def _halo_for(g, n_strips):
+    """Comfortably more than any agent's 5th-neighbour distance at the start, but no wider than the narrowest interior
+    strip (ecmgpu_comm_set_strips refuses that): the recipe of tests/test_hostdev_kernels.py for the small golden scenes."""
+    p = g.crowd.pos.astype(np.float64)
+    d2 = ((p[:, None, :] - p[None, :, :]) ** 2).sum(-1)
+    r5 = float(np.sqrt(np.sort(d2, axis=1)[:, 5]).max())
+    widths = np.diff(M.strip_bounds(g.crowd.pos[:, 0], n_strips))[1:-1]
+    return float(min(2.0 * r5 + 2.0, widths.min())) if len(widths) else 2.0 * r5 + 2.0
+
+
 def _run(g, split, ticks):
     old = os.environ.pop("ECMGPU_SPLIT", None)
     if split:
@@ -49,7 +59,7 @@ def test_split_tick_with_strips_equals_single_device():
     single, _ = _run(g, False, 60)
     os.environ["ECMGPU_SPLIT"] = "1"
     try:
-        strips = M.LocalStrips(g.world, g.crowd, g.path_off, g.path_xy, 3, step=g.step)
+        strips = M.LocalStrips(g.world, g.crowd, g.path_off, g.path_xy, 3, step=g.step, halo=_halo_for(g, 3))
     finally:
         os.environ.pop("ECMGPU_SPLIT", None)
     strips.update(60)
@@ -65,19 +75,20 @@ def test_split_tick_with_strips_equals_single_device():
     assert sum(s["halo_misses"] for s in strips.stats()) == 0
 
 
-@pytest.mark.parametrize("name", ["c2_small", "jam_small"])
-def test_compact_walk_strips_equal_single_device(name):
+@pytest.mark.parametrize("name,rebalance", [("c2_small", False), ("jam_small", True)])
+def test_compact_walk_strips_equal_single_device(name, rebalance):
     """ECMGPU_COMPACT=1: pack / cell count / scatter walk the owned share (device/strips.cuh WalkView)."""
     g = Golden(name)
     ticks = min(g.ticks("exact-knn"), 120)
     single, _ = _run(g, False, ticks)
     os.environ["ECMGPU_COMPACT"] = "1"
     try:
-        strips = M.LocalStrips(g.world, g.crowd, g.path_off, g.path_xy, 3, step=g.step)
+        strips = M.LocalStrips(g.world, g.crowd, g.path_off, g.path_xy, 3, step=g.step, halo=_halo_for(g, 3))
     finally:
         os.environ.pop("ECMGPU_COMPACT", None)
     strips.update(ticks // 2)
-    strips.rebalance()  # new borders: the lists are rebuilt
+    if rebalance:  # new borders: lists and per-rank grids are rebuilt (c2_small's middle strip is as narrow as its halo already)
+        strips.rebalance()
     strips.update(ticks - ticks // 2)
     strips.sync()
     pos, owners = strips.gather(gpu.POS)

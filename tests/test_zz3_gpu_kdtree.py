@@ -111,7 +111,7 @@ def test_kd_mode_refuses_strips():
     g = Golden("c2_small")
     from ecmgenerator_b200 import multigpu as M
 
-    strips = M.LocalStrips(g.world, g.crowd, g.path_off, g.path_xy, 2, step=g.step)
+    strips = M.LocalStrips(g.world, g.crowd, g.path_off, g.path_xy, 2, step=g.step, halo=10.0)
     with pytest.raises(gpu.EcmGpuError):
         strips.sims[0].set_neighbor_mode(gpu.NEIGHBORS_KDTREE)
 
