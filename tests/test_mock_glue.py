@@ -4,7 +4,8 @@ tests/hostdev/mock_cuda builds csrc/ecmgpu.cu for the host against a synchronous
 its kernels under the SIMT emulator (tests/hostdev/shim/simt.h).  The tests below are a subset of the `-m gpu` tests,
 unchanged, pointed at that library through the ECMGPU_LIB hook: launch order, buffer sizing, mode switches (KD-tree
 neighbour mode, split tick, compact strips), the strip phases with the in-process transport, the planner / spawn /
-query entry points and the pipelined host I/O calls are exercised through the same ctypes binding a GPU run uses.
+query entry points, the pipelined host I/O calls and the C++ drop-in Simulator are exercised through the same bindings a
+GPU run uses.
 It cannot show timing, overlap, CUDA graphs (ECMGPU_GRAPH=0), the peer / NCCL transports or the library sort.
 TEST INFRASTRUCTURE: the product library has no CPU path and nothing in the product can load this build."""
 import os
@@ -16,9 +17,7 @@ from tests.conftest import ROOT
 SUBSET = [
     "tests/test_gpu_parity.py::test_cells_and_retraction_match_reference_golden[c2_small]",
     "tests/test_gpu_parity.py::test_neighbours_bit_exact_vs_reference_golden[0.7-c2_small]",
-    "tests/test_gpu_parity.py::test_neighbours_bit_exact_vs_reference_golden[0.0-jam_small]",
     "tests/test_gpu_parity.py::test_lockstep_velocities_within_tolerance[c2_small]",
-    "tests/test_gpu_parity.py::test_free_running_matches_reference_golden[jam_small]",
     "tests/test_gpu_parity.py::test_sparse_crowd_uses_exhaustive_fallback_and_stays_exact",
     "tests/test_gpu_parity.py::test_ties_and_colocated_agents",
     "tests/test_gpu_parity.py::test_arrival_destroy_and_replan_events",
@@ -26,6 +25,10 @@ SUBSET = [
     "tests/test_gpu_parity.py::test_obstacle_lists_match_oracle",
     "tests/test_gpu_parity.py::test_update_io_pipeline_matches_plain_update",
     "tests/test_gpu_parity.py::test_update_io_owned_records_match_plain_update",
+    # the C++ drop-in Simulator (libecmsim.so): the mock library is preloaded, so its ecmgpu_* symbols are the ones bound
+    "tests/test_gpu_simulator_dropin.py::test_spawn_update_getters_match_reference",
+    "tests/test_gpu_simulator_dropin.py::test_dropin_matches_c_oracle_with_host_planner",
+    "tests/test_gpu_simulator_dropin.py::test_add_obstacle_area_equals_a_world_that_had_the_box_all_along",
     "tests/test_gpu_strips.py::test_halo_miss_is_detected_when_the_halo_is_too_small",
     "tests/test_gpu_strips.py::test_strip_validation_errors",
     "tests/test_zz2_gpu_spawn.py::test_valid_spawn_locations_equal_the_reference_scan[0.0]",
@@ -34,7 +37,7 @@ SUBSET = [
     "tests/test_zz2_gpu_split.py::test_compact_walk_strips_equal_single_device[jam_small-True]",
     "tests/test_zz3_gpu_kdtree.py::test_kd_neighbour_lists_equal_the_unmodified_reference[c2_small]",
     "tests/test_zz3_gpu_kdtree.py::test_kd_lockstep_velocities_within_tolerance[c2_small]",
-    "tests/test_zz3_gpu_kdtree.py::test_kd_free_running_matches_the_unmodified_reference[jam_small]",
+    "tests/test_zz3_gpu_kdtree.py::test_dropin_in_kd_mode_walks_like_the_unmodified_reference",
     "tests/test_zz3_gpu_kdtree.py::test_kd_mode_refuses_strips",
     "tests/test_zz4_gpu_planner.py::test_device_planner_reproduces_the_reference_polylines[c2_small]",
     "tests/test_zz4_gpu_planner.py::test_device_planner_small_pool_is_retried",
@@ -46,7 +49,7 @@ def test_gpu_suite_subset_through_the_real_c_abi_on_the_mock_runtime():
     import make_mock
 
     so = make_mock.build()
-    env = dict(os.environ, ECMGPU_LIB=so, ECMGPU_GRAPH="0")
+    env = dict(os.environ, ECMGPU_LIB=so, ECMGPU_GRAPH="0", LD_PRELOAD=so)  # LD_PRELOAD: for libecmsim.so, linked against libecmgpu
     for k in ("ECMGPU_SPLIT", "ECMGPU_COMPACT", "ECMGPU_FUSED", "ECMGPU_GATHER"):
         env.pop(k, None)
     r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + SUBSET, cwd=ROOT, env=env,
@@ -54,4 +57,4 @@ def test_gpu_suite_subset_through_the_real_c_abi_on_the_mock_runtime():
     tail = "\n".join(r.stdout.splitlines()[-25:])
     print(tail)
     assert r.returncode == 0, tail + "\n" + r.stderr[-2000:]
-    assert f"{len(SUBSET)} passed" in r.stdout
+    assert f"{len(SUBSET)} passed" in r.stdout or f"{len(SUBSET) - 2} passed, 2 skipped" in r.stdout  # two need oracle/_ref
