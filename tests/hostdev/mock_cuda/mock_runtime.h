@@ -9,12 +9,14 @@
 // What this CANNOT show: anything about timing, overlap, CUDA graphs (refused: run with ECMGPU_GRAPH=0), peer / IPC
 // transports, or the real library sort.  The product library itself has no CPU path: without a device it refuses to run.
 #pragma once
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801 };
 typedef struct HdStream* cudaStream_t;
+struct HdEvent { double t_ms; };  // an event is the wall-clock time of its record: elapsed times are host times
 typedef struct HdEvent* cudaEvent_t;
 typedef struct HdGraph* cudaGraph_t;
 typedef struct HdGraphExec* cudaGraphExec_t;
@@ -39,12 +41,13 @@ static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
-static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)malloc(8); return cudaSuccess; }
-static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)malloc(8); return cudaSuccess; }
-static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
-static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline double hd_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new HdEvent{hd_now_ms()}; return cudaSuccess; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new HdEvent{hd_now_ms()}; return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t_ms = hd_now_ms(); return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
-static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t_ms - a->t_ms); return cudaSuccess; }
 // graphs: a capture would have to record work for later replays - the mock runs everything at once, so it refuses
 static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { return cudaErrorNotSupported; }
 static inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return cudaErrorNotSupported; }

@@ -112,4 +112,5 @@ def check_window_against_oracle(world, step, before, after, radius, speed, path_
     assert dp.max() <= vel_tol, f"{label}: max |dp| = {dp.max()}"
     same = (after["vel"][inner][alive].view(np.uint32) == st["vel"][inner_l][alive].view(np.uint32)).all(axis=1)
     return {"members": m, "inner": int(len(inner)), "evaluated_cells": int(evaluated.sum()), "max_dv": float(dv.max()),
-            "velocity_rows_bit_identical": float(same.mean()), "moving": float((np.linalg.norm(before["vel"][inner], axis=1) > 0.1).mean())}
+            "velocity_rows_bit_identical": float(same.mean()), "moving": float((np.linalg.norm(before["vel"][inner], axis=1) > 1e-3).mean()),
+            "mean_speed": float(np.linalg.norm(before["vel"][inner], axis=1).mean())}
