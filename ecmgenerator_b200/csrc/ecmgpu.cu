@@ -704,7 +704,9 @@ int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
     k_scan_tiles<<<tiles, kScanBlock, 0, s->stream>>>((int4*)s->d_cell_count.p, s->d_block_sums.p);
     k_scan_sums<<<1, kScanBlock, 0, s->stream>>>(s->d_block_sums.p, tiles);
     k_scan_add<<<tiles, kScanBlock, 0, s->stream>>>((int4*)s->d_cell_count.p, s->d_block_sums.p);
-    if (t.gather && s->strips_on) CUDA_TRY(s, cudaMemsetAsync(s->d_s_ghost.p, 0, s->d_s_ghost.n, s->stream));
+    // gather mode: k_scatter writes only the slot list, so nobody clears the ghost flags of the owned rows (without strips
+    // nobody ever wrote them: a fresh allocation is not guaranteed to be zero)
+    if (t.gather) CUDA_TRY(s, cudaMemsetAsync(s->d_s_ghost.p, 0, s->d_s_ghost.n, s->stream));
     if (sv.walk.list) k_scatter_walk<<<kSMs * 8, 256, 0, s->stream>>>(sv.walk, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc, t.gather);
     else k_scatter<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc, t.gather);
     if (s->strips_on) {

@@ -29,7 +29,14 @@ static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaMemGetInfo(size_t* free_b, size_t* total_b) { *free_b = (size_t)2 << 30; *total_b = (size_t)4 << 30; return cudaSuccess; }
-static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+// fresh device memory is POISONED: cudaMalloc promises nothing about its content, and a kernel that reads what nobody
+// wrote should fail here rather than pass because a fresh GPU allocation happened to be zero
+static inline cudaError_t cudaMalloc(void** p, size_t n) {
+    *p = malloc(n ? n : 1);
+    if (!*p) return cudaErrorMemoryAllocation;
+    memset(*p, 0xA5, n);
+    return cudaSuccess;
+}
 static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
