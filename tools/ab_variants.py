@@ -23,9 +23,10 @@ def main():
 
     specs = sys.argv[1:] or ["base"]
     config = os.environ.get("AB_CONFIG", "c3_1m")
-    w, c, off, pxy = bench.build_workload(config, None)
+    w, c, off, pxy = bench.build_workload(config, int(os.environ["AB_AGENTS"]) if os.environ.get("AB_AGENTS") else None)
     n = c.n
     ref = None
+    default_lib = os.environ.get("ECMGPU_LIB") or os.path.join(os.path.dirname(gpu.__file__), "libecmgpu.so")
     for spec in specs:
         parts = spec.split(",")
         name, _, path = parts[0].partition("=")
@@ -34,7 +35,7 @@ def main():
             del os.environ[k]
         os.environ.update(env)
         gpu._lib = None
-        gpu.LIB_PATH = os.path.abspath(path) if path else os.path.join(os.path.dirname(gpu.__file__), "libecmgpu.so")
+        gpu.LIB_PATH = os.path.abspath(path) if path else default_lib
         # AB_CELL: neighbour-grid cell edge in metres (default: chosen from the crowd's density)
         sim = gpu.GpuSim(w, n, float(S.DT), device=0, record_neighbors=False, path_pool_points=int(off[-1]) + 8 * n + 4096,
                          neighbor_cell=float(os.environ.get("AB_CELL", "0")))
