@@ -24,6 +24,9 @@ python -c "import __graft_entry__ as g; g.build()" >>"$OUT/${TAG}_session.log" 2
 step "strips tests"
 timeout 900 python -m pytest tests/test_gpu_strips.py tests/test_zz2_gpu_split.py -m gpu -q -s >"$OUT/${TAG}_strips_tests.log" 2>&1
 echo "pytest exit $?" | tee -a "$OUT/${TAG}_session.log"
+step "strips tests with ECMGPU_COMPACT=1 (every transport with the compact walk)"
+ECMGPU_COMPACT=1 timeout 900 python -m pytest tests/test_gpu_strips.py -m gpu -q -s >"$OUT/${TAG}_strips_tests_compact.log" 2>&1
+echo "pytest exit $?" | tee -a "$OUT/${TAG}_session.log"
 step "bench c3_1m x$N, default strips"
 run_bench bench_n${N} "ECMGPU_COMPACT=0" --steady-tick 0
 step "bench c3_1m x$N, compact walk"
