@@ -11,8 +11,8 @@ struct DoubleBuffer {
     T* d_buffers[2];
     int selector = 0;
     DoubleBuffer(T* current, T* alternate) { d_buffers[0] = current; d_buffers[1] = alternate; }
-    T* Current() { return d_buffers[selector]; }
-    T* Alternate() { return d_buffers[selector ^ 1]; }
+    T* Current() const { return d_buffers[selector]; }
+    T* Alternate() const { return d_buffers[selector ^ 1]; }
 };
 struct DeviceRadixSort {
     template <class K, class V>

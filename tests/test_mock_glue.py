@@ -6,7 +6,8 @@ unchanged, pointed at that library through the ECMGPU_LIB hook: launch order, bu
 neighbour mode, split tick, compact strips), the strip phases with the in-process transport, the planner / spawn /
 query entry points, the pipelined host I/O calls and the C++ drop-in Simulator are exercised through the same bindings a
 GPU run uses.
-It cannot show timing, overlap, CUDA graphs (ECMGPU_GRAPH=0), the peer / NCCL transports or the library sort.
+The tick runs as a captured graph like on the GPU (the mock records the capture and replays it).  It cannot show timing,
+overlap, the peer / NCCL transports or the library sort.
 TEST INFRASTRUCTURE: the product library has no CPU path and nothing in the product can load this build."""
 import os
 import subprocess
@@ -46,7 +47,8 @@ def test_gpu_suite_subset_through_the_real_c_abi_on_the_mock_runtime():
     import make_mock
 
     so = make_mock.build()
-    env = dict(os.environ, ECMGPU_LIB=so, ECMGPU_GRAPH="0", LD_PRELOAD=so)  # LD_PRELOAD: for libecmsim.so, linked against libecmgpu
+    env = dict(os.environ, ECMGPU_LIB=so, LD_PRELOAD=so)  # LD_PRELOAD: for libecmsim.so, linked against libecmgpu
+    env.pop("ECMGPU_GRAPH", None)  # graphs on, as on the GPU: the mock records a capture as closures and replays them
     for k in ("ECMGPU_SPLIT", "ECMGPU_COMPACT", "ECMGPU_FUSED", "ECMGPU_GATHER"):
         env.pop(k, None)
     r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + SUBSET, cwd=ROOT, env=env,
