@@ -98,3 +98,43 @@ def test_compact_walk_strips_equal_single_device(name, rebalance):
     assert np.array_equal(pos[live].view(np.uint32), single["pos"][live].view(np.uint32))
     assert np.array_equal(vel[live].view(np.uint32), single["vel"][live].view(np.uint32))
     assert sum(s["halo_misses"] for s in strips.stats()) == 0
+
+
+def test_compact_walk_in_the_graph_tick_with_spawns_and_destroys():
+    """One rank that owns the whole world, driven through ecmgpu_update (the captured-graph tick): with ECMGPU_COMPACT=1
+    the list-walking kernels sit inside the graph while the list itself is rebuilt outside it whenever the host changes
+    who exists (a destroy leaves a stale entry, a spawn forces a rebuild).  Must equal the plain simulator doing the same."""
+    g = Golden("c2_small")
+    n0 = g.n - 20  # the last 20 agents are spawned later
+
+    def run(compact):
+        os.environ.pop("ECMGPU_COMPACT", None)
+        if compact:
+            os.environ["ECMGPU_COMPACT"] = "1"
+        try:
+            sim = gpu.GpuSim(g.world, g.n + 8, g.step)
+        finally:
+            os.environ.pop("ECMGPU_COMPACT", None)
+        off = g.path_off
+        sim.bulk_load(g.crowd.pos[:n0], g.crowd.radius[:n0], g.crowd.speed[:n0], off[: n0 + 1], g.path_xy[: off[n0]])
+        if compact:
+            x0, _, x1, _ = (float(v) for v in g.world.bbox)
+            sim.comm_set_strips(np.float32([x0 - 10.0, x1 + 10.0]), 5.0)  # rank 0 of 1: no neighbours, no transport
+        sim.update(15)
+        for s in (3, 77, 140):
+            sim.destroy_agent(s)
+        sim.update(15)
+        for i in range(n0, g.n):  # late arrivals, one slot at a time like Simulator::SpawnAgent
+            sim.spawn(i, g.crowd.pos[i], g.crowd.radius[i], g.crowd.speed[i], g.path_xy[off[i]:off[i + 1]])
+        sim.update(30)
+        st = sim.state(g.n)
+        launches = sim.stats()["kernel_launches"]
+        sim.close()
+        return st, launches
+
+    a, la = run(False)
+    b, lb = run(True)
+    assert not a["active"][[3, 77, 140]].any() and a["active"][n0:].all()
+    for k in a:
+        assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), f"{k} differs"
+    assert lb > la  # the pack kernel (and the list rebuilds) ran
