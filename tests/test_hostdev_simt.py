@@ -28,7 +28,8 @@ def simt():
 def test_simt_kernels_reproduce_reference_trajectories_bitwise(simt, name):
     g = Golden(name)
     d = EmuDevice(simt, g, _cell_for(g))
-    _run_against_golden(d, g, lambda: simt.emu_tick(d.h), d.state, f"{name} / simt")
+    # the jam runs in full (its LP3D queue and finisher fill up late); the two calm scenes show nothing new after a while
+    _run_against_golden(d, g, lambda: simt.emu_tick(d.h), d.state, f"{name} / simt", max_ticks=None if name == "jam_small" else 24)
     if name == "jam_small":
         assert d.counters()[C_TOTAL_LP3D] > 300
     d.close()
@@ -38,7 +39,7 @@ def test_simt_split_tick(simt):
     g = Golden("jam_small")
     d = EmuDevice(simt, g, _cell_for(g))
     simt.emu_set_split(d.h, 1)
-    _run_against_golden(d, g, lambda: simt.emu_tick(d.h), d.state, "jam_small / simt split")
+    _run_against_golden(d, g, lambda: simt.emu_tick(d.h), d.state, "jam_small / simt split", max_ticks=64)
     d.close()
 
 
@@ -49,7 +50,7 @@ def test_simt_exhaustive_fallback_search(simt):
     d = EmuDevice(simt, g, 0.12)
     fallbacks = 0
     mode = "exact-knn"
-    ticks = 3
+    ticks = 1
     for t in range(ticks):
         fallbacks += simt.emu_tick(d.h)
         st = d.state()
@@ -72,7 +73,7 @@ def test_simt_three_strips(simt, compact):
     s = EmuStrips(simt, g, _cell_for(g), 3, halo, narrow_grid=bool(compact))
     for dev in s.devs:
         simt.emu_set_compact(dev.h, compact)
-    st = _run_against_golden(s, g, s.step, s.state, f"jam_small / simt, 3 strips, compact={compact}", max_ticks=48)
+    st = _run_against_golden(s, g, s.step, s.state, f"jam_small / simt, 3 strips, compact={compact}", max_ticks=24)
     assert st["owners"].max() == 1
     assert sum(int(d.counters()[C_TOTAL_HALO_MISS]) for d in s.devs) == 0
     seen = np.zeros(g.n, np.int32)
@@ -93,7 +94,7 @@ def test_simt_kd_mode(simt):
         simt.emu_tick_kd(d.h)
         return 0
 
-    _run_against_golden(d, g, step, d.state, "c2_small / simt kd", mode="ref-kdtree")
+    _run_against_golden(d, g, step, d.state, "c2_small / simt kd", mode="ref-kdtree", max_ticks=32)
     d.close()
 
 
@@ -116,8 +117,8 @@ def test_simt_carried_list_kernel(simt):
         assert np.array_equal(cache, raw[last]), (n, last)
 
 
-@pytest.mark.parametrize("tag,flags", [("flat_prune", ["-DECM_KNN_FLAT", "-DECM_KNN_PRUNE"]), ("twopass_prune", ["-DECM_KNN_TWOPASS", "-DECM_KNN_PRUNE"]),
-                                       ("bbox4", ["-DECM_ATTRACT_BBOX4"])])
+@pytest.mark.parametrize("tag,flags", [("flat_twopass_prune_bbox4", ["-DECM_KNN_FLAT", "-DECM_KNN_PRUNE", "-DECM_ATTRACT_BBOX4"]),
+                                       ("twopass_prune", ["-DECM_KNN_TWOPASS", "-DECM_KNN_PRUNE"])])
 def test_simt_build_variants(tag, flags):
     """The switches kept for A/B, compiled INTO the kernels and run with real warps (tests/test_hostdev.py pins the same
     switches function by function)."""
