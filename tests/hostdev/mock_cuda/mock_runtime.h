@@ -26,7 +26,7 @@ typedef struct HdEvent* cudaEvent_t;
 struct HdGraph { std::vector<std::function<void()>> ops; };
 typedef HdGraph* cudaGraph_t;
 typedef HdGraph* cudaGraphExec_t;
-inline HdGraph* hd_capturing = nullptr;  // one stream captures at a time (everything here is single-threaded)
+inline thread_local HdGraph* hd_capturing = nullptr;  // per OS thread (one rank per thread in the multi-rank tests)
 template <class F>
 static inline void hd_enqueue(F&& op) {
     if (hd_capturing) hd_capturing->ops.push_back(std::function<void()>(op));
@@ -73,8 +73,9 @@ static inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g
 static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t) { for (auto& op : e->ops) op(); return cudaSuccess; }
 static inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
 static inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { delete e; return cudaSuccess; }
-static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+// all "devices" share this process's address space: a handle is the pointer itself
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return cudaSuccess; }
 static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 
 // kernel<<<grid, block, shmem, stream>>>(args) after make_mock.py

@@ -4,6 +4,8 @@
 #pragma once
 // every standard header the including files use comes FIRST: libstdc++ spells __attribute__((__noinline__)), which the
 // __noinline__ macro below would mangle if those headers were read after it
+#include <sched.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -54,8 +56,8 @@ static inline T __shfl_up_sync(unsigned, T v, int) { return v; }
 #endif
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
-static inline void __threadfence_system() {}
-static inline void __nanosleep(unsigned) {}
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __nanosleep(unsigned) { sched_yield(); }  // a spinning lane lets the other ranks' threads run
 
 template <class T, class U>
 static inline T atomicAdd(T* p, U v) { T old = *p; *p = (T)(old + (T)v); return old; }
@@ -72,7 +74,11 @@ static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f
 struct HdDim3 { int x, y, z; };
 static HdDim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
 #endif
+#ifdef HD_SIMT
+#define __shared__ static thread_local  // CTAs run one after another per OS thread; ranks on other threads have their own
+#else
 #define __shared__ static
+#endif
 #ifdef HD_MOCK_RUNTIME
 #include "mock_runtime.h"  // tests/hostdev/mock_cuda: the host side of the runtime API, synchronous (needs HD_SIMT)
 #endif

@@ -47,10 +47,10 @@ struct Cta {
     int current = -1;
     const std::function<void()>* body = nullptr;
 };
-inline Cta* g_cta = nullptr;
+inline thread_local Cta* g_cta = nullptr;  // per OS thread: the mock-runtime tests run one rank per thread
 constexpr size_t kStack = 512 * 1024;  // the kernels keep a few KB of constraint arrays per thread
 inline std::vector<char*>& stack_pool() {
-    static std::vector<char*> pool;
+    static thread_local std::vector<char*> pool;
     return pool;
 }
 
@@ -89,7 +89,7 @@ inline int my_lane() { return g_cta->fibers[g_cta->current].tid & 31; }
 
 // launch geometry: blockIdx / threadIdx are rewritten by the scheduler whenever it resumes a fiber
 struct HdDim3 { int x, y, z; };
-static HdDim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
+static thread_local HdDim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
 
 // Runs `body` as grid x block threads.
 inline void hd_simt_launch(int grid, int block, const std::function<void()>& body) {

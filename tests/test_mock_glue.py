@@ -58,3 +58,25 @@ def test_gpu_suite_subset_through_the_real_c_abi_on_the_mock_runtime():
     print(tail)
     assert r.returncode == 0, tail + "\n" + r.stderr[-2000:]
     assert f"{len(SUBSET)} passed" in r.stdout or f"{len(SUBSET) - 2} passed, 2 skipped" in r.stdout  # two need oracle/_ref
+
+
+def _threaded(name, ranks, transport, compact, ticks):
+    import json
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "hostdev", "mock_cuda", "threaded_strips.py"), name, str(ranks), transport,
+                        str(compact), str(ticks)], cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_one_strip_per_thread_over_the_nccl_and_peer_transports():
+    """The multi-rank tick as `torchrun` drives it - ecmgpu_update on every rank, NCCL send / recv or the peer transport
+    (k_pack storing into the neighbour's inbox, k_exchange_p2p spinning on the sequence number the neighbour writes, the
+    tick replayed as a captured graph per inbox generation) - with the ranks as THREADS of one process on the mock
+    runtime (mock_nccl.cpp, mock IPC handles).  Bit for bit against the reference's golden trajectory, migrations
+    included, with and without the compact walk."""
+    for transport, compact in (("nccl", 0), ("p2p", 1)):
+        res = _threaded("jam_small", 3, transport, compact, 160)
+        print(transport, compact, res)
+        assert res["owners_ok"] and res["pos_equal"] and res["vel_equal"] and res["halo_misses"] == 0
+        assert res["moved"] >= 3 and max(res["owned"]) < 200
