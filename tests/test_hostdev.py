@@ -42,7 +42,7 @@ def hd(request):
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         os.makedirs(os.path.dirname(so), exist_ok=True)
         # -ffp-contract=off == nvcc -fmad=false: IEEE mul / add without contraction; div / sqrt are IEEE on both sides
-        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HD, "shim"),
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-gnu-unique", "-fPIC", "-shared", "-I", os.path.join(HD, "shim"),
                                "-o", so, src] + VARIANTS[request.param])
     L = C.CDLL(so)
     L.hd_world.restype = C.c_void_p

@@ -32,14 +32,16 @@ def emu():
 
 
 def load_emu(flags=(), tag=""):
-    """flags: extra -D switches (build variants kept for A/B); tag names the library file."""
+    """flags: extra -D switches (build variants kept for A/B); tag names the library file.
+    -fno-gnu-unique: several builds of the same device code live in one test process; g++ would otherwise make the
+    statics of inline functions (the kernels' `__shared__` arrays) process-wide unique symbols shared by all of them."""
     so = os.path.join(HD, "_build", f"libkernels_emul{tag}.so")
     src = os.path.join(HD, "kernels_emul.cpp")
     dev = os.path.join(ROOT, "ecmgenerator_b200", "csrc", "device")
     deps = [src] + [os.path.join(HD, "shim", f) for f in os.listdir(os.path.join(HD, "shim"))] + [os.path.join(dev, f) for f in os.listdir(dev)]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         os.makedirs(os.path.dirname(so), exist_ok=True)
-        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HD, "shim"),
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-gnu-unique", "-fPIC", "-shared", "-I", os.path.join(HD, "shim"),
                                "-o", so, src] + list(flags))
     L = C.CDLL(so)
     vp = C.c_void_p
