@@ -38,7 +38,9 @@ __device__ __forceinline__ void warp_align() {
 // (k_orca was instruction-fetch bound: stall_no_instruction 4.9-14.7 per issue, profiles/).
 template <bool kSync>
 __device__ __forceinline__ void phase_barrier() {
+#ifndef ECM_NO_PHASE_BARRIER  // A/B switch (tools/build_variants.py)
     if (kSync) __syncthreads();
+#endif
 }
 
 __device__ __forceinline__ v2 V(float x, float y) { return make_float2(x, y); }
@@ -61,12 +63,16 @@ __device__ __noinline__ v2 vnormalized(v2 a) {
     return V(a.x / l, a.y / l);
 }
 // Arithmetic of the ORCA half-planes and linear programs only (orca.cuh).  Their contract is "new velocities within
-// 1e-4 m/s", not bit-exactness, so a build with -DECM_ORCA_FAST may use the SFU approximations (division 2 ulp,
-// square root 1 ulp, sine / cosine 2^-21 absolute) instead of the ~10-instruction IEEE sequences, which are a quarter
-// of k_orca's instructions (profiles/r01_v8_k_orca_by_function.txt).  Off by default: an A/B on the GPU has to show
-// both the gain and the parity statistics (tools/build_variants.py).  Everything that feeds a bit-exact decision
-// (cells, neighbour order, the obstacle range filter, preferred velocities) stays IEEE in either build.
-#ifdef ECM_ORCA_FAST
+// 1e-4 m/s per step" (BASELINE.json north_star), not bit-exactness, so they use the SFU approximations (division 2 ulp,
+// square root 1 ulp, sine / cosine 2^-21 absolute) instead of the ~10-instruction IEEE sequences, which were a quarter
+// of k_orca's warp instructions (profiles/r01_v8_k_orca_by_function.txt).  Measured on one B200, 1 M agents
+// (profiles/r02a_ab_rest.jsonl, r02a_ab_congested.jsonl, r02a_orca_fast_parity.log): tick 0.561 -> 0.497 ms from rest,
+// 0.644 -> 0.577 ms congested; worst |dv| per step against the reference 1.2e-7 .. 4.8e-7 m/s (tolerance 1e-4),
+// 84-87 % of the velocity rows still bit-identical, 600-tick trajectory RMS 6.5e-7 m.  Everything that feeds a
+// bit-exact decision (cells, neighbour order, the obstacle range filter, preferred velocities) stays IEEE.
+// -DECM_ORCA_IEEE restores the IEEE sequences: the host-side test builds of this code (tests/hostdev) use it to pin the
+// control flow and expression order bit for bit against the reference.
+#ifndef ECM_ORCA_IEEE
 __device__ __forceinline__ float odiv(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ float osqrt(float x) {
     float r;

@@ -174,37 +174,12 @@ __device__ __forceinline__ bool find_attraction_point(const EcmView& ecm, const 
     while (kSync ? __any_sync(0xffffffffu, active) : active) {
         if (active) {
             if (i < i0) {
-#ifdef ECM_ATTRACT_BBOX4
-                // The boxes of a path are contiguous and all their addresses are known once the header is: fetch the
-                // next four at once (independent loads in flight together) and test them in the same order, instead
-                // of one dependent load per box (k_attract waits on long-scoreboard stalls: header -> box -> box -> ...).
-                for (;;) {
-                    float4 c4[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) c4[u] = b - 1 - u >= 0 ? __ldg(&bbox[b - 1 - u]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    bool stop = false;
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        if (!stop) {
-                            if (--b < 0) {
-                                stop = true;
-                            } else {
-                                const float4 bb = c4[u];
-                                const float dx = fmaxf(fmaxf(bb.x - R.x, R.x - bb.z), 0.0f), dy = fmaxf(fmaxf(bb.y - R.y, R.y - bb.w), 0.0f);
-                                if (!(dx * dx + dy * dy > c2)) stop = true;
-                            }
-                        }
-                    }
-                    if (stop) break;
-                }
-#else
                 for (;;) {
                     if (--b < 0) break;
                     const float4 bb = __ldg(&bbox[b]);
                     const float dx = fmaxf(fmaxf(bb.x - R.x, R.x - bb.z), 0.0f), dy = fmaxf(fmaxf(bb.y - R.y, R.y - bb.w), 0.0f);
                     if (!(dx * dx + dy * dy > c2)) break;  // bbox is padded on the host: conservative
                 }
-#endif
                 if (b < 0) {
                     active = false;
                 } else {

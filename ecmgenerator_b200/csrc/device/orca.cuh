@@ -200,54 +200,82 @@ __device__ __forceinline__ Cons agent_constraint(v2 position, v2 velocity, float
     return cmake(vadd(velocity, vmul(U, 0.5f)), vright(rn));
 }
 
-// ORCA::RandomizedLP (ORCA.cpp:428-587).  Returns n on success, else the failing index.  The
-// arithmetic and its order are the reference's; only the control flow is flattened: a failure is
-// recorded in `result` instead of returning from inside the loops (outV stays untouched from then on).
+// ORCA::RandomizedLP (ORCA.cpp:428-587).  Returns n on success, else the failing index.  The arithmetic and its
+// order are the reference's: constraints are visited in index order, a satisfied one is skipped, a violated one
+// projects the optimum onto its line clipped by all earlier lines.
+//
+// Control flow (kSync: convergent call by the whole warp).  Stepping all lanes through i = 0 .. n-1 together made every
+// lane wait through the projection of any lane at every i: with 32 lanes almost every i has SOME lane violated, so the
+// warp paid n projections with a third of its lanes working (ncu: SIMT efficiency 0.35 in here).  Instead every lane
+// walks at its own pace: (A) skip forward to its next violated constraint - a cheap containment test per step - then
+// (B) all lanes that stopped project together, each on its own constraint i (the clip loop runs to the largest i).
+// A warp now pays max-over-lanes(violated constraints) projections instead of n.  Per lane the sequence of operations
+// is exactly the sequential one, hence bit-identical results.
 template <bool kSync>
 __device__ __forceinline__ int randomized_lp(const Cons* cs, int n, v2 opt, float maxSpeed, bool useDirOpt, v2& outV) {
     if (useDirOpt) outV = vmul(opt, maxSpeed);
     else if (ovlen(opt) > maxSpeed) outV = vmul(ovnormalized(opt), maxSpeed);
     else outV = opt;
     int result = n;
-    const int trips = warp_max_trip<kSync>(n);
-    for (int i = 0; i < trips; i++) {
-        warp_align<kSync>();
-        if (i >= n || result != n) continue;
-        const Cons h = cs[i];
-        if (ccontains(h, outV)) continue;
+    int i = 0;
+    bool live = n > 0;
+    while (kSync ? __any_sync(0xffffffffu, live) : live) {
+        // (A) advance to the next violated constraint (ORCA.cpp:477-481: `if (Contains) continue`)
+        bool hit = false;
+        Cons h = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        while (kSync ? __any_sync(0xffffffffu, live && !hit) : (live && !hit)) {
+            if (live && !hit) {
+                h = cs[i];
+                if (ccontains(h, outV)) { i++; live = i < n; }
+                else hit = true;
+            }
+        }
+        // (B) project onto constraint i, clipped by constraints 0 .. i-1
         const v2 dir = vright(cn(h));
         const float dpd = vdot(dir, cp(h));
         const float disc = dpd * dpd + maxSpeed * maxSpeed - vdot(cp(h), cp(h));
         bool bad = disc <= 0.0f;  // `return i` (ORCA.cpp:499-503)
         float left = 0.0f, right = 0.0f;
-        if (!bad) {
+        const bool clip = hit && !bad;
+        if (clip) {
             const float dsq = osqrt(disc);
             left = -dpd - dsq;
             right = -dpd + dsq;
-            for (int j = 0; j < i; j++) {  // same i for every lane in here: lock-step
+        }
+        const int trips = warp_max_trip<kSync>(clip ? i : 0);
+        for (int j = 0; j < trips; j++) {
+            warp_align<kSync>();
+            if (clip && j < i) {
                 const Cons hj = cs[j];
                 const float den = vdet(dir, vright(cn(hj)));
                 const float num = vdet(vright(cn(hj)), vsub(cp(h), cp(hj)));
                 if (fabsf(den) <= kEpsilon) {
                     if (num < 0.0f) bad = true;  // `return i` (ORCA.cpp:526-533)
-                    continue;
+                } else {
+                    const float t = odiv(num, den);
+                    if (den >= 0.0f) right = (t < right) ? t : right;  // std::min(right, t)
+                    else left = (left < t) ? t : left;                 // std::max(left, t)
+                    if (left > right) bad = true;                      // `return i` (ORCA.cpp:546-548); monotone, so order-free
                 }
-                const float t = odiv(num, den);
-                if (den >= 0.0f) right = (t < right) ? t : right;  // std::min(right, t)
-                else left = (left < t) ? t : left;                 // std::max(left, t)
-                if (left > right) bad = true;                      // `return i` (ORCA.cpp:546-548); monotone, so order-free
             }
         }
-        if (bad) {
-            result = i;
-        } else if (useDirOpt) {
-            if (vdot(opt, dir) > 0.0f) outV = vadd(cp(h), vmul(dir, right));
-            else outV = vadd(cp(h), vmul(dir, left));
-        } else {
-            const float t = vdot(dir, vsub(opt, cp(h)));
-            if (t < left) outV = vadd(cp(h), vmul(dir, left));
-            else if (t > right) outV = vadd(cp(h), vmul(dir, right));
-            else outV = vadd(cp(h), vmul(dir, t));
+        if (hit) {
+            if (bad) {
+                result = i;
+                live = false;
+            } else {
+                if (useDirOpt) {
+                    if (vdot(opt, dir) > 0.0f) outV = vadd(cp(h), vmul(dir, right));
+                    else outV = vadd(cp(h), vmul(dir, left));
+                } else {
+                    const float t = vdot(dir, vsub(opt, cp(h)));
+                    if (t < left) outV = vadd(cp(h), vmul(dir, left));
+                    else if (t > right) outV = vadd(cp(h), vmul(dir, right));
+                    else outV = vadd(cp(h), vmul(dir, t));
+                }
+                i++;
+                live = i < n;
+            }
         }
     }
     return result;

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) k_bin_count_walk(WalkView walk, const uns
 }
 
 __global__ void __launch_bounds__(256) k_scatter_walk(WalkView walk, const int* __restrict__ key, const int* __restrict__ rank,
-                                                      const int* __restrict__ cell_start, AgentArrays ag, TickScratch sc, int slots_only) {
+                                                      const int* __restrict__ cell_start, AgentArrays ag, TickScratch sc) {
     const int n = *walk.n;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
         const int i = walk.list[idx];
@@ -189,7 +189,6 @@ __global__ void __launch_bounds__(256) k_scatter_walk(WalkView walk, const int* 
         if (k < 0) continue;
         const int p = cell_start[k] + rank[i];
         sc.s_slot[p] = i;
-        if (slots_only) continue;
         sc.s_pos[p] = ag.pos[i];
         sc.s_vel[p] = ag.vel[i];
         sc.s_rad[p] = ag.radius[i];

@@ -34,6 +34,7 @@ enum Counter {
     C_TOTAL_HALO_MISS = 9,
     C_TOTAL_KD_TIES = 10,  // kdtree.cuh: tree segments (> 16 elements) whose median tied on the split axis
     C_TOTAL_KD_SMALL_TIES = 11,  // the same in segments of up to 16 elements (resolved like libstdc++)
+    C_TOTAL_EV_OVERFLOW = 12,    // events dropped because a queue was full (the host did not poll for max_agents events)
     C_COUNT = 16
 };
 
@@ -73,8 +74,8 @@ struct TickScratch {
     float2* s_pref; unsigned char* s_alive;
     unsigned char* s_ghost;  // 1: halo / self ghost (multi-GPU): a neighbour candidate only
     int* fb_list;
-    int* nbr_q;  // split tick only (k_knn_rows -> k_orca_rows): [6 * cap] neighbour rows j-major, then the count / flag word
     int* ev_replan; int* ev_destroyed;
+    int ev_cap;     // entries each event list holds; an event beyond it is dropped and counted (C_TOTAL_EV_OVERFLOW)
     unsigned long long* counters;
 };
 
@@ -168,19 +169,13 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_add(int4* __restrict__ data
 }
 
 // ------------------------------------------------------------------------------------------------
-// slots_only: write just the slot id; k_attract then GATHERS the agent's components by slot (random
-// reads that hit L2) and writes the snapshot rows coalesced, instead of six scattered writes here.
 __global__ void __launch_bounds__(256) k_scatter(int n_slots, const int* __restrict__ key, const int* __restrict__ rank,
-                                                 const int* __restrict__ cell_start, AgentArrays ag, TickScratch sc, int slots_only) {
+                                                 const int* __restrict__ cell_start, AgentArrays ag, TickScratch sc) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_slots) return;
     int k = key[i];
     if (k < 0) return;
     int p = cell_start[k] + rank[i];
-    if (slots_only) {
-        sc.s_slot[p] = i;
-        return;
-    }
     sc.s_pos[p] = ag.pos[i];
     sc.s_vel[p] = ag.vel[i];
     sc.s_rad[p] = ag.radius[i];
@@ -201,7 +196,6 @@ struct TickView {
     float step;
     int max_ring;
     int record_neighbors;
-    int gather;  // 1: k_scatter wrote only s_slot; k_attract fills the snapshot rows of owned agents
     // multi-GPU strips (strips.cuh): the grid holds every agent with x in [cover_lo, cover_hi)
     int strips;
     float cover_lo, cover_hi;
@@ -220,17 +214,8 @@ __device__ __forceinline__ void attract_agent(const TickView& t, const int p, co
     bool have = false, alive = true, need_irm = false;
     if (valid) {
         slot = t.sc.s_slot[p];
-        if (t.gather) {  // build this agent's snapshot row: gathers hit L2, the stores are coalesced
-            pos = t.ag.pos[slot];
-            t.sc.s_pos[p] = pos;
-            t.sc.s_vel[p] = t.ag.vel[slot];
-            t.sc.s_rad[p] = t.ag.radius[slot];
-            spd = t.ag.speed[slot];
-            t.sc.s_spd[p] = spd;
-        } else {
-            pos = t.sc.s_pos[p];
-            spd = t.sc.s_spd[p];
-        }
+        pos = t.sc.s_pos[p];
+        spd = t.sc.s_spd[p];
         const PathHdr hdr = t.ag.path_hdr[slot];
         path += hdr.off;
         bbox += hdr.off >> 3;
@@ -247,8 +232,9 @@ __device__ __forceinline__ void attract_agent(const TickView& t, const int p, co
                 alive = false;
                 st |= 8u;
                 t.ag.active[slot] = 0;
-                int e = (int)atomicAdd(&t.sc.counters[C_DESTROYED_N], 1ull);
-                t.sc.ev_destroyed[e] = slot;
+                const unsigned long long e = atomicAdd(&t.sc.counters[C_DESTROYED_N], 1ull);
+                if (e < (unsigned long long)t.sc.ev_cap) t.sc.ev_destroyed[e] = slot;
+                else atomicAdd(&t.sc.counters[C_TOTAL_EV_OVERFLOW], 1ull);
             }
         } else {
             need_irm = true;
@@ -267,8 +253,9 @@ __device__ __forceinline__ void attract_agent(const TickView& t, const int p, co
                 if (cell == -1) st |= 1u;
                 if (!t.ag.replan_pending[slot]) {  // one event per request; cleared by ecmgpu_set_path
                     t.ag.replan_pending[slot] = 1;
-                    int e = (int)atomicAdd(&t.sc.counters[C_REPLAN_N], 1ull);
-                    t.sc.ev_replan[e] = slot;
+                    const unsigned long long e = atomicAdd(&t.sc.counters[C_REPLAN_N], 1ull);
+                    if (e < (unsigned long long)t.sc.ev_cap) t.sc.ev_replan[e] = slot;
+                    else atomicAdd(&t.sc.counters[C_TOTAL_EV_OVERFLOW], 1ull);
                 }
             }
         } else {
@@ -374,7 +361,7 @@ __device__ __forceinline__ void orca_agent(const TickView& t, const int p, const
             t.sc.fb_list[e] = p;
         }
     }
-    __syncthreads();  // phase barrier: neighbour search | constraints + LP
+    phase_barrier<true>();  // neighbour search | constraints + LP
     st |= finish_agent<true, true>(t, p, k, mine && found);
     if (st) t.ag.status[t.sc.s_slot[p]] |= st;
     unsigned m_ovf = __ballot_sync(0xffffffffu, (st & 16u) != 0u);
@@ -393,72 +380,6 @@ __global__ void __launch_bounds__(256, ECM_ORCA_MINBLOCKS) k_orca(TickView t) {
     orca_agent(t, blockIdx.x * blockDim.x + threadIdx.x, *t.n_sorted_ptr);
 }
 
-// Split variant of k_orca (ECMGPU_SPLIT=1, off by default, same results): the neighbour search as a kernel of its own
-// at 8 CTAs per SM (32 registers, every warp slot filled: the search waits on L1 / L2 loads, long scoreboard was
-// k_orca's top stall at 62 % occupancy), its five snapshot rows handed over through `nbr_q` (24 B per agent each way);
-// the half-planes and the LP then run without the search's registers and code.
-#ifndef ECM_KNN_MINBLOCKS
-#define ECM_KNN_MINBLOCKS 8
-#endif
-constexpr int kSplitHaloMiss = 0x100;  // flag in the count word
-__global__ void __launch_bounds__(256, ECM_KNN_MINBLOCKS) k_knn_rows(TickView t, int cap) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = *t.n_sorted_ptr;
-    const bool mine = p < n && !t.sc.s_ghost[p] && t.sc.s_alive[p];
-    Knn k;
-    k.init();
-    int word = -1;  // no work for k_orca_rows
-    bool fb = false;
-    if (mine) {
-        const v2 pos = t.sc.s_pos[p];
-        if (knn_grid(k, pos, t.grid, t.max_ring)) {
-            word = k.count();
-            if (t.strips) {  // finish_agent's check, made where the 5th distance is at hand
-                const float r5 = word == kK ? sqrtf(k.d[kK - 1]) * 1.001f : CUDART_INF_F;
-                if (pos.x - r5 < t.cover_lo || pos.x + r5 >= t.cover_hi) word |= kSplitHaloMiss;
-            }
-        } else {
-            fb = true;
-            const int e = (int)atomicAdd(&t.sc.counters[C_FALLBACK_N], 1ull);
-            t.sc.fb_list[e] = p;
-            t.ag.status[t.sc.s_slot[p]] |= 32u;
-        }
-    }
-    if (p < cap) {
-#pragma unroll
-        for (int j = 0; j < kK; j++) t.sc.nbr_q[(size_t)j * cap + p] = k.q[j];
-        t.sc.nbr_q[(size_t)kK * cap + p] = word;
-    }
-    const unsigned m_fb = __ballot_sync(0xffffffffu, fb);
-    if ((threadIdx.x & 31) == 0 && m_fb) atomicAdd(&t.sc.counters[C_TOTAL_FALLBACK], (unsigned long long)__popc(m_fb));
-}
-
-// `t.strips` must be 0 here (the halo check travelled in the count word).
-__global__ void __launch_bounds__(256, ECM_ORCA_MINBLOCKS) k_orca_rows(TickView t, int cap) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = *t.n_sorted_ptr;
-    const int word = p < n && p < cap ? t.sc.nbr_q[(size_t)kK * cap + p] : -1;
-    const bool valid = word >= 0;
-    Knn k;
-    k.init();
-    if (valid) {
-#pragma unroll
-        for (int j = 0; j < kK; j++) k.q[j] = t.sc.nbr_q[(size_t)j * cap + p];
-    }
-    __syncthreads();
-    unsigned st = finish_agent<true, true>(t, p, k, valid);
-    if (valid && (word & kSplitHaloMiss)) st |= 128u;
-    if (st) t.ag.status[t.sc.s_slot[p]] |= st;
-    const unsigned m_ovf = __ballot_sync(0xffffffffu, (st & 16u) != 0u);
-    const unsigned m_lp3 = __ballot_sync(0xffffffffu, (st & 64u) != 0u);
-    const unsigned m_hm = __ballot_sync(0xffffffffu, (st & 128u) != 0u);
-    if ((threadIdx.x & 31) == 0) {
-        if (m_hm) atomicAdd(&t.sc.counters[C_TOTAL_HALO_MISS], (unsigned long long)__popc(m_hm));
-        if (m_ovf) atomicAdd(&t.sc.counters[C_TOTAL_OBST_OVF], (unsigned long long)__popc(m_ovf));
-        if (m_lp3) atomicAdd(&t.sc.counters[C_TOTAL_LP3D], (unsigned long long)__popc(m_lp3));
-    }
-}
-
 // Fixed-grid versions for strips with the compact walk (ECMGPU_COMPACT=1): a rank holds n_slots = the GLOBAL crowd but
 // its snapshot has only the rows of its share (+ ghosts); launching one CTA per possible row tile would start thousands
 // of CTAs that find nothing to do.  One resident wave of CTAs walks the row tiles that exist instead.
@@ -472,17 +393,6 @@ __global__ void __launch_bounds__(256, ECM_ORCA_MINBLOCKS) k_orca_tiles(TickView
         orca_agent(t, base + threadIdx.x, n);
         __syncthreads();
     }
-}
-
-// The whole per-agent tick in one kernel: the attraction phase is memory-latency bound (polyline
-// and header gathers), the ORCA phases are issue bound; with CTAs of one SM sitting in different
-// phases the two overlap instead of running back to back as k_attract + k_orca.
-__global__ void __launch_bounds__(256, ECM_ORCA_MINBLOCKS) k_tick(TickView t) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = *t.n_sorted_ptr;
-    attract_agent(t, p, n);  // writes s_pref[p] / s_alive[p], read back by the same thread below
-    __syncthreads();         // phase barrier
-    orca_agent(t, p, n);
 }
 
 // The stragglers of a tick, one kernel: (a) warp-per-agent exhaustive neighbour search + ORCA for agents

@@ -180,15 +180,11 @@ struct ecmgpu_sim {
     } io;
     bool ev_valid = false;
     int max_ring = 8;
-    int orca_block = 256;  // CTA size of k_orca (env ECMGPU_ORCA_BLOCK for experiments)
-    bool fused = false;    // k_tick (attraction + ORCA in one kernel); profiling mode times k_attract / k_orca separately; env ECMGPU_FUSED=0
-    // compact walk for strips (device/strips.cuh WalkView): pack / cell count / scatter walk the owned share; env ECMGPU_COMPACT=1
-    bool compact = false, walk_dirty = true;
+    // compact walk for strips (device/strips.cuh WalkView): pack / cell count / scatter walk the owned share instead of every
+    // slot (13 % off the per-rank tick at 8 x 125 k agents, profiles/r02a_strips8_compact*_launches.csv); env ECMGPU_COMPACT=0 disables
+    bool compact = true, walk_dirty = true;
     DevBuf<int> d_walk, d_walk_n;
     DevBuf<unsigned char> d_in_walk;
-    bool split = false;    // k_knn_rows + k_orca_rows instead of k_orca (same results; an A/B candidate, not measured yet); env ECMGPU_SPLIT=1
-    DevBuf<int> d_nbr_q;   // split tick: [6 * rows] neighbour rows + count word
-    bool gather = false;   // snapshot rows built by k_attract (gather) instead of k_scatter: measured neutral (profiles/r01_experiments.md); env ECMGPU_GATHER=1
     // ---- the tick as a CUDA graph (one launch instead of ~15 kernel / memset / NCCL submissions)
     bool use_graph = true;         // env ECMGPU_GRAPH=0 disables
     uint64_t config_epoch = 1;     // bumped whenever something the captured tick depends on changes
@@ -476,15 +472,14 @@ TickView make_view(ecmgpu_sim* s) {
     t.sc.s_alive = s->d_s_alive.p;
     t.sc.s_ghost = s->d_s_ghost.p;
     t.sc.fb_list = s->d_fb_list.p;
-    t.sc.nbr_q = s->d_nbr_q.p;
     t.sc.ev_replan = s->d_ev_replan.p;
     t.sc.ev_destroyed = s->d_ev_destroyed.p;
+    t.sc.ev_cap = (int)s->d_ev_destroyed.n;
     t.sc.counters = s->d_counters.p;
     t.n_sorted_ptr = s->d_cell_count.p + (size_t)s->gw * s->gh;
     t.step = s->prm.step;
     t.max_ring = s->max_ring;
     t.record_neighbors = s->prm.record_neighbors;
-    t.gather = s->gather ? 1 : 0;
     t.strips = s->strips_on ? 1 : 0;
     const float inf = std::numeric_limits<float>::infinity();
     t.cover_lo = s->strips_on && s->rank > 0 ? s->strip_lo - s->halo : -inf;
@@ -704,11 +699,8 @@ int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
     k_scan_tiles<<<tiles, kScanBlock, 0, s->stream>>>((int4*)s->d_cell_count.p, s->d_block_sums.p);
     k_scan_sums<<<1, kScanBlock, 0, s->stream>>>(s->d_block_sums.p, tiles);
     k_scan_add<<<tiles, kScanBlock, 0, s->stream>>>((int4*)s->d_cell_count.p, s->d_block_sums.p);
-    // gather mode: k_scatter writes only the slot list, so nobody clears the ghost flags of the owned rows (without strips
-    // nobody ever wrote them: a fresh allocation is not guaranteed to be zero)
-    if (t.gather) CUDA_TRY(s, cudaMemsetAsync(s->d_s_ghost.p, 0, s->d_s_ghost.n, s->stream));
-    if (sv.walk.list) k_scatter_walk<<<kSMs * 8, 256, 0, s->stream>>>(sv.walk, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc, t.gather);
-    else k_scatter<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc, t.gather);
+    if (sv.walk.list) k_scatter_walk<<<kSMs * 8, 256, 0, s->stream>>>(sv.walk, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc);
+    else k_scatter<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc);
     if (s->strips_on) {
         k_ghost_scatter<<<div_up(ng, 256), 256, 0, s->stream>>>(sv, s->d_cell_count.p, t.ag, t.sc, s->d_s_ghost.p);
         s->launches++;
@@ -763,14 +755,6 @@ int plan_alloc(ecmgpu_sim* s, int want) {
     k_plan_init<<<kSMs * 8, 256, 0, s->stream>>>(make_plan_scratch(s), (int)nV);
     s->launches++;
     CUDA_TRY(s, cudaGetLastError());
-    return ECMGPU_OK;
-}
-
-// Split tick: room for 6 ints per snapshot row the kernels cover (same row count as ecmgpu_update_phase computes).
-int ensure_split_buffer(ecmgpu_sim* s) {
-    if (!s->split) return ECMGPU_OK;
-    const size_t cap = (size_t)div_up(s->n_slots + (s->strips_on ? 2 * s->cap_halo + s->cap_self : 0), 128) * 128;
-    if (s->d_nbr_q.n < 6 * cap) CUDA_TRY(s, s->d_nbr_q.alloc(6 * cap));
     return ECMGPU_OK;
 }
 
@@ -1048,11 +1032,7 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
 #undef TRY_ALLOC
     s->h_path_hdr.assign(n, PathHdr{0, 0, 0.0f, 0.0f});
     if (const char* e = getenv("ECMGPU_GRAPH")) s->use_graph = atoi(e) != 0;
-    if (const char* e = getenv("ECMGPU_GATHER")) s->gather = atoi(e) != 0;
-    if (const char* e = getenv("ECMGPU_FUSED")) s->fused = atoi(e) != 0;
-    if (const char* e = getenv("ECMGPU_SPLIT")) s->split = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_COMPACT")) s->compact = atoi(e) != 0;
-    if (const char* e = getenv("ECMGPU_ORCA_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) s->orca_block = v; }
     s->h_path_pool.reserve(std::min<size_t>(pool, 1 << 20));
     *out = s;
     return ECMGPU_OK;
@@ -1072,7 +1052,7 @@ void ecmgpu_destroy(ecmgpu_sim* s) {
     s->d_key.free(); s->d_rank.free(); s->d_cell_count.free(); s->d_block_sums.free(); s->d_s_slot.free();
     s->d_lp3d_hdr.free(); s->d_lp3d_out.free(); s->d_lp3d_cs.free();
     s->d_fb_list.free(); s->d_ev_replan.free(); s->d_ev_destroyed.free(); s->d_s_pos.free(); s->d_s_vel.free();
-    s->d_s_pref.free(); s->d_s_rad.free(); s->d_s_spd.free(); s->d_s_alive.free(); s->d_counters.free(); s->d_nbr_q.free();
+    s->d_s_pref.free(); s->d_s_rad.free(); s->d_s_spd.free(); s->d_s_alive.free(); s->d_counters.free();
     s->d_walk.free(); s->d_walk_n.free(); s->d_in_walk.free();
     kd_free(s);
     plan_free(s);
@@ -1277,7 +1257,6 @@ int ecmgpu_update_phase(ecmgpu_sim* s, int phase) {
     if (rc) return rc;
     if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[1], s->stream));
     const int nb = div_up(s->n_slots + (s->strips_on ? 2 * s->cap_halo + s->cap_self : 0), 128);
-    const int ob = s->orca_block;
     if (s->neighbor_mode == ECMGPU_NEIGHBORS_KDTREE) {
         if (s->strips_on) return fail(s, ECMGPU_ERR_INVALID, "the KD-tree neighbour mode runs on a single handle (no strips)");
         k_attract<<<nb, 128, 0, s->stream>>>(t);
@@ -1286,30 +1265,14 @@ int ecmgpu_update_phase(ecmgpu_sim* s, int phase) {
         rc = enqueue_kd_orca(s, t, nb * 128);
         if (rc) return rc;
         s->launches -= 2;  // k_attract and k_orca_kd are counted above (3 are added below)
-    } else if (s->split) {
-        const int cap = nb * 128;  // rows the kernels cover
-        rc = ensure_split_buffer(s);  // normally done by ecmgpu_update before a capture starts
-        if (rc) return rc;
-        t.sc.nbr_q = s->d_nbr_q.p;
-        k_attract<<<nb, 128, 0, s->stream>>>(t);
-        if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
-        k_knn_rows<<<div_up(cap, 256), 256, 0, s->stream>>>(t, cap);
-        TickView t2 = t;
-        t2.strips = 0;  // the halo check travels in the count word
-        k_orca_rows<<<div_up(cap, 256), 256, 0, s->stream>>>(t2, cap);
-        s->launches += 1;  // three kernels instead of two (3 are added below)
-    } else if (s->fused) {
-        if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));  // "attract" phase is empty: all of it is k_tick
-        k_tick<<<div_up(nb * 128, ob), ob, 0, s->stream>>>(t);
-        s->launches -= 1;  // one kernel instead of two (3 are added below)
-    } else if (s->compact && s->strips_on && ob == 256) {  // one resident wave over the row tiles that exist (tick.cuh)
+    } else if (s->compact && s->strips_on) {  // one resident wave over the row tiles that exist (tick.cuh)
         k_attract_tiles<<<kSMs * ECM_ATTRACT_MINBLOCKS, 128, 0, s->stream>>>(t);
         if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
         k_orca_tiles<<<kSMs * ECM_ORCA_MINBLOCKS, 256, 0, s->stream>>>(t);
     } else {
         k_attract<<<nb, 128, 0, s->stream>>>(t);
         if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
-        k_orca<<<div_up(nb * 128, ob), ob, 0, s->stream>>>(t);
+        k_orca<<<div_up(nb * 128, 256), 256, 0, s->stream>>>(t);
     }
     k_fallback<<<kSMs * 4, 128, 0, s->stream>>>(t, 0);
     if (s->profiling) { CUDA_TRY(s, cudaEventRecord(s->ev[3], s->stream)); s->ev_valid = true; }
@@ -1330,8 +1293,6 @@ int ecmgpu_update(ecmgpu_sim* s) {
     if (s->use_graph && !nccl_tick && !s->profiling && s->n_slots > 0 && s->neighbor_mode == ECMGPU_NEIGHBORS_EXACT) {
         CUDA_TRY(s, cudaSetDevice(s->prm.device));
         int rc = ensure_ready(s);  // host-side (re)builds happen outside the capture
-        if (rc) return rc;
-        rc = ensure_split_buffer(s);
         if (rc) return rc;
         rc = ensure_walk(s);
         if (rc) return rc;
@@ -1384,7 +1345,10 @@ int ecmgpu_poll_events(ecmgpu_sim* s, int* replan_slots, int replan_cap, int* n_
     unsigned long long c[2] = {0, 0};
     CUDA_TRY(s, cudaMemcpyAsync(c, s->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(s, cudaStreamSynchronize(s->stream));
-    const int nr = (int)c[C_REPLAN_N], nd = (int)c[C_DESTROYED_N];
+    // the lists hold max_agents entries each; what a kernel could not store it dropped and counted
+    const unsigned long long cap = (unsigned long long)s->d_ev_destroyed.n;
+    const bool overflow = c[C_REPLAN_N] > cap || c[C_DESTROYED_N] > cap;
+    const int nr = (int)std::min(c[C_REPLAN_N], cap), nd = (int)std::min(c[C_DESTROYED_N], cap);
     if (n_replans) *n_replans = nr;
     if (n_destroyed) *n_destroyed = nd;
     if (replan_slots && nr > 0) {
@@ -1404,6 +1368,9 @@ int ecmgpu_poll_events(ecmgpu_sim* s, int* replan_slots, int replan_cap, int* n_
     // event order is arrival order of the atomics; report ascending slots like the reference's loops
     if (replan_slots && nr > 1) std::sort(replan_slots, replan_slots + nr);
     if (destroyed_slots && nd > 1) std::sort(destroyed_slots, destroyed_slots + nd);
+    if (overflow)
+        return fail(s, ECMGPU_ERR_CAPACITY, "ecmgpu_poll_events: an event list overflowed (more than max_agents events between two polls); "
+                    "the excess was dropped - read ECMGPU_ACTIVE / ECMGPU_REPLAN_PENDING to resynchronise");
     return ECMGPU_OK;
 }
 
@@ -1417,7 +1384,18 @@ static int xfer(ecmgpu_sim* s, int which, void* host, int first, int count, bool
     if (to_host) CUDA_TRY(s, cudaMemcpyAsync(host, dev, es * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
     else CUDA_TRY(s, cudaMemcpyAsync(dev, host, es * (size_t)count, cudaMemcpyHostToDevice, s->stream));
     if (wait) CUDA_TRY(s, cudaStreamSynchronize(s->stream));
-    if (!to_host && (which == ECMGPU_RADIUS || which == ECMGPU_SPEED)) s->bins_dirty = true;  // ranges may have grown
+    if (!to_host && (which == ECMGPU_RADIUS || which == ECMGPU_SPEED) && count > 0) {
+        // The obstacle lists of the static bins reach max(10 * speed + radius) (ORCA.cpp:27): a larger speed or radius
+        // must widen them, or find_obstacles would silently miss segments.  Rare call: read the range back and re-track.
+        std::vector<float> spd(count), rad(count);
+        CUDA_TRY(s, cudaMemcpyAsync(spd.data(), s->d_speed.p + first, sizeof(float) * count, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(rad.data(), s->d_radius.p + first, sizeof(float) * count, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        for (int i = 0; i < count; i++) {
+            const float r = kLookAhead * spd[i] + rad[i];
+            if (r == r && r < std::numeric_limits<float>::infinity()) s->tracked_range = std::max(s->tracked_range, r);
+        }
+    }
     if (!to_host) s->n_slots = std::max(s->n_slots, which == ECMGPU_ACTIVE ? first + count : s->n_slots);
     if (!to_host && which == ECMGPU_ACTIVE) { s->io.owned_confirmed = -1; s->walk_dirty = true; }
     return ECMGPU_OK;
@@ -1627,7 +1605,6 @@ int ecmgpu_find_neighbors(ecmgpu_sim* s, int count, int* out_ids5, int* out_coun
         int rc = ensure_ready(s);
         if (rc) return rc;
         TickView t = make_view(s);
-        t.gather = 0;  // no k_attract in this path: k_scatter writes the full snapshot rows
         if (s->strips_on) {
             if (s->local_transport && s->n_ranks > 1)
                 return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_find_neighbors is not available with in-process strips");
@@ -1779,7 +1756,6 @@ int ecmgpu_valid_spawn_locations(ecmgpu_sim* s, int n, const float* xy, const fl
     int rc = ensure_ready(s);
     if (rc) return rc;
     TickView t = make_view(s);
-    t.gather = 0;  // k_scatter writes the full snapshot rows
     if (s->strips_on) {
         rc = enqueue_pack(s, t);
         if (rc) return rc;
@@ -1838,6 +1814,7 @@ int ecmgpu_get_stats(ecmgpu_sim* s, ecmgpu_stats* o) {
     o->location_failures = c[C_TOTAL_LOCFAIL]; o->replans = c[C_TOTAL_REPLAN]; o->halo_misses = c[C_TOTAL_HALO_MISS];
     o->kd_median_ties = c[C_TOTAL_KD_TIES];
     o->kd_small_ties = c[C_TOTAL_KD_SMALL_TIES];
+    o->event_overflows = c[C_TOTAL_EV_OVERFLOW];
     return ECMGPU_OK;
 }
 
@@ -1845,8 +1822,8 @@ void ecmgpu_abi_sizes(int32_t out[4]) {
     out[0] = (int32_t)sizeof(ecmgpu_params);
     out[1] = (int32_t)sizeof(ecmgpu_stats);
     out[2] = (int32_t)sizeof(ecmgpu_agent_rec);
-    out[3] = 20;  // members of ecmgpu_stats
-    static_assert(sizeof(ecmgpu_stats) == 10 * 4 + 10 * 8, "ecmgpu_stats changed: update out[3] and the bindings");
+    out[3] = 21;  // members of ecmgpu_stats
+    static_assert(sizeof(ecmgpu_stats) == 10 * 4 + 11 * 8, "ecmgpu_stats changed: update out[3] and the bindings");
 }
 
 int ecmgpu_set_profiling(ecmgpu_sim* s, int on) {

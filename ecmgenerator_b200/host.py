@@ -127,6 +127,88 @@ class World:
             obst_prev=np.concatenate([self.obst_prev, prv]), obst_convex=np.concatenate([self.obst_convex, conv]),
             obst_first=np.concatenate([self.obst_first, [base + 4]]).astype(np.int32))
 
+    def with_obstacle_polygons(self, polys) -> "World":
+        """Copy of the world whose ORCA obstacles are the given polygons (lists of counter-clockwise points), in that
+        order, with the links and convexity flags of Obstacle::Initialize (ECMDataTypes.cpp:23-61: isConvex =
+        det(prev - next, p - prev) >= 0 in float arithmetic).  The ECM is unchanged, as after the reference's
+        Environment::AddObstacle without a new ComputeECM (Simulator::AddObstacleArea with updateECM = false,
+        Simulator.cpp:395-420): obstacles only feed FindNearestObstacles / ORCA."""
+        import dataclasses
+
+        xy, nxt, prv, conv, first = [], [], [], [], [0]
+        for poly in polys:
+            P = np.asarray(poly, np.float32).reshape(-1, 2)
+            m, base = len(P), first[-1]
+            for i in range(m):
+                ip, inx = (i - 1) % m, (i + 1) % m
+                a, b = P[ip] - P[inx], P[i] - P[ip]
+                conv.append(1 if m == 2 or np.float32(a[0] * b[1]) - np.float32(a[1] * b[0]) >= 0 else 0)
+                nxt.append(base + inx)
+                prv.append(base + ip)
+            xy.append(P)
+            first.append(base + m)
+        return dataclasses.replace(
+            self, obst_xy=np.concatenate(xy).astype(np.float32), obst_next=np.array(nxt, np.int32), obst_prev=np.array(prv, np.int32),
+            obst_convex=np.array(conv, np.uint8), obst_first=np.array(first, np.int32))
+
+    def obstacle_polygons(self):
+        return [self.obst_xy[self.obst_first[k]:self.obst_first[k + 1]].copy() for k in range(self.n_obstacles)]
+
+    def with_recessed_obstacles(self, seed: int, depth=(1.0, 3.0), every: int = 1) -> "World":
+        """Every `every`-th obstacle gets recesses cut into its footprint: a notch in the middle of one side (a U shape,
+        two concave vertices) and one corner cut away (an L shape, one concave vertex), so that the !isConvex legs of
+        ORCA::GenerateConstraints (ORCA.cpp:146-212) and the convexity rule (ECMDataTypes.cpp:52-59) see real input.
+        Only the obstacle polygons change (see with_obstacle_polygons); the streets and their ECM stay as they are."""
+        rng = np.random.default_rng(seed)
+        out = []
+        for k, P in enumerate(self.obstacle_polygons()):
+            P = P.astype(np.float64)
+            m = len(P)
+            if k % every or m != 4:
+                out.append(P)
+                continue
+            side, corner = int(rng.integers(0, 4)), int(rng.integers(0, 4))
+            d_side, d_corner = rng.uniform(depth[0], depth[1], size=2)
+            Q = []
+            for i in range(4):
+                a, b = P[i], P[(i + 1) % 4]
+                e = b - a
+                L = float(np.hypot(*e))
+                u = e / L
+                n_in = np.array([-u[1], u[0]])  # counter-clockwise polygon: the interior lies to the left of every edge
+                pprev = P[(i - 1) % 4]
+                uprev = (a - pprev) / float(np.hypot(*(a - pprev)))
+                if i == corner and min(L, float(np.hypot(*(a - pprev)))) > 4 * d_corner:
+                    # L shape: vertex a is replaced by three points (the middle one is concave)
+                    Q += [a - uprev * d_corner, a - uprev * d_corner + u * d_corner, a + u * d_corner]
+                else:
+                    Q.append(a)
+                if i == side and L > 6 * d_side:
+                    t0, t1 = 0.3 * L, 0.7 * L
+                    Q += [a + u * t0, a + u * t0 + n_in * d_side, a + u * t1 + n_in * d_side, a + u * t1]
+            out.append(np.array(Q))
+        return self.with_obstacle_polygons(out)
+
+    def rotated(self, angle: float) -> "World":
+        """Copy of the world turned by `angle` (radians, counter-clockwise about the origin): every vertex, closest
+        point and obstacle vertex is rotated in double precision and rounded to float once, so all cell edges and
+        obstacle segments become oblique.  bbox becomes the bounding box of the turned walkable area."""
+        import dataclasses
+
+        c, s_ = np.cos(angle), np.sin(angle)
+        R = np.array([[c, -s_], [s_, c]])
+
+        def rot(a):
+            return (a.astype(np.float64).reshape(-1, 2) @ R.T).astype(np.float32).reshape(a.shape)
+
+        bb = self.bbox.astype(np.float64)
+        corners = np.array([[bb[0], bb[1]], [bb[2], bb[1]], [bb[2], bb[3]], [bb[0], bb[3]]]) @ R.T
+        nb = np.array([corners[:, 0].min(), corners[:, 1].min(), corners[:, 0].max(), corners[:, 1].max()], np.float32)
+        w = dataclasses.replace(self, bbox=nb, vert_xy=rot(self.vert_xy), edge_cl=rot(self.edge_cl), obst_xy=rot(self.obst_xy),
+                                street_width=None, blocks_x=None, blocks_y=None)
+        # convexity is a float predicate of the turned coordinates (ECMDataTypes.cpp:52-59): recompute it
+        return w.with_obstacle_polygons(w.obstacle_polygons())
+
     @property
     def n_vertices(self) -> int:
         return int(self.vert_clear.shape[0])

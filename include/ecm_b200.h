@@ -110,7 +110,9 @@ int ecmgpu_update(ecmgpu_sim* sim);
 int ecmgpu_sync(ecmgpu_sim* sim);
 /* Drains the device event queues (waits for enqueued ticks): agents that asked for a replan
  * (Simulator.cpp:581-587; they stay flagged until ecmgpu_set_path) and agents destroyed on arrival
- * (Simulator.cpp:564-566) since the last poll.  Either array may be NULL with cap 0 to only count. */
+ * (Simulator.cpp:564-566) since the last poll.  Either array may be NULL with cap 0 to only count.
+ * Each list holds max_agents entries: a host that reuses slots (respawn) without polling for more than max_agents
+ * events loses the excess (counted in ecmgpu_stats.event_overflows) and the next poll fails with ECMGPU_ERR_CAPACITY. */
 int ecmgpu_poll_events(ecmgpu_sim* sim, int* replan_slots, int replan_cap, int* n_replans, int* destroyed_slots,
                        int destroyed_cap, int* n_destroyed);
 
@@ -218,6 +220,9 @@ typedef struct ecmgpu_stats {
      * up to 16 agents (kd_small_ties) the tie resolves like libstdc++'s std::sort does (insertion sort, stable);
      * in larger ones (kd_median_ties) the reference's tree is std::sort-defined: 0 = the tree equals the reference's */
     uint64_t kd_median_ties, kd_small_ties;
+    /* arrival / replan events dropped because a list was full: each list holds max_agents entries and is emptied by
+     * ecmgpu_poll_events, which then fails with ECMGPU_ERR_CAPACITY (poll at least once per max_agents events) */
+    uint64_t event_overflows;
 } ecmgpu_stats;
 int ecmgpu_get_stats(ecmgpu_sim* sim, ecmgpu_stats* out);
 /* sizeof(ecmgpu_params), sizeof(ecmgpu_stats), sizeof(ecmgpu_agent_rec), number of ecmgpu_stats members: lets a binding in

@@ -791,6 +791,12 @@ static v2 orca_velocity(eo_sim* s, int entity, int n_nb, const int* nb) {
         n_on = find_obstacles(s, entity, range * range, s->obst_list, s->obst_cap);
     }
     if (n_on > s->counters[2]) s->counters[2] = n_on;
+    for (int i = 0; i < n_on; i++) { /* test coverage statistics only: what kind of geometry reached GenerateConstraints */
+        const int oL = s->obst_list[i], oR = s->obst_next[oL];
+        if (!s->obst_convex[oL] || !s->obst_convex[oR]) s->counters[6]++;
+        const v2 a = obst(s, oL), b = obst(s, oR);
+        if (a.x != b.x && a.y != b.y) s->counters[7]++;
+    }
     if (n_on + EO_K > s->cons_cap) {
         s->cons_cap = (n_on + EO_K) * 2;
         s->cons = (eo_constraint*)realloc(s->cons, sizeof(eo_constraint) * (size_t)s->cons_cap);

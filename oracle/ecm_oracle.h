@@ -64,7 +64,8 @@ int eo_query_obstacles(const eo_sim* s, int slot, int* out_ids, int cap);
 /* ORCA::GetVelocity for one slot given its neighbour list. */
 void eo_orca_velocity(const eo_sim* s, int slot, int n_neighbors, const int* neighbors, float* out_v);
 /* counters accumulated over eo_step calls: [0] LP3D invocations, [1] LP calls, [2] max obstacle
- * neighbours seen, [3] IRM failures (replans), [4] point-location failures, [5] agent-updates */
+ * neighbours seen, [3] IRM failures (replans), [4] point-location failures, [5] agent-updates,
+ * [6] obstacle segments with a concave end vertex handed to GenerateConstraints, [7] oblique ones */
 const long long* eo_counters(const eo_sim* s);
 
 /* test hook: the libstdc++ std::sort restatement used by the KD-tree build, on its own */

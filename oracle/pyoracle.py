@@ -136,7 +136,7 @@ class OracleSim:
     def counters(self):
         c = self.L.eo_counters(self.h)
         return {"lp3d": c[0], "lp_calls": c[1], "max_obstacle_neighbours": c[2], "irm_failures": c[3],
-                "agent_updates": c[5]}
+                "agent_updates": c[5], "concave_segments": c[6], "oblique_segments": c[7]}
 
     def state(self, count=None):
         n = self.max_agents if count is None else int(count)

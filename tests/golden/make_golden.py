@@ -107,8 +107,10 @@ def run_mode(w, crowd, mode, ticks, paths=None):
 def make(name, w, crowd, ticks, seed):
     rng = np.random.default_rng(seed)
     data = {f"world/{k}": getattr(w, k) for k in WORLD_KEYS}
-    data["world/street_width"] = np.float32(w.street_width)
-    data["world/blocks_x"], data["world/blocks_y"] = w.blocks_x, w.blocks_y
+    # lattice metadata; NaN / empty for worlds that were turned or otherwise edited (no closed-form street mask)
+    data["world/street_width"] = np.float32(w.street_width if w.street_width is not None else np.nan)
+    data["world/blocks_x"] = w.blocks_x if w.blocks_x is not None else np.zeros(0, np.float32)
+    data["world/blocks_y"] = w.blocks_y if w.blocks_y is not None else np.zeros(0, np.float32)
     data["step"] = STEP
     data["crowd/pos"], data["crowd/goal"] = crowd.pos, crowd.goal
     data["crowd/radius"], data["crowd/speed"] = crowd.radius, crowd.speed
@@ -142,7 +144,17 @@ def make(name, w, crowd, ticks, seed):
     print(f"{name}: {crowd.n} agents, {ticks} ticks, events kd={len(ek)} exact={len(ee)}, {os.path.getsize(path) / 1e6:.2f} MB")
 
 
-def main():
+def turned(crowd, angle):
+    """The crowd of a world that is then turned by `angle` (host.World.rotated): same rotation, rounded to float once."""
+    c, s_ = np.cos(angle), np.sin(angle)
+    R = np.array([[c, -s_], [s_, c]])
+    rot = lambda a: (a.astype(np.float64) @ R.T).astype(np.float32)
+    return S.Crowd(rot(crowd.pos), rot(crowd.goal), crowd.radius.copy(), crowd.speed.copy())
+
+
+def main(only=None):
+    if only:
+        return main_new(only)
     # (1) the 5k-config world, thinned: open streets, few obstacle interactions
     w1 = S.world_c1()
     make("c1_small", w1, S.crowd_c1(w1, n=320, seed=11), 96, 101)
@@ -153,7 +165,29 @@ def main():
     w3 = lattice_world([30, 30], [12, 12, 12], 6.0, 0.0, 0.0)
     c3 = S.sample_crowd(w3, 360, 13, radius=(0.3, 0.3), speed=(1.4, 1.4), min_goal_dist=25.0, wall_margin=0.05)
     make("jam_small", w3, c3, 160, 103)
+    main_new(None)
+
+
+def main_new(only):
+    """Round 2: obstacle geometry the lattice scenes never had - oblique segments and concave vertices
+    (ORCA.cpp:146-239, ECMDataTypes.cpp:52-59, UtilityFunctions.cpp:54-86 on non-axis-aligned cell edges)."""
+    # (4) the narrow-street world turned by an angle with no special relation to the axes: every ECM cell edge and
+    #     every obstacle segment is oblique, coordinates carry rounding of the rotation
+    if only in (None, "oblique_small"):
+        w4 = lattice_world([16, 14, 18, 15, 17], [40, 36, 44], 8.0, -40.0, -60.0)
+        c4 = S.sample_crowd(w4, 280, 14, radius=(0.2, 0.4), speed=(1.0, 1.6), min_goal_dist=40.0)
+        a4 = 0.6154797
+        make("oblique_small", w4.rotated(a4), turned(c4, a4), 72, 104)
+    # (5) recessed blocks (U and L shaped obstacle polygons => concave vertices) in the jam world, turned as well: crowd
+    #     pressure pushes agents along and into the recesses, so the !isConvex legs, the foreign-leg tests against
+    #     non-rectangular neighbours and LP3D all run on oblique, concave input
+    if only in (None, "concave_small"):
+        w5 = lattice_world([30, 30], [12, 12, 12], 6.0, -33.0, -24.0).with_recessed_obstacles(7, depth=(0.8, 2.0))
+        c5 = S.sample_crowd(lattice_world([30, 30], [12, 12, 12], 6.0, -33.0, -24.0), 300, 15, radius=(0.3, 0.3), speed=(1.4, 1.4),
+                            min_goal_dist=25.0, wall_margin=0.05)
+        a5 = -0.2449787
+        make("concave_small", w5.rotated(a5), turned(c5, a5), 120, 105)
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

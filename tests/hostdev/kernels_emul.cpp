@@ -60,8 +60,7 @@ struct Emu {
     // grid + snapshot + scratch
     float gx0 = 0, gy0 = 0, gcell = 1;
     int gw = 1, gh = 1;
-    std::vector<int> key, rank, cell_count, block_sums, s_slot, fb_list, ev_replan, ev_destroyed, nbr_q;
-    bool split = false;  // ECMGPU_SPLIT: k_knn_rows + k_orca_rows instead of k_orca
+    std::vector<int> key, rank, cell_count, block_sums, s_slot, fb_list, ev_replan, ev_destroyed;
     std::vector<float2> s_pos, s_vel, s_pref;
     std::vector<float> s_rad, s_spd;
     std::vector<unsigned char> s_alive, s_ghost;
@@ -108,10 +107,10 @@ struct Emu {
         t.sc.key = key.data(); t.sc.rank = rank.data(); t.sc.cell_count = cell_count.data(); t.sc.block_sums = nullptr;
         t.sc.s_pos = s_pos.data(); t.sc.s_vel = s_vel.data(); t.sc.s_rad = s_rad.data(); t.sc.s_spd = s_spd.data();
         t.sc.s_slot = s_slot.data(); t.sc.s_pref = s_pref.data(); t.sc.s_alive = s_alive.data(); t.sc.s_ghost = s_ghost.data();
-        t.sc.fb_list = fb_list.data(); t.sc.nbr_q = nbr_q.data(); t.sc.ev_replan = ev_replan.data(); t.sc.ev_destroyed = ev_destroyed.data();
+        t.sc.fb_list = fb_list.data(); t.sc.ev_replan = ev_replan.data(); t.sc.ev_destroyed = ev_destroyed.data(); t.sc.ev_cap = (int)ev_destroyed.size();
         t.sc.counters = counters.data();
         t.n_sorted_ptr = cell_count.data() + (size_t)gw * gh;
-        t.step = step; t.max_ring = 8; t.record_neighbors = 1; t.gather = 0;
+        t.step = step; t.max_ring = 8; t.record_neighbors = 1;
         t.strips = strips ? 1 : 0;
         const float inf = CUDART_INF_F;
         t.cover_lo = strips && rank_id > 0 ? lo - halo : -inf;
@@ -211,7 +210,6 @@ void* emu_create(int nV, const float* vert_xy, int nE, const int* edge_v, const 
     return e;
 }
 void emu_destroy(void* h) { delete (Emu*)h; }
-void emu_set_split(void* h, int on) { ((Emu*)h)->split = on != 0; }
 void emu_set_compact(void* h, int on) { Emu* e = (Emu*)h; e->compact = on != 0; e->walk_dirty = true; }
 int emu_walk_len(void* h) { Emu* e = (Emu*)h; return e->walk_n.empty() ? -1 : e->walk_n[0]; }
 // ecmgpu.cu ensure_walk
@@ -309,25 +307,16 @@ int emu_tick(void* h) {
     const int ng = 2 * e->cap_halo + e->cap_self;
     if (e->strips) launch(ng, [&] { k_ghost_count(sv, gp, e->cell_count.data()); }, 256);
     emu_scan_cells(e);
-    if (sv.walk.list) launch(53, [&] { k_scatter_walk(sv.walk, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc, 0); }, 256);
-    else launch(e->n_slots, [&] { k_scatter(e->n_slots, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc, 0); }, 256);
+    if (sv.walk.list) launch(53, [&] { k_scatter_walk(sv.walk, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc); }, 256);
+    else launch(e->n_slots, [&] { k_scatter(e->n_slots, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc); }, 256);
     if (e->strips) launch(ng, [&] { k_ghost_scatter(sv, e->cell_count.data(), t.ag, t.sc, e->s_ghost.data()); }, 256);
     const int rows = e->n_slots + (e->strips ? ng : 0);
-    if (sv.walk.list && !e->split) {  // ecmgpu_update_phase: compact strips run the fixed-grid versions
+    if (sv.walk.list) {  // ecmgpu_update_phase: compact strips run the fixed-grid versions
         launch(41, [&] { k_attract_tiles(t); }, 128);
         launch(29, [&] { k_orca_tiles(t); }, 256);
     } else {
         launch(rows, [&] { k_attract(t); }, 128);
-        if (e->split) {
-            e->nbr_q.assign(6 * (size_t)rows, -7);
-            t.sc.nbr_q = e->nbr_q.data();
-            launch(rows, [&] { k_knn_rows(t, rows); }, 256);
-            TickView t2 = t;
-            t2.strips = 0;
-            launch(rows, [&] { k_orca_rows(t2, rows); }, 256);
-        } else {
-            launch(rows, [&] { k_orca(t); }, 256);
-        }
+        launch(rows, [&] { k_orca(t); }, 256);
     }
     const int fb = (int)e->counters[C_FALLBACK_N];
 #ifdef HD_SIMT
@@ -398,7 +387,7 @@ static void emu_grid_build(Emu* e, const TickView& t) {
     e->counters[C_FALLBACK_N] = 0; e->counters[C_LP3D_N] = 0;
     launch(e->n_slots, [&] { k_bin_count(e->n_slots, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data()); }, 256);
     emu_scan_cells(e);
-    launch(e->n_slots, [&] { k_scatter(e->n_slots, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc, 0); }, 256);
+    launch(e->n_slots, [&] { k_scatter(e->n_slots, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc); }, 256);
 }
 
 void emu_tick_kd(void* h) {

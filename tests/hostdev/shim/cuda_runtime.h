@@ -18,6 +18,9 @@
 #include <string>
 #include <vector>
 
+// the host builds pin expression order and control flow bit for bit against the reference: IEEE division / square root
+// in the ORCA arithmetic too (the GPU build uses the SFU approximations there, device/geom.cuh)
+#define ECM_ORCA_IEEE 1
 #define __device__
 #define __host__
 #define __global__

@@ -90,7 +90,9 @@ def test_lockstep_velocities_within_tolerance(name):
         total_rows += int(alive.sum())
         apply_events(ora, g.events_at("exact-knn", t))
     print(f"{name}: worst |dv| {worst:.3e}; {exact_rows}/{total_rows} velocity rows bit-identical")
-    assert exact_rows / total_rows > 0.9
+    # SFU division / square root / sine in the ORCA half-planes and LP (device/geom.cuh): 84-87 % of the rows stay
+    # bit-identical (it was > 99 % with the IEEE sequences); the contract is the 1e-4 m/s tolerance asserted above
+    assert exact_rows / total_rows > 0.75
 
 
 @pytest.mark.parametrize("name", GOLDEN)

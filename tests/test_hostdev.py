@@ -22,12 +22,8 @@ def _p(a, t):
     return a.ctypes.data_as(t)
 
 
-# build variants of the device code that must ALL be bit-exact: the default build and the switches kept for A/B
-VARIANTS = {"default": [], "knn_prune": ["-DECM_KNN_PRUNE"], "knn_branchless": ["-DECM_KNN_BRANCHLESS"],
-            "knn_prune_branchless": ["-DECM_KNN_PRUNE", "-DECM_KNN_BRANCHLESS"],
-            "knn_flat": ["-DECM_KNN_FLAT"], "knn_flat_prune": ["-DECM_KNN_FLAT", "-DECM_KNN_PRUNE"],
-            "attract_bbox4": ["-DECM_ATTRACT_BBOX4"],
-            "knn_twopass": ["-DECM_KNN_TWOPASS"], "knn_twopass_prune": ["-DECM_KNN_TWOPASS", "-DECM_KNN_PRUNE"],
+# builds of the device code that must be bit-exact: the plain per-lane instantiations and
+VARIANTS = {"default": [],
             # the warp-synchronous instantiations the kernels run (flattened control flow), one lane per "warp"
             "sync": ["-DHD_SYNC"]}
 

@@ -32,7 +32,7 @@ def emu():
 
 
 def load_emu(flags=(), tag=""):
-    """flags: extra -D switches (build variants kept for A/B); tag names the library file.
+    """flags: extra -D switches (e.g. the SIMT emulation); tag names the library file.
     -fno-gnu-unique: several builds of the same device code live in one test process; g++ would otherwise make the
     statics of inline functions (the kernels' `__shared__` arrays) process-wide unique symbols shared by all of them."""
     so = os.path.join(HD, "_build", f"libkernels_emul{tag}.so")
@@ -57,7 +57,6 @@ def load_emu(flags=(), tag=""):
     L.emu_exchange.argtypes = [vp, vp, vp]
     L.emu_tick.argtypes = [vp]
     L.emu_tick_kd.argtypes = [vp]
-    L.emu_set_split.argtypes = [vp, C.c_int]
     L.emu_set_compact.argtypes = [vp, C.c_int]
     L.emu_walk_len.argtypes = [vp]
     L.emu_valid_spawn.argtypes = [vp, C.c_int, f32p, f32p, u8p]
@@ -220,26 +219,14 @@ def test_kernels_reproduce_reference_trajectories_bitwise(emu, name):
     d.close()
 
 
-@pytest.mark.parametrize("name", GOLDEN)
-def test_split_tick_reproduces_reference_trajectories_bitwise(emu, name):
-    """ECMGPU_SPLIT: k_knn_rows + k_orca_rows instead of k_orca."""
-    g = Golden(name)
-    d = EmuDevice(emu, g, _cell_for(g))
-    emu.emu_set_split(d.h, 1)
-    _run_against_golden(d, g, lambda: emu.emu_tick(d.h), d.state, f"{name} / split")
-    d.close()
-
-
-@pytest.mark.parametrize("name,split", [("c2_small", 0), ("jam_small", 0), ("jam_small", 1)])
-def test_three_strips_equal_one_device_bitwise(emu, name, split):
+@pytest.mark.parametrize("name", ["c2_small", "jam_small"])
+def test_three_strips_equal_one_device_bitwise(emu, name):
     g = Golden(name)
     # halo: comfortably more than any agent's 5th-neighbour distance at the start
     r5 = _r5_max(g)
     widths = np.diff(M.strip_bounds(g.crowd.pos[:, 0], 3))[1:-1]
     halo = float(min(2.0 * r5 + 2.0, widths.min()))
     s = EmuStrips(emu, g, _cell_for(g), 3, halo)
-    for dev in s.devs:
-        emu.emu_set_split(dev.h, split)
     own0 = M.owner_of(g.crowd.pos[:, 0], s.bounds)
     st = _run_against_golden(s, g, s.step, s.state, f"{name} / 3 strips")
     assert st["owners"].max() == 1, "every live agent has exactly one owner"
@@ -252,8 +239,8 @@ def test_three_strips_equal_one_device_bitwise(emu, name, split):
     s.close()
 
 
-@pytest.mark.parametrize("name,split", [("c2_small", 0), ("jam_small", 0), ("jam_small", 1)])
-def test_three_strips_with_compact_walk_equal_one_device_bitwise(emu, name, split):
+@pytest.mark.parametrize("name", ["c2_small", "jam_small"])
+def test_three_strips_with_compact_walk_equal_one_device_bitwise(emu, name):
     """ECMGPU_COMPACT: pack / cell count / scatter walk a list of the slots a strip may own instead of every slot;
     adopted migrants are appended, nobody is listed twice."""
     g = Golden(name)
@@ -263,7 +250,6 @@ def test_three_strips_with_compact_walk_equal_one_device_bitwise(emu, name, spli
     s = EmuStrips(emu, g, _cell_for(g), 3, halo, narrow_grid=True)
     for dev in s.devs:
         emu.emu_set_compact(dev.h, 1)
-        emu.emu_set_split(dev.h, split)
     own0 = M.owner_of(g.crowd.pos[:, 0], s.bounds)
     st = _run_against_golden(s, g, s.step, s.state, f"{name} / 3 strips, compact walk")
     assert st["owners"].max() == 1

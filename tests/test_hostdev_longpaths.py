@@ -1,5 +1,5 @@
 """CPU: the polyline scan of k_attract on LONG routes (several blocks of 8 segments: block bounding boxes, backward
-scan, the four-boxes-at-once variant -DECM_ATTRACT_BBOX4) with agents anywhere along their routes, against the C
+scan) with agents anywhere along their routes, against the C
 oracle, which evaluates every segment in order like IRMPathFollower::FindAttractionPoint (IRMPathFollower.cpp:54-112).
 The golden scenes' routes mostly fit one block; this is the test of the multi-block paths.  Test infrastructure only."""
 import numpy as np
@@ -17,10 +17,9 @@ class _Scene:
         self.world, self.crowd, self.path_off, self.path_xy, self.step, self.n = world, crowd, off, pxy, step, crowd.n
 
 
-@pytest.mark.parametrize("variant", ["default", "attract_bbox4"])
-def test_attraction_points_on_long_routes(variant):
-    flags = [] if variant == "default" else ["-DECM_ATTRACT_BBOX4"]
-    emu = load_emu(flags, "" if variant == "default" else "_" + variant)
+def test_attraction_points_on_long_routes():
+    variant = "default"
+    emu = load_emu()
     w = S.world_c3()
     n = 700
     c = S.sample_crowd(w, n, 17, window=(-600, -600, 600, 600), min_goal_dist=700.0)

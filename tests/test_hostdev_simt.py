@@ -35,14 +35,6 @@ def test_simt_kernels_reproduce_reference_trajectories_bitwise(simt, name):
     d.close()
 
 
-def test_simt_split_tick(simt):
-    g = Golden("jam_small")
-    d = EmuDevice(simt, g, _cell_for(g))
-    simt.emu_set_split(d.h, 1)
-    _run_against_golden(d, g, lambda: simt.emu_tick(d.h), d.state, "jam_small / simt split", max_ticks=64)
-    d.close()
-
-
 def test_simt_exhaustive_fallback_search(simt):
     """A grid cell far too small for the crowd: eight rings do not reach the 5th neighbour, every agent goes through
     the warp-per-agent exhaustive search and its shuffle merge (knn_exhaustive) - and the trajectory stays the same."""
@@ -115,15 +107,3 @@ def test_simt_carried_list_kernel(simt):
         nbr, nbr_cnt = np.full((n, 5), -9, np.int32), np.full(n, -9, np.int32)
         simt.emu_kd_resolve(n, _p(active, u8p), _p(raw, i32p), _p(cnt, i32p), _p(cache, i32p), _p(nbr, i32p), _p(nbr_cnt, i32p))
         assert np.array_equal(cache, raw[last]), (n, last)
-
-
-@pytest.mark.parametrize("tag,flags", [("flat_twopass_prune_bbox4", ["-DECM_KNN_FLAT", "-DECM_KNN_PRUNE", "-DECM_ATTRACT_BBOX4"]),
-                                       ("twopass_prune", ["-DECM_KNN_TWOPASS", "-DECM_KNN_PRUNE"])])
-def test_simt_build_variants(tag, flags):
-    """The switches kept for A/B, compiled INTO the kernels and run with real warps (tests/test_hostdev.py pins the same
-    switches function by function)."""
-    lib = load_emu(["-DHD_SIMT"] + flags, "_simt_" + tag)
-    g = Golden("jam_small")
-    d = EmuDevice(lib, g, _cell_for(g))
-    _run_against_golden(d, g, lambda: lib.emu_tick(d.h), d.state, f"jam_small / simt {tag}", max_ticks=24)
-    d.close()

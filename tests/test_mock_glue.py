@@ -3,7 +3,7 @@
 tests/hostdev/mock_cuda builds csrc/ecmgpu.cu for the host against a synchronous stand-in for the CUDA runtime and runs
 its kernels under the SIMT emulator (tests/hostdev/shim/simt.h).  The tests below are a subset of the `-m gpu` tests,
 unchanged, pointed at that library through the ECMGPU_LIB hook: launch order, buffer sizing, mode switches (KD-tree
-neighbour mode, split tick, compact strips), the strip phases with the in-process transport, the planner / spawn /
+neighbour mode, compact strips), the strip phases with the in-process transport, the planner / spawn /
 query entry points, the pipelined host I/O calls and the C++ drop-in Simulator are exercised through the same bindings a
 GPU run uses.
 The tick runs as a captured graph like on the GPU (the mock records the capture and replays it).  It cannot show timing,
@@ -31,8 +31,7 @@ SUBSET = [
     "tests/test_gpu_strips.py::test_halo_miss_is_detected_when_the_halo_is_too_small",
     "tests/test_gpu_strips.py::test_strip_validation_errors",
     "tests/test_zz2_gpu_spawn.py::test_valid_spawn_locations_equal_the_reference_scan[0.0]",
-    "tests/test_zz2_gpu_split.py::test_split_tick_equals_default_tick_bitwise[c2_small]",
-    "tests/test_zz2_gpu_split.py::test_compact_walk_in_the_graph_tick_with_spawns_and_destroys",
+    "tests/test_zz2_gpu_compact.py::test_compact_walk_in_the_graph_tick_with_spawns_and_destroys",
     "tests/test_zz3_gpu_kdtree.py::test_kd_neighbour_lists_equal_the_unmodified_reference[c2_small]",
     "tests/test_zz3_gpu_kdtree.py::test_kd_lockstep_velocities_within_tolerance[c2_small]",
     "tests/test_zz3_gpu_kdtree.py::test_dropin_in_kd_mode_walks_like_the_unmodified_reference",
@@ -49,7 +48,7 @@ def test_gpu_suite_subset_through_the_real_c_abi_on_the_mock_runtime():
     so = make_mock.build()
     env = dict(os.environ, ECMGPU_LIB=so, LD_PRELOAD=so)  # LD_PRELOAD: for libecmsim.so, linked against libecmgpu
     env.pop("ECMGPU_GRAPH", None)  # graphs on, as on the GPU: the mock records a capture as closures and replays them
-    for k in ("ECMGPU_SPLIT", "ECMGPU_COMPACT", "ECMGPU_FUSED", "ECMGPU_GATHER"):
+    for k in ("ECMGPU_COMPACT",):
         env.pop(k, None)
     r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + SUBSET, cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=1500)

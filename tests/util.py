@@ -17,8 +17,10 @@ class Golden:
         self.name = name
         self.z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
         kw = {k: self.z["world/" + k] for k in WORLD_KEYS}
-        self.world = World(street_width=float(self.z["world/street_width"]), blocks_x=self.z["world/blocks_x"],
-                           blocks_y=self.z["world/blocks_y"], **kw)
+        sw = float(self.z["world/street_width"])
+        lattice = sw == sw  # NaN: a turned / edited world without the lattice metadata
+        self.world = World(street_width=sw if lattice else None, blocks_x=self.z["world/blocks_x"] if lattice else None,
+                           blocks_y=self.z["world/blocks_y"] if lattice else None, **kw)
         self.crowd = Crowd(self.z["crowd/pos"], self.z["crowd/goal"], self.z["crowd/radius"], self.z["crowd/speed"])
         self.path_off, self.path_xy = self.z["crowd/path_off"], self.z["crowd/path_xy"]
         self.step = float(self.z["step"])
