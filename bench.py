@@ -7,7 +7,11 @@ One JSON line on stdout (rank 0).  Workload at N=1: C3, 1M agents in the 2025-bl
 (SURVEY.md §8d); a "step" is one Simulator::Update tick over the whole crowd.
 
   value        whole-job agent-updates/s with all state resident in HBM (CUDA events on the
-               simulator's stream, max over ranks)
+               simulator's stream, max over ranks), timed on the CONGESTED crowd: the tick gets dearer
+               for the first ~400 ticks (more constraints per agent, LP3D), so the K timed ticks start at
+               tick --steady-tick (600); the window is repeated --repeats times, `ms_per_step` is the
+               median window and `windows_ms_per_step` lists all of them.  `from_rest` is the same K
+               ticks right after the warm-up (the cheap phase), reported beside it
   e2e          same metric through the C ABI with HOST buffers (ecmgpu_update_io): every tick uploads
                positions and velocities from pinned memory, runs the tick and downloads positions,
                velocities and active flags; transfers of consecutive ticks overlap with compute.
@@ -267,14 +271,14 @@ def cpu_reference_run(w, c, off, pxy, sample_agents: int, ticks: int, warm: int,
     and all obstacle segments per agent: its cost per agent-update is flat in the sample size).
     replicas > 0: additionally run that many independent copies of the same sample side by side, one per core -
     what a farm of reference processes would deliver on this box (labelled upper bound)."""
-    n = min(sample_agents, c.n)
+    n = min(sample_agents, c.n) if sample_agents > 0 else c.n
     if budget_s is not None:
         probe = _cpu_sample(w, c, off, pxy, min(256, n))
         per_agent = _cpu_run(w, *probe, 1, 0)[0] / probe[0].n
         n = int(max(64, min(n, budget_s / ((ticks + warm) * per_agent))))
     sub, sub_off, sub_xy = _cpu_sample(w, c, off, pxy, n)
     dt, kind = _cpu_run(w, sub, sub_off, sub_xy, ticks, warm)
-    res = {"value": n * ticks / dt, "unit": UNIT, "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
+    res = {"value": n * ticks / dt, "unit": UNIT, "cores": 1, "kind": kind, "host_cores": os.cpu_count(), "same_config": bool(n == c.n),
            "sample": f"{n} agents nearest the crowd centroid of the same world ({w.n_cells} ECM cells, {w.n_obst_vertices} obstacle segments), "
                      f"{ticks} ticks after {warm} warm-up", "ms_per_tick_sample": 1e3 * dt / ticks}
     if replicas > 1:
@@ -307,6 +311,45 @@ def run_reference_arm(args):
             "cpu_baseline": res,
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def strips_parity(sim, w, c, off, pxy, ticks, rank, device):
+    """Multi-GPU parity, visible in the bench line: `ticks` ticks on the strips and on ONE GPU (rank 0, a fresh single
+    simulator) from the same global state, compared bit for bit.  Collective: every rank calls it."""
+    from ecmgenerator_b200 import gpu
+    from ecmgenerator_b200.multigpu import REBALANCE_STATE, owner_of
+
+    sim.sync()
+    state = {k: sim.gather(k)[0] for k in REBALANCE_STATE}
+    owners = sim.gather(gpu.ACTIVE)[1]
+    own0 = owner_of(state[gpu.POS][:, 0], sim.bounds)
+    miss0 = sim.global_stats(("halo_misses",))["halo_misses"]
+    sim.update(ticks)
+    sim.sync()
+    pos1, owners1 = sim.gather(gpu.POS)
+    vel1, _ = sim.gather(gpu.VEL)
+    miss1 = sim.global_stats(("halo_misses",))["halo_misses"]
+    if rank != 0:
+        return None
+    n = c.n
+    one = gpu.GpuSim(w, n, float(S.DT), device=device, record_neighbors=False, neighbor_cell=float(sim.stats()["neighbor_cell"]),
+                     path_pool_points=int(off[-1] * 1.25) + 4096)
+    one.bulk_load(c.pos, c.radius, c.speed, off, pxy)
+    for k, a in state.items():
+        one.write(k, a)
+    one.write(gpu.ACTIVE, owners)
+    one.update(ticks)
+    one.sync()
+    p, v, a = one.read(gpu.POS, 0, n), one.read(gpu.VEL, 0, n), one.read(gpu.ACTIVE, 0, n) > 0
+    one.close()
+    same_owner = bool(np.array_equal(owners1 > 0, a)) and int(owners1.max()) <= 1
+    same_pos = bool(np.array_equal(pos1[a].view(np.uint32), p[a].view(np.uint32)))
+    same_vel = bool(np.array_equal(vel1[a].view(np.uint32), v[a].view(np.uint32)))
+    own1 = owner_of(pos1[:, 0], sim.bounds)
+    return {"bitwise_vs_1gpu": same_owner and same_pos and same_vel, "ticks": int(ticks), "migrations": int(((own0 != own1) & a).sum()),
+            "agents_compared": int(a.sum()), "halo_misses_during": int(miss1 - miss0),
+            "rows_differing": int((pos1[a].view(np.uint32) != p[a].view(np.uint32)).any(axis=1).sum()),
+            "how": "global state gathered from the strips, loaded into a single simulator on rank 0; both advanced, positions / velocities / ownership compared bit for bit"}
 
 
 def run_ours(args):
@@ -349,33 +392,68 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         sim.update(1)
     sim.sync()
+    raw0 = sim if world == 1 else sim.sim
+
+    def timed_window(steps):
+        """K ticks between two stream marks, barrier + synchronize on both sides; max over ranks."""
+        barrier()
+        sim.mark(0)
+        for _ in range(steps):
+            sim.update(1)
+        sim.mark(1)
+        barrier()
+        t_ms = sim.elapsed_ms(0, 1)
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([t_ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+        return t_ms
+
+    def active_now():
+        return float(sim.stats()["n_active"]) if world == 1 else float(sim.global_active())
+
+    # ---- disclosure: K ticks from the crowd at rest (the cheap phase of the run)
+    clocks = ClockSampler(local)
+    clocks.start()
+    done = max(args.warmup, 3)
+    from_rest = None
+    if args.steady_tick > done:
+        a_r = active_now()
+        st_a = sim.stats()
+        ms_r = timed_window(args.steps)
+        st_b = sim.stats()
+        done += args.steps
+        from_rest = {"from_tick": int(done - args.steps), "ms_per_step": ms_r / args.steps, "value": a_r * args.steps / (ms_r * 1e-3), "unit": UNIT,
+                     "lp3d_runs_per_tick_rank0": (st_b["lp3d_runs"] - st_a["lp3d_runs"]) / args.steps,
+                     "note": "the same K ticks right after the warm-up, crowd at rest: cheaper than the congested crowd the headline is timed on"}
+        # ---- let the crowd congest (untimed): the tick cost levels off after ~400 ticks (profiles/r01_experiments.md)
+        while done < args.steady_tick:
+            sim.update(min(50, args.steady_tick - done))
+            done += min(50, args.steady_tick - done)
+        sim.sync()
     st0 = sim.stats()
     active0 = st0["n_active"]
     # the state the timed ticks start from: the end-to-end loop below replays it, so that `value` and `e2e` time the
-    # same phase of the simulation (the tick gets dearer as the crowd congests, see "steady_state")
-    raw0 = sim if world == 1 else sim.sim
+    # same phase of the simulation
     pos_w, vel_w, act_w = raw0.read(gpu.POS, 0, n), raw0.read(gpu.VEL, 0, n), raw0.read(gpu.ACTIVE, 0, n) > 0
 
-    # ---- timed: K ticks, state resident in HBM
-    clocks = ClockSampler(local)
-    clocks.start()
-    barrier()
-    sim.mark(0)
-    for _ in range(args.steps):
-        sim.update(1)
-    sim.mark(1)
-    barrier()
-    ms = sim.elapsed_ms(0, 1)
+    # ---- timed: K ticks, state resident in HBM, repeated; the median window is the headline
+    windows, win_active = [], []
+    for _ in range(max(1, args.repeats)):
+        win_active.append(active_now())
+        windows.append(timed_window(args.steps))
+    order = sorted(range(len(windows)), key=lambda i: windows[i])
+    mid = order[len(order) // 2]
+    ms = windows[mid]
     st1 = sim.stats()
-    if world > 1:
-        import torch.distributed as dist
-
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    launches = st1["kernel_launches"] - st0["kernel_launches"]
-    updates = float(active0) * args.steps if world == 1 else float(sim.global_active()) * args.steps
+    launches = (st1["kernel_launches"] - st0["kernel_launches"]) // max(1, args.repeats)
+    updates = win_active[mid] * args.steps
     value = updates / (ms * 1e-3)
+    lp3d_per_tick = (st1["lp3d_runs"] - st0["lp3d_runs"]) / (args.steps * max(1, args.repeats))
+    timed_from = int(done)
+    done += args.steps * max(1, args.repeats)
 
     # ---- per-phase times for the roofline of the dominant kernel (separate pass, same state)
     roof = None
@@ -396,13 +474,10 @@ def run_ours(args):
         # k_attract 40 + 8 P (pos, speed, path header + polyline; attraction + prefvel out),
         # k_orca 136 (own vel/radius, 5 x (pos,vel,radius) neighbours; pos, vel, force out)
         alg = {"attract": 40.0 + 8.0 * mean_p, "orca": 136.0, "tick": 176.0 + 8.0 * mean_p}
-        fused = acc["attract"] < 0.02 * acc["orca"]  # k_tick = attraction + ORCA in one kernel (timed as the "orca" phase)
         dom = "orca" if acc["orca"] >= acc["attract"] else "attract"
-        if fused:
-            alg["orca"] = alg["tick"]
         ach = alg[dom] * active0 / (acc[dom] * 1e-3) / 1e9
         ach_tick = alg["tick"] * active0 / ((ms / args.steps) * 1e-3) / 1e9  # whole tick: the timed region itself (graph launch)
-        kname = "k_tick" if fused else "k_" + dom
+        kname = "k_" + dom
         traffic, traffic_src = ncu_traffic(kname)
         roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_agent": alg[dom],
@@ -513,39 +588,16 @@ def run_ours(args):
     raw.sync()
     e2e["link"] = {"d2h_GBps": 4 * 8 * n / (raw.elapsed_ms(0, 1) * 1e6), "h2d_GBps": 4 * 8 * n / (raw.elapsed_ms(1, 2) * 1e6)}
     lk.free()
+    # sampled over all timed regions (resident ticks, per-phase pass, end-to-end ticks)
     clk = clocks.stop()
-    # ---- disclosure: the same K ticks once the crowd has congested (the tick cost levels off after ~400 ticks)
-    steady = None
-    if args.steady_tick > 0:
-        done = max(args.warmup, 3) + 1  # the end-to-end loop replayed the post-warm-up state: the crowd is one tick past it
-        while done < args.steady_tick:
-            sim.update(min(50, args.steady_tick - done))
-            done += min(50, args.steady_tick - done)
-        st_a = sim.stats()
-        barrier()
-        sim.mark(0)
-        for _ in range(args.steps):
-            sim.update(1)
-        sim.mark(1)
-        barrier()
-        ms_s = sim.elapsed_ms(0, 1)
-        st_b = sim.stats()
-        act_s = float(st_b["n_active"]) if world == 1 else float(sim.global_active())
-        if world > 1:
-            import torch.distributed as dist
-
-            t = torch.tensor([ms_s], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_s = float(t.item())
-        steady = {"from_tick": int(done), "ms_per_step": ms_s / args.steps, "value": act_s * args.steps / (ms_s * 1e-3), "unit": UNIT,
-                  "lp3d_runs_per_tick_rank0": (st_b["lp3d_runs"] - st_a["lp3d_runs"]) / args.steps,
-                  "note": "the headline is timed on ticks [warmup, warmup+steps) from the crowd at rest; this is the same measurement on the congested crowd"}
-  # sampled over all timed regions (resident ticks, per-phase pass, end-to-end ticks)
 
     global_active = int(active0)
+    parity = None
     if world > 1:
         import torch.distributed as dist
 
+        if args.parity_ticks > 0:
+            parity = strips_parity(sim, w, c, off, pxy, args.parity_ticks, rank, local)
         global_active = sim.global_active()
         # whole-job counters; zero halo misses = every owned agent's 5-NN ball stayed inside what its rank sees,
         # i.e. the strips computed exactly what one GPU computes (DESIGN.md "Multi-GPU")
@@ -557,7 +609,7 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         t = time.time()
-        cpu = cpu_reference_run(w, c, off, pxy, args.cpu_sample, args.cpu_ticks, 1)
+        cpu = cpu_reference_run(w, c, off, pxy, args.cpu_sample, args.cpu_ticks, 1, budget_s=args.cpu_inline_budget)
         log(f"[bench] cpu baseline in {time.time() - t:.1f}s")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -580,8 +632,13 @@ def run_ours(args):
         line["roofline"] = roof
     if e2e:
         line["e2e"] = e2e
-    if steady:
-        line["steady_state"] = steady
+    line["windows_ms_per_step"] = [round(x / args.steps, 6) for x in windows]
+    line["window"] = {"from_tick": timed_from, "repeats": len(windows), "reported": "median window", "min_ms_per_step": min(windows) / args.steps,
+                      "max_ms_per_step": max(windows) / args.steps, "lp3d_runs_per_tick_rank0": lp3d_per_tick}
+    if from_rest:
+        line["from_rest"] = from_rest
+    if parity:
+        line["parity"] = parity
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
@@ -593,12 +650,18 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--cpu-budget", type=float, default=45.0, help="--impl reference: seconds of CPU time the timed sample may take")
-    ap.add_argument("--steady-tick", type=int, default=600, help="also time K ticks from this tick on (0 = skip)")
+    ap.add_argument("--steady-tick", type=int, default=600,
+                    help="the timed ticks start at this tick, on the congested crowd (0: right after the warm-up, crowd at rest)")
+    ap.add_argument("--repeats", type=int, default=5, help="how many times the K-tick window is timed (the median is reported)")
+    ap.add_argument("--parity-ticks", type=int, default=40,
+                    help="N > 1: after the timing, this many ticks on the strips AND on rank 0 alone from the same state, compared bit for bit (0 = skip)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3_1m", choices=sorted(S.CONFIGS))
     ap.add_argument("--agents", type=int, default=None)
-    ap.add_argument("--cpu-sample", type=int, default=4096, help="agents in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="agents in the CPU baseline sample (0: the whole crowd if the time budget allows, else as many as fit)")
     ap.add_argument("--cpu-ticks", type=int, default=2)
+    ap.add_argument("--cpu-inline-budget", type=float, default=20.0, help="seconds the cpu_baseline leg of our own line may take")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cell", type=float, default=0.0, help="neighbour grid cell (0 = from crowd density)")
     ap.add_argument("--bin", type=float, default=0.0, help="static bin edge (0 = from the ECM)")

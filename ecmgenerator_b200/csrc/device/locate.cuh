@@ -44,7 +44,8 @@ __device__ __forceinline__ bool cell_contains(const EcmView& ecm, int c, v2 p) {
 template <bool kSync>
 __device__ __forceinline__ int find_cell(const EcmView& ecm, const BinView& bins, v2 p, bool valid = true) {
     int res = -1;
-    const int b = valid ? bins.bin_of(p) : 0;
+    const bool level = valid && bins.level_hit(p.y);  // exactly level with a cell vertex: the bin lists do not apply (world.cuh)
+    const int b = valid && !level ? bins.bin_of(p) : 0;
     int i0 = 0, cnt = 0;
     if (valid && b >= 0) {
         i0 = __ldg(&bins.cell_start[b]);
@@ -58,7 +59,18 @@ __device__ __forceinline__ int find_cell(const EcmView& ecm, const BinView& bins
             if (cell_contains(ecm, c, p)) res = c;
         }
     }
-    if (valid && b < 0) {  // outside the static grid: the reference's linear scan
+    if (level) {  // rare (~1e-6 per query): the cells reaching into the point's bin row, in index order
+        const int r = bins.row_of(p);
+        if (r >= 0) {
+            const int a = __ldg(&bins.row_start[r]), e = __ldg(&bins.row_start[r + 1]);
+            for (int k = a; k < e && res < 0; k++) {
+                const int c = __ldg(&bins.row_items[k]);
+                if (cell_contains(ecm, c, p)) res = c;
+            }
+            return res;
+        }
+    }
+    if (valid && (b < 0 || level)) {  // outside the static grid: the reference's linear scan
         for (int c = 0; c < 2 * ecm.n_edges && res < 0; c++)
             if (cell_contains(ecm, c, p)) res = c;
     }

@@ -40,6 +40,39 @@ struct BinView {
     const int* cell_items;
     const int* obst_start;   // [w*h+1]
     const int* obst_items;
+    // The reference's even-odd test (UtilityFunctions.cpp:54-86) uses strict y comparisons, so a ray that passes exactly
+    // through a polygon vertex which is not a y-extremum of the polygon is counted once instead of twice: a point LEVEL
+    // with such a vertex is reported inside a cell that can lie arbitrarily far to its right (no such vertex exists in
+    // an axis-aligned lattice; every oblique world has them - golden scene oblique_small).  The bbox argument behind the
+    // per-bin lists does not hold for those points.  They are recognised exactly - level_y is the sorted set of the y
+    // of every cell-polygon vertex, level_bits a hash bitmap in front of it - and answered from row_items: per bin ROW
+    // the ascending list of the cells whose y-extent reaches into the row (a cell containing p under the reference's
+    // predicate has an edge with min y < p.y < max y, so it is in the list of p's row).
+    const float* level_y;
+    const unsigned* level_bits;
+    int n_levels, level_shift;
+    const int* row_start;    // [h+1]
+    const int* row_items;
+    __device__ __forceinline__ bool level_hit(float y) const {
+        if (n_levels == 0) return false;
+        const unsigned u = __float_as_uint(y == 0.0f ? 0.0f : y);  // -0 == +0
+        const unsigned hsh = (u * 2654435761u) >> level_shift;
+        if (!((__ldg(&level_bits[hsh >> 5]) >> (hsh & 31u)) & 1u)) return false;
+        int lo = 0, hi = n_levels - 1;
+        while (lo <= hi) {
+            const int mid = (lo + hi) >> 1;
+            const float v = __ldg(&level_y[mid]);
+            if (v == y) return true;
+            if (v < y) lo = mid + 1;
+            else hi = mid - 1;
+        }
+        return false;
+    }
+    __device__ __forceinline__ int row_of(v2 p) const {
+        const float fy = (p.y - y0) * inv_bin;
+        if (!(fy >= 0.0f) || !(fy < (float)h)) return -1;
+        return (int)fy;
+    }
     __device__ __forceinline__ int bin_of(v2 p) const {
         float fx = (p.x - x0) * inv_bin, fy = (p.y - y0) * inv_bin;
         // !(>=) also rejects NaN

@@ -76,7 +76,10 @@ struct ecmgpu_sim {
     DevBuf<int> d_obst_next, d_obst_prev;
     DevBuf<unsigned char> d_obst_convex;
     DevBuf<float2> d_obst_dir;
-    DevBuf<int> d_bin_cell_start, d_bin_cell_items, d_bin_obst_start, d_bin_obst_items;
+    DevBuf<int> d_bin_cell_start, d_bin_cell_items, d_bin_obst_start, d_bin_obst_items, d_row_start, d_row_items;
+    DevBuf<float> d_level_y;
+    DevBuf<unsigned> d_level_bits;
+    int n_levels = 0, level_shift = 31;
     int n_vertices = 0, n_edges = 0, n_obst = 0;
 
     // ---- agents, device (per slot)
@@ -313,6 +316,48 @@ int build_bins(ecmgpu_sim* s) {
         s->max_cell_list = 0;
         for (int i = 0; i < nb; i++) s->max_cell_list = std::max(s->max_cell_list, cstart[i + 1] - cstart[i]);
     }
+    // -- points exactly level with a cell vertex (BinView::level_hit): the sorted y set, its hash bitmap, per-row cell lists
+    std::vector<float> levels;
+    std::vector<unsigned> level_bits;
+    std::vector<int> rstart(s->bins_h + 1, 0), ritems;
+    {
+        const int nc = 2 * s->n_edges;
+        levels.reserve(6 * (size_t)s->n_edges);
+        for (int e = 0; e < s->n_edges; e++) {
+            for (int k = 0; k < 4; k++) levels.push_back(s->h_edge_cl[8 * e + 2 * k + 1]);
+            levels.push_back(s->h_vert_xy[2 * s->h_edge_v[2 * e] + 1]);
+            levels.push_back(s->h_vert_xy[2 * s->h_edge_v[2 * e + 1] + 1]);
+        }
+        for (float& v : levels) if (v == 0.0f) v = 0.0f;  // -0 -> +0
+        levels.erase(std::remove_if(levels.begin(), levels.end(), [](float v) { return !(v == v); }), levels.end());
+        std::sort(levels.begin(), levels.end());
+        levels.erase(std::unique(levels.begin(), levels.end()), levels.end());
+        int lg = 12;
+        while ((1u << lg) < 32u * levels.size() && lg < 24) lg++;
+        s->level_shift = 32 - lg;
+        level_bits.assign((size_t)1 << (lg - 5), 0u);
+        for (float v : levels) {
+            unsigned u;
+            memcpy(&u, &v, 4);
+            const unsigned hsh = (u * 2654435761u) >> s->level_shift;
+            level_bits[hsh >> 5] |= 1u << (hsh & 31u);
+        }
+        s->n_levels = (int)levels.size();
+        std::vector<int> ra(nc), rb(nc);
+        for (int c = 0; c < nc; c++) {
+            const int e = c >> 1, side = c & 1;
+            const float* cl = &s->h_edge_cl[8 * e];
+            const float ys[4] = {s->h_vert_xy[2 * s->h_edge_v[2 * e] + 1], s->h_vert_xy[2 * s->h_edge_v[2 * e + 1] + 1], cl[2 * side + 1], cl[4 + 2 * side + 1]};
+            const double lo = std::min(std::min(ys[0], ys[1]), std::min(ys[2], ys[3])), hi = std::max(std::max(ys[0], ys[1]), std::max(ys[2], ys[3]));
+            bin_range(lo, hi, y0, s->bins_h, ra[c], rb[c]);
+            for (int y = ra[c]; y <= rb[c]; y++) rstart[y + 1]++;
+        }
+        for (int i = 0; i < s->bins_h; i++) rstart[i + 1] += rstart[i];
+        ritems.resize(rstart[s->bins_h]);
+        std::vector<int> fill(rstart.begin(), rstart.end() - 1);
+        for (int c = 0; c < nc; c++)  // ascending c => every list ascending
+            for (int y = ra[c]; y <= rb[c]; y++) ritems[fill[y]++] = c;
+    }
     // -- obstacle segments within `range` of the bin rectangle
     const double range = std::max(s->prm.max_obstacle_range > 0 ? (double)s->prm.max_obstacle_range : 0.0, (double)s->tracked_range);
     std::vector<int> ostart(nb + 1, 0), oitems;
@@ -352,6 +397,14 @@ int build_bins(ecmgpu_sim* s) {
     CUDA_TRY(s, cudaMemcpyAsync(s->d_bin_cell_items.p, citems.data(), sizeof(int) * citems.size(), cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(s, cudaMemcpyAsync(s->d_bin_obst_start.p, ostart.data(), sizeof(int) * (nb + 1), cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(s, cudaMemcpyAsync(s->d_bin_obst_items.p, oitems.data(), sizeof(int) * oitems.size(), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, s->d_level_y.alloc(std::max<size_t>(levels.size(), 1)));
+    CUDA_TRY(s, s->d_level_bits.alloc(level_bits.size()));
+    CUDA_TRY(s, s->d_row_start.alloc(rstart.size()));
+    CUDA_TRY(s, s->d_row_items.alloc(std::max<size_t>(ritems.size(), 1)));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_level_y.p, levels.data(), sizeof(float) * levels.size(), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_level_bits.p, level_bits.data(), sizeof(unsigned) * level_bits.size(), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_row_start.p, rstart.data(), sizeof(int) * rstart.size(), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_row_items.p, ritems.data(), sizeof(int) * ritems.size(), cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(s, cudaStreamSynchronize(s->stream));  // the host vectors die here
     s->built_range = (float)range;
     s->bins_dirty = false;
@@ -431,6 +484,12 @@ TickView make_view(ecmgpu_sim* s) {
     t.bins.cell_items = s->d_bin_cell_items.p;
     t.bins.obst_start = s->d_bin_obst_start.p;
     t.bins.obst_items = s->d_bin_obst_items.p;
+    t.bins.level_y = s->d_level_y.p;
+    t.bins.level_bits = s->d_level_bits.p;
+    t.bins.n_levels = s->n_levels;
+    t.bins.level_shift = s->level_shift;
+    t.bins.row_start = s->d_row_start.p;
+    t.bins.row_items = s->d_row_items.p;
     t.grid.x0 = s->gx0;
     t.grid.y0 = s->gy0;
     t.grid.cell = s->cell;

@@ -111,12 +111,38 @@ void CellLocator::Build(const FlatWorld& w, float bin) {
     for (int c = 0; c < nc; c++)
         for (int y = ay[c]; y <= by[c]; y++)
             for (int x = ax[c]; x <= bx[c]; x++) items_[fill[y * w_ + x]++] = c;
+    // exact-level points: the y of every cell-polygon vertex, and per bin row the cells reaching into it
+    levels_.clear();
+    for (int e = 0; e < nE; e++) {
+        for (int k = 0; k < 4; k++) levels_.push_back(Cl(w, e, k).y);
+        levels_.push_back(Vert(w, w.ecm.edge_v[2 * e]).y);
+        levels_.push_back(Vert(w, w.ecm.edge_v[2 * e + 1]).y);
+    }
+    for (float& v : levels_) if (v == 0.0f) v = 0.0f;
+    levels_.erase(std::remove_if(levels_.begin(), levels_.end(), [](float v) { return !(v == v); }), levels_.end());
+    std::sort(levels_.begin(), levels_.end());
+    levels_.erase(std::unique(levels_.begin(), levels_.end()), levels_.end());
+    row_start_.assign(h_ + 1, 0);
+    for (int c = 0; c < nc; c++)
+        for (int y = ay[c]; y <= by[c]; y++) row_start_[y + 1]++;
+    for (int i = 0; i < h_; i++) row_start_[i + 1] += row_start_[i];
+    row_items_.resize(row_start_[h_]);
+    std::vector<int> rfill(row_start_.begin(), row_start_.end() - 1);
+    for (int c = 0; c < nc; c++)
+        for (int y = ay[c]; y <= by[c]; y++) row_items_[rfill[y]++] = c;
 }
 
 int CellLocator::FindCell(const FlatWorld& w, float x, float y) const {
     const P2f p = P(x, y);
     const float fx = (x - x0_) / bin_, fy = (y - y0_) / bin_;
-    if (fx >= 0.0f && fy >= 0.0f && fx < (float)w_ && fy < (float)h_) {
+    if (std::binary_search(levels_.begin(), levels_.end(), y)) {  // exactly level with a cell vertex (see planner.h)
+        if (fy >= 0.0f && fy < (float)h_) {
+            const int r = (int)fy;
+            for (int i = row_start_[r]; i < row_start_[r + 1]; i++)
+                if (CellContains(w, row_items_[i], p)) return row_items_[i];
+            return -1;
+        }
+    } else if (fx >= 0.0f && fy >= 0.0f && fx < (float)w_ && fy < (float)h_) {
         const int b = (int)fy * w_ + (int)fx;
         for (int i = start_[b]; i < start_[b + 1]; i++)
             if (CellContains(w, items_[i], p)) return items_[i];

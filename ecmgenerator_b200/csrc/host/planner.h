@@ -33,6 +33,11 @@ private:
     float x0_ = 0, y0_ = 0, bin_ = 1;
     int w_ = 0, h_ = 0;
     std::vector<int> start_, items_;
+    // A point exactly level with a cell vertex can be "inside" a cell far to its right under the reference's even-odd
+    // test (strict y comparisons; csrc/device/world.cuh BinView::level_hit): such points are recognised through the
+    // sorted set of vertex y values and answered from per-row cell lists instead of the bin list.
+    std::vector<float> levels_;
+    std::vector<int> row_start_, row_items_;
 };
 
 // ECM::RetractPoint (/root/reference/ECMGenerator/ECM.cpp:20-96) on a located cell.

@@ -183,10 +183,10 @@ def main_new(only):
     #     non-rectangular neighbours and LP3D all run on oblique, concave input
     if only in (None, "concave_small"):
         w5 = lattice_world([30, 30], [12, 12, 12], 6.0, -33.0, -24.0).with_recessed_obstacles(7, depth=(0.8, 2.0))
-        c5 = S.sample_crowd(lattice_world([30, 30], [12, 12, 12], 6.0, -33.0, -24.0), 300, 15, radius=(0.3, 0.3), speed=(1.4, 1.4),
+        c5 = S.sample_crowd(lattice_world([30, 30], [12, 12, 12], 6.0, -33.0, -24.0), 360, 15, radius=(0.3, 0.3), speed=(1.4, 1.4),
                             min_goal_dist=25.0, wall_margin=0.05)
         a5 = -0.2449787
-        make("concave_small", w5.rotated(a5), turned(c5, a5), 120, 105)
+        make("concave_small", w5.rotated(a5), turned(c5, a5), 160, 105)
 
 
 if __name__ == "__main__":

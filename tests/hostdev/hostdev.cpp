@@ -73,7 +73,7 @@ void* hd_world(int nV, const float* vert_xy, int nE, const int* edge_v, const fl
     w->obst_start = {0, nO};
     w->ecm = EcmView{nV, nE, w->vert_xy.data(), w->edge_v.data(), w->edge_cl.data()};
     w->obst = ObstView{nO, w->obst_xy.data(), w->obst_next.data(), w->obst_prev.data(), w->obst_convex.data(), w->obst_dir.data()};
-    BinView b;
+    BinView b{};  // one bin over everything = the reference's linear scans (no level lists needed: n_levels = 0)
     b.x0 = -1.0e9f; b.y0 = -1.0e9f; b.inv_bin = 1.0e-12f; b.w = 1; b.h = 1;
     b.cell_start = w->cell_start.data(); b.cell_items = w->cell_items.data();
     b.obst_start = w->obst_start.data(); b.obst_items = w->obst_items.data();

@@ -93,6 +93,7 @@ struct Emu {
         memset(&t, 0, sizeof(t));
         t.ecm = EcmView{(int)vert_xy.size(), (int)edge_v.size(), vert_xy.data(), edge_v.data(), edge_cl.data()};
         t.obst = ObstView{(int)obst_xy.size(), obst_xy.data(), obst_next.data(), obst_prev.data(), obst_convex.data(), obst_dir.data()};
+        t.bins = BinView{};
         t.bins.x0 = -1.0e9f; t.bins.y0 = -1.0e9f; t.bins.inv_bin = 1.0e-12f; t.bins.w = 1; t.bins.h = 1;
         t.bins.cell_start = bin_cell_start.data(); t.bins.cell_items = cell_items.data();
         t.bins.obst_start = bin_obst_start.data(); t.bins.obst_items = obst_items.data();

@@ -72,3 +72,33 @@ def test_std_sort_restatement_handles_ties():
         L.eo_test_std_sort(idx.ctypes.data_as(C.POINTER(C.c_int)), n, pos.ctypes.data_as(C.POINTER(C.c_float)), 0)
         assert sorted(idx.tolist()) == list(range(n))
         assert (np.diff(pos[idx, 0]) >= 0).all()
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_host_locator_matches_the_reference_probes(name):
+    """csrc/host/planner.cpp CellLocator (bin lists + the exact-level path) against the reference's linear scan.  In the
+    turned worlds a probe level with a cell vertex is "inside" a cell far to its right under the reference's even-odd
+    test (UtilityFunctions.cpp:54-86); the bin lists alone would miss that."""
+    from ecmgenerator_b200 import host
+
+    g = Golden(name)
+    assert np.array_equal(host.find_cells(g.world, g.z["probe/xy"]), g.z["probe/cell"])
+
+
+def test_new_goldens_hold_oblique_and_concave_geometry():
+    """obstacle segments that are not axis-aligned, concave obstacle vertices, and both reaching
+    ORCA::GenerateConstraints (ORCA.cpp:146-239) under the parity checks."""
+    for name, want_concave in (("oblique_small", False), ("concave_small", True)):
+        g = Golden(name)
+        a = g.world.obst_xy
+        b = a[g.world.obst_next]
+        oblique = (a[:, 0] != b[:, 0]) & (a[:, 1] != b[:, 1])
+        assert oblique.all(), name
+        assert ((g.world.obst_convex == 0).sum() > 0) == want_concave, name
+        o = OracleSim(g.world, g.n + 8, g.step, "exact-knn")
+        o.bulk_load(g.crowd.pos, g.crowd.radius, g.crowd.speed, g.path_off, g.path_xy)
+        o.step(g.ticks("exact-knn"))
+        c = o.counters()
+        assert c["oblique_segments"] > 50_000, c
+        if want_concave:
+            assert c["concave_segments"] > 100_000 and c["lp3d"] > 300, c

@@ -1,0 +1,29 @@
+#!/usr/bin/env bash
+# One short GPU call: [pytest -m gpu] + A/B of build variants (from rest and congested) + optional ncu capture.
+#   gpurun --timeout 900 -- 'bash tools/gpu_ab.sh <tag> "<variant specs>" [tests] [ncu]'
+set -u
+TAG=${1:-ab}
+V=${2:-base}
+OUT=gpurun_out
+mkdir -p "$OUT"
+export PYTHONUNBUFFERED=1
+export ECM_WORKLOAD_CACHE=$PWD/workloads
+step() { echo "=== $1 ($(date +%T))" | tee -a "$OUT/${TAG}_session.log"; }
+if [[ " ${*:3} " == *" tests "* ]]; then
+  step "pytest -m gpu"
+  timeout 900 python -m pytest tests -m gpu -q -x -s >"$OUT/${TAG}_gpu_tests.log" 2>&1
+  echo "pytest exit $?" | tee -a "$OUT/${TAG}_session.log"; tail -3 "$OUT/${TAG}_gpu_tests.log"
+fi
+step "A/B from rest"
+timeout 600 python tools/ab_variants.py $V >"$OUT/${TAG}_ab_rest.jsonl" 2>"$OUT/${TAG}_ab_rest.err"
+step "A/B congested (400 ticks of pre-roll)"
+AB_PREROLL=400 timeout 600 python tools/ab_variants.py $V >"$OUT/${TAG}_ab_congested.jsonl" 2>"$OUT/${TAG}_ab_congested.err"
+if [[ " ${*:3} " == *" ncu "* ]]; then
+  step "ncu launch list"
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file "$OUT/${TAG}_launches.csv" \
+      python bench.py --steps 2 --warmup 3 --no-cpu --steady-tick 0 >"$OUT/${TAG}_ncu_launch_bench.log" 2>&1
+  step "ncu --set full"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_orca|k_attract|k_scatter|k_bin_count" --launch-skip 12 -c 4 \
+      -o "$OUT/${TAG}_full" -f python bench.py --steps 3 --warmup 5 --no-cpu --steady-tick 0 >"$OUT/${TAG}_ncu_full_bench.log" 2>&1
+fi
+step "done"
