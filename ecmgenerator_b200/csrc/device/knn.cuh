@@ -29,11 +29,11 @@ struct Knn {
     // compare-exchange chain: the candidate sinks to its place, the displaced entry is carried on.
     // Exact distance ties (ordered by slot id) take the out-of-line path: they are rare and keeping
     // them out of the inlined chain keeps the hot loop small (the kernels are I-cache bound).
-    __device__ __noinline__ void insert_with_ties(float cd, int cq, const int* __restrict__ s_slot) {
+    __device__ __noinline__ void insert_with_ties(float cd, int cq, const GridView& g) {
         bool placed = false;  // once the candidate sits, the displaced entries just shift down
         for (int j = 0; j < kK; j++) {
             bool less = placed || cd < d[j];
-            if (!placed && cd == d[j] && q[j] >= 0) less = __ldg(&s_slot[cq]) < __ldg(&s_slot[q[j]]);  // tie: lower slot id first
+            if (!placed && cd == d[j] && q[j] >= 0) less = g.slot_of_row(cq) < g.slot_of_row(q[j]);  // tie: lower slot id first
             placed = less;
             if (less) {
                 float td = d[j]; d[j] = cd; cd = td;
@@ -41,9 +41,9 @@ struct Knn {
             }
         }
     }
-    __device__ __forceinline__ void insert(float cd, int cq, const int* __restrict__ s_slot) {
+    __device__ __forceinline__ void insert(float cd, int cq, const GridView& g) {
         const bool tie = (cd == d[0]) | (cd == d[1]) | (cd == d[2]) | (cd == d[3]) | (cd == d[4]);
-        if (tie) { insert_with_ties(cd, cq, s_slot); return; }
+        if (tie) { insert_with_ties(cd, cq, g); return; }
         bool placed = false;
 #pragma unroll
         for (int j = 0; j < kK; j++) {
@@ -64,7 +64,7 @@ struct Knn {
         v2 pj = __ldg(&g.s_pos[cand]);
         float dx = pj.x - self.x, dy = pj.y - self.y;
         float dd = dx * dx + dy * dy;
-        if (dd > kEpsilon && dd <= d[kK - 1]) insert(dd, cand, g.s_slot);
+        if (dd > kEpsilon && dd <= d[kK - 1]) insert(dd, cand, g);
     }
 };
 
@@ -129,7 +129,7 @@ __device__ __forceinline__ void knn_exhaustive(Knn& k, v2 self, const GridView& 
         for (int j = 0; j < kK; j++) {
             float dd = __shfl_sync(0xffffffffu, k.d[j], src);
             int qq = __shfl_sync(0xffffffffu, k.q[j], src);
-            if (qq >= 0 && dd <= m.d[kK - 1]) m.insert(dd, qq, g.s_slot);
+            if (qq >= 0 && dd <= m.d[kK - 1]) m.insert(dd, qq, g);
         }
     }
     k = m;

@@ -70,7 +70,7 @@ __device__ __forceinline__ int find_cell(const EcmView& ecm, const BinView& bins
             return res;
         }
     }
-    if (valid && (b < 0 || level)) {  // outside the static grid: the reference's linear scan
+    if (valid && (b < 0 || level) && !bins.closed) {  // outside a static grid that does not hold every cell: the reference's linear scan
         for (int c = 0; c < 2 * ecm.n_edges && res < 0; c++)
             if (cell_contains(ecm, c, p)) res = c;
     }

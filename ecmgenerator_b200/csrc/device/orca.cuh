@@ -51,7 +51,7 @@ __device__ __forceinline__ int find_obstacles(const ObstView& ob, const BinView&
             if (obstacle_in_range(ob, o, a, range2)) { if (n < cap) out[n] = o; n++; }
         }
     }
-    if (valid && b < 0) {  // outside the static grid: exhaustive scan (exactness over speed)
+    if (valid && b < 0 && !bins.closed) {  // outside a static grid that is not known to hold every obstacle's reach: exhaustive scan
         for (int o = 0; o < ob.n; o++)
             if (obstacle_in_range(ob, o, a, range2)) { if (n < cap) out[n] = o; n++; }
     }
@@ -235,8 +235,13 @@ __device__ __forceinline__ int randomized_lp(const Cons* cs, int n, v2 opt, floa
         const float dpd = vdot(dir, cp(h));
         const float disc = dpd * dpd + maxSpeed * maxSpeed - vdot(cp(h), cp(h));
         bool bad = disc <= 0.0f;  // `return i` (ORCA.cpp:499-503)
+        // `if (disc <= 0) return i; else if (disc > 0) {...}` (ORCA.cpp:499-507) does NEITHER for a NaN discriminant: the
+        // constraint is passed over.  It happens: an agent exactly level with an obstacle vertex it touches has sp == 1.0,
+        // no collision case applies and the leg is sqrt(distSq - r*r) of a negative number (ORCA.cpp:171-183): a NaN
+        // obstacle constraint the reference's LP then ignores (tests/golden/nan_case.npz, found at tick 832 of the 1 M run)
+        const bool skip = !bad && !(disc > 0.0f);
         float left = 0.0f, right = 0.0f;
-        const bool clip = hit && !bad;
+        const bool clip = hit && !bad && !skip;
         if (clip) {
             const float dsq = osqrt(disc);
             left = -dpd - dsq;
@@ -263,6 +268,9 @@ __device__ __forceinline__ int randomized_lp(const Cons* cs, int n, v2 opt, floa
             if (bad) {
                 result = i;
                 live = false;
+            } else if (skip) {
+                i++;
+                live = i < n;
             } else {
                 if (useDirOpt) {
                     if (vdot(opt, dir) > 0.0f) outV = vadd(cp(h), vmul(dir, right));

@@ -165,18 +165,15 @@ __global__ void __launch_bounds__(kPackBlock) k_pack_walk(AgentArrays ag, StripV
 
 // k_bin_count / k_scatter over the list (tick.cuh has the all-slots versions).
 __global__ void __launch_bounds__(256) k_bin_count_walk(WalkView walk, const unsigned char* __restrict__ active, const float2* __restrict__ pos, GridParams gp,
-                                                        int* __restrict__ cell_count, int* __restrict__ key, int* __restrict__ rank) {
+                                                        int* __restrict__ cell_count, int* __restrict__ key, int* __restrict__ rank,
+                                                        unsigned* __restrict__ status, unsigned long long* __restrict__ counters) {
     const int n = *walk.n;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
         const int i = walk.list[idx];
         if (!active[i]) { key[i] = -1; continue; }
-        const float2 p = pos[i];
-        const float fx = (p.x - gp.x0) * gp.inv_cell, fy = (p.y - gp.y0) * gp.inv_cell;
-        const int cx = fx >= 0.0f ? (fx < (float)gp.w ? (int)fx : gp.w - 1) : 0;
-        const int cy = fy >= 0.0f ? (fy < (float)gp.h ? (int)fy : gp.h - 1) : 0;
-        const int k = cy * gp.w + cx;
+        const int k = grid_key(gp, pos[i], status, counters, i);
         key[i] = k;
-        rank[i] = atomicAdd(&cell_count[k], 1);
+        if (k >= 0) rank[i] = atomicAdd(&cell_count[k], 1);
     }
 }
 
@@ -199,7 +196,8 @@ __global__ void __launch_bounds__(256) k_scatter_walk(WalkView walk, const int* 
 
 // k_collect_owned (tick.cuh) over the list: the records of ecmgpu_update_io_owned.
 __global__ void __launch_bounds__(kCollectBlock) k_collect_owned_walk(WalkView walk, const unsigned char* __restrict__ active, const float2* __restrict__ pos,
-                                                                      const float2* __restrict__ vel, AgentRec* __restrict__ out, int* __restrict__ count) {
+                                                                      const float2* __restrict__ vel, AgentRec* __restrict__ out, int* __restrict__ count,
+                                                                      const int* __restrict__ ext_of) {
     __shared__ int s_warp[33];
     const int n = *walk.n;
     const int stride = gridDim.x * blockDim.x;
@@ -212,7 +210,7 @@ __global__ void __launch_bounds__(kCollectBlock) k_collect_owned_walk(WalkView w
         if (mine) {
             const float2 p = pos[i], v = vel[i];
             AgentRec r;
-            r.slot = i; r.x = p.x; r.y = p.y; r.vx = v.x; r.vy = v.y;
+            r.slot = ext_of ? ext_of[i] : i; r.x = p.x; r.y = p.y; r.vx = v.x; r.vy = v.y;
             out[e] = r;
         }
     }

@@ -34,7 +34,8 @@ enum Counter {
     C_TOTAL_HALO_MISS = 9,
     C_TOTAL_KD_TIES = 10,  // kdtree.cuh: tree segments (> 16 elements) whose median tied on the split axis
     C_TOTAL_KD_SMALL_TIES = 11,  // the same in segments of up to 16 elements (resolved like libstdc++)
-    C_TOTAL_EV_OVERFLOW = 12,    // events dropped because a queue was full (the host did not poll for max_agents events)
+    C_TOTAL_EV_OVERFLOW = 12,
+    C_TOTAL_NONFINITE = 13,      // agent-ticks skipped because the agent's position is not finite (see grid_key)    // events dropped because a queue was full (the host did not poll for max_agents events)
     C_COUNT = 16
 };
 
@@ -85,19 +86,35 @@ struct GridParams {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Cell key of an agent, -1 if it takes no part in the tick.  The reference's own arithmetic can produce a NaN velocity
+// (a jammed agent whose LP3D projects two constraints with identical normals, (N_j - N_i).Normalized() = 0: reproduced
+// bit for bit by the C oracle, profiles/r02_nan_case.md); from then on the reference is in undefined behaviour (a 0-point
+// path is indexed at -1, Simulator.cpp:554).  Here such an agent stays active and keeps its non-finite state, but is
+// left out of the neighbour grid - it can be nobody's neighbour anyway, sqDist > EPSILON is false for NaN
+// (KDTree.cpp:112) - and is not updated again: otherwise ONE such agent costs every tick the exhaustive scans meant for
+// points outside the static grid (measured: tick 0.54 -> 11.7 ms at 1 M agents).
+__device__ __forceinline__ int grid_key(const GridParams& gp, float2 p, unsigned* __restrict__ status, unsigned long long* __restrict__ counters, int i) {
+    const float fx = (p.x - gp.x0) * gp.inv_cell, fy = (p.y - gp.y0) * gp.inv_cell;
+    if (!(fabsf(fx) < CUDART_INF_F) || !(fabsf(fy) < CUDART_INF_F)) {  // NaN or infinite
+        status[i] = 256u;  // ECMGPU_ST_NONFINITE
+        atomicAdd(&counters[C_TOTAL_NONFINITE], 1ull);
+        return -1;
+    }
+    const int cx = fx >= 0.0f ? (fx < (float)gp.w ? (int)fx : gp.w - 1) : 0;
+    const int cy = fy >= 0.0f ? (fy < (float)gp.h ? (int)fy : gp.h - 1) : 0;
+    return cy * gp.w + cx;
+}
+
 __global__ void __launch_bounds__(256) k_bin_count(int n_slots, const unsigned char* __restrict__ active,
                                                    const float2* __restrict__ pos, GridParams gp, int* __restrict__ cell_count,
-                                                   int* __restrict__ key, int* __restrict__ rank) {
+                                                   int* __restrict__ key, int* __restrict__ rank, unsigned* __restrict__ status,
+                                                   unsigned long long* __restrict__ counters) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_slots) return;
     if (!active[i]) { key[i] = -1; return; }
-    float2 p = pos[i];
-    float fx = (p.x - gp.x0) * gp.inv_cell, fy = (p.y - gp.y0) * gp.inv_cell;
-    int cx = fx >= 0.0f ? (fx < (float)gp.w ? (int)fx : gp.w - 1) : 0;
-    int cy = fy >= 0.0f ? (fy < (float)gp.h ? (int)fy : gp.h - 1) : 0;
-    int k = cy * gp.w + cx;
+    const int k = grid_key(gp, pos[i], status, counters, i);
     key[i] = k;
-    rank[i] = atomicAdd(&cell_count[k], 1);
+    if (k >= 0) rank[i] = atomicAdd(&cell_count[k], 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -322,7 +339,7 @@ __device__ __forceinline__ unsigned finish_agent(const TickView& t, int p, const
     if (!(r.status & kLp3dDeferred)) integrate_agent(t, slot, pos, vel, r.velocity);
     if (t.record_neighbors) {
 #pragma unroll
-        for (int j = 0; j < kK; j++) t.ag.nbr[kK * slot + j] = k.q[j] >= 0 ? t.sc.s_slot[k.q[j]] : -1;
+        for (int j = 0; j < kK; j++) t.ag.nbr[kK * slot + j] = k.q[j] >= 0 ? t.grid.slot_of_row(k.q[j]) : -1;
         t.ag.nbr_cnt[slot] = n_nb;
     }
     return (r.status & ~kLp3dDeferred) | extra;
@@ -418,7 +435,7 @@ __global__ void __launch_bounds__(128) k_fallback(TickView t, int mode) {
                 if (st) t.ag.status[t.sc.s_slot[p]] |= st;
             } else {
                 const int slot = t.sc.s_slot[p];
-                for (int j = 0; j < kK; j++) t.ag.nbr[kK * slot + j] = k.q[j] >= 0 ? t.sc.s_slot[k.q[j]] : -1;
+                for (int j = 0; j < kK; j++) t.ag.nbr[kK * slot + j] = k.q[j] >= 0 ? t.grid.slot_of_row(k.q[j]) : -1;
                 t.ag.nbr_cnt[slot] = k.count();
             }
         }
@@ -454,7 +471,7 @@ __global__ void __launch_bounds__(128) k_knn_query(TickView t) {
     if (knn_grid(k, t.sc.s_pos[p], t.grid, t.max_ring)) {
         const int slot = t.sc.s_slot[p];
 #pragma unroll
-        for (int j = 0; j < kK; j++) t.ag.nbr[kK * slot + j] = k.q[j] >= 0 ? t.sc.s_slot[k.q[j]] : -1;
+        for (int j = 0; j < kK; j++) t.ag.nbr[kK * slot + j] = k.q[j] >= 0 ? t.grid.slot_of_row(k.q[j]) : -1;
         t.ag.nbr_cnt[slot] = k.count();
     } else {
         int e = (int)atomicAdd(&t.sc.counters[C_FALLBACK_N], 1ull);
@@ -524,6 +541,19 @@ __device__ __forceinline__ int cta_reserve(bool want, int* counter, int* s_warp 
     return idx;
 }
 
+// ---- transfers by slot id while the arrays are indexed internally (spatial renumbering, ecmgpu.cu) ----
+struct Int5 { int v[5]; };  // one ECMGPU_NEIGHBORS element
+template <class T>
+__global__ void __launch_bounds__(256) k_gather_slots(int count, int first, const int* __restrict__ int_of, const T* __restrict__ src, T* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = src[int_of[first + i]];
+}
+template <class T>
+__global__ void __launch_bounds__(256) k_scatter_slots(int count, int first, const int* __restrict__ int_of, const T* __restrict__ src, T* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[int_of[first + i]] = src[i];
+}
+
 // ---- host I/O as records of owned agents (ecmgpu_update_io_owned) --------------------------------
 struct AgentRec {  // == ecmgpu_agent_rec (include/ecm_b200.h)
     int slot;
@@ -532,19 +562,22 @@ struct AgentRec {  // == ecmgpu_agent_rec (include/ecm_b200.h)
 
 // Host-provided state: position and velocity of the listed slots, where this handle owns them.
 __global__ void __launch_bounds__(256) k_apply_records(int n, const AgentRec* __restrict__ rec, int max_slots, const unsigned char* __restrict__ active,
-                                                       float2* __restrict__ pos, float2* __restrict__ vel) {
+                                                       float2* __restrict__ pos, float2* __restrict__ vel, const int* __restrict__ int_of) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const AgentRec r = rec[i];
-    if (r.slot < 0 || r.slot >= max_slots || !active[r.slot]) return;
-    pos[r.slot] = make_float2(r.x, r.y);
-    vel[r.slot] = make_float2(r.vx, r.vy);
+    if (r.slot < 0 || r.slot >= max_slots) return;
+    const int a = int_of ? int_of[r.slot] : r.slot;  // records name agents by slot id; arrays are indexed internally
+    if (!active[a]) return;
+    pos[a] = make_float2(r.x, r.y);
+    vel[a] = make_float2(r.vx, r.vy);
 }
 
 // Compacts the owned agents into records (one atomic per CTA; ascending slots within a CTA).
 constexpr int kCollectBlock = 1024;
 __global__ void __launch_bounds__(kCollectBlock) k_collect_owned(int n_slots, const unsigned char* __restrict__ active, const float2* __restrict__ pos,
-                                                                 const float2* __restrict__ vel, AgentRec* __restrict__ out, int* __restrict__ count) {
+                                                                 const float2* __restrict__ vel, AgentRec* __restrict__ out, int* __restrict__ count,
+                                                                 const int* __restrict__ ext_of) {
     __shared__ int s_warp[33];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool mine = i < n_slots && active[i];
@@ -552,7 +585,7 @@ __global__ void __launch_bounds__(kCollectBlock) k_collect_owned(int n_slots, co
     if (!mine) return;
     const float2 p = pos[i], v = vel[i];
     AgentRec r;
-    r.slot = i; r.x = p.x; r.y = p.y; r.vx = v.x; r.vy = v.y;
+    r.slot = ext_of ? ext_of[i] : i; r.x = p.x; r.y = p.y; r.vx = v.x; r.vy = v.y;
     out[e] = r;
 }
 

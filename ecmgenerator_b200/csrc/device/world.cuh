@@ -41,13 +41,19 @@ struct BinView {
     const int* obst_start;   // [w*h+1]
     const int* obst_items;
     // The reference's even-odd test (UtilityFunctions.cpp:54-86) uses strict y comparisons, so a ray that passes exactly
-    // through a polygon vertex which is not a y-extremum of the polygon is counted once instead of twice: a point LEVEL
-    // with such a vertex is reported inside a cell that can lie arbitrarily far to its right (no such vertex exists in
-    // an axis-aligned lattice; every oblique world has them - golden scene oblique_small).  The bbox argument behind the
-    // per-bin lists does not hold for those points.  They are recognised exactly - level_y is the sorted set of the y
-    // of every cell-polygon vertex, level_bits a hash bitmap in front of it - and answered from row_items: per bin ROW
+    // through a polygon vertex where the boundary crosses from below to above (a "pass-through" vertex, not a y-extremum)
+    // counts that crossing zero times: a point LEVEL with such a vertex and to its left gets the wrong parity and can be
+    // reported inside a cell arbitrarily far to its right (golden scene oblique_small).  The bbox argument behind the
+    // per-bin lists does not hold for those points.  They are recognised exactly - level_y is the sorted set of the
+    // pass-through vertex heights (host/flat_world.h pass_through_levels; empty for axis-aligned lattices, whose paths
+    // DO run along vertex levels), level_bits a hash bitmap in front of it - and answered from row_items: per bin ROW
     // the ascending list of the cells whose y-extent reaches into the row (a cell containing p under the reference's
     // predicate has an edge with min y < p.y < max y, so it is in the list of p's row).
+    // 1: every ECM cell lies inside the grid and every obstacle vertex at least max_range inside it (checked on the host
+    // when the lists are built): a point OUTSIDE the grid is then in no cell and has no obstacle in range, and the
+    // exhaustive scans that would answer it exactly are skipped (an agent pushed out of the world would otherwise cost
+    // one thread a scan of every cell and every segment, every tick)
+    int closed;
     const float* level_y;
     const unsigned* level_bits;
     int n_levels, level_shift;
@@ -91,7 +97,14 @@ struct GridView {
     const float2* s_pos;      // [n_sorted] pre-tick position
     const float2* s_vel;      // [n_sorted] pre-tick velocity
     const float* s_rad;       // [n_sorted] radius
-    const int* s_slot;        // [n_sorted] slot id (global agent id)
+    const int* s_slot;        // [n_sorted] internal agent index (what the per-agent arrays are indexed by)
+    // The library renumbers agents in spatial order when they are loaded (ecmgpu.cu "spatial renumbering"): ext_of maps an
+    // internal index to the caller's slot id, nullptr = identity.  The reference's tie-break is by SLOT id.
+    const int* ext_of;
+    __device__ __forceinline__ int slot_of_row(int row) const {
+        const int i = __ldg(&s_slot[row]);
+        return ext_of ? __ldg(&ext_of[i]) : i;
+    }
     __device__ __forceinline__ void cell_of(v2 p, int& cx, int& cy) const {
         float fx = (p.x - x0) * inv_cell, fy = (p.y - y0) * inv_cell;
         // clamp (NaN -> 0): agents outside the grid live in the border cells

@@ -19,6 +19,7 @@
 
 #include <dlfcn.h>
 
+#include "host/flat_world.h"
 #include "device/strips.cuh"
 #include "device/kdtree.cuh"
 #include "device/planner.cuh"
@@ -80,6 +81,7 @@ struct ecmgpu_sim {
     DevBuf<float> d_level_y;
     DevBuf<unsigned> d_level_bits;
     int n_levels = 0, level_shift = 31;
+    bool bins_closed = false;
     int n_vertices = 0, n_edges = 0, n_obst = 0;
 
     // ---- agents, device (per slot)
@@ -97,6 +99,18 @@ struct ecmgpu_sim {
     std::vector<float4> h_path_bbox;  // [h_path_pool.size()/8 rounded up]
     size_t pool_uploaded = 0;  // prefix of h_path_pool already resident on the device
     int n_slots = 0;
+
+    // ---- spatial renumbering.  Every per-agent device array is indexed by an INTERNAL index; the caller's slot id maps
+    // to it through int_of / ext_of.  ecmgpu_bulk_load hands the internal indices of the slots it loads out in spatial
+    // order (row-major 4 m cells), so agents that are close in the world are close in memory: the snapshot scatter, the
+    // path-header gathers and the per-agent result stores of a warp then touch a few sectors instead of 32 (round 1
+    // measured 3.2x DRAM write amplification in k_orca and 75 MB of pure overhead in k_scatter with slots in load
+    // order).  Identity until the first large load; the KD-tree mode (which walks slots in ascending order) restores it.
+    bool coherent = true;  // env ECMGPU_COHERENT=0 disables
+    bool perm_identity = true;
+    std::vector<int> h_int_of, h_ext_of;
+    DevBuf<int> d_int_of, d_ext_of;
+    DevBuf<unsigned char> d_xfer;  // staging of ecmgpu_read / ecmgpu_write while the mapping is not the identity
 
     // ---- neighbour grid + snapshot
     float cell = 0.0f;
@@ -270,10 +284,15 @@ int build_bins(ecmgpu_sim* s) {
     // keep the bin count bounded
     while ((W / bin + 3) * (H / bin + 3) > 16.0e6) bin *= 1.5;
     s->static_bin = (float)bin;
-    s->bins_x0 = (float)(s->bbox[0] - bin);
-    s->bins_y0 = (float)(s->bbox[1] - bin);
-    s->bins_w = (int)std::ceil((W + 2 * bin) / bin) + 1;
-    s->bins_h = (int)std::ceil((H + 2 * bin) / bin) + 1;
+    // margin around the walkable area: at least one bin, and at least the obstacle range, so that a point outside the grid
+    // is out of reach of every obstacle inside the area (BinView::closed)
+    const double range0 = std::max(s->prm.max_obstacle_range > 0 ? (double)s->prm.max_obstacle_range : 0.0, (double)s->tracked_range);
+    const double margin = std::ceil(std::max(bin, range0 * 1.0001 + 1e-3 * bin + 2e-3) / bin) * bin;
+    s->bins_x0 = (float)(s->bbox[0] - margin);
+    s->bins_y0 = (float)(s->bbox[1] - margin);
+    s->bins_w = (int)std::ceil((W + 2 * margin) / bin) + 1;
+    s->bins_h = (int)std::ceil((H + 2 * margin) / bin) + 1;
+    bool closed = true;  // cleared below by a cell that leaves the grid or an obstacle vertex outside the area
     const int nb = s->bins_w * s->bins_h;
     const double x0 = s->bins_x0, y0 = s->bins_y0;
     // The device computes the bin as (int)((p - x0) * inv_bin) in float; pad every footprint by
@@ -282,6 +301,7 @@ int build_bins(ecmgpu_sim* s) {
     auto bin_range = [&](double lo, double hi, double origin, int n, int& a, int& b) {
         a = (int)std::floor((lo - slack - origin) / bin);
         b = (int)std::floor((hi + slack - origin) / bin);
+        if (a < 0 || b > n - 1 || !(lo == lo) || !(hi == hi)) closed = false;
         a = std::max(a, 0);
         b = std::min(b, n - 1);
     };
@@ -316,20 +336,19 @@ int build_bins(ecmgpu_sim* s) {
         s->max_cell_list = 0;
         for (int i = 0; i < nb; i++) s->max_cell_list = std::max(s->max_cell_list, cstart[i + 1] - cstart[i]);
     }
-    // -- points exactly level with a cell vertex (BinView::level_hit): the sorted y set, its hash bitmap, per-row cell lists
+    // -- points exactly level with a pass-through cell vertex (BinView::level_hit, host/flat_world.h): the sorted y set, its
+    //    hash bitmap, per-row cell lists
     std::vector<float> levels;
     std::vector<unsigned> level_bits;
     std::vector<int> rstart(s->bins_h + 1, 0), ritems;
     {
         const int nc = 2 * s->n_edges;
-        levels.reserve(6 * (size_t)s->n_edges);
-        for (int e = 0; e < s->n_edges; e++) {
-            for (int k = 0; k < 4; k++) levels.push_back(s->h_edge_cl[8 * e + 2 * k + 1]);
-            levels.push_back(s->h_vert_xy[2 * s->h_edge_v[2 * e] + 1]);
-            levels.push_back(s->h_vert_xy[2 * s->h_edge_v[2 * e + 1] + 1]);
+        for (int c = 0; c < nc; c++) {  // polygon of cell c: v0, boundary.p0, boundary.p1, v1 (ECMCellCollection.cpp:62-80)
+            const int e = c >> 1, side = c & 1;
+            const float* cl = &s->h_edge_cl[8 * e];
+            const float ys[4] = {s->h_vert_xy[2 * s->h_edge_v[2 * e] + 1], cl[2 * side + 1], cl[4 + 2 * side + 1], s->h_vert_xy[2 * s->h_edge_v[2 * e + 1] + 1]};
+            ecmb200::pass_through_levels(ys, levels);
         }
-        for (float& v : levels) if (v == 0.0f) v = 0.0f;  // -0 -> +0
-        levels.erase(std::remove_if(levels.begin(), levels.end(), [](float v) { return !(v == v); }), levels.end());
         std::sort(levels.begin(), levels.end());
         levels.erase(std::unique(levels.begin(), levels.end()), levels.end());
         int lg = 12;
@@ -370,7 +389,7 @@ int build_bins(ecmgpu_sim* s) {
             const int nx = s->h_obst_next[o];
             const double bx_ = s->h_obst_xy[2 * nx], by_ = s->h_obst_xy[2 * nx + 1];
             int xa, xb, ya, yb;
-            bin_range(std::min(ax_, bx_) - R, std::max(ax_, bx_) + R, x0, s->bins_w, xa, xb);
+            bin_range(std::min(ax_, bx_) - R, std::max(ax_, bx_) + R, x0, s->bins_w, xa, xb);  // leaves the grid => not closed
             bin_range(std::min(ay_, by_) - R, std::max(ay_, by_) + R, y0, s->bins_h, ya, yb);
             for (int y = ya; y <= yb; y++)
                 for (int x = xa; x <= xb; x++) {
@@ -407,6 +426,7 @@ int build_bins(ecmgpu_sim* s) {
     CUDA_TRY(s, cudaMemcpyAsync(s->d_row_items.p, ritems.data(), sizeof(int) * ritems.size(), cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(s, cudaStreamSynchronize(s->stream));  // the host vectors die here
     s->built_range = (float)range;
+    s->bins_closed = closed;
     s->bins_dirty = false;
     s->config_epoch++;
     return ECMGPU_OK;
@@ -484,6 +504,7 @@ TickView make_view(ecmgpu_sim* s) {
     t.bins.cell_items = s->d_bin_cell_items.p;
     t.bins.obst_start = s->d_bin_obst_start.p;
     t.bins.obst_items = s->d_bin_obst_items.p;
+    t.bins.closed = s->bins_closed ? 1 : 0;
     t.bins.level_y = s->d_level_y.p;
     t.bins.level_bits = s->d_level_bits.p;
     t.bins.n_levels = s->n_levels;
@@ -502,6 +523,7 @@ TickView make_view(ecmgpu_sim* s) {
     t.grid.s_vel = s->d_s_vel.p;
     t.grid.s_rad = s->d_s_rad.p;
     t.grid.s_slot = s->d_s_slot.p;
+    t.grid.ext_of = s->perm_identity ? nullptr : s->d_ext_of.p;
     t.ag.pos = s->d_pos.p;
     t.ag.vel = s->d_vel.p;
     t.ag.prefvel = s->d_prefvel.p;
@@ -747,8 +769,8 @@ int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
     CUDA_TRY(s, cudaMemsetAsync(s->d_counters.p + C_FALLBACK_N, 0, 2 * sizeof(unsigned long long), s->stream));
     const int nb = div_up(s->n_slots, 256);
     StripView sv = make_strip_view(s);
-    if (sv.walk.list) k_bin_count_walk<<<kSMs * 8, 256, 0, s->stream>>>(sv.walk, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p);
-    else k_bin_count<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p);
+    if (sv.walk.list) k_bin_count_walk<<<kSMs * 8, 256, 0, s->stream>>>(sv.walk, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p, s->d_status.p, s->d_counters.p);
+    else k_bin_count<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p, s->d_status.p, s->d_counters.p);
     const int ng = 2 * s->cap_halo + s->cap_self;
     if (s->strips_on) {
         k_ghost_count<<<div_up(ng, 256), 256, 0, s->stream>>>(sv, gp, s->d_cell_count.p);
@@ -1076,6 +1098,7 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
     TRY_ALLOC(s->d_lp3d_cs.alloc((size_t)s->lp3d_cap * kMaxCons));
     TRY_ALLOC(s->d_ev_replan.alloc(n)); TRY_ALLOC(s->d_ev_destroyed.alloc(n));
     TRY_ALLOC(s->d_counters.alloc(C_COUNT));
+    TRY_ALLOC(s->d_int_of.alloc(n)); TRY_ALLOC(s->d_ext_of.alloc(n));
     TRY_ALLOC(cudaMemsetAsync(s->d_pos.p, 0, 8 * n, s->stream)); TRY_ALLOC(cudaMemsetAsync(s->d_vel.p, 0, 8 * n, s->stream));
     TRY_ALLOC(cudaMemsetAsync(s->d_prefvel.p, 0, 8 * n, s->stream)); TRY_ALLOC(cudaMemsetAsync(s->d_attraction.p, 0, 8 * n, s->stream));
     TRY_ALLOC(cudaMemsetAsync(s->d_force.p, 0, 8 * n, s->stream));
@@ -1090,6 +1113,10 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
     TRY_ALLOC(cudaStreamSynchronize(s->stream));
 #undef TRY_ALLOC
     s->h_path_hdr.assign(n, PathHdr{0, 0, 0.0f, 0.0f});
+    s->h_int_of.resize(n);
+    s->h_ext_of.resize(n);
+    for (size_t i = 0; i < n; i++) s->h_int_of[i] = s->h_ext_of[i] = (int)i;
+    if (const char* e = getenv("ECMGPU_COHERENT")) s->coherent = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_GRAPH")) s->use_graph = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_COMPACT")) s->compact = atoi(e) != 0;
     s->h_path_pool.reserve(std::min<size_t>(pool, 1 << 20));
@@ -1113,6 +1140,7 @@ void ecmgpu_destroy(ecmgpu_sim* s) {
     s->d_fb_list.free(); s->d_ev_replan.free(); s->d_ev_destroyed.free(); s->d_s_pos.free(); s->d_s_vel.free();
     s->d_s_pref.free(); s->d_s_rad.free(); s->d_s_spd.free(); s->d_s_alive.free(); s->d_counters.free();
     s->d_walk.free(); s->d_walk_n.free(); s->d_in_walk.free();
+    s->d_int_of.free(); s->d_ext_of.free(); s->d_xfer.free();
     kd_free(s);
     plan_free(s);
     s->d_vert_clear.free(); s->d_vert_he.free(); s->d_he_next.free();
@@ -1218,56 +1246,101 @@ int ecmgpu_bulk_load(ecmgpu_sim* s, int n, const int* slots, const float* pos_xy
         if (path_off[i + 1] - path_off[i] < 1) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_bulk_load: empty path");
         hi = std::max(hi, slot + 1);
     }
+    if (n == 0) return ECMGPU_OK;
     s->n_slots = hi;
     s->io.owned_confirmed = -1;
     s->walk_dirty = true;
-    // host staging in slot order when contiguous, otherwise per-element copies
-    const bool contiguous = [&] {
-        if (!slots) return true;
-        for (int i = 0; i < n; i++) if (slots[i] != slots[0] + i) return false;
-        return true;
-    }();
-    const int first = slots ? (n > 0 ? slots[0] : 0) : 0;
-    for (int i = 0; i < n; i++) {
-        int slot = slots ? slots[i] : i;
-        int rc = upload_path(s, slot, path_xy + 2 * (size_t)path_off[i], path_off[i + 1] - path_off[i]);
+    // ---- spatial renumbering: the internal indices the loaded slots hold are handed out again in spatial order.  The
+    // key uses nothing but the loaded positions, so every rank of a strips run (each loads the same crowd) derives the
+    // same mapping: the halo / migrant messages can name agents by internal index.
+    std::vector<int> order(n);  // order[r] = input position of the r-th agent in internal order
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::vector<int> ids(n);    // ids[r] = internal index of that agent (ascending)
+    for (int i = 0; i < n; i++) ids[i] = s->h_int_of[slots ? slots[i] : i];
+    {
+        std::vector<int> chk(ids);
+        std::sort(chk.begin(), chk.end());
+        if (std::adjacent_find(chk.begin(), chk.end()) != chk.end()) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_bulk_load: a slot is listed twice");
+    }
+    const bool remap = s->coherent && n >= 64 && s->neighbor_mode == ECMGPU_NEIGHBORS_EXACT;
+    if (remap) {
+        double x0 = pos_xy[0], y0 = pos_xy[1], x1 = x0;
+        for (int i = 1; i < n; i++) {
+            x0 = std::min<double>(x0, pos_xy[2 * i]); x1 = std::max<double>(x1, pos_xy[2 * i]);
+            y0 = std::min<double>(y0, pos_xy[2 * i + 1]);
+        }
+        const double cell = 4.0;
+        const long long gw = (long long)std::floor((x1 - x0) / cell) + 1;
+        std::vector<long long> key(n);
+        for (int i = 0; i < n; i++) {
+            const double fx = (pos_xy[2 * i] - x0) / cell, fy = (pos_xy[2 * i + 1] - y0) / cell;
+            key[i] = (fx == fx && fy == fy) ? (long long)std::floor(fy) * gw + (long long)std::floor(fx) : -1;
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+        std::sort(ids.begin(), ids.end());
+        for (int r = 0; r < n; r++) {
+            const int slot = slots ? slots[order[r]] : order[r];
+            s->h_int_of[slot] = ids[r];
+            s->h_ext_of[ids[r]] = slot;
+        }
+        bool ident = true;
+        for (int i = 0; i < s->n_slots && ident; i++) ident = s->h_int_of[i] == i;
+        s->perm_identity = ident;
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_int_of.p, s->h_int_of.data(), sizeof(int) * (size_t)s->prm.max_agents, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_ext_of.p, s->h_ext_of.data(), sizeof(int) * (size_t)s->prm.max_agents, cudaMemcpyHostToDevice, s->stream));
+        s->config_epoch++;  // the captured tick holds the ext_of pointer (or its absence)
+    }
+    // ---- paths (host mirror indexed internally) and the obstacle range
+    for (int r = 0; r < n; r++) {
+        const int i = order[r];
+        int rc = upload_path(s, ids[r], path_xy + 2 * (size_t)path_off[i], path_off[i + 1] - path_off[i]);
         if (rc) return rc;
         s->tracked_range = std::max(s->tracked_range, kLookAhead * speed[i] + radius[i]);
     }
+    // ---- components: staged in internal order when the indices are one run, otherwise element by element
+    bool contiguous = true;
+    for (int r = 1; r < n && contiguous; r++) contiguous = ids[r] == ids[0] + r;
+    const int first = ids[0];
     std::vector<unsigned char> ones(n, 1);
-    if (contiguous && n > 0) {
-        CUDA_TRY(s, cudaMemcpyAsync(s->d_pos.p + first, pos_xy, sizeof(float2) * n, cudaMemcpyHostToDevice, s->stream));
-        CUDA_TRY(s, cudaMemcpyAsync(s->d_radius.p + first, radius, sizeof(float) * n, cudaMemcpyHostToDevice, s->stream));
-        CUDA_TRY(s, cudaMemcpyAsync(s->d_speed.p + first, speed, sizeof(float) * n, cudaMemcpyHostToDevice, s->stream));
+    if (contiguous) {
+        std::vector<float2> hp(n);
+        std::vector<float> hr(n), hs(n);
+        for (int r = 0; r < n; r++) {
+            const int i = order[r];
+            hp[r] = make_float2(pos_xy[2 * i], pos_xy[2 * i + 1]);
+            hr[r] = radius[i];
+            hs[r] = speed[i];
+        }
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_pos.p + first, hp.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_radius.p + first, hr.data(), sizeof(float) * n, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_speed.p + first, hs.data(), sizeof(float) * n, cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(s, cudaMemcpyAsync(s->d_active.p + first, ones.data(), n, cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(s, cudaMemsetAsync(s->d_vel.p + first, 0, sizeof(float2) * n, s->stream));
         CUDA_TRY(s, cudaMemsetAsync(s->d_prefvel.p + first, 0, sizeof(float2) * n, s->stream));
         CUDA_TRY(s, cudaMemsetAsync(s->d_force.p + first, 0, sizeof(float2) * n, s->stream));
         CUDA_TRY(s, cudaMemsetAsync(s->d_attraction.p + first, 0, sizeof(float2) * n, s->stream));
         CUDA_TRY(s, cudaMemsetAsync(s->d_replan_pending.p + first, 0, n, s->stream));
-    } else {
-        for (int i = 0; i < n; i++) {
-            int slot = slots[i];
-            CUDA_TRY(s, cudaMemcpyAsync(s->d_pos.p + slot, pos_xy + 2 * i, sizeof(float2), cudaMemcpyHostToDevice, s->stream));
-            CUDA_TRY(s, cudaMemcpyAsync(s->d_radius.p + slot, radius + i, sizeof(float), cudaMemcpyHostToDevice, s->stream));
-            CUDA_TRY(s, cudaMemcpyAsync(s->d_speed.p + slot, speed + i, sizeof(float), cudaMemcpyHostToDevice, s->stream));
-            CUDA_TRY(s, cudaMemcpyAsync(s->d_active.p + slot, ones.data(), 1, cudaMemcpyHostToDevice, s->stream));
-            CUDA_TRY(s, cudaMemsetAsync(s->d_vel.p + slot, 0, sizeof(float2), s->stream));
-            CUDA_TRY(s, cudaMemsetAsync(s->d_prefvel.p + slot, 0, sizeof(float2), s->stream));
-            CUDA_TRY(s, cudaMemsetAsync(s->d_force.p + slot, 0, sizeof(float2), s->stream));
-            CUDA_TRY(s, cudaMemsetAsync(s->d_attraction.p + slot, 0, sizeof(float2), s->stream));
-            CUDA_TRY(s, cudaMemsetAsync(s->d_replan_pending.p + slot, 0, 1, s->stream));
-        }
-    }
-    // path pool tail + touched headers
-    { int rc = flush_pool(s); if (rc) return rc; }
-    if (contiguous && n > 0) {
+        { int rc = flush_pool(s); if (rc) return rc; }
         CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p + first, s->h_path_hdr.data() + first, sizeof(PathHdr) * n, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));  // the staging vectors die here
     } else {
-        for (int i = 0; i < n; i++)
-            CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p + slots[i], &s->h_path_hdr[slots[i]], sizeof(PathHdr), cudaMemcpyHostToDevice, s->stream));
+        for (int r = 0; r < n; r++) {
+            const int i = order[r], a = ids[r];
+            CUDA_TRY(s, cudaMemcpyAsync(s->d_pos.p + a, pos_xy + 2 * i, sizeof(float2), cudaMemcpyHostToDevice, s->stream));
+            CUDA_TRY(s, cudaMemcpyAsync(s->d_radius.p + a, radius + i, sizeof(float), cudaMemcpyHostToDevice, s->stream));
+            CUDA_TRY(s, cudaMemcpyAsync(s->d_speed.p + a, speed + i, sizeof(float), cudaMemcpyHostToDevice, s->stream));
+            CUDA_TRY(s, cudaMemcpyAsync(s->d_active.p + a, ones.data(), 1, cudaMemcpyHostToDevice, s->stream));
+            CUDA_TRY(s, cudaMemsetAsync(s->d_vel.p + a, 0, sizeof(float2), s->stream));
+            CUDA_TRY(s, cudaMemsetAsync(s->d_prefvel.p + a, 0, sizeof(float2), s->stream));
+            CUDA_TRY(s, cudaMemsetAsync(s->d_force.p + a, 0, sizeof(float2), s->stream));
+            CUDA_TRY(s, cudaMemsetAsync(s->d_attraction.p + a, 0, sizeof(float2), s->stream));
+            CUDA_TRY(s, cudaMemsetAsync(s->d_replan_pending.p + a, 0, 1, s->stream));
+        }
+        { int rc = flush_pool(s); if (rc) return rc; }
+        for (int r = 0; r < n; r++)
+            CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p + ids[r], &s->h_path_hdr[ids[r]], sizeof(PathHdr), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     }
-    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     return ECMGPU_OK;
 }
 
@@ -1281,12 +1354,13 @@ int ecmgpu_set_path(ecmgpu_sim* s, int slot, const float* path_xy, int n_points)
     if (!s) return ECMGPU_ERR_INVALID;
     if (slot < 0 || slot >= s->n_slots || !path_xy) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_path: bad arguments");
     CUDA_TRY(s, cudaSetDevice(s->prm.device));
-    int rc = upload_path(s, slot, path_xy, n_points);
+    const int a = s->h_int_of[slot];
+    int rc = upload_path(s, a, path_xy, n_points);
     if (rc) return rc;
     const unsigned char zero = 0;
     { int rc2 = flush_pool(s); if (rc2) return rc2; }
-    CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p + slot, &s->h_path_hdr[slot], sizeof(PathHdr), cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(s, cudaMemcpyAsync(s->d_replan_pending.p + slot, &zero, 1, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_path_hdr.p + a, &s->h_path_hdr[a], sizeof(PathHdr), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_replan_pending.p + a, &zero, 1, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     return ECMGPU_OK;
 }
@@ -1295,7 +1369,7 @@ int ecmgpu_destroy_agent(ecmgpu_sim* s, int slot) {
     if (!s) return ECMGPU_ERR_INVALID;
     if (slot < 0 || slot >= s->prm.max_agents) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_destroy_agent: bad slot");
     CUDA_TRY(s, cudaSetDevice(s->prm.device));
-    CUDA_TRY(s, cudaMemsetAsync(s->d_active.p + slot, 0, 1, s->stream));
+    CUDA_TRY(s, cudaMemsetAsync(s->d_active.p + s->h_int_of[slot], 0, 1, s->stream));
     return ECMGPU_OK;
 }
 
@@ -1424,6 +1498,11 @@ int ecmgpu_poll_events(ecmgpu_sim* s, int* replan_slots, int replan_cap, int* n_
         if (destroyed_slots) CUDA_TRY(s, cudaMemsetAsync(s->d_counters.p + C_DESTROYED_N, 0, sizeof(unsigned long long), s->stream));
     }
     CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    // the kernels name agents by internal index
+    if (!s->perm_identity) {
+        if (replan_slots) for (int k = 0; k < nr; k++) replan_slots[k] = s->h_ext_of[replan_slots[k]];
+        if (destroyed_slots) for (int k = 0; k < nd; k++) destroyed_slots[k] = s->h_ext_of[destroyed_slots[k]];
+    }
     // event order is arrival order of the atomics; report ascending slots like the reference's loops
     if (replan_slots && nr > 1) std::sort(replan_slots, replan_slots + nr);
     if (destroyed_slots && nd > 1) std::sort(destroyed_slots, destroyed_slots + nd);
@@ -1433,24 +1512,58 @@ int ecmgpu_poll_events(ecmgpu_sim* s, int* replan_slots, int replan_cap, int* n_
     return ECMGPU_OK;
 }
 
+// dst[i] = src[int_of[first + i]] (gather) or the reverse (scatter) for one of the per-agent arrays; `es` = element size
+static void launch_remap(ecmgpu_sim* s, bool gather, size_t es, int count, int first, const void* src, void* dst) {
+    const int nb = div_up(count, 256);
+    const int* m = s->d_int_of.p;
+#define ECM_REMAP(T)                                                                                              \
+    do {                                                                                                          \
+        if (gather) k_gather_slots<T><<<nb, 256, 0, s->stream>>>(count, first, m, (const T*)src, (T*)dst);         \
+        else k_scatter_slots<T><<<nb, 256, 0, s->stream>>>(count, first, m, (const T*)src, (T*)dst);               \
+    } while (0)
+    if (es == 1) ECM_REMAP(unsigned char);
+    else if (es == 4) ECM_REMAP(unsigned);
+    else if (es == 8) ECM_REMAP(float2);
+    else ECM_REMAP(Int5);
+#undef ECM_REMAP
+    s->launches++;
+}
+
 static int xfer(ecmgpu_sim* s, int which, void* host, int first, int count, bool to_host, bool wait) {
     int rc = check_range(s, which, first, count);
     if (rc) return rc;
     if (!host) return fail(s, ECMGPU_ERR_INVALID, "null host buffer");
     CUDA_TRY(s, cudaSetDevice(s->prm.device));
     const size_t es = elem_size(which);
-    char* dev = (char*)dev_array(s, which) + es * (size_t)first;
-    if (to_host) CUDA_TRY(s, cudaMemcpyAsync(host, dev, es * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
-    else CUDA_TRY(s, cudaMemcpyAsync(dev, host, es * (size_t)count, cudaMemcpyHostToDevice, s->stream));
+    if (s->perm_identity || count == 0) {
+        char* dev = (char*)dev_array(s, which) + es * (size_t)first;
+        if (to_host) CUDA_TRY(s, cudaMemcpyAsync(host, dev, es * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
+        else CUDA_TRY(s, cudaMemcpyAsync(dev, host, es * (size_t)count, cudaMemcpyHostToDevice, s->stream));
+    } else {  // the arrays are indexed internally: stage the slot range through a gather / scatter kernel
+        const size_t bytes = es * (size_t)count;
+        if (s->d_xfer.n < bytes) {
+            CUDA_TRY(s, cudaStreamSynchronize(s->stream));  // an earlier asynchronous transfer may still use the old staging
+            CUDA_TRY(s, s->d_xfer.alloc(bytes + bytes / 2 + 1024));
+        }
+        if (to_host) {
+            launch_remap(s, true, es, count, first, dev_array(s, which), s->d_xfer.p);
+            CUDA_TRY(s, cudaMemcpyAsync(host, s->d_xfer.p, bytes, cudaMemcpyDeviceToHost, s->stream));
+        } else {
+            CUDA_TRY(s, cudaMemcpyAsync(s->d_xfer.p, host, bytes, cudaMemcpyHostToDevice, s->stream));
+            launch_remap(s, false, es, count, first, s->d_xfer.p, dev_array(s, which));
+        }
+        CUDA_TRY(s, cudaGetLastError());
+    }
     if (wait) CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     if (!to_host && (which == ECMGPU_RADIUS || which == ECMGPU_SPEED) && count > 0) {
         // The obstacle lists of the static bins reach max(10 * speed + radius) (ORCA.cpp:27): a larger speed or radius
-        // must widen them, or find_obstacles would silently miss segments.  Rare call: read the range back and re-track.
-        std::vector<float> spd(count), rad(count);
-        CUDA_TRY(s, cudaMemcpyAsync(spd.data(), s->d_speed.p + first, sizeof(float) * count, cudaMemcpyDeviceToHost, s->stream));
-        CUDA_TRY(s, cudaMemcpyAsync(rad.data(), s->d_radius.p + first, sizeof(float) * count, cudaMemcpyDeviceToHost, s->stream));
+        // must widen them, or find_obstacles would silently miss segments.  Rare call: read everything back and re-track.
+        const int m = std::max(s->n_slots, first + count);
+        std::vector<float> spd(m), rad(m);
+        CUDA_TRY(s, cudaMemcpyAsync(spd.data(), s->d_speed.p, sizeof(float) * m, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(s, cudaMemcpyAsync(rad.data(), s->d_radius.p, sizeof(float) * m, cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(s, cudaStreamSynchronize(s->stream));
-        for (int i = 0; i < count; i++) {
+        for (int i = 0; i < m; i++) {
             const float r = kLookAhead * spd[i] + rad[i];
             if (r == r && r < std::numeric_limits<float>::infinity()) s->tracked_range = std::max(s->tracked_range, r);
         }
@@ -1506,15 +1619,27 @@ int ecmgpu_update_io(ecmgpu_sim* s, int count, const float* in_pos, const float*
     CUDA_TRY(s, cudaEventRecord(io.in_done[b], io.s_in));
     // main stream: adopt the inputs, tick, publish the results
     CUDA_TRY(s, cudaStreamWaitEvent(s->stream, io.in_done[b], 0));
-    if (in_pos) CUDA_TRY(s, cudaMemcpyAsync(s->d_pos.p, si, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
-    if (in_vel) CUDA_TRY(s, cudaMemcpyAsync(s->d_vel.p, si + n8, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
+    // host arrays are indexed by slot, the device arrays internally (spatial renumbering): copy, or scatter through int_of
+    if (s->perm_identity) {
+        if (in_pos) CUDA_TRY(s, cudaMemcpyAsync(s->d_pos.p, si, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
+        if (in_vel) CUDA_TRY(s, cudaMemcpyAsync(s->d_vel.p, si + n8, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
+    } else if (count > 0) {
+        if (in_pos) launch_remap(s, false, 8, count, 0, si, s->d_pos.p);
+        if (in_vel) launch_remap(s, false, 8, count, 0, si + n8, s->d_vel.p);
+    }
     CUDA_TRY(s, cudaEventRecord(io.in_consumed[b], s->stream));
     rc = ecmgpu_update(s);
     if (rc) return rc;
     CUDA_TRY(s, cudaStreamWaitEvent(s->stream, io.out_done[b], 0));  // the download that last read staging b is over
-    if (out_pos) CUDA_TRY(s, cudaMemcpyAsync(so, s->d_pos.p, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
-    if (out_vel) CUDA_TRY(s, cudaMemcpyAsync(so + n8, s->d_vel.p, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
-    if (out_active) CUDA_TRY(s, cudaMemcpyAsync(so + 2 * n8, s->d_active.p, c, cudaMemcpyDeviceToDevice, s->stream));
+    if (s->perm_identity) {
+        if (out_pos) CUDA_TRY(s, cudaMemcpyAsync(so, s->d_pos.p, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
+        if (out_vel) CUDA_TRY(s, cudaMemcpyAsync(so + n8, s->d_vel.p, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
+        if (out_active) CUDA_TRY(s, cudaMemcpyAsync(so + 2 * n8, s->d_active.p, c, cudaMemcpyDeviceToDevice, s->stream));
+    } else if (count > 0) {
+        if (out_pos) launch_remap(s, true, 8, count, 0, s->d_pos.p, so);
+        if (out_vel) launch_remap(s, true, 8, count, 0, s->d_vel.p, so + n8);
+        if (out_active) launch_remap(s, true, 1, count, 0, s->d_active.p, so + 2 * n8);
+    }
     CUDA_TRY(s, cudaEventRecord(io.tick_done[b], s->stream));
     // download
     CUDA_TRY(s, cudaStreamWaitEvent(io.s_out, io.tick_done[b], 0));
@@ -1550,7 +1675,8 @@ int ecmgpu_update_io_owned(ecmgpu_sim* s, int n_in, const ecmgpu_agent_rec* in, 
     CUDA_TRY(s, cudaEventRecord(io.in_done[b], io.s_in));
     CUDA_TRY(s, cudaStreamWaitEvent(s->stream, io.in_done[b], 0));
     if (n_in) {
-        k_apply_records<<<div_up(n_in, 256), 256, 0, s->stream>>>(n_in, si, s->prm.max_agents, s->d_active.p, s->d_pos.p, s->d_vel.p);
+        k_apply_records<<<div_up(n_in, 256), 256, 0, s->stream>>>(n_in, si, s->prm.max_agents, s->d_active.p, s->d_pos.p, s->d_vel.p,
+                                                                    s->perm_identity ? nullptr : s->d_int_of.p);
         s->launches++;
     }
     CUDA_TRY(s, cudaEventRecord(io.in_consumed[b], s->stream));
@@ -1560,8 +1686,9 @@ int ecmgpu_update_io_owned(ecmgpu_sim* s, int n_in, const ecmgpu_agent_rec* in, 
     CUDA_TRY(s, cudaMemsetAsync(so_count, 0, sizeof(int), s->stream));
     if (s->n_slots > 0) {
         const StripView sv = make_strip_view(s);
-        if (sv.walk.list && !s->walk_dirty) k_collect_owned_walk<<<kSMs * 2, kCollectBlock, 0, s->stream>>>(sv.walk, s->d_active.p, s->d_pos.p, s->d_vel.p, so, so_count);
-        else k_collect_owned<<<div_up(s->n_slots, kCollectBlock), kCollectBlock, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, s->d_vel.p, so, so_count);
+        const int* ext = s->perm_identity ? nullptr : s->d_ext_of.p;
+        if (sv.walk.list && !s->walk_dirty) k_collect_owned_walk<<<kSMs * 2, kCollectBlock, 0, s->stream>>>(sv.walk, s->d_active.p, s->d_pos.p, s->d_vel.p, so, so_count, ext);
+        else k_collect_owned<<<div_up(s->n_slots, kCollectBlock), kCollectBlock, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, s->d_vel.p, so, so_count, ext);
         s->launches++;
     }
     CUDA_TRY(s, cudaEventRecord(io.tick_done[b], s->stream));
@@ -1693,9 +1820,11 @@ int ecmgpu_find_neighbors(ecmgpu_sim* s, int count, int* out_ids5, int* out_coun
         CUDA_TRY(s, cudaGetLastError());
     }
     const int m = std::min(count, s->n_slots);
-    if (m > 0) {
-        CUDA_TRY(s, cudaMemcpyAsync(out_ids5, s->d_nbr.p, sizeof(int) * 5 * (size_t)m, cudaMemcpyDeviceToHost, s->stream));
-        CUDA_TRY(s, cudaMemcpyAsync(out_counts, s->d_nbr_cnt.p, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, s->stream));
+    if (m > 0) {  // the lists hold slot ids already (GridView::slot_of_row); the rows are indexed internally
+        int rc = xfer(s, ECMGPU_NEIGHBORS, out_ids5, 0, m, true, false);
+        if (rc) return rc;
+        rc = xfer(s, ECMGPU_NEIGHBOR_COUNT, out_counts, 0, m, true, false);
+        if (rc) return rc;
     }
     CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     for (int i = m; i < count; i++) { out_counts[i] = -1; for (int j = 0; j < 5; j++) out_ids5[5 * i + j] = -1; }
@@ -1709,9 +1838,10 @@ int ecmgpu_find_obstacles(ecmgpu_sim* s, int slot, int* out_ids, int cap, int* o
     int rc = ensure_ready(s);
     if (rc) return rc;
     float2 pos; float rad, spd;
-    CUDA_TRY(s, cudaMemcpyAsync(&pos, s->d_pos.p + slot, sizeof(float2), cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(s, cudaMemcpyAsync(&rad, s->d_radius.p + slot, sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(s, cudaMemcpyAsync(&spd, s->d_speed.p + slot, sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    const int a = s->h_int_of[slot];
+    CUDA_TRY(s, cudaMemcpyAsync(&pos, s->d_pos.p + a, sizeof(float2), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(&rad, s->d_radius.p + a, sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(&spd, s->d_speed.p + a, sizeof(float), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     const float range = kLookAhead * spd + rad;
     DevBuf<int> dout, dn;
@@ -1838,13 +1968,55 @@ int ecmgpu_valid_spawn_locations(ecmgpu_sim* s, int n, const float* xy, const fl
     return ECMGPU_OK;
 }
 
+// Back to "internal index = slot id": every per-agent array is permuted once.  The KD-tree mode needs it (it walks the
+// slots in ascending order like KDTree::Construct and ORCA's carried neighbour list, KDTree.cpp:34-41, ORCA.h:100).
+static int restore_identity(ecmgpu_sim* s) {
+    if (s->perm_identity) return ECMGPU_OK;
+    const int n = s->n_slots;
+    if (n > 0) {
+        DevBuf<unsigned char> tmp;
+        CUDA_TRY(s, tmp.alloc(20 * (size_t)n));
+        auto fix = [&](void* arr, size_t es) -> cudaError_t {
+            const int nb = div_up(n, 256);
+            const int* m = s->d_int_of.p;
+            if (es == 1) k_gather_slots<unsigned char><<<nb, 256, 0, s->stream>>>(n, 0, m, (const unsigned char*)arr, (unsigned char*)tmp.p);
+            else if (es == 4) k_gather_slots<unsigned><<<nb, 256, 0, s->stream>>>(n, 0, m, (const unsigned*)arr, (unsigned*)tmp.p);
+            else if (es == 8) k_gather_slots<float2><<<nb, 256, 0, s->stream>>>(n, 0, m, (const float2*)arr, (float2*)tmp.p);
+            else if (es == 16) k_gather_slots<float4><<<nb, 256, 0, s->stream>>>(n, 0, m, (const float4*)arr, (float4*)tmp.p);
+            else k_gather_slots<Int5><<<nb, 256, 0, s->stream>>>(n, 0, m, (const Int5*)arr, (Int5*)tmp.p);
+            s->launches++;
+            return cudaMemcpyAsync(arr, tmp.p, es * (size_t)n, cudaMemcpyDeviceToDevice, s->stream);
+        };
+        static_assert(sizeof(PathHdr) == 16, "path headers move as float4");
+        CUDA_TRY(s, fix(s->d_pos.p, 8)); CUDA_TRY(s, fix(s->d_vel.p, 8)); CUDA_TRY(s, fix(s->d_prefvel.p, 8));
+        CUDA_TRY(s, fix(s->d_attraction.p, 8)); CUDA_TRY(s, fix(s->d_force.p, 8));
+        CUDA_TRY(s, fix(s->d_radius.p, 4)); CUDA_TRY(s, fix(s->d_speed.p, 4)); CUDA_TRY(s, fix(s->d_status.p, 4));
+        CUDA_TRY(s, fix(s->d_cell.p, 4)); CUDA_TRY(s, fix(s->d_nbr_cnt.p, 4));
+        CUDA_TRY(s, fix(s->d_active.p, 1)); CUDA_TRY(s, fix(s->d_replan_pending.p, 1));
+        CUDA_TRY(s, fix(s->d_nbr.p, 20)); CUDA_TRY(s, fix(s->d_path_hdr.p, 16));
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        std::vector<PathHdr> hdr(s->h_path_hdr);
+        for (int e = 0; e < n; e++) s->h_path_hdr[e] = hdr[s->h_int_of[e]];
+    }
+    for (size_t i = 0; i < s->h_int_of.size(); i++) s->h_int_of[i] = s->h_ext_of[i] = (int)i;
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_int_of.p, s->h_int_of.data(), sizeof(int) * s->h_int_of.size(), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(s->d_ext_of.p, s->h_ext_of.data(), sizeof(int) * s->h_ext_of.size(), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    s->perm_identity = true;
+    s->walk_dirty = true;
+    s->config_epoch++;
+    return ECMGPU_OK;
+}
+
 int ecmgpu_set_neighbor_mode(ecmgpu_sim* s, int mode) {
     if (!s) return ECMGPU_ERR_INVALID;
     if (mode != ECMGPU_NEIGHBORS_EXACT && mode != ECMGPU_NEIGHBORS_KDTREE) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_set_neighbor_mode: unknown mode");
     CUDA_TRY(s, cudaSetDevice(s->prm.device));
     if (mode == ECMGPU_NEIGHBORS_KDTREE) {
         if (s->strips_on) return fail(s, ECMGPU_ERR_INVALID, "the KD-tree neighbour mode runs on a single handle (no strips)");
-        int rc = kd_alloc(s);
+        int rc = restore_identity(s);
+        if (rc) return rc;
+        rc = kd_alloc(s);
         if (rc) return rc;
         CUDA_TRY(s, cudaMemsetAsync(s->d_kd_cache.p, 0, sizeof(int) * 10, s->stream));  // a fresh ORCA object (ORCA.h:87)
     }
@@ -1874,6 +2046,7 @@ int ecmgpu_get_stats(ecmgpu_sim* s, ecmgpu_stats* o) {
     o->kd_median_ties = c[C_TOTAL_KD_TIES];
     o->kd_small_ties = c[C_TOTAL_KD_SMALL_TIES];
     o->event_overflows = c[C_TOTAL_EV_OVERFLOW];
+    o->nonfinite_agent_ticks = c[C_TOTAL_NONFINITE];
     return ECMGPU_OK;
 }
 
@@ -1881,8 +2054,8 @@ void ecmgpu_abi_sizes(int32_t out[4]) {
     out[0] = (int32_t)sizeof(ecmgpu_params);
     out[1] = (int32_t)sizeof(ecmgpu_stats);
     out[2] = (int32_t)sizeof(ecmgpu_agent_rec);
-    out[3] = 21;  // members of ecmgpu_stats
-    static_assert(sizeof(ecmgpu_stats) == 10 * 4 + 11 * 8, "ecmgpu_stats changed: update out[3] and the bindings");
+    out[3] = 22;  // members of ecmgpu_stats
+    static_assert(sizeof(ecmgpu_stats) == 10 * 4 + 12 * 8, "ecmgpu_stats changed: update out[3] and the bindings");
 }
 
 int ecmgpu_set_profiling(ecmgpu_sim* s, int on) {

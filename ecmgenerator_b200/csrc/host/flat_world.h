@@ -44,6 +44,26 @@ struct FlatWorld {
     FlatObstacles obst;
 };
 
+// Levels at which the reference's even-odd test (strict y comparisons, UtilityFunctions.cpp:68-83) miscounts for the cell
+// polygon with vertex heights y[0..3] (polygon order): a maximal run of consecutive vertices exactly at one y whose
+// neighbours before and after it lie on OPPOSITE sides is a real crossing of the ray that neither incident edge counts,
+// so a point level with it and to its left gets the wrong parity - it can be "inside" a cell far to its right.  Touching
+// runs (same side) and extremal vertices are counted correctly.  An axis-aligned lattice has no such level (its cells
+// meet every vertex level from one side); a turned world has about two per cell.  Shared by the host locator
+// (planner.cpp) and the device bins (csrc/ecmgpu.cu).
+inline void pass_through_levels(const float y[4], std::vector<float>& out) {
+    for (int i = 0; i < 4; i++) {
+        const float L = y[i];
+        if (!(L == L)) continue;
+        if (y[(i + 3) & 3] == L) continue;  // not the first vertex of its run
+        int j = i, len = 1;
+        while (len < 4 && y[(j + 1) & 3] == L) { j++; len++; }
+        if (len == 4) continue;             // all four on one level: the strict test never counts anything
+        const float before = y[(i + 3) & 3], after = y[(j + 1) & 3];
+        if ((before < L) != (after < L)) out.push_back(L == 0.0f ? 0.0f : L);
+    }
+}
+
 // Appends one polygonal obstacle (CCW vertex order) and fills next/prev/convex with the
 // reference's rule (/root/reference/ECMGenerator/ECMDataTypes.cpp:23-61).
 void AppendObstacle(FlatObstacles& o, const float* xy, int n);

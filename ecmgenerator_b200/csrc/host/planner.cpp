@@ -113,13 +113,11 @@ void CellLocator::Build(const FlatWorld& w, float bin) {
             for (int x = ax[c]; x <= bx[c]; x++) items_[fill[y * w_ + x]++] = c;
     // exact-level points: the y of every cell-polygon vertex, and per bin row the cells reaching into it
     levels_.clear();
-    for (int e = 0; e < nE; e++) {
-        for (int k = 0; k < 4; k++) levels_.push_back(Cl(w, e, k).y);
-        levels_.push_back(Vert(w, w.ecm.edge_v[2 * e]).y);
-        levels_.push_back(Vert(w, w.ecm.edge_v[2 * e + 1]).y);
+    for (int c = 0; c < nc; c++) {
+        const int e = c >> 1, side = c & 1;
+        const float ys[4] = {Vert(w, w.ecm.edge_v[2 * e]).y, Cl(w, e, side).y, Cl(w, e, 2 + side).y, Vert(w, w.ecm.edge_v[2 * e + 1]).y};
+        pass_through_levels(ys, levels_);
     }
-    for (float& v : levels_) if (v == 0.0f) v = 0.0f;
-    levels_.erase(std::remove_if(levels_.begin(), levels_.end(), [](float v) { return !(v == v); }), levels_.end());
     std::sort(levels_.begin(), levels_.end());
     levels_.erase(std::unique(levels_.begin(), levels_.end()), levels_.end());
     row_start_.assign(h_ + 1, 0);

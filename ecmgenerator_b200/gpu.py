@@ -57,7 +57,7 @@ class Stats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("knn_fallbacks", C.c_uint64), ("obstacle_overflows", C.c_uint64),
                 ("lp3d_runs", C.c_uint64), ("location_failures", C.c_uint64), ("replans", C.c_uint64),
                 ("halo_misses", C.c_uint64),
-                ("kd_median_ties", C.c_uint64), ("kd_small_ties", C.c_uint64), ("event_overflows", C.c_uint64)]
+                ("kd_median_ties", C.c_uint64), ("kd_small_ties", C.c_uint64), ("event_overflows", C.c_uint64), ("nonfinite_agent_ticks", C.c_uint64)]
 
 
 class EcmGpuError(RuntimeError):

@@ -71,7 +71,10 @@ enum {
     ECMGPU_ST_OBST_OVERFLOW = 16u, /* more obstacle neighbours than the device cap (excess dropped) */
     ECMGPU_ST_KNN_FALLBACK = 32u,  /* neighbour search left the ring budget; resolved by the exhaustive pass */
     ECMGPU_ST_LP3D = 64u,          /* RandomizedLP failed, RandomizedLP3D ran  (ORCA.cpp:51-54) */
-    ECMGPU_ST_HALO_MISS = 128u     /* multi-GPU: search reached beyond the received halo */
+    ECMGPU_ST_HALO_MISS = 128u,    /* multi-GPU: search reached beyond the received halo */
+    ECMGPU_ST_NONFINITE = 256u     /* the agent's position is NaN or infinite (the reference's LP3D can produce NaN velocities;
+                                    * from there the reference is undefined): the agent stays active, is nobody's neighbour
+                                    * and is no longer updated */
 };
 
 /* -- lifetime ---------------------------------------------------------------------------------
@@ -223,6 +226,8 @@ typedef struct ecmgpu_stats {
     /* arrival / replan events dropped because a list was full: each list holds max_agents entries and is emptied by
      * ecmgpu_poll_events, which then fails with ECMGPU_ERR_CAPACITY (poll at least once per max_agents events) */
     uint64_t event_overflows;
+    /* agent-ticks skipped because the agent's position was not finite (ECMGPU_ST_NONFINITE) */
+    uint64_t nonfinite_agent_ticks;
 } ecmgpu_stats;
 int ecmgpu_get_stats(ecmgpu_sim* sim, ecmgpu_stats* out);
 /* sizeof(ecmgpu_params), sizeof(ecmgpu_stats), sizeof(ecmgpu_agent_rec), number of ecmgpu_stats members: lets a binding in

@@ -722,6 +722,7 @@ static int randomized_lp(eo_sim* s, const eo_constraint* cs, int n, v2 opt, floa
         float dpd = vdot(dir, h->p);
         float disc = dpd * dpd + maxSpeed * maxSpeed - vdot(h->p, h->p);
         if (disc <= 0.0f) return i;
+        if (!(disc > 0.0f)) continue; /* NaN: `if (d <= 0) return i; else if (d > 0) {...}` does neither (ORCA.cpp:499-507) */
         float dsq = sqrtf(disc);
         float left = -dpd - dsq;
         float right = -dpd + dsq;

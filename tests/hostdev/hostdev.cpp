@@ -116,7 +116,7 @@ int hd_tick(void* h, int n, float step, float cell, int max_ring, float* pos_io,
     for (int i = 0; i < n; i++) if (active_io[i]) { n_act++; x0 = std::min(x0, pos[i].x); y0 = std::min(y0, pos[i].y); x1 = std::max(x1, pos[i].x); y1 = std::max(y1, pos[i].y); }
     *n_replan_o = 0; *n_destroyed_o = 0;
     if (n_act == 0) return 0;
-    GridView g;
+    GridView g{};
     g.x0 = x0 - cell; g.y0 = y0 - cell; g.cell = cell; g.inv_cell = 1.0f / cell;
     g.w = (int)((x1 - g.x0) / cell) + 2; g.h = (int)((y1 - g.y0) / cell) + 2;
     std::vector<int> key(n, -1), start((size_t)g.w * g.h + 1, 0);
@@ -130,7 +130,7 @@ int hd_tick(void* h, int n, float step, float cell, int max_ring, float* pos_io,
         int p = fill[key[i]]++;
         s_slot[p] = i; s_pos[p] = pos[i]; s_vel[p] = vel[i]; s_rad[p] = radius[i]; s_spd[p] = speed[i];
     }
-    g.n_sorted = n_act; g.cell_start = start.data(); g.s_pos = s_pos.data(); g.s_vel = s_vel.data(); g.s_rad = s_rad.data(); g.s_slot = s_slot.data();
+    g.n_sorted = n_act; g.cell_start = start.data(); g.s_pos = s_pos.data(); g.s_vel = s_vel.data(); g.s_rad = s_rad.data(); g.s_slot = s_slot.data(); g.ext_of = nullptr;
     // ---- attract_agent (UpdateAttractionPointSystem + ApplySteeringForce)
     std::vector<float2> poly;
     std::vector<float4> boxes;
@@ -226,7 +226,7 @@ void hd_neighbors(int n, float cell, int max_ring, const float* pos_in, const un
     for (int i = 0; i < n; i++) if (active[i]) { n_act++; x0 = std::min(x0, pos[i].x); y0 = std::min(y0, pos[i].y); x1 = std::max(x1, pos[i].x); y1 = std::max(y1, pos[i].y); }
     for (int i = 0; i < n; i++) { nbr_cnt_o[i] = 0; for (int j = 0; j < kK; j++) nbr_o[kK * i + j] = -1; }
     if (n_act == 0) return;
-    GridView g;
+    GridView g{};
     g.x0 = x0 - cell; g.y0 = y0 - cell; g.cell = cell; g.inv_cell = 1.0f / cell;
     g.w = (int)((x1 - g.x0) / cell) + 2; g.h = (int)((y1 - g.y0) / cell) + 2;
     std::vector<int> key(n, -1), start((size_t)g.w * g.h + 1, 0);

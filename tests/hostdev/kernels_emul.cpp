@@ -99,7 +99,7 @@ struct Emu {
         t.bins.obst_start = bin_obst_start.data(); t.bins.obst_items = obst_items.data();
         t.grid.x0 = gx0; t.grid.y0 = gy0; t.grid.cell = gcell; t.grid.inv_cell = 1.0f / gcell; t.grid.w = gw; t.grid.h = gh;
         t.grid.n_sorted = 0; t.grid.cell_start = cell_count.data();
-        t.grid.s_pos = s_pos.data(); t.grid.s_vel = s_vel.data(); t.grid.s_rad = s_rad.data(); t.grid.s_slot = s_slot.data();
+        t.grid.s_pos = s_pos.data(); t.grid.s_vel = s_vel.data(); t.grid.s_rad = s_rad.data(); t.grid.s_slot = s_slot.data(); t.grid.ext_of = nullptr;
         t.ag.pos = pos.data(); t.ag.vel = vel.data(); t.ag.prefvel = prefvel.data(); t.ag.attraction = attraction.data();
         t.ag.force = force.data(); t.ag.radius = radius.data(); t.ag.speed = speed.data(); t.ag.active = active.data();
         t.ag.replan_pending = replan_pending.data(); t.ag.status = status.data(); t.ag.cell = cell.data();
@@ -242,6 +242,14 @@ void emu_set_path(void* h, int slot, const float* xy, int np) {
     e->replan_pending[slot] = 0;
 }
 void emu_destroy_agent(void* h, int slot) { ((Emu*)h)->active[slot] = 0; }
+// ecmgpu_write(VEL / ATTRACTION): a mid-run state for single-tick replays
+void emu_set_state(void* h, const float* vel, const float* attraction) {
+    Emu* e = (Emu*)h;
+    for (int i = 0; i < e->n_slots; i++) {
+        e->vel[i] = make_float2(vel[2 * i], vel[2 * i + 1]);
+        e->attraction[i] = make_float2(attraction[2 * i], attraction[2 * i + 1]);
+    }
+}
 
 // ecmgpu_comm_set_strips (fixed capacities given by the caller) + k_assign_owner
 void emu_set_strips(void* h, int rank, int n_ranks, float lo, float hi, float halo, int cap_halo, int cap_migr) {
@@ -303,8 +311,8 @@ int emu_tick(void* h) {
     GridParams gp{e->gx0, e->gy0, e->gcell, 1.0f / e->gcell, e->gw, e->gh};
     std::fill(e->cell_count.begin(), e->cell_count.end(), 0);
     e->counters[C_FALLBACK_N] = 0; e->counters[C_LP3D_N] = 0;
-    if (sv.walk.list) launch(53, [&] { k_bin_count_walk(sv.walk, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data()); }, 256);
-    else launch(e->n_slots, [&] { k_bin_count(e->n_slots, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data()); }, 256);
+    if (sv.walk.list) launch(53, [&] { k_bin_count_walk(sv.walk, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data(), e->status.data(), e->counters.data()); }, 256);
+    else launch(e->n_slots, [&] { k_bin_count(e->n_slots, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data(), e->status.data(), e->counters.data()); }, 256);
     const int ng = 2 * e->cap_halo + e->cap_self;
     if (e->strips) launch(ng, [&] { k_ghost_count(sv, gp, e->cell_count.data()); }, 256);
     emu_scan_cells(e);
@@ -386,7 +394,7 @@ static void emu_grid_build(Emu* e, const TickView& t) {
     GridParams gp{e->gx0, e->gy0, e->gcell, 1.0f / e->gcell, e->gw, e->gh};
     std::fill(e->cell_count.begin(), e->cell_count.end(), 0);
     e->counters[C_FALLBACK_N] = 0; e->counters[C_LP3D_N] = 0;
-    launch(e->n_slots, [&] { k_bin_count(e->n_slots, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data()); }, 256);
+    launch(e->n_slots, [&] { k_bin_count(e->n_slots, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data(), e->status.data(), e->counters.data()); }, 256);
     emu_scan_cells(e);
     launch(e->n_slots, [&] { k_scatter(e->n_slots, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc); }, 256);
 }
@@ -515,13 +523,13 @@ int emu_collect_owned(void* h, AgentRec* out) {
     Emu* e = (Emu*)h;
     int count = 0;
     StripView sv = e->sview();
-    if (sv.walk.list && !e->walk_dirty) launch(19, [&] { k_collect_owned_walk(sv.walk, e->active.data(), e->pos.data(), e->vel.data(), out, &count); }, kCollectBlock);
-    else launch(e->n_slots, [&] { k_collect_owned(e->n_slots, e->active.data(), e->pos.data(), e->vel.data(), out, &count); }, kCollectBlock);
+    if (sv.walk.list && !e->walk_dirty) launch(19, [&] { k_collect_owned_walk(sv.walk, e->active.data(), e->pos.data(), e->vel.data(), out, &count, nullptr); }, kCollectBlock);
+    else launch(e->n_slots, [&] { k_collect_owned(e->n_slots, e->active.data(), e->pos.data(), e->vel.data(), out, &count, nullptr); }, kCollectBlock);
     return count;
 }
 void emu_apply_records(void* h, int n, const AgentRec* rec) {
     Emu* e = (Emu*)h;
-    launch(n, [&] { k_apply_records(n, rec, e->n, e->active.data(), e->pos.data(), e->vel.data()); }, 256);
+    launch(n, [&] { k_apply_records(n, rec, e->n, e->active.data(), e->pos.data(), e->vel.data(), nullptr); }, 256);
 }
 
 }  // extern "C"

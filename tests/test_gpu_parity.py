@@ -446,3 +446,58 @@ def test_counterflow_jam_lockstep():
     lp3d = sim.stats()["lp3d_runs"]
     print(f"counterflow: worst |dv| {worst:.3e}; LP3D ran for {lp3d} agent-updates in 20 ticks")
     assert worst <= VEL_TOL and lp3d > 50
+
+
+def test_nan_obstacle_constraint_case_matches_the_reference():
+    """tests/golden/nan_case.npz: an agent exactly level with a block corner it touches gets a NaN obstacle constraint
+    (ORCA.cpp:171-183) that the reference's LP passes over (ORCA.cpp:499-507); expected state from the unmodified
+    reference.  Found at tick 832 of the 1 M-agent run, where projecting on it turned the agent into NaN."""
+    import os
+
+    from ecmgenerator_b200 import scenarios as S
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nan_case.npz"))
+    m = len(z["near"])
+    sim = gpu.GpuSim(S.world_c3(), m + 8, float(S.DT), path_pool_points=int(z["path_off"][-1]) + 8 * m + 4096)
+    sim.bulk_load(z["pos"], z["radius"], z["speed"], z["path_off"], z["path_xy"])
+    sim.write(gpu.VEL, z["vel"])
+    sim.write(gpu.ATTRACTION, z["attraction"])
+    sim.update(1)
+    a = sim.state(m)
+    st = sim.stats()
+    sim.close()
+    assert np.isfinite(a["vel"]).all() and np.isfinite(a["pos"]).all()
+    assert st["nonfinite_agent_ticks"] == 0
+    assert_bits_equal(a["attraction"], z["ref_attraction"], "attraction")
+    assert_bits_equal(a["prefvel"], z["ref_prefvel"], "prefvel")
+    assert np.abs(a["vel"] - z["ref_vel"]).max() <= VEL_TOL
+    assert np.abs(a["pos"] - z["ref_pos"]).max() <= VEL_TOL
+
+
+def test_nonfinite_agent_leaves_the_tick():
+    """An agent whose position is NaN (the reference is undefined from there) stays active and untouched, is nobody's
+    neighbour, is counted - and does not cost the exhaustive scans kept for points outside the static grid."""
+    g = Golden("c2_small")
+    sim = gpu.GpuSim(g.world, g.n + 8, g.step)
+    sim.bulk_load(g.crowd.pos, g.crowd.radius, g.crowd.speed, g.path_off, g.path_xy)
+    ora = OracleSim(g.world, g.n + 8, g.step, MODE)
+    ora.bulk_load(g.crowd.pos, g.crowd.radius, g.crowd.speed, g.path_off, g.path_xy)
+    sim.update(3)
+    ora.step(3)
+    bad = 17
+    pos = sim.read(gpu.POS, 0, g.n)
+    pos[bad] = np.nan
+    sim.write(gpu.POS, pos)
+    ora.destroy_agent(bad)  # the others must behave as if it were not there
+    sim.update(5)
+    ora.step(5)
+    a, b = sim.state(g.n), ora.state(g.n)
+    st = sim.stats()
+    status = sim.read(gpu.STATUS, 0, g.n)
+    sim.close()
+    ora.close()
+    assert a["active"][bad] == 1 and np.isnan(a["pos"][bad]).all()
+    assert status[bad] == 256 and st["nonfinite_agent_ticks"] == 5
+    keep = np.arange(g.n) != bad
+    assert np.abs(a["vel"][keep] - b["vel"][keep]).max() <= VEL_TOL
+    assert np.abs(a["pos"][keep] - b["pos"][keep]).max() <= VEL_TOL

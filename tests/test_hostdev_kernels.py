@@ -52,6 +52,7 @@ def load_emu(flags=(), tag=""):
     L.emu_load.argtypes = [vp, C.c_int, f32p, f32p, f32p, i32p, f32p]
     L.emu_set_path.argtypes = [vp, C.c_int, f32p, C.c_int]
     L.emu_destroy_agent.argtypes = [vp, C.c_int]
+    L.emu_set_state.argtypes = [vp, f32p, f32p]
     L.emu_set_strips.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]
     L.emu_pack.argtypes = [vp]
     L.emu_exchange.argtypes = [vp, vp, vp]
@@ -114,6 +115,10 @@ class EmuDevice:
 
     def destroy_agent(self, slot):
         self.L.emu_destroy_agent(self.h, int(slot))
+
+    def set_state(self, vel, attraction):
+        v, a = np.ascontiguousarray(vel, np.float32), np.ascontiguousarray(attraction, np.float32)
+        self.L.emu_set_state(self.h, _p(v, f32p), _p(a, f32p))
 
     def set_path(self, slot, path):
         p = np.ascontiguousarray(path, np.float32).reshape(-1, 2)

@@ -55,3 +55,24 @@ def test_attraction_points_on_long_routes():
     assert located.mean() > 0.5
     d.close()
     ora.close()
+
+
+def test_nan_obstacle_constraint_case_on_the_device_code():
+    """tests/golden/nan_case.npz (see tests/test_oracle_golden.py): the device code must pass over the NaN obstacle
+    constraint exactly like the reference's RandomizedLP does (ORCA.cpp:499-507), not project on it."""
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nan_case.npz"))
+    emu = load_emu()
+    w = S.world_c3()
+    m = len(z["near"])
+    c = S.Crowd(z["pos"].copy(), z["pos"].copy(), z["radius"].copy(), z["speed"].copy())
+    g = _Scene(w, c, z["path_off"], z["path_xy"], float(S.DT))
+    d = EmuDevice(emu, g, 3.4)
+    d.set_state(vel=z["vel"], attraction=z["attraction"])
+    emu.emu_tick(d.h)
+    a = d.state()
+    assert np.isfinite(a["vel"]).all()
+    for k in ("attraction", "prefvel", "pos", "vel"):
+        assert_bits_equal(a[k], z["ref_" + k], k)
+    d.close()

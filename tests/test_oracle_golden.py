@@ -1,5 +1,7 @@
 """CPU: the plain-C oracle (oracle/ecm_oracle.c) against golden vectors produced by the unmodified
 reference (tests/golden/make_golden.py).  Bit-exact in both neighbour modes."""
+import os
+
 import numpy as np
 import pytest
 
@@ -102,3 +104,26 @@ def test_new_goldens_hold_oblique_and_concave_geometry():
         assert c["oblique_segments"] > 50_000, c
         if want_concave:
             assert c["concave_segments"] > 100_000 and c["lp3d"] > 300, c
+
+
+def test_nan_obstacle_constraint_is_passed_over_like_the_reference():
+    """tests/golden/nan_case.npz: 486 agents around one that is exactly level with a block corner it touches (found at tick
+    832 of the 1 M-agent run).  ORCA.cpp:171-183 then takes the square root of a negative number: a NaN obstacle
+    constraint, which RandomizedLP passes over because `if (d <= 0) return i; else if (d > 0) {...}` (ORCA.cpp:499-507)
+    does neither for NaN.  The expected state in the file was computed by the UNMODIFIED reference (oracle/_ref, both
+    neighbour modes agree); a restatement that projects on the NaN constraint turns the agent's velocity into NaN."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nan_case.npz"))
+    from ecmgenerator_b200 import scenarios as S
+
+    w = S.world_c3()
+    m = len(z["near"])
+    o = OracleSim(w, m + 8, float(S.DT), "exact-knn")
+    o.bulk_load(z["pos"], z["radius"], z["speed"], z["path_off"], z["path_xy"])
+    for k in range(m):
+        o.set_kinematics(k, z["pos"][k], z["vel"][k])
+        o.set_attraction(k, z["attraction"][k])
+    o.step(1)
+    st = o.state(m)
+    assert np.isfinite(st["vel"]).all()
+    for k in ("pos", "vel", "prefvel", "attraction", "force"):
+        assert_bits_equal(st[k], z["ref_" + k], k)
