@@ -480,7 +480,7 @@ def test_nonfinite_agent_leaves_the_tick():
     g = Golden("c2_small")
     sim = gpu.GpuSim(g.world, g.n + 8, g.step)
     sim.bulk_load(g.crowd.pos, g.crowd.radius, g.crowd.speed, g.path_off, g.path_xy)
-    ora = OracleSim(g.world, g.n + 8, g.step, MODE)
+    ora = OracleSim(g.world, g.n + 8, g.step, "exact-knn")
     ora.bulk_load(g.crowd.pos, g.crowd.radius, g.crowd.speed, g.path_off, g.path_xy)
     sim.update(3)
     ora.step(3)
