@@ -91,7 +91,7 @@ def build_workload(config: str, agents: int | None, rank: int = 0, world: int = 
     # ECM_WORKLOAD_CACHE=<dir>: measurement sessions that build the same workload several times (tools/gpu_session.sh)
     # keep the sampled crowd and its planned routes on disk; worlds and crowds are seeded, so the content is the same
     cache = os.environ.get("ECM_WORKLOAD_CACHE")
-    cache_file = os.path.join(cache, f"{config}_{agents or 0}.npz") if cache and world == 1 else None
+    cache_file = os.path.join(cache, f"{config}_{agents or 0}.npz") if cache else None  # every rank reads it; rank 0 writes it
     if cache_file and os.path.exists(cache_file):
         z = np.load(cache_file)
         c = S.Crowd(z["pos"], z["goal"], z["radius"], z["speed"])
@@ -115,7 +115,7 @@ def build_workload(config: str, agents: int | None, rank: int = 0, world: int = 
     LAST_SETUP.update(planner=planner, plan_seconds=round(time.time() - t1, 2), queries=int(len(lens)))
     log(f"[bench] {config}: {c.n} agents sampled in {t1 - t:.1f}s, paths planned on the {planner} in {time.time() - t1:.1f}s "
         f"(mean {np.diff(off).mean():.1f} points, {int((~good).sum())} dropped)")
-    if cache_file:
+    if cache_file and rank == 0:
         os.makedirs(cache, exist_ok=True)
         np.savez(cache_file, pos=c.pos, goal=c.goal, radius=c.radius, speed=c.speed, off=off, pxy=pxy)
     return w, c, off, pxy

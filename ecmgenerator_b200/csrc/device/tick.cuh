@@ -1,7 +1,7 @@
 // Kernels of one simulation tick (Simulator::Update, /root/reference/ECMAgentSimulator/Simulator.cpp:314-323).
 //
 //   k_bin_count   cell key + rank of every active agent            (replaces KDTree::Construct, KDTree.cpp:22-57)
-//   k_scan_*      exclusive scan of the per-cell counts
+//   k_scan_onepass exclusive scan of the per-cell counts
 //   k_scatter     counting-sort scatter: SoA snapshot of the pre-tick state in cell order
 //   k_attract     arrival test, ECM point location, IRM attraction point, preferred velocity
 //                 (UpdateAttractionPointSystem + ApplySteeringForce, Simulator.cpp:538-590, 638-657)
@@ -70,7 +70,6 @@ struct TickScratch {
     int* key;       // [slot] cell key, -1 inactive
     int* rank;      // [slot] arrival order inside the cell
     int* cell_count;  // [ncells_padded] -> scanned in place into cell_start
-    int* block_sums;
     float2* s_pos; float2* s_vel; float* s_rad; float* s_spd; int* s_slot;
     float2* s_pref; unsigned char* s_alive;
     unsigned char* s_ghost;  // 1: halo / self ghost (multi-GPU): a neighbour candidate only
@@ -149,41 +148,72 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int& total) {
     return base + x - v;
 }
 
-__global__ void __launch_bounds__(kScanBlock) k_scan_tiles(int4* __restrict__ data, int* __restrict__ block_sums) {
-    int idx = blockIdx.x * kScanBlock + threadIdx.x;
-    int4 v = data[idx];
-    int s = v.x + v.y + v.z + v.w, total;
-    int ex = block_exclusive_scan(s, total);
-    int4 o;
-    o.x = ex; o.y = ex + v.x; o.z = o.y + v.y; o.w = o.z + v.z;
-    data[idx] = o;
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(kScanBlock) k_scan_sums(int* __restrict__ block_sums, int n) {
-    // single block; n <= 4096 * k handled in chunks with a running carry
-    __shared__ int carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
+// The scan in ONE launch (decoupled look-back): a reduce / scan-of-sums / add chain of three dependent launches costs
+// more than the work itself once the cell table is a rank's share of the world (strips: 20 tiles at 8 x 125 k agents).  Tiles are handed out by an atomic
+// ticket, so every predecessor of a tile has started and the look-back cannot wait for a CTA that is not scheduled.
+// state[tile] = (epoch << 34) | (flag << 32) | value, flag 1 = the tile's own sum, 2 = the inclusive prefix; entries of an
+// earlier launch carry an older epoch and read as "not there yet", so nothing has to be cleared between ticks: the last
+// CTA to finish resets the ticket and advances the epoch (ctl[0] epoch, ctl[1] finished tiles, ctl[2] next ticket), and
+// the launch replays inside a CUDA graph.
+__global__ void __launch_bounds__(kScanBlock) k_scan_onepass(int4* __restrict__ data, int tiles, unsigned long long* __restrict__ state,
+                                                             unsigned* __restrict__ ctl) {
+    __shared__ int s_tile, s_prefix;
+    __shared__ unsigned s_epoch;
+    if (threadIdx.x == 0) {
+        s_tile = (int)atomicAdd(&ctl[2], 1u);
+        s_epoch = *(volatile unsigned*)&ctl[0];
+    }
     __syncthreads();
-    for (int base = 0; base < n; base += kScanBlock) {
-        int i = base + threadIdx.x;
-        int v = i < n ? block_sums[i] : 0, total;
-        int ex = block_exclusive_scan(v, total);
-        int carry = carry_s;
-        if (i < n) block_sums[i] = ex + carry;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + total;
-        __syncthreads();
+    const int tile = s_tile;
+    const unsigned long long ep = (unsigned long long)(s_epoch & 0x3fffffffu) << 34;
+    const int idx = tile * kScanBlock + threadIdx.x;
+    const int4 v = data[idx];
+    int total;
+    const int ex = block_exclusive_scan(v.x + v.y + v.z + v.w, total);
+    if (threadIdx.x < 32) {  // warp 0 publishes and looks back
+        const int lane = threadIdx.x;
+        volatile unsigned long long* st = state;
+        int prefix = 0;
+        if (tile == 0) {
+            if (lane == 0) st[0] = ep | (2ull << 32) | (unsigned)total;
+        } else {
+            if (lane == 0) st[tile] = ep | (1ull << 32) | (unsigned)total;
+            int j = tile - 1;  // lane l inspects tile j - l
+            for (;;) {
+                const int t = j - lane;
+                unsigned long long w = 0;
+                if (t >= 0) {
+                    do { w = st[t]; } while ((w >> 34) != (ep >> 34) || ((w >> 32) & 3ull) == 0ull);
+                }
+                const unsigned incl = __ballot_sync(0xffffffffu, t >= 0 && ((w >> 32) & 3ull) == 2ull);
+                const int stop = incl ? __ffs(incl) - 1 : 31;  // nearest tile with an inclusive prefix, else the whole window
+                int val = (t >= 0 && lane <= stop) ? (int)(unsigned)w : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                prefix += val;
+                if (incl || j - 31 <= 0) break;
+                j -= 32;
+            }
+            if (lane == 0) st[tile] = ep | (2ull << 32) | (unsigned)(prefix + total);
+        }
+        if (lane == 0) s_prefix = prefix;
+    }
+    __syncthreads();
+    const int base = s_prefix + ex;
+    int4 o;
+    o.x = base; o.y = base + v.x; o.z = o.y + v.y; o.w = o.z + v.z;
+    data[idx] = o;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&ctl[1], 1u) == (unsigned)tiles - 1u) {  // last tile out: ready for the next launch
+            ctl[1] = 0u;
+            ctl[2] = 0u;
+            __threadfence();
+            ctl[0] = s_epoch + 1u;
+        }
     }
 }
 
-__global__ void __launch_bounds__(kScanBlock) k_scan_add(int4* __restrict__ data, const int* __restrict__ block_sums) {
-    int idx = blockIdx.x * kScanBlock + threadIdx.x;
-    int add = block_sums[blockIdx.x];
-    int4 v = data[idx];
-    v.x += add; v.y += add; v.z += add; v.w += add;
-    data[idx] = v;
-}
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scatter(int n_slots, const int* __restrict__ key, const int* __restrict__ rank,
@@ -484,12 +514,7 @@ __global__ void __launch_bounds__(128) k_knn_query(TickView t) {
 // reference's expression fl(fl(dx*dx) + fl(dy*dy)) < fl(c*c), dx = location.x - position.x.  Only the cells the
 // clearance box touches (plus one cell of slack for the rounding of the box corners) are scanned; agents beyond the
 // grid sit in the border cells of their clamped coordinates, which the clamped box then covers too.
-__global__ void __launch_bounds__(128) k_valid_spawn(GridView g, int n, const float2* __restrict__ xy, const float* __restrict__ clearance,
-                                                      unsigned char* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const v2 loc = xy[i];
-    const float c = clearance[i];
+__device__ __forceinline__ bool spawn_location_valid(const GridView& g, v2 loc, float c) {
     const float c2 = c * c;
     int xa, ya, xb, yb;
     g.cell_of(V(loc.x - c, loc.y - c), xa, ya);
@@ -497,17 +522,54 @@ __global__ void __launch_bounds__(128) k_valid_spawn(GridView g, int n, const fl
     if (!(c == c) || !(loc.x == loc.x) || !(loc.y == loc.y)) { xa = 0; ya = 0; xb = g.w - 1; yb = g.h - 1; }  // NaN: scan everything
     xa = max(xa - 1, 0); ya = max(ya - 1, 0);
     xb = min(xb + 1, g.w - 1); yb = min(yb + 1, g.h - 1);
-    bool ok = true;
-    for (int y = ya; y <= yb && ok; y++) {
+    for (int y = ya; y <= yb; y++) {
         const int a = __ldg(&g.cell_start[y * g.w + xa]);
         const int b = __ldg(&g.cell_start[y * g.w + xb + 1]);
         for (int k = a; k < b; k++) {
             const v2 pj = __ldg(&g.s_pos[k]);
             const float dx = loc.x - pj.x, dy = loc.y - pj.y;
-            if (dx * dx + dy * dy < c2) { ok = false; break; }
+            if (dx * dx + dy * dy < c2) return false;
         }
     }
-    out[i] = ok ? 1 : 0;
+    return true;
+}
+
+__global__ void __launch_bounds__(128) k_valid_spawn(GridView g, int n, const float2* __restrict__ xy, const float* __restrict__ clearance,
+                                                      unsigned char* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = spawn_location_valid(g, xy[i], clearance[i]) ? 1 : 0;
+}
+
+// Simulator::UpdateSpawnAreas' inner loop (Simulator.cpp:501-527) with a counter-based generator instead of C rand():
+// request i tries up to max_attempts positions uniform in its spawn box and keeps the first that passes
+// ValidSpawnLocation; the goal is uniform in its goal box.  Every draw is a pure function of (seed, counter, i, attempt),
+// so a run is reproducible whatever the batching; the STREAM differs from rand()'s, i.e. parity with the reference is
+// statistical only.
+__device__ __forceinline__ float spawn_u01(unsigned long long seed, unsigned long long counter, unsigned i, unsigned k) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (counter + 1ull) + 0xD1B54A32D192ED03ull * (unsigned long long)i + 0x8CB92BA72F3D8DD7ull * (unsigned long long)k;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;  // splitmix64 finaliser
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(z >> 40) * (1.0f / 16777216.0f);  // 24 bits: [0, 1)
+}
+
+__global__ void __launch_bounds__(128) k_draw_spawns(GridView g, int n, const float4* __restrict__ spawn_box, const float4* __restrict__ goal_box,
+                                                      const float* __restrict__ clearance, unsigned long long seed, unsigned long long counter,
+                                                      int max_attempts, float2* __restrict__ out_start, float2* __restrict__ out_goal,
+                                                      unsigned char* __restrict__ out_ok) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 sb = spawn_box[i], gb = goal_box[i];  // xmin ymin xmax ymax
+    const float c = clearance[i];
+    bool ok = false;
+    v2 start = V(sb.x, sb.y);
+    for (int a = 0; a < max_attempts && !ok; a++) {
+        start = V(sb.x + spawn_u01(seed, counter, (unsigned)i, 2u * a) * (sb.z - sb.x), sb.y + spawn_u01(seed, counter, (unsigned)i, 2u * a + 1u) * (sb.w - sb.y));
+        ok = g.n_sorted == 0 || spawn_location_valid(g, start, c);
+    }
+    out_start[i] = start;
+    out_goal[i] = V(gb.x + spawn_u01(seed, counter, (unsigned)i, 0x10000u) * (gb.z - gb.x), gb.y + spawn_u01(seed, counter, (unsigned)i, 0x10001u) * (gb.w - gb.y));
+    out_ok[i] = ok ? 1 : 0;
 }
 
 __global__ void k_find_obstacles(ObstView ob, BinView bins, float2 pos, float range2, int* out, int cap, int* out_n) {

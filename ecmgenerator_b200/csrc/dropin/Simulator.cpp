@@ -136,6 +136,11 @@ void Simulator::UpdatePath(const Entity& e, const Point& location, const Point& 
 int Simulator::SpawnAgent(const Point& start, const Point& goal, float clearance, float preferredSpeed) {  // Simulator.cpp:168-200
     if (free_slots_.empty()) return -1;
     if (!ValidSpawnLocation(start, clearance)) return -1;
+    return SpawnChecked(start, goal, clearance, preferredSpeed);
+}
+
+int Simulator::SpawnChecked(const Point& start, const Point& goal, float clearance, float preferredSpeed) {
+    if (free_slots_.empty()) return -1;
     std::vector<ecmb200::P2f> path;
     if (!planner_->FindPath(ecmb200::P2f{start.x, start.y}, ecmb200::P2f{goal.x, goal.y}, clearance, path) || path.size() < 2) return -1;
     count_++;
@@ -162,6 +167,7 @@ int Simulator::SpawnAgent(const Point& start, const Point& goal, float clearance
     vel_[idx].dx = vel_[idx].dy = 0.0f;
     attraction_[idx].x = attraction_[idx].y = 0.0f;
     nbr_valid_ = false;
+    spawned_this_tick_.push_back(start);
     return idx;
 }
 
@@ -200,7 +206,64 @@ void Simulator::TrimLastSlot() {  // Simulator.cpp:481-492
     last_slot_ = last_slot_ - emptyCounter;
 }
 
-void Simulator::RunSpawnAreas() {  // Simulator.cpp:494-536
+// ---- rand() checkpoints ------------------------------------------------------------------------------------------
+// glibc's rand() is random() on a state array that setstate(3) can switch: swapping to a scratch state hands out the address
+// of the live one and writes its read position into its first word, so a memcpy of the array IS the generator.
+namespace {
+#if defined(__GLIBC__)
+struct RandCheckpoint {
+    unsigned char data[256];
+    size_t bytes = 0;
+};
+char* ScratchRandState() {
+    static char scratch[128];
+    static bool ready = false;
+    if (!ready) {
+        char* live = initstate(1u, scratch, sizeof(scratch));  // initialises `scratch` and switches to it ...
+        setstate(live);                                        // ... so switch straight back
+        ready = true;
+    }
+    return scratch;
+}
+size_t RandStateBytes(const char* state) {
+    int32_t word0;
+    memcpy(&word0, state, 4);
+    static const size_t kBytes[5] = {8, 32, 64, 128, 256};  // TYPE_0 .. TYPE_4 (stdlib/random_r.c)
+    return kBytes[((word0 % 5) + 5) % 5];
+}
+bool SaveRand(RandCheckpoint& cp) {
+    char* live = setstate(ScratchRandState());
+    if (!live) return false;
+    cp.bytes = RandStateBytes(live);
+    memcpy(cp.data, live, cp.bytes);
+    setstate(live);
+    return true;
+}
+void RestoreRand(const RandCheckpoint& cp) {
+    char* live = setstate(ScratchRandState());
+    memcpy(live, cp.data, cp.bytes);
+    setstate(live);
+}
+constexpr bool kRandCheckpoints = true;
+#else
+struct RandCheckpoint {};
+bool SaveRand(RandCheckpoint&) { return false; }
+void RestoreRand(const RandCheckpoint&) {}
+constexpr bool kRandCheckpoints = false;
+#endif
+}  // namespace
+
+bool Simulator::ClashesWithThisTick(const Point& p, float clearance) const {
+    const float c2 = clearance * clearance;
+    for (const Point& q : spawned_this_tick_) {
+        const float dx = p.x - q.x, dy = p.y - q.y;
+        if (dx * dx + dy * dy < c2) return true;  // the expression of ValidSpawnLocation (Simulator.cpp:303-306)
+    }
+    return false;
+}
+
+// The reference's loop, attempt by attempt on the host mirrors (Simulator.cpp:494-536).
+void Simulator::RunSpawnAreasSequential() {
     for (auto iter = spawn_areas_.begin(); iter != spawn_areas_.end(); iter++) {
         SpawnArea& area = iter->second;
         for (int ga = 0; ga < (int)area.connectedGoalAreas.size(); ga++) {
@@ -215,6 +278,7 @@ void Simulator::RunSpawnAreas() {  // Simulator.cpp:494-536
                 for (int spawnAttempts = 0; spawnAttempts < maxSpawnAttempts; spawnAttempts++) {
                     start = area.GetRandomPositionInArea();
                     foundValidLocation = ValidSpawnLocation(start, clearance);
+                    spawn_checks_host_++;
                     if (foundValidLocation) break;
                 }
                 if (!foundValidLocation) {
@@ -226,6 +290,111 @@ void Simulator::RunSpawnAreas() {  // Simulator.cpp:494-536
             }
             area.timeSinceLastSpawn[ga] -= (float)agentsToSpawn / area.spawnRate[ga];
         }
+    }
+}
+
+void Simulator::RunSpawnAreas() {  // Simulator.cpp:494-536
+    spawned_this_tick_.clear();
+    if (spawn_mode_ == SPAWN_RAND_SEQUENTIAL || (spawn_mode_ == SPAWN_RAND_BATCHED && !kRandCheckpoints)) {
+        RunSpawnAreasSequential();
+        return;
+    }
+    // The requests of a tick - which area, towards which goal area, how many - do not depend on any random number or
+    // validity test: only the DRAWS do.  Collect them in the reference's order, then answer them in batches.
+    std::vector<SpawnRequest> req;
+    for (auto iter = spawn_areas_.begin(); iter != spawn_areas_.end(); iter++) {
+        SpawnArea& area = iter->second;
+        for (int ga = 0; ga < (int)area.connectedGoalAreas.size(); ga++) {
+            area.timeSinceLastSpawn[ga] += tick_seconds_;
+            int agentsToSpawn = area.timeSinceLastSpawn[ga] * area.spawnRate[ga];
+            for (int i = 0; i < agentsToSpawn; i++)
+                req.push_back(SpawnRequest{&area, area.connectedGoalAreas[ga], area.spawnConfiguration.clearanceMin, area.spawnConfiguration.preferredSpeedMin});
+            area.timeSinceLastSpawn[ga] -= (float)agentsToSpawn / area.spawnRate[ga];
+        }
+    }
+    if (req.empty()) return;
+    if (spawn_mode_ == SPAWN_DEVICE_COUNTER) RunSpawnRequestsOnDevice(req);
+    else RunSpawnRequestsBatched(req);
+}
+
+// rand() in the reference's order, validity on the GPU.  Speculation: every request succeeds at its first attempt, so the
+// stream is start(3 numbers), goal(3), start, goal, ...; all starts of the round are tested in ONE device call.  The
+// first request whose start turns out invalid stops the round: the generator goes back to the state right after that
+// start was drawn and the request is finished attempt by attempt (attempts 2 .. 10, one device test each), then the
+// next round begins.  Agents spawned earlier in the tick are not on the device yet when a batch is tested: the few of
+// them are compared on the host, with ValidSpawnLocation's own expression.
+void Simulator::RunSpawnRequestsBatched(const std::vector<SpawnRequest>& req) {
+    const int maxSpawnAttempts = 10;
+    size_t next = 0;
+    std::vector<Point> start, goal;
+    std::vector<RandCheckpoint> after_start;
+    std::vector<float> xy, cl;
+    std::vector<uint8_t> ok;
+    while (next < req.size()) {
+        const size_t m = req.size() - next;
+        start.resize(m); goal.resize(m); after_start.resize(m); xy.resize(2 * m); cl.resize(m); ok.assign(m, 0);
+        for (size_t k = 0; k < m; k++) {
+            const SpawnRequest& r = req[next + k];
+            start[k] = r.area->GetRandomPositionInArea();
+            SaveRand(after_start[k]);
+            goal[k] = goal_areas_[r.goalArea].GetRandomPositionInArea();
+            xy[2 * k] = start[k].x; xy[2 * k + 1] = start[k].y;
+            cl[k] = r.clearance;
+        }
+        Check(ecmgpu_valid_spawn_locations(gpu_, (int)m, xy.data(), cl.data(), ok.data()), "ecmgpu_valid_spawn_locations");
+        spawn_checks_device_ += (long long)m;
+        size_t k = 0;
+        for (; k < m; k++) {
+            const SpawnRequest& r = req[next + k];
+            if (!ok[k] || ClashesWithThisTick(start[k], r.clearance)) break;
+            SpawnChecked(start[k], goal[k], r.clearance, r.speed);
+        }
+        next += k;
+        if (k == m) break;
+        // request `next` failed its first attempt: everything drawn after its start is undone
+        const SpawnRequest& r = req[next];
+        RestoreRand(after_start[k]);
+        bool found = false;
+        Point s2;
+        for (int attempt = 1; attempt < maxSpawnAttempts && !found; attempt++) {
+            s2 = r.area->GetRandomPositionInArea();
+            const float p[2] = {s2.x, s2.y};
+            uint8_t v = 0;
+            Check(ecmgpu_valid_spawn_locations(gpu_, 1, p, &r.clearance, &v), "ecmgpu_valid_spawn_locations");
+            spawn_checks_device_++;
+            found = v != 0 && !ClashesWithThisTick(s2, r.clearance);
+        }
+        if (!found) {
+            printf("Could not find a valid spawn position in the spawn area!\n");
+        } else {
+            Point g2 = goal_areas_[r.goalArea].GetRandomPositionInArea();
+            SpawnChecked(s2, g2, r.clearance, r.speed);
+        }
+        next++;
+    }
+}
+
+// Draws from the counter-based generator on the device (ecmgpu_draw_spawns): one call per tick.
+void Simulator::RunSpawnRequestsOnDevice(const std::vector<SpawnRequest>& req) {
+    const size_t m = req.size();
+    std::vector<float> sb(4 * m), gb(4 * m), cl(m), s_xy(2 * m), g_xy(2 * m);
+    std::vector<uint8_t> ok(m, 0);
+    for (size_t k = 0; k < m; k++) {
+        const Area& a = *req[k].area;
+        const Area& g = goal_areas_[req[k].goalArea];
+        sb[4 * k] = a.Position.x - a.HalfWidth; sb[4 * k + 1] = a.Position.y - a.HalfHeight;
+        sb[4 * k + 2] = a.Position.x + a.HalfWidth; sb[4 * k + 3] = a.Position.y + a.HalfHeight;
+        gb[4 * k] = g.Position.x - g.HalfWidth; gb[4 * k + 1] = g.Position.y - g.HalfHeight;
+        gb[4 * k + 2] = g.Position.x + g.HalfWidth; gb[4 * k + 3] = g.Position.y + g.HalfHeight;
+        cl[k] = req[k].clearance;
+    }
+    Check(ecmgpu_draw_spawns(gpu_, (int)m, sb.data(), gb.data(), cl.data(), spawn_seed_, spawn_counter_++, 10, s_xy.data(), g_xy.data(), ok.data()),
+          "ecmgpu_draw_spawns");
+    spawn_checks_device_ += (long long)m;
+    for (size_t k = 0; k < m; k++) {
+        const Point s(s_xy[2 * k], s_xy[2 * k + 1]), g(g_xy[2 * k], g_xy[2 * k + 1]);
+        if (!ok[k] || ClashesWithThisTick(s, req[k].clearance)) continue;  // dropped, like a request that found no valid position
+        SpawnChecked(s, g, req[k].clearance, req[k].speed);
     }
 }
 

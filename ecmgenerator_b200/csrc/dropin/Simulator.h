@@ -3,10 +3,10 @@
 // meaning, slot allocation order and error behaviour; the per-tick systems run on the GPU through
 // the C ABI of include/ecm_b200.h.  C++17, no CUDA headers needed to use it.
 //
-// What stays on the host, exactly like the reference: the free-slot stack (Simulator.h:66-69),
-// ValidSpawnLocation's O(N) scan (Simulator.cpp:295-311), spawn areas with C rand()
-// (Area.h:39-53, Simulator.cpp:494-536), global path planning on spawn / replan
-// (Simulator.cpp:97-124) through ecmb200::PathPlanner.
+// What stays on the host, exactly like the reference: the free-slot stack (Simulator.h:66-69), spawn areas drawing from
+// C rand() in the reference's order (Area.h:39-53, Simulator.cpp:494-536; their validity tests run on the GPU in batches,
+// see SetSpawnMode), global path planning on spawn / replan (Simulator.cpp:97-124) through ecmb200::PathPlanner.
+// ValidSpawnLocation as a public query keeps the reference's O(N) scan over the host mirrors (Simulator.cpp:295-311).
 //
 // Differences from the reference, all at points where the reference has undefined behaviour:
 //   * a failed path query keeps the agent's previous path (the reference stores a 0-point path and
@@ -71,6 +71,21 @@ public:
     void Update(float ignored);  // the constructor's step is used, like the reference (Simulator.cpp:314-323)
     void Reset();
 
+    // ---- how the spawn areas run (Simulator::UpdateSpawnAreas, Simulator.cpp:494-536)
+    //   SPAWN_RAND_BATCHED (default): C rand() consumed in exactly the reference's order - same slots, same positions -
+    //       but the ValidSpawnLocation tests of a tick go to the GPU in batches (ecmgpu_valid_spawn_locations on the
+    //       neighbour grid) instead of one O(N) host scan per attempt.  The draws of a batch assume every first attempt
+    //       succeeds; where one does not, the generator is rewound to that point (glibc: rand()'s state is switchable,
+    //       setstate(3)) and that request is finished attempt by attempt.  Without glibc it degrades to SEQUENTIAL.
+    //   SPAWN_RAND_SEQUENTIAL: the reference's loop as it is, one host scan per attempt.
+    //   SPAWN_DEVICE_COUNTER: draws from a counter-based generator ON the device (ecmgpu_draw_spawns); reproducible for a
+    //       seed, NOT the rand() stream - parity with the reference is statistical only.
+    enum SpawnMode { SPAWN_RAND_BATCHED = 0, SPAWN_RAND_SEQUENTIAL = 1, SPAWN_DEVICE_COUNTER = 2 };
+    void SetSpawnMode(SpawnMode mode, unsigned long long seed = 0) { spawn_mode_ = mode; spawn_seed_ = seed; }
+    // spawn attempts answered by the GPU / by the host scan since construction (what the batching saved)
+    long long SpawnChecksOnDevice() const { return spawn_checks_device_; }
+    long long SpawnChecksOnHost() const { return spawn_checks_host_; }
+
     // ---- agents
     int SpawnAgent(const Point& from, const Point& to, float radius, float speed);
     void DestroyAgent(int slot);
@@ -107,6 +122,12 @@ private:
     void ReleaseAll();
     void TrimLastSlot();
     void RunSpawnAreas();
+    void RunSpawnAreasSequential();
+    struct SpawnRequest { SpawnArea* area; int goalArea; float clearance, speed; };
+    void RunSpawnRequestsBatched(const std::vector<SpawnRequest>& req);
+    void RunSpawnRequestsOnDevice(const std::vector<SpawnRequest>& req);
+    int SpawnChecked(const Point& from, const Point& to, float radius, float speed);  // SpawnAgent after a validity test already made
+    bool ClashesWithThisTick(const Point& p, float clearance) const;
     void StoreRoute(int slot, const std::vector<ecmb200::P2f>& polyline);
     void Check(int rc, const char* what);
 
@@ -137,6 +158,11 @@ private:
     ClearanceComponent* radius_ = nullptr;
     SpeedComponent* pref_speed_ = nullptr;
     PathComponent* routes_ = nullptr;
+
+    SpawnMode spawn_mode_ = SPAWN_RAND_BATCHED;
+    unsigned long long spawn_seed_ = 0, spawn_counter_ = 0;
+    long long spawn_checks_device_ = 0, spawn_checks_host_ = 0;
+    std::vector<Point> spawned_this_tick_;  // agents spawned since the device positions the batch tests ran on
 
     bool nbr_valid_ = false;
     std::vector<int> nbr_ids_, nbr_counts_;

@@ -111,6 +111,8 @@ int ecmsim_add_spawn_area(void* h, float x, float y, float hw, float hh, float c
     return ((SimBox*)h)->sim->AddSpawnArea(Point(x, y), Vec2(hw, hh), cfg);
 }
 int ecmsim_add_goal_area(void* h, float x, float y, float hw, float hh) { return ((SimBox*)h)->sim->AddGoalArea(Point(x, y), Vec2(hw, hh)); }
+void ecmsim_set_spawn_mode(void* h, int mode, unsigned long long seed) { ((SimBox*)h)->sim->SetSpawnMode((Simulator::SpawnMode)mode, seed); }
+void ecmsim_spawn_checks(void* h, long long out[2]) { out[0] = ((SimBox*)h)->sim->SpawnChecksOnDevice(); out[1] = ((SimBox*)h)->sim->SpawnChecksOnHost(); }
 void ecmsim_connect_areas(void* h, int spawn_id, int goal_id, float rate) { ((SimBox*)h)->sim->ConnectSpawnGoalAreas(spawn_id, goal_id, rate); }
 int ecmsim_add_obstacle_area(void* h, float x, float y, float hw, float hh, int update_ecm) {
     GUARD(return ((SimBox*)h)->sim->AddObstacleArea(Point(x, y), Vec2(hw, hh), update_ecm != 0), -2)

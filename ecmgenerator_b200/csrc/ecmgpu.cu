@@ -117,7 +117,7 @@ struct ecmgpu_sim {
     int gw = 0, gh = 0, ncells_padded = 0;
     float gx0 = 0, gy0 = 0;
     bool grid_dirty = true;
-    DevBuf<int> d_key, d_rank, d_cell_count, d_block_sums, d_s_slot, d_fb_list, d_ev_replan, d_ev_destroyed;
+    DevBuf<int> d_key, d_rank, d_cell_count, d_s_slot, d_fb_list, d_ev_replan, d_ev_destroyed;
     // LP3D queue (orca.cuh Lp3dQueue): one row per slot, 32 + 16 * kMaxCons bytes each
     DevBuf<int4> d_lp3d_hdr;
     DevBuf<float4> d_lp3d_out, d_lp3d_cs;
@@ -125,7 +125,8 @@ struct ecmgpu_sim {
     DevBuf<float2> d_s_pos, d_s_vel, d_s_pref;
     DevBuf<float> d_s_rad, d_s_spd;
     DevBuf<unsigned char> d_s_alive;
-    DevBuf<unsigned long long> d_counters;
+    DevBuf<unsigned long long> d_counters, d_scan_state;  // scan: one look-back word per tile of 4096 cells
+    DevBuf<unsigned> d_scan_ctl;                          // scan: epoch, finished tiles, next ticket
 
     // ---- multi-GPU strips (device/strips.cuh)
     bool strips_on = false;
@@ -476,7 +477,14 @@ int build_grid(ecmgpu_sim* s) {
     const int ncells = s->gw * s->gh;
     s->ncells_padded = div_up(ncells + 1, kScanTile) * kScanTile;
     CUDA_TRY(s, s->d_cell_count.alloc(s->ncells_padded));
-    CUDA_TRY(s, s->d_block_sums.alloc(s->ncells_padded / kScanTile));
+    CUDA_TRY(s, s->d_scan_state.alloc(s->ncells_padded / kScanTile));
+    CUDA_TRY(s, cudaMemsetAsync(s->d_scan_state.p, 0, sizeof(unsigned long long) * s->d_scan_state.n, s->stream));
+    if (!s->d_scan_ctl.p) {
+        CUDA_TRY(s, s->d_scan_ctl.alloc(4));
+        const unsigned ctl0[4] = {1u, 0u, 0u, 0u};  // epoch 1: zeroed states read as "an earlier launch"
+        CUDA_TRY(s, cudaMemcpyAsync(s->d_scan_ctl.p, ctl0, sizeof(ctl0), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    }
     s->grid_dirty = false;
     s->config_epoch++;
     return ECMGPU_OK;
@@ -543,7 +551,6 @@ TickView make_view(ecmgpu_sim* s) {
     t.sc.key = s->d_key.p;
     t.sc.rank = s->d_rank.p;
     t.sc.cell_count = s->d_cell_count.p;
-    t.sc.block_sums = s->d_block_sums.p;
     t.sc.s_pos = s->d_s_pos.p;
     t.sc.s_vel = s->d_s_vel.p;
     t.sc.s_rad = s->d_s_rad.p;
@@ -769,24 +776,27 @@ int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
     CUDA_TRY(s, cudaMemsetAsync(s->d_counters.p + C_FALLBACK_N, 0, 2 * sizeof(unsigned long long), s->stream));
     const int nb = div_up(s->n_slots, 256);
     StripView sv = make_strip_view(s);
-    if (sv.walk.list) k_bin_count_walk<<<kSMs * 8, 256, 0, s->stream>>>(sv.walk, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p, s->d_status.p, s->d_counters.p);
-    else k_bin_count<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p, s->d_status.p, s->d_counters.p);
     const int ng = 2 * s->cap_halo + s->cap_self;
-    if (s->strips_on) {
-        k_ghost_count<<<div_up(ng, 256), 256, 0, s->stream>>>(sv, gp, s->d_cell_count.p);
-        s->launches++;
+    // compact strips: the list-walking kernels take the ghosts along (one launch each instead of two)
+    if (sv.walk.list) k_bin_count_walk<<<kSMs * 8, 256, 0, s->stream>>>(sv, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p, s->d_status.p, s->d_counters.p);
+    else {
+        k_bin_count<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p, s->d_status.p, s->d_counters.p);
+        if (s->strips_on) {
+            k_ghost_count<<<div_up(ng, 256), 256, 0, s->stream>>>(sv, gp, s->d_cell_count.p);
+            s->launches++;
+        }
     }
     const int tiles = s->ncells_padded / kScanTile;
-    k_scan_tiles<<<tiles, kScanBlock, 0, s->stream>>>((int4*)s->d_cell_count.p, s->d_block_sums.p);
-    k_scan_sums<<<1, kScanBlock, 0, s->stream>>>(s->d_block_sums.p, tiles);
-    k_scan_add<<<tiles, kScanBlock, 0, s->stream>>>((int4*)s->d_cell_count.p, s->d_block_sums.p);
-    if (sv.walk.list) k_scatter_walk<<<kSMs * 8, 256, 0, s->stream>>>(sv.walk, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc);
-    else k_scatter<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc);
-    if (s->strips_on) {
-        k_ghost_scatter<<<div_up(ng, 256), 256, 0, s->stream>>>(sv, s->d_cell_count.p, t.ag, t.sc, s->d_s_ghost.p);
-        s->launches++;
+    k_scan_onepass<<<tiles, kScanBlock, 0, s->stream>>>((int4*)s->d_cell_count.p, tiles, s->d_scan_state.p, s->d_scan_ctl.p);
+    if (sv.walk.list) k_scatter_walk<<<kSMs * 8, 256, 0, s->stream>>>(sv, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc);
+    else {
+        k_scatter<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc);
+        if (s->strips_on) {
+            k_ghost_scatter<<<div_up(ng, 256), 256, 0, s->stream>>>(sv, s->d_cell_count.p, t.ag, t.sc);
+            s->launches++;
+        }
     }
-    s->launches += 5;
+    s->launches += 3;
     CUDA_TRY(s, cudaGetLastError());
     return ECMGPU_OK;
 }
@@ -1135,7 +1145,7 @@ void ecmgpu_destroy(ecmgpu_sim* s) {
     s->d_pos.free(); s->d_vel.free(); s->d_prefvel.free(); s->d_attraction.free(); s->d_force.free();
     s->d_radius.free(); s->d_speed.free(); s->d_active.free(); s->d_replan_pending.free(); s->d_status.free();
     s->d_cell.free(); s->d_nbr.free(); s->d_nbr_cnt.free(); s->d_path_hdr.free(); s->d_path_pool.free(); s->d_path_bbox.free();
-    s->d_key.free(); s->d_rank.free(); s->d_cell_count.free(); s->d_block_sums.free(); s->d_s_slot.free();
+    s->d_key.free(); s->d_rank.free(); s->d_cell_count.free(); s->d_scan_state.free(); s->d_scan_ctl.free(); s->d_s_slot.free();
     s->d_lp3d_hdr.free(); s->d_lp3d_out.free(); s->d_lp3d_cs.free();
     s->d_fb_list.free(); s->d_ev_replan.free(); s->d_ev_destroyed.free(); s->d_s_pos.free(); s->d_s_vel.free();
     s->d_s_pref.free(); s->d_s_rad.free(); s->d_s_spd.free(); s->d_s_alive.free(); s->d_counters.free();
@@ -1965,6 +1975,49 @@ int ecmgpu_valid_spawn_locations(ecmgpu_sim* s, int n, const float* xy, const fl
     CUDA_TRY(s, cudaMemcpyAsync(out_valid, d_out.p, (size_t)n, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     d_xy.free(); d_c.free(); d_out.free();
+    return ECMGPU_OK;
+}
+
+int ecmgpu_draw_spawns(ecmgpu_sim* s, int n, const float* spawn_boxes, const float* goal_boxes, const float* clearance, uint64_t seed, uint64_t counter,
+                       int max_attempts, float* out_start_xy, float* out_goal_xy, uint8_t* out_ok) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (n < 0 || max_attempts < 1 || (n > 0 && (!spawn_boxes || !goal_boxes || !clearance || !out_start_xy || !out_goal_xy || !out_ok)))
+        return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_draw_spawns: bad arguments");
+    if (n == 0) return ECMGPU_OK;
+    CUDA_TRY(s, cudaSetDevice(s->prm.device));
+    if (s->strips_on && s->local_transport && s->n_ranks > 1)
+        return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_draw_spawns is not available with in-process strips");
+    TickView t = make_view(s);
+    t.grid.n_sorted = 0;  // no crowd yet: every draw is valid
+    if (s->n_slots > 0) {
+        int rc = ensure_ready(s);
+        if (rc) return rc;
+        t = make_view(s);
+        if (s->strips_on) {
+            rc = enqueue_pack(s, t);
+            if (rc) return rc;
+            rc = enqueue_exchange(s, t);
+            if (rc) return rc;
+        }
+        rc = enqueue_grid_build(s, t);
+        if (rc) return rc;
+        t.grid.n_sorted = 1;  // "there is a snapshot": the kernel only tests for zero
+    }
+    DevBuf<float4> d_sb, d_gb;
+    DevBuf<float> d_c;
+    DevBuf<float2> d_start, d_goal;
+    DevBuf<unsigned char> d_ok;
+    CUDA_TRY(s, d_sb.alloc(n)); CUDA_TRY(s, d_gb.alloc(n)); CUDA_TRY(s, d_c.alloc(n)); CUDA_TRY(s, d_start.alloc(n)); CUDA_TRY(s, d_goal.alloc(n)); CUDA_TRY(s, d_ok.alloc(n));
+    CUDA_TRY(s, cudaMemcpyAsync(d_sb.p, spawn_boxes, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(d_gb.p, goal_boxes, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(d_c.p, clearance, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+    k_draw_spawns<<<div_up(n, 128), 128, 0, s->stream>>>(t.grid, n, d_sb.p, d_gb.p, d_c.p, seed, counter, max_attempts, d_start.p, d_goal.p, d_ok.p);
+    s->launches++;
+    CUDA_TRY(s, cudaGetLastError());
+    CUDA_TRY(s, cudaMemcpyAsync(out_start_xy, d_start.p, sizeof(float2) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(out_goal_xy, d_goal.p, sizeof(float2) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaMemcpyAsync(out_ok, d_ok.p, (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     return ECMGPU_OK;
 }
 

@@ -48,6 +48,8 @@ def lib():
         L.ecmsim_find_neighbors.argtypes = [vp, C.c_int, i32p]
         L.ecmsim_find_obstacles.argtypes = [vp, C.c_int, C.c_float, i32p, C.c_int]
         L.ecmsim_add_spawn_area.argtypes = [vp] + [C.c_float] * 6
+        L.ecmsim_set_spawn_mode.argtypes = [vp, C.c_int, C.c_uint64]
+        L.ecmsim_spawn_checks.argtypes = [vp, C.POINTER(C.c_longlong)]
         L.ecmsim_add_goal_area.argtypes = [vp] + [C.c_float] * 4
         L.ecmsim_connect_areas.argtypes = [vp, C.c_int, C.c_int, C.c_float]
         L.ecmsim_add_obstacle_area.argtypes = [vp] + [C.c_float] * 4 + [C.c_int]
@@ -141,6 +143,19 @@ class Simulator:
 
     def add_goal_area(self, pos, half) -> int:
         return self.L.ecmsim_add_goal_area(self.h, float(pos[0]), float(pos[1]), float(half[0]), float(half[1]))
+
+    SPAWN_RAND_BATCHED, SPAWN_RAND_SEQUENTIAL, SPAWN_DEVICE_COUNTER = 0, 1, 2
+
+    def set_spawn_mode(self, mode: int, seed: int = 0):
+        """Simulator::SetSpawnMode: rand() in the reference's order with GPU validity batches (default), the reference's
+        own loop, or the counter-based generator on the device."""
+        self.L.ecmsim_set_spawn_mode(self.h, int(mode), int(seed))
+
+    def spawn_checks(self):
+        """(validity tests answered by the GPU, by the host scan) since construction."""
+        out = (C.c_longlong * 2)()
+        self.L.ecmsim_spawn_checks(self.h, out)
+        return int(out[0]), int(out[1])
 
     def connect_areas(self, spawn_id, goal_id, rate):
         self.L.ecmsim_connect_areas(self.h, int(spawn_id), int(goal_id), float(rate))

@@ -39,7 +39,7 @@ EXPORTS = [
     "ecmgpu_locate", "ecmgpu_retract", "ecmgpu_find_neighbors", "ecmgpu_find_obstacles", "ecmgpu_get_stats",
     "ecmgpu_last_tick_ms", "ecmgpu_set_profiling", "ecmgpu_mark", "ecmgpu_mark_elapsed_ms", "ecmgpu_stream", "ecmgpu_comm_unique_id", "ecmgpu_comm_init",
     "ecmgpu_comm_set_strips", "ecmgpu_comm_init_local", "ecmgpu_update_phase", "ecmgpu_update_io", "ecmgpu_update_io_owned", "ecmgpu_io_wait", "ecmgpu_comm_p2p_export", "ecmgpu_comm_p2p_connect",
-    "ecmgpu_set_neighbor_mode", "ecmgpu_valid_spawn_locations", "ecmgpu_set_ecm_topology", "ecmgpu_plan_paths",
+    "ecmgpu_set_neighbor_mode", "ecmgpu_valid_spawn_locations", "ecmgpu_draw_spawns", "ecmgpu_set_ecm_topology", "ecmgpu_plan_paths",
     "ecmgpu_abi_sizes",
 ]
 
@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
         L.ecmgpu_io_wait.argtypes = [vp, C.c_uint64]
         L.ecmgpu_set_neighbor_mode.argtypes = [vp, C.c_int]
         L.ecmgpu_valid_spawn_locations.argtypes = [vp, C.c_int, f32p, f32p, u8p]
+        L.ecmgpu_draw_spawns.argtypes = [vp, C.c_int, f32p, f32p, f32p, C.c_uint64, C.c_uint64, C.c_int, f32p, f32p, u8p]
         L.ecmgpu_set_ecm_topology.argtypes = [vp, i32p, i32p]
         L.ecmgpu_abi_sizes.argtypes = [i32p]
         L.ecmgpu_abi_sizes.restype = None
@@ -382,6 +383,16 @@ class GpuSim:
         out = np.zeros(len(xy), np.uint8)
         self._ck(self.L.ecmgpu_valid_spawn_locations(self.h, len(xy), _p(xy, f32p), _p(cl, f32p), _p(out, u8p)))
         return out
+
+    def draw_spawns(self, spawn_boxes, goal_boxes, clearance, seed: int, counter: int, max_attempts: int = 10):
+        """Spawn draws with the counter-based generator on the device (ecmgpu_draw_spawns): (start[n,2], goal[n,2], ok[n])."""
+        sb = np.ascontiguousarray(spawn_boxes, np.float32).reshape(-1, 4)
+        gb = np.ascontiguousarray(goal_boxes, np.float32).reshape(-1, 4)
+        cl = np.ascontiguousarray(np.broadcast_to(np.asarray(clearance, np.float32), (len(sb),)))
+        start, goal, ok = np.zeros((len(sb), 2), np.float32), np.zeros((len(sb), 2), np.float32), np.zeros(len(sb), np.uint8)
+        self._ck(self.L.ecmgpu_draw_spawns(self.h, len(sb), _p(sb, f32p), _p(gb, f32p), _p(cl, f32p), int(seed), int(counter), int(max_attempts),
+                                           _p(start, f32p), _p(goal, f32p), _p(ok, u8p)))
+        return start, goal, ok
 
     def set_neighbor_mode(self, mode: int):
         """NEIGHBORS_EXACT (default) or NEIGHBORS_KDTREE: the reference's own KD-tree lists (parity mode)."""

@@ -178,6 +178,16 @@ int ecmgpu_find_obstacles(ecmgpu_sim* sim, int slot, int* out_ids, int cap, int*
  * (owned + halo), and - like ecmgpu_find_neighbors - a collective call: every rank runs the halo exchange. */
 int ecmgpu_valid_spawn_locations(ecmgpu_sim* sim, int n, const float* xy, const float* clearance, uint8_t* out_valid);
 
+/* Simulator::UpdateSpawnAreas' draws (Simulator.cpp:501-527, Area::GetRandomPositionInArea Area.h:39-53) on the device with
+ * a counter-based generator instead of C rand() - opt-in, for hosts that do not need the reference's rand() stream: request i
+ * tries up to max_attempts positions uniform in spawn_boxes[4i..4i+3] (xmin ymin xmax ymax) and keeps the first that passes
+ * Simulator::ValidSpawnLocation on the CURRENT positions (out_ok[i] = 0: none did, out_start is the last try); its goal is
+ * uniform in goal_boxes[4i..]. Every draw is a pure function of (seed, counter, i, attempt): reproducible, independent of
+ * batching, NOT the reference's stream (parity is statistical).  Requests of one call do not see each other; the caller
+ * resolves those few conflicts in request order, as UpdateSpawnAreas does one by one.  Collective with strips. */
+int ecmgpu_draw_spawns(ecmgpu_sim* sim, int n, const float* spawn_boxes, const float* goal_boxes, const float* clearance, uint64_t seed,
+                       uint64_t counter, int max_attempts, float* out_start_xy, float* out_goal_xy, uint8_t* out_ok);
+
 /* -- batched path planning on the device -------------------------------------
  * The half-edge rings of the ECM graph, needed by the planner only: vert_he[v] = one half-edge leaving vertex v
  * (ECMVertex::half_edge_idx, ECM.h:41-47), he_next[h] = the next half-edge around h's source vertex

@@ -60,11 +60,12 @@ struct Emu {
     // grid + snapshot + scratch
     float gx0 = 0, gy0 = 0, gcell = 1;
     int gw = 1, gh = 1;
-    std::vector<int> key, rank, cell_count, block_sums, s_slot, fb_list, ev_replan, ev_destroyed;
+    std::vector<int> key, rank, cell_count, s_slot, fb_list, ev_replan, ev_destroyed;
     std::vector<float2> s_pos, s_vel, s_pref;
     std::vector<float> s_rad, s_spd;
     std::vector<unsigned char> s_alive, s_ghost;
-    std::vector<unsigned long long> counters;
+    std::vector<unsigned long long> counters, scan_state;
+    unsigned scan_ctl[4] = {1u, 0u, 0u, 0u};
     std::vector<int4> lp3d_hdr;
     std::vector<float4> lp3d_out, lp3d_cs;
     // strips
@@ -105,7 +106,7 @@ struct Emu {
         t.ag.replan_pending = replan_pending.data(); t.ag.status = status.data(); t.ag.cell = cell.data();
         t.ag.nbr = nbr.data(); t.ag.nbr_cnt = nbr_cnt.data();
         t.ag.path_hdr = path_hdr.data(); t.ag.path_pool = path_pool.data(); t.ag.path_bbox = path_bbox.data();
-        t.sc.key = key.data(); t.sc.rank = rank.data(); t.sc.cell_count = cell_count.data(); t.sc.block_sums = nullptr;
+        t.sc.key = key.data(); t.sc.rank = rank.data(); t.sc.cell_count = cell_count.data();
         t.sc.s_pos = s_pos.data(); t.sc.s_vel = s_vel.data(); t.sc.s_rad = s_rad.data(); t.sc.s_spd = s_spd.data();
         t.sc.s_slot = s_slot.data(); t.sc.s_pref = s_pref.data(); t.sc.s_alive = s_alive.data(); t.sc.s_ghost = s_ghost.data();
         t.sc.fb_list = fb_list.data(); t.sc.ev_replan = ev_replan.data(); t.sc.ev_destroyed = ev_destroyed.data(); t.sc.ev_cap = (int)ev_destroyed.size();
@@ -151,14 +152,12 @@ struct Emu {
     }
 };
 
-// Exclusive scan of the cell counts in place, total behind the last cell.  SIMT build: the three scan kernels
-// themselves (tick.cuh), launched like enqueue_grid_build does; plain build: a host prefix sum stands in.
+// Exclusive scan of the cell counts in place, total behind the last cell.  SIMT build: the scan kernel
+// itself (tick.cuh), launched like enqueue_grid_build does; plain build: a host prefix sum stands in.
 static void emu_scan_cells(Emu* e) {
 #ifdef HD_SIMT
     const int tiles = (int)(e->cell_count.size() / kScanTile);
-    launch(tiles * kScanBlock, [&] { k_scan_tiles((int4*)e->cell_count.data(), e->block_sums.data()); }, kScanBlock);
-    launch(kScanBlock, [&] { k_scan_sums(e->block_sums.data(), tiles); }, kScanBlock);
-    launch(tiles * kScanBlock, [&] { k_scan_add((int4*)e->cell_count.data(), e->block_sums.data()); }, kScanBlock);
+    launch(tiles * kScanBlock, [&] { k_scan_onepass((int4*)e->cell_count.data(), tiles, e->scan_state.data(), e->scan_ctl); }, kScanBlock);
 #else
     int run = 0;
     for (size_t c = 0; c < (size_t)e->gw * e->gh + 1; c++) { int v = e->cell_count[c]; e->cell_count[c] = run; run += v; }
@@ -201,7 +200,7 @@ void* emu_create(int nV, const float* vert_xy, int nE, const int* edge_v, const 
     e->path_hdr.assign(n, PathHdr{0, 0, 0.0f, 0.0f});
     e->key.assign(n, -1); e->rank.assign(n, 0);
     const size_t padded = (((size_t)gw * gh + 1 + kScanTile - 1) / kScanTile) * kScanTile;  // ecmgpu.cu build_grid: ncells_padded
-    e->cell_count.assign(padded, 0); e->block_sums.assign(padded / kScanTile, 0);
+    e->cell_count.assign(padded, 0); e->scan_state.assign(padded / kScanTile, 0ull);
     e->counters.assign(C_COUNT, 0ull);
     e->ev_replan.assign(n, 0); e->ev_destroyed.assign(n, 0);
     e->lp3d_hdr.resize(n); e->lp3d_out.resize(n); e->lp3d_cs.resize((size_t)n * kMaxCons);
@@ -311,14 +310,14 @@ int emu_tick(void* h) {
     GridParams gp{e->gx0, e->gy0, e->gcell, 1.0f / e->gcell, e->gw, e->gh};
     std::fill(e->cell_count.begin(), e->cell_count.end(), 0);
     e->counters[C_FALLBACK_N] = 0; e->counters[C_LP3D_N] = 0;
-    if (sv.walk.list) launch(53, [&] { k_bin_count_walk(sv.walk, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data(), e->status.data(), e->counters.data()); }, 256);
+    if (sv.walk.list) launch(53, [&] { k_bin_count_walk(sv, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data(), e->status.data(), e->counters.data()); }, 256);
     else launch(e->n_slots, [&] { k_bin_count(e->n_slots, e->active.data(), e->pos.data(), gp, e->cell_count.data(), e->key.data(), e->rank.data(), e->status.data(), e->counters.data()); }, 256);
     const int ng = 2 * e->cap_halo + e->cap_self;
-    if (e->strips) launch(ng, [&] { k_ghost_count(sv, gp, e->cell_count.data()); }, 256);
+    if (e->strips && !sv.walk.list) launch(ng, [&] { k_ghost_count(sv, gp, e->cell_count.data()); }, 256);
     emu_scan_cells(e);
-    if (sv.walk.list) launch(53, [&] { k_scatter_walk(sv.walk, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc); }, 256);
+    if (sv.walk.list) launch(53, [&] { k_scatter_walk(sv, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc); }, 256);
     else launch(e->n_slots, [&] { k_scatter(e->n_slots, e->key.data(), e->rank.data(), e->cell_count.data(), t.ag, t.sc); }, 256);
-    if (e->strips) launch(ng, [&] { k_ghost_scatter(sv, e->cell_count.data(), t.ag, t.sc, e->s_ghost.data()); }, 256);
+    if (e->strips && !sv.walk.list) launch(ng, [&] { k_ghost_scatter(sv, e->cell_count.data(), t.ag, t.sc); }, 256);
     const int rows = e->n_slots + (e->strips ? ng : 0);
     if (sv.walk.list) {  // ecmgpu_update_phase: compact strips run the fixed-grid versions
         launch(41, [&] { k_attract_tiles(t); }, 128);

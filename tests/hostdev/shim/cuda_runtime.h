@@ -56,10 +56,13 @@ template <class T>
 static inline T __shfl_sync(unsigned, T v, int) { return v; }
 template <class T>
 static inline T __shfl_up_sync(unsigned, T v, int) { return v; }
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
 #endif
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __nanosleep(unsigned) { sched_yield(); }  // a spinning lane lets the other ranks' threads run
 
 template <class T, class U>

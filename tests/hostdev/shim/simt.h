@@ -173,6 +173,8 @@ static inline T __shfl_up_sync(unsigned, T v, int delta) {
     const int lane = hdsimt::my_lane();
     return hd_exchange(v, lane >= delta ? lane - delta : lane);  // lanes below delta keep their own value
 }
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int mask) { return hd_exchange(v, hdsimt::my_lane() ^ mask); }
 static inline unsigned __ballot_sync(unsigned, bool p) {
     hdsimt::Warp& w = hdsimt::my_warp();
     w.pred[hdsimt::my_lane()] = p ? 1 : 0;
