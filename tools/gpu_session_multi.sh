@@ -21,7 +21,7 @@ run_bench() {  # name, extra env, bench args...
 nvidia-smi -L >>"$OUT/${TAG}_session.log" 2>&1
 if [[ " ${*:3} " == *" tests "* ]]; then
   step "strips tests"
-  timeout 900 python -m pytest tests/test_gpu_strips.py tests/test_zz2_gpu_compact.py -m gpu -q -s >"$OUT/${TAG}_strips_tests.log" 2>&1
+  timeout 1200 python -m pytest tests -m gpu -q -s >"$OUT/${TAG}_strips_tests.log" 2>&1
   echo "pytest exit $?" | tee -a "$OUT/${TAG}_session.log"; tail -3 "$OUT/${TAG}_strips_tests.log"
 fi
 step "bench c3_1m x$N"
