@@ -346,7 +346,11 @@ def strips_parity(sim, w, c, off, pxy, ticks, rank, device):
     same_pos = bool(np.array_equal(pos1[a].view(np.uint32), p[a].view(np.uint32)))
     same_vel = bool(np.array_equal(vel1[a].view(np.uint32), v[a].view(np.uint32)))
     own1 = owner_of(pos1[:, 0], sim.bounds)
+    inner = np.asarray(sim.bounds[1:-1], np.float32)
+    near = int((np.abs(pos1[a][:, :1] - inner[None, :]).min(axis=1) < 1.0).sum()) if len(inner) else 0
+    dx = np.abs(pos1[a][:, 0] - state[gpu.POS][a][:, 0])
     return {"bitwise_vs_1gpu": same_owner and same_pos and same_vel, "ticks": int(ticks), "migrations": int(((own0 != own1) & a).sum()),
+            "agents_within_1m_of_a_border": near, "mean_abs_dx_m": float(dx.mean()),
             "agents_compared": int(a.sum()), "halo_misses_during": int(miss1 - miss0),
             "rows_differing": int((pos1[a].view(np.uint32) != p[a].view(np.uint32)).any(axis=1).sum()),
             "how": "global state gathered from the strips, loaded into a single simulator on rank 0; both advanced, positions / velocities / ownership compared bit for bit"}

@@ -1,8 +1,13 @@
 // C ABI of the host-side helpers (include/ecm_b200_host.h).
 #include "../../../include/ecm_b200_host.h"
 
+#include <algorithm>
+#include <cstring>
+#include <string>
+
 #include "flat_world.h"
 #include "lattice_world.h"
+#include "polygon_world.h"
 #include "planner.h"
 
 struct ecmhost_world {
@@ -21,6 +26,21 @@ ecmhost_world* ecmhost_lattice_world(int nbx, const float* bx, int nby, const fl
                                      float y0) {
     auto* h = new ecmhost_world();
     if (!bx || !by || !ecmb200::BuildLatticeWorld(nbx, bx, nby, by, W, x0, y0, h->w)) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+ecmhost_world* ecmhost_polygon_world(const float bbox[4], int n_polys, const int* poly_first, const float* poly_xy, char* error, int error_cap) {
+    auto* h = new ecmhost_world();
+    std::string msg;
+    if (!bbox || !ecmb200::BuildPolygonWorld(bbox, n_polys, poly_first, poly_xy, h->w, &msg)) {
+        if (error && error_cap > 0) {
+            const size_t m = std::min<size_t>(msg.size(), (size_t)error_cap - 1);
+            memcpy(error, msg.data(), m);
+            error[m] = 0;
+        }
         delete h;
         return nullptr;
     }

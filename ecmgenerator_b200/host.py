@@ -52,6 +52,8 @@ def lib() -> C.CDLL:
         L = C.CDLL(_LIB_PATH)
         L.ecmhost_lattice_world.restype = C.c_void_p
         L.ecmhost_lattice_world.argtypes = [C.c_int, c_float_p, C.c_int, c_float_p, C.c_float, C.c_float, C.c_float]
+        L.ecmhost_polygon_world.restype = C.c_void_p
+        L.ecmhost_polygon_world.argtypes = [c_float_p, C.c_int, c_int_p, c_float_p, C.c_char_p, C.c_int]
         L.ecmhost_world_from_arrays.restype = C.c_void_p
         L.ecmhost_world_from_arrays.argtypes = [C.POINTER(_WorldView)]
         L.ecmhost_world_free.argtypes = [C.c_void_p]
@@ -268,6 +270,50 @@ def lattice_world(blocks_x, blocks_y, street_width: float, x0: float = 0.0, y0: 
     finally:
         L.ecmhost_world_free(h)
     return w
+
+
+def _world_from_handle(L, h, **meta) -> World:
+    v = _WorldView()
+    L.ecmhost_world_get_view(h, C.byref(v))
+    nV, nE, nO, nB = v.n_vertices, v.n_edges, v.n_obst_vertices, v.n_obstacles
+    return World(
+        bbox=np.array(list(v.bbox), dtype=np.float32),
+        vert_xy=_copy(v.vert_xy, 2 * nV, np.float32, (nV, 2)),
+        vert_clear=_copy(v.vert_clear, nV, np.float32, (nV,)),
+        vert_he=_copy(v.vert_he, nV, np.int32, (nV,)),
+        edge_v=_copy(v.edge_v, 2 * nE, np.int32, (nE, 2)),
+        edge_cl=_copy(v.edge_cl, 8 * nE, np.float32, (nE, 4, 2)),
+        he_next=_copy(v.he_next, 2 * nE, np.int32, (2 * nE,)),
+        obst_xy=_copy(v.obst_xy, 2 * nO, np.float32, (nO, 2)),
+        obst_next=_copy(v.obst_next, nO, np.int32, (nO,)),
+        obst_prev=_copy(v.obst_prev, nO, np.int32, (nO,)),
+        obst_convex=_copy(v.obst_convex, nO, np.uint8, (nO,)),
+        obst_first=_copy(v.obst_first, nB + 1, np.int32, (nB + 1,)),
+        **meta,
+    )
+
+
+def polygon_world(bbox, polygons) -> World:
+    """ECM of a rectangular walkable area with polygonal obstacles (counter-clockwise point lists strictly inside it),
+    built without Boost by csrc/host/polygon_world.cpp; e.g. the reference's DEBUG1 scene (Environment.cpp:147-171):
+    polygon_world((-500, -500, 500, 500), [[(-50, 50), (-150, 50), (-150, -50), (-50, -50)], [(150, 50), (50, 50), (50, -50), (150, -50)]])."""
+    bb = np.ascontiguousarray(bbox, np.float32)
+    first = np.zeros(len(polygons) + 1, np.int32)
+    pts = []
+    for k, poly in enumerate(polygons):
+        p = np.asarray(poly, np.float32).reshape(-1, 2)
+        pts.append(p)
+        first[k + 1] = first[k] + len(p)
+    xy = np.ascontiguousarray(np.concatenate(pts) if pts else np.zeros((0, 2), np.float32))
+    L = lib()
+    err = C.create_string_buffer(256)
+    h = L.ecmhost_polygon_world(fptr(bb), len(polygons), iptr(first), fptr(xy) if len(xy) else None, err, 256)
+    if not h:
+        raise ValueError(f"polygon_world: {err.value.decode() or 'invalid input'}")
+    try:
+        return _world_from_handle(L, h)
+    finally:
+        L.ecmhost_world_free(h)
 
 
 class _WorldHandle:

@@ -189,6 +189,67 @@ def crowd_c5(w: World, n: int = 250_000, seed: int = 5) -> Crowd:
     return Crowd(c.pos, goal.astype(np.float32), c.radius, c.speed)
 
 
+# ------------------------------------------------------------------------------------------------
+# Polygonal scenes for host.polygon_world (the Boost-free ECM generator): the reference's own test environments
+# (Environment.cpp:27-185) and one with oblique, non-rectangular obstacles.  (bbox, [counter-clockwise polygons]).
+# ------------------------------------------------------------------------------------------------
+SCENES = {
+    # Environment::TestEnvironment::DEBUG1 (Environment.cpp:147-171): two boxes
+    "debug1": ((-500, -500, 500, 500), [[(-50, 50), (-150, 50), (-150, -50), (-50, -50)], [(150, 50), (50, 50), (50, -50), (150, -50)]]),
+    # Environment::TestEnvironment::CLASSIC (Environment.cpp:27-48): one U-shaped obstacle (two concave vertices)
+    "classic": ((-500, -500, 500, 500), [[(200, -250), (200, 250), (100, 250), (100, -150), (-100, -150), (-100, 250), (-200, 250), (-200, -250)]]),
+    # Environment::TestEnvironment::SQUARE (Environment.cpp:49-66)
+    "square": ((-500, -500, 500, 500), [[(200, -250), (200, 250), (-200, 250), (-200, -250)]]),
+    # not from the reference: a triangle, a turned rectangle, an L and a pentagon in a 120 x 90 yard
+    "yard": ((-60, -45, 60, 45), [[(-40, -30), (-22, -33), (-30, -12)],
+                                  [(-5, -20), (18, -28), (22, -17), (-1, -9)],
+                                  [(30, -5), (48, -5), (48, 25), (40, 25), (40, 3), (30, 3)],
+                                  [(-35, 8), (-20, 5), (-12, 18), (-22, 30), (-38, 24)]]),
+}
+
+
+def scene_polygons(name: str):
+    bbox, polys = SCENES[name]
+    return bbox, polys
+
+
+def crowd_in_scene(w: World, n: int, seed: int, radius=0.3, speed=1.4, window=None, min_goal_dist: float = 30.0, spacing: float = 1.2) -> Crowd:
+    """n agents on a jittered grid over the free space of a polygonal scene (inside `window` = x0 y0 x1 y1), goals drawn
+    from the same points at least min_goal_dist away."""
+    rng = np.random.default_rng(seed)
+    bb = np.array(window if window is not None else w.bbox, np.float64)
+    gx = np.arange(bb[0] + spacing, bb[2] - spacing, spacing)
+    gy = np.arange(bb[1] + spacing, bb[3] - spacing, spacing)
+    X, Y = np.meshgrid(gx, gy, indexing="xy")
+    pts = np.stack([X.ravel(), Y.ravel()], axis=1) + rng.uniform(-0.25, 0.25, size=(X.size, 2)) * (spacing - 2 * radius - 0.1)
+    # keep points at least radius + 0.3 away from every obstacle edge and outside the obstacles
+    keep = np.ones(len(pts), bool)
+    for k in range(w.n_obstacles):
+        poly = w.obst_xy[w.obst_first[k]:w.obst_first[k + 1]].astype(np.float64)
+        inside = np.zeros(len(pts), bool)
+        dmin = np.full(len(pts), np.inf)
+        for i in range(len(poly)):
+            p, q = poly[i], poly[(i + 1) % len(poly)]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                inside ^= ((p[1] > pts[:, 1]) != (q[1] > pts[:, 1])) & (pts[:, 0] < (q[0] - p[0]) * (pts[:, 1] - p[1]) / (q[1] - p[1]) + p[0])
+            d = q - p
+            t = np.clip(((pts - p) @ d) / (d @ d), 0, 1)
+            dmin = np.minimum(dmin, np.linalg.norm(pts - (p + t[:, None] * d), axis=1))
+        keep &= ~inside & (dmin > radius + 0.3)
+    pts = pts[keep]
+    if len(pts) < n:
+        raise ValueError(f"only {len(pts)} free grid points for {n} agents")
+    sel = rng.permutation(len(pts))[:n]
+    pos = pts[sel]
+    goal = pts[rng.integers(0, len(pts), size=n)]
+    for _ in range(64):
+        bad = np.hypot(*(goal - pos).T) < min_goal_dist
+        if not bad.any():
+            break
+        goal[bad] = pts[rng.integers(0, len(pts), size=int(bad.sum()))]
+    return Crowd(pos.astype(np.float32), goal.astype(np.float32), np.full(n, radius, np.float32), np.full(n, speed, np.float32))
+
+
 CONFIGS = {
     "c1_5k": (world_c1, crowd_c1),
     "c2_50k": (world_c2, crowd_c2),

@@ -3,7 +3,7 @@
  * library (ecm_b200.h) consumes, plus global path planning.  None of this is on the per-tick hot path.
  *
  * Reference interfaces restated here (all under /root/reference):
- *   ECMGenerator::GenerateECM            ECMGenerator/ECMGenerator.h:19      (lattice worlds only)
+ *   ECMGenerator::GenerateECM            ECMGenerator/ECMGenerator.h:19      (lattice worlds in closed form; polygonal scenes directly)
  *   Environment::AddWalkableArea/AddObstacle  ECMGenerator/Environment.h:47-48
  *   ECMPathPlanner::FindPath             ECMGenerator/ECMPathPlanner.h:55
  */
@@ -37,6 +37,13 @@ typedef struct ecmhost_world_view {
 /* Blocks bx[0..nbx) x by[0..nby) separated by streets of width W; NULL on invalid input. */
 ecmhost_world* ecmhost_lattice_world(int nbx, const float* bx, int nby, const float* by, float W,
                                      float x0, float y0);
+/* ECMGenerator::GenerateECM (ECMGenerator/ECMGenerator.cpp:235-256) for a rectangular walkable area with polygonal
+ * obstacles, without Boost: the segment Voronoi diagram of the area's edges and the obstacle edges is computed directly
+ * (csrc/host/polygon_world.h) and its primary edges in free space become the ECM, in the reference's conventions.
+ * poly_first[n_polys+1] indexes the counter-clockwise vertices in poly_xy; obstacles lie strictly inside the area and do
+ * not touch.  For scenes of up to a few hundred edges (the reference's own test environments, Environment.cpp:27-185).
+ * NULL on invalid input, with a message in `error` (may be NULL). */
+ecmhost_world* ecmhost_polygon_world(const float bbox[4], int n_polys, const int* poly_first, const float* poly_xy, char* error, int error_cap);
 /* Wrap caller-provided flat arrays (copied). */
 ecmhost_world* ecmhost_world_from_arrays(const ecmhost_world_view* view);
 void ecmhost_world_free(ecmhost_world* w);

@@ -181,6 +181,14 @@ def main_new(only):
     # (5) recessed blocks (U and L shaped obstacle polygons => concave vertices) in the jam world, turned as well: crowd
     #     pressure pushes agents along and into the recesses, so the !isConvex legs, the foreign-leg tests against
     #     non-rectangular neighbours and LP3D all run on oblique, concave input
+    # (6) a scene from the Boost-free ECM generator (host.polygon_world): oblique triangle / rectangle / pentagon and an
+    #     L-shaped obstacle with a CONSISTENT medial axis (the recesses of (5) leave the lattice ECM as it was)
+    if only in (None, "yard_small"):
+        from ecmgenerator_b200.host import polygon_world
+
+        w6 = polygon_world(*S.scene_polygons("yard"))
+        c6 = S.crowd_in_scene(w6, 300, 16, radius=0.3, speed=1.4, min_goal_dist=45.0, spacing=1.6)
+        make("yard_small", w6, c6, 140, 106)
     if only in (None, "concave_small"):
         w5 = lattice_world([30, 30], [12, 12, 12], 6.0, -33.0, -24.0).with_recessed_obstacles(7, depth=(0.8, 2.0))
         c5 = S.sample_crowd(lattice_world([30, 30], [12, 12, 12], 6.0, -33.0, -24.0), 360, 15, radius=(0.3, 0.3), speed=(1.4, 1.4),

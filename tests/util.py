@@ -7,7 +7,7 @@ from ecmgenerator_b200.host import World
 from ecmgenerator_b200.scenarios import Crowd
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN = ("c1_small", "c2_small", "jam_small", "oblique_small", "concave_small")
+GOLDEN = ("c1_small", "c2_small", "jam_small", "oblique_small", "concave_small", "yard_small")
 WORLD_KEYS = ("bbox", "vert_xy", "vert_clear", "vert_he", "edge_v", "edge_cl", "he_next", "obst_xy", "obst_next",
               "obst_prev", "obst_convex", "obst_first")
 
