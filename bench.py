@@ -606,6 +606,8 @@ def run_ours(args):
         # whole-job counters; zero halo misses = every owned agent's 5-NN ball stayed inside what its rank sees,
         # i.e. the strips computed exactly what one GPU computes (DESIGN.md "Multi-GPU")
         job_counters = sim.global_stats(("halo_misses", "knn_fallbacks", "obstacle_overflows", "lp3d_runs", "location_failures", "replans"))
+        if job_counters["halo_misses"] > 0:  # loud: from the first miss on the strips do not compute what one GPU computes
+            log(f"[bench] WARNING: {job_counters['halo_misses']} halo misses - the multi-GPU result is NOT the single-GPU result; widen the halo")
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:

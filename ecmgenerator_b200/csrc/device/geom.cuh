@@ -38,9 +38,7 @@ __device__ __forceinline__ void warp_align() {
 // (k_orca was instruction-fetch bound: stall_no_instruction 4.9-14.7 per issue, profiles/).
 template <bool kSync>
 __device__ __forceinline__ void phase_barrier() {
-#ifndef ECM_NO_PHASE_BARRIER  // A/B switch (tools/build_variants.py)
-    if (kSync) __syncthreads();
-#endif
+    if (kSync) __syncthreads();  // without it: +4 % (from rest) .. +8 % (congested) per tick, profiles/r02i_ab_*.jsonl
 }
 
 __device__ __forceinline__ v2 V(float x, float y) { return make_float2(x, y); }
@@ -73,37 +71,21 @@ __device__ __noinline__ v2 vnormalized(v2 a) {
 // -DECM_ORCA_IEEE restores the IEEE sequences: the host-side test builds of this code (tests/hostdev) use it to pin the
 // control flow and expression order bit for bit against the reference.
 #ifndef ECM_ORCA_IEEE
-#ifdef ECM_IEEE_DIV  // bisection switches (tools/nan_probe.py): one function back to its IEEE form
-__device__ __forceinline__ float odiv(float a, float b) { return a / b; }
-#else
 __device__ __forceinline__ float odiv(float a, float b) { return __fdividef(a, b); }
-#endif
-#ifdef ECM_IEEE_SQRT
-__device__ __forceinline__ float osqrt(float x) { return sqrtf(x); }
-#else
 __device__ __forceinline__ float osqrt(float x) {
     float r;
     asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-#endif
-#ifdef ECM_IEEE_SINCOS
-__device__ __forceinline__ void osincos(float a, float* sn, float* cs) { sincosf(a, sn, cs); }
-#else
 __device__ __forceinline__ void osincos(float a, float* sn, float* cs) { __sincosf(a, sn, cs); }
-#endif
 __device__ __forceinline__ v2 ovdiv(v2 a, float s) { return V(odiv(a.x, s), odiv(a.y, s)); }
 __device__ __forceinline__ float ovlen(v2 a) { return osqrt(a.x * a.x + a.y * a.y); }
-#ifdef ECM_IEEE_NORM
-__device__ __forceinline__ v2 ovnormalized(v2 a) { return vnormalized(a); }
-#else
 __device__ __forceinline__ v2 ovnormalized(v2 a) {
     const float l2 = a.x * a.x + a.y * a.y;
     if (l2 == 0.0f) return a;
     const float inv = rsqrtf(l2);
     return V(a.x * inv, a.y * inv);
 }
-#endif
 #else
 __device__ __forceinline__ float odiv(float a, float b) { return a / b; }
 __device__ __forceinline__ float osqrt(float x) { return sqrtf(x); }

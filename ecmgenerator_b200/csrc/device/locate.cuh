@@ -181,31 +181,54 @@ __device__ __forceinline__ bool find_attraction_point(const EcmView& ecm, const 
     const int nseg = np - 1;
     int b = go ? (nseg + kPathBlock - 1) / kPathBlock : 0;  // blocks still to look at
     int i = 0, i0 = 1;                                      // i < i0: fetch the next overlapping block
-    bool found = false, line_hit = false, active = go;
-    v2 pb = V(0.0f, 0.0f);
+    bool found = false, line_hit = false, active = go, cand = false;
+    v2 pa = V(0.0f, 0.0f), pb = V(0.0f, 0.0f);
+    // Two-speed scan.  Most segments a lane looks at are dismissed by the cheap half of irm_segment - the segment's LINE
+    // misses the disk - or because the segment's padded box does not touch the disk (then no intersection point can
+    // have t in [0, 1]: the padding is the block boxes', far above the rounding of the intersection arithmetic); only
+    // the survivors need the square root and six divisions.  Stepping all lanes segment by segment made every lane wait
+    // through the expensive half of any lane (ncu: 7.7 of 32 lanes active in it).  So (A) every lane skips ahead at its
+    // own pace to its next surviving segment, then (B) the lanes that have one evaluate it together.
+    const float kPad = 0.05f;
     while (kSync ? __any_sync(0xffffffffu, active) : active) {
-        if (active) {
-            if (i < i0) {
-                for (;;) {
-                    if (--b < 0) break;
-                    const float4 bb = __ldg(&bbox[b]);
-                    const float dx = fmaxf(fmaxf(bb.x - R.x, R.x - bb.z), 0.0f), dy = fmaxf(fmaxf(bb.y - R.y, R.y - bb.w), 0.0f);
-                    if (!(dx * dx + dy * dy > c2)) break;  // bbox is padded on the host: conservative
+        while (kSync ? __any_sync(0xffffffffu, active && !cand) : (active && !cand)) {
+            if (active && !cand) {
+                if (i < i0) {
+                    for (;;) {
+                        if (--b < 0) break;
+                        const float4 bb = __ldg(&bbox[b]);
+                        const float dx = fmaxf(fmaxf(bb.x - R.x, R.x - bb.z), 0.0f), dy = fmaxf(fmaxf(bb.y - R.y, R.y - bb.w), 0.0f);
+                        if (!(dx * dx + dy * dy > c2)) break;  // bbox is padded on the host: conservative
+                    }
+                    if (b < 0) {
+                        active = false;
+                    } else {
+                        i0 = b * kPathBlock;
+                        i = min(i0 + kPathBlock, nseg) - 1;
+                        pb = path[i + 1];
+                    }
                 }
-                if (b < 0) {
-                    active = false;
-                } else {
-                    i0 = b * kPathBlock;
-                    i = min(i0 + kPathBlock, nseg) - 1;
-                    pb = path[i + 1];
+                if (active) {
+                    pa = path[i];
+                    const v2 p1 = vsub(pa, R), p2 = vsub(pb, R);
+                    const float el2 = vlen2(vsub(p2, p1)), det = vdet(p1, p2);
+                    bool want = false;
+                    if (!(c2 * el2 - det * det < kEpsilon)) {  // the line meets the disk (IRMPathFollower.cpp:66-70)
+                        line_hit = true;
+                        const float dx = fmaxf(fmaxf(fminf(pa.x, pb.x) - kPad - R.x, R.x - (fmaxf(pa.x, pb.x) + kPad)), 0.0f);
+                        const float dy = fmaxf(fmaxf(fminf(pa.y, pb.y) - kPad - R.y, R.y - (fmaxf(pa.y, pb.y) + kPad)), 0.0f);
+                        want = !(dx * dx + dy * dy > c2);
+                    }
+                    if (want) cand = true;
+                    else { pb = pa; i--; }
                 }
             }
-            if (active) {
-                const v2 pa = path[i];
-                if (irm_segment(pa, pb, R, c2, out, line_hit)) { found = true; active = false; }
-                pb = pa;
-                i--;
-            }
+        }
+        if (cand) {
+            if (irm_segment(pa, pb, R, c2, out, line_hit)) { found = true; active = false; }
+            pb = pa;
+            i--;
+            cand = false;
         }
     }
     if (go) {

@@ -81,9 +81,12 @@ class LocalStrips:
     """n strips inside one process; strips r lives on devices[r % len(devices)]."""
 
     def __init__(self, world, crowd, path_off, path_xy, n_strips: int, devices=(0,), halo: float | None = None,
-                 neighbor_cell: float = 0.0, record_neighbors: bool = True, step: float = float(DT), bounds=None):
+                 neighbor_cell: float = 0.0, record_neighbors: bool = True, step: float = float(DT), bounds=None,
+                 rebalance_every: int = 0, rebalance_tolerance: float = 0.15):
         n = crowd.n
         self.n = n
+        self.ticks, self.rebalances, self._misses_seen = 0, 0, 0
+        self.rebalance_every, self.rebalance_tolerance = int(rebalance_every), float(rebalance_tolerance)
         self.bounds = strip_bounds(crowd.pos[:, 0], n_strips) if bounds is None else np.asarray(bounds, np.float32)
         self.sims = []
         pool = int(path_off[-1] * 1.25) + 4096
@@ -107,6 +110,31 @@ class LocalStrips:
             for phase in (0, 1, 2):
                 for s in self.sims:
                     s.update_phase(phase)
+            self.ticks += 1
+            if self.rebalance_every and self.ticks % self.rebalance_every == 0:
+                self.maybe_rebalance()
+
+    def owned_counts(self):
+        return [int(s.read(gpu.ACTIVE, 0, self.n).sum()) for s in self.sims]
+
+    def maybe_rebalance(self) -> bool:
+        """equal-count borders again once a strip holds more than (1 + tolerance) of its share."""
+        self.sync()
+        counts = self.owned_counts()
+        if max(counts) <= (1.0 + self.rebalance_tolerance) * (sum(counts) / len(counts)):
+            return False
+        self.rebalance()
+        self.rebalances += 1
+        return True
+
+    def check_exact(self):
+        """Fails loudly if an agent's neighbour search reached beyond the halo since the last check: from that tick on
+        the strips no longer compute what one GPU computes.  (Nothing repairs the tick; widen the halo.)"""
+        self.sync()
+        misses = sum(s["halo_misses"] for s in self.stats())
+        if misses > self._misses_seen:
+            new, self._misses_seen = misses - self._misses_seen, misses
+            raise RuntimeError(f"{new} halo misses: the strips diverged from the single-GPU result; widen the halo (now {self.halo:.2f} m)")
 
     def sync(self):
         for s in self.sims:
@@ -136,6 +164,12 @@ class LocalStrips:
             s.write(gpu.ACTIVE, owners)
             s.comm_set_strips(self.bounds, self.halo)
 
+    def set_path(self, slot: int, path_xy):
+        """A replan answered on EVERY strip: paths are replicated at load time and do not travel with a migrant, so a
+        new polyline has to reach all ranks or the agent would follow a stale one after crossing a border."""
+        for s in self.sims:
+            s.set_path(slot, path_xy)
+
     def stats(self):
         return [s.stats() for s in self.sims]
 
@@ -148,10 +182,13 @@ class StripSim:
     """One strip per process (torchrun): rank r drives cuda:local_rank through libecmgpu + NCCL."""
 
     def __init__(self, world, crowd, path_off, path_xy, rank: int, n_ranks: int, device: int, halo: float | None = None,
-                 neighbor_cell: float = 0.0, record_neighbors: bool = False, step: float = float(DT)):
+                 neighbor_cell: float = 0.0, record_neighbors: bool = False, step: float = float(DT),
+                 rebalance_every: int = 0, rebalance_tolerance: float = 0.15):
         import torch.distributed as dist
 
         self.rank, self.n_ranks, self.n = rank, n_ranks, crowd.n
+        self.ticks, self.rebalances, self._misses_seen = 0, 0, 0
+        self.rebalance_every, self.rebalance_tolerance = int(rebalance_every), float(rebalance_tolerance)
         self.sim = gpu.GpuSim(world, crowd.n, step, device=device, neighbor_cell=neighbor_cell, record_neighbors=record_neighbors,
                               path_pool_points=int(path_off[-1] * 1.25) + 4096)
         self.sim.bulk_load(crowd.pos, crowd.radius, crowd.speed, path_off, path_xy)
@@ -175,7 +212,37 @@ class StripSim:
 
     # the bench / tests drive a StripSim like a GpuSim
     def update(self, n: int = 1):
-        self.sim.update(n)
+        if not self.rebalance_every:
+            self.sim.update(n)
+            self.ticks += n
+            return
+        while n > 0:  # in chunks that end on the re-balancing ticks (a collective: every rank takes the same decisions)
+            k = min(n, self.rebalance_every - self.ticks % self.rebalance_every)
+            self.sim.update(k)
+            self.ticks += k
+            n -= k
+            if self.ticks % self.rebalance_every == 0:
+                self.maybe_rebalance()
+
+    def maybe_rebalance(self) -> bool:
+        """equal-count borders again once a strip holds more than (1 + tolerance) of its share
+        (collective; the counts travel in one small all-reduce, the state only if the borders do move)."""
+        self.sim.sync()
+        mine = np.zeros(self.n_ranks, np.int64)
+        mine[self.rank] = int(self.sim.read(gpu.ACTIVE, 0, self.n).sum())
+        counts = self._all_reduce_sum(mine)
+        if counts.max() <= (1.0 + self.rebalance_tolerance) * counts.mean():
+            return False
+        self.rebalance()
+        self.rebalances += 1
+        return True
+
+    def check_exact(self):
+        """Fails loudly (on every rank) if an agent's neighbour search reached beyond the halo since the last check."""
+        misses = self.global_stats(("halo_misses",))["halo_misses"]
+        if misses > self._misses_seen:
+            new, self._misses_seen = misses - self._misses_seen, misses
+            raise RuntimeError(f"{new} halo misses: the strips diverged from the single-GPU result; widen the halo (now {self.halo:.2f} m)")
 
     def sync(self):
         self.sim.sync()
@@ -201,6 +268,11 @@ class StripSim:
             t = t.cuda()
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t.cpu().numpy()
+
+    def set_path(self, slot: int, path_xy):
+        """A replan answered on this rank's copy; a COLLECTIVE by convention: every rank must call it with the same
+        arguments (paths are replicated, they do not travel with a migrant)."""
+        self.sim.set_path(slot, path_xy)
 
     def global_active(self) -> int:
         act = self.sim.read(gpu.ACTIVE, 0, self.n)

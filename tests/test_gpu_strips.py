@@ -94,6 +94,30 @@ def test_rebalance_moves_the_borders_and_keeps_results_bitwise():
     single.close()
 
 
+def test_automatic_rebalancing_keeps_results_bitwise():
+    """rebalance_every = M: every M ticks the drivers compare the strips' agent counts and move the borders when one
+    holds more than 15 % over its share - here twice, starting from 20 / 30 / 50 %."""
+    n, ticks = 6000, 120
+    w, c, off, pxy = _crowd(n, 45)
+    xs = np.sort(c.pos[:, 0])
+    skew = np.array([xs[0] - 1.0, xs[int(0.2 * n)], xs[int(0.5 * n)], xs[-1] + 1.0], np.float32)
+    single = gpu.GpuSim(w, n, float(S.DT), path_pool_points=int(off[-1] * 1.25) + 4096)
+    single.bulk_load(c.pos, c.radius, c.speed, off, pxy)
+    strips = M.LocalStrips(w, c, off, pxy, 3, devices=(0,), bounds=skew, rebalance_every=40)
+    single.update(ticks)
+    strips.update(ticks)
+    strips.check_exact()
+    assert strips.rebalances >= 1 and max(strips.owned_counts()) < 0.40 * n
+    pos, owners = strips.gather(gpu.POS)
+    act = single.read(gpu.ACTIVE, 0, n)
+    assert np.array_equal(owners, act)
+    a = act > 0
+    assert_bits_equal(pos[a], single.read(gpu.POS, 0, n)[a], "positions")
+    assert_bits_equal(strips.gather(gpu.VEL)[0][a], single.read(gpu.VEL, 0, n)[a], "velocities")
+    strips.close()
+    single.close()
+
+
 def test_halo_miss_is_detected_when_the_halo_is_too_small():
     n = 3000
     w, c, off, pxy = _crowd(n, 42)
@@ -101,6 +125,8 @@ def test_halo_miss_is_detected_when_the_halo_is_too_small():
     strips.update(3)
     strips.sync()
     assert sum(s["halo_misses"] for s in strips.stats()) > 0
+    with pytest.raises(RuntimeError, match="halo misses"):
+        strips.check_exact()  # loud: the strips no longer compute what one GPU computes
     strips.close()
 
 

@@ -11,8 +11,14 @@ export ECM_WORKLOAD_CACHE=$PWD/workloads
 step() { echo "=== $1 ($(date +%T))" | tee -a "$OUT/${TAG}_session.log"; }
 if [[ " ${*:3} " == *" tests "* ]]; then
   step "pytest -m gpu"
-  timeout 900 python -m pytest tests -m gpu -q -x -s >"$OUT/${TAG}_gpu_tests.log" 2>&1
+  timeout 900 python -m pytest tests -m gpu -q -s >"$OUT/${TAG}_gpu_tests.log" 2>&1
   echo "pytest exit $?" | tee -a "$OUT/${TAG}_session.log"; tail -3 "$OUT/${TAG}_gpu_tests.log"
+fi
+if [[ " ${*:3} " == *" memcheck "* ]]; then
+  step "compute-sanitizer memcheck over a slice of the suite"
+  SLICE='tests/test_gpu_parity.py::test_lockstep_velocities_within_tolerance[jam_small] tests/test_gpu_parity.py::test_lockstep_velocities_within_tolerance[yard_small] tests/test_gpu_parity.py::test_ties_and_colocated_agents tests/test_gpu_parity.py::test_arrival_destroy_and_replan_events tests/test_gpu_parity.py::test_update_io_owned_records_match_plain_update tests/test_gpu_parity.py::test_nonfinite_agent_leaves_the_tick tests/test_gpu_strips.py::test_in_process_strips_match_single_gpu_bitwise tests/test_gpu_strips.py::test_automatic_rebalancing_keeps_results_bitwise tests/test_zz2_gpu_compact.py::test_compact_walk_in_the_graph_tick_with_spawns_and_destroys tests/test_zz2_gpu_spawn.py tests/test_zz4_gpu_planner.py::test_device_planner_reproduces_the_reference_polylines[c2_small]'
+  timeout 900 compute-sanitizer --tool memcheck --leak-check no --error-exitcode 3 --log-file "$OUT/${TAG}_memcheck.txt" python -m pytest -m gpu -q $SLICE >"$OUT/${TAG}_memcheck_pytest.log" 2>&1
+  echo "memcheck exit $?" | tee -a "$OUT/${TAG}_session.log"; tail -2 "$OUT/${TAG}_memcheck_pytest.log"; tail -2 "$OUT/${TAG}_memcheck.txt"
 fi
 step "A/B from rest"
 timeout 600 python tools/ab_variants.py $V >"$OUT/${TAG}_ab_rest.jsonl" 2>"$OUT/${TAG}_ab_rest.err"
