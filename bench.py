@@ -84,14 +84,29 @@ def _plan_sharded(w, c, rank: int, world: int, planner: str = "host", device: in
     return out_off, pts
 
 
+def _workload_stamp() -> str:
+    import hashlib
+
+    h = hashlib.sha1()
+    base = os.path.join(ROOT, "ecmgenerator_b200")
+    for rel in ("scenarios.py", "csrc/host/lattice_world.cpp", "csrc/host/planner.cpp", "csrc/host/planner.h"):
+        with open(os.path.join(base, rel), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:10]
+
+
 def build_workload(config: str, agents: int | None, rank: int = 0, world: int = 1, planner: str = "host", device: int = 0):
     world_fn, crowd_fn = S.CONFIGS[config]
     w = world_fn()
     t = time.time()
     # ECM_WORKLOAD_CACHE=<dir>: measurement sessions that build the same workload several times (tools/gpu_session.sh)
     # keep the sampled crowd and its planned routes on disk; worlds and crowds are seeded, so the content is the same
-    cache = os.environ.get("ECM_WORKLOAD_CACHE")
-    cache_file = os.path.join(cache, f"{config}_{agents or 0}.npz") if cache else None  # every rank reads it; rank 0 writes it
+    # The sampled crowd and its planned routes are kept on disk (seeded, so the content is what a fresh build gives; the
+    # file name carries a hash of the sources that define it): ECM_WORKLOAD_CACHE=<dir>, default ./workloads if it
+    # exists (git-ignored, travels to the GPU box), ECM_WORKLOAD_CACHE= (empty) to switch it off.  Set-up only: the
+    # planning time is outside every timed region either way.
+    cache = os.environ.get("ECM_WORKLOAD_CACHE", os.path.join(ROOT, "workloads") if os.path.isdir(os.path.join(ROOT, "workloads")) else "")
+    cache_file = os.path.join(cache, f"{config}_{agents or 0}_{_workload_stamp()}.npz") if cache else None  # every rank reads it; rank 0 writes it
     if cache_file and os.path.exists(cache_file):
         z = np.load(cache_file)
         c = S.Crowd(z["pos"], z["goal"], z["radius"], z["speed"])
@@ -418,6 +433,18 @@ def run_ours(args):
     def active_now():
         return float(sim.stats()["n_active"]) if world == 1 else float(sim.global_active())
 
+    def phase_pass(reps):
+        """Per-phase CUDA-event times (launch by launch, no graph), averaged over `reps` ticks of the current state."""
+        sim.set_profiling(True)
+        acc_ = {"grid": 0.0, "attract": 0.0, "orca": 0.0, "tick": 0.0}
+        for _ in range(reps):
+            sim.update(1)
+            t_ms = sim.last_tick_ms()
+            for k_ in acc_:
+                acc_[k_] += t_ms[k_] / reps
+        sim.set_profiling(False)
+        return acc_
+
     # ---- disclosure: K ticks from the crowd at rest (the cheap phase of the run)
     clocks = ClockSampler(local)
     clocks.start()
@@ -429,7 +456,12 @@ def run_ours(args):
         ms_r = timed_window(args.steps)
         st_b = sim.stats()
         done += args.steps
-        from_rest = {"from_tick": int(done - args.steps), "ms_per_step": ms_r / args.steps, "value": a_r * args.steps / (ms_r * 1e-3), "unit": UNIT,
+        rest_phases = None
+        if world == 1:
+            rest_phases = phase_pass(10)
+            done += 10
+        from_rest = {"from_tick": int(done - args.steps - (10 if world == 1 else 0)), "ms_per_step": ms_r / args.steps, "value": a_r * args.steps / (ms_r * 1e-3), "unit": UNIT,
+                     "phase_ms": rest_phases,
                      "lp3d_runs_per_tick_rank0": (st_b["lp3d_runs"] - st_a["lp3d_runs"]) / args.steps,
                      "note": "the same K ticks right after the warm-up, crowd at rest: cheaper than the congested crowd the headline is timed on"}
         # ---- let the crowd congest (untimed): the tick cost levels off after ~400 ticks (profiles/r01_experiments.md)
@@ -462,17 +494,7 @@ def run_ours(args):
     # ---- per-phase times for the roofline of the dominant kernel (separate pass, same state)
     roof = None
     if world == 1:
-        sim.set_profiling(True)
-        acc = {"grid": 0.0, "attract": 0.0, "orca": 0.0, "tick": 0.0}
-        reps = max(3, min(args.steps, 20))
-        for _ in range(reps):
-            sim.update(1)
-            t_ms = sim.last_tick_ms()
-            for k in acc:
-                acc[k] += t_ms[k]
-        sim.set_profiling(False)
-        for k in acc:
-            acc[k] /= reps
+        acc = phase_pass(max(3, min(args.steps, 20)))
         peak, peak_src = measured_hbm_peak()
         # algorithmic bytes per agent-update (DESIGN.md "Roofline"): whole tick 176 + 8 P;
         # k_attract 40 + 8 P (pos, speed, path header + polyline; attraction + prefvel out),
@@ -486,7 +508,12 @@ def run_ours(args):
         roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_agent": alg[dom],
                 "kernel_ms": acc[dom], "phase_ms": acc,
-                "whole_tick": {"achieved": ach_tick, "frac": ach_tick / peak, "algorithmic_bytes_per_agent": alg["tick"]}}
+                "whole_tick": {"achieved": ach_tick, "frac": ach_tick / peak, "algorithmic_bytes_per_agent": alg["tick"]},
+                "state": f"congested crowd (from tick {timed_from}), like the headline"}
+        if from_rest and from_rest.get("phase_ms"):  # the same kernel on the crowd at rest (what round 1's line reported)
+            k_ms = from_rest["phase_ms"][dom]
+            roof["from_rest"] = {"kernel_ms": k_ms, "achieved": alg[dom] * active0 / (k_ms * 1e-3) / 1e9,
+                                 "frac": alg[dom] * active0 / (k_ms * 1e-3) / 1e9 / peak}
     # ---- end to end through the C ABI with host buffers.  One GPU: whole slot arrays (ecmgpu_update_io);
     # strips: every rank moves the records of the agents it owns (ecmgpu_update_io_owned)
     e2e = None

@@ -111,7 +111,7 @@ def test_batched_spawn_checks_keep_the_reference_rand_stream_through_rewinds():
     a validity test at its threshold now and then in a box this crowded, so only the totals are compared."""
     import os
 
-    ticks = 60 if "mock" in os.environ.get("ECMGPU_LIB", "") else 150
+    ticks = 40 if "mock" in os.environ.get("ECMGPU_LIB", "") else 150
     ref = _crowded_spawn_run("ref", ticks=ticks)
     bat = _crowded_spawn_run("sim", dropin.Simulator.SPAWN_RAND_BATCHED, ticks=ticks)
     seq = _crowded_spawn_run("sim", dropin.Simulator.SPAWN_RAND_SEQUENTIAL, ticks=ticks)

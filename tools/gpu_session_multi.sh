@@ -24,8 +24,10 @@ if [[ " ${*:3} " == *" tests "* ]]; then
   timeout 1200 python -m pytest tests -m gpu -q -s >"$OUT/${TAG}_strips_tests.log" 2>&1
   echo "pytest exit $?" | tee -a "$OUT/${TAG}_session.log"; tail -3 "$OUT/${TAG}_strips_tests.log"
 fi
-step "bench c3_1m x$N"
-run_bench bench_n${N} "X=1"
+if [[ " ${*:3} " != *" noc3 "* ]]; then
+  step "bench c3_1m x$N"
+  run_bench bench_n${N} "X=1"
+fi
 if [[ " ${*:3} " == *" c4 "* ]]; then
   step "bench c4_4m x$N (routes planned on the GPUs)"
   ECM_WORKLOAD_CACHE= run_bench bench_c4_n${N} "X=1" --config c4_4m --planner device --steps 50
