@@ -117,6 +117,7 @@ struct ecmgpu_sim {
     int gw = 0, gh = 0, ncells_padded = 0;
     float gx0 = 0, gy0 = 0;
     bool grid_dirty = true;
+    int grid_n_slots = 0;  // n_slots when the (automatic) cell was last chosen
     DevBuf<int> d_key, d_rank, d_cell_count, d_s_slot, d_fb_list, d_ev_replan, d_ev_destroyed;
     // LP3D queue (orca.cuh Lp3dQueue): one row per slot, 32 + 16 * kMaxCons bytes each
     DevBuf<int4> d_lp3d_hdr;
@@ -231,12 +232,18 @@ int fail(ecmgpu_sim* s, int code, const std::string& msg) {
     } while (0)
 
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
+// What the per-slot kernels of a tick cover: n_slots rounded up to 4096 (slots beyond n_slots are inactive and cost a
+// flag read), so that a host that spawns agents one by one (the drop-in's spawn areas, every tick) does not change the
+// launch geometry - and with it re-capture and re-instantiate the tick's CUDA graph - with every new slot.
+inline int launch_slots(const ecmgpu_sim* s);
 // SMs of a B200: fixed-size grids are multiples of it.  (The host-side test build of this file shrinks it so that its
 // thread emulator does not have to start hundreds of thousands of idle threads per launch.)
 #ifndef ECM_SM_COUNT
 #define ECM_SM_COUNT 148
 #endif
 constexpr int kSMs = ECM_SM_COUNT;
+
+inline int launch_slots(const ecmgpu_sim* s) { return std::min(s->prm.max_agents, div_up(s->n_slots, 4096) * 4096); }
 
 // ---- host geometry for the static bins --------------------------------------------------------
 struct Rect { double x0, y0, x1, y1; };
@@ -486,6 +493,7 @@ int build_grid(ecmgpu_sim* s) {
         CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     }
     s->grid_dirty = false;
+    s->grid_n_slots = std::max(s->n_slots, 1);
     s->config_epoch++;
     return ECMGPU_OK;
 }
@@ -587,6 +595,12 @@ int ensure_ready(ecmgpu_sim* s) {
         int rc = build_bins(s);
         if (rc) return rc;
     }
+    // The automatic cell edge comes from the crowd's density when the grid is built.  A simulator that starts empty and
+    // fills through spawn areas would keep the cell chosen for its first handful of agents (exact, but 10-20 x the
+    // candidates per search): choose again whenever the loaded slots have doubled (or halved) since.
+    if (!s->grid_dirty && !(s->prm.neighbor_cell > 0) && !s->strips_on && s->grid_n_slots > 0 &&
+        (s->n_slots > 2 * s->grid_n_slots || 2 * s->n_slots < s->grid_n_slots))
+        s->grid_dirty = true;
     if (s->grid_dirty) {
         int rc = build_grid(s);
         if (rc) return rc;
@@ -723,7 +737,7 @@ int enqueue_pack(ecmgpu_sim* s, const TickView& t) {
     else for (int d = 0; d < 2; d++) CUDA_TRY(s, cudaMemsetAsync(s->d_send[d].p, 0, sizeof(MsgHeader), s->stream));
     CUDA_TRY(s, cudaMemsetAsync(s->d_self_ghost_n.p, 0, sizeof(int), s->stream));
     if (sv.walk.list) k_pack_walk<<<kSMs * 2, kPackBlock, 0, s->stream>>>(t.ag, sv, s->d_counters.p);
-    else k_pack<<<div_up(s->n_slots, kPackBlock), kPackBlock, 0, s->stream>>>(s->n_slots, t.ag, sv, s->d_counters.p);
+    else k_pack<<<div_up(launch_slots(s), kPackBlock), kPackBlock, 0, s->stream>>>(launch_slots(s), t.ag, sv, s->d_counters.p);
     s->launches++;
     if (s->local_transport) CUDA_TRY(s, cudaEventRecord(s->ev_packed, s->stream));
     CUDA_TRY(s, cudaGetLastError());
@@ -774,13 +788,13 @@ int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
     CUDA_TRY(s, cudaMemsetAsync(s->d_cell_count.p, 0, sizeof(int) * s->ncells_padded, s->stream));
     static_assert(C_LP3D_N == C_FALLBACK_N + 1, "the two per-tick counters are cleared by one memset");
     CUDA_TRY(s, cudaMemsetAsync(s->d_counters.p + C_FALLBACK_N, 0, 2 * sizeof(unsigned long long), s->stream));
-    const int nb = div_up(s->n_slots, 256);
+    const int nls = launch_slots(s), nb = div_up(nls, 256);
     StripView sv = make_strip_view(s);
     const int ng = 2 * s->cap_halo + s->cap_self;
     // compact strips: the list-walking kernels take the ghosts along (one launch each instead of two)
     if (sv.walk.list) k_bin_count_walk<<<kSMs * 8, 256, 0, s->stream>>>(sv, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p, s->d_status.p, s->d_counters.p);
     else {
-        k_bin_count<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p, s->d_status.p, s->d_counters.p);
+        k_bin_count<<<nb, 256, 0, s->stream>>>(nls, s->d_active.p, s->d_pos.p, gp, s->d_cell_count.p, s->d_key.p, s->d_rank.p, s->d_status.p, s->d_counters.p);
         if (s->strips_on) {
             k_ghost_count<<<div_up(ng, 256), 256, 0, s->stream>>>(sv, gp, s->d_cell_count.p);
             s->launches++;
@@ -790,7 +804,7 @@ int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
     k_scan_onepass<<<tiles, kScanBlock, 0, s->stream>>>((int4*)s->d_cell_count.p, tiles, s->d_scan_state.p, s->d_scan_ctl.p);
     if (sv.walk.list) k_scatter_walk<<<kSMs * 8, 256, 0, s->stream>>>(sv, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc);
     else {
-        k_scatter<<<nb, 256, 0, s->stream>>>(s->n_slots, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc);
+        k_scatter<<<nb, 256, 0, s->stream>>>(nls, s->d_key.p, s->d_rank.p, s->d_cell_count.p, t.ag, t.sc);
         if (s->strips_on) {
             k_ghost_scatter<<<div_up(ng, 256), 256, 0, s->stream>>>(sv, s->d_cell_count.p, t.ag, t.sc);
             s->launches++;
@@ -1399,7 +1413,7 @@ int ecmgpu_update_phase(ecmgpu_sim* s, int phase) {
     rc = enqueue_grid_build(s, t);
     if (rc) return rc;
     if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[1], s->stream));
-    const int nb = div_up(s->n_slots + (s->strips_on ? 2 * s->cap_halo + s->cap_self : 0), 128);
+    const int nb = div_up(launch_slots(s) + (s->strips_on ? 2 * s->cap_halo + s->cap_self : 0), 128);
     if (s->neighbor_mode == ECMGPU_NEIGHBORS_KDTREE) {
         if (s->strips_on) return fail(s, ECMGPU_ERR_INVALID, "the KD-tree neighbour mode runs on a single handle (no strips)");
         k_attract<<<nb, 128, 0, s->stream>>>(t);
@@ -1440,7 +1454,7 @@ int ecmgpu_update(ecmgpu_sim* s) {
         rc = ensure_walk(s);
         if (rc) return rc;
         const int g = (int)(s->comm_seq & 1u);
-        if (!s->graph_exec[g] || s->graph_epoch[g] != s->config_epoch || s->graph_n_slots[g] != s->n_slots) {
+        if (!s->graph_exec[g] || s->graph_epoch[g] != s->config_epoch || s->graph_n_slots[g] != launch_slots(s)) {
             if (s->graph_exec[g]) { cudaGraphExecDestroy(s->graph_exec[g]); s->graph_exec[g] = nullptr; }
             if (s->graph[g]) { cudaGraphDestroy(s->graph[g]); s->graph[g] = nullptr; }
             const uint64_t l0 = s->launches, t0 = s->ticks;
@@ -1456,7 +1470,7 @@ int ecmgpu_update(ecmgpu_sim* s) {
             if (ce != cudaSuccess) return fail(s, ECMGPU_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
             CUDA_TRY(s, cudaGraphInstantiate(&s->graph_exec[g], s->graph[g], 0));
             s->graph_epoch[g] = s->config_epoch;
-            s->graph_n_slots[g] = s->n_slots;
+            s->graph_n_slots[g] = launch_slots(s);
         }
         CUDA_TRY(s, cudaGraphLaunch(s->graph_exec[g], s->stream));
         s->launches += s->graph_launches[g];
