@@ -79,12 +79,25 @@ __device__ __forceinline__ float osqrt(float x) {
 }
 __device__ __forceinline__ void osincos(float a, float* sn, float* cs) { __sincosf(a, sn, cs); }
 __device__ __forceinline__ v2 ovdiv(v2 a, float s) { return V(odiv(a.x, s), odiv(a.y, s)); }
-__device__ __forceinline__ float ovlen(v2 a) { return osqrt(a.x * a.x + a.y * a.y); }
+__device__ __forceinline__ float ovlen(v2 a) { return osqrt(__fmaf_rn(a.x, a.x, a.y * a.y)); }
 __device__ __forceinline__ v2 ovnormalized(v2 a) {
-    const float l2 = a.x * a.x + a.y * a.y;
+    const float l2 = __fmaf_rn(a.x, a.x, a.y * a.y);
     if (l2 == 0.0f) return a;
     const float inv = rsqrtf(l2);
     return V(a.x * inv, a.y * inv);
+}
+// a*b + c*d, a*b - c*d, a*b + c with ONE rounding fewer (this file is compiled with -fmad=false for the bit-exact parts;
+// the half-plane arithmetic asks for the contraction explicitly): a third of the instructions of every dot product,
+// determinant and point-plus-scaled-direction below.
+__device__ __forceinline__ float o2p(float a, float b, float c, float d) { return __fmaf_rn(a, b, c * d); }
+__device__ __forceinline__ float o2m(float a, float b, float c, float d) { return __fmaf_rn(a, b, -(c * d)); }
+__device__ __forceinline__ float omad(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+// sin and cos of atan(r / l), r >= 0, l > 0 (the half-angle of a velocity obstacle, ORCA.cpp:375-379): r and l over the
+// hypotenuse - one rsqrt instead of a division, the atanf polynomial and two SFU sine / cosine evaluations.
+__device__ __forceinline__ void osincos_atan(float r, float l, float* sn, float* cs) {
+    const float inv = rsqrtf(__fmaf_rn(r, r, l * l));
+    *sn = r * inv;
+    *cs = l * inv;
 }
 #else
 __device__ __forceinline__ float odiv(float a, float b) { return a / b; }
@@ -93,7 +106,17 @@ __device__ __forceinline__ void osincos(float a, float* sn, float* cs) { sincosf
 __device__ __forceinline__ v2 ovdiv(v2 a, float s) { return vdiv(a, s); }
 __device__ __forceinline__ float ovlen(v2 a) { return vlen(a); }
 __device__ __forceinline__ v2 ovnormalized(v2 a) { return vnormalized(a); }
+__device__ __forceinline__ float o2p(float a, float b, float c, float d) { return a * b + c * d; }
+__device__ __forceinline__ float o2m(float a, float b, float c, float d) { return a * b - c * d; }
+__device__ __forceinline__ float omad(float a, float b, float c) { return a * b + c; }
+__device__ __forceinline__ void osincos_atan(float r, float l, float* sn, float* cs) { sincosf(atanf(r / l), sn, cs); }
 #endif
+// the vector forms of the above (same expression shapes as vdot / vdet / vlen2 / vadd(p, vmul(d, t)) / vsub(p, vmul(d, t)))
+__device__ __forceinline__ float odot(v2 a, v2 b) { return o2p(a.x, b.x, a.y, b.y); }
+__device__ __forceinline__ float odet(v2 a, v2 b) { return o2m(a.x, b.y, a.y, b.x); }
+__device__ __forceinline__ float olen2(v2 a) { return o2p(a.x, a.x, a.y, a.y); }
+__device__ __forceinline__ v2 ovmad(v2 p, v2 d, float t) { return V(omad(d.x, t, p.x), omad(d.y, t, p.y)); }
+__device__ __forceinline__ v2 ovmsub(v2 p, v2 d, float t) { return V(omad(-d.x, t, p.x), omad(-d.y, t, p.y)); }
 // Point::Approximate (ECMDataTypes.cpp:97-100): open +-EPSILON box.
 __device__ __forceinline__ bool approx(v2 a, v2 b) {
     return a.x < (b.x + kEpsilon) && a.x > (b.x - kEpsilon) && a.y < (b.y + kEpsilon) && a.y > (b.y - kEpsilon);

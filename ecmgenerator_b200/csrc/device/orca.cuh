@@ -18,7 +18,7 @@ __device__ __forceinline__ Cons cmake(v2 point, v2 normal) { return make_float4(
 __device__ __forceinline__ v2 cn(const Cons& c) { return V(c.x, c.y); }
 __device__ __forceinline__ v2 cp(const Cons& c) { return V(c.z, c.w); }
 // Constraint::Contains, methodB (ORCA.h:52)
-__device__ __forceinline__ bool ccontains(const Cons& c, v2 p) { return vdet(vright(cn(c)), vsub(cp(c), p)) <= 0.0f; }
+__device__ __forceinline__ bool ccontains(const Cons& c, v2 p) { return odet(vright(cn(c)), vsub(cp(c), p)) <= 0.0f; }
 
 // The reference filter of Simulator.cpp:271-287 for one segment o -> next[o].
 __device__ __forceinline__ bool obstacle_in_range(const ObstView& ob, int o, v2 a, float range2) {
@@ -65,9 +65,9 @@ __device__ __forceinline__ bool obstacle_constraint(const ObstView& ob, int oL, 
     bool cvxL = __ldg(&ob.convex[oL]) != 0, cvxR = __ldg(&ob.convex[oR]) != 0;
     v2 rp1 = vsub(pL, position), rp2 = vsub(pR, position);
     v2 segDir = vsub(pR, pL);
-    const float sp = odiv(vdot(vmul(rp1, -1.0f), segDir), vlen2(segDir));
-    const float distSqLine = vlen2(vsub(vmul(rp1, -1.0f), vmul(segDir, sp)));
-    const float distSq1 = vlen2(rp1), distSq2 = vlen2(rp2);
+    const float sp = odiv(odot(vmul(rp1, -1.0f), segDir), olen2(segDir));
+    const float distSqLine = olen2(ovmsub(vmul(rp1, -1.0f), segDir, sp));
+    const float distSq1 = olen2(rp1), distSq2 = olen2(rp2);
     segDir = __ldg(&ob.dir[oL]);  // = Normalize(segDir)
     const float radiusSq = clearance * clearance;
 
@@ -76,7 +76,7 @@ __device__ __forceinline__ bool obstacle_constraint(const ObstView& ob, int oL, 
         return false;
     } else if (sp > 1.0f && distSq2 <= radiusSq) {  // collision with the right vertex (ORCA.cpp:108-121)
         v2 rnd = __ldg(&ob.dir[oR]);  // = Normalize(next(R).p - R.p)
-        if (cvxR && vdet(rp2, rnd) >= 0.0f) { c = cmake(V(0.0f, 0.0f), ovnormalized(vmul(rp2, -1.0f))); return true; }
+        if (cvxR && odet(rp2, rnd) >= 0.0f) { c = cmake(V(0.0f, 0.0f), ovnormalized(vmul(rp2, -1.0f))); return true; }
         return false;
     } else if (sp >= 0.0f && sp < 1.0f && distSqLine <= radiusSq) {  // collision with the segment (ORCA.cpp:124-135)
         c = cmake(V(0.0f, 0.0f), vright(segDir));
@@ -88,24 +88,24 @@ __device__ __forceinline__ bool obstacle_constraint(const ObstView& ob, int oL, 
         if (!cvxL) return false;
         oR = oL; pR = pL; cvxR = cvxL;
         const float leg1 = osqrt(distSq1 - radiusSq);
-        leftLeg = ovdiv(V(rp1.x * leg1 - rp1.y * clearance, rp1.x * clearance + rp1.y * leg1), distSq1);
-        rightLeg = ovdiv(V(rp1.x * leg1 + rp1.y * clearance, -rp1.x * clearance + rp1.y * leg1), distSq1);
+        leftLeg = ovdiv(V(o2m(rp1.x, leg1, rp1.y, clearance), o2p(rp1.x, clearance, rp1.y, leg1)), distSq1);
+        rightLeg = ovdiv(V(o2p(rp1.x, leg1, rp1.y, clearance), o2p(-rp1.x, clearance, rp1.y, leg1)), distSq1);
     } else if (sp > 1.0f && distSqLine <= radiusSq) {  // ORCA.cpp:171-183
         if (!cvxR) return false;
         oL = oR; pL = pR; cvxL = cvxR;
         const float leg2 = osqrt(distSq2 - radiusSq);
-        leftLeg = ovdiv(V(rp2.x * leg2 - rp2.y * clearance, rp2.x * clearance + rp2.y * leg2), distSq2);
-        rightLeg = ovdiv(V(rp2.x * leg2 + rp2.y * clearance, -rp2.x * clearance + rp2.y * leg2), distSq2);
+        leftLeg = ovdiv(V(o2m(rp2.x, leg2, rp2.y, clearance), o2p(rp2.x, clearance, rp2.y, leg2)), distSq2);
+        rightLeg = ovdiv(V(o2p(rp2.x, leg2, rp2.y, clearance), o2p(-rp2.x, clearance, rp2.y, leg2)), distSq2);
     } else {  // ORCA.cpp:186-212
         if (cvxL) {
             const float leg1 = osqrt(distSq1 - radiusSq);
-            leftLeg = ovdiv(V(rp1.x * leg1 - rp1.y * clearance, rp1.x * clearance + rp1.y * leg1), distSq1);
+            leftLeg = ovdiv(V(o2m(rp1.x, leg1, rp1.y, clearance), o2p(rp1.x, clearance, rp1.y, leg1)), distSq1);
         } else {
             leftLeg = vmul(segDir, -1.0f);
         }
         if (cvxR) {
             const float leg2 = osqrt(distSq2 - radiusSq);
-            rightLeg = ovdiv(V(rp2.x * leg2 + rp2.y * clearance, -rp2.x * clearance + rp2.y * leg2), distSq2);
+            rightLeg = ovdiv(V(o2p(rp2.x, leg2, rp2.y, clearance), o2p(-rp2.x, clearance, rp2.y, leg2)), distSq2);
         } else {
             rightLeg = segDir;
         }
@@ -114,46 +114,46 @@ __device__ __forceinline__ bool obstacle_constraint(const ObstView& ob, int oL, 
     // foreign legs (ORCA.cpp:218-239)
     bool leftForeign = false, rightForeign = false;
     v2 lnd = __ldg(&ob.dir[__ldg(&ob.prev[oL])]);  // = Normalize(L.p - prev(L).p)
-    if (cvxL && vdet(leftLeg, vmul(lnd, -1.0f)) >= 0.0f) { leftLeg = vmul(lnd, -1.0f); leftForeign = true; }
+    if (cvxL && odet(leftLeg, vmul(lnd, -1.0f)) >= 0.0f) { leftLeg = vmul(lnd, -1.0f); leftForeign = true; }
     v2 rnd = __ldg(&ob.dir[oR]);  // = Normalize(next(R).p - R.p)
-    if (cvxR && vdet(rightLeg, rnd) <= 0.0f) { rightLeg = rnd; rightForeign = true; }
+    if (cvxR && odet(rightLeg, rnd) <= 0.0f) { rightLeg = rnd; rightForeign = true; }
 
     const float recip = 1.0f / kLookAhead;  // ORCA.cpp:241
     const v2 leftCutoff = vmul(vsub(pL, position), recip);
     const v2 rightCutoff = vmul(vsub(pR, position), recip);
     const v2 cutoffVec = vsub(rightCutoff, leftCutoff);
     const bool same = (oL == oR);
-    const float t = same ? 0.5f : odiv(vdot(vsub(velocity, leftCutoff), cutoffVec), vlen2(cutoffVec));
-    const float tLeft = vdot(vsub(velocity, leftCutoff), leftLeg);
-    const float tRight = vdot(vsub(velocity, rightCutoff), rightLeg);
+    const float t = same ? 0.5f : odiv(odot(vsub(velocity, leftCutoff), cutoffVec), olen2(cutoffVec));
+    const float tLeft = odot(vsub(velocity, leftCutoff), leftLeg);
+    const float tRight = odot(vsub(velocity, rightCutoff), rightLeg);
 
     if ((t < 0.0f && tLeft < 0.0f) || (same && tLeft < 0.0f && tRight < 0.0f)) {  // ORCA.cpp:259-268
         v2 unitW = ovnormalized(vsub(velocity, leftCutoff));
-        c = cmake(vadd(leftCutoff, vmul(vmul(unitW, recip), clearance)), unitW);
+        c = cmake(ovmad(leftCutoff, vmul(unitW, recip), clearance), unitW);
         return true;
     } else if (t > 1.0f && tRight < 0.0f) {  // ORCA.cpp:270-280
         v2 unitW = ovnormalized(vsub(velocity, rightCutoff));
-        c = cmake(vadd(rightCutoff, vmul(vmul(unitW, recip), clearance)), unitW);
+        c = cmake(ovmad(rightCutoff, vmul(unitW, recip), clearance), unitW);
         return true;
     }
     // ORCA.cpp:284-286
-    const float distSqCutoff = (t < 0.0f || t > 1.0f || same) ? CUDART_INF_F : vlen2(vsub(velocity, vadd(leftCutoff, vmul(cutoffVec, t))));
-    const float distSqLeft = (tLeft < 0.0f) ? CUDART_INF_F : vlen2(vsub(velocity, vadd(leftCutoff, vmul(leftLeg, tLeft))));
-    const float distSqRight = (tRight < 0.0f) ? CUDART_INF_F : vlen2(vsub(velocity, vadd(rightCutoff, vmul(rightLeg, tRight))));
+    const float distSqCutoff = (t < 0.0f || t > 1.0f || same) ? CUDART_INF_F : olen2(vsub(velocity, ovmad(leftCutoff, cutoffVec, t)));
+    const float distSqLeft = (tLeft < 0.0f) ? CUDART_INF_F : olen2(vsub(velocity, ovmad(leftCutoff, leftLeg, tLeft)));
+    const float distSqRight = (tRight < 0.0f) ? CUDART_INF_F : olen2(vsub(velocity, ovmad(rightCutoff, rightLeg, tRight)));
 
     if (distSqCutoff <= distSqLeft && distSqCutoff <= distSqRight) {  // ORCA.cpp:289-301
         v2 normal = vleft(vmul(segDir, -1.0f));
-        c = cmake(vadd(leftCutoff, vmul(vmul(normal, recip), clearance)), normal);
+        c = cmake(ovmad(leftCutoff, vmul(normal, recip), clearance), normal);
         return true;
     } else if (distSqLeft <= distSqRight) {  // ORCA.cpp:303-317
         if (leftForeign) return false;
         v2 normal = vleft(leftLeg);
-        c = cmake(vadd(leftCutoff, vmul(vmul(normal, clearance), recip)), normal);
+        c = cmake(ovmad(leftCutoff, vmul(normal, clearance), recip), normal);
         return true;
     }
     if (rightForeign) return false;  // ORCA.cpp:319-332
     v2 normal = vright(rightLeg);
-    c = cmake(vadd(rightCutoff, vmul(vmul(normal, clearance), recip)), normal);
+    c = cmake(ovmad(rightCutoff, vmul(normal, clearance), recip), normal);
     return true;
 }
 
@@ -171,33 +171,33 @@ __device__ __forceinline__ Cons agent_constraint(v2 position, v2 velocity, float
         float wLength = ovlen(w);
         v2 unitW = ovdiv(w, wLength);
         v2 U = vmul(unitW, (odiv(combinedRadius, stepSize) - wLength));
-        return cmake(vadd(velocity, vmul(U, 0.5f)), unitW);
+        return cmake(ovmad(velocity, U, 0.5f), unitW);
     }
-    float tanHalfAngle = atanf(odiv(VORadius, VOPosLength));  // atan, not asin (ORCA.cpp:375-376)
-    // RotateVector(VOPos, +a) and RotateVector(VOPos, -a): one sincosf serves both (sin is odd, cos even, exactly)
+    // the half-angle is atan(VORadius / VOPosLength): atan, not asin (ORCA.cpp:375-376).  RotateVector(VOPos, +a) and
+    // RotateVector(VOPos, -a): one sine / cosine pair serves both (sin is odd, cos even, exactly)
     float sn, cs;
-    osincos(tanHalfAngle, &sn, &cs);
-    v2 VOLeftLeg = V(VOPos.x * cs - VOPos.y * sn, VOPos.x * sn + VOPos.y * cs);
-    v2 VORightLeg = V(VOPos.x * cs + VOPos.y * sn, VOPos.y * cs - VOPos.x * sn);
-    float sqDistFromCircleCentre = sqdist(VOPos, relVel);
+    osincos_atan(VORadius, VOPosLength, &sn, &cs);
+    v2 VOLeftLeg = V(o2m(VOPos.x, cs, VOPos.y, sn), o2p(VOPos.x, sn, VOPos.y, cs));
+    v2 VORightLeg = V(o2p(VOPos.x, cs, VOPos.y, sn), o2m(VOPos.y, cs, VOPos.x, sn));
     v2 base = vsub(VOLeftLeg, VOPos), chk = vsub(relVel, VOPos);
-    bool liesBelow = base.x * chk.y - base.y * chk.x > 0.0f;  // IsLeftOfVector (UtilityFunctions.cpp:198-201)
+    float sqDistFromCircleCentre = olen2(chk);  // SquareDistance(VOPos, relVel)
+    bool liesBelow = odet(base, chk) > 0.0f;  // IsLeftOfVector (UtilityFunctions.cpp:198-201)
     if (liesBelow) {  // ORCA.cpp:385-397
         float distToEdge = VORadius - osqrt(sqDistFromCircleCentre);
         v2 lineNormal = ovnormalized(vsub(relVel, VOPos));
-        return cmake(vadd(velocity, vmul(vmul(lineNormal, distToEdge), 0.5f)), lineNormal);
+        return cmake(ovmad(velocity, vmul(lineNormal, distToEdge), 0.5f), lineNormal);
     }
     v2 leftPerp = ovdiv(vleft(VOPos), VOPosLength);
-    if (vdot(leftPerp, relVel) >= 0.0f) {  // closer to the left leg (ORCA.cpp:403-412)
+    if (odot(leftPerp, relVel) >= 0.0f) {  // closer to the left leg (ORCA.cpp:403-412)
         v2 ln = ovnormalized(VOLeftLeg);
-        float l = vdot(relVel, ln);  // GetClosestPointOnLineThroughOrigin (UtilityFunctions.cpp:316-320)
+        float l = odot(relVel, ln);  // GetClosestPointOnLineThroughOrigin (UtilityFunctions.cpp:316-320)
         v2 U = vsub(vmul(ln, l), relVel);
-        return cmake(vadd(velocity, vmul(U, 0.5f)), vleft(ln));
+        return cmake(ovmad(velocity, U, 0.5f), vleft(ln));
     }
     v2 rn = ovnormalized(VORightLeg);
-    float l = vdot(relVel, rn);
+    float l = odot(relVel, rn);
     v2 U = vsub(vmul(rn, l), relVel);
-    return cmake(vadd(velocity, vmul(U, 0.5f)), vright(rn));
+    return cmake(ovmad(velocity, U, 0.5f), vright(rn));
 }
 
 // ORCA::RandomizedLP (ORCA.cpp:428-587).  Returns n on success, else the failing index.  The arithmetic and its
@@ -232,8 +232,8 @@ __device__ __forceinline__ int randomized_lp(const Cons* cs, int n, v2 opt, floa
         }
         // (B) project onto constraint i, clipped by constraints 0 .. i-1
         const v2 dir = vright(cn(h));
-        const float dpd = vdot(dir, cp(h));
-        const float disc = dpd * dpd + maxSpeed * maxSpeed - vdot(cp(h), cp(h));
+        const float dpd = odot(dir, cp(h));
+        const float disc = o2p(dpd, dpd, maxSpeed, maxSpeed) - odot(cp(h), cp(h));
         bool bad = disc <= 0.0f;  // `return i` (ORCA.cpp:499-503)
         // `if (disc <= 0) return i; else if (disc > 0) {...}` (ORCA.cpp:499-507) does NEITHER for a NaN discriminant: the
         // constraint is passed over.  It happens: an agent exactly level with an obstacle vertex it touches has sp == 1.0,
@@ -252,8 +252,8 @@ __device__ __forceinline__ int randomized_lp(const Cons* cs, int n, v2 opt, floa
             warp_align<kSync>();
             if (clip && j < i) {
                 const Cons hj = cs[j];
-                const float den = vdet(dir, vright(cn(hj)));
-                const float num = vdet(vright(cn(hj)), vsub(cp(h), cp(hj)));
+                const float den = odet(dir, vright(cn(hj)));
+                const float num = odet(vright(cn(hj)), vsub(cp(h), cp(hj)));
                 if (fabsf(den) <= kEpsilon) {
                     if (num < 0.0f) bad = true;  // `return i` (ORCA.cpp:526-533)
                 } else {
@@ -273,13 +273,13 @@ __device__ __forceinline__ int randomized_lp(const Cons* cs, int n, v2 opt, floa
                 live = i < n;
             } else {
                 if (useDirOpt) {
-                    if (vdot(opt, dir) > 0.0f) outV = vadd(cp(h), vmul(dir, right));
-                    else outV = vadd(cp(h), vmul(dir, left));
+                    if (odot(opt, dir) > 0.0f) outV = ovmad(cp(h), dir, right);
+                    else outV = ovmad(cp(h), dir, left);
                 } else {
-                    const float t = vdot(dir, vsub(opt, cp(h)));
-                    if (t < left) outV = vadd(cp(h), vmul(dir, left));
-                    else if (t > right) outV = vadd(cp(h), vmul(dir, right));
-                    else outV = vadd(cp(h), vmul(dir, t));
+                    const float t = odot(dir, vsub(opt, cp(h)));
+                    if (t < left) outV = ovmad(cp(h), dir, left);
+                    else if (t > right) outV = ovmad(cp(h), dir, right);
+                    else outV = ovmad(cp(h), dir, t);
                 }
                 i++;
                 live = i < n;
@@ -295,25 +295,25 @@ __device__ __noinline__ void randomized_lp3d(int nObst, const Cons* cs, int tota
     for (int i = failed; i < total; i++) {
         const Cons ci = cs[i];
         v2 dir = vright(cn(ci));
-        if (vdet(dir, vsub(cp(ci), outV)) <= maxPen) continue;
+        if (odet(dir, vsub(cp(ci), outV)) <= maxPen) continue;
         int np = 0;
         for (int k = 0; k < nObst; k++) proj[np++] = cs[k];
         for (int j = nObst; j < i; j++) {
             const Cons cj = cs[j];
-            float det = vdet(dir, vright(cn(cj)));
+            float det = odet(dir, vright(cn(cj)));
             v2 pt;
             if (fabsf(det) <= kEpsilon) {
-                if (vdot(cn(ci), cn(cj)) > 0.0f) continue;
+                if (odot(cn(ci), cn(cj)) > 0.0f) continue;
                 pt = vmul(vadd(cp(ci), cp(cj)), 0.5f);
             } else {
-                float t = odiv(vdet(vright(cn(cj)), vsub(cp(ci), cp(cj))), det);
-                pt = vadd(cp(ci), vmul(dir, t));
+                float t = odiv(odet(vright(cn(cj)), vsub(cp(ci), cp(cj))), det);
+                pt = ovmad(cp(ci), dir, t);
             }
             proj[np++] = cmake(pt, ovnormalized(vsub(cn(cj), cn(ci))));
         }
         const v2 temp = outV;
         if (randomized_lp<false>(proj, np, cn(ci), maxSpeed, true, outV) < np) outV = temp;
-        maxPen = vdet(dir, vsub(cp(ci), outV));
+        maxPen = odet(dir, vsub(cp(ci), outV));
     }
 }
 

@@ -31,7 +31,7 @@ def main():
         parts = spec.split(",")
         name, _, path = parts[0].partition("=")
         env = dict(p.split("=", 1) for p in parts[1:])
-        for k in [k for k in os.environ if k.startswith("ECMGPU_") and k != "ECMGPU_LIB"]:
+        for k in [k for k in os.environ if (k.startswith("ECMGPU_") and k != "ECMGPU_LIB") or k == "AB_CELL"]:
             del os.environ[k]
         os.environ.update(env)
         gpu._lib = None

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # One short GPU call: [pytest -m gpu] + A/B of build variants (from rest and congested) + optional ncu capture.
-#   gpurun --timeout 900 -- 'bash tools/gpu_ab.sh <tag> "<variant specs>" [tests] [ncu]'
+#   gpurun --timeout 900 -- 'bash tools/gpu_ab.sh <tag> "<variant specs>" [tests] [memcheck] [ncu] [strips8]'
 set -u
 TAG=${1:-ab}
 V=${2:-base}
@@ -31,5 +31,10 @@ if [[ " ${*:3} " == *" ncu "* ]]; then
   step "ncu --set full"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_orca|k_attract|k_scatter|k_bin_count" --launch-skip 12 -c 4 \
       -o "$OUT/${TAG}_full" -f python bench.py --steps 3 --warmup 5 --no-cpu --steady-tick 0 >"$OUT/${TAG}_ncu_full_bench.log" 2>&1
+fi
+if [[ " ${*:3} " == *" strips8 "* ]]; then
+  step "ncu launch list of 8 in-process strips (per-rank problem size of an 8-GPU run)"
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file "$OUT/${TAG}_strips8_launches.csv" \
+      python tools/strip_profile.py --strips 8 --ticks 2 >"$OUT/${TAG}_strips8.log" 2>&1
 fi
 step "done"
