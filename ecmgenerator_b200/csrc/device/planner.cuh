@@ -13,10 +13,17 @@
 // heap_push / heap_pop below restate libstdc++'s std::push_heap / std::pop_heap (__push_heap, __adjust_heap), the
 // algorithms behind the reference's std::priority_queue in the oracle's build.
 //
-// Per-worker scratch lives in global memory (PlanScratch): the A* arrays over all vertices (reset through the touched
-// list, like the host planner, instead of the reference's O(V) sweep per query, AStar.cpp:162-176), the heap, the
-// half-edge path, the portals and the polyline under construction.  Every capacity that an input could exceed is
-// checked and reported per query (kPlanOverflow); the heap cannot overflow (at most 2E + 2 pushes per query).
+// Per-worker scratch lives in global memory (PlanScratch): the A* node records over all vertices (reset through the
+// touched list, like the host planner, instead of the reference's O(V) sweep per query, AStar.cpp:162-176), the heap,
+// the half-edge path, the portals and the polyline under construction.  Every capacity that an input could exceed is
+// checked and reported per query (kPlanOverflow).
+//
+// What bounds it (profiles/r03b_planner_probe.jsonl, ncu in profiles/r02_experiments.md section 8): ~100 k queries in
+// flight, each chasing pointers through its own scratch - far more than any cache holds, so every access of a query is
+// a 32-byte DRAM sector of its own (2 MB of DRAM traffic per query).  Hence the layout: ONE 16-byte record per vertex
+// (g, f, parent, visited: the four are almost always touched together, as four arrays they were four sectors), and
+// capacities sized for the usual query, with the rare query that exceeds them planned again with the full ones
+// (ecmgpu_plan_paths, csrc/ecmgpu.cu), so that the scratch budget buys queries in flight instead of head room.
 #pragma once
 #include "locate.cuh"
 
@@ -32,13 +39,16 @@ struct PlanView {
     const int* he_next;       // [2 nE] next outgoing half-edge around the same source vertex (ECMHalfEdge::next_idx)
 };
 
+struct alignas(16) PlanNode {  // AStarNode (AStar.h:12-28)
+    float g, f;   // gCost, fCost: MAX_FLOAT when idle
+    int parent;   // parentIndex, nV = INVALID_NODE_INDEX when idle
+    int visited;
+};
+
 struct PlanScratch {  // worker k owns [k * stride, (k + 1) * stride) of every array
     int n_workers;
     int cap_push, cap_path, cap_portals, cap_out;
-    float* g;                // [workers * nV]  AStarNode::gCost, MAX_FLOAT when idle
-    float* f;                // [workers * nV]  fCost
-    int* parent;             // [workers * nV]  parentIndex, nV = INVALID_NODE_INDEX when idle
-    unsigned char* visited;  // [workers * nV]
+    PlanNode* node;          // [workers * nV]
     int* heap;               // [workers * cap_push]
     int* touched;            // [workers * cap_push]
     int* vpath;              // [workers * cap_path] A* vertex path, then reused
@@ -74,22 +84,23 @@ __device__ __forceinline__ float plan_tri_area(v2 p1, v2 p2, v2 p3) {
 
 // std::push_heap after push_back (libstdc++ __push_heap): the new last element climbs while its parent compares
 // "greater", i.e. has the larger f cost NOW.
-__device__ __forceinline__ void heap_sift_up(int* heap, int hole, int top, int value, const float* f) {
+__device__ __forceinline__ void heap_sift_up(int* heap, int hole, int top, int value, const PlanNode* nd) {
     int parent = (hole - 1) / 2;
-    while (hole > top && f[heap[parent]] > f[value]) {
+    const float fv = nd[value].f;  // no cost changes while an element climbs
+    while (hole > top && nd[heap[parent]].f > fv) {
         heap[hole] = heap[parent];
         hole = parent;
         parent = (hole - 1) / 2;
     }
     heap[hole] = value;
 }
-__device__ __forceinline__ void heap_push(int* heap, int& size, int value, const float* f) {
-    heap_sift_up(heap, size, 0, value, f);
+__device__ __forceinline__ void heap_push(int* heap, int& size, int value, const PlanNode* nd) {
+    heap_sift_up(heap, size, 0, value, nd);
     size++;
 }
 // std::pop_heap + pop_back (libstdc++ __pop_heap / __adjust_heap): the hole left by the top sinks to the bottom
 // along the children that do NOT compare greater, then the former last element climbs back from there.
-__device__ __forceinline__ void heap_pop(int* heap, int& size, const float* f) {
+__device__ __forceinline__ void heap_pop(int* heap, int& size, const PlanNode* nd) {
     if (size > 1) {
         const int len = size - 1;
         const int value = heap[len];
@@ -97,7 +108,7 @@ __device__ __forceinline__ void heap_pop(int* heap, int& size, const float* f) {
         int hole = 0, child = 0;
         while (child < (len - 1) / 2) {
             child = 2 * (child + 1);
-            if (f[heap[child]] > f[heap[child - 1]]) child--;
+            if (nd[heap[child]].f > nd[heap[child - 1]].f) child--;
             heap[hole] = heap[child];
             hole = child;
         }
@@ -106,45 +117,45 @@ __device__ __forceinline__ void heap_pop(int* heap, int& size, const float* f) {
             heap[hole] = heap[child - 1];
             hole = child - 1;
         }
-        heap_sift_up(heap, hole, 0, value, f);
+        heap_sift_up(heap, hole, 0, value, nd);
     }
     size--;
 }
 
 // AStar::FindPath (AStar.cpp:44-160) + ConstructPath (:184-212).  vpath receives the vertex path in travel order.
-__device__ __forceinline__ int plan_astar(const PlanView& w, int nV, float* g, float* f, int* parent, unsigned char* visited, int* heap, int* touched,
-                                          v2 startLoc, v2 goalLoc, int startEdge, int goalEdge, float clearance, int* vpath, int cap_path, int& n_path) {
+__device__ __forceinline__ int plan_astar(const PlanView& w, int nV, PlanNode* nd, int* heap, int* touched, int cap_push, v2 startLoc, v2 goalLoc,
+                                          int startEdge, int goalEdge, float clearance, int* vpath, int cap_path, int& n_path) {
     int n_heap = 0, n_touched = 0;
     const int2 se = __ldg(&w.ecm.edge_v[startEdge]), ge = __ldg(&w.ecm.edge_v[goalEdge]);
     const int sa = se.y, sb = se.x;  // half_edges[0].v_target_idx, half_edges[1].v_target_idx
     const int ga = ge.y, gb = ge.x;
     touched[n_touched++] = sa;
     touched[n_touched++] = sb;
-    g[sa] = plan_distance(startLoc, plan_vert(w, sa));
-    f[sa] = g[sa] + plan_distance(plan_vert(w, sa), goalLoc);
-    g[sb] = plan_distance(startLoc, plan_vert(w, sb));
-    f[sb] = g[sb] + plan_distance(plan_vert(w, sb), goalLoc);
-    heap_push(heap, n_heap, sa, f);
-    heap_push(heap, n_heap, sb, f);
+    nd[sa].g = plan_distance(startLoc, plan_vert(w, sa));
+    nd[sa].f = nd[sa].g + plan_distance(plan_vert(w, sa), goalLoc);
+    nd[sb].g = plan_distance(startLoc, plan_vert(w, sb));
+    nd[sb].f = nd[sb].g + plan_distance(plan_vert(w, sb), goalLoc);
+    heap_push(heap, n_heap, sa, nd);
+    heap_push(heap, n_heap, sb, nd);
     int status = kPlanNoPath;
     n_path = 0;
     while (n_heap > 0) {
-        while (n_heap > 0 && visited[heap[0]]) heap_pop(heap, n_heap, f);  // AStar.cpp:82-85
+        while (n_heap > 0 && nd[heap[0]].visited) heap_pop(heap, n_heap, nd);  // AStar.cpp:82-85
         if (n_heap == 0) break;
         const int cur = heap[0];
-        heap_pop(heap, n_heap, f);
-        visited[cur] = 1;
+        heap_pop(heap, n_heap, nd);
+        nd[cur].visited = 1;
         if (__ldg(&w.vert_clear[cur]) < clearance) continue;  // AStar.cpp:99
         if (cur == ga || cur == gb) {
             // reversed: the goal edge's other vertex, the reached one, then the parents back to a start vertex
             int len = 2;
-            for (int nxt = parent[cur]; nxt < nV; nxt = parent[nxt]) len++;
+            for (int nxt = nd[cur].parent; nxt < nV; nxt = nd[nxt].parent) len++;
             if (len > cap_path) { status = kPlanOverflow; break; }
             n_path = len;
             vpath[len - 1] = cur == ga ? gb : ga;
             vpath[len - 2] = cur;
             int k = len - 3;
-            for (int nxt = parent[cur]; nxt < nV; nxt = parent[nxt]) vpath[k--] = nxt;
+            for (int nxt = nd[cur].parent; nxt < nV; nxt = nd[nxt].parent) vpath[k--] = nxt;
             status = kPlanOk;
             break;
         }
@@ -157,30 +168,31 @@ __device__ __forceinline__ int plan_astar(const PlanView& w, int nV, float* g, f
             nb = he_target(w, he);
         } while (startNb != nb);
         const v2 cp = plan_vert(w, cur);
+        const float gCur = nd[cur].g;
+        bool full = false;
         do {
-            if (!visited[nb]) {
-                heap_push(heap, n_heap, nb, f);  // pushed with its OLD cost, updated below (AStar.cpp:131-145)
+            const PlanNode nn = nd[nb];
+            if (!nn.visited) {
+                if (n_touched >= cap_push) { full = true; break; }
+                heap_push(heap, n_heap, nb, nd);  // pushed with its OLD cost, updated below (AStar.cpp:131-145)
                 touched[n_touched++] = nb;
                 const v2 np = plan_vert(w, nb);
-                const float newG = g[cur] + plan_distance(cp, np);
-                if (newG < g[nb]) {
+                const float newG = gCur + plan_distance(cp, np);
+                if (newG < nn.g) {
                     const float newF = newG + plan_distance(np, goalLoc);
-                    parent[nb] = cur;
-                    f[nb] = newF;
-                    g[nb] = newG;
+                    PlanNode upd;
+                    upd.g = newG; upd.f = newF; upd.parent = cur; upd.visited = 0;
+                    nd[nb] = upd;
                 }
             }
             he = __ldg(&w.he_next[he]);
             nb = he_target(w, he);
         } while (nb != startNb);
+        if (full) { status = kPlanOverflow; break; }  // the heap / touched list of this pass is full: planned again with room for 2E + 4
     }
-    for (int k = 0; k < n_touched; k++) {  // CleanRequestData (AStar.cpp:162-176) for what this query touched
-        const int v = touched[k];
-        f[v] = kMaxFloat;
-        g[v] = kMaxFloat;
-        parent[v] = nV;
-        visited[v] = 0;
-    }
+    PlanNode idle;
+    idle.g = kMaxFloat; idle.f = kMaxFloat; idle.parent = nV; idle.visited = 0;
+    for (int k = 0; k < n_touched; k++) nd[touched[k]] = idle;  // CleanRequestData (AStar.cpp:162-176) for what this query touched
     return status;
 }
 
@@ -301,9 +313,8 @@ __device__ __forceinline__ int plan_path(const PlanView& w, const PlanScratch& s
     int* vpath = sc.vpath + (size_t)k * sc.cap_path;
     int* epath = sc.epath + (size_t)k * sc.cap_path;
     int n_v = 0;
-    int st = plan_astar(w, nV, sc.g + (size_t)k * nV, sc.f + (size_t)k * nV, sc.parent + (size_t)k * nV, sc.visited + (size_t)k * nV,
-                        sc.heap + (size_t)k * sc.cap_push, sc.touched + (size_t)k * sc.cap_push, rs, rg, startEdge, goalEdge, clearance, vpath,
-                        sc.cap_path, n_v);
+    int st = plan_astar(w, nV, sc.node + (size_t)k * nV, sc.heap + (size_t)k * sc.cap_push, sc.touched + (size_t)k * sc.cap_push, sc.cap_push, rs, rg,
+                        startEdge, goalEdge, clearance, vpath, sc.cap_path, n_v);
     if (st != kPlanOk) return st;
     // half-edge path (ECMPathPlanner.cpp:93-113)
     int m = 0;
@@ -357,20 +368,28 @@ __device__ __forceinline__ int plan_path(const PlanView& w, const PlanScratch& s
 
 // One thread per worker, queries in a grid-stride loop.  Paths are packed into `pool` through one atomic cursor
 // (order of arrival); per query: offset, length (0 = the reference's FindPath returned false) and status.
-__global__ void __launch_bounds__(128) k_plan_paths(PlanView w, PlanScratch sc, int n, const float2* __restrict__ start, const float2* __restrict__ goal,
+// subset: the queries to plan (second pass), or nullptr for 0 .. n-1.
+constexpr int kPlanBlock = 128;
+#ifndef ECM_PLAN_MINBLOCKS
+#define ECM_PLAN_MINBLOCKS 6
+#endif
+constexpr int kPlanThreadsPerSM = kPlanBlock * ECM_PLAN_MINBLOCKS;
+__global__ void __launch_bounds__(kPlanBlock, ECM_PLAN_MINBLOCKS) k_plan_paths(PlanView w, PlanScratch sc, int n, const int* __restrict__ subset,
+                                                    const float2* __restrict__ start, const float2* __restrict__ goal,
                                                     const float* __restrict__ clearance, int* __restrict__ out_off, int* __restrict__ out_len,
                                                     unsigned char* __restrict__ out_status, float2* __restrict__ pool, int pool_cap, int* cursor) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= sc.n_workers) return;
     const float2* mine = sc.out + (size_t)k * sc.cap_out;
-    for (int q = k; q < n; q += sc.n_workers) {
+    for (int i = k; i < n; i += sc.n_workers) {
+        const int q = subset ? subset[i] : i;
         int len = 0;
         int st = plan_path(w, sc, k, start[q], goal[q], clearance[q], len);
         int off = 0;
         if (st == kPlanOk) {
             off = atomicAdd(cursor, len);
             if (off + len > pool_cap) { st = kPlanOverflow; }
-            else for (int i = 0; i < len; i++) pool[off + i] = mine[i];
+            else for (int j = 0; j < len; j++) pool[off + j] = mine[j];
         }
         if (st != kPlanOk) len = 0;
         out_off[q] = off;
@@ -382,12 +401,9 @@ __global__ void __launch_bounds__(128) k_plan_paths(PlanView w, PlanScratch sc, 
 // Idle state of the A* arrays (AStar::Initialize, AStar.cpp:27-42).
 __global__ void __launch_bounds__(256) k_plan_init(PlanScratch sc, int nV) {
     const size_t total = (size_t)sc.n_workers * nV;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        sc.g[i] = kMaxFloat;
-        sc.f[i] = kMaxFloat;
-        sc.parent[i] = nV;
-        sc.visited[i] = 0;
-    }
+    PlanNode idle;
+    idle.g = kMaxFloat; idle.f = kMaxFloat; idle.parent = nV; idle.visited = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) sc.node[i] = idle;
 }
 
 }  // namespace ecm

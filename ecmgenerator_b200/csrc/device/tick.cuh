@@ -395,6 +395,9 @@ __device__ __forceinline__ void lp3d_parked(const TickView& t) {
 #ifndef ECM_ORCA_MINBLOCKS
 #define ECM_ORCA_MINBLOCKS 5
 #endif
+#ifndef ECM_ORCA_BLOCK
+#define ECM_ORCA_BLOCK 256
+#endif
 __device__ __forceinline__ void orca_agent(const TickView& t, const int p, const int n) {
     unsigned st = 0u;
     const bool mine = p < n && !t.sc.s_ghost[p] && t.sc.s_alive[p];
@@ -423,7 +426,7 @@ __device__ __forceinline__ void orca_agent(const TickView& t, const int p, const
     }
 }
 
-__global__ void __launch_bounds__(256, ECM_ORCA_MINBLOCKS) k_orca(TickView t) {
+__global__ void __launch_bounds__(ECM_ORCA_BLOCK, ECM_ORCA_MINBLOCKS) k_orca(TickView t) {
     orca_agent(t, blockIdx.x * blockDim.x + threadIdx.x, *t.n_sorted_ptr);
 }
 
@@ -434,7 +437,7 @@ __global__ void __launch_bounds__(128, ECM_ATTRACT_MINBLOCKS) k_attract_tiles(Ti
     const int n = *t.n_sorted_ptr;
     for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) attract_agent(t, base + threadIdx.x, n);
 }
-__global__ void __launch_bounds__(256, ECM_ORCA_MINBLOCKS) k_orca_tiles(TickView t) {
+__global__ void __launch_bounds__(ECM_ORCA_BLOCK, ECM_ORCA_MINBLOCKS) k_orca_tiles(TickView t) {
     const int n = *t.n_sorted_ptr;
     for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {  // uniform per CTA: the phase barriers stay legal
         orca_agent(t, base + threadIdx.x, n);

@@ -163,12 +163,17 @@ struct ecmgpu_sim {
     DevBuf<float> d_vert_clear;
     DevBuf<int> d_vert_he, d_he_next;
     bool have_topology = false;
-    DevBuf<float> d_pl_g, d_pl_f;
-    DevBuf<int> d_pl_parent, d_pl_heap, d_pl_touched, d_pl_vpath, d_pl_epath;
-    DevBuf<unsigned char> d_pl_visited;
-    DevBuf<float4> d_pl_portals;
-    DevBuf<float2> d_pl_out;
-    int pl_workers = 0, pl_cap_push = 0, pl_cap_path = 0, pl_cap_portals = 0, pl_cap_out = 0;
+    struct PlanBufs {  // per-worker scratch of the device planner (device/planner.cuh: PlanScratch)
+        DevBuf<PlanNode> node;
+        DevBuf<int> heap, touched, vpath, epath;
+        DevBuf<float4> portals;
+        DevBuf<float2> out;
+        int workers = 0, cap_push = 0, cap_path = 0, cap_portals = 0, cap_out = 0;
+        void free() { node.free(); heap.free(); touched.free(); vpath.free(); epath.free(); portals.free(); out.free(); workers = 0; }
+    } pl;
+    int pl_last_workers = 0, pl_last_second_pass = 0;
+    cudaEvent_t pl_ev[2] = {nullptr, nullptr};
+    float pl_last_ms = 0.0f;
 
     // ---- bookkeeping
     uint64_t ticks = 0, launches = 0;
@@ -816,48 +821,56 @@ int enqueue_grid_build(ecmgpu_sim* s, const TickView& t) {
 }
 
 // ---- batched path planning (device/planner.cuh) ----------------------------------------------------
-void plan_free(ecmgpu_sim* s) {
-    s->d_pl_g.free(); s->d_pl_f.free(); s->d_pl_parent.free(); s->d_pl_heap.free(); s->d_pl_touched.free(); s->d_pl_vpath.free();
-    s->d_pl_epath.free(); s->d_pl_visited.free(); s->d_pl_portals.free(); s->d_pl_out.free();
-    s->pl_workers = 0;
-}
+void plan_free(ecmgpu_sim* s) { s->pl.free(); }
 
-PlanScratch make_plan_scratch(ecmgpu_sim* s) {
+PlanScratch make_plan_scratch(ecmgpu_sim::PlanBufs& b) {
     PlanScratch sc;
-    sc.n_workers = s->pl_workers;
-    sc.cap_push = s->pl_cap_push; sc.cap_path = s->pl_cap_path; sc.cap_portals = s->pl_cap_portals; sc.cap_out = s->pl_cap_out;
-    sc.g = s->d_pl_g.p; sc.f = s->d_pl_f.p; sc.parent = s->d_pl_parent.p; sc.visited = s->d_pl_visited.p;
-    sc.heap = s->d_pl_heap.p; sc.touched = s->d_pl_touched.p; sc.vpath = s->d_pl_vpath.p; sc.epath = s->d_pl_epath.p;
-    sc.portals = s->d_pl_portals.p; sc.out = s->d_pl_out.p;
+    sc.n_workers = b.workers;
+    sc.cap_push = b.cap_push; sc.cap_path = b.cap_path; sc.cap_portals = b.cap_portals; sc.cap_out = b.cap_out;
+    sc.node = b.node.p; sc.heap = b.heap.p; sc.touched = b.touched.p; sc.vpath = b.vpath.p; sc.epath = b.epath.p;
+    sc.portals = b.portals.p; sc.out = b.out.p;
     return sc;
 }
 
-// Per-worker scratch for `want` concurrent queries, within a memory budget (env ECMGPU_PLAN_MB overrides it).
-int plan_alloc(ecmgpu_sim* s, int want) {
+// Per-worker scratch for `want` concurrent queries, within a memory budget: a quarter of the free device memory, at
+// most 48 GB (first pass; env ECMGPU_PLAN_MB overrides) / 8 GB (second pass).
+//   full = true:  2E + 4 pushes (a query pushes at most once per directed edge, plus the two start vertices) and the
+//                 capacities include/ecm_b200.h documents (2048 graph vertices, 8192 portals, 1024 points).
+//   full = false: the first pass: 2048 portals, and the same room for pushes as long as 32 k such workers fit the
+//                 budget - the kernel is bound by the sector rate of DRAM and gains nothing beyond ~100 k queries in
+//                 flight, but loses below ~50 k (profiles/r03b_planner_probe.jsonl).  On a graph too large for that
+//                 the push capacity shrinks (>= 8192) and the queries that fill it are planned again in the second
+//                 pass (1.4 % of the C3 crowd's routes push more than 8192 times, 14 % more than 4096:
+//                 profiles/r03c_planner_sweep.jsonl).  Env ECMGPU_PLAN_PUSH sets the first-pass capacity.
+int plan_alloc(ecmgpu_sim* s, ecmgpu_sim::PlanBufs& b, int want, bool full) {
     const size_t nV = (size_t)s->n_vertices, nE = (size_t)s->n_edges;
-    const int cap_push = (int)(2 * nE + 4);                    // a query pushes at most once per directed edge, plus the two start vertices
     const int cap_path = (int)std::min<size_t>(nV + 2, 2048);  // vertices of one A* path
-    const int cap_portals = 8192, cap_out = 1024;
-    const size_t per_worker = nV * 13 + (size_t)cap_push * 8 + (size_t)cap_path * 8 + (size_t)cap_portals * 16 + (size_t)cap_out * 8;
-    // The kernel is latency-bound pointer chasing: the more queries in flight the better, up to what the SMs can hold
-    // (80 registers: 768 threads per SM).  Scratch budget: a quarter of the free device memory, at most 48 GB.
+    const int cap_portals = full ? 8192 : 2048, cap_out = 1024;
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(s, cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = std::min<size_t>(free_b / 4, (size_t)48 << 30);
-    if (const char* e = getenv("ECMGPU_PLAN_MB")) budget = (size_t)std::max(16, atoi(e)) << 20;
-    int workers = (int)std::min<size_t>({(size_t)want, (size_t)kSMs * 768, std::max<size_t>(budget / per_worker, 32)});
+    size_t budget = std::min<size_t>(free_b / 4, (size_t)(full ? 8 : 48) << 30);
+    if (!full) if (const char* e = getenv("ECMGPU_PLAN_MB")) budget = (size_t)std::max(16, atoi(e)) << 20;
+    const size_t fixed = nV * sizeof(PlanNode) + (size_t)cap_path * 8 + (size_t)cap_portals * 16 + (size_t)cap_out * 8;
+    size_t push = 2 * nE + 4;
+    if (!full) {
+        const size_t per_worker_min = budget / 32768;
+        if (fixed + push * 8 > per_worker_min) push = std::min(push, std::max<size_t>(8192, per_worker_min > fixed ? (per_worker_min - fixed) / 8 : 0));
+        if (const char* e = getenv("ECMGPU_PLAN_PUSH")) push = std::min<size_t>(2 * nE + 4, (size_t)std::max(64, atoi(e)));
+    }
+    const int cap_push = (int)std::min<size_t>(push, (size_t)INT32_MAX);
+    const size_t per_worker = fixed + (size_t)cap_push * 8;
+    int workers = (int)std::min<size_t>({(size_t)want, (size_t)kSMs * kPlanThreadsPerSM, std::max<size_t>(budget / per_worker, 32)});
     workers = div_up(workers, 32) * 32;
-    if (s->pl_workers >= workers) return ECMGPU_OK;
-    plan_free(s);
+    if (b.workers >= workers && b.cap_push == cap_push && b.cap_portals == cap_portals) return ECMGPU_OK;
+    b.free();
     const size_t w = (size_t)workers;
-    CUDA_TRY(s, s->d_pl_g.alloc(w * nV)); CUDA_TRY(s, s->d_pl_f.alloc(w * nV)); CUDA_TRY(s, s->d_pl_parent.alloc(w * nV));
-    CUDA_TRY(s, s->d_pl_visited.alloc(w * nV));
-    CUDA_TRY(s, s->d_pl_heap.alloc(w * cap_push)); CUDA_TRY(s, s->d_pl_touched.alloc(w * cap_push));
-    CUDA_TRY(s, s->d_pl_vpath.alloc(w * cap_path)); CUDA_TRY(s, s->d_pl_epath.alloc(w * cap_path));
-    CUDA_TRY(s, s->d_pl_portals.alloc(w * cap_portals)); CUDA_TRY(s, s->d_pl_out.alloc(w * cap_out));
-    s->pl_workers = workers;
-    s->pl_cap_push = cap_push; s->pl_cap_path = cap_path; s->pl_cap_portals = cap_portals; s->pl_cap_out = cap_out;
-    k_plan_init<<<kSMs * 8, 256, 0, s->stream>>>(make_plan_scratch(s), (int)nV);
+    CUDA_TRY(s, b.node.alloc(w * nV));
+    CUDA_TRY(s, b.heap.alloc(w * cap_push)); CUDA_TRY(s, b.touched.alloc(w * cap_push));
+    CUDA_TRY(s, b.vpath.alloc(w * cap_path)); CUDA_TRY(s, b.epath.alloc(w * cap_path));
+    CUDA_TRY(s, b.portals.alloc(w * cap_portals)); CUDA_TRY(s, b.out.alloc(w * cap_out));
+    b.workers = workers;
+    b.cap_push = cap_push; b.cap_path = cap_path; b.cap_portals = cap_portals; b.cap_out = cap_out;
+    k_plan_init<<<kSMs * 8, 256, 0, s->stream>>>(make_plan_scratch(b), (int)nV);
     s->launches++;
     CUDA_TRY(s, cudaGetLastError());
     return ECMGPU_OK;
@@ -1153,6 +1166,7 @@ void ecmgpu_destroy(ecmgpu_sim* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : s->marks) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : s->pl_ev) if (ev) cudaEventDestroy(ev);
     s->d_vert_xy.free(); s->d_edge_cl.free(); s->d_obst_xy.free(); s->d_edge_v.free();
     s->d_obst_next.free(); s->d_obst_prev.free(); s->d_obst_convex.free(); s->d_obst_dir.free();
     s->d_bin_cell_start.free(); s->d_bin_cell_items.free(); s->d_bin_obst_start.free(); s->d_bin_obst_items.free();
@@ -1425,11 +1439,11 @@ int ecmgpu_update_phase(ecmgpu_sim* s, int phase) {
     } else if (s->compact && s->strips_on) {  // one resident wave over the row tiles that exist (tick.cuh)
         k_attract_tiles<<<kSMs * ECM_ATTRACT_MINBLOCKS, 128, 0, s->stream>>>(t);
         if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
-        k_orca_tiles<<<kSMs * ECM_ORCA_MINBLOCKS, 256, 0, s->stream>>>(t);
+        k_orca_tiles<<<kSMs * ECM_ORCA_MINBLOCKS, ECM_ORCA_BLOCK, 0, s->stream>>>(t);
     } else {
         k_attract<<<nb, 128, 0, s->stream>>>(t);
         if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
-        k_orca<<<div_up(nb * 128, 256), 256, 0, s->stream>>>(t);
+        k_orca<<<div_up(nb * 128, ECM_ORCA_BLOCK), ECM_ORCA_BLOCK, 0, s->stream>>>(t);
     }
     k_fallback<<<kSMs * 4, 128, 0, s->stream>>>(t, 0);
     if (s->profiling) { CUDA_TRY(s, cudaEventRecord(s->ev[3], s->stream)); s->ev_valid = true; }
@@ -1918,7 +1932,7 @@ int ecmgpu_plan_paths(ecmgpu_sim* s, int n, const float* start_xy, const float* 
     CUDA_TRY(s, cudaSetDevice(s->prm.device));
     int rc = ensure_bins(s);
     if (rc) return rc;
-    rc = plan_alloc(s, n);
+    rc = plan_alloc(s, s->pl, n, false);
     if (rc) return rc;
     const TickView t = make_view(s);
     PlanView w;
@@ -1937,21 +1951,60 @@ int ecmgpu_plan_paths(ecmgpu_sim* s, int n, const float* start_xy, const float* 
     CUDA_TRY(s, cudaMemcpyAsync(d_goal.p, goal_xy, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(s, cudaMemcpyAsync(d_cl.p, clearance, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(s, cudaMemsetAsync(d_cursor.p, 0, sizeof(int), s->stream));
-    const PlanScratch sc = make_plan_scratch(s);
-    k_plan_paths<<<div_up(sc.n_workers, 128), 128, 0, s->stream>>>(w, sc, n, d_start.p, d_goal.p, d_cl.p, d_off.p, d_len.p, d_st.p, d_pool.p,
-                                                                   cap_points, d_cursor.p);
+    const PlanScratch sc = make_plan_scratch(s->pl);
+    if (!s->pl_ev[0]) { CUDA_TRY(s, cudaEventCreate(&s->pl_ev[0])); CUDA_TRY(s, cudaEventCreate(&s->pl_ev[1])); }
+    CUDA_TRY(s, cudaEventRecord(s->pl_ev[0], s->stream));
+    k_plan_paths<<<div_up(sc.n_workers, kPlanBlock), kPlanBlock, 0, s->stream>>>(w, sc, n, nullptr, d_start.p, d_goal.p, d_cl.p, d_off.p, d_len.p, d_st.p,
+                                                                                 d_pool.p, cap_points, d_cursor.p);
     s->launches++;
     CUDA_TRY(s, cudaGetLastError());
+    // second pass: the queries that ran out of first-pass capacity, with the full capacities (their first attempt
+    // appended nothing to the pool)
+    std::vector<unsigned char> st_host((size_t)n);
+    CUDA_TRY(s, cudaMemcpyAsync(st_host.data(), d_st.p, (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    std::vector<int> redo;
+    for (int q = 0; q < n; q++) if (st_host[q] == kPlanOverflow) redo.push_back(q);
+    s->pl_last_workers = sc.n_workers;
+    s->pl_last_second_pass = (int)redo.size();
+    if (!redo.empty()) {
+        ecmgpu_sim::PlanBufs full;
+        DevBuf<int> d_redo;
+        rc = plan_alloc(s, full, (int)redo.size(), true);
+        if (!rc && d_redo.alloc(redo.size()) != cudaSuccess) rc = fail(s, ECMGPU_ERR_CUDA, "ecmgpu_plan_paths: out of device memory");
+        if (!rc) {
+            CUDA_TRY(s, cudaMemcpyAsync(d_redo.p, redo.data(), sizeof(int) * redo.size(), cudaMemcpyHostToDevice, s->stream));
+            const PlanScratch sc2 = make_plan_scratch(full);
+            k_plan_paths<<<div_up(sc2.n_workers, kPlanBlock), kPlanBlock, 0, s->stream>>>(w, sc2, (int)redo.size(), d_redo.p, d_start.p, d_goal.p, d_cl.p, d_off.p,
+                                                                                           d_len.p, d_st.p, d_pool.p, cap_points, d_cursor.p);
+            s->launches++;
+            CUDA_TRY(s, cudaGetLastError());
+            CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        }
+        full.free();
+        d_redo.free();
+        if (rc) return rc;
+    }
+    CUDA_TRY(s, cudaEventRecord(s->pl_ev[1], s->stream));
     int used = 0;
     CUDA_TRY(s, cudaMemcpyAsync(&used, d_cursor.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(s, cudaMemcpyAsync(out_off, d_off.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(s, cudaMemcpyAsync(out_len, d_len.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
     if (out_status) CUDA_TRY(s, cudaMemcpyAsync(out_status, d_st.p, (size_t)n, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    CUDA_TRY(s, cudaEventElapsedTime(&s->pl_last_ms, s->pl_ev[0], s->pl_ev[1]));
     const int have = std::min(used, cap_points);
     if (have > 0) CUDA_TRY(s, cudaMemcpy(out_xy, d_pool.p, sizeof(float2) * (size_t)have, cudaMemcpyDeviceToHost));
     if (out_points) *out_points = used;
     d_start.free(); d_goal.free(); d_pool.free(); d_cl.free(); d_off.free(); d_len.free(); d_cursor.free(); d_st.free();
+    return ECMGPU_OK;
+}
+
+int ecmgpu_plan_info(ecmgpu_sim* s, int* workers, float* kernel_ms, int* second_pass) {
+    if (!s) return ECMGPU_ERR_INVALID;
+    if (workers) *workers = s->pl_last_workers;
+    if (kernel_ms) *kernel_ms = s->pl_last_ms;
+    if (second_pass) *second_pass = s->pl_last_second_pass;
     return ECMGPU_OK;
 }
 

@@ -39,7 +39,7 @@ EXPORTS = [
     "ecmgpu_locate", "ecmgpu_retract", "ecmgpu_find_neighbors", "ecmgpu_find_obstacles", "ecmgpu_get_stats",
     "ecmgpu_last_tick_ms", "ecmgpu_set_profiling", "ecmgpu_mark", "ecmgpu_mark_elapsed_ms", "ecmgpu_stream", "ecmgpu_comm_unique_id", "ecmgpu_comm_init",
     "ecmgpu_comm_set_strips", "ecmgpu_comm_init_local", "ecmgpu_update_phase", "ecmgpu_update_io", "ecmgpu_update_io_owned", "ecmgpu_io_wait", "ecmgpu_comm_p2p_export", "ecmgpu_comm_p2p_connect",
-    "ecmgpu_set_neighbor_mode", "ecmgpu_valid_spawn_locations", "ecmgpu_draw_spawns", "ecmgpu_set_ecm_topology", "ecmgpu_plan_paths",
+    "ecmgpu_set_neighbor_mode", "ecmgpu_valid_spawn_locations", "ecmgpu_draw_spawns", "ecmgpu_set_ecm_topology", "ecmgpu_plan_paths", "ecmgpu_plan_info",
     "ecmgpu_abi_sizes",
 ]
 
@@ -375,6 +375,13 @@ class GpuSim:
         total = int(out_off[-1])
         idx = np.repeat(off.astype(np.int64), ln) + (np.arange(total) - np.repeat(out_off[:-1].astype(np.int64), ln))
         return out_off, pool[idx], int((ln > 0).sum())
+
+    def plan_info(self):
+        """(queries the last plan_paths kept in flight, device time of its kernels in ms, queries that needed the second
+        pass) - ecmgpu_plan_info."""
+        wk, ms, sp = C.c_int(0), C.c_float(0.0), C.c_int(0)
+        self._ck(self.L.ecmgpu_plan_info(self.h, C.byref(wk), C.byref(ms), C.byref(sp)))
+        return wk.value, ms.value, sp.value
 
     def valid_spawn_locations(self, xy, clearance):
         """Simulator::ValidSpawnLocation for a batch of points on the current positions (uint8 flags)."""

@@ -204,6 +204,12 @@ int ecmgpu_set_ecm_topology(ecmgpu_sim* sim, const int* vert_he, const int* he_n
  * pool).  Waits for the result. */
 int ecmgpu_plan_paths(ecmgpu_sim* sim, int n, const float* start_xy, const float* goal_xy, const float* clearance, int* out_off,
                       int* out_len, uint8_t* out_status, float* out_xy, int cap_points, int* out_points);
+/* Measurement aid for the call above: how many queries the last ecmgpu_plan_paths kept in flight (workers with their
+ * own scratch), the device time of its kernels in milliseconds (CUDA events on the simulator's stream; the copies of
+ * the queries and of the polylines are not in it) and how many queries needed the second pass (the first one runs with
+ * scratch sized for the usual query; a query that exceeds it is planned again with the full capacities).  Any pointer
+ * may be NULL. */
+int ecmgpu_plan_info(ecmgpu_sim* sim, int* workers, float* kernel_ms, int* second_pass);
 
 /* -- neighbour mode ---------------------------------------------------------------------------
  * ECMGPU_NEIGHBORS_EXACT (default): the exact 5-NN contract of DESIGN.md on the per-tick uniform grid.

@@ -453,7 +453,7 @@ void emu_set_topology(void* h, const float* vert_clear, const int* vert_he, cons
     e->he_next.assign(he_next, he_next + 2 * e->edge_v.size());
 }
 int emu_plan_paths(void* h, int workers, int n, const float* start, const float* goal, const float* clearance, int* out_off, int* out_len,
-                   unsigned char* out_status, float* pool, int pool_cap, int cap_path, int cap_portals, int cap_out) {
+                   unsigned char* out_status, float* pool, int pool_cap, int cap_path, int cap_portals, int cap_out, int cap_push) {
     Emu* e = (Emu*)h;
     TickView t = e->view();
     PlanView w;
@@ -461,23 +461,23 @@ int emu_plan_paths(void* h, int workers, int n, const float* start, const float*
     w.vert_clear = e->vert_clear.data(); w.vert_he = e->vert_he.data(); w.he_next = e->he_next.data();
     const int nV = (int)e->vert_xy.size(), nE = (int)e->edge_v.size();
     PlanScratch sc;
-    sc.n_workers = workers; sc.cap_push = 2 * nE + 4; sc.cap_path = cap_path; sc.cap_portals = cap_portals; sc.cap_out = cap_out;
-    std::vector<float> g((size_t)workers * nV), f((size_t)workers * nV);
-    std::vector<int> parent((size_t)workers * nV), heap((size_t)workers * sc.cap_push), touched((size_t)workers * sc.cap_push),
+    // cap_push <= 0: room for every possible push (2E + 4); else the first-pass capacity of ecmgpu_plan_paths
+    sc.n_workers = workers; sc.cap_push = cap_push > 0 ? std::min(cap_push, 2 * nE + 4) : 2 * nE + 4; sc.cap_path = cap_path; sc.cap_portals = cap_portals; sc.cap_out = cap_out;
+    std::vector<PlanNode> node((size_t)workers * nV);
+    std::vector<int> heap((size_t)workers * sc.cap_push), touched((size_t)workers * sc.cap_push),
         vpath((size_t)workers * cap_path), epath((size_t)workers * cap_path);
-    std::vector<unsigned char> visited((size_t)workers * nV);
     std::vector<float4> portals((size_t)workers * cap_portals);
     std::vector<float2> out((size_t)workers * cap_out);
-    sc.g = g.data(); sc.f = f.data(); sc.parent = parent.data(); sc.visited = visited.data(); sc.heap = heap.data(); sc.touched = touched.data();
+    sc.node = node.data(); sc.heap = heap.data(); sc.touched = touched.data();
     sc.vpath = vpath.data(); sc.epath = epath.data(); sc.portals = portals.data(); sc.out = out.data();
     launch(64, [&] { k_plan_init(sc, nV); }, 256);
     int cursor = 0;
     launch(workers, [&] {
-        k_plan_paths(w, sc, n, (const float2*)start, (const float2*)goal, clearance, out_off, out_len, out_status, (float2*)pool, pool_cap, &cursor);
+        k_plan_paths(w, sc, n, nullptr, (const float2*)start, (const float2*)goal, clearance, out_off, out_len, out_status, (float2*)pool, pool_cap, &cursor);
     }, 128);
-    // every query must leave the A* arrays idle again (CleanRequestData through the touched list)
-    for (size_t i = 0; i < g.size(); i++)
-        if (g[i] != kMaxFloat || f[i] != kMaxFloat || parent[i] != nV || visited[i]) return -1;
+    // every query must leave the A* records idle again (CleanRequestData through the touched list)
+    for (size_t i = 0; i < node.size(); i++)
+        if (node[i].g != kMaxFloat || node[i].f != kMaxFloat || node[i].parent != nV || node[i].visited) return -1;
     return cursor;
 }
 

@@ -25,14 +25,14 @@ class _Scene:
         self.crowd.pos[:] = self.path_xy[::2]
 
 
-def _emu_plan(emu, world, start, goal, clearance, workers=7, cap_path=2048, cap_portals=8192, cap_out=1024, pool_cap=None, dev=None):
-    """Capacities default to ecmgpu.cu's plan_alloc."""
+def _emu_plan(emu, world, start, goal, clearance, workers=7, cap_path=2048, cap_portals=8192, cap_out=1024, pool_cap=None, dev=None, cap_push=0):
+    """Capacities default to the second (full) pass of ecmgpu.cu's plan_alloc; cap_push = 0: room for every push (2E + 4)."""
     own = dev is None
     if own:
         dev = EmuDevice(emu, _Scene(world), 4.0)
     w = world
     emu.emu_set_topology.argtypes = [C.c_void_p, f32p, i32p, i32p]
-    emu.emu_plan_paths.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, f32p, f32p, i32p, i32p, u8p, f32p, C.c_int, C.c_int, C.c_int, C.c_int]
+    emu.emu_plan_paths.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, f32p, f32p, i32p, i32p, u8p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     keep = [np.ascontiguousarray(w.vert_clear, np.float32), np.ascontiguousarray(w.vert_he, np.int32), np.ascontiguousarray(w.he_next, np.int32)]
     emu.emu_set_topology(dev.h, _p(keep[0], f32p), _p(keep[1], i32p), _p(keep[2], i32p))
     n = len(start)
@@ -41,7 +41,7 @@ def _emu_plan(emu, world, start, goal, clearance, workers=7, cap_path=2048, cap_
     pool_cap = pool_cap or 256 * n + 64
     pool = np.zeros((pool_cap, 2), np.float32)
     used = emu.emu_plan_paths(dev.h, workers, n, _p(a[0], f32p), _p(a[1], f32p), _p(a[2], f32p), _p(off, i32p), _p(ln, i32p), _p(st, u8p),
-                              _p(pool, f32p), pool_cap, cap_path, cap_portals, cap_out)
+                              _p(pool, f32p), pool_cap, cap_path, cap_portals, cap_out, cap_push)
     assert used >= 0, "a query left the A* arrays dirty"
     if own:
         dev.close()
@@ -100,3 +100,11 @@ def test_device_planner_reports_capacity_overflow(emu):
     assert used == int(g.path_off[-1]) and (st == 2).any() and (st == 0).any()
     fit = st == 0
     assert ((off + ln)[fit] <= 300).all() and np.array_equal(ln[fit], ref_len[fit])
+    # the first pass of ecmgpu_plan_paths runs with a push capacity sized for the usual query: a query that fills it is
+    # reported (and planned again with the full capacity by the caller), the others are untouched by it, and the A*
+    # records are left idle either way (checked inside _emu_plan)
+    off, ln, st, pool, _ = _emu_plan(emu, g.world, g.crowd.pos, g.crowd.goal, g.crowd.radius, cap_push=24)
+    assert (st == 2).any() and (st == 0).any()
+    assert np.array_equal(ln[st == 0], ref_len[st == 0]) and (ln[st == 2] == 0).all()
+    _compare(off[st == 0], ln[st == 0], st[st == 0], pool, np.concatenate([[0], np.cumsum(ref_len[st == 0])]).astype(np.int32),
+             np.concatenate([g.path_xy[g.path_off[i]:g.path_off[i + 1]] for i in np.flatnonzero(st == 0)]), "small push capacity")

@@ -57,3 +57,22 @@ def test_device_planner_small_pool_is_retried():
     off, xy, _ = sim.plan_paths(g.crowd.pos, g.crowd.goal, g.crowd.radius, points_per_path=1)
     assert np.array_equal(off, g.path_off)
     assert_bits_equal(xy, g.path_xy, "polylines after the pool was enlarged")
+
+
+def test_queries_that_fill_the_first_pass_scratch_are_planned_again(monkeypatch):
+    """The first pass runs with scratch sized for the usual query (csrc/ecmgpu.cu: plan_alloc); a query that fills it is
+    planned again with the full capacities.  With room for 24 pushes only, most routes of the golden scene take the
+    second pass - and the polylines still equal the reference's bit for bit."""
+    g = Golden("c2_small")
+    monkeypatch.setenv("ECMGPU_PLAN_PUSH", "24")
+    sim = gpu.GpuSim(g.world, 8, g.step)
+    off, xy, n_ok = sim.plan_paths(g.crowd.pos, g.crowd.goal, g.crowd.radius)
+    workers, ms, second = sim.plan_info()
+    print(f"{second} of {g.n} queries took the second pass; {workers} workers, {ms:.3f} ms")
+    assert 0 < second <= g.n
+    assert np.array_equal(off, g.path_off) and n_ok == g.n
+    assert_bits_equal(xy, g.path_xy, "polylines after the second pass")
+    monkeypatch.delenv("ECMGPU_PLAN_PUSH")
+    sim2 = gpu.GpuSim(g.world, 8, g.step)
+    sim2.plan_paths(g.crowd.pos, g.crowd.goal, g.crowd.radius)
+    assert sim2.plan_info()[2] == 0

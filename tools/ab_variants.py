@@ -26,19 +26,31 @@ def main():
     w, c, off, pxy = bench.build_workload(config, int(os.environ["AB_AGENTS"]) if os.environ.get("AB_AGENTS") else None)
     n = c.n
     ref = None
+    auto_cell = None  # what build_grid chooses for this crowd (= 1.7 / sqrt(local density) when this was written)
     default_lib = os.environ.get("ECMGPU_LIB") or os.path.join(os.path.dirname(gpu.__file__), "libecmgpu.so")
     for spec in specs:
         parts = spec.split(",")
         name, _, path = parts[0].partition("=")
         env = dict(p.split("=", 1) for p in parts[1:])
-        for k in [k for k in os.environ if (k.startswith("ECMGPU_") and k != "ECMGPU_LIB") or k == "AB_CELL"]:
+        for k in [k for k in os.environ if (k.startswith("ECMGPU_") and k != "ECMGPU_LIB") or k in ("AB_CELL", "AB_CELL_SCALE")]:
             del os.environ[k]
         os.environ.update(env)
         gpu._lib = None
         gpu.LIB_PATH = os.path.abspath(path) if path else default_lib
-        # AB_CELL: neighbour-grid cell edge in metres (default: chosen from the crowd's density)
+        # AB_CELL: neighbour-grid cell edge in metres (default: chosen from the crowd's density);
+        # AB_CELL_SCALE: the same as a multiple of the automatic choice
+        cell = float(os.environ.get("AB_CELL", "0"))
+        if os.environ.get("AB_CELL_SCALE"):
+            if auto_cell is None:
+                probe = gpu.GpuSim(w, n, float(S.DT), device=0, record_neighbors=False, path_pool_points=int(off[-1]) + 8 * n + 4096)
+                probe.bulk_load(c.pos, c.radius, c.speed, off, pxy)
+                probe.update(1)
+                probe.sync()
+                auto_cell = probe.stats()["neighbor_cell"]
+                probe.close()
+            cell = auto_cell * float(os.environ["AB_CELL_SCALE"])
         sim = gpu.GpuSim(w, n, float(S.DT), device=0, record_neighbors=False, path_pool_points=int(off[-1]) + 8 * n + 4096,
-                         neighbor_cell=float(os.environ.get("AB_CELL", "0")))
+                         neighbor_cell=cell)
         sim.bulk_load(c.pos, c.radius, c.speed, off, pxy)
         sim.update(5 + int(os.environ.get("AB_PREROLL", "0")))  # AB_PREROLL: let the crowd congest first (tick cost drifts)
         sim.sync()
