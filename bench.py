@@ -434,7 +434,10 @@ def run_ours(args):
         return float(sim.stats()["n_active"]) if world == 1 else float(sim.global_active())
 
     def phase_pass(reps):
-        """Per-phase CUDA-event times (launch by launch, no graph), averaged over `reps` ticks of the current state."""
+        """Per-phase CUDA-event times, averaged over `reps` ticks of the current state.  The events are event-record nodes
+        inside the captured tick (csrc/ecmgpu.cu: ecmgpu_set_profiling), i.e. the phases of the same graph the timed windows
+        replay - not of a launch-by-launch tick with its host gaps.  (Strips over NCCL and the KD-tree mode are launch by
+        launch either way.)"""
         sim.set_profiling(True)
         acc_ = {"grid": 0.0, "attract": 0.0, "orca": 0.0, "tick": 0.0}
         for _ in range(reps):

@@ -178,6 +178,7 @@ struct ecmgpu_sim {
     // ---- bookkeeping
     uint64_t ticks = 0, launches = 0;
     bool profiling = false;
+    bool profile_in_graph = true;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // ---- pipelined host I/O (ecmgpu_update_io): two copy streams, double-buffered device staging
@@ -832,8 +833,9 @@ PlanScratch make_plan_scratch(ecmgpu_sim::PlanBufs& b) {
     return sc;
 }
 
-// Per-worker scratch for `want` concurrent queries, within a memory budget: a quarter of the free device memory, at
-// most 48 GB (first pass; env ECMGPU_PLAN_MB overrides) / 8 GB (second pass).
+// Per-worker scratch for `want` concurrent queries, within a memory budget: half of the free device memory, at most
+// 96 GB (first pass; env ECMGPU_PLAN_MB overrides; the 4 M-agent map's graph needs 1.5 MB per query in flight) / a
+// quarter, at most 8 GB (second pass).  ecmgpu_plan_paths keeps up to 2 GB of it between calls.
 //   full = true:  2E + 4 pushes (a query pushes at most once per directed edge, plus the two start vertices) and the
 //                 capacities include/ecm_b200.h documents (2048 graph vertices, 8192 portals, 1024 points).
 //   full = false: the first pass: 2048 portals, and the same room for pushes as long as 32 k such workers fit the
@@ -848,7 +850,7 @@ int plan_alloc(ecmgpu_sim* s, ecmgpu_sim::PlanBufs& b, int want, bool full) {
     const int cap_portals = full ? 8192 : 2048, cap_out = 1024;
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(s, cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = std::min<size_t>(free_b / 4, (size_t)(full ? 8 : 48) << 30);
+    size_t budget = full ? std::min<size_t>(free_b / 4, (size_t)8 << 30) : std::min<size_t>(free_b / 2, (size_t)96 << 30);
     if (!full) if (const char* e = getenv("ECMGPU_PLAN_MB")) budget = (size_t)std::max(16, atoi(e)) << 20;
     const size_t fixed = nV * sizeof(PlanNode) + (size_t)cap_path * 8 + (size_t)cap_portals * 16 + (size_t)cap_out * 8;
     size_t push = 2 * nE + 4;
@@ -1155,6 +1157,7 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
     for (size_t i = 0; i < n; i++) s->h_int_of[i] = s->h_ext_of[i] = (int)i;
     if (const char* e = getenv("ECMGPU_COHERENT")) s->coherent = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_GRAPH")) s->use_graph = atoi(e) != 0;
+    if (const char* e = getenv("ECMGPU_PROFILE_GRAPH")) s->profile_in_graph = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_COMPACT")) s->compact = atoi(e) != 0;
     s->h_path_pool.reserve(std::min<size_t>(pool, 1 << 20));
     *out = s;
@@ -1461,7 +1464,9 @@ int ecmgpu_update(ecmgpu_sim* s) {
     // NCCL transport the tick is submitted launch by launch.  The peer transport is plain kernels and memsets.
     const bool nccl_tick = s->strips_on && !s->local_transport && s->n_ranks > 1 && !s->p2p;
     // the KD-tree mode submits a library sort per tree level: launch by launch as well
-    if (s->use_graph && !nccl_tick && !s->profiling && s->n_slots > 0 && s->neighbor_mode == ECMGPU_NEIGHBORS_EXACT) {
+    // (profiling: the phase events are captured as event-record nodes, so the phases are timed inside the very tick the
+    // unprofiled run replays, not in a launch-by-launch one with its host gaps; ECMGPU_PROFILE_GRAPH=0: launch by launch)
+    if (s->use_graph && !nccl_tick && (!s->profiling || s->profile_in_graph) && s->n_slots > 0 && s->neighbor_mode == ECMGPU_NEIGHBORS_EXACT) {
         CUDA_TRY(s, cudaSetDevice(s->prm.device));
         int rc = ensure_ready(s);  // host-side (re)builds happen outside the capture
         if (rc) return rc;
@@ -1997,6 +2002,11 @@ int ecmgpu_plan_paths(ecmgpu_sim* s, int n, const float* start_xy, const float* 
     if (have > 0) CUDA_TRY(s, cudaMemcpy(out_xy, d_pool.p, sizeof(float2) * (size_t)have, cudaMemcpyDeviceToHost));
     if (out_points) *out_points = used;
     d_start.free(); d_goal.free(); d_pool.free(); d_cl.free(); d_off.free(); d_len.free(); d_cursor.free(); d_st.free();
+    // a batch that took tens of gigabytes of scratch (the routes of a whole crowd) gives them back; the scratch of the
+    // per-tick replans (a few hundred queries) stays for the next call
+    const size_t held = (size_t)s->pl.workers * ((size_t)s->n_vertices * sizeof(PlanNode) + (size_t)s->pl.cap_push * 8 + (size_t)s->pl.cap_path * 8 +
+                                                  (size_t)s->pl.cap_portals * 16 + (size_t)s->pl.cap_out * 8);
+    if (held > ((size_t)2 << 30)) plan_free(s);
     return ECMGPU_OK;
 }
 
@@ -2180,6 +2190,7 @@ void ecmgpu_abi_sizes(int32_t out[4]) {
 
 int ecmgpu_set_profiling(ecmgpu_sim* s, int on) {
     if (!s) return ECMGPU_ERR_INVALID;
+    if (s->profiling != (on != 0)) s->config_epoch++;  // the captured tick gains / loses its event-record nodes
     s->profiling = on != 0;
     s->ev_valid = false;
     return ECMGPU_OK;

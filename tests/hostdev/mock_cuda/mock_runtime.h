@@ -64,7 +64,8 @@ static inline double hd_now_ms() { return std::chrono::duration<double, std::mil
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new HdEvent{hd_now_ms()}; return cudaSuccess; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new HdEvent{hd_now_ms()}; return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
-static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { if (!hd_capturing) e->t_ms = hd_now_ms(); return cudaSuccess; }
+// captured like every other stream operation: an event-record node stamps the event at every graph launch
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { hd_enqueue([=] { e->t_ms = hd_now_ms(); }); return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t_ms - a->t_ms); return cudaSuccess; }
 static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { hd_capturing = new HdGraph; return cudaSuccess; }

@@ -47,6 +47,14 @@ def main():
         print(json.dumps({"budget_mb": mb, "queries": n, "first_call_s": round(warm, 3), "s": round(best, 3), "us_per_query": round(best / n * 1e6, 3),
                           "workers": workers, "second_pass": second, "kernel_ms": round(kern, 2), "kernel_us_per_query": round(kern * 1e3 / n, 3), "ok": int(ok), "same_as_first": same}), flush=True)
         sim.close()
+    if os.environ.get("PROBE_HOST"):  # the host planner (csrc/host/planner.cpp) on all cores of this box, same queries
+        from ecmgenerator_b200 import host
+        m = min(n, int(os.environ["PROBE_HOST"]))
+        t = time.time()
+        ho, hp, hok = host.plan_paths(w, c.pos[:m], c.goal[:m], c.radius[:m], threads=0)
+        dt = time.time() - t
+        print(json.dumps({"host_planner": True, "cores": os.cpu_count(), "queries": m, "s": round(dt, 3), "us_per_query": round(dt / m * 1e6, 3),
+                          "same_as_device": bool(m == n and np.array_equal(ho, ref[0]) and np.array_equal(hp.view(np.uint32), ref[1].view(np.uint32)))}), flush=True)
 
 
 if __name__ == "__main__":
