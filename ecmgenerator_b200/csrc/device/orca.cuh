@@ -317,6 +317,71 @@ __device__ __noinline__ void randomized_lp3d(int nObst, const Cons* cs, int tota
     }
 }
 
+// The same program for a whole warp of parked agents (k_fallback), one per lane, lanes without an entry pass
+// valid = false.  Per lane the operations and their order are those of randomized_lp3d above, hence the same bits; what
+// changes is who waits for whom.  Run lane by lane, a warp of 32 different programs executed every lane's constraint
+// loop, projection loop and inner 2-D program one after the other (ncu: k_fallback 60 us per tick for the 13 % of the
+// congested 1 M crowd that needs it).  Here (A) every lane skips at its own pace to ITS next constraint that is violated
+// by more than the penetration reached so far - a cheap test - then (B) the lanes that stopped build their projected
+// constraints and run the inner program TOGETHER, through the warp-convergent randomized_lp<true>.
+__device__ __forceinline__ void randomized_lp3d_warp(bool valid, int nObst, const Cons* cs, int total, float maxSpeed, int failed, v2& outV, Cons* proj) {
+    float maxPen = 0.0f;
+    int i = failed;
+    bool live = valid && i < total;
+    while (__any_sync(0xffffffffu, live)) {
+        bool hit = false;
+        Cons ci = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        v2 dir = V(0.0f, 0.0f);
+        while (__any_sync(0xffffffffu, live && !hit)) {  // (A)
+            if (live && !hit) {
+                ci = cs[i];
+                dir = vright(cn(ci));
+                if (odet(dir, vsub(cp(ci), outV)) <= maxPen) { i++; live = i < total; }
+                else hit = true;
+            }
+        }
+        // (B) the obstacle constraints as they are, the agent constraints before i projected onto constraint i
+        int np = 0;
+        {
+            const int trips = warp_max_trip<true>(hit ? nObst : 0);
+            for (int k = 0; k < trips; k++) {
+                warp_align<true>();
+                if (hit && k < nObst) proj[np++] = cs[k];
+            }
+        }
+        {
+            const int trips = warp_max_trip<true>(hit ? i - nObst : 0);
+            for (int jj = 0; jj < trips; jj++) {
+                warp_align<true>();
+                const int j = nObst + jj;
+                if (hit && j < i) {
+                    const Cons cj = cs[j];
+                    const float det = odet(dir, vright(cn(cj)));
+                    v2 pt;
+                    bool keep = true;
+                    if (fabsf(det) <= kEpsilon) {
+                        if (odot(cn(ci), cn(cj)) > 0.0f) keep = false;
+                        pt = vmul(vadd(cp(ci), cp(cj)), 0.5f);
+                    } else {
+                        const float t = odiv(odet(vright(cn(cj)), vsub(cp(ci), cp(cj))), det);
+                        pt = ovmad(cp(ci), dir, t);
+                    }
+                    if (keep) proj[np++] = cmake(pt, ovnormalized(vsub(cn(cj), cn(ci))));
+                }
+            }
+        }
+        v2 o = outV;
+        const int n_in = hit ? np : 0;
+        const int r = randomized_lp<true>(proj, n_in, cn(ci), maxSpeed, true, o);
+        if (hit) {
+            if (!(r < np)) outV = o;  // an infeasible inner program leaves the velocity as it was (ORCA.cpp:658-664)
+            maxPen = odet(dir, vsub(cp(ci), outV));
+            i++;
+            live = i < total;
+        }
+    }
+}
+
 struct OrcaResult {
     v2 velocity;
     unsigned status;  // ECMGPU_ST_OBST_OVERFLOW | ECMGPU_ST_LP3D | kLp3dDeferred

@@ -375,18 +375,28 @@ __device__ __forceinline__ unsigned finish_agent(const TickView& t, int p, const
     return (r.status & ~kLp3dDeferred) | extra;
 }
 
-// RandomizedLP3D + integration for the agents k_orca parked, one thread per entry (second half of k_fallback).
+// RandomizedLP3D + integration for the agents k_orca parked, one lane per entry, a warp's 32 entries in step
+// (randomized_lp3d_warp; second half of k_fallback).  Convergent: every lane of the warp makes the same trips.
+// Measured against every lane running its own program: tick 0.497 -> 0.489 ms on the congested 1 M crowd
+// (profiles/r03i_ab_congested_lp3d.jsonl: base vs lanewise), same state bit for bit.
 __device__ __forceinline__ void lp3d_parked(const TickView& t) {
     const Lp3dQueue dq = t.lp3d;
     const int n = (int)min(*dq.count, (unsigned long long)dq.cap);
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        const int4 h = dq.hdr[e];  // (p, nObst, nc, failed)
-        const float4 o = dq.out[e];
+    const int lane = threadIdx.x & 31;
+    const int stride = gridDim.x * blockDim.x;
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
+        const int e = base + lane;
+        const bool valid = e < n;
+        int4 h = make_int4(0, 0, 0, 0);  // (p, nObst, nc, failed)
+        float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (valid) { h = dq.hdr[e]; o = dq.out[e]; }
         Cons cs[kMaxCons], proj[kMaxCons];
-        for (int i = 0; i < h.z; i++) cs[i] = dq.cs[(size_t)i * dq.cap + e];
+        const int trips = warp_max_trip<true>(h.z);
+        for (int i = 0; i < trips; i++)
+            if (i < h.z) cs[i] = dq.cs[(size_t)i * dq.cap + e];
         v2 out = V(o.x, o.y);
-        randomized_lp3d(h.y, cs, h.z, o.z, h.w, out, proj);
-        integrate_agent(t, t.sc.s_slot[h.x], t.sc.s_pos[h.x], t.sc.s_vel[h.x], out);
+        randomized_lp3d_warp(valid, h.y, cs, h.z, o.z, h.w, out, proj);
+        if (valid) integrate_agent(t, t.sc.s_slot[h.x], t.sc.s_pos[h.x], t.sc.s_vel[h.x], out);
     }
 }
 
@@ -448,6 +458,9 @@ __global__ void __launch_bounds__(ECM_ORCA_BLOCK, ECM_ORCA_MINBLOCKS) k_orca_til
 // The stragglers of a tick, one kernel: (a) warp-per-agent exhaustive neighbour search + ORCA for agents
 // whose ring budget ran out, (b) LP3D + integration for the agents k_orca parked.
 // mode 0: full tick; mode 1: neighbour query only (ecmgpu_find_neighbors)
+#ifndef ECM_FALLBACK_CTAS
+#define ECM_FALLBACK_CTAS 4  // CTAs per SM in the tick's launch (8 or 16: within 0.3 %, profiles/r03i_ab_congested_lp3d.jsonl)
+#endif
 __global__ void __launch_bounds__(128) k_fallback(TickView t, int mode) {
     const int warps_total = (gridDim.x * blockDim.x) >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -1414,6 +1414,16 @@ int ecmgpu_destroy_agent(ecmgpu_sim* s, int slot) {
     return ECMGPU_OK;
 }
 
+// Phase boundary for ecmgpu_last_tick_ms.  Inside a stream capture a plain cudaEventRecord only orders captured work;
+// the external flag makes it an event-record node that stamps the event at every replay of the graph.
+cudaError_t record_phase_event(ecmgpu_sim* s, int i) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaError_t e = cudaStreamIsCapturing(s->stream, &st);
+    if (e != cudaSuccess) return e;
+    if (st == cudaStreamCaptureStatusActive) return cudaEventRecordWithFlags(s->ev[i], s->stream, cudaEventRecordExternal);
+    return cudaEventRecord(s->ev[i], s->stream);
+}
+
 int ecmgpu_update_phase(ecmgpu_sim* s, int phase) {
     if (!s) return ECMGPU_ERR_INVALID;
     if (phase < 0 || phase > 2) return fail(s, ECMGPU_ERR_INVALID, "ecmgpu_update_phase: phase must be 0, 1 or 2");
@@ -1423,33 +1433,33 @@ int ecmgpu_update_phase(ecmgpu_sim* s, int phase) {
     if (rc) return rc;
     TickView t = make_view(s);
     if (phase == 0) {
-        if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[0], s->stream));
+        if (s->profiling) CUDA_TRY(s, record_phase_event(s, 0));
         return s->strips_on ? enqueue_pack(s, t) : ECMGPU_OK;
     }
     if (phase == 1) return s->strips_on ? enqueue_exchange(s, t) : ECMGPU_OK;
     rc = enqueue_grid_build(s, t);
     if (rc) return rc;
-    if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[1], s->stream));
+    if (s->profiling) CUDA_TRY(s, record_phase_event(s, 1));
     const int nb = div_up(launch_slots(s) + (s->strips_on ? 2 * s->cap_halo + s->cap_self : 0), 128);
     if (s->neighbor_mode == ECMGPU_NEIGHBORS_KDTREE) {
         if (s->strips_on) return fail(s, ECMGPU_ERR_INVALID, "the KD-tree neighbour mode runs on a single handle (no strips)");
         k_attract<<<nb, 128, 0, s->stream>>>(t);
         s->launches++;
-        if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
+        if (s->profiling) CUDA_TRY(s, record_phase_event(s, 2));
         rc = enqueue_kd_orca(s, t, nb * 128);
         if (rc) return rc;
         s->launches -= 2;  // k_attract and k_orca_kd are counted above (3 are added below)
     } else if (s->compact && s->strips_on) {  // one resident wave over the row tiles that exist (tick.cuh)
         k_attract_tiles<<<kSMs * ECM_ATTRACT_MINBLOCKS, 128, 0, s->stream>>>(t);
-        if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
+        if (s->profiling) CUDA_TRY(s, record_phase_event(s, 2));
         k_orca_tiles<<<kSMs * ECM_ORCA_MINBLOCKS, ECM_ORCA_BLOCK, 0, s->stream>>>(t);
     } else {
         k_attract<<<nb, 128, 0, s->stream>>>(t);
-        if (s->profiling) CUDA_TRY(s, cudaEventRecord(s->ev[2], s->stream));
+        if (s->profiling) CUDA_TRY(s, record_phase_event(s, 2));
         k_orca<<<div_up(nb * 128, ECM_ORCA_BLOCK), ECM_ORCA_BLOCK, 0, s->stream>>>(t);
     }
-    k_fallback<<<kSMs * 4, 128, 0, s->stream>>>(t, 0);
-    if (s->profiling) { CUDA_TRY(s, cudaEventRecord(s->ev[3], s->stream)); s->ev_valid = true; }
+    k_fallback<<<kSMs * ECM_FALLBACK_CTAS, 128, 0, s->stream>>>(t, 0);
+    if (s->profiling) { CUDA_TRY(s, record_phase_event(s, 3)); s->ev_valid = true; }
     s->launches += 3;
     s->ticks++;
     CUDA_TRY(s, cudaGetLastError());

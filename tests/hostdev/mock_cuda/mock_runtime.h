@@ -66,6 +66,10 @@ static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 // captured like every other stream operation: an event-record node stamps the event at every graph launch
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { hd_enqueue([=] { e->t_ms = hd_now_ms(); }); return cudaSuccess; }
+enum cudaStreamCaptureStatus { cudaStreamCaptureStatusNone = 0, cudaStreamCaptureStatusActive = 1 };
+static const unsigned cudaEventRecordExternal = 1u;
+static inline cudaError_t cudaStreamIsCapturing(cudaStream_t, cudaStreamCaptureStatus* st) { *st = hd_capturing ? cudaStreamCaptureStatusActive : cudaStreamCaptureStatusNone; return cudaSuccess; }
+static inline cudaError_t cudaEventRecordWithFlags(cudaEvent_t e, cudaStream_t st, unsigned) { return cudaEventRecord(e, st); }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t_ms - a->t_ms); return cudaSuccess; }
 static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { hd_capturing = new HdGraph; return cudaSuccess; }

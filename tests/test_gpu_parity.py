@@ -300,6 +300,35 @@ def test_large_crowd_properties():
     assert np.isfinite(v).all() and np.linalg.norm(v, axis=1).max() <= 1.4 * 1.01
 
 
+def test_phase_timings_are_taken_inside_the_graph_tick():
+    """ecmgpu_set_profiling: the phase events are event-record nodes of the captured tick (bench.py's roofline times
+    k_orca through them), so profiling neither changes the results nor switches to another way of running the tick."""
+    g = Golden("jam_small")
+    a = gpu.GpuSim(g.world, g.n, g.step)
+    b = gpu.GpuSim(g.world, g.n, g.step)
+    for s in (a, b):
+        s.bulk_load(g.crowd.pos, g.crowd.radius, g.crowd.speed, g.path_off, g.path_xy)
+    a.update(3)
+    b.update(3)
+    l0 = b.stats()["kernel_launches"]
+    b.update(1)
+    per_tick = b.stats()["kernel_launches"] - l0
+    a.set_profiling(True)
+    for _ in range(5):
+        l0 = a.stats()["kernel_launches"]
+        a.update(1)
+        ms = a.last_tick_ms()
+        assert a.stats()["kernel_launches"] - l0 == per_tick
+        assert all(np.isfinite(v) and v >= 0.0 for v in ms.values()) and ms["tick"] > 0.0
+        assert abs(ms["grid"] + ms["attract"] + ms["orca"] - ms["tick"]) <= 1e-3 + 0.02 * ms["tick"]
+    a.set_profiling(False)
+    a.update(2)
+    b.update(6)
+    assert_bits_equal(a.read(gpu.POS, 0, g.n), b.read(gpu.POS, 0, g.n), "positions with and without profiling")
+    with pytest.raises(gpu.EcmGpuError):
+        a.last_tick_ms()
+
+
 def test_update_io_pipeline_matches_plain_update():
     """ecmgpu_update_io (overlapped upload | tick | download) gives the same state as write + update + read."""
     g = Golden("c2_small")
