@@ -68,6 +68,8 @@ static inline void __nanosleep(unsigned) { sched_yield(); }  // a spinning lane 
 template <class T, class U>
 static inline T atomicAdd(T* p, U v) { T old = *p; *p = (T)(old + (T)v); return old; }
 static inline int atomicMax(int* p, int v) { int old = *p; if (v > old) *p = v; return old; }
+template <class T>
+static inline T atomicCAS(T* p, T cmp, T val) { T old = *p; if (old == cmp) *p = val; return old; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
