@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kPackBlock) k_pack_walk(AgentArrays ag, StripV
 
 // k_collect_owned (tick.cuh) over the list: the records of ecmgpu_update_io_owned.
 __global__ void __launch_bounds__(kCollectBlock) k_collect_owned_walk(WalkView walk, const unsigned char* __restrict__ active, const float2* __restrict__ pos,
-                                                                      const float2* __restrict__ vel, AgentRec* __restrict__ out, int* __restrict__ count,
+                                                                      const float2* __restrict__ vel, AgentRec* __restrict__ out, int out_cap, int* __restrict__ count,
                                                                       const int* __restrict__ ext_of) {
     __shared__ int s_warp[33];
     const int n = *walk.n;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kCollectBlock) k_collect_owned_walk(WalkView w
         const int i = idx < n ? walk.list[idx] : 0;
         const bool mine = idx < n && active[i];
         const int e = cta_reserve(mine, count, s_warp);
-        if (mine) {
+        if (mine && e < out_cap) {
             const float2 p = pos[i], v = vel[i];
             AgentRec r;
             r.slot = ext_of ? ext_of[i] : i; r.x = p.x; r.y = p.y; r.vx = v.x; r.vy = v.y;

@@ -632,6 +632,26 @@ __global__ void __launch_bounds__(256) k_scatter_slots(int count, int first, con
     if (i < count) dst[int_of[first + i]] = src[i];
 }
 
+// ecmgpu_update_io with renumbered arrays: the host's slot order in and out in ONE kernel each way (int_of read once)
+__global__ void __launch_bounds__(256) k_io_adopt(int count, const int* __restrict__ int_of, const float2* __restrict__ in_pos,
+                                                  const float2* __restrict__ in_vel, float2* __restrict__ pos, float2* __restrict__ vel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int a = int_of[i];
+    if (in_pos) pos[a] = in_pos[i];
+    if (in_vel) vel[a] = in_vel[i];
+}
+__global__ void __launch_bounds__(256) k_io_publish(int count, const int* __restrict__ int_of, const float2* __restrict__ pos,
+                                                    const float2* __restrict__ vel, const unsigned char* __restrict__ active,
+                                                    float2* __restrict__ out_pos, float2* __restrict__ out_vel, unsigned char* __restrict__ out_active) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int a = int_of[i];
+    if (out_pos) out_pos[i] = pos[a];
+    if (out_vel) out_vel[i] = vel[a];
+    if (out_active) out_active[i] = active[a];
+}
+
 // ---- host I/O as records of owned agents (ecmgpu_update_io_owned) --------------------------------
 struct AgentRec {  // == ecmgpu_agent_rec (include/ecm_b200.h)
     int slot;
@@ -654,13 +674,13 @@ __global__ void __launch_bounds__(256) k_apply_records(int n, const AgentRec* __
 // Compacts the owned agents into records (one atomic per CTA; ascending slots within a CTA).
 constexpr int kCollectBlock = 1024;
 __global__ void __launch_bounds__(kCollectBlock) k_collect_owned(int n_slots, const unsigned char* __restrict__ active, const float2* __restrict__ pos,
-                                                                 const float2* __restrict__ vel, AgentRec* __restrict__ out, int* __restrict__ count,
+                                                                 const float2* __restrict__ vel, AgentRec* __restrict__ out, int out_cap, int* __restrict__ count,
                                                                  const int* __restrict__ ext_of) {
     __shared__ int s_warp[33];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool mine = i < n_slots && active[i];
     const int e = cta_reserve(mine, count, s_warp);
-    if (!mine) return;
+    if (!mine || e >= out_cap) return;  // `out` may be the caller's own (pinned) buffer: never past its end; the count tells
     const float2 p = pos[i], v = vel[i];
     AgentRec r;
     r.slot = ext_of ? ext_of[i] : i; r.x = p.x; r.y = p.y; r.vx = v.x; r.vy = v.y;

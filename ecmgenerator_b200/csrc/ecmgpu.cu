@@ -184,6 +184,7 @@ struct ecmgpu_sim {
     // ---- pipelined host I/O (ecmgpu_update_io): two copy streams, double-buffered device staging
     struct IoPipe {
         bool ready = false;
+        bool direct_ok = false;  // ECMGPU_IO_DIRECT=1: owned records straight into the caller's pinned buffer (measured slower, see ecmgpu_update_io_owned)
         int cap = 0;
         cudaStream_t s_in = nullptr, s_out = nullptr;
         // staging, two generations each.  Dense calls: in = [pos 8n | vel 8n], out = [pos 8n | vel 8n | active n];
@@ -1158,6 +1159,7 @@ int ecmgpu_create(const ecmgpu_params* params, ecmgpu_sim** out) {
     if (const char* e = getenv("ECMGPU_COHERENT")) s->coherent = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_GRAPH")) s->use_graph = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_PROFILE_GRAPH")) s->profile_in_graph = atoi(e) != 0;
+    if (const char* e = getenv("ECMGPU_IO_DIRECT")) s->io.direct_ok = atoi(e) != 0;
     if (const char* e = getenv("ECMGPU_COMPACT")) s->compact = atoi(e) != 0;
     s->h_path_pool.reserve(std::min<size_t>(pool, 1 << 20));
     *out = s;
@@ -1676,9 +1678,10 @@ int ecmgpu_update_io(ecmgpu_sim* s, int count, const float* in_pos, const float*
     if (s->perm_identity) {
         if (in_pos) CUDA_TRY(s, cudaMemcpyAsync(s->d_pos.p, si, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
         if (in_vel) CUDA_TRY(s, cudaMemcpyAsync(s->d_vel.p, si + n8, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
-    } else if (count > 0) {
-        if (in_pos) launch_remap(s, false, 8, count, 0, si, s->d_pos.p);
-        if (in_vel) launch_remap(s, false, 8, count, 0, si + n8, s->d_vel.p);
+    } else if (count > 0 && (in_pos || in_vel)) {
+        k_io_adopt<<<div_up(count, 256), 256, 0, s->stream>>>(count, s->d_int_of.p, in_pos ? (const float2*)si : nullptr,
+                                                              in_vel ? (const float2*)(si + n8) : nullptr, s->d_pos.p, s->d_vel.p);
+        s->launches++;
     }
     CUDA_TRY(s, cudaEventRecord(io.in_consumed[b], s->stream));
     rc = ecmgpu_update(s);
@@ -1688,10 +1691,11 @@ int ecmgpu_update_io(ecmgpu_sim* s, int count, const float* in_pos, const float*
         if (out_pos) CUDA_TRY(s, cudaMemcpyAsync(so, s->d_pos.p, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
         if (out_vel) CUDA_TRY(s, cudaMemcpyAsync(so + n8, s->d_vel.p, sizeof(float2) * c, cudaMemcpyDeviceToDevice, s->stream));
         if (out_active) CUDA_TRY(s, cudaMemcpyAsync(so + 2 * n8, s->d_active.p, c, cudaMemcpyDeviceToDevice, s->stream));
-    } else if (count > 0) {
-        if (out_pos) launch_remap(s, true, 8, count, 0, s->d_pos.p, so);
-        if (out_vel) launch_remap(s, true, 8, count, 0, s->d_vel.p, so + n8);
-        if (out_active) launch_remap(s, true, 1, count, 0, s->d_active.p, so + 2 * n8);
+    } else if (count > 0 && (out_pos || out_vel || out_active)) {
+        k_io_publish<<<div_up(count, 256), 256, 0, s->stream>>>(count, s->d_int_of.p, s->d_pos.p, s->d_vel.p, s->d_active.p,
+                                                                out_pos ? (float2*)so : nullptr, out_vel ? (float2*)(so + n8) : nullptr,
+                                                                out_active ? so + 2 * n8 : nullptr);
+        s->launches++;
     }
     CUDA_TRY(s, cudaEventRecord(io.tick_done[b], s->stream));
     // download
@@ -1737,25 +1741,41 @@ int ecmgpu_update_io_owned(ecmgpu_sim* s, int n_in, const ecmgpu_agent_rec* in, 
     if (rc) return rc;
     CUDA_TRY(s, cudaStreamWaitEvent(s->stream, io.out_done[b], 0));
     CUDA_TRY(s, cudaMemsetAsync(so_count, 0, sizeof(int), s->stream));
+    // Where the records go.  The host cannot know this tick's count when the download is issued, so the staged copy is
+    // sized from a bound (the last confirmed count plus room for migrants).  ECMGPU_IO_DIRECT=1 (opt-in) lets the collect
+    // kernel store the records straight into `out` when that is pinned memory the device can address: exactly the owned
+    // ones, no staging, no bound - but 20-byte records stored by SM threads cross PCIe as small writes and the kernel sits
+    // on the tick's stream: measured 4.1 ms instead of 1.4 ms per tick end to end on the 4 M map on 8 GPUs
+    // (profiles/r03p_bench_c4_4m_n8_direct_io.json).  Kept for hosts behind a coherent link.
+    AgentRec* direct = nullptr;
+    if (io.direct_ok && out_cap > 0) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, out) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) direct = (AgentRec*)pa.devicePointer;
+        else cudaGetLastError();  // an unregistered pointer is not an error of this call
+    }
     if (s->n_slots > 0) {
         const StripView sv = make_strip_view(s);
         const int* ext = s->perm_identity ? nullptr : s->d_ext_of.p;
-        if (sv.walk.list && !s->walk_dirty) k_collect_owned_walk<<<kSMs * 2, kCollectBlock, 0, s->stream>>>(sv.walk, s->d_active.p, s->d_pos.p, s->d_vel.p, so, so_count, ext);
-        else k_collect_owned<<<div_up(s->n_slots, kCollectBlock), kCollectBlock, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, s->d_vel.p, so, so_count, ext);
+        AgentRec* dst = direct ? direct : so;
+        const int dst_cap = direct ? out_cap : s->n_slots;
+        if (sv.walk.list && !s->walk_dirty) k_collect_owned_walk<<<kSMs * 2, kCollectBlock, 0, s->stream>>>(sv.walk, s->d_active.p, s->d_pos.p, s->d_vel.p, dst, dst_cap, so_count, ext);
+        else k_collect_owned<<<div_up(s->n_slots, kCollectBlock), kCollectBlock, 0, s->stream>>>(s->n_slots, s->d_active.p, s->d_pos.p, s->d_vel.p, dst, dst_cap, so_count, ext);
         s->launches++;
     }
     CUDA_TRY(s, cudaEventRecord(io.tick_done[b], s->stream));
-    // how many records to bring back: the host cannot know the count of this tick yet
-    long long bound = s->n_slots;
-    if (io.owned_confirmed >= 0) {
-        const long long per_tick = s->strips_on ? 2ll * s->cap_migr : 0ll;
-        // every tick since the confirmed one - through this call or plain ecmgpu_update - may have brought migrants in
-        bound = std::min(bound, io.owned_confirmed + per_tick * (long long)(s->ticks - io.owned_confirmed_tick));
-    }
-    const int copied = (int)std::min<long long>(bound, out_cap);
+    int copied = out_cap;
     CUDA_TRY(s, cudaStreamWaitEvent(io.s_out, io.tick_done[b], 0));
     CUDA_TRY(s, cudaMemcpyAsync(out_count, so_count, sizeof(int), cudaMemcpyDeviceToHost, io.s_out));
-    if (copied) CUDA_TRY(s, cudaMemcpyAsync(out, so, sizeof(ecmgpu_agent_rec) * (size_t)copied, cudaMemcpyDeviceToHost, io.s_out));
+    if (!direct) {
+        long long bound = s->n_slots;
+        if (io.owned_confirmed >= 0) {
+            const long long per_tick = s->strips_on ? 2ll * s->cap_migr : 0ll;
+            // every tick since the confirmed one - through this call or plain ecmgpu_update - may have brought migrants in
+            bound = std::min(bound, io.owned_confirmed + per_tick * (long long)(s->ticks - io.owned_confirmed_tick));
+        }
+        copied = (int)std::min<long long>(bound, out_cap);
+        if (copied) CUDA_TRY(s, cudaMemcpyAsync(out, so, sizeof(ecmgpu_agent_rec) * (size_t)copied, cudaMemcpyDeviceToHost, io.s_out));
+    }
     CUDA_TRY(s, cudaEventRecord(io.out_done[b], io.s_out));
     CUDA_TRY(s, cudaEventRecord(io.ticket_done[io.calls % io.kTickets], io.s_out));
     io.owned_count[io.calls % io.kTickets] = out_count;

@@ -145,10 +145,12 @@ int ecmgpu_io_wait(ecmgpu_sim* sim, uint64_t ticket);
  * every rank transfers its share of the crowd.  `in` (PINNED, may be NULL with n_in = 0): records whose
  * slot this handle owns overwrite position and velocity before the tick, other records are ignored.
  * After the tick `out` (PINNED, room for out_cap records) receives one record per owned agent, in no
- * particular order, and *out_count (PINNED) their number.  The copy is sized from the count confirmed by
- * the last ecmgpu_io_wait plus the migrants that may have arrived since, so the first calls after a
- * spawn / bulk load move max_agents records and later ones only the owned share; ecmgpu_io_wait fails
- * with ECMGPU_ERR_CAPACITY when out_cap was too small for the tick's count. */
+ * particular order, and *out_count (PINNED) their number.  The records are staged on the device and the
+ * copy is sized from the count confirmed by the last ecmgpu_io_wait plus the migrants that may have arrived
+ * since (the first calls after a spawn / bulk load move max_agents records).  ECMGPU_IO_DIRECT=1 (opt-in,
+ * slower over PCIe) stores them straight into `out` when that is pinned memory the device can address.
+ * ecmgpu_io_wait fails with ECMGPU_ERR_CAPACITY when out_cap was too small for the tick's count (nothing is
+ * written past out_cap). */
 typedef struct ecmgpu_agent_rec {
     int32_t slot;
     float x, y, vx, vy;

@@ -522,8 +522,8 @@ int emu_collect_owned(void* h, AgentRec* out) {
     Emu* e = (Emu*)h;
     int count = 0;
     StripView sv = e->sview();
-    if (sv.walk.list && !e->walk_dirty) launch(19, [&] { k_collect_owned_walk(sv.walk, e->active.data(), e->pos.data(), e->vel.data(), out, &count, nullptr); }, kCollectBlock);
-    else launch(e->n_slots, [&] { k_collect_owned(e->n_slots, e->active.data(), e->pos.data(), e->vel.data(), out, &count, nullptr); }, kCollectBlock);
+    if (sv.walk.list && !e->walk_dirty) launch(19, [&] { k_collect_owned_walk(sv.walk, e->active.data(), e->pos.data(), e->vel.data(), out, e->n, &count, nullptr); }, kCollectBlock);
+    else launch(e->n_slots, [&] { k_collect_owned(e->n_slots, e->active.data(), e->pos.data(), e->vel.data(), out, e->n, &count, nullptr); }, kCollectBlock);
     return count;
 }
 void emu_apply_records(void* h, int n, const AgentRec* rec) {

@@ -70,6 +70,10 @@ enum cudaStreamCaptureStatus { cudaStreamCaptureStatusNone = 0, cudaStreamCaptur
 static const unsigned cudaEventRecordExternal = 1u;
 static inline cudaError_t cudaStreamIsCapturing(cudaStream_t, cudaStreamCaptureStatus* st) { *st = hd_capturing ? cudaStreamCaptureStatusActive : cudaStreamCaptureStatusNone; return cudaSuccess; }
 static inline cudaError_t cudaEventRecordWithFlags(cudaEvent_t e, cudaStream_t st, unsigned) { return cudaEventRecord(e, st); }
+// every "device" pointer of the mock is host memory the kernels can address
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; void* devicePointer; void* hostPointer; };
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) { a->type = cudaMemoryTypeHost; a->device = 0; a->devicePointer = (void*)p; a->hostPointer = (void*)p; return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t_ms - a->t_ms); return cudaSuccess; }
 static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { hd_capturing = new HdGraph; return cudaSuccess; }

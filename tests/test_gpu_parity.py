@@ -361,9 +361,12 @@ def test_update_io_pipeline_matches_plain_update():
         x.free()
 
 
-def test_update_io_owned_records_match_plain_update():
+@pytest.mark.parametrize("direct", [1, 0])
+def test_update_io_owned_records_match_plain_update(direct, monkeypatch):
     """ecmgpu_update_io_owned: records in -> tick -> records of the live agents out, pipelined two deep, equals
-    write + update + read; agents that arrive drop out of the records; the copy shrinks to the confirmed count."""
+    write + update + read; agents that arrive drop out of the records.  direct = 0 (default): staged copy sized from the
+    confirmed count; 1 (opt-in): the collect kernel stores the records straight into the caller's pinned buffer."""
+    monkeypatch.setenv("ECMGPU_IO_DIRECT", str(direct))
     g = Golden("c2_small")
     n = g.n
     a = gpu.GpuSim(g.world, n + 5, g.step)

@@ -24,7 +24,8 @@ SUBSET = [
     "tests/test_gpu_parity.py::test_outside_world_and_bin_fallback_paths",
     "tests/test_gpu_parity.py::test_obstacle_lists_match_oracle",
     "tests/test_gpu_parity.py::test_update_io_pipeline_matches_plain_update",
-    "tests/test_gpu_parity.py::test_update_io_owned_records_match_plain_update",
+    "tests/test_gpu_parity.py::test_update_io_owned_records_match_plain_update[1]",
+    "tests/test_gpu_parity.py::test_update_io_owned_records_match_plain_update[0]",
     # the C++ drop-in Simulator (libecmsim.so): the mock library is preloaded, so its ecmgpu_* symbols are the ones bound
     "tests/test_gpu_simulator_dropin.py::test_spawn_update_getters_match_reference",
     "tests/test_gpu_simulator_dropin.py::test_dropin_matches_c_oracle_with_host_planner",
