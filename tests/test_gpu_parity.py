@@ -271,6 +271,30 @@ def test_obstacle_lists_match_oracle():
     assert sim.stats()["obstacle_overflows"] == 0
 
 
+def test_obstacle_range_follows_speeds_written_later():
+    """the per-bin obstacle lists are sized from 10 * speed + radius.  Speeds written AFTER the load (three
+    times the loaded ones for every third agent) must widen them, or find_obstacles silently misses segments."""
+    g = Golden("c2_small")
+    sim = gpu.GpuSim(g.world, g.n + 8, g.step)
+    sim.bulk_load(g.crowd.pos, g.crowd.radius, g.crowd.speed, g.path_off, g.path_xy)
+    sim.step(1)  # the bins exist, built for the loaded speeds
+    fast = g.crowd.speed.copy()
+    fast[::3] *= 3.0
+    sim.write(gpu.SPEED, fast)
+    sim.write(gpu.POS, g.crowd.pos)
+    ora = OracleSim(g.world, g.n + 8, g.step, "exact-knn")
+    ora.bulk_load(g.crowd.pos, g.crowd.radius, fast, g.path_off, g.path_xy)
+    longer = 0
+    for slot in range(0, g.n, 3):
+        a, b = sim.query_obstacles(slot), ora.query_obstacles(slot)
+        assert np.array_equal(a, b), slot
+        longer += len(b)
+    slow = OracleSim(g.world, g.n + 8, g.step, "exact-knn")
+    slow.bulk_load(g.crowd.pos, g.crowd.radius, g.crowd.speed, g.path_off, g.path_xy)
+    assert longer > sum(len(slow.query_obstacles(slot)) for slot in range(0, g.n, 3)), "the wider range must matter in this scene"
+    assert sim.stats()["obstacle_overflows"] == 0
+
+
 def test_large_crowd_properties():
     """BASELINE-size check without an oracle run: invariants of one tick on a big crowd."""
     w = S.world_c3()
