@@ -7,13 +7,14 @@ OUT=gpurun_out
 mkdir -p "$OUT"
 export PYTHONUNBUFFERED=1
 step() { echo "=== $1 ($(date +%T))" | tee -a "$OUT/${TAG}_session.log"; }
-SLICE='tests/test_gpu_parity.py::test_lockstep_velocities_within_tolerance[jam_small] tests/test_gpu_parity.py::test_lockstep_velocities_within_tolerance[yard_small] tests/test_gpu_parity.py::test_ties_and_colocated_agents tests/test_gpu_parity.py::test_arrival_destroy_and_replan_events tests/test_gpu_parity.py::test_update_io_owned_records_match_plain_update tests/test_gpu_parity.py::test_nonfinite_agent_leaves_the_tick tests/test_gpu_strips.py::test_in_process_strips_match_single_gpu_bitwise tests/test_zz2_gpu_compact.py::test_compact_walk_in_the_graph_tick_with_spawns_and_destroys tests/test_zz2_gpu_spawn.py tests/test_zz4_gpu_planner.py::test_device_planner_reproduces_the_reference_polylines[c2_small]'
+SLICE='tests/test_gpu_parity.py::test_lockstep_velocities_within_tolerance[jam_small] tests/test_gpu_parity.py::test_lockstep_velocities_within_tolerance[yard_small] tests/test_gpu_parity.py::test_ties_and_colocated_agents tests/test_gpu_parity.py::test_arrival_destroy_and_replan_events tests/test_gpu_parity.py::test_update_io_owned_records_match_plain_update tests/test_gpu_parity.py::test_update_io_pipeline_matches_plain_update tests/test_gpu_parity.py::test_phase_timings_are_taken_inside_the_graph_tick tests/test_gpu_parity.py::test_lockstep_velocities_within_tolerance[concave_small] tests/test_gpu_parity.py::test_nonfinite_agent_leaves_the_tick tests/test_gpu_strips.py::test_in_process_strips_match_single_gpu_bitwise tests/test_zz2_gpu_compact.py::test_compact_walk_in_the_graph_tick_with_spawns_and_destroys tests/test_zz2_gpu_spawn.py tests/test_zz4_gpu_planner.py::test_device_planner_reproduces_the_reference_polylines[c2_small] tests/test_zz4_gpu_planner.py::test_queries_that_fill_the_first_pass_scratch_are_planned_again'
 step "memcheck"
 timeout 900 compute-sanitizer --tool memcheck --leak-check no --error-exitcode 3 --log-file "$OUT/${TAG}_memcheck.txt" python -m pytest -m gpu -q -x $SLICE >"$OUT/${TAG}_memcheck_pytest.log" 2>&1
 echo "memcheck exit $?" | tee -a "$OUT/${TAG}_session.log"; tail -2 "$OUT/${TAG}_memcheck_pytest.log"; grep -c "Invalid\|error" "$OUT/${TAG}_memcheck.txt"; tail -3 "$OUT/${TAG}_memcheck.txt"
 step "racecheck"
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 3 --log-file "$OUT/${TAG}_racecheck.txt" python -m pytest -m gpu -q -x 'tests/test_gpu_parity.py::test_lockstep_velocities_within_tolerance[jam_small]' tests/test_gpu_strips.py::test_in_process_strips_match_single_gpu_bitwise >"$OUT/${TAG}_racecheck_pytest.log" 2>&1
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 3 --log-file "$OUT/${TAG}_racecheck.txt" python -m pytest -m gpu -q -x 'tests/test_gpu_parity.py::test_lockstep_velocities_within_tolerance[jam_small]' 'tests/test_gpu_parity.py::test_lockstep_velocities_within_tolerance[concave_small]' tests/test_gpu_strips.py::test_in_process_strips_match_single_gpu_bitwise >"$OUT/${TAG}_racecheck_pytest.log" 2>&1
 echo "racecheck exit $?" | tee -a "$OUT/${TAG}_session.log"; tail -2 "$OUT/${TAG}_racecheck_pytest.log"; tail -3 "$OUT/${TAG}_racecheck.txt"
+if [[ " ${*:2} " != *" planner "* ]]; then step "done"; exit 0; fi
 step "ncu: device planner, 200 k queries of the 1 M crowd"
 export ECM_WORKLOAD_CACHE=$PWD/workloads
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_plan_paths -c 1 -o "$OUT/${TAG}_planner" -f python - >"$OUT/${TAG}_planner.log" 2>&1 <<'PY'
