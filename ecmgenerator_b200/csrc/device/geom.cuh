@@ -36,9 +36,12 @@ __device__ __forceinline__ void warp_align() {
 // Block-wide phase barrier (kSync kernels only): keeps all warps of a CTA in the same phase of a
 // long kernel so that the CTA's instruction working set is one phase, not the whole kernel
 // (k_orca was instruction-fetch bound: stall_no_instruction 4.9-14.7 per issue, profiles/).
-template <bool kSync>
+#ifndef ECM_PHASE_BARRIERS
+#define ECM_PHASE_BARRIERS 15  // bit i: barrier i of k_orca is there (0 search | 1 obstacles | 2 obstacle half-planes | 3 agent half-planes | LP)
+#endif
+template <bool kSync, int kId = 0>
 __device__ __forceinline__ void phase_barrier() {
-    if (kSync) __syncthreads();  // without it: +4 % (from rest) .. +8 % (congested) per tick, profiles/r02i_ab_*.jsonl
+    if (kSync && ((ECM_PHASE_BARRIERS >> kId) & 1)) __syncthreads();  // without all four: +4 % (from rest) .. +8 % (congested) per tick, profiles/r02i_ab_*.jsonl
 }
 
 __device__ __forceinline__ v2 V(float x, float y) { return make_float2(x, y); }

@@ -418,7 +418,7 @@ __device__ __forceinline__ OrcaResult orca_velocity(const ObstView& ob, const Bi
     int n_on = find_obstacles<kSync>(ob, bins, position, range * range, on, kMaxObstNeighbors, valid);
     if (n_on > kMaxObstNeighbors) { n_on = kMaxObstNeighbors; res.status |= 16u; }
     int nc = 0;
-    phase_barrier<kSync>();
+    phase_barrier<kSync, 1>();
     {
         const int trips = warp_max_trip<kSync>(n_on);
         for (int i = 0; i < trips; i++) {
@@ -430,7 +430,7 @@ __device__ __forceinline__ OrcaResult orca_velocity(const ObstView& ob, const Bi
         }
     }
     const int nObst = nc;
-    phase_barrier<kSync>();
+    phase_barrier<kSync, 2>();
     {
         const int trips = warp_max_trip<kSync>(n_nb);
         for (int i = 0; i < trips; i++) {
@@ -442,7 +442,7 @@ __device__ __forceinline__ OrcaResult orca_velocity(const ObstView& ob, const Bi
         }
     }
     v2 out = V(0.0f, 0.0f);
-    phase_barrier<kSync>();
+    phase_barrier<kSync, 3>();
     int failed = randomized_lp<kSync>(cs, nc, prefVel, maxSpeed, false, out);
     if (failed < nc) {
         res.status |= 64u;

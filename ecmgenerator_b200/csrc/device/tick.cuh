@@ -421,7 +421,7 @@ __device__ __forceinline__ void orca_agent(const TickView& t, const int p, const
             t.sc.fb_list[e] = p;
         }
     }
-    phase_barrier<true>();  // neighbour search | constraints + LP
+    phase_barrier<true, 0>();  // neighbour search | constraints + LP
     st |= finish_agent<true, true>(t, p, k, mine && found);
     if (st) t.ag.status[t.sc.s_slot[p]] |= st;
     unsigned m_ovf = __ballot_sync(0xffffffffu, (st & 16u) != 0u);

@@ -111,11 +111,12 @@ def test_batched_spawn_checks_keep_the_reference_rand_stream_through_rewinds():
     a validity test at its threshold now and then in a box this crowded, so only the totals are compared."""
     import os
 
-    ticks = 40 if "mock" in os.environ.get("ECMGPU_LIB", "") else 150
+    mock = "mock" in os.environ.get("ECMGPU_LIB", "")
+    ticks = 18 if mock else 150  # (the emulator behind the mock runs every launch as thousands of fibers: seconds per tick)
     ref = _crowded_spawn_run("ref", ticks=ticks)
     bat = _crowded_spawn_run("sim", dropin.Simulator.SPAWN_RAND_BATCHED, ticks=ticks)
     seq = _crowded_spawn_run("sim", dropin.Simulator.SPAWN_RAND_SEQUENTIAL, ticks=ticks)
-    assert bat[0] == seq[0] > 50 and bat[1] == seq[1] and np.array_equal(bat[2], seq[2])
+    assert bat[0] == seq[0] > (20 if mock else 50) and bat[1] == seq[1] and np.array_equal(bat[2], seq[2])
     assert np.array_equal(bat[3].view(np.uint32), seq[3].view(np.uint32))
     assert bat[4] == seq[4], "rand() stream position after the run"
     dev_b, host_b = bat[5]
