@@ -222,9 +222,6 @@ def ncu_traffic(kernel: str):
         d = json.load(open(files[-1]))
         k = d["kernels"][kernel]
         mb = k["dram_read_mbytes"] + k["dram_write_mbytes"]
-        if kernel == "k_orca" and "k_fallback" in d["kernels"]:  # the "orca" phase the roofline times is k_orca + k_fallback
-            f = d["kernels"]["k_fallback"]
-            mb += f["dram_read_mbytes"] + f["dram_write_mbytes"]
         return mb * 1e6, os.path.basename(files[-1])
     except Exception:
         return None, None
@@ -443,10 +440,10 @@ def run_ours(args):
         replay - not of a launch-by-launch tick with its host gaps.  (Strips over NCCL and the KD-tree mode are launch by
         launch either way.)"""
         sim.set_profiling(True)
-        acc_ = {"grid": 0.0, "attract": 0.0, "orca": 0.0, "tick": 0.0}
+        acc_ = {"grid": 0.0, "attract": 0.0, "orca": 0.0, "fallback": 0.0, "tick": 0.0}  # orca = k_orca alone, fallback = k_fallback
         for _ in range(reps):
             sim.update(3)  # back to back like the timed windows; the events of the last tick are read (each tick overwrites them)
-            t_ms = sim.last_tick_ms()
+            t_ms = sim.last_tick_phases()
             for k_ in acc_:
                 acc_[k_] += t_ms[k_] / reps
         sim.set_profiling(False)
@@ -517,7 +514,7 @@ def run_ours(args):
                 "kernel_ms": acc[dom], "phase_ms": acc,
                 "whole_tick": {"achieved": ach_tick, "frac": ach_tick / peak, "algorithmic_bytes_per_agent": alg["tick"]},
                 "state": f"congested crowd (from tick {timed_from}), like the headline",
-                # the four event-record nodes drain the GPU between the phases: the profiled tick runs this much longer than
+                # the five event-record nodes drain the GPU between the phases: the profiled tick runs this much longer than
                 # the timed windows' tick, so kernel_ms errs on the slow side (frac on the low side) by at most this
                 "phase_events_overhead_ms": acc["tick"] - ms / args.steps}
         if from_rest and from_rest.get("phase_ms"):  # the same kernel on the crowd at rest (what round 1's line reported)

@@ -1460,6 +1460,7 @@ int ecmgpu_update_phase(ecmgpu_sim* s, int phase) {
         if (s->profiling) CUDA_TRY(s, record_phase_event(s, 2));
         k_orca<<<div_up(nb * 128, ECM_ORCA_BLOCK), ECM_ORCA_BLOCK, 0, s->stream>>>(t);
     }
+    if (s->profiling) CUDA_TRY(s, record_phase_event(s, 4));  // k_orca | k_fallback (ecmgpu_last_tick_phases)
     k_fallback<<<kSMs * ECM_FALLBACK_CTAS, 128, 0, s->stream>>>(t, 0);
     if (s->profiling) { CUDA_TRY(s, record_phase_event(s, 3)); s->ev_valid = true; }
     s->launches += 3;
@@ -2235,6 +2236,17 @@ int ecmgpu_last_tick_ms(ecmgpu_sim* s, float out_ms[4]) {
     CUDA_TRY(s, cudaEventElapsedTime(&out_ms[1], s->ev[0], s->ev[1]));
     CUDA_TRY(s, cudaEventElapsedTime(&out_ms[2], s->ev[1], s->ev[2]));
     CUDA_TRY(s, cudaEventElapsedTime(&out_ms[3], s->ev[2], s->ev[3]));
+    return ECMGPU_OK;
+}
+
+int ecmgpu_last_tick_phases(ecmgpu_sim* s, float out_ms[5]) {
+    if (!s || !out_ms) return ECMGPU_ERR_INVALID;
+    float four[4];
+    int rc = ecmgpu_last_tick_ms(s, four);
+    if (rc) return rc;
+    float fb = 0.0f;
+    CUDA_TRY(s, cudaEventElapsedTime(&fb, s->ev[4], s->ev[3]));
+    out_ms[0] = four[0]; out_ms[1] = four[1]; out_ms[2] = four[2]; out_ms[3] = four[3] - fb; out_ms[4] = fb;
     return ECMGPU_OK;
 }
 

@@ -37,7 +37,7 @@ EXPORTS = [
     "ecmgpu_bulk_load", "ecmgpu_set_path", "ecmgpu_destroy_agent", "ecmgpu_update", "ecmgpu_sync", "ecmgpu_poll_events",
     "ecmgpu_read", "ecmgpu_write", "ecmgpu_read_async", "ecmgpu_write_async", "ecmgpu_alloc_pinned", "ecmgpu_free_pinned",
     "ecmgpu_locate", "ecmgpu_retract", "ecmgpu_find_neighbors", "ecmgpu_find_obstacles", "ecmgpu_get_stats",
-    "ecmgpu_last_tick_ms", "ecmgpu_set_profiling", "ecmgpu_mark", "ecmgpu_mark_elapsed_ms", "ecmgpu_stream", "ecmgpu_comm_unique_id", "ecmgpu_comm_init",
+    "ecmgpu_last_tick_ms", "ecmgpu_last_tick_phases", "ecmgpu_set_profiling", "ecmgpu_mark", "ecmgpu_mark_elapsed_ms", "ecmgpu_stream", "ecmgpu_comm_unique_id", "ecmgpu_comm_init",
     "ecmgpu_comm_set_strips", "ecmgpu_comm_init_local", "ecmgpu_update_phase", "ecmgpu_update_io", "ecmgpu_update_io_owned", "ecmgpu_io_wait", "ecmgpu_comm_p2p_export", "ecmgpu_comm_p2p_connect",
     "ecmgpu_set_neighbor_mode", "ecmgpu_valid_spawn_locations", "ecmgpu_draw_spawns", "ecmgpu_set_ecm_topology", "ecmgpu_plan_paths", "ecmgpu_plan_info",
     "ecmgpu_abi_sizes",
@@ -96,6 +96,7 @@ def lib() -> C.CDLL:
         L.ecmgpu_find_obstacles.argtypes = [vp, C.c_int, i32p, C.c_int, i32p]
         L.ecmgpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.ecmgpu_last_tick_ms.argtypes = [vp, f32p]
+        L.ecmgpu_last_tick_phases.argtypes = [vp, f32p]
         L.ecmgpu_set_profiling.argtypes = [vp, C.c_int]
         L.ecmgpu_mark.argtypes = [vp, C.c_int]
         L.ecmgpu_mark_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, f32p]
@@ -432,3 +433,9 @@ class GpuSim:
         out = (C.c_float * 4)()
         self._ck(self.L.ecmgpu_last_tick_ms(self.h, out))
         return {"tick": out[0], "grid": out[1], "attract": out[2], "orca": out[3]}
+
+    def last_tick_phases(self):
+        """Like last_tick_ms with k_orca and k_fallback apart (ecmgpu_last_tick_phases)."""
+        out = (C.c_float * 5)()
+        self._ck(self.L.ecmgpu_last_tick_phases(self.h, out))
+        return {"tick": out[0], "grid": out[1], "attract": out[2], "orca": out[3], "fallback": out[4]}

@@ -254,7 +254,12 @@ void ecmgpu_abi_sizes(int32_t out[4]);
 /* CUDA-event time of each phase of the LAST completed tick, milliseconds.
  * phases: 0 whole tick, 1 grid build (count+scan+scatter), 2 attraction (locate+IRM+steer), 3 ORCA (kNN+obstacles+LP+integrate) */
 int ecmgpu_last_tick_ms(ecmgpu_sim* sim, float out_ms[4]);
-/* Enables per-phase event recording (adds 4 event records per tick). */
+/* The same with phase 3 split: 0 whole tick, 1 grid build, 2 attraction, 3 k_orca alone (default neighbour mode; in the
+ * KD-tree mode: tree build + search + ORCA), 4 k_fallback (stragglers of the neighbour search and RandomizedLP3D of the
+ * agents k_orca parked: 13 % of a congested crowd). */
+int ecmgpu_last_tick_phases(ecmgpu_sim* sim, float out_ms[5]);
+/* Enables per-phase event recording: 5 event records per tick, inside the captured graph of the tick (external
+ * event-record nodes), so the phases are those of the tick an unprofiled run replays. */
 int ecmgpu_set_profiling(ecmgpu_sim* sim, int on);
 /* Stream-ordered time marks (CUDA events on the handle's stream): record mark `which` (0..7) now;
  * elapsed waits for mark b and returns the device time between marks a and b in milliseconds. */

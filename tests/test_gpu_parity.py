@@ -345,6 +345,8 @@ def test_phase_timings_are_taken_inside_the_graph_tick():
         assert a.stats()["kernel_launches"] - l0 == per_tick
         assert all(np.isfinite(v) and v >= 0.0 for v in ms.values()) and ms["tick"] > 0.0
         assert abs(ms["grid"] + ms["attract"] + ms["orca"] - ms["tick"]) <= 1e-3 + 0.02 * ms["tick"]
+        ph = a.last_tick_phases()  # the ORCA phase split into k_orca and k_fallback
+        assert ph["orca"] >= 0.0 and ph["fallback"] >= 0.0 and abs(ph["orca"] + ph["fallback"] - ms["orca"]) <= 1e-3
     a.set_profiling(False)
     a.update(2)
     b.update(6)
