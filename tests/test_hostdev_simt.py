@@ -107,3 +107,45 @@ def test_simt_carried_list_kernel(simt):
         nbr, nbr_cnt = np.full((n, 5), -9, np.int32), np.full(n, -9, np.int32)
         simt.emu_kd_resolve(n, _p(active, u8p), _p(raw, i32p), _p(cnt, i32p), _p(cache, i32p), _p(nbr, i32p), _p(nbr_cnt, i32p))
         assert np.array_equal(cache, raw[last]), (n, last)
+
+
+def test_simt_lp3d_of_a_packed_crowd(simt):
+    """A crowd packed into a few metres, everybody heading elsewhere: hundreds of infeasible 2-D programs per tick, with
+    obstacle constraints among them.  k_orca parks those agents, k_fallback runs RandomizedLP3D for a warp's 32 agents in
+    step (randomized_lp3d_warp) - bit for bit the C oracle, which runs the reference's loops in place.  (The golden scenes
+    reach the queue with a few agents per tick; this fills it.)"""
+    from ecmgenerator_b200 import host
+    from oracle.pyoracle import OracleSim
+
+    class _Scene:
+        def __init__(self, world, crowd, off, pxy, step):
+            self.world, self.crowd, self.path_off, self.path_xy, self.step, self.n = world, crowd, off, pxy, step, crowd.n
+
+    g0 = Golden("concave_small")  # recessed, turned blocks: obstacle constraints with concave ends in the programs
+    w = g0.world
+    rng = np.random.default_rng(11)
+    n = 640
+    centre = g0.crowd.pos.mean(axis=0)
+    c = g0.crowd.take(rng.integers(0, g0.n, n))
+    side = int(np.ceil(np.sqrt(n)))
+    lattice = np.stack(np.meshgrid(np.arange(side), np.arange(side)), -1).reshape(-1, 2)[:n].astype(np.float32)
+    c.pos[:] = (centre + (lattice - side / 2) * 0.62 + rng.normal(0, 0.02, (n, 2))).astype(np.float32)
+    off, pxy, _ = host.plan_paths(w, c.pos, c.goal, c.radius, threads=0)
+    c = c.take(np.flatnonzero(np.diff(off) >= 2))
+    off, pxy, _ = host.plan_paths(w, c.pos, c.goal, c.radius, threads=0)
+    assert c.n > 200 and (np.diff(off) >= 2).all()
+    g = _Scene(w, c, off, pxy, g0.step)
+    d = EmuDevice(simt, g, 2.0)
+    ora = OracleSim(w, c.n + 8, g.step, "exact-knn")
+    ora.bulk_load(c.pos, c.radius, c.speed, off, pxy)
+    for t in range(12):
+        simt.emu_tick(d.h)
+        ora.step(1)
+        a, b = d.state(), ora.state(c.n)
+        for k in ("pos", "vel"):
+            assert_bits_equal(a[k], b[k], f"{k} after tick {t}")
+    runs = int(d.counters()[C_TOTAL_LP3D])
+    print(f"{c.n} agents, {runs} LP3D runs in 12 ticks; oracle counters {ora.counters()}")
+    assert runs > 400
+    d.close()
+    ora.close()
