@@ -458,10 +458,18 @@ __global__ void __launch_bounds__(ECM_ORCA_BLOCK, ECM_ORCA_MINBLOCKS) k_orca_til
 // The stragglers of a tick, one kernel: (a) warp-per-agent exhaustive neighbour search + ORCA for agents
 // whose ring budget ran out, (b) LP3D + integration for the agents k_orca parked.
 // mode 0: full tick; mode 1: neighbour query only (ecmgpu_find_neighbors)
+// 8 CTAs of 128 threads per SM at 64 registers (72 unconstrained: 7 CTAs).  With a short LP3D queue the kernel is as long
+// as its slowest warp and the geometry hardly matters (1 M agents from rest: +1 %, congested: -1.5 %); with a long one -
+// the 4 M map, where 46 % of the congested crowd needs RandomizedLP3D: 58 k batches for 2 400 warp slots - resident warps
+// are throughput: tick 3.09-3.20 -> 2.85 ms (profiles/r04b_ab_c4_fallback_occupancy.jsonl, r04c_ab_*).  12 CTAs at 40
+// registers: the same within noise.
 #ifndef ECM_FALLBACK_CTAS
-#define ECM_FALLBACK_CTAS 4  // CTAs per SM in the tick's launch (8 or 16: within 0.3 %, profiles/r03i_ab_congested_lp3d.jsonl)
+#define ECM_FALLBACK_CTAS 8  // CTAs per SM in the tick's launch
 #endif
-__global__ void __launch_bounds__(128) k_fallback(TickView t, int mode) {
+#ifndef ECM_FALLBACK_MINBLOCKS
+#define ECM_FALLBACK_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, ECM_FALLBACK_MINBLOCKS) k_fallback(TickView t, int mode) {
     const int warps_total = (gridDim.x * blockDim.x) >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
