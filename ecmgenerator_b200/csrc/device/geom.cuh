@@ -65,7 +65,7 @@ __device__ __noinline__ v2 vnormalized(v2 a) {
 }
 // Arithmetic of the ORCA half-planes and linear programs only (orca.cuh).  Their contract is "new velocities within
 // 1e-4 m/s per step" (BASELINE.json north_star), not bit-exactness, so they use the SFU approximations (division 2 ulp,
-// square root 1 ulp, sine / cosine 2^-21 absolute) instead of the ~10-instruction IEEE sequences, which were a quarter
+// square root and reciprocal square root 1-2 ulp) instead of the ~10-instruction IEEE sequences, which were a quarter
 // of k_orca's warp instructions (profiles/r01_v8_k_orca_by_function.txt).  Measured on one B200, 1 M agents
 // (profiles/r02a_ab_rest.jsonl, r02a_ab_congested.jsonl, r02a_orca_fast_parity.log): tick 0.561 -> 0.497 ms from rest,
 // 0.644 -> 0.577 ms congested; worst |dv| per step against the reference 1.2e-7 .. 4.8e-7 m/s (tolerance 1e-4),
@@ -80,7 +80,6 @@ __device__ __forceinline__ float osqrt(float x) {
     asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ void osincos(float a, float* sn, float* cs) { __sincosf(a, sn, cs); }
 __device__ __forceinline__ v2 ovdiv(v2 a, float s) { return V(odiv(a.x, s), odiv(a.y, s)); }
 __device__ __forceinline__ float ovlen(v2 a) { return osqrt(__fmaf_rn(a.x, a.x, a.y * a.y)); }
 __device__ __forceinline__ v2 ovnormalized(v2 a) {
@@ -105,7 +104,6 @@ __device__ __forceinline__ void osincos_atan(float r, float l, float* sn, float*
 #else
 __device__ __forceinline__ float odiv(float a, float b) { return a / b; }
 __device__ __forceinline__ float osqrt(float x) { return sqrtf(x); }
-__device__ __forceinline__ void osincos(float a, float* sn, float* cs) { sincosf(a, sn, cs); }
 __device__ __forceinline__ v2 ovdiv(v2 a, float s) { return vdiv(a, s); }
 __device__ __forceinline__ float ovlen(v2 a) { return vlen(a); }
 __device__ __forceinline__ v2 ovnormalized(v2 a) { return vnormalized(a); }
